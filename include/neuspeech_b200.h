@@ -1,0 +1,165 @@
+/*
+ * neuspeech_b200.h -- C-ABI of the B200-native NeuSpeech hot path (libneuspeech_b200.so).
+ *
+ * The reference (NeuSpeech/NeuSpeech1) has no FFI of its own: its hot path is PyTorch library calls made from
+ * utils/load_model.py / utils/model_utils.py / utils/augment_eeg.py.  Each entry point below
+ * therefore cites the reference call site whose arithmetic it replaces.  The Python host (neuspeech1_b200/) binds these
+ * with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative ns_status otherwise; ns_last_error_string() explains (thread-local)
+ *   - all data pointers are DEVICE pointers (HBM), row-major; `stream` is a cudaStream_t passed as void*
+ *   - functions never allocate device memory, never synchronise, never touch the host copy of the data
+ *   - ns_dtype says how activations are stored (NS_F32 / NS_BF16); arithmetic accumulates in fp32 in both cases
+ *   - "fast" variants (tcgen05/TMEM/TMA, sm_100a) are selected automatically when dtype == NS_BF16 and the shape
+ *     qualifies; ns_set_path() can force the plain SIMT kernels (parity debugging), ns_get_counters() reports which ran
+ */
+#ifndef NEUSPEECH_B200_H
+#define NEUSPEECH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { NS_OK = 0, NS_ERR_ARG = -1, NS_ERR_CUDA = -2, NS_ERR_UNSUPPORTED = -3, NS_ERR_WORKSPACE = -4 } ns_status;
+typedef enum { NS_F32 = 0, NS_BF16 = 1 } ns_dtype;
+typedef enum { NS_ACT_NONE = 0, NS_ACT_GELU = 1, NS_ACT_DGELU = 2 } ns_act;
+typedef enum { NS_PATH_AUTO = 0, NS_PATH_SIMT = 1, NS_PATH_FAST = 2 } ns_path;
+
+/* ---- library ---- */
+int         ns_version(void);
+const char* ns_last_error_string(void);
+int         ns_set_path(int path);                 /* ns_path; returns previous */
+int         ns_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* counters[0]=tcgen05 GEMM launches, [1]=SIMT GEMM launches, [2]=tensor-core attention launches, [3]=SIMT attention
+ * launches, [4]=other kernel launches, [5]=tcgen05 wgrad launches.  Reset with ns_reset_counters(). */
+int         ns_get_counters(long long* counters, int n);
+int         ns_reset_counters(void);
+
+/* ---- fused GEMM:  D = epilogue( A[M,K] * W[N,K]^T  (+ A2[M,K2] * W2[N,K2]^T) )
+ * Replaces nn.Linear (+ PEFT lora.Linear, finetune.py:194-212) at HF modeling_whisper.py:310,331-332,355,404,406 and
+ * the tied proj_out (utils/load_model.py:1047).  The second product is the LoRA branch: A2 = t = x*A^T (M,K2), W2 = s*B.
+ * Epilogue order: +bias[n]; *alpha for columns < alpha_cols (q pre-scale, HF:310); act; +residual.
+ *   act NS_ACT_GELU : y = gelu_erf(z); if aux_out != NULL the pre-activation z is stored there (ld = ldaux)
+ *   act NS_ACT_DGELU: y = z * gelu'(aux_in[m,n])                (backward through GELU; aux_in = saved pre-activation)
+ *   residual: D += R[row % res_mod, n] when res_mod > 0 (position table, utils/load_model.py:413-416) else R[row, n] */
+typedef struct {
+  const float* bias;
+  float        alpha;
+  int          alpha_cols;
+  int          act;
+  const void*  aux_in;
+  void*        aux_out;
+  long long    ldaux;
+  const void*  residual;
+  long long    ldr;
+  int          res_mod;
+  int          out_dtype;     /* ns_dtype of D (NS_F32 allowed with NS_BF16 inputs) */
+  int          a2_group_cols; /* > 0: stacked adapters -- output columns [g*a2_group_cols, (g+1)*a2_group_cols) use
+                                 A2[:, g*K2 : (g+1)*K2] (q/k/v share one t = x*[Aq;Ak;Av]^T buffer, lda2 >= G*K2) */
+} ns_epilogue;
+
+int ns_gemm_nt(int dtype, long long M, int N, int K, const void* A, long long lda, const void* W, long long ldw,
+               void* D, long long ldd, const ns_epilogue* ep,
+               const void* A2, long long lda2, const void* W2, long long ldw2, int K2, void* stream);
+
+/* ---- weight-gradient GEMM:  G[i*si + j*sj] += alpha * sum_m X[m,i] * Y[m,j]   (G fp32, caller zeroes it)
+ * Replaces autograd's wgrad of the LoRA A/B linears (PEFT) : dB = s*dy^T t, dA = dt^T x. */
+int ns_gemm_tn(int dtype, long long M, int I, int J, const void* X, long long ldx, const void* Y, long long ldy,
+               float* G, long long si, long long sj, float alpha, void* stream);
+
+/* ---- stem convolution (kernel 3, pad 1, stride 1|2) on channels-last activations, as an implicit GEMM.
+ * Replaces nn.Conv1d + GELU at utils/model_utils.py:12-16 and utils/load_model.py:410-411 (+ the permute and
+ * embed_positions add of :413-416 through ep->residual/res_mod).
+ *   x  (B, Tin, Cp)  channels-last, Cp = padded channel count (multiple of 16; pad channels are zero)
+ *   w  (3, N, Cp)    tap-major re-layout of Conv1d.weight (N, C, 3)
+ *   y  (B, Tout, N)  Tout = Tin/stride.   Epilogue as ns_gemm_nt (row index for res_mod is the output time t). */
+int ns_conv3_fwd(int dtype, int B, int Tin, int Cp, int N, int stride, const void* x, const void* w, void* y,
+                 const ns_epilogue* ep, void* stream);
+/* input gradient: dx (B,Tin,Cp) = conv_transpose(dz (B,Tout,N), w);  wt = (3, Cp, N) tap-major transposed weight.
+ * ep may carry NS_ACT_DGELU (dx *= gelu'(aux_in)) so the previous conv's GELU backward is fused. */
+int ns_conv3_dgrad(int dtype, int B, int Tin, int Cp, int N, int stride, const void* dz, const void* wt, void* dx,
+                   const ns_epilogue* ep, void* stream);
+/* weight gradient: dw (3, N, Cp) fp32 += sum_{b,t} dz[b,t,n] * x[b, stride*t + k - 1, c];  db (N) fp32 += sum dz */
+int ns_conv3_wgrad(int dtype, int B, int Tin, int Cp, int N, int stride, const void* dz, const void* x, float* dw,
+                   float* db, void* stream);
+
+/* ---- LayerNorm over the last dim (eps 1e-5, affine).  HF modeling_whisper.py:393,403; utils/load_model.py:468.
+ * mean/rstd (fp32, per row) are saved for the backward when non-NULL. */
+int ns_layernorm_fwd(int dtype, long long rows, int d, const void* x, const float* gamma, const float* beta, void* y,
+                     float* mean, float* rstd, float eps, void* stream);
+/* dx = LN'(dy) (gamma/beta are frozen in the reference: no parameter grads).  If dres != NULL: dx += dres (residual). */
+int ns_layernorm_bwd(int dtype, long long rows, int d, const void* dy, const void* x, const float* gamma,
+                     const float* mean, const float* rstd, const void* dres, void* dx, void* stream);
+
+/* ---- multi-head attention, head_dim 64|32, q pre-scaled (HF:215-238, :310).  Tensors are addressed with element strides
+ *   q[b, i, h, :] = q + b*q_bs + i*q_rs + h*Dh   (same for k, v, o) so packed qkv / cross-KV buffers are read in place.
+ *   causal != 0: key j visible to query i iff j <= i + (Lk - Lq).   lse (B,H,Lq) fp32 saved for the backward. */
+typedef struct {
+  int B, H, Lq, Lk, Dh, causal;
+  long long q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs;
+} ns_attn_shape;
+int ns_attention_fwd(int dtype, const ns_attn_shape* s, const void* q, const void* k, const void* v, void* o, float* lse,
+                     void* stream);
+/* do has o's strides; dq/dk/dv have q/k/v's strides.  delta (B,H,Lq) fp32 is scratch. */
+int ns_attention_bwd(int dtype, const ns_attn_shape* s, const void* q, const void* k, const void* v, const void* o,
+                     const void* d_o, const float* lse, float* delta, void* dq, void* dk, void* dv, void* stream);
+
+/* ---- decoder embedding: h[b,l,:] = E[ids[b,l]] + P[pos0 + l]   (utils/load_model.py:646-660) */
+int ns_embed(int dtype, int B, int L, int d, const long long* ids, const void* E, const void* P, int pos0, void* h,
+             void* stream);
+/* ---- cross-entropy over logits (rows, ld>=V): per-row loss (0 where label==-100), optional in-place dlogits
+ *  (softmax - onehot) * (grad_scale / n_valid); pad columns [V, ld) are zeroed.  utils/load_model.py:1051-1054.
+ *  n_valid is counted on device into *n_valid_out (int); loss_sum_out = sum of row losses (fp32). */
+int ns_cross_entropy(int dtype, long long rows, int V, long long ld, void* logits, const long long* labels,
+                     float* row_loss, float* loss_sum_out, int* n_valid_out, int write_grad, float grad_scale,
+                     void* stream);
+/* ---- greedy next token: argmax over logits[b, :V] with `suppress` ids at -inf, finished rows emit pad
+ *  (GenerationMixin greedy + SuppressTokensAtBegin, HF generation_whisper.py:1774-1813). */
+int ns_greedy_pick(int dtype, int B, int V, long long ld, const void* logits, const int* suppress, int n_suppress,
+                   int eos, int pad, unsigned char* finished, long long* next_ids, void* stream);
+
+/* ---- EEG augmentation + pad + cast + layout pass (utils/reader.py:552-594, :496-506; utils/augment_eeg.py:15-26,54-56;
+ *  utils/utils.py:33-60).  One read of x (B,C,Tin) f32, one write of y.
+ *   per sample b: n[b] valid samples, shift[b], taylor edges e0[b], e1[b]; keep-grid bits grid + b*grid_stride (row-major
+ *   gc x gl bytes, NULL pointer or flags bit0 clear = no mask) expanded with rep_c[b], rep_t[b];
+ *   noise (flags bit1): y = 2x + sigma[b,c]*N(0,1) (Philox, seed) -- the reference's 2x quirk kept.
+ *   layout 0: y (B,C,T) like the reference collator;  layout 1: y (B,T,Cp) channels-last, pad channels zero. */
+typedef struct {
+  int B, C, Tin, T, Cp, layout, out_dtype;
+  const int* n; const int* shift; const int* e0; const int* e1; const int* flags;
+  const unsigned char* grid; long long grid_stride; const int* gl; const int* rep_c; const int* rep_t;
+  const float* sigma; unsigned long long seed;
+} ns_aug_args;
+int ns_aug_pass(const ns_aug_args* a, const float* x, void* y, void* stream);
+/* per-(b,c) mean square over the first n[b] samples (for the noise sigma): ms (B,C) fp32 */
+int ns_channel_meansq(int B, int C, int Tin, const int* n, const float* x, float* ms, void* stream);
+
+/* ---- small utilities */
+int ns_cast(int src_dtype, int dst_dtype, long long n, const void* src, void* dst, void* stream);
+/* dst (cols, rows_pad>=rows) = scale * src (rows, cols)^T, dst leading dim ldd; pad rows zero-filled up to ldd */
+int ns_transpose(int src_dtype, int dst_dtype, int rows, int cols, const void* src, long long lds, void* dst,
+                 long long ldd, float scale, void* stream);
+/* conv weight re-layouts: w (N,C,3) fp32 -> (3,N,Cp) and (3,Cp,N) in dtype; and the fp32 gradient back (3,N,Cp)->(N,C,3) */
+int ns_conv_weight_pack(int dtype, int N, int C, int Cp, const float* w, void* w_tap, void* w_tap_t, void* stream);
+int ns_conv_weight_unpack_grad(int N, int C, int Cp, const float* dw_tap, float* dw, void* stream);
+/* y = a + b elementwise (dtype) */
+int ns_add(int dtype, long long n, const void* a, const void* b, void* y, void* stream);
+/* dz = dy * gelu_erf'(z) elementwise: backward through F.gelu(conv2(.)) at utils/load_model.py:411 (the only GELU on the
+ * path whose backward cannot ride in a GEMM epilogue) */
+int ns_dgelu_mul(int dtype, long long n, const void* dy, const void* z, void* dz, void* stream);
+
+/* ---- fused clip + AdamW over one flat fp32 parameter/gradient buffer (HF trainer.py:2493,1760; finetune.py:236-247).
+ *  Step 1: ns_sumsq accumulates sum(g^2) into *out (caller zeroes).  Step 2: ns_adamw_clip reads *sumsq on device,
+ *  scales g by min(1, max_norm/(sqrt(sumsq*gscale^2)+1e-6))*gscale and applies torch.optim.AdamW semantics. */
+int ns_sumsq(long long n, const float* g, float* out, void* stream);
+int ns_adamw_clip(long long n, float* p, const float* g, float* m, float* v, const float* sumsq, float gscale,
+                  float max_norm, float lr, float beta1, float beta2, float eps, float wd, int step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEUSPEECH_B200_H */

@@ -1,0 +1,333 @@
+// SIMT (CUDA-core, fp32) multi-head attention forward / backward with online softmax; any Lq/Lk, head_dim 32 or 64,
+// optional causal mask.  Used for NS_F32 storage (fp32 parity mode), for the small decoder attentions and as the checker of
+// the tensor-core attention.  q is pre-scaled by the caller (HF modeling_whisper.py:310), so scores are plain q.k.
+//
+// forward : grid (ceil(Lq/16), H, B), 8 warps, each warp owns 2 queries; K/V tiles of 64 keys staged in shared memory.
+// backward: delta = rowsum(dO*O); dq kernel (same structure as forward); dk/dv kernel (one warp per 2 keys, loops queries).
+#include "ns_common.cuh"
+
+namespace ns {
+
+constexpr int kQPB = 16;    // queries per block
+constexpr int kKT = 64;     // keys per shared tile
+
+template <typename T, int DH>
+__global__ void __launch_bounds__(256) attn_fwd_simt_kernel(const ns_attn_shape s, const T* __restrict__ q, const T* __restrict__ k,
+                                                            const T* __restrict__ v, T* __restrict__ o, float* __restrict__ lse) {
+  constexpr int DPL = DH / 32;
+  __shared__ float Ks[kKT][DH + 1];
+  __shared__ float Vs[kKT][DH + 1];
+  __shared__ float Qs[kQPB][DH];
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kQPB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int off = s.Lk - s.Lq;
+  for (int e = threadIdx.x; e < kQPB * DH; e += 256) {
+    const int r = e / DH, d = e % DH;
+    const int qi = q0 + r;
+    Qs[r][d] = qi < s.Lq ? to_f<T>(q[b * s.q_bs + static_cast<long long>(qi) * s.q_rs + h * DH + d]) : 0.f;
+  }
+  float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+  float acc[2][DPL];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int d = 0; d < DPL; ++d) acc[i][d] = 0.f;
+  // keys needed by this block (causal): up to q0 + kQPB - 1 + off
+  const int k_end = s.causal ? min(s.Lk, q0 + kQPB + off) : s.Lk;
+  for (int k0 = 0; k0 < k_end; k0 += kKT) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < kKT * DH; e += 256) {
+      const int r = e / DH, d = e % DH;
+      const int kj = k0 + r;
+      float kv = 0.f, vv = 0.f;
+      if (kj < s.Lk) {
+        kv = to_f<T>(k[b * s.k_bs + static_cast<long long>(kj) * s.k_rs + h * DH + d]);
+        vv = to_f<T>(v[b * s.v_bs + static_cast<long long>(kj) * s.v_rs + h * DH + d]);
+      }
+      Ks[r][d] = kv; Vs[r][d] = vv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = warp * 2 + i;
+      const int qi = q0 + r;
+      if (qi >= s.Lq) continue;   // warp-uniform
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+      for (int d = 0; d < DH; ++d) {
+        const float qd = Qs[r][d];
+        s0 = fmaf(qd, Ks[lane][d], s0);
+        s1 = fmaf(qd, Ks[lane + 32][d], s1);
+      }
+      const int j0 = k0 + lane, j1 = k0 + lane + 32;
+      const int lim = s.causal ? qi + off : s.Lk - 1;
+      if (j0 >= s.Lk || j0 > lim) s0 = -INFINITY;
+      if (j1 >= s.Lk || j1 > lim) s1 = -INFINITY;
+      const float mn = fmaxf(m[i], warp_max(fmaxf(s0, s1)));
+      if (mn == -INFINITY) continue;
+      const float corr = __expf(m[i] - mn);
+      const float p0 = __expf(s0 - mn), p1 = __expf(s1 - mn);
+      l[i] = l[i] * corr + warp_sum(p0 + p1);
+      m[i] = mn;
+#pragma unroll
+      for (int d = 0; d < DPL; ++d) acc[i][d] *= corr;
+      for (int j = 0; j < 32; ++j) {
+        const float pa = __shfl_sync(0xffffffffu, p0, j);
+        const float pb = __shfl_sync(0xffffffffu, p1, j);
+#pragma unroll
+        for (int d = 0; d < DPL; ++d) {
+          acc[i][d] = fmaf(pa, Vs[j][lane + 32 * d], acc[i][d]);
+          acc[i][d] = fmaf(pb, Vs[j + 32][lane + 32 * d], acc[i][d]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int qi = q0 + warp * 2 + i;
+    if (qi >= s.Lq) continue;
+    const float inv = l[i] > 0.f ? 1.0f / l[i] : 0.f;
+#pragma unroll
+    for (int d = 0; d < DPL; ++d)
+      o[b * s.o_bs + static_cast<long long>(qi) * s.o_rs + h * DH + lane + 32 * d] = from_f<T>(acc[i][d] * inv);
+    if (lse && lane == 0) lse[(static_cast<long long>(b) * s.H + h) * s.Lq + qi] = m[i] + logf(l[i]);
+  }
+}
+
+// delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]
+template <typename T, int DH>
+__global__ void attn_delta_kernel(const ns_attn_shape s, const T* __restrict__ o, const T* __restrict__ d_o, float* __restrict__ delta) {
+  const long long idx = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const long long total = static_cast<long long>(s.B) * s.H * s.Lq;
+  if (idx >= total) return;
+  const int qi = static_cast<int>(idx % s.Lq);
+  const int h = static_cast<int>((idx / s.Lq) % s.H);
+  const int b = static_cast<int>(idx / (static_cast<long long>(s.Lq) * s.H));
+  float a = 0.f;
+  for (int d = lane; d < DH; d += 32) {
+    const long long off = b * s.o_bs + static_cast<long long>(qi) * s.o_rs + h * DH + d;
+    a = fmaf(to_f<T>(o[off]), to_f<T>(d_o[off]), a);
+  }
+  a = warp_sum(a);
+  if (lane == 0) delta[idx] = a;
+}
+
+// dq_i = sum_j p_ij (dp_ij - delta_i) k_j,   p_ij = exp(s_ij - lse_i),  dp_ij = dO_i . v_j
+template <typename T, int DH>
+__global__ void __launch_bounds__(256) attn_bwd_dq_simt_kernel(const ns_attn_shape s, const T* __restrict__ q, const T* __restrict__ k,
+                                                               const T* __restrict__ v, const T* __restrict__ d_o,
+                                                               const float* __restrict__ lse, const float* __restrict__ delta,
+                                                               T* __restrict__ dq) {
+  constexpr int DPL = DH / 32;
+  __shared__ float Ks[kKT][DH + 1];
+  __shared__ float Vs[kKT][DH + 1];
+  __shared__ float Qs[kQPB][DH];
+  __shared__ float Os[kQPB][DH];
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kQPB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int off = s.Lk - s.Lq;
+  for (int e = threadIdx.x; e < kQPB * DH; e += 256) {
+    const int r = e / DH, d = e % DH;
+    const int qi = q0 + r;
+    Qs[r][d] = qi < s.Lq ? to_f<T>(q[b * s.q_bs + static_cast<long long>(qi) * s.q_rs + h * DH + d]) : 0.f;
+    Os[r][d] = qi < s.Lq ? to_f<T>(d_o[b * s.o_bs + static_cast<long long>(qi) * s.o_rs + h * DH + d]) : 0.f;
+  }
+  float acc[2][DPL];
+  float ls[2], dl[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int qi = q0 + warp * 2 + i;
+    const long long idx = (static_cast<long long>(b) * s.H + h) * s.Lq + qi;
+    ls[i] = qi < s.Lq ? lse[idx] : 0.f;
+    dl[i] = qi < s.Lq ? delta[idx] : 0.f;
+#pragma unroll
+    for (int d = 0; d < DPL; ++d) acc[i][d] = 0.f;
+  }
+  const int k_end = s.causal ? min(s.Lk, q0 + kQPB + off) : s.Lk;
+  for (int k0 = 0; k0 < k_end; k0 += kKT) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < kKT * DH; e += 256) {
+      const int r = e / DH, d = e % DH;
+      const int kj = k0 + r;
+      float kv = 0.f, vv = 0.f;
+      if (kj < s.Lk) {
+        kv = to_f<T>(k[b * s.k_bs + static_cast<long long>(kj) * s.k_rs + h * DH + d]);
+        vv = to_f<T>(v[b * s.v_bs + static_cast<long long>(kj) * s.v_rs + h * DH + d]);
+      }
+      Ks[r][d] = kv; Vs[r][d] = vv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = warp * 2 + i;
+      const int qi = q0 + r;
+      if (qi >= s.Lq) continue;
+      float s0 = 0.f, s1 = 0.f, p0 = 0.f, p1 = 0.f;
+#pragma unroll 8
+      for (int d = 0; d < DH; ++d) {
+        const float qd = Qs[r][d], od = Os[r][d];
+        s0 = fmaf(qd, Ks[lane][d], s0); s1 = fmaf(qd, Ks[lane + 32][d], s1);
+        p0 = fmaf(od, Vs[lane][d], p0); p1 = fmaf(od, Vs[lane + 32][d], p1);
+      }
+      const int j0 = k0 + lane, j1 = k0 + lane + 32;
+      const int lim = s.causal ? qi + off : s.Lk - 1;
+      const float ds0 = (j0 >= s.Lk || j0 > lim) ? 0.f : __expf(s0 - ls[i]) * (p0 - dl[i]);
+      const float ds1 = (j1 >= s.Lk || j1 > lim) ? 0.f : __expf(s1 - ls[i]) * (p1 - dl[i]);
+      for (int j = 0; j < 32; ++j) {
+        const float a0 = __shfl_sync(0xffffffffu, ds0, j);
+        const float a1 = __shfl_sync(0xffffffffu, ds1, j);
+#pragma unroll
+        for (int d = 0; d < DPL; ++d) {
+          acc[i][d] = fmaf(a0, Ks[j][lane + 32 * d], acc[i][d]);
+          acc[i][d] = fmaf(a1, Ks[j + 32][lane + 32 * d], acc[i][d]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int qi = q0 + warp * 2 + i;
+    if (qi >= s.Lq) continue;
+#pragma unroll
+    for (int d = 0; d < DPL; ++d)
+      dq[b * s.q_bs + static_cast<long long>(qi) * s.q_rs + h * DH + lane + 32 * d] = from_f<T>(acc[i][d]);
+  }
+}
+
+// dv_j = sum_i p_ij dO_i ;  dk_j = sum_i p_ij (dp_ij - delta_i) q_i      (block = 16 keys, loops over query tiles of 64)
+template <typename T, int DH>
+__global__ void __launch_bounds__(256) attn_bwd_dkv_simt_kernel(const ns_attn_shape s, const T* __restrict__ q, const T* __restrict__ k,
+                                                                const T* __restrict__ v, const T* __restrict__ d_o,
+                                                                const float* __restrict__ lse, const float* __restrict__ delta,
+                                                                T* __restrict__ dk, T* __restrict__ dv) {
+  constexpr int DPL = DH / 32;
+  __shared__ float Qs[kKT][DH + 1];
+  __shared__ float Os[kKT][DH + 1];
+  __shared__ float Ls[kKT], Ds[kKT];
+  __shared__ float Kb[kQPB][DH];
+  __shared__ float Vb[kQPB][DH];
+  const int b = blockIdx.z, h = blockIdx.y, kb0 = blockIdx.x * kQPB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int off = s.Lk - s.Lq;
+  for (int e = threadIdx.x; e < kQPB * DH; e += 256) {
+    const int r = e / DH, d = e % DH;
+    const int kj = kb0 + r;
+    Kb[r][d] = kj < s.Lk ? to_f<T>(k[b * s.k_bs + static_cast<long long>(kj) * s.k_rs + h * DH + d]) : 0.f;
+    Vb[r][d] = kj < s.Lk ? to_f<T>(v[b * s.v_bs + static_cast<long long>(kj) * s.v_rs + h * DH + d]) : 0.f;
+  }
+  float acck[2][DPL], accv[2][DPL];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int d = 0; d < DPL; ++d) { acck[i][d] = 0.f; accv[i][d] = 0.f; }
+  // causal: key j is seen by queries i >= j - off
+  const int q_begin = s.causal ? max(0, kb0 - off) : 0;
+  for (int qt = (q_begin / kKT) * kKT; qt < s.Lq; qt += kKT) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < kKT * DH; e += 256) {
+      const int r = e / DH, d = e % DH;
+      const int qi = qt + r;
+      float qv = 0.f, ov = 0.f;
+      if (qi < s.Lq) {
+        qv = to_f<T>(q[b * s.q_bs + static_cast<long long>(qi) * s.q_rs + h * DH + d]);
+        ov = to_f<T>(d_o[b * s.o_bs + static_cast<long long>(qi) * s.o_rs + h * DH + d]);
+      }
+      Qs[r][d] = qv; Os[r][d] = ov;
+    }
+    if (threadIdx.x < kKT) {
+      const int qi = qt + threadIdx.x;
+      const long long idx = (static_cast<long long>(b) * s.H + h) * s.Lq + qi;
+      Ls[threadIdx.x] = qi < s.Lq ? lse[idx] : 0.f;
+      Ds[threadIdx.x] = qi < s.Lq ? delta[idx] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = warp * 2 + i;
+      const int kj = kb0 + r;
+      if (kj >= s.Lk) continue;
+      float s0 = 0.f, s1 = 0.f, p0 = 0.f, p1 = 0.f;   // lane handles queries qt+lane and qt+lane+32
+#pragma unroll 8
+      for (int d = 0; d < DH; ++d) {
+        const float kd = Kb[r][d], vd = Vb[r][d];
+        s0 = fmaf(kd, Qs[lane][d], s0); s1 = fmaf(kd, Qs[lane + 32][d], s1);
+        p0 = fmaf(vd, Os[lane][d], p0); p1 = fmaf(vd, Os[lane + 32][d], p1);
+      }
+      const int i0 = qt + lane, i1 = qt + lane + 32;
+      const bool ok0 = i0 < s.Lq && (!s.causal || kj <= i0 + off);
+      const bool ok1 = i1 < s.Lq && (!s.causal || kj <= i1 + off);
+      const float pr0 = ok0 ? __expf(s0 - Ls[lane]) : 0.f;
+      const float pr1 = ok1 ? __expf(s1 - Ls[lane + 32]) : 0.f;
+      const float ds0 = pr0 * (p0 - Ds[lane]);
+      const float ds1 = pr1 * (p1 - Ds[lane + 32]);
+      for (int j = 0; j < 32; ++j) {
+        const float a0 = __shfl_sync(0xffffffffu, pr0, j), a1 = __shfl_sync(0xffffffffu, pr1, j);
+        const float c0 = __shfl_sync(0xffffffffu, ds0, j), c1 = __shfl_sync(0xffffffffu, ds1, j);
+#pragma unroll
+        for (int d = 0; d < DPL; ++d) {
+          accv[i][d] = fmaf(a0, Os[j][lane + 32 * d], accv[i][d]);
+          accv[i][d] = fmaf(a1, Os[j + 32][lane + 32 * d], accv[i][d]);
+          acck[i][d] = fmaf(c0, Qs[j][lane + 32 * d], acck[i][d]);
+          acck[i][d] = fmaf(c1, Qs[j + 32][lane + 32 * d], acck[i][d]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int kj = kb0 + warp * 2 + i;
+    if (kj >= s.Lk) continue;
+#pragma unroll
+    for (int d = 0; d < DPL; ++d) {
+      dk[b * s.k_bs + static_cast<long long>(kj) * s.k_rs + h * DH + lane + 32 * d] = from_f<T>(acck[i][d]);
+      dv[b * s.v_bs + static_cast<long long>(kj) * s.v_rs + h * DH + lane + 32 * d] = from_f<T>(accv[i][d]);
+    }
+  }
+}
+
+template <typename T, int DH>
+static int attn_fwd_simt_t(const ns_attn_shape& s, const void* q, const void* k, const void* v, void* o, float* lse, cudaStream_t st) {
+  dim3 grid((s.Lq + kQPB - 1) / kQPB, s.H, s.B);
+  attn_fwd_simt_kernel<T, DH><<<grid, 256, 0, st>>>(s, reinterpret_cast<const T*>(q), reinterpret_cast<const T*>(k),
+                                                    reinterpret_cast<const T*>(v), reinterpret_cast<T*>(o), lse);
+  NS_LAUNCH_CHECK();
+  count(C_ATTN_SIMT);
+  return NS_OK;
+}
+
+template <typename T, int DH>
+static int attn_bwd_simt_t(const ns_attn_shape& s, const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                           const float* lse, float* delta, void* dq, void* dk, void* dv, cudaStream_t st) {
+  const long long total = static_cast<long long>(s.B) * s.H * s.Lq;
+  attn_delta_kernel<T, DH><<<static_cast<unsigned>((total + 7) / 8), 256, 0, st>>>(s, reinterpret_cast<const T*>(o),
+                                                                                    reinterpret_cast<const T*>(d_o), delta);
+  NS_LAUNCH_CHECK();
+  dim3 gq((s.Lq + kQPB - 1) / kQPB, s.H, s.B);
+  attn_bwd_dq_simt_kernel<T, DH><<<gq, 256, 0, st>>>(s, reinterpret_cast<const T*>(q), reinterpret_cast<const T*>(k),
+                                                     reinterpret_cast<const T*>(v), reinterpret_cast<const T*>(d_o), lse, delta,
+                                                     reinterpret_cast<T*>(dq));
+  NS_LAUNCH_CHECK();
+  dim3 gk((s.Lk + kQPB - 1) / kQPB, s.H, s.B);
+  attn_bwd_dkv_simt_kernel<T, DH><<<gk, 256, 0, st>>>(s, reinterpret_cast<const T*>(q), reinterpret_cast<const T*>(k),
+                                                      reinterpret_cast<const T*>(v), reinterpret_cast<const T*>(d_o), lse, delta,
+                                                      reinterpret_cast<T*>(dk), reinterpret_cast<T*>(dv));
+  NS_LAUNCH_CHECK();
+  count(C_ATTN_SIMT, 3);
+  return NS_OK;
+}
+
+int attention_fwd_simt(int dtype, const ns_attn_shape& s, const void* q, const void* k, const void* v, void* o, float* lse, cudaStream_t st) {
+  if (dtype == NS_F32) return s.Dh == 64 ? attn_fwd_simt_t<float, 64>(s, q, k, v, o, lse, st) : attn_fwd_simt_t<float, 32>(s, q, k, v, o, lse, st);
+  return s.Dh == 64 ? attn_fwd_simt_t<__nv_bfloat16, 64>(s, q, k, v, o, lse, st) : attn_fwd_simt_t<__nv_bfloat16, 32>(s, q, k, v, o, lse, st);
+}
+int attention_bwd_simt(int dtype, const ns_attn_shape& s, const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                       const float* lse, float* delta, void* dq, void* dk, void* dv, cudaStream_t st) {
+  if (dtype == NS_F32)
+    return s.Dh == 64 ? attn_bwd_simt_t<float, 64>(s, q, k, v, o, d_o, lse, delta, dq, dk, dv, st)
+                      : attn_bwd_simt_t<float, 32>(s, q, k, v, o, d_o, lse, delta, dq, dk, dv, st);
+  return s.Dh == 64 ? attn_bwd_simt_t<__nv_bfloat16, 64>(s, q, k, v, o, d_o, lse, delta, dq, dk, dv, st)
+                    : attn_bwd_simt_t<__nv_bfloat16, 32>(s, q, k, v, o, d_o, lse, delta, dq, dk, dv, st);
+}
+
+}  // namespace ns

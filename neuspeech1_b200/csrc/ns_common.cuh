@@ -1,0 +1,123 @@
+// Shared host/device helpers for libneuspeech_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/neuspeech_b200.h"
+
+namespace ns {
+
+// ---------------------------------------------------------------- error handling (no exceptions across the ABI)
+void set_error(const char* fmt, ...);
+extern thread_local int g_path;           // ns_path
+enum Counter { C_GEMM_TC = 0, C_GEMM_SIMT = 1, C_ATTN_TC = 2, C_ATTN_SIMT = 3, C_OTHER = 4, C_WGRAD_TC = 5, C_NUM = 8 };
+void count(int which, long long n = 1);
+int sm_count();
+
+#define NS_CHECK_ARG(cond, ...)                       \
+  do {                                                \
+    if (!(cond)) {                                    \
+      ns::set_error(__VA_ARGS__);                     \
+      return NS_ERR_ARG;                              \
+    }                                                 \
+  } while (0)
+
+#define NS_CUDA(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      ns::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return NS_ERR_CUDA;                                                                      \
+    }                                                                                          \
+  } while (0)
+
+#define NS_LAUNCH_CHECK() NS_CUDA(cudaPeekAtLastError())
+
+inline size_t dsize(int dt) { return dt == NS_BF16 ? 2 : 4; }
+inline bool valid_dtype(int dt) { return dt == NS_F32 || dt == NS_BF16; }
+
+// ---------------------------------------------------------------- device numeric helpers
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// d/dx [x * Phi(x)] = Phi(x) + x * phi(x)
+__device__ __forceinline__ float dgelu_erf(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(v);
+}
+
+// Epilogue description in device form (shared by the SIMT and the tcgen05 GEMMs).
+struct EpiDev {
+  const float* bias;
+  float alpha;
+  int alpha_cols;
+  int act;
+  const void* aux_in;
+  void* aux_out;
+  long long ldaux;
+  const void* residual;
+  long long ldr;
+  int res_mod;
+  int out_f32;   // 1: D is fp32
+};
+
+inline EpiDev make_epi(const ns_epilogue* ep, int dtype) {
+  EpiDev e;
+  memset(&e, 0, sizeof(e));
+  e.alpha = 1.0f;
+  e.out_f32 = (dtype == NS_F32);
+  if (ep) {
+    e.bias = ep->bias; e.alpha = ep->alpha; e.alpha_cols = ep->alpha_cols; e.act = ep->act;
+    e.aux_in = ep->aux_in; e.aux_out = ep->aux_out; e.ldaux = ep->ldaux;
+    e.residual = ep->residual; e.ldr = ep->ldr; e.res_mod = ep->res_mod;
+    e.out_f32 = (ep->out_dtype == NS_F32);
+  }
+  return e;
+}
+
+// Apply the element epilogue.  `T` = storage type of aux/residual (the activation dtype).
+template <typename T>
+__device__ __forceinline__ float epi_apply(const EpiDev& e, float acc, long long row, long long res_row, int col) {
+  float x = acc;
+  if (e.bias) x += __ldg(e.bias + col);
+  if (col < e.alpha_cols) x *= e.alpha;
+  if (e.act == NS_ACT_GELU) {
+    if (e.aux_out) reinterpret_cast<T*>(e.aux_out)[row * e.ldaux + col] = from_f<T>(x);
+    x = gelu_erf(x);
+  } else if (e.act == NS_ACT_DGELU) {
+    x *= dgelu_erf(to_f<T>(reinterpret_cast<const T*>(e.aux_in)[row * e.ldaux + col]));
+  }
+  if (e.residual) x += to_f<T>(reinterpret_cast<const T*>(e.residual)[res_row * e.ldr + col]);
+  return x;
+}
+
+}  // namespace ns

@@ -1,0 +1,775 @@
+// tcgen05 / TMEM / TMA GEMM family for sm_100a (bf16 operands, fp32 accumulation in tensor memory).
+//
+//   gemm_nt_kernel<BN> : persistent, warp-specialised  D = epi( sum_seg A_seg * W_seg^T )   (both operands K-major)
+//        segments = main product, optional LoRA product (K2 = rank), or the 3 taps of a k=3 convolution (implicit GEMM:
+//        the A tile of tap k is the same activation tensor at a shifted / parity-selected row coordinate; TMA zero-fills
+//        the out-of-range rows, which is exactly the conv's zero padding).
+//   gemm_tn_kernel     : split-K weight-gradient GEMM  G += alpha * X^T Y  (both operands MN-major, fp32 atomics).
+//
+// Warp roles (gemm_nt): warp0 = TMA producer, warp1 = MMA issuer (single thread), warp2 = TMEM allocator,
+// warps 4..11 = epilogue (TMEM -> registers -> fused bias/scale/GELU/residual -> global).  Two TMEM accumulator stages
+// let the epilogue of tile i overlap the main loop of tile i+1.
+#include "ns_common.cuh"
+#include "ns_sm100.cuh"
+#include "ns_gemm.cuh"
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+namespace ns {
+using namespace sm100;
+
+// ------------------------------------------------------------------------------------------------ tensor maps
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = []() -> PFN_encodeTiled {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+    if (q != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<PFN_encodeTiled>(f);
+  }();
+  return fn;
+}
+
+// bf16 tensor map, 128B swizzle, zero OOB fill.  dims[0] is the contiguous dim; strides in BYTES for dims 1..rank-1.
+static int make_map(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_b,
+                    const uint32_t* box) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return NS_ERR_CUDA;
+  }
+  cuuint64_t gd[5];
+  cuuint64_t gs[4];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) {
+      gs[i - 1] = strides_b[i - 1];
+      if (gs[i - 1] % 16 != 0) {
+        set_error("tensor map stride %d = %llu bytes is not a multiple of 16", i, (unsigned long long)gs[i - 1]);
+        return NS_ERR_ARG;
+      }
+    }
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) {
+    set_error("tensor map base pointer not 16-byte aligned");
+    return NS_ERR_ARG;
+  }
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu,%llu box %u,%u,%u)", (int)r, rank,
+              (unsigned long long)gd[0], (unsigned long long)(rank > 1 ? gd[1] : 0),
+              (unsigned long long)(rank > 2 ? gd[2] : 0), bx[0], rank > 1 ? bx[1] : 0, rank > 2 ? bx[2] : 0);
+    return NS_ERR_CUDA;
+  }
+  return NS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel parameters
+struct Seg {
+  int kblocks;      // 64-wide K blocks in this segment
+  int last_ksteps;  // UMMA K=16 steps issued in the last block (1..4)
+  int a_map, b_map; // which tensor map
+  int a_off;        // row offset added to the tile's first row (conv taps)
+  int a_par;        // parity coordinate (stride-2 convs view the input as (.., T/2, 2, C))
+  int b_tap;        // 3rd coordinate of the weight map
+  int a_ngrp;       // if > 0: A's k coordinate is advanced by (n0 / a_ngrp) * a_kstep (stacked LoRA adapters)
+  int a_kstep;
+};
+
+struct TileProg {
+  int nseg;
+  Seg seg[4];
+  int batches, tout, tiles_per_batch, n_tiles, N;
+  long long out_bs, out_rs, out_off, ldd;
+  void* D;
+  EpiDev epi;
+  int vec_out, vec_aux, vec_res;
+};
+
+struct Maps {
+  CUtensorMap a[2];
+  CUtensorMap b[2];
+};
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kABytes = kBM * kBK * 2;
+constexpr int kNtThreads = 384;
+
+template <int BN> struct NtCfg {
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ------------------------------------------------------------------------------------------------ epilogue helpers
+__device__ __forceinline__ void load32_bf16(const __nv_bfloat16* p, bool vec, int ncols, float (&o)[32]) {
+  if (vec) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 u = __ldg(q + i);
+      float2 f;
+      f = unpack_bf16x2(u.x); o[8 * i + 0] = f.x; o[8 * i + 1] = f.y;
+      f = unpack_bf16x2(u.y); o[8 * i + 2] = f.x; o[8 * i + 3] = f.y;
+      f = unpack_bf16x2(u.z); o[8 * i + 4] = f.x; o[8 * i + 5] = f.y;
+      f = unpack_bf16x2(u.w); o[8 * i + 6] = f.x; o[8 * i + 7] = f.y;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = (j < ncols) ? __bfloat162float(p[j]) : 0.0f;
+  }
+}
+__device__ __forceinline__ void store32_bf16(__nv_bfloat16* p, bool vec, int ncols, const float (&x)[32]) {
+  if (vec) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 u;
+      u.x = pack_bf16x2(x[8 * i + 0], x[8 * i + 1]);
+      u.y = pack_bf16x2(x[8 * i + 2], x[8 * i + 3]);
+      u.z = pack_bf16x2(x[8 * i + 4], x[8 * i + 5]);
+      u.w = pack_bf16x2(x[8 * i + 6], x[8 * i + 7]);
+      q[i] = u;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < ncols) p[j] = __float2bfloat16_rn(x[j]);
+  }
+}
+__device__ __forceinline__ void store32_f32(float* p, bool vec, int ncols, const float (&x)[32]) {
+  if (vec) {
+    float4* q = reinterpret_cast<float4*>(p);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < ncols) p[j] = x[j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ NT kernel
+template <int BN>
+__global__ void __launch_bounds__(kNtThreads, 1)
+gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TileProg p) {
+  using Cfg = NtCfg<BN>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + S * Cfg::kStageBytes;
+  // barrier addresses
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.batches * p.tiles_per_batch * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a[0]);
+    tma_prefetch_desc(&maps.b[0]);
+    if (p.nseg > 1) {
+      tma_prefetch_desc(&maps.a[1]);
+      tma_prefetch_desc(&maps.b[1]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 8);   // one arrive per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        const int b = m_tile / p.tiles_per_batch;
+        const int t0 = (m_tile % p.tiles_per_batch) * kBM;
+        const int n0 = n_tile * BN;
+        for (int s = 0; s < p.nseg; ++s) {
+          const Seg& sg = p.seg[s];
+          const int kbase = sg.a_ngrp > 0 ? (n0 / sg.a_ngrp) * sg.a_kstep : 0;
+          for (int kb = 0; kb < sg.kblocks; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+            const uint32_t sb = sa + kABytes;
+            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            tma_load_4d(&maps.a[sg.a_map], full_bar(stage), sa, kbase + kb * kBK, sg.a_par, t0 + sg.a_off, b);
+            tma_load_3d(&maps.b[sg.b_map], full_bar(stage), sb, kb * kBK, n0, sg.b_tap);
+            if (++stage == S) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+      uint32_t accumulate = 0;
+      for (int s = 0; s < p.nseg; ++s) {
+        const Seg& sg = p.seg[s];
+        for (int kb = 0; kb < sg.kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+            const uint32_t sb = sa + kABytes;
+            const int ksteps = (kb == sg.kblocks - 1) ? sg.last_ksteps : 4;
+            const uint64_t adesc = umma_smem_desc(sa, 16, 1024);
+            const uint64_t bdesc = umma_smem_desc(sb, 16, 1024);
+            for (int k = 0; k < ksteps; ++k) {
+              // advance 16 elements (32 B) along K inside the 128B swizzle row: +2 in the (addr >> 4) field
+              umma_f16(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(empty_bar(stage));   // frees the smem stage when these MMAs have read it
+          }
+          __syncwarp();
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+      }
+      if (lane == 0) umma_commit(tfull_bar(acc));
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ================================================================ epilogue
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;  // which half of the tile's columns
+    constexpr int kHalfCols = (BN >= 64) ? BN / 2 : BN;
+    const EpiDev& e = p.epi;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int b = m_tile / p.tiles_per_batch;
+      const int t = (m_tile % p.tiles_per_batch) * kBM + q * 32 + lane;
+      const int n0 = n_tile * BN;
+      const bool valid = t < p.tout;
+      const long long row = static_cast<long long>(b) * p.out_bs + static_cast<long long>(t) * p.out_rs + p.out_off;
+      const long long res_row = e.res_mod > 0 ? ((static_cast<long long>(t) * p.out_rs + p.out_off) % e.res_mod) : row;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      if (BN >= 64 || half == 0) {
+#pragma unroll 1
+        for (int c = 0; c < kHalfCols; c += 32) {
+          const int col0 = n0 + half * kHalfCols + c;
+          if (col0 >= p.N) break;   // warp-uniform
+          const int ncols = min(32, p.N - col0);
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + half * kHalfCols + c), v);
+          tmem_ld_wait();
+          float x[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+          if (e.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) x[j] += __ldg(e.bias + col0 + j);
+          }
+          if (col0 < e.alpha_cols) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < e.alpha_cols) x[j] *= e.alpha;
+          }
+          const bool full = (ncols == 32);
+          if (e.act == NS_ACT_GELU) {
+            if (e.aux_out && valid)
+              store32_bf16(reinterpret_cast<__nv_bfloat16*>(e.aux_out) + row * e.ldaux + col0, p.vec_aux && full, ncols, x);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+          } else if (e.act == NS_ACT_DGELU) {
+            if (valid) {
+              float z[32];
+              load32_bf16(reinterpret_cast<const __nv_bfloat16*>(e.aux_in) + row * e.ldaux + col0, p.vec_aux && full, ncols, z);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] *= dgelu_erf(z[j]);
+            }
+          }
+          if (e.residual && valid) {
+            float r[32];
+            load32_bf16(reinterpret_cast<const __nv_bfloat16*>(e.residual) + res_row * e.ldr + col0, p.vec_res && full, ncols, r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] += r[j];
+          }
+          if (valid) {
+            if (e.out_f32)
+              store32_f32(reinterpret_cast<float*>(p.D) + row * p.ldd + col0, p.vec_out && full, ncols, x);
+            else
+              store32_bf16(reinterpret_cast<__nv_bfloat16*>(p.D) + row * p.ldd + col0, p.vec_out && full, ncols, x);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ TN (wgrad) kernel
+struct TnProg {
+  int batches, tout;          // contraction = batches x tout rows (tout padded per batch by TMA zero fill)
+  int blocks_per_batch;       // ceil(tout / 64)
+  int total_blocks, blocks_per_split, nsplit;
+  int i_tiles, j_tiles, ntaps;
+  int I, J, bj;               // logical sizes; bj = UMMA N (multiple of 16, <= 256)
+  int y_off[3], y_par[3];     // per tap: row offset / parity coordinate of Y
+  long long si, sj, stap;     // output strides
+  float* G;
+  float alpha;
+};
+struct TnMaps {
+  CUtensorMap x;
+  CUtensorMap y;
+};
+constexpr int kTnThreads = 256;
+constexpr int kTnStages = 4;
+constexpr int kTnABytes = 128 * 64 * 2;        // two [64 m][64 i] boxes
+constexpr int kTnBBytes = 256 * 64 * 2;        // up to four [64 m][64 j] boxes
+constexpr int kTnStageBytes = kTnABytes + kTnBBytes;
+constexpr int kTnSmemBytes = kTnStages * kTnStageBytes + 1024 + 256;
+
+__global__ void __launch_bounds__(kTnThreads, 1)
+gemm_tn_kernel(const __grid_constant__ TnMaps maps, const __grid_constant__ TnProg p) {
+  constexpr int S = kTnStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + S * kTnStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * S);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 1);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // decode work item: (tile, split)
+  const int split = blockIdx.x % p.nsplit;
+  int tile = blockIdx.x / p.nsplit;
+  const int j_tile = tile % p.j_tiles; tile /= p.j_tiles;
+  const int i_tile = tile % p.i_tiles; tile /= p.i_tiles;
+  const int tap = tile;
+  const int blk0 = split * p.blocks_per_split;
+  const int blk1 = min(p.total_blocks, blk0 + p.blocks_per_split);
+  const int nblk = max(0, blk1 - blk0);
+  const int i0 = i_tile * 128;
+  const int j0 = j_tile * 256;
+  const int jboxes = (p.bj + 63) / 64;
+  const uint32_t stage_tx = kTnABytes + static_cast<uint32_t>(jboxes) * 8192u;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int blk = blk0; blk < blk1; ++blk) {
+        const int b = blk / p.blocks_per_batch;
+        const int t0 = (blk % p.blocks_per_batch) * 64;
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sa = smem_base + stage * kTnStageBytes;
+        const uint32_t sb = sa + kTnABytes;
+        mbar_expect_tx(full_bar(stage), stage_tx);
+        tma_load_4d(&maps.x, full_bar(stage), sa, i0, 0, t0, b);
+        tma_load_4d(&maps.x, full_bar(stage), sa + 8192u, i0 + 64, 0, t0, b);
+        for (int g = 0; g < jboxes; ++g)
+          tma_load_4d(&maps.y, full_bar(stage), sb + 8192u * g, j0 + 64 * g, p.y_par[tap], t0 + p.y_off[tap], b);
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = umma_idesc_bf16(128, p.bj, 1, 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t accumulate = 0;
+    for (int blk = blk0; blk < blk1; ++blk) {
+      mbar_wait(full_bar(stage), phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_base + stage * kTnStageBytes;
+        const uint32_t sb = sa + kTnABytes;
+        // MN-major: LBO = distance between 64-element MN groups (8192 B), SBO = distance between 8-row K groups (1024 B)
+        const uint64_t adesc = umma_smem_desc(sa, 8192, 1024);
+        const uint64_t bdesc = umma_smem_desc(sb, 8192, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // 16 contraction rows = 2048 B  -> +128 in the (addr >> 4) field
+          umma_f16(tmem_base, adesc + static_cast<uint64_t>(128 * k), bdesc + static_cast<uint64_t>(128 * k), idesc, accumulate);
+          accumulate = 1;
+        }
+        umma_commit(empty_bar(stage));
+      }
+      __syncwarp();
+      if (++stage == S) { stage = 0; phase ^= 1u; }
+    }
+    if (lane == 0) umma_commit(tfull_bar);
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    if (nblk > 0) {
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+      const int i = i0 + q * 32 + lane;
+      float* g_row = p.G + static_cast<long long>(tap) * p.stap + static_cast<long long>(i) * p.si;
+#pragma unroll 1
+      for (int c = 0; c < p.bj; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c), v);
+        tmem_ld_wait();
+        if (i < p.I) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int jj = j0 + c + j;
+            if (jj < p.J) atomicAdd(g_row + static_cast<long long>(jj) * p.sj, p.alpha * __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host launchers
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int BN>
+static int launch_nt(const Maps& maps, TileProg& prog, cudaStream_t st) {
+  using Cfg = NtCfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    NS_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  prog.n_tiles = (prog.N + BN - 1) / BN;
+  const long long total = static_cast<long long>(prog.batches) * prog.tiles_per_batch * prog.n_tiles;
+  const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
+  if (grid <= 0) return NS_OK;
+  gemm_nt_kernel<BN><<<grid, kNtThreads, Cfg::kSmemBytes, st>>>(maps, prog);
+  NS_LAUNCH_CHECK();
+  count(C_GEMM_TC);
+  return NS_OK;
+}
+
+static int dispatch_nt(const Maps& maps, TileProg& prog, cudaStream_t st) {
+  const int N = prog.N;
+  if (N >= 256 || N > 128) return launch_nt<256>(maps, prog, st);
+  if (N > 64) return launch_nt<128>(maps, prog, st);
+  if (N > 32) return launch_nt<64>(maps, prog, st);
+  return launch_nt<32>(maps, prog, st);
+}
+
+static void fill_epi(TileProg& prog, const EpiDev& e) {
+  prog.epi = e;
+  const bool f32 = e.out_f32;
+  prog.vec_out = aligned16(prog.D) && (prog.ldd % (f32 ? 4 : 8) == 0);
+  const void* aux = e.act == NS_ACT_GELU ? e.aux_out : e.aux_in;
+  prog.vec_aux = aux && aligned16(aux) && (e.ldaux % 8 == 0);
+  prog.vec_res = e.residual && aligned16(e.residual) && (e.ldr % 8 == 0);
+}
+
+static void seg_from_k(Seg& s, int K) {
+  s.kblocks = (K + kBK - 1) / kBK;
+  const int rem = K - (s.kblocks - 1) * kBK;
+  s.last_ksteps = (rem + 15) / 16;
+}
+
+// Fast path of ns_gemm_nt.  Returns NS_ERR_UNSUPPORTED when the shape does not qualify.
+int gemm_nt_fast(long long M, int N, int K, const void* A, long long lda, const void* W, long long ldw, void* D,
+                 long long ldd, const EpiDev& epi, const void* A2, long long lda2, const void* W2, long long ldw2,
+                 int K2, int a2_ngrp, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return NS_OK;
+  if (K % 16 != 0 || lda % 8 != 0 || ldw % 8 != 0 || !aligned16(A) || !aligned16(W)) return NS_ERR_UNSUPPORTED;
+  if (A2 && (K2 % 16 != 0 || lda2 % 8 != 0 || ldw2 % 8 != 0 || !aligned16(A2) || !aligned16(W2))) return NS_ERR_UNSUPPORTED;
+  if (M > 0x7fffffffLL) return NS_ERR_UNSUPPORTED;
+  Maps maps;
+  TileProg prog;
+  memset(&prog, 0, sizeof(prog));
+  const int bn = (N > 128) ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
+  {
+    uint64_t dims[4] = {(uint64_t)K, 1, (uint64_t)M, 1};
+    uint64_t str[3] = {(uint64_t)lda * 2, (uint64_t)lda * 2, (uint64_t)lda * 2 * (uint64_t)M};
+    uint32_t box[4] = {kBK, 1, kBM, 1};
+    int r = make_map(&maps.a[0], A, 4, dims, str, box);
+    if (r) return r;
+    uint64_t dimb[3] = {(uint64_t)K, (uint64_t)N, 1};
+    uint64_t strb[2] = {(uint64_t)ldw * 2, (uint64_t)ldw * 2 * (uint64_t)N};
+    uint32_t boxb[3] = {kBK, (uint32_t)bn, 1};
+    r = make_map(&maps.b[0], W, 3, dimb, strb, boxb);
+    if (r) return r;
+  }
+  prog.nseg = 1;
+  seg_from_k(prog.seg[0], K);
+  if (A2) {
+    // the LoRA operand may be a column window of a wider stacked buffer: expose the whole row (lda2 columns)
+    uint64_t dims[4] = {(uint64_t)(a2_ngrp > 0 ? lda2 : K2), 1, (uint64_t)M, 1};
+    uint64_t str[3] = {(uint64_t)lda2 * 2, (uint64_t)lda2 * 2, (uint64_t)lda2 * 2 * (uint64_t)M};
+    uint32_t box[4] = {kBK, 1, kBM, 1};
+    int r = make_map(&maps.a[1], A2, 4, dims, str, box);
+    if (r) return r;
+    uint64_t dimb[3] = {(uint64_t)K2, (uint64_t)N, 1};
+    uint64_t strb[2] = {(uint64_t)ldw2 * 2, (uint64_t)ldw2 * 2 * (uint64_t)N};
+    uint32_t boxb[3] = {kBK, (uint32_t)bn, 1};
+    r = make_map(&maps.b[1], W2, 3, dimb, strb, boxb);
+    if (r) return r;
+    prog.nseg = 2;
+    seg_from_k(prog.seg[1], K2);
+    prog.seg[1].a_map = 1;
+    prog.seg[1].b_map = 1;
+    prog.seg[1].a_ngrp = a2_ngrp;
+    prog.seg[1].a_kstep = K2;
+  } else {
+    maps.a[1] = maps.a[0];
+    maps.b[1] = maps.b[0];
+  }
+  prog.batches = 1;
+  prog.tout = static_cast<int>(M);
+  prog.tiles_per_batch = static_cast<int>((M + kBM - 1) / kBM);
+  prog.N = N;
+  prog.out_bs = 0; prog.out_rs = 1; prog.out_off = 0;
+  prog.ldd = ldd;
+  prog.D = D;
+  fill_epi(prog, epi);
+  return dispatch_nt(maps, prog, st);
+}
+
+// Implicit-GEMM k=3 convolution forward on channels-last bf16 (see ns_conv3_fwd).
+int conv3_fwd_fast(int B, int Tin, int Cp, int N, int stride, const void* x, const void* w, void* y, const EpiDev& epi,
+                   cudaStream_t st) {
+  if (Cp % 16 != 0 || !aligned16(x) || !aligned16(w) || (stride != 1 && stride != 2) || Tin % stride != 0)
+    return NS_ERR_UNSUPPORTED;
+  Maps maps;
+  TileProg prog;
+  memset(&prog, 0, sizeof(prog));
+  const int Tout = Tin / stride;
+  const int bn = (N > 128) ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
+  uint64_t dims[4] = {(uint64_t)Cp, (uint64_t)stride, (uint64_t)Tout, (uint64_t)B};
+  uint64_t str[3] = {(uint64_t)Cp * 2, (uint64_t)Cp * 2 * stride, (uint64_t)Cp * 2 * (uint64_t)Tin};
+  uint32_t box[4] = {kBK, 1, kBM, 1};
+  int r = make_map(&maps.a[0], x, 4, dims, str, box);
+  if (r) return r;
+  uint64_t dimb[3] = {(uint64_t)Cp, (uint64_t)N, 3};
+  uint64_t strb[2] = {(uint64_t)Cp * 2, (uint64_t)Cp * 2 * (uint64_t)N};
+  uint32_t boxb[3] = {kBK, (uint32_t)bn, 1};
+  r = make_map(&maps.b[0], w, 3, dimb, strb, boxb);
+  if (r) return r;
+  maps.a[1] = maps.a[0];
+  maps.b[1] = maps.b[0];
+  prog.nseg = 3;
+  for (int k = 0; k < 3; ++k) {
+    seg_from_k(prog.seg[k], Cp);
+    prog.seg[k].b_tap = k;
+    if (stride == 1) {
+      prog.seg[k].a_off = k - 1;
+      prog.seg[k].a_par = 0;
+    } else {  // input row 2t+k-1:  k=0 -> (t-1, parity 1), k=1 -> (t, 0), k=2 -> (t, 1)
+      prog.seg[k].a_off = (k == 0) ? -1 : 0;
+      prog.seg[k].a_par = (k == 1) ? 0 : 1;
+    }
+  }
+  prog.batches = B;
+  prog.tout = Tout;
+  prog.tiles_per_batch = (Tout + kBM - 1) / kBM;
+  prog.N = N;
+  prog.out_bs = Tout; prog.out_rs = 1; prog.out_off = 0;
+  prog.ldd = N;
+  prog.D = y;
+  fill_epi(prog, epi);
+  return dispatch_nt(maps, prog, st);
+}
+
+// Input gradient of the stride-2 conv: one launch per output-row parity (see ns_conv3_dgrad).
+int conv3_dgrad_fast(int B, int Tin, int Cp, int N, int stride, const void* dz, const void* wt, void* dx,
+                     const EpiDev& epi, cudaStream_t st) {
+  if (stride != 2 || N % 16 != 0 || Cp % 8 != 0 || !aligned16(dz) || !aligned16(wt) || Tin % 2 != 0)
+    return NS_ERR_UNSUPPORTED;
+  const int Tout = Tin / 2;
+  const int bn = (Cp > 128) ? 256 : (Cp > 64 ? 128 : (Cp > 32 ? 64 : 32));
+  Maps maps;
+  uint64_t dims[4] = {(uint64_t)N, 1, (uint64_t)Tout, (uint64_t)B};
+  uint64_t str[3] = {(uint64_t)N * 2, (uint64_t)N * 2, (uint64_t)N * 2 * (uint64_t)Tout};
+  uint32_t box[4] = {kBK, 1, kBM, 1};
+  int r = make_map(&maps.a[0], dz, 4, dims, str, box);
+  if (r) return r;
+  uint64_t dimb[3] = {(uint64_t)N, (uint64_t)Cp, 3};
+  uint64_t strb[2] = {(uint64_t)N * 2, (uint64_t)N * 2 * (uint64_t)Cp};
+  uint32_t boxb[3] = {kBK, (uint32_t)bn, 1};
+  r = make_map(&maps.b[0], wt, 3, dimb, strb, boxb);
+  if (r) return r;
+  maps.a[1] = maps.a[0];
+  maps.b[1] = maps.b[0];
+  for (int par = 0; par < 2; ++par) {
+    TileProg prog;
+    memset(&prog, 0, sizeof(prog));
+    if (par == 0) {          // dx[2j]   = dz[j] W1
+      prog.nseg = 1;
+      seg_from_k(prog.seg[0], N);
+      prog.seg[0].b_tap = 1;
+    } else {                 // dx[2j+1] = dz[j] W2 + dz[j+1] W0
+      prog.nseg = 2;
+      seg_from_k(prog.seg[0], N); prog.seg[0].b_tap = 2; prog.seg[0].a_off = 0;
+      seg_from_k(prog.seg[1], N); prog.seg[1].b_tap = 0; prog.seg[1].a_off = 1;
+    }
+    prog.batches = B;
+    prog.tout = Tout;
+    prog.tiles_per_batch = (Tout + kBM - 1) / kBM;
+    prog.N = Cp;
+    prog.out_bs = Tin; prog.out_rs = 2; prog.out_off = par;
+    prog.ldd = Cp;
+    prog.D = dx;
+    fill_epi(prog, epi);
+    r = dispatch_nt(maps, prog, st);
+    if (r) return r;
+  }
+  return NS_OK;
+}
+
+static int launch_tn(const TnMaps& maps, TnProg& p, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    NS_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTnSmemBytes));
+    attr_done = true;
+  }
+  p.blocks_per_batch = (p.tout + 63) / 64;
+  p.total_blocks = p.batches * p.blocks_per_batch;
+  p.i_tiles = (p.I + 127) / 128;
+  p.j_tiles = (p.J + 255) / 256;
+  const int jt = p.J < 256 ? p.J : 256;   // all j tiles use the same UMMA N (tail columns masked in the epilogue)
+  p.bj = (jt + 15) / 16 * 16;
+  const int tiles = p.i_tiles * p.j_tiles * p.ntaps;
+  int nsplit = (2 * sm_count() + tiles - 1) / tiles;
+  const int max_split = (p.total_blocks + 3) / 4;           // at least 4 contraction blocks per CTA
+  if (nsplit > max_split) nsplit = max_split;
+  if (nsplit < 1) nsplit = 1;
+  p.blocks_per_split = (p.total_blocks + nsplit - 1) / nsplit;
+  p.nsplit = (p.total_blocks + p.blocks_per_split - 1) / p.blocks_per_split;
+  gemm_tn_kernel<<<tiles * p.nsplit, kTnThreads, kTnSmemBytes, st>>>(maps, p);
+  NS_LAUNCH_CHECK();
+  count(C_WGRAD_TC);
+  return NS_OK;
+}
+
+int gemm_tn_fast(long long M, int I, int J, const void* X, long long ldx, const void* Y, long long ldy, float* G,
+                 long long si, long long sj, float alpha, cudaStream_t st) {
+  if (ldx % 8 != 0 || ldy % 8 != 0 || !aligned16(X) || !aligned16(Y) || M > 0x7fffffffLL) return NS_ERR_UNSUPPORTED;
+  if (I % 8 != 0 || J % 8 != 0) return NS_ERR_UNSUPPORTED;
+  TnMaps maps;
+  uint64_t dx[4] = {(uint64_t)I, 1, (uint64_t)M, 1};
+  uint64_t sx[3] = {(uint64_t)ldx * 2, (uint64_t)ldx * 2, (uint64_t)ldx * 2 * (uint64_t)M};
+  uint32_t box[4] = {64, 1, 64, 1};
+  int r = make_map(&maps.x, X, 4, dx, sx, box);
+  if (r) return r;
+  uint64_t dy[4] = {(uint64_t)J, 1, (uint64_t)M, 1};
+  uint64_t sy[3] = {(uint64_t)ldy * 2, (uint64_t)ldy * 2, (uint64_t)ldy * 2 * (uint64_t)M};
+  r = make_map(&maps.y, Y, 4, dy, sy, box);
+  if (r) return r;
+  TnProg p;
+  memset(&p, 0, sizeof(p));
+  p.batches = 1; p.tout = static_cast<int>(M); p.ntaps = 1;
+  p.I = I; p.J = J; p.si = si; p.sj = sj; p.stap = 0; p.G = G; p.alpha = alpha;
+  return launch_tn(maps, p, st);
+}
+
+// dw (3, N, Cp) += sum_{b,t} dz[b,t,n] x[b, stride*t + k - 1, c]
+int conv3_wgrad_fast(int B, int Tin, int Cp, int N, int stride, const void* dz, const void* x, float* dw,
+                     cudaStream_t st) {
+  if (Cp % 8 != 0 || N % 8 != 0 || !aligned16(dz) || !aligned16(x) || (stride != 1 && stride != 2) || Tin % stride != 0)
+    return NS_ERR_UNSUPPORTED;
+  const int Tout = Tin / stride;
+  TnMaps maps;
+  uint64_t dxm[4] = {(uint64_t)N, 1, (uint64_t)Tout, (uint64_t)B};
+  uint64_t sxm[3] = {(uint64_t)N * 2, (uint64_t)N * 2, (uint64_t)N * 2 * (uint64_t)Tout};
+  uint32_t box[4] = {64, 1, 64, 1};
+  int r = make_map(&maps.x, dz, 4, dxm, sxm, box);
+  if (r) return r;
+  uint64_t dym[4] = {(uint64_t)Cp, (uint64_t)stride, (uint64_t)Tout, (uint64_t)B};
+  uint64_t sym[3] = {(uint64_t)Cp * 2, (uint64_t)Cp * 2 * stride, (uint64_t)Cp * 2 * (uint64_t)Tin};
+  r = make_map(&maps.y, x, 4, dym, sym, box);
+  if (r) return r;
+  TnProg p;
+  memset(&p, 0, sizeof(p));
+  p.batches = B; p.tout = Tout; p.ntaps = 3;
+  p.I = N; p.J = Cp; p.si = Cp; p.sj = 1; p.stap = static_cast<long long>(N) * Cp; p.G = dw; p.alpha = 1.0f;
+  for (int k = 0; k < 3; ++k) {
+    if (stride == 1) { p.y_off[k] = k - 1; p.y_par[k] = 0; }
+    else { p.y_off[k] = (k == 0) ? -1 : 0; p.y_par[k] = (k == 1) ? 0 : 1; }
+  }
+  return launch_tn(maps, p, st);
+}
+
+}  // namespace ns

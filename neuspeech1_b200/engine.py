@@ -1,0 +1,722 @@
+"""Execution engine of the EEG-conditioned Whisper hot path on B200.
+
+Host-side orchestration (which kernel, on which buffer, in which order) of the path the reference runs through
+`utils/load_model.py::WhisperForConditionalGeneration.forward/generate` (utils/load_model.py:371-476, :534-767,
+:976-1070, :1072-1351) with PEFT LoRA on the encoder linears (finetune.py:194-212).  All arithmetic happens in
+libneuspeech_b200.so (neuspeech1_b200/ops.py); torch only owns the HBM buffers and the stream.
+
+Data layout in HBM (row-major, activations in `dtype` = bf16 or fp32, statistics / master weights / grads in fp32):
+  x_cl   (B, T, Cp)        channels-last EEG after the augmentation pass, Cp = eeg_ch rounded up to 16
+  a*,z*  (B, T|T/2|S, d)   stem activations / pre-activations (z kept for the GELU backward)
+  h      (B*S, d)          residual stream;  qkv (B*S, 3d) packed [q|k|v];  m,z1 (B*S, F)
+  t_*    (B*S, r|3r)       LoRA bottlenecks t = s * x A^T (s = alpha/r folded in)
+  kv_all (B*S, Nd*2d)      cross-attention K|V of all decoder layers, one GEMM
+  trainable parameters live in ONE flat fp32 buffer (LoRA A/B per layer, then the three stem convs) with a flat fp32
+  gradient buffer of the same layout: one fused clip+AdamW launch and one all-reduce cover everything.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+from ._abi import ACT_DGELU, ACT_GELU, ACT_NONE, NS_BF16, NS_F32
+
+ENC_LORA_TARGETS = ("q_proj", "k_proj", "v_proj", "out_proj", "fc1", "fc2")
+
+
+@dataclass
+class ModelDims:
+    """The WhisperConfig fields the path reads (+ the EEG stem's channel count and the LoRA hyper-parameters)."""
+    d_model: int = 512
+    enc_layers: int = 6
+    dec_layers: int = 6
+    enc_heads: int = 8
+    dec_heads: int = 8
+    enc_ffn: int = 2048
+    dec_ffn: int = 2048
+    vocab: int = 51865
+    max_source_positions: int = 1500
+    max_target_positions: int = 448
+    eeg_ch: int = 208
+    pad_token_id: int = 50257
+    eos_token_id: int = 50257
+    decoder_start_token_id: int = 50258
+    begin_suppress_tokens: Tuple[int, ...] = (220, 50256)
+    lora_r: int = 32
+    lora_alpha: int = 64
+
+    @property
+    def T(self) -> int:
+        return self.max_source_positions * 4
+
+    @property
+    def lora_scale(self) -> float:
+        return self.lora_alpha / self.lora_r
+
+    @property
+    def Cp(self) -> int:
+        return (self.eeg_ch + 15) // 16 * 16
+
+    @property
+    def Vp(self) -> int:
+        return (self.vocab + 15) // 16 * 16
+
+    @classmethod
+    def from_any(cls, o) -> "ModelDims":
+        """Build from any object with the same attribute names (e.g. the oracle's Dims or a dict)."""
+        get = (lambda k: o[k]) if isinstance(o, dict) else (lambda k: getattr(o, k))
+        return cls(**{f: get(f) for f in cls.__dataclass_fields__})
+
+
+def lora_module_name(layer: int, target: str) -> str:
+    return f"model.encoder.layers.{layer}." + (target if target.startswith("fc") else f"self_attn.{target}")
+
+
+class TrainableLayout:
+    """Flat layout of the trainable set (finetune.py:176-212): LoRA A/B of 6 linears per encoder layer + 3 stem convs."""
+
+    def __init__(self, dims: ModelDims, with_lora: bool = True):
+        self.entries: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
+        off = 0
+        d, r, F = dims.d_model, dims.lora_r, dims.enc_ffn
+
+        def add(name, shape):
+            nonlocal off
+            n = int(math.prod(shape))
+            self.entries[name] = (off, tuple(shape))
+            off += (n + 63) // 64 * 64
+
+        self.lora_begin = off
+        if with_lora:
+            for i in range(dims.enc_layers):
+                for t in ("q_proj", "k_proj", "v_proj"):          # A_q, A_k, A_v contiguous -> stacked (3r, d) view
+                    add(lora_module_name(i, t) + ".lora_A.default.weight", (r, d))
+                for t in ("q_proj", "k_proj", "v_proj"):          # B_q, B_k, B_v contiguous -> stacked (3d, r) view
+                    add(lora_module_name(i, t) + ".lora_B.default.weight", (d, r))
+                add(lora_module_name(i, "out_proj") + ".lora_A.default.weight", (r, d))
+                add(lora_module_name(i, "out_proj") + ".lora_B.default.weight", (d, r))
+                add(lora_module_name(i, "fc1") + ".lora_A.default.weight", (r, d))
+                add(lora_module_name(i, "fc1") + ".lora_B.default.weight", (F, r))
+                add(lora_module_name(i, "fc2") + ".lora_A.default.weight", (r, F))
+                add(lora_module_name(i, "fc2") + ".lora_B.default.weight", (d, r))
+        self.lora_end = off
+        add("model.encoder.conv1.0.weight", (d, dims.eeg_ch, 3)); add("model.encoder.conv1.0.bias", (d,))
+        add("model.encoder.conv1.2.weight", (d, d, 3)); add("model.encoder.conv1.2.bias", (d,))
+        add("model.encoder.conv2.weight", (d, d, 3)); add("model.encoder.conv2.bias", (d,))
+        self.size = off
+        if with_lora:
+            assert (r * d) % 64 == 0, "stacked q/k/v views need unpadded entries"
+
+    def view(self, flat: torch.Tensor, name: str) -> torch.Tensor:
+        off, shape = self.entries[name]
+        return flat[off: off + int(math.prod(shape))].view(shape)
+
+
+class Workspace:
+    """Named, lazily allocated, reused HBM buffers."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs: Dict[str, torch.Tensor] = {}
+
+    def get(self, name: str, shape, dtype, zero: bool = False) -> torch.Tensor:
+        shape = tuple(int(s) for s in shape)
+        t = self.bufs.get(name)
+        if t is None or t.shape != shape or t.dtype != dtype:
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
+            self.bufs[name] = t
+        return t
+
+    def bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.bufs.values())
+
+
+class WhisperEEGEngine:
+    def __init__(self, dims: ModelDims, params: Dict[str, torch.Tensor], lora: Optional[Dict[str, torch.Tensor]] = None,
+                 dtype: torch.dtype = torch.bfloat16, device="cuda"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("neuspeech1_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        ops.lib()
+        self.dims = dims
+        self.dtype = dtype
+        self.ns = ops.ns_dtype(dtype)
+        self.device = torch.device(device)
+        self.ws = Workspace(self.device)
+        self.has_lora = lora is not None
+        self.layout = TrainableLayout(dims, with_lora=self.has_lora)
+        self.flat = torch.zeros(self.layout.size, dtype=torch.float32, device=self.device)
+        self.grad = torch.zeros_like(self.flat)
+        self.adam_m = torch.zeros_like(self.flat)
+        self.adam_v = torch.zeros_like(self.flat)
+        self.opt_step = 0
+        self.sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.P: Dict[str, torch.Tensor] = {}
+        self.load_params(params, lora)
+
+    # ------------------------------------------------------------------ parameters
+    def _c(self, t: torch.Tensor) -> torch.Tensor:
+        """fp32 device tensor -> compute-dtype copy (one ns_cast launch)."""
+        t = t.contiguous()
+        if self.dtype == torch.float32:
+            return t.clone()
+        out = torch.empty(t.shape, dtype=self.dtype, device=self.device)
+        return ops.cast(t, out)
+
+    def _ct(self, t: torch.Tensor, scale: float = 1.0, pad_to: Optional[int] = None) -> torch.Tensor:
+        """fp32 (rows, cols) -> compute-dtype transposed copy (cols, rows[, padded])."""
+        t = t.contiguous()
+        rows, cols = t.shape
+        out = torch.empty((cols, pad_to or rows), dtype=self.dtype, device=self.device)
+        return ops.transpose(t, out, scale)
+
+    def load_params(self, params: Dict[str, torch.Tensor], lora: Optional[Dict[str, torch.Tensor]] = None):
+        """(Re)load weights.  `params`: HF-named fp32 tensors (see oracle.init_params / state_dict of the HF model)."""
+        dm = self.dims
+        d = dm.d_model
+        dev = self.device
+        f32 = lambda k: params[k].detach().to(dev, torch.float32).contiguous()
+        W: Dict[str, torch.Tensor] = {}
+        for name in self.layout.entries:
+            src = lora if (lora is not None and name in lora) else params
+            self.layout.view(self.flat, name).copy_(src[name].detach().to(dev, torch.float32))
+        W["enc_pos"] = self._c(f32("model.encoder.embed_positions.weight"))
+        eh_scale = (d // dm.enc_heads) ** -0.5
+        dh_scale = (d // dm.dec_heads) ** -0.5
+        zeros_d = torch.zeros(d, dtype=torch.float32, device=dev)
+
+        def ln(pre, key):
+            W[key + ".g"] = f32(pre + ".weight"); W[key + ".b"] = f32(pre + ".bias")
+
+        def qscaled_t(wq, wk, wv, scale):
+            """transposed [q;k;v] weight with the q rows pre-multiplied by `scale` (backward through q * Dh^-0.5)."""
+            return self._ct(torch.cat([wq * scale, wk, wv], dim=0))
+
+        for i in range(dm.enc_layers):
+            pre = f"model.encoder.layers.{i}"
+            k = f"enc{i}"
+            wq, wk, wv = (f32(f"{pre}.self_attn.{n}.weight") for n in ("q_proj", "k_proj", "v_proj"))
+            W[k + ".wqkv"] = self._c(torch.cat([wq, wk, wv], dim=0))
+            W[k + ".bqkv"] = torch.cat([f32(f"{pre}.self_attn.q_proj.bias"), zeros_d, f32(f"{pre}.self_attn.v_proj.bias")])
+            W[k + ".wqkv_t"] = qscaled_t(wq, wk, wv, eh_scale)
+            wo = f32(f"{pre}.self_attn.out_proj.weight")
+            W[k + ".wo"] = self._c(wo); W[k + ".wo_t"] = self._ct(wo); W[k + ".bo"] = f32(f"{pre}.self_attn.out_proj.bias")
+            w1 = f32(f"{pre}.fc1.weight"); w2 = f32(f"{pre}.fc2.weight")
+            W[k + ".w1"] = self._c(w1); W[k + ".w1_t"] = self._ct(w1); W[k + ".b1"] = f32(f"{pre}.fc1.bias")
+            W[k + ".w2"] = self._c(w2); W[k + ".w2_t"] = self._ct(w2); W[k + ".b2"] = f32(f"{pre}.fc2.bias")
+            ln(pre + ".self_attn_layer_norm", k + ".ln1"); ln(pre + ".final_layer_norm", k + ".ln2")
+        ln("model.encoder.layer_norm", "enc.lnf")
+
+        E = f32("model.decoder.embed_tokens.weight")
+        W["dec.E"] = self._c(E)
+        W["dec.E_t"] = self._ct(E, pad_to=dm.Vp)                        # (d, Vp) for dy = dlogits @ E
+        W["dec.pos"] = self._c(f32("model.decoder.embed_positions.weight"))
+        kv_w, kv_b = [], []
+        for i in range(dm.dec_layers):
+            pre = f"model.decoder.layers.{i}"
+            k = f"dec{i}"
+            wq, wk, wv = (f32(f"{pre}.self_attn.{n}.weight") for n in ("q_proj", "k_proj", "v_proj"))
+            W[k + ".wqkv"] = self._c(torch.cat([wq, wk, wv], dim=0))
+            W[k + ".bqkv"] = torch.cat([f32(f"{pre}.self_attn.q_proj.bias"), zeros_d, f32(f"{pre}.self_attn.v_proj.bias")])
+            W[k + ".wqkv_t"] = qscaled_t(wq, wk, wv, dh_scale)
+            wo = f32(f"{pre}.self_attn.out_proj.weight")
+            W[k + ".wo"] = self._c(wo); W[k + ".wo_t"] = self._ct(wo); W[k + ".bo"] = f32(f"{pre}.self_attn.out_proj.bias")
+            wqc = f32(f"{pre}.encoder_attn.q_proj.weight")
+            W[k + ".wqc"] = self._c(wqc); W[k + ".wqc_t"] = self._ct(wqc, scale=dh_scale)
+            W[k + ".bqc"] = f32(f"{pre}.encoder_attn.q_proj.bias")
+            kv_w += [f32(f"{pre}.encoder_attn.k_proj.weight"), f32(f"{pre}.encoder_attn.v_proj.weight")]
+            kv_b += [zeros_d, f32(f"{pre}.encoder_attn.v_proj.bias")]
+            woc = f32(f"{pre}.encoder_attn.out_proj.weight")
+            W[k + ".woc"] = self._c(woc); W[k + ".woc_t"] = self._ct(woc); W[k + ".boc"] = f32(f"{pre}.encoder_attn.out_proj.bias")
+            w1 = f32(f"{pre}.fc1.weight"); w2 = f32(f"{pre}.fc2.weight")
+            W[k + ".w1"] = self._c(w1); W[k + ".w1_t"] = self._ct(w1); W[k + ".b1"] = f32(f"{pre}.fc1.bias")
+            W[k + ".w2"] = self._c(w2); W[k + ".w2_t"] = self._ct(w2); W[k + ".b2"] = f32(f"{pre}.fc2.bias")
+            ln(pre + ".self_attn_layer_norm", k + ".ln1"); ln(pre + ".encoder_attn_layer_norm", k + ".ln2")
+            ln(pre + ".final_layer_norm", k + ".ln3")
+        ln("model.decoder.layer_norm", "dec.lnf")
+        wkv = torch.cat(kv_w, dim=0)                                     # (Nd*2d, d): [k0; v0; k1; v1; ...]
+        W["dec.wkv"] = self._c(wkv); W["dec.wkv_t"] = self._ct(wkv); W["dec.bkv"] = torch.cat(kv_b)
+        self.P = W
+        self.suppress = torch.tensor(list(dm.begin_suppress_tokens), dtype=torch.int32, device=dev)
+        self._packed = False
+
+    def trainable(self, name: str) -> torch.Tensor:
+        return self.layout.view(self.flat, name)
+
+    def trainable_grad(self, name: str) -> torch.Tensor:
+        return self.layout.view(self.grad, name)
+
+    def pack_trainable(self):
+        """Refresh the compute-dtype copies of the trainable weights (LoRA A/B + transposes, stem tap layouts)."""
+        dm, lay, W = self.dims, self.layout, self.P
+        d, r, F = dm.d_model, dm.lora_r, dm.enc_ffn
+        if self.has_lora:
+            nl = lay.lora_end - lay.lora_begin
+            if self.dtype == torch.float32:
+                lc = self.flat[lay.lora_begin: lay.lora_end]
+            else:
+                lc = ops.cast(self.flat[lay.lora_begin: lay.lora_end], self.ws.get("lora_c", (nl,), self.dtype))
+
+            def cv(name):
+                off, shape = lay.entries[name]
+                return lc[off - lay.lora_begin: off - lay.lora_begin + int(math.prod(shape))].view(shape)
+
+            for i in range(dm.enc_layers):
+                k = f"enc{i}"
+                aq = cv(lora_module_name(i, "q_proj") + ".lora_A.default.weight")
+                bq = cv(lora_module_name(i, "q_proj") + ".lora_B.default.weight")
+                off_a = lay.entries[lora_module_name(i, "q_proj") + ".lora_A.default.weight"][0] - lay.lora_begin
+                off_b = lay.entries[lora_module_name(i, "q_proj") + ".lora_B.default.weight"][0] - lay.lora_begin
+                W[k + ".A_qkv"] = lc[off_a: off_a + 3 * r * d].view(3 * r, d)        # stacked [Aq;Ak;Av]
+                W[k + ".B_qkv"] = lc[off_b: off_b + 3 * d * r].view(3 * d, r)        # stacked [Bq;Bk;Bv]
+                W[k + ".A_qkv_t"] = ops.transpose(W[k + ".A_qkv"], self.ws.get(k + ".A_qkv_t", (d, 3 * r), self.dtype))
+                for g in range(3):
+                    W[k + f".B_qkv_t{g}"] = ops.transpose(W[k + ".B_qkv"][g * d:(g + 1) * d],
+                                                           self.ws.get(k + f".B_qkv_t{g}", (r, d), self.dtype))
+                for t, fin, fout in (("out_proj", d, d), ("fc1", d, F), ("fc2", F, d)):
+                    a = cv(lora_module_name(i, t) + ".lora_A.default.weight")
+                    b = cv(lora_module_name(i, t) + ".lora_B.default.weight")
+                    W[f"{k}.A_{t}"] = a; W[f"{k}.B_{t}"] = b
+                    W[f"{k}.A_{t}_t"] = ops.transpose(a, self.ws.get(f"{k}.A_{t}_t", (fin, r), self.dtype))
+                    W[f"{k}.B_{t}_t"] = ops.transpose(b, self.ws.get(f"{k}.B_{t}_t", (r, fout), self.dtype))
+        Cp = dm.Cp
+        for key, name, cin, cp in (("stemA", "model.encoder.conv1.0", dm.eeg_ch, Cp), ("stemB", "model.encoder.conv1.2", d, d),
+                                   ("stemC", "model.encoder.conv2", d, d)):
+            w = self.trainable(name + ".weight")
+            wt = self.ws.get(key + ".w", (3, d, cp), self.dtype)
+            wtt = self.ws.get(key + ".wt", (3, cp, d), self.dtype)
+            ops.conv_weight_pack(w, wt, wtt)
+            W[key + ".w"] = wt; W[key + ".wt"] = wtt; W[key + ".b"] = self.trainable(name + ".bias")
+        self._packed = True
+
+    # ------------------------------------------------------------------ encoder forward
+    def _ep(self, **kw):
+        kw.setdefault("out_dtype", self.ns)
+        return ops.epilogue(**kw)
+
+    def input_to_channels_last(self, x: torch.Tensor, aug: Optional[dict] = None) -> torch.Tensor:
+        """(B,C,T) fp32 -> (B,T,Cp) compute dtype through the augmentation/pad/cast pass (identity when aug is None)."""
+        dm = self.dims
+        B = x.shape[0]
+        if x.shape[1] != dm.eeg_ch:
+            raise ValueError(f"expected {dm.eeg_ch} EEG channels, got {x.shape[1]}")
+        y = self.ws.get("x_cl", (B, dm.T, dm.Cp), self.dtype)
+        x = x.to(self.device, torch.float32).contiguous()
+        ops.aug_pass(x, y, layout=1, **(aug or {}))
+        return y
+
+    def encode(self, x: torch.Tensor, aug: Optional[dict] = None, save: bool = False) -> torch.Tensor:
+        """input_features (B, eeg_ch, T) -> encoder_last_hidden_state (B, S, d).  utils/load_model.py:371-476."""
+        dm, W, ws, dt = self.dims, self.P, self.ws, self.dtype
+        if x.shape[-1] != dm.T and (aug is None or "n" not in aug):
+            raise ValueError(f"Whisper expects the input features to be of length {dm.T}, but found {x.shape[-1]}")  # HF:613
+        if not self._packed:
+            self.pack_trainable()
+        B = x.shape[0]
+        d, S, T, F, r, H = dm.d_model, dm.max_source_positions, dm.T, dm.enc_ffn, dm.lora_r, dm.enc_heads
+        M = B * S
+        s = dm.lora_scale
+        xcl = self.input_to_channels_last(x, aug)
+        zA = ws.get("zA", (B, T, d), dt); aA = ws.get("aA", (B, T, d), dt)
+        ops.conv3_fwd(xcl, W["stemA.w"], aA, 1, self._ep(bias=W["stemA.b"], act=ACT_GELU, aux_out=zA if save else None, ldaux=d))
+        zB = ws.get("zB", (B, T // 2, d), dt); aB = ws.get("aB", (B, T // 2, d), dt)
+        ops.conv3_fwd(aA, W["stemB.w"], aB, 2, self._ep(bias=W["stemB.b"], act=ACT_GELU, aux_out=zB if save else None, ldaux=d))
+        zC = ws.get("zC", (B, S, d), dt)
+        h = ws.get("h0", (M, d), dt)
+        ops.conv3_fwd(aB, W["stemC.w"], h.view(B, S, d), 2,
+                      self._ep(bias=W["stemC.b"], act=ACT_GELU, aux_out=zC if save else None, ldaux=d, residual=W["enc_pos"], ldr=d, res_mod=S))
+        Dh = d // H
+        shp = ops.attn_shape(B, H, S, S, Dh, False, S * 3 * d, 3 * d, S * 3 * d, 3 * d, S * 3 * d, 3 * d, S * d, d)
+        for i in range(dm.enc_layers):
+            k = f"enc{i}"
+            sfx = f".{i}" if save else ""        # per-layer buffers only when the backward needs them
+            u1 = ws.get("u1" + sfx, (M, d), dt)
+            mean1 = ws.get("mean1" + sfx, (M,), torch.float32); rstd1 = ws.get("rstd1" + sfx, (M,), torch.float32)
+            ops.layernorm_fwd(h, W[k + ".ln1.g"], W[k + ".ln1.b"], u1, mean1, rstd1)
+            qkv = ws.get("qkv" + sfx, (M, 3 * d), dt)
+            if self.has_lora:
+                t_qkv = ws.get("t_qkv" + sfx, (M, 3 * r), dt)
+                ops.gemm_nt(u1, W[k + ".A_qkv"], t_qkv, self._ep(alpha=s, alpha_cols=3 * r))
+                ops.gemm_nt(u1, W[k + ".wqkv"], qkv, self._ep(bias=W[k + ".bqkv"], alpha=Dh ** -0.5, alpha_cols=d, a2_group_cols=d),
+                            a2=t_qkv, w2=W[k + ".B_qkv"], k2=r)
+            else:
+                ops.gemm_nt(u1, W[k + ".wqkv"], qkv, self._ep(bias=W[k + ".bqkv"], alpha=Dh ** -0.5, alpha_cols=d))
+            o = ws.get("o" + sfx, (M, d), dt)
+            lse = ws.get("lse" + sfx, (B, H, S), torch.float32)
+            ops.attention_fwd(shp, qkv, qkv[:, d:], qkv[:, 2 * d:], o, lse)
+            hm = ws.get("hm" + sfx, (M, d), dt)
+            if self.has_lora:
+                t_o = ws.get("t_o" + sfx, (M, r), dt)
+                ops.gemm_nt(o, W[k + ".A_out_proj"], t_o, self._ep(alpha=s, alpha_cols=r))
+                ops.gemm_nt(o, W[k + ".wo"], hm, self._ep(bias=W[k + ".bo"], residual=h, ldr=d), a2=t_o, w2=W[k + ".B_out_proj"], k2=r)
+            else:
+                ops.gemm_nt(o, W[k + ".wo"], hm, self._ep(bias=W[k + ".bo"], residual=h, ldr=d))
+            u2 = ws.get("u2" + sfx, (M, d), dt)
+            mean2 = ws.get("mean2" + sfx, (M,), torch.float32); rstd2 = ws.get("rstd2" + sfx, (M,), torch.float32)
+            ops.layernorm_fwd(hm, W[k + ".ln2.g"], W[k + ".ln2.b"], u2, mean2, rstd2)
+            z1 = ws.get("z1" + sfx, (M, F), dt) if save else None
+            m = ws.get("m" + sfx, (M, F), dt)
+            if self.has_lora:
+                t_1 = ws.get("t_1" + sfx, (M, r), dt)
+                ops.gemm_nt(u2, W[k + ".A_fc1"], t_1, self._ep(alpha=s, alpha_cols=r))
+                ops.gemm_nt(u2, W[k + ".w1"], m, self._ep(bias=W[k + ".b1"], act=ACT_GELU, aux_out=z1, ldaux=F), a2=t_1, w2=W[k + ".B_fc1"], k2=r)
+            else:
+                ops.gemm_nt(u2, W[k + ".w1"], m, self._ep(bias=W[k + ".b1"], act=ACT_GELU, aux_out=z1, ldaux=F))
+            hn = ws.get(f"h{i + 1}" if save else f"h{(i + 1) % 2 + 1}", (M, d), dt)
+            if self.has_lora:
+                t_2 = ws.get("t_2" + sfx, (M, r), dt)
+                ops.gemm_nt(m, W[k + ".A_fc2"], t_2, self._ep(alpha=s, alpha_cols=r))
+                ops.gemm_nt(m, W[k + ".w2"], hn, self._ep(bias=W[k + ".b2"], residual=hm, ldr=d), a2=t_2, w2=W[k + ".B_fc2"], k2=r)
+            else:
+                ops.gemm_nt(m, W[k + ".w2"], hn, self._ep(bias=W[k + ".b2"], residual=hm, ldr=d))
+            if save:
+                self._saved_h = getattr(self, "_saved_h", {})
+                self._saved_h[i] = h
+            h = hn
+        enc = ws.get("enc", (M, d), dt)
+        meanf = ws.get("meanf", (M,), torch.float32); rstdf = ws.get("rstdf", (M,), torch.float32)
+        ops.layernorm_fwd(h, W["enc.lnf.g"], W["enc.lnf.b"], enc, meanf, rstdf)
+        self._h_last = h
+        self._B = B
+        return enc.view(B, S, d)
+
+    # ------------------------------------------------------------------ decoder (teacher forced) + loss
+    @staticmethod
+    def shift_tokens_right(labels: torch.Tensor, pad: int, start: int) -> torch.Tensor:
+        out = torch.empty_like(labels)
+        out[:, 1:] = labels[:, :-1]
+        out[:, 0] = start
+        return out.masked_fill_(out == -100, pad)
+
+    def _decoder_layers_fwd(self, hd: torch.Tensor, B: int, L: int, kv_all: torch.Tensor, save: bool):
+        dm, W, ws, dt = self.dims, self.P, self.ws, self.dtype
+        d, S, F, H = dm.d_model, dm.max_source_positions, dm.dec_ffn, dm.dec_heads
+        Dh = d // H
+        ML = B * L
+        nkv = dm.dec_layers * 2 * d
+        shp_s = ops.attn_shape(B, H, L, L, Dh, True, L * 3 * d, 3 * d, L * 3 * d, 3 * d, L * 3 * d, 3 * d, L * d, d)
+        shp_c = ops.attn_shape(B, H, L, S, Dh, False, L * d, d, S * nkv, nkv, S * nkv, nkv, L * d, d)
+        for i in range(dm.dec_layers):
+            k = f"dec{i}"
+            sfx = f".{i}" if save else ""
+            u = ws.get("d_u", (ML, d), dt)
+            m1 = ws.get("d_mean1" + sfx, (ML,), torch.float32); r1 = ws.get("d_rstd1" + sfx, (ML,), torch.float32)
+            ops.layernorm_fwd(hd, W[k + ".ln1.g"], W[k + ".ln1.b"], u, m1, r1)
+            qkv = ws.get("d_qkv" + sfx, (ML, 3 * d), dt)
+            ops.gemm_nt(u, W[k + ".wqkv"], qkv, self._ep(bias=W[k + ".bqkv"], alpha=Dh ** -0.5, alpha_cols=d))
+            o = ws.get("d_o" + sfx, (ML, d), dt); lse = ws.get("d_lse" + sfx, (B, H, L), torch.float32)
+            ops.attention_fwd(shp_s, qkv, qkv[:, d:], qkv[:, 2 * d:], o, lse)
+            h1 = ws.get("d_h1" + sfx, (ML, d), dt)
+            ops.gemm_nt(o, W[k + ".wo"], h1, self._ep(bias=W[k + ".bo"], residual=hd, ldr=d))
+            m2 = ws.get("d_mean2" + sfx, (ML,), torch.float32); r2 = ws.get("d_rstd2" + sfx, (ML,), torch.float32)
+            ops.layernorm_fwd(h1, W[k + ".ln2.g"], W[k + ".ln2.b"], u, m2, r2)
+            qc = ws.get("d_qc" + sfx, (ML, d), dt)
+            ops.gemm_nt(u, W[k + ".wqc"], qc, self._ep(bias=W[k + ".bqc"], alpha=Dh ** -0.5, alpha_cols=d))
+            oc = ws.get("d_oc" + sfx, (ML, d), dt); lsec = ws.get("d_lsec" + sfx, (B, H, L), torch.float32)
+            ops.attention_fwd(shp_c, qc, kv_all[:, i * 2 * d:], kv_all[:, i * 2 * d + d:], oc, lsec)
+            h2 = ws.get("d_h2" + sfx, (ML, d), dt)
+            ops.gemm_nt(oc, W[k + ".woc"], h2, self._ep(bias=W[k + ".boc"], residual=h1, ldr=d))
+            m3 = ws.get("d_mean3" + sfx, (ML,), torch.float32); r3 = ws.get("d_rstd3" + sfx, (ML,), torch.float32)
+            ops.layernorm_fwd(h2, W[k + ".ln3.g"], W[k + ".ln3.b"], u, m3, r3)
+            z = ws.get("d_z" + sfx, (ML, F), dt) if save else None
+            mm = ws.get("d_m", (ML, F), dt)
+            ops.gemm_nt(u, W[k + ".w1"], mm, self._ep(bias=W[k + ".b1"], act=ACT_GELU, aux_out=z, ldaux=F))
+            h3 = ws.get(f"d_h{i + 1}" if save else f"d_h{(i + 1) % 2 + 1}x", (ML, d), dt)
+            ops.gemm_nt(mm, W[k + ".w2"], h3, self._ep(bias=W[k + ".b2"], residual=h2, ldr=d))
+            if save:
+                self._saved_hd = getattr(self, "_saved_hd", {})
+                self._saved_hd[i] = hd
+            hd = h3
+        return hd
+
+    def forward_loss(self, x: torch.Tensor, labels: Optional[torch.Tensor] = None, decoder_input_ids: Optional[torch.Tensor] = None,
+                     aug: Optional[dict] = None, save: bool = True, logits_dtype: Optional[torch.dtype] = None):
+        """model(input_features, labels) -> (loss (0-d fp32 tensor or None), logits (B,L,V) view, enc (B,S,d)).
+        utils/load_model.py:976-1070."""
+        dm, W, ws, dt = self.dims, self.P, self.ws, self.dtype
+        d, S = dm.d_model, dm.max_source_positions
+        if decoder_input_ids is not None and labels is not None:
+            pass  # HF allows both; labels only drive the loss then
+        enc = self.encode(x, aug=aug, save=save)
+        B = x.shape[0]
+        if decoder_input_ids is None:
+            if labels is None:
+                raise ValueError("You have to specify either decoder_input_ids or labels")
+            decoder_input_ids = self.shift_tokens_right(labels.to(self.device), dm.pad_token_id, dm.decoder_start_token_id)
+        ids = decoder_input_ids.to(self.device, torch.long).contiguous()
+        L = ids.shape[1]
+        ML = B * L
+        nkv = dm.dec_layers * 2 * d
+        kv_all = ws.get("kv_all", (B * S, nkv), dt)
+        ops.gemm_nt(enc.view(B * S, d), W["dec.wkv"], kv_all, self._ep(bias=W["dec.bkv"]))
+        hd = ws.get("d_h0", (ML, d), dt)
+        ops.embed(ids, W["dec.E"], W["dec.pos"], 0, hd)
+        hd = self._decoder_layers_fwd(hd, B, L, kv_all, save)
+        y = ws.get("d_y", (ML, d), dt)
+        mf = ws.get("d_meanf", (ML,), torch.float32); rf = ws.get("d_rstdf", (ML,), torch.float32)
+        ops.layernorm_fwd(hd, W["dec.lnf.g"], W["dec.lnf.b"], y, mf, rf)
+        self._hd_last = hd
+        ldt = logits_dtype or dt
+        logits = ws.get("logits", (ML, dm.Vp), ldt)
+        ops.gemm_nt(y, W["dec.E"], logits, self._ep(out_dtype=ops.ns_dtype(ldt)), N=dm.vocab)
+        loss = None
+        self._L = L
+        if labels is not None:
+            lab = labels.to(self.device, torch.long).contiguous().view(-1)
+            self._labels = lab
+            row_loss = ws.get("row_loss", (ML,), torch.float32)
+            loss_sum = ws.get("loss_sum", (1,), torch.float32)
+            n_valid = ws.get("n_valid", (1,), torch.int32)
+            ops.cross_entropy(logits, dm.vocab, lab, row_loss, loss_sum, n_valid, write_grad=False)
+            loss = (loss_sum / n_valid.to(torch.float32).clamp_min(1.0)).squeeze(0)
+        return loss, logits.view(B, L, dm.Vp)[:, :, :dm.vocab], enc
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, grad_scale: float = 1.0):
+        """Gradients of the mean token cross-entropy w.r.t. the trainable set into self.grad (flat fp32).
+        Must follow forward_loss(..., labels=..., save=True).  Mirrors autograd through utils/load_model.py:976-1070 with
+        every non-LoRA / non-stem weight frozen (finetune.py:176-177)."""
+        dm, W, ws, dt = self.dims, self.P, self.ws, self.dtype
+        d, S, T, F, r, H = dm.d_model, dm.max_source_positions, dm.T, dm.enc_ffn, dm.lora_r, dm.enc_heads
+        B, L = self._B, self._L
+        M, ML = B * S, B * L
+        s = dm.lora_scale
+        self.grad.zero_()
+        # ---- loss -> logits (in place) -> decoder output
+        logits = ws.bufs["logits"]
+        ops.cross_entropy(logits, dm.vocab, self._labels, ws.bufs["row_loss"], None, ws.bufs["n_valid"], write_grad=True, grad_scale=grad_scale)
+        if logits.dtype != dt:
+            dl = ops.cast(logits, ws.get("dlogits_c", logits.shape, dt))
+        else:
+            dl = logits
+        dy = ws.get("d_dy", (ML, d), dt)
+        ops.gemm_nt(dl, W["dec.E_t"], dy, self._ep())
+        dh = ws.get("d_dh_a", (ML, d), dt)
+        ops.layernorm_bwd(dy, self._hd_last, W["dec.lnf.g"], ws.bufs["d_meanf"], ws.bufs["d_rstdf"], dh)
+        # ---- decoder layers (frozen: input gradients only)
+        Hd = dm.dec_heads
+        Dhd = d // Hd
+        nkv = dm.dec_layers * 2 * d
+        kv_all = ws.bufs["kv_all"]
+        dkv_all = ws.get("dkv_all", (M, nkv), dt)
+        delta = ws.get("delta", (B * max(H, Hd) * max(S, L),), torch.float32)
+        shp_s = ops.attn_shape(B, Hd, L, L, Dhd, True, L * 3 * d, 3 * d, L * 3 * d, 3 * d, L * 3 * d, 3 * d, L * d, d)
+        shp_c = ops.attn_shape(B, Hd, L, S, Dhd, False, L * d, d, S * nkv, nkv, S * nkv, nkv, L * d, d)
+        Fd = dm.dec_ffn
+        for i in reversed(range(dm.dec_layers)):
+            k = f"dec{i}"
+            sfx = f".{i}"
+            g = lambda n: ws.bufs[n + sfx]
+            dm_ = ws.get("d_dm", (ML, Fd), dt)
+            ops.gemm_nt(dh, W[k + ".w2_t"], dm_, self._ep(act=ACT_DGELU, aux_in=g("d_z"), ldaux=Fd))
+            du = ws.get("d_du", (ML, d), dt)
+            ops.gemm_nt(dm_, W[k + ".w1_t"], du, self._ep())
+            dh2 = ws.get("d_dh_b", (ML, d), dt)
+            ops.layernorm_bwd(du, g("d_h2"), W[k + ".ln3.g"], g("d_mean3"), g("d_rstd3"), dh2, dres=dh)
+            doc = ws.get("d_doc", (ML, d), dt)
+            ops.gemm_nt(dh2, W[k + ".woc_t"], doc, self._ep())
+            dqc = ws.get("d_dqc", (ML, d), dt)
+            ops.attention_bwd(shp_c, g("d_qc"), kv_all[:, i * 2 * d:], kv_all[:, i * 2 * d + d:], g("d_oc"), doc, g("d_lsec"), delta,
+                              dqc, dkv_all[:, i * 2 * d:], dkv_all[:, i * 2 * d + d:])
+            ops.gemm_nt(dqc, W[k + ".wqc_t"], du, self._ep())
+            dh1 = ws.get("d_dh_c", (ML, d), dt)
+            ops.layernorm_bwd(du, g("d_h1"), W[k + ".ln2.g"], g("d_mean2"), g("d_rstd2"), dh1, dres=dh2)
+            dos = ws.get("d_dos", (ML, d), dt)
+            ops.gemm_nt(dh1, W[k + ".wo_t"], dos, self._ep())
+            dqkv = ws.get("d_dqkv", (ML, 3 * d), dt)
+            qkv = g("d_qkv")
+            ops.attention_bwd(shp_s, qkv, qkv[:, d:], qkv[:, 2 * d:], g("d_o"), dos, g("d_lse"), delta,
+                              dqkv, dqkv[:, d:], dqkv[:, 2 * d:])
+            ops.gemm_nt(dqkv, W[k + ".wqkv_t"], du, self._ep())
+            ops.layernorm_bwd(du, self._saved_hd[i], W[k + ".ln1.g"], g("d_mean1"), g("d_rstd1"), dh, dres=dh1)
+        # ---- cross K/V projections of all layers back to the encoder output
+        denc = ws.get("denc", (M, d), dt)
+        ops.gemm_nt(dkv_all, W["dec.wkv_t"], denc, self._ep())
+        dh = ws.get("dh_a", (M, d), dt)
+        ops.layernorm_bwd(denc, self._h_last, W["enc.lnf.g"], ws.bufs["meanf"], ws.bufs["rstdf"], dh)
+        # ---- encoder layers
+        Dh = d // H
+        qs = Dh ** -0.5
+        shp = ops.attn_shape(B, H, S, S, Dh, False, S * 3 * d, 3 * d, S * 3 * d, 3 * d, S * 3 * d, 3 * d, S * d, d)
+        lay = self.layout
+        for i in reversed(range(dm.enc_layers)):
+            k = f"enc{i}"
+            sfx = f".{i}"
+            g = lambda n: ws.bufs[n + sfx]
+            G = lambda t, ab: self.trainable_grad(lora_module_name(i, t) + f".lora_{ab}.default.weight")
+            # fc2
+            dz1 = ws.get("dz1", (M, F), dt)
+            if self.has_lora:
+                dt2 = ws.get("dt_r", (M, r), dt)
+                ops.gemm_nt(dh, W[k + ".B_fc2_t"], dt2, self._ep(alpha=s, alpha_cols=r))
+                ops.gemm_tn(dh, g("t_2"), G("fc2", "B"), r, 1)
+                ops.gemm_tn(g("m"), dt2, G("fc2", "A"), 1, F)
+                ops.gemm_nt(dh, W[k + ".w2_t"], dz1, self._ep(act=ACT_DGELU, aux_in=g("z1"), ldaux=F), a2=dt2, w2=W[k + ".A_fc2_t"], k2=r)
+            else:
+                ops.gemm_nt(dh, W[k + ".w2_t"], dz1, self._ep(act=ACT_DGELU, aux_in=g("z1"), ldaux=F))
+            # fc1
+            du2 = ws.get("du", (M, d), dt)
+            if self.has_lora:
+                dt1 = ws.get("dt_r", (M, r), dt)
+                ops.gemm_nt(dz1, W[k + ".B_fc1_t"], dt1, self._ep(alpha=s, alpha_cols=r))
+                ops.gemm_tn(dz1, g("t_1"), G("fc1", "B"), r, 1)
+                ops.gemm_tn(g("u2"), dt1, G("fc1", "A"), 1, d)
+                ops.gemm_nt(dz1, W[k + ".w1_t"], du2, self._ep(), a2=dt1, w2=W[k + ".A_fc1_t"], k2=r)
+            else:
+                ops.gemm_nt(dz1, W[k + ".w1_t"], du2, self._ep())
+            dhm = ws.get("dh_b", (M, d), dt)
+            ops.layernorm_bwd(du2, g("hm"), W[k + ".ln2.g"], g("mean2"), g("rstd2"), dhm, dres=dh)
+            # out_proj
+            do = ws.get("do", (M, d), dt)
+            if self.has_lora:
+                dto = ws.get("dt_r", (M, r), dt)
+                ops.gemm_nt(dhm, W[k + ".B_out_proj_t"], dto, self._ep(alpha=s, alpha_cols=r))
+                ops.gemm_tn(dhm, g("t_o"), G("out_proj", "B"), r, 1)
+                ops.gemm_tn(g("o"), dto, G("out_proj", "A"), 1, d)
+                ops.gemm_nt(dhm, W[k + ".wo_t"], do, self._ep(), a2=dto, w2=W[k + ".A_out_proj_t"], k2=r)
+            else:
+                ops.gemm_nt(dhm, W[k + ".wo_t"], do, self._ep())
+            # attention
+            dqkv = ws.get("dqkv", (M, 3 * d), dt)
+            qkv = g("qkv")
+            ops.attention_bwd(shp, qkv, qkv[:, d:], qkv[:, 2 * d:], g("o"), do, g("lse"), delta, dqkv, dqkv[:, d:], dqkv[:, 2 * d:])
+            # q/k/v projections (dq carries the Dh^-0.5 of the forward: folded into alpha / pre-scaled transposed weight)
+            du1 = du2
+            if self.has_lora:
+                dtq = ws.get("dt_qkv", (M, 3 * r), dt)
+                t_qkv = g("t_qkv")
+                for gi, tname in enumerate(("q_proj", "k_proj", "v_proj")):
+                    sc = qs if gi == 0 else 1.0
+                    ops.gemm_nt(dqkv[:, gi * d:(gi + 1) * d], W[k + f".B_qkv_t{gi}"], dtq[:, gi * r:(gi + 1) * r],
+                                self._ep(alpha=s * sc, alpha_cols=r))
+                    ops.gemm_tn(dqkv[:, gi * d:(gi + 1) * d], t_qkv[:, gi * r:(gi + 1) * r], G(tname, "B"), r, 1, alpha=sc)
+                # dA for q,k,v in one launch: the three (r,d) gradients are contiguous = one (3r, d) matrix
+                ops.gemm_tn(g("u1"), dtq, G("q_proj", "A"), 1, d)
+                ops.gemm_nt(dqkv, W[k + ".wqkv_t"], du1, self._ep(), a2=dtq, w2=W[k + ".A_qkv_t"], k2=3 * r)
+            else:
+                ops.gemm_nt(dqkv, W[k + ".wqkv_t"], du1, self._ep())
+            ops.layernorm_bwd(du1, self._saved_h[i], W[k + ".ln1.g"], g("mean1"), g("rstd1"), dh, dres=dhm)
+        # ---- stem (all three convs trainable; conv A's input needs no gradient)
+        Cp = dm.Cp
+        dzC = ws.get("dzC", (B, S, d), dt)
+        ops.dgelu_mul(dh, ws.bufs["zC"], dzC)
+        aA, aB, xcl = ws.bufs["aA"], ws.bufs["aB"], ws.bufs["x_cl"]
+        self._conv_wgrad("model.encoder.conv2", dzC, aB, 2, d, d)
+        dzB = ws.get("dzB", (B, T // 2, d), dt)
+        ops.conv3_dgrad(dzC, W["stemC.wt"], dzB, 2, self._ep(act=ACT_DGELU, aux_in=ws.bufs["zB"], ldaux=d))
+        self._conv_wgrad("model.encoder.conv1.2", dzB, aA, 2, d, d)
+        dzA = ws.get("dzA", (B, T, d), dt)
+        ops.conv3_dgrad(dzB, W["stemB.wt"], dzA, 2, self._ep(act=ACT_DGELU, aux_in=ws.bufs["zA"], ldaux=d))
+        self._conv_wgrad("model.encoder.conv1.0", dzA, xcl, 1, dm.eeg_ch, Cp)
+        return self.grad
+
+    def _conv_wgrad(self, name: str, dz: torch.Tensor, xin: torch.Tensor, stride: int, cin: int, cp: int):
+        d = self.dims.d_model
+        dwt = self.ws.get(f"dw_tap.{cp}", (3, d, cp), torch.float32)
+        dwt.zero_()
+        ops.conv3_wgrad(dz, xin, dwt, self.trainable_grad(name + ".bias"), stride)
+        ops.conv_weight_unpack_grad(dwt, self.trainable_grad(name + ".weight"))
+
+    # ------------------------------------------------------------------ optimizer
+    def optimizer_step(self, lr: float, max_grad_norm: float = 1.0, betas=(0.9, 0.999), eps: float = 1e-8,
+                       weight_decay: float = 0.0, grad_scale: float = 1.0):
+        """clip_grad_norm_(max_grad_norm) + AdamW over the flat buffer (HF trainer.py:2493,1760; finetune.py:236-247).
+        Returns the 0-d tensor holding sum(g^2) (pre-clip norm squared) without synchronising."""
+        self.sumsq.zero_()
+        ops.sumsq(self.grad, self.sumsq)
+        self.opt_step += 1
+        ops.adamw_clip(self.flat, self.grad, self.adam_m, self.adam_v, self.sumsq, grad_scale, max_grad_norm, lr, betas[0],
+                       betas[1], eps, weight_decay, self.opt_step)
+        self._packed = False
+        return self.sumsq
+
+    def train_step(self, x, labels, lr: float, aug: Optional[dict] = None, all_reduce=None):
+        """One Trainer.training_step + optimizer step.  `all_reduce(flat_grad)` is the data-parallel hook."""
+        self.pack_trainable()
+        loss, _, _ = self.forward_loss(x, labels, aug=aug, save=True)
+        self.backward()
+        if all_reduce is not None:
+            all_reduce(self.grad)
+        self.optimizer_step(lr)
+        return loss
+
+    # ------------------------------------------------------------------ greedy decode with KV cache
+    @torch.no_grad()
+    def greedy(self, x: torch.Tensor, max_length: int, prompt: Optional[torch.Tensor] = None, aug: Optional[dict] = None) -> torch.Tensor:
+        """Batched greedy generate (utils/load_model.py:1072-1351 -> GenerationMixin greedy): encoder once, cross-K/V once,
+        then one-token decoder steps against the self-attention cache.  Returns the generated suffix (B, n_new) int64;
+        rows that hit EOS emit pad afterwards; begin_suppress_tokens are masked at the first generated position."""
+        dm, W, ws, dt = self.dims, self.P, self.ws, self.dtype
+        d, S, F, H = dm.d_model, dm.max_source_positions, dm.dec_ffn, dm.dec_heads
+        Dh = d // H
+        B = x.shape[0]
+        enc = self.encode(x, aug=aug, save=False)
+        nkv = dm.dec_layers * 2 * d
+        kv_all = ws.get("kv_all", (B * S, nkv), dt)
+        ops.gemm_nt(enc.view(B * S, d), W["dec.wkv"], kv_all, self._ep(bias=W["dec.bkv"]))
+        if prompt is None:
+            prompt = torch.full((B, 1), dm.decoder_start_token_id, dtype=torch.long, device=self.device)
+        prompt = prompt.to(self.device, torch.long).contiguous()
+        L0 = prompt.shape[1]
+        Tmax = max_length
+        if Tmax > dm.max_target_positions:
+            raise ValueError(f"max_length {Tmax} exceeds max_target_positions {dm.max_target_positions}")
+        n_new = Tmax - L0
+        out = torch.empty((B, max(n_new, 0)), dtype=torch.long, device=self.device)
+        if n_new <= 0:
+            return out
+        cache = [ws.get(f"g_qkv.{i}", (B, Tmax, 3 * d), dt) for i in range(dm.dec_layers)]
+        finished = ws.get("g_fin", (B,), torch.uint8); finished.zero_()
+        nxt = ws.get("g_next", (B,), torch.long)
+        logits = ws.get("g_logits", (B, dm.Vp), torch.float32 if dt == torch.float32 else dt)
+        ids = prompt
+        pos = 0
+        for step in range(n_new):
+            Lq = ids.shape[1]
+            MLq = B * Lq
+            hd = ws.get(f"g_h0.{Lq}", (MLq, d), dt)
+            ops.embed(ids, W["dec.E"], W["dec.pos"], pos, hd)
+            for i in range(dm.dec_layers):
+                k = f"dec{i}"
+                u = ws.get(f"g_u.{Lq}", (MLq, d), dt)
+                ops.layernorm_fwd(hd, W[k + ".ln1.g"], W[k + ".ln1.b"], u)
+                qkv_new = cache[i][:, pos:pos + Lq]                     # rows (b, pos..pos+Lq) of the cache, written in place
+                if Lq == 1:
+                    ops.gemm_nt(u, W[k + ".wqkv"], qkv_new.view(B, 3 * d) if Tmax == 1 else qkv_new.squeeze(1),
+                                self._ep(bias=W[k + ".bqkv"], alpha=Dh ** -0.5, alpha_cols=d))
+                else:
+                    tmp = ws.get(f"g_qkvtmp.{Lq}", (MLq, 3 * d), dt)
+                    ops.gemm_nt(u, W[k + ".wqkv"], tmp, self._ep(bias=W[k + ".bqkv"], alpha=Dh ** -0.5, alpha_cols=d))
+                    qkv_new.copy_(tmp.view(B, Lq, 3 * d))
+                Lk = pos + Lq
+                shp_s = ops.attn_shape(B, H, Lq, Lk, Dh, True, Tmax * 3 * d, 3 * d, Tmax * 3 * d, 3 * d, Tmax * 3 * d, 3 * d, Lq * d, d)
+                o = ws.get(f"g_o.{Lq}", (MLq, d), dt)
+                c = cache[i]
+                ops.attention_fwd(shp_s, c[:, pos:], c[:, :, d:], c[:, :, 2 * d:], o)
+                h1 = ws.get(f"g_h1.{Lq}", (MLq, d), dt)
+                ops.gemm_nt(o, W[k + ".wo"], h1, self._ep(bias=W[k + ".bo"], residual=hd, ldr=d))
+                ops.layernorm_fwd(h1, W[k + ".ln2.g"], W[k + ".ln2.b"], u)
+                qc = ws.get(f"g_qc.{Lq}", (MLq, d), dt)
+                ops.gemm_nt(u, W[k + ".wqc"], qc, self._ep(bias=W[k + ".bqc"], alpha=Dh ** -0.5, alpha_cols=d))
+                shp_c = ops.attn_shape(B, H, Lq, S, Dh, False, Lq * d, d, S * nkv, nkv, S * nkv, nkv, Lq * d, d)
+                ops.attention_fwd(shp_c, qc, kv_all[:, i * 2 * d:], kv_all[:, i * 2 * d + d:], o)
+                h2 = ws.get(f"g_h2.{Lq}", (MLq, d), dt)
+                ops.gemm_nt(o, W[k + ".woc"], h2, self._ep(bias=W[k + ".boc"], residual=h1, ldr=d))
+                ops.layernorm_fwd(h2, W[k + ".ln3.g"], W[k + ".ln3.b"], u)
+                mm = ws.get(f"g_m.{Lq}", (MLq, F), dt)
+                ops.gemm_nt(u, W[k + ".w1"], mm, self._ep(bias=W[k + ".b1"], act=ACT_GELU))
+                hd2 = ws.get(f"g_h3.{Lq}.{i % 2}", (MLq, d), dt)
+                ops.gemm_nt(mm, W[k + ".w2"], hd2, self._ep(bias=W[k + ".b2"], residual=h2, ldr=d))
+                hd = hd2
+            y = ws.get(f"g_y.{Lq}", (MLq, d), dt)
+            ops.layernorm_fwd(hd, W["dec.lnf.g"], W["dec.lnf.b"], y)
+            y_last = y.view(B, Lq, d)[:, Lq - 1]                          # (B, d) view, row stride Lq*d
+            ops.gemm_nt(y_last, W["dec.E"], logits, self._ep(out_dtype=ops.ns_dtype(logits)), N=dm.vocab, M=B, K=d)
+            ops.greedy_pick(logits, dm.vocab, self.suppress if step == 0 else None, dm.eos_token_id, dm.pad_token_id, finished, nxt)
+            out[:, step].copy_(nxt)
+            pos += Lq
+            ids = nxt.view(B, 1)
+        return out

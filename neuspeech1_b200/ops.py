@@ -1,0 +1,197 @@
+"""Thin torch-tensor wrappers over the C-ABI (include/neuspeech_b200.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every computation below is one `ns_*` call into
+libneuspeech_b200.so on the current CUDA stream.  Tensors must live on a CUDA device; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _abi
+from ._abi import ACT_DGELU, ACT_GELU, ACT_NONE, AttnShape, AugArgs, Epilogue, NS_BF16, NS_F32, check
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = _abi.load()
+    return _lib
+
+
+def ns_dtype(t) -> int:
+    dt = t if isinstance(t, torch.dtype) else t.dtype
+    if dt == torch.float32:
+        return NS_F32
+    if dt == torch.bfloat16:
+        return NS_BF16
+    raise TypeError(f"neuspeech1_b200 supports float32 and bfloat16 storage, got {dt}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _abi.NeuSpeechB200Error("neuspeech1_b200 ops need CUDA tensors (no CPU fallback)")
+    return t.data_ptr()
+
+
+def epilogue(bias=None, alpha=1.0, alpha_cols=0, act=ACT_NONE, aux_in=None, aux_out=None, ldaux=0, residual=None, ldr=0,
+             res_mod=0, out_dtype=NS_BF16, a2_group_cols=0) -> Epilogue:
+    return Epilogue(_p(bias), alpha, alpha_cols, act, _p(aux_in), _p(aux_out), ldaux, _p(residual), ldr, res_mod,
+                    out_dtype, a2_group_cols)
+
+
+def gemm_nt(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, ep: Optional[Epilogue] = None, a2=None, w2=None,
+            k2: int = 0, M: Optional[int] = None, N: Optional[int] = None, K: Optional[int] = None):
+    """out[M,N] = epi(a[M,K] @ w[N,K]^T (+ a2[M,k2] @ w2[N,k2]^T)).  Leading dims are taken from .stride(0)."""
+    M = a.shape[0] if M is None else M
+    K = a.shape[1] if K is None else K
+    N = w.shape[0] if N is None else N
+    if ep is None:
+        ep = epilogue(out_dtype=ns_dtype(out))
+    check(lib().ns_gemm_nt(ns_dtype(a), M, N, K, _p(a), a.stride(0), _p(w), w.stride(0), _p(out), out.stride(0),
+                           C.byref(ep), _p(a2), a2.stride(0) if a2 is not None else 0, _p(w2),
+                           w2.stride(0) if w2 is not None else 0, k2, _stream()), "ns_gemm_nt")
+    return out
+
+
+def gemm_tn(x: torch.Tensor, y: torch.Tensor, g: torch.Tensor, si: int, sj: int, alpha: float = 1.0,
+            I: Optional[int] = None, J: Optional[int] = None):
+    """g[i*si + j*sj] += alpha * sum_m x[m,i] * y[m,j]   (g fp32)."""
+    I = x.shape[1] if I is None else I
+    J = y.shape[1] if J is None else J
+    check(lib().ns_gemm_tn(ns_dtype(x), x.shape[0], I, J, _p(x), x.stride(0), _p(y), y.stride(0), _p(g), si, sj, alpha,
+                           _stream()), "ns_gemm_tn")
+    return g
+
+
+def conv3_fwd(x, w_tap, y, stride: int, ep: Epilogue):
+    B, Tin, Cp = x.shape
+    N = w_tap.shape[1]
+    check(lib().ns_conv3_fwd(ns_dtype(x), B, Tin, Cp, N, stride, _p(x), _p(w_tap), _p(y), C.byref(ep), _stream()), "ns_conv3_fwd")
+    return y
+
+
+def conv3_dgrad(dz, w_tap_t, dx, stride: int, ep: Epilogue):
+    B, Tin, Cp = dx.shape
+    N = dz.shape[2]
+    check(lib().ns_conv3_dgrad(ns_dtype(dz), B, Tin, Cp, N, stride, _p(dz), _p(w_tap_t), _p(dx), C.byref(ep), _stream()), "ns_conv3_dgrad")
+    return dx
+
+
+def conv3_wgrad(dz, x, dw_tap, db, stride: int):
+    B, Tin, Cp = x.shape
+    N = dz.shape[2]
+    check(lib().ns_conv3_wgrad(ns_dtype(dz), B, Tin, Cp, N, stride, _p(dz), _p(x), _p(dw_tap), _p(db), _stream()), "ns_conv3_wgrad")
+
+
+def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps: float = 1e-5):
+    d = x.shape[-1]
+    check(lib().ns_layernorm_fwd(ns_dtype(x), x.numel() // d, d, _p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), eps, _stream()), "ns_layernorm_fwd")
+    return y
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dres=None):
+    d = x.shape[-1]
+    check(lib().ns_layernorm_bwd(ns_dtype(x), x.numel() // d, d, _p(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dres), _p(dx), _stream()), "ns_layernorm_bwd")
+    return dx
+
+
+def attn_shape(B, H, Lq, Lk, Dh, causal, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs) -> AttnShape:
+    return AttnShape(B, H, Lq, Lk, Dh, int(causal), q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs)
+
+
+def attention_fwd(shape: AttnShape, q, k, v, o, lse=None):
+    check(lib().ns_attention_fwd(ns_dtype(q), C.byref(shape), _p(q), _p(k), _p(v), _p(o), _p(lse), _stream()), "ns_attention_fwd")
+    return o
+
+
+def attention_bwd(shape: AttnShape, q, k, v, o, d_o, lse, delta, dq, dk, dv):
+    check(lib().ns_attention_bwd(ns_dtype(q), C.byref(shape), _p(q), _p(k), _p(v), _p(o), _p(d_o), _p(lse), _p(delta), _p(dq), _p(dk), _p(dv), _stream()), "ns_attention_bwd")
+
+
+def embed(ids, E, P, pos0: int, h):
+    B, L = ids.shape
+    check(lib().ns_embed(ns_dtype(E), B, L, E.shape[1], _p(ids), _p(E), _p(P), pos0, _p(h), _stream()), "ns_embed")
+    return h
+
+
+def cross_entropy(logits, V: int, labels, row_loss, loss_sum, n_valid, write_grad: bool, grad_scale: float = 1.0):
+    rows = logits.shape[0]
+    check(lib().ns_cross_entropy(ns_dtype(logits), rows, V, logits.stride(0), _p(logits), _p(labels), _p(row_loss), _p(loss_sum), _p(n_valid), int(write_grad), grad_scale, _stream()), "ns_cross_entropy")
+
+
+def greedy_pick(logits, V: int, suppress, eos: int, pad: int, finished, next_ids):
+    n_sup = 0 if suppress is None else suppress.numel()
+    check(lib().ns_greedy_pick(ns_dtype(logits), logits.shape[0], V, logits.stride(0), _p(logits), _p(suppress), n_sup, eos, pad, _p(finished), _p(next_ids), _stream()), "ns_greedy_pick")
+    return next_ids
+
+
+def cast(src, dst):
+    check(lib().ns_cast(ns_dtype(src), ns_dtype(dst), src.numel(), _p(src), _p(dst), _stream()), "ns_cast")
+    return dst
+
+
+def transpose(src, dst, scale: float = 1.0):
+    """dst (cols, ldd>=rows) = scale * src(rows, cols)^T ; columns [rows, ldd) of dst are zero-filled."""
+    rows, cols = src.shape
+    check(lib().ns_transpose(ns_dtype(src), ns_dtype(dst), rows, cols, _p(src), src.stride(0), _p(dst), dst.stride(0), scale, _stream()), "ns_transpose")
+    return dst
+
+
+def conv_weight_pack(w, w_tap, w_tap_t):
+    N, Cin, _ = w.shape
+    ref = w_tap if w_tap is not None else w_tap_t
+    Cp = w_tap.shape[2] if w_tap is not None else w_tap_t.shape[1]
+    check(lib().ns_conv_weight_pack(ns_dtype(ref), N, Cin, Cp, _p(w), _p(w_tap), _p(w_tap_t), _stream()), "ns_conv_weight_pack")
+
+
+def conv_weight_unpack_grad(dw_tap, dw):
+    N, Cin, _ = dw.shape
+    check(lib().ns_conv_weight_unpack_grad(N, Cin, dw_tap.shape[2], _p(dw_tap), _p(dw), _stream()), "ns_conv_weight_unpack_grad")
+
+
+def add(a, b, y):
+    check(lib().ns_add(ns_dtype(a), a.numel(), _p(a), _p(b), _p(y), _stream()), "ns_add")
+    return y
+
+
+def dgelu_mul(dy, z, dz):
+    check(lib().ns_dgelu_mul(ns_dtype(dy), dy.numel(), _p(dy), _p(z), _p(dz), _stream()), "ns_dgelu_mul")
+    return dz
+
+
+def sumsq(g, out):
+    check(lib().ns_sumsq(g.numel(), _p(g), _p(out), _stream()), "ns_sumsq")
+
+
+def adamw_clip(p, g, m, v, sumsq_t, gscale, max_norm, lr, beta1, beta2, eps, wd, step):
+    check(lib().ns_adamw_clip(p.numel(), _p(p), _p(g), _p(m), _p(v), _p(sumsq_t), gscale, max_norm, lr, beta1, beta2, eps, wd, step, _stream()), "ns_adamw_clip")
+
+
+def aug_pass(x, y, layout: int, n=None, shift=None, e0=None, e1=None, flags=None, grid=None, grid_stride=0, gl=None,
+             rep_c=None, rep_t=None, sigma=None, seed: int = 0):
+    B, Cc, Tin = x.shape
+    if layout == 0:
+        T, Cp = y.shape[2], Cc
+    else:
+        T, Cp = y.shape[1], y.shape[2]
+    a = AugArgs(B, Cc, Tin, T, Cp, layout, ns_dtype(y), _p(n), _p(shift), _p(e0), _p(e1), _p(flags), _p(grid), grid_stride,
+                _p(gl), _p(rep_c), _p(rep_t), _p(sigma), seed)
+    check(lib().ns_aug_pass(C.byref(a), _p(x), _p(y), _stream()), "ns_aug_pass")
+    return y
+
+
+def channel_meansq(x, n, ms):
+    B, Cc, Tin = x.shape
+    check(lib().ns_channel_meansq(B, Cc, Tin, _p(n), _p(x), _p(ms), _stream()), "ns_channel_meansq")
+    return ms

@@ -1,0 +1,413 @@
+"""Per-kernel parity tests on the GPU: every C-ABI entry point against a plain PyTorch fp32 restatement of the same op
+(bf16 storage: tolerance 2e-2 relative; fp32 storage: 1e-4 .. 1e-3), through the ctypes binding (neuspeech1_b200/ops.py)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from neuspeech1_b200 import _abi, ops
+    DEV = torch.device("cuda")
+
+
+def rel(a, b):
+    a = a.double(); b = b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def tol(dtype):
+    return 2e-2 if dtype == torch.bfloat16 else 2e-4
+
+
+def rnd(*shape, dtype=torch.float32, scale=1.0, seed=None):
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed if seed is not None else (abs(hash(shape)) % 100000))
+    return (torch.randn(*shape, generator=g) * scale).to(DEV, dtype)
+
+
+def gelu_grad(z):
+    z = z.double()
+    return (0.5 * (1 + torch.erf(z / math.sqrt(2))) + z * torch.exp(-0.5 * z * z) / math.sqrt(2 * math.pi)).float()
+
+
+@pytest.fixture(autouse=True)
+def _auto_path():
+    _abi.set_path(_abi.PATH_AUTO)
+    yield
+    _abi.set_path(_abi.PATH_AUTO)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM NT
+GEMM_CASES = [
+    # M, N, K, flags
+    (128, 256, 64, ""), (128, 256, 16, ""), (128, 256, 128, ""), (300, 512, 512, "bias"), (1000, 1536, 512, "bias,alpha"),
+    (257, 96, 512, "alpha_all"), (512, 32, 512, ""), (640, 64, 2048, "bias"), (384, 128, 512, "res"),
+    (1500, 512, 512, "bias,res,posmod"), (700, 2048, 512, "bias,gelu,aux"), (700, 512, 2048, "dgelu"),
+    (256, 1000, 512, "f32out"), (130, 1003, 512, "bias"), (128, 512, 208, ""), (3000, 512, 1536, "bias,res"),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("M,N,K,flags", GEMM_CASES)
+def test_gemm_nt(M, N, K, flags, dtype):
+    fl = set(flags.split(","))
+    a = rnd(M, K, dtype=dtype, seed=1); w = rnd(N, K, dtype=dtype, scale=K ** -0.5, seed=2)
+    ref = a.float() @ w.float().t()
+    kw = {}
+    bias = None
+    if "bias" in fl:
+        bias = rnd(N, seed=3); ref = ref + bias; kw["bias"] = bias
+    if "alpha" in fl:
+        kw.update(alpha=0.125, alpha_cols=512); ref[:, :512] *= 0.125
+    if "alpha_all" in fl:
+        kw.update(alpha=2.0, alpha_cols=N); ref = ref * 2.0
+    aux_out = None
+    if "gelu" in fl:
+        kw["act"] = _abi.ACT_GELU
+        if "aux" in fl:
+            aux_out = torch.zeros(M, N, dtype=dtype, device=DEV); kw.update(aux_out=aux_out, ldaux=N)
+        z_ref = ref.clone(); ref = F.gelu(ref)
+    if "dgelu" in fl:
+        z = rnd(M, N, dtype=dtype, seed=4)
+        kw.update(act=_abi.ACT_DGELU, aux_in=z, ldaux=N); ref = ref * gelu_grad(z.float())
+    if "res" in fl:
+        if "posmod" in fl:
+            r = rnd(500, N, dtype=dtype, seed=5); kw.update(residual=r, ldr=N, res_mod=500)
+            ref = ref + r.float()[torch.arange(M, device=DEV) % 500]
+        else:
+            r = rnd(M, N, dtype=dtype, seed=5); kw.update(residual=r, ldr=N); ref = ref + r.float()
+    odt = torch.float32 if "f32out" in fl else dtype
+    ldd = (N + 15) // 16 * 16
+    out = torch.full((M, ldd), 7.0, dtype=odt, device=DEV)
+    _abi.reset_counters()
+    ops.gemm_nt(a, w, out, ops.epilogue(out_dtype=ops.ns_dtype(odt), **kw), N=N)
+    torch.cuda.synchronize()
+    c = _abi.counters()
+    if dtype == torch.bfloat16 and K % 16 == 0:
+        assert c["gemm_tcgen05"] == 1 and c["gemm_simt"] == 0, c
+    else:
+        assert c["gemm_simt"] == 1, c
+    assert rel(out[:, :N].float(), ref) < tol(dtype), (rel(out[:, :N].float(), ref))
+    if ldd > N:
+        assert bool((out[:, N:] == 7.0).all()), "columns beyond N were written"
+    if aux_out is not None:
+        assert rel(aux_out.float(), z_ref) < tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("r", [32, 16, 8])
+def test_gemm_nt_lora_grouped(dtype, r):
+    """qkv projection with three stacked adapters: out[:, g*d:(g+1)*d] += t[:, g*r:(g+1)*r] @ B_g^T."""
+    M, d = 777, 256
+    a = rnd(M, d, dtype=dtype, seed=1); w = rnd(3 * d, d, dtype=dtype, scale=d ** -0.5, seed=2)
+    t = rnd(M, 3 * r, dtype=dtype, seed=3); b = rnd(3 * d, r, dtype=dtype, scale=0.2, seed=4)
+    bias = rnd(3 * d, seed=5)
+    ref = a.float() @ w.float().t() + bias
+    for g in range(3):
+        ref[:, g * d:(g + 1) * d] += t.float()[:, g * r:(g + 1) * r] @ b.float()[g * d:(g + 1) * d].t()
+    ref[:, :d] *= 0.125
+    out = torch.empty(M, 3 * d, dtype=dtype, device=DEV)
+    ops.gemm_nt(a, w, out, ops.epilogue(bias=bias, alpha=0.125, alpha_cols=d, a2_group_cols=d, out_dtype=ops.ns_dtype(dtype)), a2=t, w2=b, k2=r)
+    assert rel(out.float(), ref) < tol(dtype)
+    # single adapter, strided output view
+    out2 = torch.zeros(M, 2 * d, dtype=dtype, device=DEV)
+    ops.gemm_nt(a, w[:d], out2[:, d:], ops.epilogue(out_dtype=ops.ns_dtype(dtype)), a2=t[:, :r], w2=b[:d], k2=r)
+    ref2 = a.float() @ w.float()[:d].t() + t.float()[:, :r] @ b.float()[:d].t()
+    assert rel(out2[:, d:].float(), ref2) < tol(dtype)
+    assert bool((out2[:, :d] == 0).all())
+
+
+def test_gemm_nt_simt_equals_fast():
+    M, N, K = 500, 768, 512
+    a = rnd(M, K, dtype=torch.bfloat16, seed=1); w = rnd(N, K, dtype=torch.bfloat16, scale=K ** -0.5, seed=2)
+    o1 = torch.empty(M, N, dtype=torch.bfloat16, device=DEV); o2 = torch.empty_like(o1)
+    ops.gemm_nt(a, w, o1)
+    _abi.set_path(_abi.PATH_SIMT)
+    ops.gemm_nt(a, w, o2)
+    assert rel(o1.float(), o2.float()) < 5e-3
+
+
+def test_fast_path_required_fails_loudly():
+    a = rnd(64, 24, dtype=torch.bfloat16); w = rnd(32, 24, dtype=torch.bfloat16)
+    out = torch.empty(64, 32, dtype=torch.bfloat16, device=DEV)
+    _abi.set_path(_abi.PATH_FAST)
+    with pytest.raises(_abi.NeuSpeechB200Error):
+        ops.gemm_nt(a, w, out)      # K = 24 is not a multiple of 16
+
+
+# ------------------------------------------------------------------------------------------------ GEMM TN (wgrad)
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("M,I,J", [(64, 128, 32), (128, 128, 64), (1000, 512, 32), (4096, 2048, 32), (3001, 512, 96), (2000, 512, 208), (1500, 256, 512)])
+def test_gemm_tn(M, I, J, dtype):
+    x = rnd(M, I, dtype=dtype, seed=1); y = rnd(M, J, dtype=dtype, seed=2)
+    ref = 0.5 * (x.float().t() @ y.float())
+    g = torch.zeros(I, J, dtype=torch.float32, device=DEV)
+    ops.gemm_tn(x, y, g, J, 1, alpha=0.5)
+    assert rel(g, ref) < tol(dtype), rel(g, ref)
+    gt = torch.zeros(J, I, dtype=torch.float32, device=DEV)          # transposed store (the dA case)
+    ops.gemm_tn(x, y, gt, 1, I, alpha=0.5)
+    assert rel(gt, ref.t()) < tol(dtype)
+    ops.gemm_tn(x, y, gt, 1, I, alpha=0.5)                            # accumulates
+    assert rel(gt, 2 * ref.t()) < tol(dtype)
+
+
+def test_gemm_tn_column_windows():
+    """X / Y given as column windows of wider buffers (dB_g = dqkv_g^T t_g)."""
+    M, d, r = 900, 256, 32
+    dq = rnd(M, 3 * d, dtype=torch.bfloat16, seed=1); t = rnd(M, 3 * r, dtype=torch.bfloat16, seed=2)
+    for g in range(3):
+        out = torch.zeros(d, r, dtype=torch.float32, device=DEV)
+        ops.gemm_tn(dq[:, g * d:(g + 1) * d], t[:, g * r:(g + 1) * r], out, r, 1)
+        ref = dq.float()[:, g * d:(g + 1) * d].t() @ t.float()[:, g * r:(g + 1) * r]
+        assert rel(out, ref) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------ stem convolutions
+def _conv_ref(x_cl, w, b, stride):
+    """x_cl (B,T,C) fp32, w (N,C,3) -> z (B,Tout,N)"""
+    return F.conv1d(x_cl.permute(0, 2, 1), w, b, stride=stride, padding=1).permute(0, 2, 1).contiguous()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("B,T,C,N,stride", [(2, 256, 16, 128, 1), (3, 600, 208, 512, 1), (2, 600, 512, 512, 2), (1, 6000, 208, 512, 1),
+                                            (2, 3000, 512, 512, 2), (2, 520, 273, 256, 1)])
+def test_conv3_fwd_dgrad_wgrad(B, T, C, N, stride, dtype):
+    Cp = (C + 15) // 16 * 16
+    x = rnd(B, T, C, seed=1, scale=0.5)
+    w = rnd(N, C, 3, seed=2, scale=(3 * C) ** -0.5); b = rnd(N, seed=3, scale=0.1)
+    xq = x.to(dtype); wq = w.to(dtype)
+    x_cl = torch.zeros(B, T, Cp, dtype=dtype, device=DEV); x_cl[:, :, :C] = xq
+    w_tap = torch.empty(3, N, Cp, dtype=dtype, device=DEV); w_tap_t = torch.empty(3, Cp, N, dtype=dtype, device=DEV)
+    ops.conv_weight_pack(w, w_tap, w_tap_t)
+    assert torch.equal(w_tap[:, :, :C], wq.permute(2, 0, 1)) and torch.equal(w_tap_t[:, :C], wq.permute(2, 1, 0))
+    Tout = T // stride
+    z_ref = _conv_ref(xq.float(), wq.float(), b, stride)
+    pos = rnd(Tout, N, dtype=dtype, seed=4)
+    y = torch.empty(B, Tout, N, dtype=dtype, device=DEV); z = torch.empty_like(y)
+    ops.conv3_fwd(x_cl, w_tap, y, stride, ops.epilogue(bias=b, act=_abi.ACT_GELU, aux_out=z, ldaux=N, residual=pos, ldr=N, res_mod=Tout,
+                                                       out_dtype=ops.ns_dtype(dtype)))
+    assert rel(z.float(), z_ref) < tol(dtype)
+    assert rel(y.float(), F.gelu(z_ref) + pos.float()) < tol(dtype)
+    # wgrad
+    dz = rnd(B, Tout, N, dtype=dtype, seed=5)
+    xr = xq.float().requires_grad_(True); wr = wq.float().requires_grad_(True); br = b.clone().requires_grad_(True)
+    _conv_ref(xr, wr, br, stride).backward(dz.float())
+    dw_tap = torch.zeros(3, N, Cp, dtype=torch.float32, device=DEV); db = torch.zeros(N, dtype=torch.float32, device=DEV)
+    ops.conv3_wgrad(dz, x_cl, dw_tap, db, stride)
+    dw = torch.empty(N, C, 3, dtype=torch.float32, device=DEV)
+    ops.conv_weight_unpack_grad(dw_tap, dw)
+    assert rel(dw, wr.grad) < tol(dtype), rel(dw, wr.grad)
+    assert rel(db, br.grad) < tol(dtype)
+    if stride == 2:
+        zprev = rnd(B, T, Cp, dtype=dtype, seed=6)
+        dx = torch.empty(B, T, Cp, dtype=dtype, device=DEV)
+        ops.conv3_dgrad(dz, w_tap_t, dx, 2, ops.epilogue(act=_abi.ACT_DGELU, aux_in=zprev, ldaux=Cp, out_dtype=ops.ns_dtype(dtype)))
+        assert rel(dx[:, :, :C].float(), xr.grad * gelu_grad(zprev[:, :, :C].float())) < tol(dtype)
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("rows,d", [(1000, 512), (37, 128), (513, 1280), (100, 200)])
+def test_layernorm(rows, d, dtype):
+    x = rnd(rows, d, dtype=dtype, seed=1, scale=2.0) + 0.5
+    g = rnd(d, seed=2) * 0.1 + 1; b = rnd(d, seed=3) * 0.1
+    y = torch.empty_like(x); mean = torch.empty(rows, device=DEV); rstd = torch.empty(rows, device=DEV)
+    ops.layernorm_fwd(x, g, b, y, mean, rstd)
+    xr = x.float().requires_grad_(True)
+    ref = F.layer_norm(xr, (d,), g, b, 1e-5)
+    assert rel(y.float(), ref) < tol(dtype)
+    assert rel(mean, x.float().mean(1)) < 1e-4
+    dy = rnd(rows, d, dtype=dtype, seed=4); dres = rnd(rows, d, dtype=dtype, seed=5)
+    ref.backward(dy.float())
+    dx = torch.empty_like(x)
+    ops.layernorm_bwd(dy, x, g, mean, rstd, dx, dres=dres)
+    assert rel(dx.float(), xr.grad + dres.float()) < tol(dtype)
+    ops.layernorm_bwd(dy, x, g, mean, rstd, dx)
+    assert rel(dx.float(), xr.grad) < tol(dtype)
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def _attn_ref(q, k, v, causal):
+    """q (B,Lq,H,Dh) etc. fp32"""
+    qh, kh, vh = (t.permute(0, 2, 1, 3) for t in (q, k, v))
+    w = qh @ kh.transpose(2, 3)
+    Lq, Lk = q.shape[1], k.shape[1]
+    if causal:
+        m = torch.ones(Lq, Lk, dtype=torch.bool, device=q.device).tril(Lk - Lq)
+        w = w.masked_fill(~m, float("-inf"))
+    lse = torch.logsumexp(w, dim=-1)
+    return (w.softmax(-1) @ vh).permute(0, 2, 1, 3), lse
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("B,H,Lq,Lk,Dh,causal", [(2, 2, 64, 64, 64, False), (2, 8, 1500, 1500, 64, False), (3, 4, 32, 32, 64, True),
+                                                  (2, 8, 32, 1500, 64, False), (4, 2, 1, 77, 64, True), (2, 2, 5, 9, 32, True), (1, 2, 100, 100, 32, False)])
+def test_attention_fwd_bwd(B, H, Lq, Lk, Dh, causal, dtype):
+    d = H * Dh
+    packed = Lq == Lk
+    if packed:   # packed qkv buffer like the encoder
+        qkv = rnd(B * Lq, 3 * d, dtype=dtype, seed=1, scale=0.5)
+        q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
+        strides = (Lq * 3 * d, 3 * d) * 3
+    else:
+        q = rnd(B * Lq, d, dtype=dtype, seed=1, scale=0.5); kv = rnd(B * Lk, 2 * d, dtype=dtype, seed=2, scale=0.5)
+        k, v = kv[:, :d], kv[:, d:]
+        strides = (Lq * d, d, Lk * 2 * d, 2 * d, Lk * 2 * d, 2 * d)
+    shp = ops.attn_shape(B, H, Lq, Lk, Dh, causal, *strides, Lq * d, d)
+    o = torch.empty(B * Lq, d, dtype=dtype, device=DEV); lse = torch.empty(B, H, Lq, device=DEV)
+    ops.attention_fwd(shp, q, k, v, o, lse)
+    qf = q.float().reshape(B, Lq, H, Dh).requires_grad_(True)
+    kf = k.float().reshape(B, Lk, H, Dh).requires_grad_(True)
+    vf = v.float().reshape(B, Lk, H, Dh).requires_grad_(True)
+    ref, lse_ref = _attn_ref(qf, kf, vf, causal)
+    assert rel(o.float().view(B, Lq, H, Dh), ref) < tol(dtype)
+    assert rel(lse, lse_ref) < 1e-2 if dtype == torch.bfloat16 else rel(lse, lse_ref) < 1e-4
+    do = rnd(B * Lq, d, dtype=dtype, seed=3)
+    ref.backward(do.float().view(B, Lq, H, Dh))
+    dq = torch.empty(B * Lq, d, dtype=dtype, device=DEV); dk = torch.empty(B * Lk, d, dtype=dtype, device=DEV); dv = torch.empty_like(dk)
+    delta = torch.empty(B * H * Lq, device=DEV)
+    shp2 = ops.attn_shape(B, H, Lq, Lk, Dh, causal, *strides, Lq * d, d)
+    # gradients into fresh contiguous buffers need their own strides: reuse q/k/v strides by allocating like the inputs
+    if packed:
+        dqkv = torch.empty(B * Lq, 3 * d, dtype=dtype, device=DEV)
+        dq, dk, dv = dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:]
+    else:
+        dq = torch.empty(B * Lq, d, dtype=dtype, device=DEV); dkv = torch.empty(B * Lk, 2 * d, dtype=dtype, device=DEV)
+        dk, dv = dkv[:, :d], dkv[:, d:]
+    ops.attention_bwd(shp2, q, k, v, o, do, lse, delta, dq, dk, dv)
+    t = 3e-2 if dtype == torch.bfloat16 else 5e-4
+    assert rel(dq.float().reshape(B, Lq, H, Dh), qf.grad) < t
+    assert rel(dk.float().reshape(B, Lk, H, Dh), kf.grad) < t
+    assert rel(dv.float().reshape(B, Lk, H, Dh), vf.grad) < t
+
+
+# ------------------------------------------------------------------------------------------------ loss / decode helpers
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_cross_entropy(dtype):
+    rows, V = 96, 51865
+    Vp = (V + 15) // 16 * 16
+    logits = torch.zeros(rows, Vp, dtype=dtype, device=DEV)
+    logits[:, :V] = rnd(rows, V, dtype=dtype, seed=1, scale=2.0)
+    labels = torch.randint(0, V, (rows,), device=DEV); labels[::5] = -100
+    lf = logits[:, :V].float().clone().requires_grad_(True)
+    ref = F.cross_entropy(lf, labels, ignore_index=-100)
+    ref.backward()
+    row_loss = torch.empty(rows, device=DEV); loss_sum = torch.empty(1, device=DEV); nv = torch.empty(1, dtype=torch.int32, device=DEV)
+    ops.cross_entropy(logits, V, labels, row_loss, loss_sum, nv, write_grad=False)
+    assert int(nv) == int((labels != -100).sum())
+    assert abs(float(loss_sum) / int(nv) - float(ref)) < 1e-3 * float(ref)
+    ops.cross_entropy(logits, V, labels, row_loss, None, nv, write_grad=True)
+    assert rel(logits[:, :V].float(), lf.grad) < (2e-2 if dtype == torch.bfloat16 else 1e-4)
+    assert bool((logits[:, V:] == 0).all())
+
+
+def test_greedy_pick_and_embed():
+    B, V = 7, 1000
+    logits = rnd(B, 1008, seed=1)
+    logits[0, 5] = 50.0; logits[1, 220] = 60.0; logits[1, 9] = 55.0; logits[2, 997] = 70.0
+    sup = torch.tensor([220, 996], dtype=torch.int32, device=DEV)
+    fin = torch.zeros(B, dtype=torch.uint8, device=DEV); fin[3] = 1
+    nxt = torch.empty(B, dtype=torch.long, device=DEV)
+    ops.greedy_pick(logits, V, sup, 997, 997, fin, nxt)
+    ref = logits[:, :V].clone(); ref[:, [220, 996]] = float("-inf")
+    exp = ref.argmax(-1); exp[3] = 997
+    assert torch.equal(nxt, exp)
+    assert fin.tolist() == [0, 0, 1, 1, 0, 0, 0]
+    E = rnd(V, 64, seed=2); P = rnd(32, 64, seed=3)
+    ids = torch.randint(0, V, (B, 5), device=DEV)
+    h = torch.empty(B * 5, 64, device=DEV)
+    ops.embed(ids, E, P, 3, h)
+    assert torch.allclose(h.view(B, 5, 64), E[ids] + P[3:8])
+
+
+def test_adamw_clip_matches_torch():
+    n = 10000
+    p = rnd(n, seed=1); ref_p = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([ref_p], lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
+    m = torch.zeros(n, device=DEV); v = torch.zeros(n, device=DEV); ss = torch.zeros(1, device=DEV)
+    for step in range(1, 4):
+        g = rnd(n, seed=10 + step) * 0.05
+        ref_p.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_([ref_p], 1.0)
+        opt.step()
+        ss.zero_(); ops.sumsq(g, ss)
+        assert abs(float(ss) - float((g.double() ** 2).sum())) < 1e-3 * float(ss)
+        ops.adamw_clip(p, g, m, v, ss, 1.0, 1.0, 1e-2, 0.9, 0.999, 1e-8, 0.0, step)
+        assert rel(p, ref_p.detach()) < 1e-5
+
+
+def test_transpose_cast_add_dgelu():
+    a = rnd(100, 37, seed=1)
+    t = torch.full((37, 112), 9.0, dtype=torch.bfloat16, device=DEV)
+    ops.transpose(a, t, 0.5)
+    assert torch.equal(t[:, :100], (a.t() * 0.5).to(torch.bfloat16)) and bool((t[:, 100:] == 0).all())
+    c = torch.empty(100, 37, dtype=torch.bfloat16, device=DEV)
+    assert torch.equal(ops.cast(a, c), a.to(torch.bfloat16))
+    y = torch.empty_like(a); assert torch.equal(ops.add(a, a, y), a + a)
+    dz = torch.empty_like(a); ops.dgelu_mul(a, a * 2, dz)
+    assert rel(dz, a * gelu_grad(a * 2)) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ augmentation pass
+def test_aug_pass_matches_oracle():
+    from oracle import augment as A
+    B, C, T = 4, 21, 600
+    Cp = 32
+    cfg = {"noise": {"prob": 0.0, "min_snr_dB": 20, "max_snr_dB": 50},
+           "mask": {"prob": 1.0, "kwargs": {"unit": [2, 40], "mask_prob": 0.25, "random_type": 1}},
+           "taylor": {"prob": 1.0}, "shift": {"prob": 1.0}}
+    rng = np.random.RandomState(0)
+    torch.manual_seed(3); np.random.seed(3)
+    xs, plans, refs = [], [], []
+    for b in range(B):
+        n = int(rng.randint(150, 400))
+        x = rng.randn(C, n).astype(np.float32)
+        plan = A.draw_plan(x.shape, cfg, max_length=T, sample_rate=200)
+        xs.append(x); plans.append(plan); refs.append(A.apply_plan(x, plan, T))
+    Tin = max(x.shape[1] for x in xs)
+    xb = torch.zeros(B, C, Tin)
+    for b, x in enumerate(xs):
+        xb[b, :, :x.shape[1]] = torch.from_numpy(x)
+    gmax = max(p.grid.numel() for p in plans)
+    grid = torch.zeros(B, gmax, dtype=torch.uint8)
+    for b, p in enumerate(plans):
+        grid[b, :p.grid.numel()] = p.grid.reshape(-1).to(torch.uint8)
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=DEV)
+    kw = dict(n=i32([p.n for p in plans]), shift=i32([p.shift for p in plans]), e0=i32([p.edge0 for p in plans]),
+              e1=i32([p.edge1 for p in plans]), flags=i32([1] * B), grid=grid.to(DEV), grid_stride=gmax,
+              gl=i32([p.grid.shape[1] for p in plans]), rep_c=i32([p.rep_c for p in plans]), rep_t=i32([p.rep_t for p in plans]))
+    ref = torch.from_numpy(np.stack(refs)).to(DEV)
+    y0 = torch.empty(B, C, T, device=DEV)
+    ops.aug_pass(xb.to(DEV), y0, 0, **kw)
+    assert torch.equal(y0, ref)                                   # bit-exact in fp32 (mask / taylor / shift / pad)
+    y1 = torch.full((B, T, Cp), 5.0, dtype=torch.bfloat16, device=DEV)
+    ops.aug_pass(xb.to(DEV), y1, 1, **kw)
+    assert torch.equal(y1[:, :, :C], ref.permute(0, 2, 1).to(torch.bfloat16)) and bool((y1[:, :, C:] == 0).all())
+    # identity configuration (configs/augmentation1.json): pad + cast only
+    y2 = torch.empty(B, T, Cp, dtype=torch.float32, device=DEV)
+    ops.aug_pass(xb.to(DEV), y2, 1, n=kw["n"])
+    pad = torch.zeros(B, C, T); pad[:, :, :Tin] = xb
+    for b, p in enumerate(plans):
+        pad[b, :, p.n:] = 0
+    assert torch.equal(y2[:, :, :C].cpu(), pad.permute(0, 2, 1))
+
+
+def test_aug_noise_statistics():
+    B, C, T = 2, 8, 4000
+    x = (0.3 * torch.randn(B, C, T)).clamp(-1, 1).to(DEV)
+    n = torch.tensor([T, T], dtype=torch.int32, device=DEV)
+    ms = torch.empty(B, C, device=DEV)
+    ops.channel_meansq(x, n, ms)
+    assert rel(ms, (x ** 2).mean(-1)) < 1e-4
+    snr_db = 20.0
+    sigma = torch.sqrt(ms / 10 ** (snr_db / 10))
+    y = torch.empty(B, C, T, device=DEV)
+    ops.aug_pass(x, y, 0, n=n, flags=torch.tensor([2, 2], dtype=torch.int32, device=DEV), sigma=sigma, seed=1234)
+    resid = y - 2 * x                                              # the reference returns 2*signal + noise (utils/utils.py:55-58)
+    got_db = 10 * torch.log10((x ** 2).mean(-1) / (resid ** 2).mean(-1))
+    assert float((got_db - snr_db).abs().max()) < 0.5
+    assert abs(float(resid.mean())) < 0.01
