@@ -12,6 +12,9 @@ pytestmark = pytest.mark.gpu
 if torch.cuda.is_available():
     from neuspeech1_b200 import _abi, ops
     DEV = torch.device("cuda")
+    # the torch restatements are the fp32 reference: keep cuDNN / cuBLAS from silently using TF32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def rel(a, b):
