@@ -14,6 +14,38 @@ from . import _abi
 from ._abi import ACT_DGELU, ACT_GELU, ACT_NONE, AttnShape, AugArgs, Epilogue, NS_BF16, NS_F32, check
 
 _lib = None
+_fn_cache = {}
+_prof = None          # when a list: (name, flops, bytes, start_event, end_event) per launch
+
+
+def profile_begin():
+    """Record a CUDA-event pair around every ns_* call (on the current stream) until profile_end()."""
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """-> list of dicts {name, ms, flops, bytes} in launch order (synchronises)."""
+    global _prof
+    rec, _prof = _prof, None
+    torch.cuda.synchronize()
+    return [dict(name=n, flops=f, bytes=b, ms=s.elapsed_time(e)) for (n, f, b, s, e) in rec]
+
+
+def _call(name, work, *args):
+    fn = _fn_cache.get(name)
+    if fn is None:
+        fn = _fn_cache[name] = getattr(lib(), name)
+    if _prof is None:
+        st = fn(*args)
+    else:
+        s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+        s.record()
+        st = fn(*args)
+        e.record()
+        _prof.append((name, float(work[0]), float(work[1]), s, e))
+    if st != 0:
+        check(st, name)
 
 
 def lib():
@@ -58,9 +90,9 @@ def gemm_nt(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, ep: Optional[Ep
     N = w.shape[0] if N is None else N
     if ep is None:
         ep = epilogue(out_dtype=ns_dtype(out))
-    check(lib().ns_gemm_nt(ns_dtype(a), M, N, K, _p(a), a.stride(0), _p(w), w.stride(0), _p(out), out.stride(0),
-                           C.byref(ep), _p(a2), a2.stride(0) if a2 is not None else 0, _p(w2),
-                           w2.stride(0) if w2 is not None else 0, k2, _stream()), "ns_gemm_nt")
+    _call("ns_gemm_nt", (2.0 * M * N * (K + k2), 0), ns_dtype(a), M, N, K, _p(a), a.stride(0), _p(w), w.stride(0), _p(out),
+          out.stride(0), C.byref(ep), _p(a2), a2.stride(0) if a2 is not None else 0, _p(w2),
+          w2.stride(0) if w2 is not None else 0, k2, _stream())
     return out
 
 
@@ -69,40 +101,40 @@ def gemm_tn(x: torch.Tensor, y: torch.Tensor, g: torch.Tensor, si: int, sj: int,
     """g[i*si + j*sj] += alpha * sum_m x[m,i] * y[m,j]   (g fp32)."""
     I = x.shape[1] if I is None else I
     J = y.shape[1] if J is None else J
-    check(lib().ns_gemm_tn(ns_dtype(x), x.shape[0], I, J, _p(x), x.stride(0), _p(y), y.stride(0), _p(g), si, sj, alpha,
-                           _stream()), "ns_gemm_tn")
+    _call("ns_gemm_tn", (2.0 * x.shape[0] * I * J, 0), ns_dtype(x), x.shape[0], I, J, _p(x), x.stride(0), _p(y), y.stride(0),
+          _p(g), si, sj, alpha, _stream())
     return g
 
 
 def conv3_fwd(x, w_tap, y, stride: int, ep: Epilogue):
     B, Tin, Cp = x.shape
     N = w_tap.shape[1]
-    check(lib().ns_conv3_fwd(ns_dtype(x), B, Tin, Cp, N, stride, _p(x), _p(w_tap), _p(y), C.byref(ep), _stream()), "ns_conv3_fwd")
+    _call("ns_conv3_fwd", (6.0 * B * (Tin // stride) * Cp * N, 0), ns_dtype(x), B, Tin, Cp, N, stride, _p(x), _p(w_tap), _p(y), C.byref(ep), _stream())
     return y
 
 
 def conv3_dgrad(dz, w_tap_t, dx, stride: int, ep: Epilogue):
     B, Tin, Cp = dx.shape
     N = dz.shape[2]
-    check(lib().ns_conv3_dgrad(ns_dtype(dz), B, Tin, Cp, N, stride, _p(dz), _p(w_tap_t), _p(dx), C.byref(ep), _stream()), "ns_conv3_dgrad")
+    _call("ns_conv3_dgrad", (6.0 * B * (Tin // stride) * Cp * N, 0), ns_dtype(dz), B, Tin, Cp, N, stride, _p(dz), _p(w_tap_t), _p(dx), C.byref(ep), _stream())
     return dx
 
 
 def conv3_wgrad(dz, x, dw_tap, db, stride: int):
     B, Tin, Cp = x.shape
     N = dz.shape[2]
-    check(lib().ns_conv3_wgrad(ns_dtype(dz), B, Tin, Cp, N, stride, _p(dz), _p(x), _p(dw_tap), _p(db), _stream()), "ns_conv3_wgrad")
+    _call("ns_conv3_wgrad", (6.0 * B * (Tin // stride) * Cp * N, 0), ns_dtype(dz), B, Tin, Cp, N, stride, _p(dz), _p(x), _p(dw_tap), _p(db), _stream())
 
 
 def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps: float = 1e-5):
     d = x.shape[-1]
-    check(lib().ns_layernorm_fwd(ns_dtype(x), x.numel() // d, d, _p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), eps, _stream()), "ns_layernorm_fwd")
+    _call("ns_layernorm_fwd", (0, 2.0 * x.numel() * x.element_size()), ns_dtype(x), x.numel() // d, d, _p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), eps, _stream())
     return y
 
 
 def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dres=None):
     d = x.shape[-1]
-    check(lib().ns_layernorm_bwd(ns_dtype(x), x.numel() // d, d, _p(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dres), _p(dx), _stream()), "ns_layernorm_bwd")
+    _call("ns_layernorm_bwd", (0, (4.0 if dres is not None else 3.0) * x.numel() * x.element_size()), ns_dtype(x), x.numel() // d, d, _p(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dres), _p(dx), _stream())
     return dx
 
 
@@ -111,40 +143,40 @@ def attn_shape(B, H, Lq, Lk, Dh, causal, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_b
 
 
 def attention_fwd(shape: AttnShape, q, k, v, o, lse=None):
-    check(lib().ns_attention_fwd(ns_dtype(q), C.byref(shape), _p(q), _p(k), _p(v), _p(o), _p(lse), _stream()), "ns_attention_fwd")
+    _call("ns_attention_fwd", (4.0 * shape.B * shape.H * shape.Lq * shape.Lk * shape.Dh * (0.5 if shape.causal else 1.0), 0), ns_dtype(q), C.byref(shape), _p(q), _p(k), _p(v), _p(o), _p(lse), _stream())
     return o
 
 
 def attention_bwd(shape: AttnShape, q, k, v, o, d_o, lse, delta, dq, dk, dv):
-    check(lib().ns_attention_bwd(ns_dtype(q), C.byref(shape), _p(q), _p(k), _p(v), _p(o), _p(d_o), _p(lse), _p(delta), _p(dq), _p(dk), _p(dv), _stream()), "ns_attention_bwd")
+    _call("ns_attention_bwd", (10.0 * shape.B * shape.H * shape.Lq * shape.Lk * shape.Dh * (0.5 if shape.causal else 1.0), 0), ns_dtype(q), C.byref(shape), _p(q), _p(k), _p(v), _p(o), _p(d_o), _p(lse), _p(delta), _p(dq), _p(dk), _p(dv), _stream())
 
 
 def embed(ids, E, P, pos0: int, h):
     B, L = ids.shape
-    check(lib().ns_embed(ns_dtype(E), B, L, E.shape[1], _p(ids), _p(E), _p(P), pos0, _p(h), _stream()), "ns_embed")
+    _call("ns_embed", (0, 0), ns_dtype(E), B, L, E.shape[1], _p(ids), _p(E), _p(P), pos0, _p(h), _stream())
     return h
 
 
 def cross_entropy(logits, V: int, labels, row_loss, loss_sum, n_valid, write_grad: bool, grad_scale: float = 1.0):
     rows = logits.shape[0]
-    check(lib().ns_cross_entropy(ns_dtype(logits), rows, V, logits.stride(0), _p(logits), _p(labels), _p(row_loss), _p(loss_sum), _p(n_valid), int(write_grad), grad_scale, _stream()), "ns_cross_entropy")
+    _call("ns_cross_entropy", (0, (3.0 if write_grad else 2.0) * logits.numel() * logits.element_size()), ns_dtype(logits), rows, V, logits.stride(0), _p(logits), _p(labels), _p(row_loss), _p(loss_sum), _p(n_valid), int(write_grad), grad_scale, _stream())
 
 
 def greedy_pick(logits, V: int, suppress, eos: int, pad: int, finished, next_ids):
     n_sup = 0 if suppress is None else suppress.numel()
-    check(lib().ns_greedy_pick(ns_dtype(logits), logits.shape[0], V, logits.stride(0), _p(logits), _p(suppress), n_sup, eos, pad, _p(finished), _p(next_ids), _stream()), "ns_greedy_pick")
+    _call("ns_greedy_pick", (0, 0), ns_dtype(logits), logits.shape[0], V, logits.stride(0), _p(logits), _p(suppress), n_sup, eos, pad, _p(finished), _p(next_ids), _stream())
     return next_ids
 
 
 def cast(src, dst):
-    check(lib().ns_cast(ns_dtype(src), ns_dtype(dst), src.numel(), _p(src), _p(dst), _stream()), "ns_cast")
+    _call("ns_cast", (0, 0), ns_dtype(src), ns_dtype(dst), src.numel(), _p(src), _p(dst), _stream())
     return dst
 
 
 def transpose(src, dst, scale: float = 1.0):
     """dst (cols, ldd>=rows) = scale * src(rows, cols)^T ; columns [rows, ldd) of dst are zero-filled."""
     rows, cols = src.shape
-    check(lib().ns_transpose(ns_dtype(src), ns_dtype(dst), rows, cols, _p(src), src.stride(0), _p(dst), dst.stride(0), scale, _stream()), "ns_transpose")
+    _call("ns_transpose", (0, 0), ns_dtype(src), ns_dtype(dst), rows, cols, _p(src), src.stride(0), _p(dst), dst.stride(0), scale, _stream())
     return dst
 
 
@@ -152,30 +184,30 @@ def conv_weight_pack(w, w_tap, w_tap_t):
     N, Cin, _ = w.shape
     ref = w_tap if w_tap is not None else w_tap_t
     Cp = w_tap.shape[2] if w_tap is not None else w_tap_t.shape[1]
-    check(lib().ns_conv_weight_pack(ns_dtype(ref), N, Cin, Cp, _p(w), _p(w_tap), _p(w_tap_t), _stream()), "ns_conv_weight_pack")
+    _call("ns_conv_weight_pack", (0, 0), ns_dtype(ref), N, Cin, Cp, _p(w), _p(w_tap), _p(w_tap_t), _stream())
 
 
 def conv_weight_unpack_grad(dw_tap, dw):
     N, Cin, _ = dw.shape
-    check(lib().ns_conv_weight_unpack_grad(N, Cin, dw_tap.shape[2], _p(dw_tap), _p(dw), _stream()), "ns_conv_weight_unpack_grad")
+    _call("ns_conv_weight_unpack_grad", (0, 0), N, Cin, dw_tap.shape[2], _p(dw_tap), _p(dw), _stream())
 
 
 def add(a, b, y):
-    check(lib().ns_add(ns_dtype(a), a.numel(), _p(a), _p(b), _p(y), _stream()), "ns_add")
+    _call("ns_add", (0, 0), ns_dtype(a), a.numel(), _p(a), _p(b), _p(y), _stream())
     return y
 
 
 def dgelu_mul(dy, z, dz):
-    check(lib().ns_dgelu_mul(ns_dtype(dy), dy.numel(), _p(dy), _p(z), _p(dz), _stream()), "ns_dgelu_mul")
+    _call("ns_dgelu_mul", (0, 0), ns_dtype(dy), dy.numel(), _p(dy), _p(z), _p(dz), _stream())
     return dz
 
 
 def sumsq(g, out):
-    check(lib().ns_sumsq(g.numel(), _p(g), _p(out), _stream()), "ns_sumsq")
+    _call("ns_sumsq", (0, 0), g.numel(), _p(g), _p(out), _stream())
 
 
 def adamw_clip(p, g, m, v, sumsq_t, gscale, max_norm, lr, beta1, beta2, eps, wd, step):
-    check(lib().ns_adamw_clip(p.numel(), _p(p), _p(g), _p(m), _p(v), _p(sumsq_t), gscale, max_norm, lr, beta1, beta2, eps, wd, step, _stream()), "ns_adamw_clip")
+    _call("ns_adamw_clip", (0, 0), p.numel(), _p(p), _p(g), _p(m), _p(v), _p(sumsq_t), gscale, max_norm, lr, beta1, beta2, eps, wd, step, _stream())
 
 
 def aug_pass(x, y, layout: int, n=None, shift=None, e0=None, e1=None, flags=None, grid=None, grid_stride=0, gl=None,
@@ -187,11 +219,11 @@ def aug_pass(x, y, layout: int, n=None, shift=None, e0=None, e1=None, flags=None
         T, Cp = y.shape[1], y.shape[2]
     a = AugArgs(B, Cc, Tin, T, Cp, layout, ns_dtype(y), _p(n), _p(shift), _p(e0), _p(e1), _p(flags), _p(grid), grid_stride,
                 _p(gl), _p(rep_c), _p(rep_t), _p(sigma), seed)
-    check(lib().ns_aug_pass(C.byref(a), _p(x), _p(y), _stream()), "ns_aug_pass")
+    _call("ns_aug_pass", (0, x.numel() * 4.0 + y.numel() * y.element_size()), C.byref(a), _p(x), _p(y), _stream())
     return y
 
 
 def channel_meansq(x, n, ms):
     B, Cc, Tin = x.shape
-    check(lib().ns_channel_meansq(B, Cc, Tin, _p(n), _p(x), _p(ms), _stream()), "ns_channel_meansq")
+    _call("ns_channel_meansq", (0, 0), B, Cc, Tin, _p(n), _p(x), _p(ms), _stream())
     return ms

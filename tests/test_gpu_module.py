@@ -1,0 +1,90 @@
+"""The drop-in nn.Module (neuspeech1_b200.load_model) on the GPU: autograd path (what HF Trainer drives), external torch
+optimizer on the aliased parameters, generate, stem swap, no-grad evaluation."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import whisper_eeg as O
+
+if torch.cuda.is_available():
+    from neuspeech1_b200.engine import ModelDims
+    from neuspeech1_b200.load_model import WhisperForConditionalGeneration
+    from neuspeech1_b200.model_utils import projection_module
+    DEV = torch.device("cuda")
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().double().cpu(); b = torch.as_tensor(b).detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def test_autograd_path_matches_oracle_and_external_optimizer_works():
+    dims = O.TINY
+    P = O.init_params(dims, seed=0); lora = O.init_lora(dims, seed=1, b_std=0.05)
+    x, labels = O.synthetic_batch(dims, B=2, L=8, seed=1)
+    loss_ref, grads_ref, enc_ref = O.grads(x, labels, P, dims, lora)
+    m = WhisperForConditionalGeneration(ModelDims.from_any(dims), P, lora, dtype=torch.float32, device=DEV)
+    m.train()
+    out = m(input_features=x.to(DEV), labels=labels.to(DEV))
+    assert abs(float(out.loss) - float(loss_ref)) < 1e-3 * float(loss_ref)
+    assert float(out["loss"]) == float(out.loss)
+    assert out.logits.shape == (2, 8, dims.vocab)
+    (out.loss * 0.5).backward()
+    named = dict(m.named_parameters())
+    for k, g in grads_ref.items():
+        p = named[k]
+        assert p.grad is not None, k
+        assert rel(p.grad, 0.5 * g) < 2e-3, k
+    frozen = [k for k, p in named.items() if not p.requires_grad]
+    assert all(named[k].grad is None for k in frozen)
+    # external optimizer on the aliased parameters changes what the engine computes
+    opt = torch.optim.AdamW([p for p in m.parameters() if p.requires_grad], lr=1e-2, weight_decay=0.0)
+    opt.step(); opt.zero_grad(set_to_none=True)
+    out2 = m(input_features=x.to(DEV), labels=labels.to(DEV))
+    assert float(out2.loss) < float(out.loss)
+    # oracle takes the same (unclipped) AdamW step
+    st = O.AdamWState()
+    both = {**lora, **{k: P[k] for k in grads_ref if k in P}}
+    O.clip_and_adamw(both, {k: 0.5 * g for k, g in grads_ref.items()}, st, lr=1e-2, max_norm=1e9)
+    loss_ref2, _, _ = O.grads(x, labels, P, dims, lora)
+    assert abs(float(out2.loss) - float(loss_ref2)) < 2e-3 * float(loss_ref2)
+
+
+def test_eval_generate_and_stem_swap():
+    dims = O.TINY
+    P = O.init_params(dims, seed=0)
+    x, labels = O.synthetic_batch(dims, B=2, L=8, seed=1)
+    m = WhisperForConditionalGeneration(ModelDims.from_any(dims), P, None, dtype=torch.float32, device=DEV)
+    m.eval()
+    with torch.no_grad():
+        out = m(input_features=x.to(DEV), decoder_input_ids=O.shift_tokens_right(labels, dims.pad_token_id, dims.decoder_start_token_id).to(DEV))
+    _, logits_ref, _ = O.forward_loss(x, labels, P, dims)
+    assert out.loss is None and rel(out.logits, logits_ref) < 1e-3                      # evaluation.py:392-395 path
+    ids = m.generate(x.to(DEV), do_sample=False, num_beams=1, max_new_tokens=10)
+    ids_ref = O.greedy_decode(x, P, dims, max_length=11)
+    assert torch.equal(ids.cpu(), ids_ref)
+    enc = m.get_encoder()(x.to(DEV)).last_hidden_state
+    assert rel(enc, O.encoder(x, P, dims)) < 1e-3
+    # cross-dataset stem swap (finetune.py:150-163): new channel count, transformer weights kept
+    new_ch = 21
+    stem = projection_module("base", meg_ch=new_ch, d_model=dims.d_model)
+    m.model.encoder.set_input_embeddings(stem)
+    dims2 = O.Dims(**{**dims.__dict__, "eeg_ch": new_ch})
+    P2 = dict(P)
+    for k, v in stem.state_dict().items():
+        P2["model.encoder.conv1." + k] = v.detach().clone()
+    x2, _ = O.synthetic_batch(dims2, B=2, L=8, seed=2)
+    out = m(input_features=x2.to(DEV), labels=labels.to(DEV))
+    loss_ref, _, enc_ref = O.forward_loss(x2, labels, P2, dims2)
+    assert rel(out.encoder_last_hidden_state, enc_ref) < 1e-3
+    assert abs(float(out.loss) - float(loss_ref)) < 1e-3 * float(loss_ref)
+
+
+def test_fused_training_step_reduces_loss_bf16():
+    dims = O.TINY
+    P = O.init_params(dims, seed=0); lora = O.init_lora(dims, seed=1, b_std=0.0)
+    x, labels = O.synthetic_batch(dims, B=4, L=8, seed=3)
+    m = WhisperForConditionalGeneration(ModelDims.from_any(dims), P, lora, dtype=torch.bfloat16, device=DEV)
+    losses = [float(m.training_step(x.to(DEV), labels.to(DEV), lr=2e-3).loss) for _ in range(8)]
+    assert losses[-1] < losses[0] - 0.05, losses

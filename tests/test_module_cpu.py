@@ -1,0 +1,98 @@
+"""CPU-side checks of the drop-in module's object contract: module tree / parameter names as PEFT and the
+reference's scripts expect them, checkpoint round trips, merge semantics.  No engine (no GPU) involved."""
+import os
+
+import pytest
+import torch
+
+from neuspeech1_b200 import lora as L
+from neuspeech1_b200.engine import ModelDims, TrainableLayout
+from neuspeech1_b200.load_model import WhisperForConditionalGeneration
+from neuspeech1_b200.model_utils import projection_module
+from neuspeech1_b200.weights import merge_lora, random_lora, random_params
+from oracle import whisper_eeg as O
+
+DIMS = ModelDims.from_any(O.TINY)
+
+
+def make(lora=True):
+    return WhisperForConditionalGeneration(DIMS, random_params(DIMS), random_lora(DIMS, b_std=0.05) if lora else None, device="cpu")
+
+
+def test_projection_module_matches_reference_contract():
+    m = projection_module("base", meg_ch=208, d_model=512)
+    assert m.stride == (2,) and m[0].weight.shape == (512, 208, 3) and m[2].stride == (2,)
+    with pytest.raises(NotImplementedError):
+        projection_module("nope")
+
+
+def test_parameter_names_match_hf_and_peft():
+    m = make()
+    names = dict(m.named_parameters())
+    for k in ("model.encoder.conv1.0.weight", "model.encoder.conv1.2.bias", "model.encoder.conv2.weight",
+              "model.encoder.layers.1.self_attn.q_proj.base_layer.weight", "model.encoder.layers.1.self_attn.q_proj.lora_A.default.weight",
+              "model.encoder.layers.0.fc2.lora_B.default.weight", "model.decoder.layers.1.encoder_attn.k_proj.weight",
+              "model.decoder.embed_tokens.weight"):
+        assert k in names, k
+    assert "model.encoder.layers.0.self_attn.k_proj.base_layer.bias" not in names          # k_proj has no bias (HF:279)
+    trainable = {k for k, p in names.items() if p.requires_grad}
+    lay = TrainableLayout(DIMS)
+    norm = {k.replace(".base_layer.", ".") for k in trainable}
+    assert norm == set(lay.entries), norm ^ set(lay.entries)
+    assert m.model.encoder.conv2.in_channels == DIMS.d_model                               # finetune.py:140
+    assert m.model.encoder.conv1.stride[0] * m.model.encoder.conv2.stride[0] == 4          # generation_whisper.py:653
+    assert m.proj_out.weight is m.model.decoder.embed_tokens.weight
+
+
+def test_match_modules_string_picks_the_36_encoder_linears():
+    m = make(lora=False)
+    names = L.match_modules_string(m.named_modules(), ["model.encoder"], ["k_proj", "q_proj", "v_proj", "out_proj", "fc1", "fc2"])
+    assert len(names) == DIMS.enc_layers * 6 and all(n.startswith("model.encoder.layers.") for n in names)
+
+
+def test_adapter_round_trip_and_merge(tmp_path):
+    m = make()
+    L.lora_inject(m, r=DIMS.lora_r, lora_alpha=DIMS.lora_alpha, modules_to_save=["model.encoder.conv1", "model.encoder.conv2"])
+    assert m.model.encoder.conv1.stride == (2,)                                            # resolves through the wrapper
+    sd = L.adapter_state_dict(m)
+    assert "base_model.model.model.encoder.conv1.modules_to_save.default.0.weight" in sd
+    L.save_adapter(m, str(tmp_path))
+    m2 = make()
+    L.lora_inject(m2, r=DIMS.lora_r, lora_alpha=DIMS.lora_alpha, modules_to_save=["model.encoder.conv1", "model.encoder.conv2"])
+    for p in m2.parameters():
+        if p.requires_grad:
+            p.data.add_(1.0)
+    L.load_adapter(m2, str(tmp_path))
+    for (k, a), (_, b) in zip(sorted(L.adapter_state_dict(m).items()), sorted(L.adapter_state_dict(m2).items())):
+        assert torch.equal(a, b), k
+    # merge_and_unload == W + (alpha/r) B A
+    P = random_params(DIMS); lo = random_lora(DIMS, b_std=0.05)
+    m3 = WhisperForConditionalGeneration(DIMS, P, lo, device="cpu")
+    L.merge_and_unload(m3)
+    ref = merge_lora(P, lo, DIMS.lora_scale)
+    got = dict(m3.named_parameters())
+    for k in ("model.encoder.layers.0.self_attn.q_proj.weight", "model.encoder.layers.1.fc2.weight"):
+        assert torch.allclose(got[k], ref[k], atol=1e-6)
+    assert not any(".lora_" in k for k in got)
+
+
+def test_from_pretrained_reads_hf_checkpoint(tmp_path):
+    """A stock HF Whisper checkpoint directory (mel stem) loads; the EEG stem is created fresh (finetune.py:127-148)."""
+    from oracle.hf_bridge import hf_config
+    from transformers import WhisperForConditionalGeneration as HF
+    hf = HF(hf_config(O.TINY))
+    hf.save_pretrained(str(tmp_path))
+    m = WhisperForConditionalGeneration.from_pretrained(str(tmp_path), eeg_ch=16, device="cpu")
+    sd = hf.state_dict()
+    got = m.state_dict()
+    for k in ("model.encoder.layers.0.fc1.weight", "model.decoder.embed_tokens.weight", "model.encoder.conv2.weight"):
+        assert torch.equal(got[k], sd[k]), k
+    assert got["model.encoder.conv1.0.weight"].shape == (O.TINY.d_model, 16, 3)
+
+
+def test_forward_argument_errors():
+    m = make()
+    with pytest.raises(ValueError):
+        m.forward(input_features=torch.zeros(1, 16, 256))
+    with pytest.raises(NotImplementedError):
+        m.generate(torch.zeros(1, 16, 256), num_beams=5)
