@@ -317,6 +317,21 @@ static int attn_bwd_simt_t(const ns_attn_shape& s, const void* q, const void* k,
   return NS_OK;
 }
 
+int attention_delta(int dtype, const ns_attn_shape& s, const void* o, const void* d_o, float* delta, cudaStream_t st) {
+  const long long total = static_cast<long long>(s.B) * s.H * s.Lq;
+  const unsigned grid = static_cast<unsigned>((total + 7) / 8);
+  if (dtype == NS_F32) {
+    if (s.Dh == 64) attn_delta_kernel<float, 64><<<grid, 256, 0, st>>>(s, reinterpret_cast<const float*>(o), reinterpret_cast<const float*>(d_o), delta);
+    else attn_delta_kernel<float, 32><<<grid, 256, 0, st>>>(s, reinterpret_cast<const float*>(o), reinterpret_cast<const float*>(d_o), delta);
+  } else {
+    if (s.Dh == 64) attn_delta_kernel<__nv_bfloat16, 64><<<grid, 256, 0, st>>>(s, reinterpret_cast<const __nv_bfloat16*>(o), reinterpret_cast<const __nv_bfloat16*>(d_o), delta);
+    else attn_delta_kernel<__nv_bfloat16, 32><<<grid, 256, 0, st>>>(s, reinterpret_cast<const __nv_bfloat16*>(o), reinterpret_cast<const __nv_bfloat16*>(d_o), delta);
+  }
+  NS_LAUNCH_CHECK();
+  count(C_OTHER);
+  return NS_OK;
+}
+
 int attention_fwd_simt(int dtype, const ns_attn_shape& s, const void* q, const void* k, const void* v, void* o, float* lse, cudaStream_t st) {
   if (dtype == NS_F32) return s.Dh == 64 ? attn_fwd_simt_t<float, 64>(s, q, k, v, o, lse, st) : attn_fwd_simt_t<float, 32>(s, q, k, v, o, lse, st);
   return s.Dh == 64 ? attn_fwd_simt_t<__nv_bfloat16, 64>(s, q, k, v, o, lse, st) : attn_fwd_simt_t<__nv_bfloat16, 32>(s, q, k, v, o, lse, st);

@@ -1,13 +1,550 @@
-// Tensor-core attention (placeholder dispatch until the tcgen05 flash kernels land: reports "unsupported" so that the
-// caller takes the SIMT kernels -- still a CUDA path, never a CPU one).
+// Flash-style attention on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), head_dim 64, bf16, non-causal.
+//
+// forward, one CTA per (batch, head, 128-query tile), two CTAs resident per SM so one CTA's softmax overlaps the other's MMAs:
+//   warp 0      TMA producer : Q tile once, then K / V tiles of 128 keys through a 2-stage ring
+//   warp 1      MMA issuer   : S = Q K^T (SS form, 128x128 fp32 in TMEM), then O += P V (TS form: P read from TMEM, V MN-major)
+//   warps 2..5  softmax      : one query row per thread (TMEM lane = row): two passes over S with tcgen05.ld -- row max, then
+//                              p = exp2((s - m) * log2e), row sum, bf16 P written back to TMEM with tcgen05.st.
+//                              O is rescaled lazily (only when the running max grew by > 8 in log2 units), so most tiles skip
+//                              the TMEM round trip of the accumulator.
+// TMEM columns: [0,128) S, [128,192) P (bf16 pairs), [192,256) O.   q is pre-scaled by the caller (HF modeling_whisper.py:310).
 #include "ns_common.cuh"
+#include "ns_sm100.cuh"
 
 namespace ns {
-int attention_fwd_tc(const ns_attn_shape&, const void*, const void*, const void*, void*, float*, cudaStream_t) {
-  return NS_ERR_UNSUPPORTED;
+using namespace sm100;
+
+struct AttnMaps {
+  CUtensorMap q, k, v;
+};
+struct AttnFwdProg {
+  int B, H, Lq, Lk;
+  long long o_bs, o_rs;
+  __nv_bfloat16* o;
+  float* lse;
+};
+
+constexpr int kAtThreads = 192;
+constexpr int kTile = 128 * 64 * 2;                          // one [128][64] bf16 tile, 128B-swizzled
+constexpr int kAtSmem = kTile * 5 + 1024 + 256;
+constexpr float kLog2e = 1.4426950408889634f;
+
+__global__ void __launch_bounds__(kAtThreads, 2)
+attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnFwdProg p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = smem_base;
+  auto sK = [&](int s) { return smem_base + kTile * (1 + s); };
+  auto sV = [&](int s) { return smem_base + kTile * (3 + s); };
+  const uint32_t bar = smem_base + kTile * 5;
+  const uint32_t q_full = bar;
+  auto k_full = [&](int s) { return bar + 8u * (1 + s); };
+  auto v_full = [&](int s) { return bar + 8u * (3 + s); };
+  auto k_empty = [&](int s) { return bar + 8u * (5 + s); };
+  auto v_empty = [&](int s) { return bar + 8u * (7 + s); };
+  const uint32_t s_full = bar + 8u * 9, p_full = bar + 8u * 10, o_full = bar + 8u * 11;
+  const uint32_t tmem_slot = bar + 8u * 12;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int n_kv = (p.Lk + 127) / 128;
+
+  if (warp == 0 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(k_full(s), 1); mbar_init(v_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_empty(s), 1); }
+    mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t tS = tmem, tP = tmem + 128, tO = tmem + 192;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, kTile);
+      tma_load_3d(&maps.q, q_full, sQ, h * 64, q0, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1u;
+        mbar_wait(k_empty(s), ph ^ 1u);
+        mbar_expect_tx(k_full(s), kTile);
+        tma_load_3d(&maps.k, k_full(s), sK(s), h * 64, j * 128, b);
+        mbar_wait(v_empty(s), ph ^ 1u);
+        mbar_expect_tx(v_full(s), kTile);
+        tma_load_3d(&maps.v, v_full(s), sV(s), h * 64, j * 128, b);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idescS = umma_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idescO = umma_idesc_bf16(128, 64, 0, 1);          // B = V is MN-major (keys x head_dim rows)
+    mbar_wait(q_full, 0);
+    for (int j = 0; j < n_kv; ++j) {
+      const int s = j & 1;
+      const uint32_t ph = (j >> 1) & 1u;
+      mbar_wait(k_full(s), ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t qd = umma_smem_desc(sQ, 16, 1024), kd = umma_smem_desc(sK(s), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tS, qd + 2u * k, kd + 2u * k, idescS, k > 0);
+        umma_commit(k_empty(s));
+        umma_commit(s_full);
+      }
+      __syncwarp();
+      mbar_wait(p_full, j & 1);
+      tc_fence_after();
+      mbar_wait(v_full(s), ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t vd = umma_smem_desc(sV(s), 8192, 1024);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) umma_f16_ts(tO, tP + 8u * k, vd + 128u * k, idescO, (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(v_empty(s));
+        if (j == n_kv - 1) umma_commit(o_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    float m_used = -INFINITY, l = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int nvalid = min(128, p.Lk - j * 128);
+      uint32_t v[32];
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld32(tS + lane_addr + 32u * c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      if (j == 0) {
+        m_used = mx;
+      } else {
+        const bool need = mx > m_used + 5.545177f;                       // 8 / log2(e)
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = fmaxf(m_used, mx);
+          const float sc = exp2f((m_used - m_new) * kLog2e);
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            tmem_ld32(tO + lane_addr + 32u * c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * sc);
+            tmem_st32(tO + lane_addr + 32u * c, v);
+          }
+          l *= sc;
+          m_used = m_new;
+        }
+      }
+      const float mb = m_used * kLog2e;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld32(tS + lane_addr + 32u * c, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), kLog2e, -mb));
+          float p1 = exp2f(fmaf(__uint_as_float(v[2 * i + 1]), kLog2e, -mb));
+          if (c * 32 + 2 * i >= nvalid) p0 = 0.f;
+          if (c * 32 + 2 * i + 1 >= nvalid) p1 = 0.f;
+          l += p0 + p1;
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+        tmem_st16(tP + lane_addr + 16u * c, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const int qi = q0 + row;
+    const float inv = 1.0f / l;
+    __nv_bfloat16* orow = p.o + b * p.o_bs + static_cast<long long>(qi) * p.o_rs + h * 64;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tO + lane_addr + 32u * c, v);
+      tmem_ld_wait();
+      if (qi < p.Lq) {
+        uint4* dst = reinterpret_cast<uint4*>(orow + 32 * c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
+          dst[i] = u;
+        }
+      }
+    }
+    if (p.lse && qi < p.Lq) p.lse[(static_cast<long long>(b) * p.H + h) * p.Lq + qi] = m_used + logf(l);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
 }
-int attention_bwd_tc(const ns_attn_shape&, const void*, const void*, const void*, const void*, const void*, const float*,
-                     float*, void*, void*, void*, cudaStream_t) {
-  return NS_ERR_UNSUPPORTED;
+
+static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static int head_map(CUtensorMap* m, const void* base, int H, int L, int B, long long bs, long long rs) {
+  uint64_t dims[3] = {(uint64_t)H * 64, (uint64_t)L, (uint64_t)B};
+  uint64_t str[2] = {(uint64_t)rs * 2, (uint64_t)bs * 2};
+  uint32_t box[3] = {64, 128, 1};
+  return make_map(m, base, 3, dims, str, box);
+}
+
+static bool tc_eligible(const ns_attn_shape& s, const void* q, const void* k, const void* v, const void* o) {
+  return s.Dh == 64 && !s.causal && al16(q) && al16(k) && al16(v) && al16(o) && s.q_rs % 8 == 0 && s.k_rs % 8 == 0 &&
+         s.v_rs % 8 == 0 && s.o_rs % 8 == 0 && s.q_bs % 8 == 0 && s.k_bs % 8 == 0 && s.v_bs % 8 == 0 && s.o_bs % 8 == 0 &&
+         s.Lk >= 1 && s.H <= 65535 && s.B <= 65535;
+}
+
+int attention_fwd_tc(const ns_attn_shape& s, const void* q, const void* k, const void* v, void* o, float* lse, cudaStream_t st) {
+  if (!tc_eligible(s, q, k, v, o)) return NS_ERR_UNSUPPORTED;
+  static bool attr_done = false;
+  if (!attr_done) {
+    NS_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+    attr_done = true;
+  }
+  AttnMaps maps;
+  int r;
+  if ((r = head_map(&maps.q, q, s.H, s.Lq, s.B, s.q_bs, s.q_rs))) return r;
+  if ((r = head_map(&maps.k, k, s.H, s.Lk, s.B, s.k_bs, s.k_rs))) return r;
+  if ((r = head_map(&maps.v, v, s.H, s.Lk, s.B, s.v_bs, s.v_rs))) return r;
+  AttnFwdProg prog{s.B, s.H, s.Lq, s.Lk, s.o_bs, s.o_rs, reinterpret_cast<__nv_bfloat16*>(o), lse};
+  dim3 grid((s.Lq + 127) / 128, s.H, s.B);
+  attn_fwd_tc_kernel<<<grid, kAtThreads, kAtSmem, st>>>(maps, prog);
+  NS_LAUNCH_CHECK();
+  count(C_ATTN_TC);
+  return NS_OK;
+}
+
+// =================================================================================================== backward
+// Two kernels, no atomics (deterministic):
+//   attn_bwd_dkdv_tc_kernel : CTA = (b, h, 128 keys).  TMEM lanes = keys.  Per 64-query step:
+//        S^T = K Q^T, dP^T = V dO^T (SS) -> P^T = exp2(S^T*log2e - lse[q]), dS^T = P^T (dP^T - delta[q]) (8 compute warps,
+//        lse/delta per COLUMN via broadcast shared loads) -> bf16 P^T / dS^T written over the consumed S^T / dP^T columns
+//        -> dV += P^T dO, dK += dS^T Q  (TS: A from TMEM, B = dO / Q tile MN-major).
+//   attn_bwd_dq_tc_kernel   : CTA = (b, h, 128 queries).  TMEM lanes = queries (lse/delta are per-thread scalars).  Per 64-key
+//        step: S = Q K^T, dP = dO V^T -> dS = P (dP - delta) -> dQ += dS K  (TS, B = K tile MN-major).
+// TMEM budget 256 columns per CTA so that two CTAs share an SM (one computes while the other's MMAs run).
+struct AttnBwdMaps {
+  CUtensorMap q, k, v, d_o;     // box {64, 128} for the resident operand, {64, 64} for the streamed one (see host code)
+};
+struct AttnBwdProg {
+  int B, H, Lq, Lk;
+  const float* lse;
+  const float* delta;
+  long long g_bs, g_rs, g2_bs, g2_rs;   // output strides: dkdv kernel -> (dk, dv); dq kernel -> (dq, unused)
+  __nv_bfloat16* out0;
+  __nv_bfloat16* out1;
+};
+
+constexpr int kBwThreads = 320;                       // warp0 TMA, warp1 MMA, warps 2..9 compute
+constexpr int kHalf = 64 * 64 * 2;                    // [64][64] bf16 tile
+constexpr int kBwSmem = 2 * kTile + 4 * kHalf + 1024 + 2048 + 256;
+
+// column offset (in 32-bit TMEM columns) of the bf16 pair block for step-local index k16 (16 contraction elements)
+__device__ __forceinline__ uint32_t pk_col(int k16) { return static_cast<uint32_t>((k16 >> 1) * 32 + (k16 & 1) * 8); }
+
+template <bool kDQ>
+__global__ void __launch_bounds__(kBwThreads, 2)
+attn_bwd_tc_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant__ AttnBwdProg p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  // resident 128-row tiles: dkdv -> K, V ; dq -> Q, dO.   streamed 64-row tiles (2 stages): dkdv -> Q, dO ; dq -> K, V
+  const uint32_t sR0 = smem_base, sR1 = smem_base + kTile;
+  auto sS0 = [&](int s) { return smem_base + 2 * kTile + kHalf * (2 * s); };
+  auto sS1 = [&](int s) { return smem_base + 2 * kTile + kHalf * (2 * s + 1); };
+  const uint32_t stat_off = 2 * kTile + 4 * kHalf;                     // float lse_s[2][64], delta_s[2][64]
+  float* stat = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + stat_off);
+  const uint32_t bar = smem_base + stat_off + 2048;
+  const uint32_t r_full = bar;
+  auto s_full = [&](int s) { return bar + 8u * (1 + s); };
+  auto s_empty = [&](int s) { return bar + 8u * (3 + s); };
+  const uint32_t sdp_full = bar + 8u * 5, pds_full = bar + 8u * 6, acc_done = bar + 8u * 7;
+  const uint32_t tmem_slot = bar + 8u * 8;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int Lstream = kDQ ? p.Lk : p.Lq;
+  const int n_steps = (Lstream + 63) / 64;
+
+  if (warp == 0 && lane == 0) {
+    mbar_init(r_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(s_full(s), 1); mbar_init(s_empty(s), 1); }
+    mbar_init(sdp_full, 1); mbar_init(pds_full, 8); mbar_init(acc_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t tS = tmem, tdP = tmem + 64, tA0 = tmem + 128, tA1 = tmem + 192;   // accumulators: dkdv -> dV, dK ; dq -> dQ
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(r_full, 2 * kTile);
+      if (kDQ) {
+        tma_load_3d(&maps.q, r_full, sR0, h * 64, r0, b);
+        tma_load_3d(&maps.d_o, r_full, sR1, h * 64, r0, b);
+      } else {
+        tma_load_3d(&maps.k, r_full, sR0, h * 64, r0, b);
+        tma_load_3d(&maps.v, r_full, sR1, h * 64, r0, b);
+      }
+      for (int i = 0; i < n_steps; ++i) {
+        const int s = i & 1;
+        mbar_wait(s_empty(s), ((i >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(s_full(s), 2 * kHalf);
+        if (kDQ) {
+          tma_load_3d(&maps.k, s_full(s), sS0(s), h * 64, i * 64, b);
+          tma_load_3d(&maps.v, s_full(s), sS1(s), h * 64, i * 64, b);
+        } else {
+          tma_load_3d(&maps.q, s_full(s), sS0(s), h * 64, i * 64, b);
+          tma_load_3d(&maps.d_o, s_full(s), sS1(s), h * 64, i * 64, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idescS = umma_idesc_bf16(128, 64, 0, 0);        // [128 x 64] = resident(128 rows) x streamed(64 rows)^T
+    constexpr uint32_t idescA = umma_idesc_bf16(128, 64, 0, 1);        // accumulators: A from TMEM, B MN-major
+    mbar_wait(r_full, 0);
+    for (int i = 0; i < n_steps; ++i) {
+      const int s = i & 1;
+      mbar_wait(s_full(s), (i >> 1) & 1u);
+      if (i > 0) mbar_wait(acc_done, (i - 1) & 1u);                    // P/dS columns of step i-1 fully consumed (WAR)
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t a0 = umma_smem_desc(sR0, 16, 1024), a1 = umma_smem_desc(sR1, 16, 1024);
+        const uint64_t b0 = umma_smem_desc(sS0(s), 16, 1024), b1 = umma_smem_desc(sS1(s), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tS, a0 + 2u * k, b0 + 2u * k, idescS, k > 0);     // dkdv: K Q^T ; dq: Q K^T
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tdP, a1 + 2u * k, b1 + 2u * k, idescS, k > 0);    // dkdv: V dO^T; dq: dO V^T
+        umma_commit(sdp_full);
+      }
+      __syncwarp();
+      mbar_wait(pds_full, i & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t acc = (i > 0) ? 1u : 0u;
+        if (kDQ) {
+          const uint64_t kd = umma_smem_desc(sS0(s), 4096, 1024);      // K tile [64 keys][64 dh] as MN-major B
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_ts(tA0, tS + pk_col(k), kd + 128u * k, idescA, (acc | (k > 0)) ? 1u : 0u);
+        } else {
+          const uint64_t od = umma_smem_desc(sS1(s), 4096, 1024);      // dO tile [64 q][64 dh] as MN-major B
+          const uint64_t qd = umma_smem_desc(sS0(s), 4096, 1024);      // Q  tile [64 q][64 dh] as MN-major B
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_ts(tA0, tS + pk_col(k), od + 128u * k, idescA, (acc | (k > 0)) ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_ts(tA1, tdP + pk_col(k), qd + 128u * k, idescA, (acc | (k > 0)) ? 1u : 0u);
+        }
+        umma_commit(s_empty(s));
+        umma_commit(acc_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int cw = warp - 2;                          // 0..7
+    const int quarter = warp & 3;
+    const int chalf = cw >> 2;                        // which 32 of the step's 64 columns
+    const int row = quarter * 32 + lane;
+    const int tid_c = cw * 32 + lane;                 // 0..255
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const long long stat_base = (static_cast<long long>(b) * p.H + h) * p.Lq;
+    float my_lse = 0.f, my_delta = 0.f;               // dq kernel: per-row scalars
+    if (kDQ) {
+      const int qi = r0 + row;
+      my_lse = qi < p.Lq ? p.lse[stat_base + qi] * kLog2e : INFINITY;
+      my_delta = qi < p.Lq ? p.delta[stat_base + qi] : 0.f;
+    }
+    // dkdv kernel: stage the per-column lse/delta of step 0
+    float pre = 0.f;
+    auto fetch_stat = [&](int step) -> float {
+      if (tid_c < 64) { const int qi = step * 64 + tid_c; return qi < p.Lq ? p.lse[stat_base + qi] * kLog2e : INFINITY; }
+      if (tid_c < 128) { const int qi = step * 64 + tid_c - 64; return qi < p.Lq ? p.delta[stat_base + qi] : 0.f; }
+      return 0.f;
+    };
+    if (!kDQ) {
+      pre = fetch_stat(0);
+      if (tid_c < 128) stat[tid_c] = pre;             // stage 0: [0,64) lse, [64,128) delta
+    }
+    for (int i = 0; i < n_steps; ++i) {
+      const int s = i & 1;
+      if (!kDQ) {
+        if (i + 1 < n_steps) pre = fetch_stat(i + 1);
+        named_bar_sync(1, 256);                       // stage s visible to all compute warps
+      }
+      mbar_wait(sdp_full, i & 1);
+      tc_fence_after();
+      const float* lse_s = stat + s * 128;
+      const float* del_s = lse_s + 64;
+      const int nvalid = min(64, Lstream - i * 64);   // valid streamed rows in this step (columns of S)
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {                   // 16 columns at a time
+        const int col0 = chalf * 32 + c * 16;
+        uint32_t sv[16], dv[16];
+        tmem_ld16(tS + lane_addr + static_cast<uint32_t>(col0), sv);
+        tmem_ld16(tdP + lane_addr + static_cast<uint32_t>(col0), dv);
+        tmem_ld_wait();
+        uint32_t pp[8], ds[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float pr[2], dd[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int col = col0 + 2 * e + u;
+            const float ls = kDQ ? my_lse : lse_s[col];
+            const float dl = kDQ ? my_delta : del_s[col];
+            float pv = exp2f(fmaf(__uint_as_float(sv[2 * e + u]), kLog2e, -ls));
+            if (kDQ && col >= nvalid) pv = 0.f;       // zero-filled keys would otherwise contribute exp(-lse)
+            pr[u] = pv;
+            dd[u] = pv * (__uint_as_float(dv[2 * e + u]) - dl);
+          }
+          pp[e] = pack_bf16x2(pr[0], pr[1]);
+          ds[e] = pack_bf16x2(dd[0], dd[1]);
+        }
+        // bf16 pairs for columns [col0, col0+16) -> 8 TMEM columns at pk_col(col0/16); these lie inside the fp32 columns this
+        // thread's warp has already consumed ([chalf*32, col0+16)), never in the other warp's half.
+        const uint32_t pc = pk_col(col0 >> 4);
+        if (kDQ) {
+          tmem_st8(tS + lane_addr + pc, ds);          // dq only needs dS
+        } else {
+          tmem_st8(tS + lane_addr + pc, pp);
+          tmem_st8(tdP + lane_addr + pc, ds);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      if (!kDQ && i + 1 < n_steps && tid_c < 128) stat[((i + 1) & 1) * 128 + tid_c] = pre;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+    }
+    // ---- write the accumulators
+    mbar_wait(acc_done, (n_steps - 1) & 1);
+    tc_fence_after();
+    const int ri = r0 + row;
+    const int Lres = kDQ ? p.Lq : p.Lk;
+    if (kDQ) {
+      // dQ (64 columns): warp half 0 writes columns 0..31, half 1 columns 32..63
+      uint32_t v[32];
+      tmem_ld32(tA0 + lane_addr + 32u * chalf, v);
+      tmem_ld_wait();
+      if (ri < Lres) {
+        uint4* dst = reinterpret_cast<uint4*>(p.out0 + b * p.g_bs + static_cast<long long>(ri) * p.g_rs + h * 64 + 32 * chalf);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(v[8 * e + 0]), __uint_as_float(v[8 * e + 1]));
+          u.y = pack_bf16x2(__uint_as_float(v[8 * e + 2]), __uint_as_float(v[8 * e + 3]));
+          u.z = pack_bf16x2(__uint_as_float(v[8 * e + 4]), __uint_as_float(v[8 * e + 5]));
+          u.w = pack_bf16x2(__uint_as_float(v[8 * e + 6]), __uint_as_float(v[8 * e + 7]));
+          dst[e] = u;
+        }
+      }
+    } else {
+      // half 0 writes dV (tA0), half 1 writes dK (tA1): 64 columns each
+      const uint32_t tacc = chalf == 0 ? tA0 : tA1;
+      __nv_bfloat16* base = chalf == 0 ? p.out1 + b * p.g2_bs + static_cast<long long>(ri) * p.g2_rs
+                                       : p.out0 + b * p.g_bs + static_cast<long long>(ri) * p.g_rs;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tacc + lane_addr + 32u * c, v);
+        tmem_ld_wait();
+        if (ri < Lres) {
+          uint4* dst = reinterpret_cast<uint4*>(base + h * 64 + 32 * c);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(v[8 * e + 0]), __uint_as_float(v[8 * e + 1]));
+            u.y = pack_bf16x2(__uint_as_float(v[8 * e + 2]), __uint_as_float(v[8 * e + 3]));
+            u.z = pack_bf16x2(__uint_as_float(v[8 * e + 4]), __uint_as_float(v[8 * e + 5]));
+            u.w = pack_bf16x2(__uint_as_float(v[8 * e + 6]), __uint_as_float(v[8 * e + 7]));
+            dst[e] = u;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+int attention_delta(int dtype, const ns_attn_shape& s, const void* o, const void* d_o, float* delta, cudaStream_t st);
+
+static int head_map_rows(CUtensorMap* m, const void* base, int H, int L, int B, long long bs, long long rs, int rows) {
+  uint64_t dims[3] = {(uint64_t)H * 64, (uint64_t)L, (uint64_t)B};
+  uint64_t str[2] = {(uint64_t)rs * 2, (uint64_t)bs * 2};
+  uint32_t box[3] = {64, (uint32_t)rows, 1};
+  return make_map(m, base, 3, dims, str, box);
+}
+
+int attention_bwd_tc(const ns_attn_shape& s, const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                     const float* lse, float* delta, void* dq, void* dk, void* dv, cudaStream_t st) {
+  if (!tc_eligible(s, q, k, v, o) || !al16(d_o) || !al16(dq) || !al16(dk) || !al16(dv)) return NS_ERR_UNSUPPORTED;
+  static bool attr_done = false;
+  if (!attr_done) {
+    NS_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwSmem));
+    NS_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwSmem));
+    attr_done = true;
+  }
+  int r = attention_delta(NS_BF16, s, o, d_o, delta, st);
+  if (r) return r;
+  {   // dK, dV: resident K, V (128-row boxes); streamed Q, dO (64-row boxes)
+    AttnBwdMaps maps;
+    if ((r = head_map_rows(&maps.k, k, s.H, s.Lk, s.B, s.k_bs, s.k_rs, 128))) return r;
+    if ((r = head_map_rows(&maps.v, v, s.H, s.Lk, s.B, s.v_bs, s.v_rs, 128))) return r;
+    if ((r = head_map_rows(&maps.q, q, s.H, s.Lq, s.B, s.q_bs, s.q_rs, 64))) return r;
+    if ((r = head_map_rows(&maps.d_o, d_o, s.H, s.Lq, s.B, s.o_bs, s.o_rs, 64))) return r;
+    AttnBwdProg prog{s.B, s.H, s.Lq, s.Lk, lse, delta, s.k_bs, s.k_rs, s.v_bs, s.v_rs,
+                     reinterpret_cast<__nv_bfloat16*>(dk), reinterpret_cast<__nv_bfloat16*>(dv)};
+    dim3 grid((s.Lk + 127) / 128, s.H, s.B);
+    attn_bwd_tc_kernel<false><<<grid, kBwThreads, kBwSmem, st>>>(maps, prog);
+    NS_LAUNCH_CHECK();
+  }
+  {   // dQ: resident Q, dO; streamed K, V
+    AttnBwdMaps maps;
+    if ((r = head_map_rows(&maps.q, q, s.H, s.Lq, s.B, s.q_bs, s.q_rs, 128))) return r;
+    if ((r = head_map_rows(&maps.d_o, d_o, s.H, s.Lq, s.B, s.o_bs, s.o_rs, 128))) return r;
+    if ((r = head_map_rows(&maps.k, k, s.H, s.Lk, s.B, s.k_bs, s.k_rs, 64))) return r;
+    if ((r = head_map_rows(&maps.v, v, s.H, s.Lk, s.B, s.v_bs, s.v_rs, 64))) return r;
+    AttnBwdProg prog{s.B, s.H, s.Lq, s.Lk, lse, delta, s.q_bs, s.q_rs, 0, 0, reinterpret_cast<__nv_bfloat16*>(dq), nullptr};
+    dim3 grid((s.Lq + 127) / 128, s.H, s.B);
+    attn_bwd_tc_kernel<true><<<grid, kBwThreads, kBwSmem, st>>>(maps, prog);
+    NS_LAUNCH_CHECK();
+  }
+  count(C_ATTN_TC, 2);
+  return NS_OK;
 }
 }  // namespace ns

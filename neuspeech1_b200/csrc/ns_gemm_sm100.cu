@@ -37,8 +37,8 @@ static PFN_encodeTiled get_encode() {
 }
 
 // bf16 tensor map, 128B swizzle, zero OOB fill.  dims[0] is the contiguous dim; strides in BYTES for dims 1..rank-1.
-static int make_map(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_b,
-                    const uint32_t* box) {
+int make_map(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_b,
+             const uint32_t* box) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
