@@ -171,7 +171,6 @@ def run_ours(args):
     x_host, labels_host = synthetic_host_batch(dims, B, L, seed=100 + rank)
     x_host = x_host.pin_memory(); labels_host = labels_host.pin_memory()
     x_dev = x_host.to(dev); labels_dev = labels_host.to(dev)
-    x_stage = torch.empty_like(x_dev); labels_stage = torch.empty_like(labels_dev)
     lr = 1e-3
 
     def allreduce(flat):
@@ -182,11 +181,40 @@ def run_ours(args):
     def step_resident():
         return eng.train_step(x_dev, labels_dev, lr=lr, all_reduce=allreduce if world > 1 else None)
 
+    # e2e: host (pinned) batch -> H2D on a copy stream (double buffered, prefetching step i+1 during step i) -> training step
+    # through the module API -> D2H of the loss (read back one step later so the host never stalls the launch queue).
+    copy_stream = torch.cuda.Stream(device=dev)
+    stages = [(torch.empty_like(x_dev), torch.empty_like(labels_dev)) for _ in range(2)]
+    ev_ready = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    ev_loss = [torch.cuda.Event() for _ in range(2)]
+    e2e_state = {"i": 0, "losses": []}
+
+    def h2d(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_free[slot])
+            stages[slot][0].copy_(x_host, non_blocking=True)
+            stages[slot][1].copy_(labels_host, non_blocking=True)
+            ev_ready[slot].record(copy_stream)
+
     def step_e2e():
-        x_stage.copy_(x_host, non_blocking=True)
-        labels_stage.copy_(labels_host, non_blocking=True)
-        out = model.training_step(x_stage, labels_stage, lr=lr, all_reduce=allreduce if world > 1 else None)
-        return float(out.loss)                                 # D2H read of the step's result
+        i = e2e_state["i"]
+        slot = i & 1
+        cur = torch.cuda.current_stream()
+        if i == 0:
+            ev_free[0].record(cur); ev_free[1].record(cur)
+            h2d(0)
+        h2d(slot ^ 1)                                          # prefetch the next step's batch
+        cur.wait_event(ev_ready[slot])
+        out = model.training_step(stages[slot][0], stages[slot][1], lr=lr, all_reduce=allreduce if world > 1 else None)
+        ev_free[slot].record(cur)
+        loss_host[slot].copy_(out.loss, non_blocking=True)     # D2H of the step's result
+        ev_loss[slot].record(cur)
+        if i > 0:
+            ev_loss[slot ^ 1].synchronize()
+            e2e_state["losses"].append(float(loss_host[slot ^ 1]))
+        e2e_state["i"] = i + 1
 
     def barrier():
         if world > 1:
@@ -220,6 +248,7 @@ def run_ours(args):
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps) / args.steps
+    assert all(l == l for l in e2e_state["losses"]), "NaN loss in the e2e run"
     e2e_value = world * B * 1e3 / ms_e2e
 
     line = None

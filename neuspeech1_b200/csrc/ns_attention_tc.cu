@@ -29,6 +29,12 @@ constexpr int kTile = 128 * 64 * 2;                          // one [128][64] bf
 constexpr int kAtSmem = kTile * 5 + 1024 + 256;
 constexpr float kLog2e = 1.4426950408889634f;
 
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __global__ void __launch_bounds__(kAtThreads, 2)
 attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnFwdProg p) {
   extern __shared__ uint8_t smem_raw[];
@@ -120,52 +126,72 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int nvalid = min(128, p.Lk - j * 128);
+      const bool full = nvalid == 128;
       uint32_t v[32];
-      float mx = -INFINITY;
+      if (j == 0) {                                   // first tile: the row max has to be known before the exponentials
+        float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        tmem_ld32(tS + lane_addr + 32u * c, v);
-        tmem_ld_wait();
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld32(tS + lane_addr + 32u * c, v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
-      }
-      if (j == 0) {
+          for (int i = 0; i < 32; ++i)
+            if (full || c * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
         m_used = mx;
-      } else {
-        const bool need = mx > m_used + 5.545177f;                       // 8 / log2(e)
-        if (__any_sync(0xffffffffu, need)) {
-          const float m_new = fmaxf(m_used, mx);
-          const float sc = exp2f((m_used - m_new) * kLog2e);
+      }
+      // One pass: p = exp2((s - m_used) * log2e) with the max of the PREVIOUS tiles, tracking this tile's max on the side.
+      // Only if some row's max grew by more than 8 (log2 units) the accumulator is rescaled and the pass is redone.
+      float l_tile = 0.f, mx = -INFINITY;
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        const float mb = m_used * kLog2e;
+        l_tile = 0.f;
 #pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            tmem_ld32(tO + lane_addr + 32u * c, v);
-            tmem_ld_wait();
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld32(tS + lane_addr + 32u * c, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+          if (full) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * sc);
-            tmem_st32(tO + lane_addr + 32u * c, v);
+            for (int i = 0; i < 16; ++i) {
+              const float s0 = __uint_as_float(v[2 * i]), s1 = __uint_as_float(v[2 * i + 1]);
+              mx = fmaxf(mx, fmaxf(s0, s1));
+              const float p0 = fast_exp2(fmaf(s0, kLog2e, -mb)), p1 = fast_exp2(fmaf(s1, kLog2e, -mb));
+              l_tile += p0 + p1;
+              pk[i] = pack_bf16x2(p0, p1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const bool ok0 = c * 32 + 2 * i < nvalid, ok1 = c * 32 + 2 * i + 1 < nvalid;
+              const float s0 = __uint_as_float(v[2 * i]), s1 = __uint_as_float(v[2 * i + 1]);
+              if (ok0) mx = fmaxf(mx, s0);
+              if (ok1) mx = fmaxf(mx, s1);
+              const float p0 = ok0 ? fast_exp2(fmaf(s0, kLog2e, -mb)) : 0.f;
+              const float p1 = ok1 ? fast_exp2(fmaf(s1, kLog2e, -mb)) : 0.f;
+              l_tile += p0 + p1;
+              pk[i] = pack_bf16x2(p0, p1);
+            }
           }
-          l *= sc;
-          m_used = m_new;
+          tmem_st16(tP + lane_addr + 16u * c, pk);
         }
-      }
-      const float mb = m_used * kLog2e;
+        const bool need = mx > m_used + 5.545177f;     // 8 / log2(e)
+        if (attempt == 1 || !__any_sync(0xffffffffu, need)) break;
+        const float m_new = fmaxf(m_used, mx);
+        const float sc = fast_exp2((m_used - m_new) * kLog2e);
+        tmem_st_wait();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        tmem_ld32(tS + lane_addr + 32u * c, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld32(tO + lane_addr + 32u * c, v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), kLog2e, -mb));
-          float p1 = exp2f(fmaf(__uint_as_float(v[2 * i + 1]), kLog2e, -mb));
-          if (c * 32 + 2 * i >= nvalid) p0 = 0.f;
-          if (c * 32 + 2 * i + 1 >= nvalid) p1 = 0.f;
-          l += p0 + p1;
-          pk[i] = pack_bf16x2(p0, p1);
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * sc);
+          tmem_st32(tO + lane_addr + 32u * c, v);
         }
-        tmem_st16(tP + lane_addr + 16u * c, pk);
+        l *= sc;
+        m_used = m_new;
       }
+      l += l_tile;
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -422,7 +448,7 @@ attn_bwd_tc_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_consta
             const int col = col0 + 2 * e + u;
             const float ls = kDQ ? my_lse : lse_s[col];
             const float dl = kDQ ? my_delta : del_s[col];
-            float pv = exp2f(fmaf(__uint_as_float(sv[2 * e + u]), kLog2e, -ls));
+            float pv = fast_exp2(fmaf(__uint_as_float(sv[2 * e + u]), kLog2e, -ls));
             if (kDQ && col >= nvalid) pv = 0.f;       // zero-filled keys would otherwise contribute exp(-lse)
             pr[u] = pv;
             dd[u] = pv * (__uint_as_float(dv[2 * e + u]) - dl);

@@ -95,7 +95,7 @@ struct TileProg {
   long long out_bs, out_rs, out_off, ldd;
   void* D;
   EpiDev epi;
-  int vec_out, vec_aux, vec_res;
+  int vec_out, vec_aux, vec_res, vec_bias;
 };
 
 struct Maps {
@@ -310,9 +310,18 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
           if (e.bias) {
+            if (ncols == 32 && p.vec_bias) {
+              const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);   // col0 % 32 == 0, bias 16B-aligned (checked on host)
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) x[j] += __ldg(e.bias + col0 + j);
+              for (int j = 0; j < 8; ++j) {
+                const float4 bb = __ldg(b4 + j);
+                x[4 * j] += bb.x; x[4 * j + 1] += bb.y; x[4 * j + 2] += bb.z; x[4 * j + 3] += bb.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) x[j] += __ldg(e.bias + col0 + j);
+            }
           }
           if (col0 < e.alpha_cols) {
 #pragma unroll
@@ -324,13 +333,13 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
             if (e.aux_out && valid)
               store32_bf16(reinterpret_cast<__nv_bfloat16*>(e.aux_out) + row * e.ldaux + col0, p.vec_aux && full, ncols, x);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+            for (int j = 0; j < 32; ++j) x[j] = gelu_fast(x[j]);
           } else if (e.act == NS_ACT_DGELU) {
             if (valid) {
               float z[32];
               load32_bf16(reinterpret_cast<const __nv_bfloat16*>(e.aux_in) + row * e.ldaux + col0, p.vec_aux && full, ncols, z);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] *= dgelu_erf(z[j]);
+              for (int j = 0; j < 32; ++j) x[j] *= dgelu_fast(z[j]);
             }
           }
           if (e.residual && valid) {
@@ -372,6 +381,7 @@ struct TnProg {
   long long si, sj, stap;     // output strides
   float* G;
   float alpha;
+  int stage_bytes;            // 16 KB (X) + 8 KB per 64 columns of Y
 };
 struct TnMaps {
   CUtensorMap x;
@@ -389,7 +399,7 @@ gemm_tn_kernel(const __grid_constant__ TnMaps maps, const __grid_constant__ TnPr
   constexpr int S = kTnStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + S * kTnStageBytes;
+  const uint32_t bar_base = smem_base + S * p.stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
   const uint32_t tfull_bar = bar_base + 8u * (2 * S);
@@ -438,7 +448,7 @@ gemm_tn_kernel(const __grid_constant__ TnMaps maps, const __grid_constant__ TnPr
         const int b = blk / p.blocks_per_batch;
         const int t0 = (blk % p.blocks_per_batch) * 64;
         mbar_wait(empty_bar(stage), phase ^ 1u);
-        const uint32_t sa = smem_base + stage * kTnStageBytes;
+        const uint32_t sa = smem_base + stage * p.stage_bytes;
         const uint32_t sb = sa + kTnABytes;
         mbar_expect_tx(full_bar(stage), stage_tx);
         tma_load_4d(&maps.x, full_bar(stage), sa, i0, 0, t0, b);
@@ -457,7 +467,7 @@ gemm_tn_kernel(const __grid_constant__ TnMaps maps, const __grid_constant__ TnPr
       mbar_wait(full_bar(stage), phase);
       tc_fence_after();
       if (lane == 0) {
-        const uint32_t sa = smem_base + stage * kTnStageBytes;
+        const uint32_t sa = smem_base + stage * p.stage_bytes;
         const uint32_t sb = sa + kTnABytes;
         // MN-major: LBO = distance between 64-element MN groups (8192 B), SBO = distance between 8-row K groups (1024 B)
         const uint64_t adesc = umma_smem_desc(sa, 8192, 1024);
@@ -536,6 +546,7 @@ static int dispatch_nt(const Maps& maps, TileProg& prog, cudaStream_t st) {
 
 static void fill_epi(TileProg& prog, const EpiDev& e) {
   prog.epi = e;
+  prog.vec_bias = e.bias && aligned16(e.bias);
   const bool f32 = e.out_f32;
   prog.vec_out = aligned16(prog.D) && (prog.ldd % (f32 ? 4 : 8) == 0);
   const void* aux = e.act == NS_ACT_GELU ? e.aux_out : e.aux_in;
@@ -718,7 +729,9 @@ static int launch_tn(const TnMaps& maps, TnProg& p, cudaStream_t st) {
   if (nsplit < 1) nsplit = 1;
   p.blocks_per_split = (p.total_blocks + nsplit - 1) / nsplit;
   p.nsplit = (p.total_blocks + p.blocks_per_split - 1) / p.blocks_per_split;
-  gemm_tn_kernel<<<tiles * p.nsplit, kTnThreads, kTnSmemBytes, st>>>(maps, p);
+  p.stage_bytes = kTnABytes + ((p.bj + 63) / 64) * 8192;
+  const int smem = kTnStages * p.stage_bytes + 1024 + 256;
+  gemm_tn_kernel<<<tiles * p.nsplit, kTnThreads, smem, st>>>(maps, p);
   NS_LAUNCH_CHECK();
   count(C_WGRAD_TC);
   return NS_OK;
