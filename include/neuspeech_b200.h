@@ -107,6 +107,17 @@ int ns_attention_fwd(int dtype, const ns_attn_shape* s, const void* q, const voi
 /* do has o's strides; dq/dk/dv have q/k/v's strides.  delta (B,H,Lq) fp32 is scratch. */
 int ns_attention_bwd(int dtype, const ns_attn_shape* s, const void* q, const void* k, const void* v, const void* o,
                      const void* d_o, const float* lse, float* delta, void* dq, void* dk, void* dv, void* stream);
+/* Same gradients through the fused single-pass kernel (exp evaluated once, dQ accumulated in fp32 with TMA reduce-add) when
+ * the shape qualifies (bf16, head_dim 64, non-causal) and `workspace` (1024-byte aligned device memory) holds at least
+ * ns_attention_bwd_workspace_bytes(s) bytes; otherwise it behaves exactly like ns_attention_bwd.  The library never
+ * allocates: the caller owns the workspace (contents are scratch). */
+long long ns_attention_bwd_workspace_bytes(const ns_attn_shape* s);
+/* Developer aid: when a device buffer of 4*512*2 int64 is registered, CTA (0,0,0) of the fused backward records a
+ * (tag, clock64) timeline of its warp roles into it; NULL (the default) disables it. */
+int ns_debug_attn_trace(long long* device_buffer);
+int ns_attention_bwd_ws(int dtype, const ns_attn_shape* s, const void* q, const void* k, const void* v, const void* o,
+                        const void* d_o, const float* lse, float* delta, void* dq, void* dk, void* dv, void* workspace,
+                        long long workspace_bytes, void* stream);
 
 /* ---- decoder embedding: h[b,l,:] = E[ids[b,l]] + P[pos0 + l]   (utils/load_model.py:646-660) */
 int ns_embed(int dtype, int B, int L, int d, const long long* ids, const void* E, const void* P, int pos0, void* h,

@@ -56,6 +56,8 @@ SIGNATURES = {
     "ns_layernorm_bwd": [c_i, c_ll, c_i, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "ns_attention_fwd": [c_i, C.POINTER(AttnShape), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "ns_attention_bwd": [c_i, C.POINTER(AttnShape), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "ns_attention_bwd_ws": [c_i, C.POINTER(AttnShape), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_vp],
+    "ns_debug_attn_trace": [c_vp],
     "ns_embed": [c_i, c_i, c_i, c_i, c_vp, c_vp, c_vp, c_i, c_vp, c_vp],
     "ns_cross_entropy": [c_i, c_ll, c_i, c_ll, c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_f, c_vp],
     "ns_greedy_pick": [c_i, c_i, c_i, c_ll, c_vp, c_vp, c_i, c_i, c_i, c_vp, c_vp, c_vp],
@@ -92,6 +94,8 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = c_i
+    lib.ns_attention_bwd_workspace_bytes.argtypes = [C.POINTER(AttnShape)]
+    lib.ns_attention_bwd_workspace_bytes.restype = c_ll
     lib.ns_last_error_string.argtypes = []
     lib.ns_last_error_string.restype = C.c_char_p
     _lib = lib

@@ -36,6 +36,11 @@ int attention_fwd_tc(const ns_attn_shape& s, const void* q, const void* k, const
 int attention_bwd_tc(const ns_attn_shape& s, const void* q, const void* k, const void* v, const void* o, const void* d_o,
                      const float* lse, float* delta, void* dq, void* dk, void* dv, cudaStream_t st);
 
+size_t attention_bwd_fused_ws(const ns_attn_shape& s);
+int attention_bwd_fused(const ns_attn_shape& s, const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                        const float* lse, float* delta, void* dq, void* dk, void* dv, void* ws, size_t ws_bytes, cudaStream_t st);
+
+void set_attn_trace(long long* p);
 static bool want_fast(int dtype) { return dtype == NS_BF16 && g_path != NS_PATH_SIMT; }
 static int fast_required_failed(const char* what) {
   set_error("%s: NS_PATH_FAST requested but the shape/dtype does not qualify for the tcgen05 path", what);
@@ -244,6 +249,29 @@ int ns_attention_bwd(int dtype, const ns_attn_shape* s, const void* q, const voi
     if (g_path == NS_PATH_FAST) return fast_required_failed("ns_attention_bwd");
   }
   return attention_bwd_simt(dtype, *s, q, k, v, o, d_o, lse, delta, dq, dk, dv, st);
+}
+
+int ns_debug_attn_trace(long long* device_buffer) {
+  set_attn_trace(device_buffer);
+  return NS_OK;
+}
+
+long long ns_attention_bwd_workspace_bytes(const ns_attn_shape* s) {
+  if (!s || check_attn(s)) return 0;
+  return static_cast<long long>(attention_bwd_fused_ws(*s));
+}
+
+int ns_attention_bwd_ws(int dtype, const ns_attn_shape* s, const void* q, const void* k, const void* v, const void* o,
+                        const void* d_o, const float* lse, float* delta, void* dq, void* dk, void* dv, void* workspace,
+                        long long workspace_bytes, void* stream) {
+  NS_CHECK_ARG(valid_dtype(dtype) && q && k && v && o && d_o && lse && delta && dq && dk && dv, "ns_attention_bwd_ws: bad arguments");
+  if (int r = check_attn(s)) return r;
+  if (want_fast(dtype) && workspace && workspace_bytes > 0) {
+    const int r = attention_bwd_fused(*s, q, k, v, o, d_o, lse, delta, dq, dk, dv, workspace, static_cast<size_t>(workspace_bytes),
+                                      reinterpret_cast<cudaStream_t>(stream));
+    if (r != NS_ERR_UNSUPPORTED) return r;
+  }
+  return ns_attention_bwd(dtype, s, q, k, v, o, d_o, lse, delta, dq, dk, dv, stream);
 }
 
 }  // extern "C"

@@ -73,7 +73,7 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
   const uint32_t tS = tmem, tP = tmem + 128, tO = tmem + 192;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(q_full, kTile);
       tma_load_3d(&maps.q, q_full, sQ, h * 64, q0, b);
       for (int j = 0; j < n_kv; ++j) {
@@ -96,7 +96,7 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
       const uint32_t ph = (j >> 1) & 1u;
       mbar_wait(k_full(s), ph);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint64_t qd = umma_smem_desc(sQ, 16, 1024), kd = umma_smem_desc(sK(s), 16, 1024);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_f16(tS, qd + 2u * k, kd + 2u * k, idescS, k > 0);
@@ -108,7 +108,7 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
       tc_fence_after();
       mbar_wait(v_full(s), ph);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint64_t vd = umma_smem_desc(sV(s), 8192, 1024);
 #pragma unroll
         for (int k = 0; k < 8; ++k) umma_f16_ts(tO, tP + 8u * k, vd + 128u * k, idescO, (j > 0 || k > 0) ? 1u : 0u);
@@ -334,7 +334,7 @@ attn_bwd_tc_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_consta
   const uint32_t tS = tmem, tdP = tmem + 64, tA0 = tmem + 128, tA1 = tmem + 192;   // accumulators: dkdv -> dV, dK ; dq -> dQ
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(r_full, 2 * kTile);
       if (kDQ) {
         tma_load_3d(&maps.q, r_full, sR0, h * 64, r0, b);
@@ -365,7 +365,7 @@ attn_bwd_tc_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_consta
       mbar_wait(s_full(s), (i >> 1) & 1u);
       if (i > 0) mbar_wait(acc_done, (i - 1) & 1u);                    // P/dS columns of step i-1 fully consumed (WAR)
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint64_t a0 = umma_smem_desc(sR0, 16, 1024), a1 = umma_smem_desc(sR1, 16, 1024);
         const uint64_t b0 = umma_smem_desc(sS0(s), 16, 1024), b1 = umma_smem_desc(sS1(s), 16, 1024);
 #pragma unroll
@@ -377,7 +377,7 @@ attn_bwd_tc_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_consta
       __syncwarp();
       mbar_wait(pds_full, i & 1);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t acc = (i > 0) ? 1u : 0u;
         if (kDQ) {
           const uint64_t kd = umma_smem_desc(sS0(s), 4096, 1024);      // K tile [64 keys][64 dh] as MN-major B

@@ -37,8 +37,18 @@ static PFN_encodeTiled get_encode() {
 }
 
 // bf16 tensor map, 128B swizzle, zero OOB fill.  dims[0] is the contiguous dim; strides in BYTES for dims 1..rank-1.
+static int make_map_t(CUtensorMap* out, CUtensorMapDataType dt, const void* ptr, int rank, const uint64_t* dims,
+                      const uint64_t* strides_b, const uint32_t* box);
 int make_map(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_b,
              const uint32_t* box) {
+  return make_map_t(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, ptr, rank, dims, strides_b, box);
+}
+int make_map_f32(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_b,
+                 const uint32_t* box) {
+  return make_map_t(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, ptr, rank, dims, strides_b, box);
+}
+static int make_map_t(CUtensorMap* out, CUtensorMapDataType dt, const void* ptr, int rank, const uint64_t* dims,
+                      const uint64_t* strides_b, const uint32_t* box) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -64,7 +74,7 @@ int make_map(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, 
     set_error("tensor map base pointer not 16-byte aligned");
     return NS_ERR_ARG;
   }
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gd, gs, bx, es,
+  CUresult r = enc(out, dt, rank, const_cast<void*>(ptr), gd, gs, bx, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -215,7 +225,7 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
 
   if (warp == 0) {
     // ================================================================ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -257,7 +267,7 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
         for (int kb = 0; kb < sg.kblocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
             const uint32_t sb = sa + kABytes;
             const int ksteps = (kb == sg.kblocks - 1) ? sg.last_ksteps : 4;
@@ -274,7 +284,7 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
       }
-      if (lane == 0) umma_commit(tfull_bar(acc));
+      if (elect_one()) umma_commit(tfull_bar(acc));
       __syncwarp();
     }
   } else if (warp >= 4) {
@@ -441,7 +451,7 @@ gemm_tn_kernel(const __grid_constant__ TnMaps maps, const __grid_constant__ TnPr
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int blk = blk0; blk < blk1; ++blk) {
@@ -466,7 +476,7 @@ gemm_tn_kernel(const __grid_constant__ TnMaps maps, const __grid_constant__ TnPr
     for (int blk = blk0; blk < blk1; ++blk) {
       mbar_wait(full_bar(stage), phase);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t sa = smem_base + stage * p.stage_bytes;
         const uint32_t sb = sa + kTnABytes;
         // MN-major: LBO = distance between 64-element MN groups (8192 B), SBO = distance between 8-row K groups (1024 B)
@@ -483,7 +493,7 @@ gemm_tn_kernel(const __grid_constant__ TnMaps maps, const __grid_constant__ TnPr
       __syncwarp();
       if (++stage == S) { stage = 0; phase ^= 1u; }
     }
-    if (lane == 0) umma_commit(tfull_bar);
+    if (elect_one()) umma_commit(tfull_bar);
     __syncwarp();
   } else if (warp >= 4) {
     const int q = warp & 3;

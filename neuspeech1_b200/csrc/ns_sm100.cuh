@@ -9,6 +9,20 @@ namespace sm100 {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
+// One lane of a converged warp.  ptxas recognises the elect.sync predicate and emits the single-thread uniform-datapath
+// instructions (UTCHMMA / UTMALDG / UTCBAR) straight; behind a plain `lane == 0` test it wraps each of them in an
+// ELECT ... BRA.U.ANY emulation loop with R2UR moves, ~60 issue cycles per MMA.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -36,6 +50,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Wait for several barriers at once: the try_waits are issued back to back, so already-completed barriers cost one
+// ~90-cycle probe latency in total instead of one each.  `use_x == false` skips that barrier.
+__device__ __forceinline__ void mbar_wait3(uint32_t a, uint32_t pa, bool use_b, uint32_t b, uint32_t pb, bool use_c, uint32_t c,
+                                           uint32_t pc) {
+  bool oa = mbar_try_wait(a, pa);
+  bool ob = use_b ? mbar_try_wait(b, pb) : true;
+  bool oc = use_c ? mbar_try_wait(c, pc) : true;
+  while (!(oa && ob && oc)) {
+    if (!oa) oa = mbar_try_wait(a, pa);
+    if (!ob) ob = mbar_try_wait(b, pb);
+    if (!oc) oc = mbar_try_wait(c, pc);
+  }
+}
+__device__ __forceinline__ void mbar_wait2(uint32_t a, uint32_t pa, uint32_t b, uint32_t pb) { mbar_wait3(a, pa, true, b, pb, false, 0, 0); }
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3) {
   asm volatile(
@@ -48,6 +77,29 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+// 1-D bulk copy global -> shared (16-byte aligned, size multiple of 16), completion on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// shared -> global tile with element-wise add in L2 (fp32 accumulation buffers); bulk-group completion
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (TMA / tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -172,4 +224,6 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn_ma
 
 // bf16 tensor map with 128B swizzle and zero OOB fill (ns_gemm_sm100.cu).  dims[0] contiguous; strides in bytes for dims 1..
 int make_map(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_b, const uint32_t* box);
+// same for fp32 elements (inner box <= 32 elements = one 128-byte swizzle row)
+int make_map_f32(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_b, const uint32_t* box);
 }  // namespace ns

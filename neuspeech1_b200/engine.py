@@ -147,6 +147,7 @@ class WhisperEEGEngine:
         self.device = torch.device(device)
         self.ws = Workspace(self.device)
         self.has_lora = lora is not None
+        self.fuse_cross_bwd = True       # decoder cross-attention backward through the fused single-pass kernel
         self.layout = TrainableLayout(dims, with_lora=self.has_lora)
         self.flat = torch.zeros(self.layout.size, dtype=torch.float32, device=self.device)
         self.grad = torch.zeros_like(self.flat)
@@ -519,8 +520,8 @@ class WhisperEEGEngine:
             doc = ws.get("d_doc", (ML, d), dt)
             ops.gemm_nt(dh2, W[k + ".woc_t"], doc, self._ep())
             dqc = ws.get("d_dqc", (ML, d), dt)
-            ops.attention_bwd(shp_c, g("d_qc"), kv_all[:, i * 2 * d:], kv_all[:, i * 2 * d + d:], g("d_oc"), doc, g("d_lsec"), delta,
-                              dqc, dkv_all[:, i * 2 * d:], dkv_all[:, i * 2 * d + d:])
+            ops.attention_bwd_ws(shp_c, g("d_qc"), kv_all[:, i * 2 * d:], kv_all[:, i * 2 * d + d:], g("d_oc"), doc, g("d_lsec"), delta,
+                                 dqc, dkv_all[:, i * 2 * d:], dkv_all[:, i * 2 * d + d:], self._attn_ws(shp_c) if self.fuse_cross_bwd else None)
             ops.gemm_nt(dqc, W[k + ".wqc_t"], du, self._ep())
             dh1 = ws.get("d_dh_c", (ML, d), dt)
             ops.layernorm_bwd(du, g("d_h1"), W[k + ".ln2.g"], g("d_mean2"), g("d_rstd2"), dh1, dres=dh2)
@@ -582,7 +583,8 @@ class WhisperEEGEngine:
             # attention
             dqkv = ws.get("dqkv", (M, 3 * d), dt)
             qkv = g("qkv")
-            ops.attention_bwd(shp, qkv, qkv[:, d:], qkv[:, 2 * d:], g("o"), do, g("lse"), delta, dqkv, dqkv[:, d:], dqkv[:, 2 * d:])
+            ops.attention_bwd_ws(shp, qkv, qkv[:, d:], qkv[:, 2 * d:], g("o"), do, g("lse"), delta, dqkv, dqkv[:, d:], dqkv[:, 2 * d:],
+                                 self._attn_ws(shp))
             # q/k/v projections (dq carries the Dh^-0.5 of the forward: folded into alpha / pre-scaled transposed weight)
             du1 = du2
             if self.has_lora:
@@ -612,6 +614,18 @@ class WhisperEEGEngine:
         ops.conv3_dgrad(dzB, W["stemB.wt"], dzA, 2, self._ep(act=ACT_DGELU, aux_in=ws.bufs["zA"], ldaux=d))
         self._conv_wgrad("model.encoder.conv1.0", dzA, xcl, 1, dm.eeg_ch, Cp)
         return self.grad
+
+    def _attn_ws(self, shp) -> Optional[torch.Tensor]:
+        """1024-byte aligned scratch for the fused attention backward (fp32 dQ accumulator + tile-major softmax statistics);
+        None when the shape does not qualify (fp32 storage, causal, head_dim != 64) and the two-kernel path runs."""
+        if self.dtype != torch.bfloat16:
+            return None
+        n = ops.attention_bwd_workspace_bytes(shp)
+        if n <= 0:
+            return None
+        buf = self.ws.get(f"attn_bwd_ws.{n}", (n + 1024,), torch.uint8)
+        off = (-buf.data_ptr()) % 1024
+        return buf[off: off + n]
 
     def _conv_wgrad(self, name: str, dz: torch.Tensor, xin: torch.Tensor, stride: int, cin: int, cp: int):
         d = self.dims.d_model

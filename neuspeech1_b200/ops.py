@@ -151,6 +151,17 @@ def attention_bwd(shape: AttnShape, q, k, v, o, d_o, lse, delta, dq, dk, dv):
     _call("ns_attention_bwd", (10.0 * shape.B * shape.H * shape.Lq * shape.Lk * shape.Dh * (0.5 if shape.causal else 1.0), 0), ns_dtype(q), C.byref(shape), _p(q), _p(k), _p(v), _p(o), _p(d_o), _p(lse), _p(delta), _p(dq), _p(dk), _p(dv), _stream())
 
 
+def attention_bwd_workspace_bytes(shape: AttnShape) -> int:
+    return int(lib().ns_attention_bwd_workspace_bytes(C.byref(shape)))
+
+
+def attention_bwd_ws(shape: AttnShape, q, k, v, o, d_o, lse, delta, dq, dk, dv, ws: Optional[torch.Tensor]):
+    """attention_bwd through the fused single-pass kernel when `ws` (uint8 device buffer, >= attention_bwd_workspace_bytes)
+    is given and the shape qualifies; identical results contract."""
+    nbytes = 0 if ws is None else ws.numel() * ws.element_size()
+    _call("ns_attention_bwd_ws", (10.0 * shape.B * shape.H * shape.Lq * shape.Lk * shape.Dh * (0.5 if shape.causal else 1.0), 0), ns_dtype(q), C.byref(shape), _p(q), _p(k), _p(v), _p(o), _p(d_o), _p(lse), _p(delta), _p(dq), _p(dk), _p(dv), _p(ws), nbytes, _stream())
+
+
 def embed(ids, E, P, pos0: int, h):
     B, L = ids.shape
     _call("ns_embed", (0, 0), ns_dtype(E), B, L, E.shape[1], _p(ids), _p(E), _p(P), pos0, _p(h), _stream())

@@ -1,0 +1,170 @@
+"""Kernel micro-benchmarks at the encoder shapes of the headline workload (B=64, S=1500, d=512, H=8, F=2048, r=32).
+
+    python tools/kbench.py [attn] [gemm] [ln] [--B 64] [--iters 20]
+
+Every timing is CUDA events on the launching stream after 3 warm-up calls; inputs (hundreds of MB) exceed the L2.  Each
+attention variant is first checked against a torch fp32 restatement on a B=2 slice."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+
+from neuspeech1_b200 import ops
+from neuspeech1_b200._abi import ACT_DGELU, ACT_GELU
+
+DEV = torch.device("cuda")
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def timeit(fn, iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def rel(a, b):
+    a = a.double(); b = b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def attn_ref(q, k, v):
+    qh, kh, vh = (t.permute(0, 2, 1, 3) for t in (q, k, v))
+    w = qh @ kh.transpose(2, 3)
+    return (w.softmax(-1) @ vh).permute(0, 2, 1, 3), torch.logsumexp(w, dim=-1)
+
+
+def bench_attn(B, iters, out):
+    H, S, Dh = 8, 1500, 64
+    d = H * Dh
+    g = torch.Generator().manual_seed(0)
+    qkv = (torch.randn(B * S, 3 * d, generator=g) * 0.5).to(DEV, torch.bfloat16)
+    do = torch.randn(B * S, d, generator=g).to(DEV, torch.bfloat16)
+    q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
+    shp = ops.attn_shape(B, H, S, S, Dh, False, S * 3 * d, 3 * d, S * 3 * d, 3 * d, S * 3 * d, 3 * d, S * d, d)
+    o = torch.empty(B * S, d, dtype=torch.bfloat16, device=DEV)
+    lse = torch.empty(B, H, S, device=DEV)
+    delta = torch.empty(B * H * S, device=DEV)
+    dqkv = torch.zeros(B * S, 3 * d, dtype=torch.bfloat16, device=DEV)
+    dq, dk, dv = dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:]
+    ws = torch.empty(ops.attention_bwd_workspace_bytes(shp) + 1024, dtype=torch.uint8, device=DEV)
+    off = (-ws.data_ptr()) % 1024
+    ws = ws[off: off + ops.attention_bwd_workspace_bytes(shp)]
+    ops.attention_fwd(shp, q, k, v, o, lse)
+    # ---- correctness on the first 2 batch entries
+    nb = min(B, 2)
+    qf = q[: nb * S].float().reshape(nb, S, H, Dh).requires_grad_(True)
+    kf = k[: nb * S].float().reshape(nb, S, H, Dh).requires_grad_(True)
+    vf = v[: nb * S].float().reshape(nb, S, H, Dh).requires_grad_(True)
+    ref, lse_ref = attn_ref(qf, kf, vf)
+    ref.backward(do[: nb * S].float().view(nb, S, H, Dh))
+    res = {"fwd_o": rel(o[: nb * S].float().view(nb, S, H, Dh), ref), "fwd_lse": rel(lse[:nb], lse_ref)}
+    for name, fn in (("bwd2k", lambda: ops.attention_bwd(shp, q, k, v, o, do, lse, delta, dq, dk, dv)),
+                     ("bwdfused", lambda: ops.attention_bwd_ws(shp, q, k, v, o, do, lse, delta, dq, dk, dv, ws))):
+        dqkv.zero_()
+        fn()
+        torch.cuda.synchronize()
+        res[name + "_dq"] = rel(dq[: nb * S].float().reshape(nb, S, H, Dh), qf.grad)
+        res[name + "_dk"] = rel(dk[: nb * S].float().reshape(nb, S, H, Dh), kf.grad)
+        res[name + "_dv"] = rel(dv[: nb * S].float().reshape(nb, S, H, Dh), vf.grad)
+    fl = 4.0 * B * H * S * S * Dh
+    t = timeit(lambda: ops.attention_fwd(shp, q, k, v, o, lse), iters)
+    res["fwd_ms"] = t; res["fwd_tflops"] = fl / t / 1e9
+    t = timeit(lambda: ops.attention_bwd(shp, q, k, v, o, do, lse, delta, dq, dk, dv), iters)
+    res["bwd2k_ms"] = t; res["bwd2k_tflops"] = 2.5 * fl / t / 1e9
+    t = timeit(lambda: ops.attention_bwd_ws(shp, q, k, v, o, do, lse, delta, dq, dk, dv, ws), iters)
+    res["bwdfused_ms"] = t; res["bwdfused_tflops"] = 2.5 * fl / t / 1e9
+    out["attn"] = res
+
+
+def bench_gemm(B, iters, out):
+    S, d, F, r = 1500, 512, 2048, 32
+    M = B * S
+    g = torch.Generator().manual_seed(1)
+    mk = lambda *s: (torch.randn(*s, generator=g) * 0.05).to(DEV, torch.bfloat16)
+    x512, x2048 = mk(M, d), mk(M, F)
+    res = {}
+
+    def run(name, a, w, N, ep_kw=None, a2=None, w2=None, k2=0, outbuf=None):
+        o = outbuf if outbuf is not None else torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+        ep = ops.epilogue(**(ep_kw or {}))
+        fn = lambda: ops.gemm_nt(a, w, o, ep, a2=a2, w2=w2, k2=k2)
+        t = timeit(fn, iters)
+        fl = 2.0 * M * N * (a.shape[1] + k2)
+        res[name] = {"ms": t, "tflops": fl / t / 1e9}
+
+    bias512 = torch.zeros(d, device=DEV); bias2048 = torch.zeros(F, device=DEV); bias1536 = torch.zeros(3 * d, device=DEV)
+    t32, t96 = mk(M, r), mk(M, 3 * r)
+    z1 = torch.empty(M, F, dtype=torch.bfloat16, device=DEV)
+    res_h = mk(M, d)
+    run("qkv+lora", x512, mk(3 * d, d), 3 * d, dict(bias=bias1536, alpha=0.125, alpha_cols=d, a2_group_cols=d), a2=t96, w2=mk(3 * d, r), k2=r)
+    run("out+lora+res", x512, mk(d, d), d, dict(bias=bias512, residual=res_h, ldr=d), a2=t32, w2=mk(d, r), k2=r)
+    run("fc1+lora+gelu+aux", x512, mk(F, d), F, dict(bias=bias2048, act=ACT_GELU, aux_out=z1, ldaux=F), a2=t32, w2=mk(F, r), k2=r)
+    run("fc1+lora+gelu", x512, mk(F, d), F, dict(bias=bias2048, act=ACT_GELU), a2=t32, w2=mk(F, r), k2=r)
+    run("fc1 plain", x512, mk(F, d), F)
+    run("fc2+lora+res", x2048, mk(d, F), d, dict(bias=bias512, residual=res_h, ldr=d), a2=t32, w2=mk(d, r), k2=r)
+    run("dfc2+dgelu", x512, mk(F, d), F, dict(act=ACT_DGELU, aux_in=z1, ldaux=F), a2=t32, w2=mk(F, r), k2=r)
+    run("dqkv", mk(M, 3 * d), mk(d, 3 * d), d, None, a2=t96, w2=mk(d, 3 * r), k2=3 * r)
+    run("kv_all", x512, mk(6 * 2 * d, d), 6 * 2 * d, dict(bias=torch.zeros(6 * 2 * d, device=DEV)))
+    run("lora_t 512->32", x512, mk(r, d), r, dict(alpha=2.0, alpha_cols=r))
+    run("lora_t 512->96", x512, mk(3 * r, d), 3 * r, dict(alpha=2.0, alpha_cols=3 * r))
+    run("lora_t 2048->32", x2048, mk(r, F), r, dict(alpha=2.0, alpha_cols=r))
+    # wgrad
+    G = torch.zeros(d * r, device=DEV)
+    t = timeit(lambda: ops.gemm_tn(x512, t32, G, r, 1), iters)
+    res["wgrad 512x32"] = {"ms": t, "tflops": 2.0 * M * d * r / t / 1e9}
+    G2 = torch.zeros(F * r, device=DEV)
+    t = timeit(lambda: ops.gemm_tn(x2048, t32, G2, r, 1), iters)
+    res["wgrad 2048x32"] = {"ms": t, "tflops": 2.0 * M * F * r / t / 1e9}
+    out["gemm"] = res
+
+
+def bench_ln(B, iters, out):
+    S, d = 1500, 512
+    M = B * S
+    x = torch.randn(M, d, device=DEV).to(torch.bfloat16)
+    y = torch.empty_like(x); dx = torch.empty_like(x)
+    gm = torch.ones(d, device=DEV); bt = torch.zeros(d, device=DEV)
+    mean = torch.empty(M, device=DEV); rstd = torch.empty(M, device=DEV)
+    t = timeit(lambda: ops.layernorm_fwd(x, gm, bt, y, mean, rstd), iters)
+    res = {"fwd_ms": t, "fwd_gbs": 2.0 * M * d * 2 / t / 1e6}
+    t = timeit(lambda: ops.layernorm_bwd(y, x, gm, mean, rstd, dx, dres=x), iters)
+    res["bwd_ms"] = t; res["bwd_gbs"] = 4.0 * M * d * 2 / t / 1e6
+    out["ln"] = res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", nargs="*", default=["attn", "gemm", "ln"])
+    ap.add_argument("--B", type=int, default=64)
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+    out = {}
+    if "attn" in a.what:
+        bench_attn(a.B, a.iters, out)
+    if "gemm" in a.what:
+        bench_gemm(a.B, a.iters, out)
+    if "ln" in a.what:
+        bench_ln(a.B, a.iters, out)
+    s = json.dumps(out, indent=1)
+    print(s)
+    if a.out:
+        open(a.out, "w").write(s)
+
+
+if __name__ == "__main__":
+    main()
