@@ -45,7 +45,9 @@ int         ns_reset_counters(void);
  * Epilogue order: +bias[n]; *alpha for columns < alpha_cols (q pre-scale, HF:310); act; +residual.
  *   act NS_ACT_GELU : y = gelu_erf(z); if aux_out != NULL the pre-activation z is stored there (ld = ldaux)
  *   act NS_ACT_DGELU: y = z * gelu'(aux_in[m,n])                (backward through GELU; aux_in = saved pre-activation)
- *   residual: D += R[row % res_mod, n] when res_mod > 0 (position table, utils/load_model.py:413-416) else R[row, n] */
+ *   residual: D += R[row % res_mod, n] when res_mod > 0 (position table, utils/load_model.py:413-416) else R[row, n]
+ * Output tiles are stored with 16-byte granularity: when N is not a multiple of 8 (bf16) and ldd leaves room, the pad
+ * columns [N, round_up(N, 8)) of D (and of aux_out) may be written with zeros; nothing beyond that is touched. */
 typedef struct {
   const float* bias;
   float        alpha;

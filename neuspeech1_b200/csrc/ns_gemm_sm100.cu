@@ -13,6 +13,8 @@
 #include "ns_sm100.cuh"
 #include "ns_gemm.cuh"
 
+#include <stdlib.h>
+
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -106,11 +108,14 @@ struct TileProg {
   void* D;
   EpiDev epi;
   int vec_out, vec_aux, vec_res, vec_bias;
+  int tma_out;      // 1: bf16 output (and aux) tiles leave through shared memory + TMA store (BN >= 128 only)
 };
 
 struct Maps {
   CUtensorMap a[2];
   CUtensorMap b[2];
+  CUtensorMap d;    // output, box {64 columns, 128 rows, 1}: used when tma_out
+  CUtensorMap aux;  // pre-activation output (NS_ACT_GELU with aux_out), same box
 };
 
 constexpr int kBM = 128;
@@ -123,7 +128,9 @@ template <int BN> struct NtCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  // output staging for the TMA-store epilogue: one [128 rows][64 columns] bf16 tile (128B swizzle) per column half
+  static constexpr int kStagingBytes = (BN >= 128) ? 2 * kBM * 128 : 0;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 // ------------------------------------------------------------------------------------------------ epilogue helpers
@@ -182,7 +189,8 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + S * Cfg::kStageBytes;
+  const uint32_t staging_base = smem_base + S * Cfg::kStageBytes;
+  const uint32_t bar_base = staging_base + Cfg::kStagingBytes;
   // barrier addresses
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
@@ -201,6 +209,10 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
     if (p.nseg > 1) {
       tma_prefetch_desc(&maps.a[1]);
       tma_prefetch_desc(&maps.b[1]);
+    }
+    if (p.tma_out) {
+      tma_prefetch_desc(&maps.d);
+      if (p.epi.aux_out) tma_prefetch_desc(&maps.aux);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -223,8 +235,11 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // warps 0..3 (TMA, MMA, TMEM owner, idle) give registers to the two epilogue warpgroups; the setmaxnreg sits inside
+  // each role branch so that ptxas allocates every role under its own limit
   if (warp == 0) {
     // ================================================================ TMA producer
+    setmaxnreg_dec<56>();
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
@@ -251,6 +266,7 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
+    setmaxnreg_dec<56>();
     constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
@@ -287,8 +303,11 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
       if (elect_one()) umma_commit(tfull_bar(acc));
       __syncwarp();
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
+    setmaxnreg_dec<56>();
+  } else {
     // ================================================================ epilogue
+    setmaxnreg_inc<216>();
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;  // which half of the tile's columns
     constexpr int kHalfCols = (BN >= 64) ? BN / 2 : BN;
@@ -307,57 +326,116 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
       const long long res_row = e.res_mod > 0 ? ((static_cast<long long>(t) * p.out_rs + p.out_off) % e.res_mod) : row;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      if (BN >= 64 || half == 0) {
+      // One 32-column slice of this thread's row: TMEM -> registers -> bias / scale / activation / residual.
+      // `z_out` receives the pre-activation when NS_ACT_GELU has an aux output.
+      auto slice = [&](int c, int col0, int ncols, float (&x)[32], float (&z_out)[32]) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + half * kHalfCols + c), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+        if (e.bias) {
+          if (ncols == 32 && p.vec_bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);   // col0 % 32 == 0, bias 16B-aligned (checked on host)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = __ldg(b4 + j);
+              x[4 * j] += bb.x; x[4 * j + 1] += bb.y; x[4 * j + 2] += bb.z; x[4 * j + 3] += bb.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) x[j] += __ldg(e.bias + col0 + j);
+          }
+        }
+        if (col0 < e.alpha_cols) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < e.alpha_cols) x[j] *= e.alpha;
+        }
+        const bool full = (ncols == 32);
+        if (e.act == NS_ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { z_out[j] = x[j]; x[j] = gelu_fast(x[j]); }
+        } else if (e.act == NS_ACT_DGELU) {
+          if (valid) {
+            float z[32];
+            load32_bf16(reinterpret_cast<const __nv_bfloat16*>(e.aux_in) + row * e.ldaux + col0, p.vec_aux && full, ncols, z);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] *= dgelu_fast(z[j]);
+          }
+        }
+        if (e.residual && valid) {
+          float r[32];
+          load32_bf16(reinterpret_cast<const __nv_bfloat16*>(e.residual) + res_row * e.ldr + col0, p.vec_res && full, ncols, r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] += r[j];
+        }
+      };
+      if (BN >= 128 && p.tma_out) {
+        // ---- bf16 tiles leave through shared memory: each thread writes its 128-byte row slice (64 columns) into a
+        // 128B-swizzled [128 rows][64 columns] staging tile, then one thread per column half issues a TMA store.  The
+        // direct path below writes 16 bytes per lane into 32 different rows per instruction (LSU bound).
+        const uint32_t stage_row = staging_base + static_cast<uint32_t>(half) * (kBM * 128) + static_cast<uint32_t>(q * 32 + lane) * 128u;
+        const uint32_t sw = static_cast<uint32_t>(lane & 7);
+        const int t_tile = (m_tile % p.tiles_per_batch) * kBM;
+        const bool issuer = (q == 0);                                         // first warp of this column half
+        auto stage_store = [&](const CUtensorMap* map, const uint32_t (&pk)[2][16], int col0) {
+          if (issuer) {
+            if (elect_one()) bulk_wait_read0();                               // the previous store has read the staging tile
+          }
+          named_bar_sync(1 + half, 128);
+#pragma unroll
+          for (int sidx = 0; sidx < 2; ++sidx)
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+              st_shared_v4(stage_row + ((static_cast<uint32_t>(4 * sidx + cc) ^ sw) << 4), pk[sidx][4 * cc], pk[sidx][4 * cc + 1],
+                           pk[sidx][4 * cc + 2], pk[sidx][4 * cc + 3]);
+          fence_proxy_async();
+          named_bar_sync(1 + half, 128);
+          if (issuer) {
+            if (elect_one()) {
+              tma_store_3d(map, staging_base + static_cast<uint32_t>(half) * (kBM * 128), col0, t_tile, b);
+              bulk_commit();
+            }
+          }
+        };
+#pragma unroll 1
+        for (int c = 0; c < kHalfCols; c += 64) {
+          const int col0 = n0 + half * kHalfCols + c;
+          if (col0 >= p.N) break;                                             // uniform over the 4 warps of this half
+          uint32_t pk_out[2][16], pk_aux[2][16];
+#pragma unroll
+          for (int sidx = 0; sidx < 2; ++sidx) {
+            const int cs = col0 + 32 * sidx;
+            float x[32], z[32];
+            if (cs < p.N) {
+              slice(c + 32 * sidx, cs, min(32, p.N - cs), x, z);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { x[j] = 0.f; z[j] = 0.f; }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk_out[sidx][j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+            if (e.act == NS_ACT_GELU && e.aux_out) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pk_aux[sidx][j] = pack_bf16x2(z[2 * j], z[2 * j + 1]);
+            }
+          }
+          if (e.act == NS_ACT_GELU && e.aux_out) stage_store(&maps.aux, pk_aux, col0);
+          stage_store(&maps.d, pk_out, col0);
+        }
+      } else if (BN >= 64 || half == 0) {
 #pragma unroll 1
         for (int c = 0; c < kHalfCols; c += 32) {
           const int col0 = n0 + half * kHalfCols + c;
           if (col0 >= p.N) break;   // warp-uniform
           const int ncols = min(32, p.N - col0);
-          uint32_t v[32];
-          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + half * kHalfCols + c), v);
-          tmem_ld_wait();
-          float x[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-          if (e.bias) {
-            if (ncols == 32 && p.vec_bias) {
-              const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);   // col0 % 32 == 0, bias 16B-aligned (checked on host)
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 bb = __ldg(b4 + j);
-                x[4 * j] += bb.x; x[4 * j + 1] += bb.y; x[4 * j + 2] += bb.z; x[4 * j + 3] += bb.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncols) x[j] += __ldg(e.bias + col0 + j);
-            }
-          }
-          if (col0 < e.alpha_cols) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < e.alpha_cols) x[j] *= e.alpha;
-          }
           const bool full = (ncols == 32);
-          if (e.act == NS_ACT_GELU) {
-            if (e.aux_out && valid)
-              store32_bf16(reinterpret_cast<__nv_bfloat16*>(e.aux_out) + row * e.ldaux + col0, p.vec_aux && full, ncols, x);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = gelu_fast(x[j]);
-          } else if (e.act == NS_ACT_DGELU) {
-            if (valid) {
-              float z[32];
-              load32_bf16(reinterpret_cast<const __nv_bfloat16*>(e.aux_in) + row * e.ldaux + col0, p.vec_aux && full, ncols, z);
-#pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] *= dgelu_fast(z[j]);
-            }
-          }
-          if (e.residual && valid) {
-            float r[32];
-            load32_bf16(reinterpret_cast<const __nv_bfloat16*>(e.residual) + res_row * e.ldr + col0, p.vec_res && full, ncols, r);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] += r[j];
-          }
+          float x[32], z[32];
+          slice(c, col0, ncols, x, z);
+          if (e.act == NS_ACT_GELU && e.aux_out && valid)
+            store32_bf16(reinterpret_cast<__nv_bfloat16*>(e.aux_out) + row * e.ldaux + col0, p.vec_aux && full, ncols, z);
           if (valid) {
             if (e.out_f32)
               store32_f32(reinterpret_cast<float*>(p.D) + row * p.ldd + col0, p.vec_out && full, ncols, x);
@@ -369,6 +447,9 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+    if (BN >= 128 && p.tma_out && q == 0) {
+      if (elect_one()) bulk_wait0();                                          // outstanding tile stores of this thread
     }
   }
 
@@ -564,6 +645,29 @@ static void fill_epi(TileProg& prog, const EpiDev& e) {
   prog.vec_res = e.residual && aligned16(e.residual) && (e.ldr % 8 == 0);
 }
 
+// Output tensor maps for the TMA-store epilogue (bf16 output, 16-byte aligned rows, N > 64 so that BN >= 128 runs).
+static int setup_out_maps(Maps& maps, TileProg& prog) {
+  const EpiDev& e = prog.epi;
+  maps.d = maps.a[0];
+  maps.aux = maps.a[0];
+  prog.tma_out = 0;
+  static const bool disabled = getenv("NS_GEMM_NO_TMA_STORE") != nullptr;
+  const bool has_aux = (e.act == NS_ACT_GELU && e.aux_out);
+  if (disabled || e.out_f32 || prog.N <= 64 || !prog.vec_out || (has_aux && !prog.vec_aux)) return NS_OK;
+  auto mk = [&](CUtensorMap* m, void* base, long long ld) -> int {
+    uint64_t dims[3] = {(uint64_t)prog.N, (uint64_t)prog.tout, (uint64_t)prog.batches};
+    const long long bs = prog.batches > 1 ? prog.out_bs : static_cast<long long>(prog.tout) * prog.out_rs;
+    uint64_t str[2] = {(uint64_t)(prog.out_rs * ld * 2), (uint64_t)(bs * ld * 2)};
+    uint32_t box[3] = {64, kBM, 1};
+    return make_map(m, reinterpret_cast<char*>(base) + prog.out_off * ld * 2, 3, dims, str, box);
+  };
+  int r = mk(&maps.d, prog.D, prog.ldd);
+  if (r) return r;
+  if (has_aux && (r = mk(&maps.aux, e.aux_out, e.ldaux))) return r;
+  prog.tma_out = 1;
+  return NS_OK;
+}
+
 static void seg_from_k(Seg& s, int K) {
   s.kblocks = (K + kBK - 1) / kBK;
   const int rem = K - (s.kblocks - 1) * kBK;
@@ -626,6 +730,7 @@ int gemm_nt_fast(long long M, int N, int K, const void* A, long long lda, const 
   prog.ldd = ldd;
   prog.D = D;
   fill_epi(prog, epi);
+  if (int r = setup_out_maps(maps, prog)) return r;
   return dispatch_nt(maps, prog, st);
 }
 
@@ -671,6 +776,7 @@ int conv3_fwd_fast(int B, int Tin, int Cp, int N, int stride, const void* x, con
   prog.ldd = N;
   prog.D = y;
   fill_epi(prog, epi);
+  if (int r = setup_out_maps(maps, prog)) return r;
   return dispatch_nt(maps, prog, st);
 }
 
@@ -714,6 +820,7 @@ int conv3_dgrad_fast(int B, int Tin, int Cp, int N, int stride, const void* dz, 
     prog.ldd = Cp;
     prog.D = dx;
     fill_epi(prog, epi);
+    if ((r = setup_out_maps(maps, prog))) return r;
     r = dispatch_nt(maps, prog, st);
     if (r) return r;
   }
