@@ -56,6 +56,7 @@ SIGNATURES = {
     "ns_layernorm_bwd": [c_i, c_ll, c_i, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "ns_attention_fwd": [c_i, C.POINTER(AttnShape), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "ns_attention_bwd": [c_i, C.POINTER(AttnShape), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "ns_attention_bwd_workspace_bytes": [C.POINTER(AttnShape)],
     "ns_attention_bwd_ws": [c_i, C.POINTER(AttnShape), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_vp],
     "ns_debug_attn_trace": [c_vp],
     "ns_embed": [c_i, c_i, c_i, c_i, c_vp, c_vp, c_vp, c_i, c_vp, c_vp],
@@ -72,6 +73,8 @@ SIGNATURES = {
     "ns_sumsq": [c_ll, c_vp, c_vp, c_vp],
     "ns_adamw_clip": [c_ll, c_vp, c_vp, c_vp, c_vp, c_vp, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_vp],
 }
+
+RESTYPES = {"ns_attention_bwd_workspace_bytes": c_ll}      # everything else returns an int status
 
 _lib = None
 
@@ -93,9 +96,7 @@ def load():
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
-        fn.restype = c_i
-    lib.ns_attention_bwd_workspace_bytes.argtypes = [C.POINTER(AttnShape)]
-    lib.ns_attention_bwd_workspace_bytes.restype = c_ll
+        fn.restype = RESTYPES.get(name, c_i)
     lib.ns_last_error_string.argtypes = []
     lib.ns_last_error_string.restype = C.c_char_p
     _lib = lib

@@ -109,6 +109,11 @@ struct TileProg {
   EpiDev epi;
   int vec_out, vec_aux, vec_res, vec_bias;
   int tma_out;      // 1: bf16 output (and aux) tiles leave through shared memory + TMA store (BN >= 128 only)
+  int tma_in;       // with tma_out: 1 = aux_in (NS_ACT_DGELU), 2 = residual tiles arrive through TMA + shared memory
+  int in_batched;   // tma_in: the input tensor has a batch coordinate (0: one [rows][N] table shared by all batches)
+  int m_fast;       // tile raster: 1 = consecutive tiles walk M first (small M, large N: the weight tile is the one to reuse)
+  int stages;       // operand ring depth (what fits beside the staging tiles)
+  int staging_tiles;  // 0, 2 (one output tile per column half) or 4 (+ one aux-output or input tile per half)
 };
 
 struct Maps {
@@ -116,6 +121,7 @@ struct Maps {
   CUtensorMap b[2];
   CUtensorMap d;    // output, box {64 columns, 128 rows, 1}: used when tma_out
   CUtensorMap aux;  // pre-activation output (NS_ACT_GELU with aux_out), same box
+  CUtensorMap in;   // epilogue input tile (aux_in or residual), same box
 };
 
 constexpr int kBM = 128;
@@ -126,11 +132,15 @@ constexpr int kNtThreads = 384;
 template <int BN> struct NtCfg {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kMaxSmem = 232448 - 1024;      // 227 KB opt-in limit minus the 1 KB the runtime reserves per CTA
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
-  // output staging for the TMA-store epilogue: one [128 rows][64 columns] bf16 tile (128B swizzle) per column half
-  static constexpr int kStagingBytes = (BN >= 128) ? 2 * kBM * 128 : 0;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  // staging for the TMA epilogue: [128 rows][64 columns] bf16 tiles (128B swizzle), see TileProg::staging_tiles
+  static constexpr int kStagingTile = kBM * 128;
+  static int stages_for(int staging_tiles) {
+    const int s = (kMaxSmem - 1024 - 256 - staging_tiles * kStagingTile) / kStageBytes;
+    return s > 8 ? 8 : s;
+  }
+  static int smem_bytes(int stages, int staging_tiles) { return stages * kStageBytes + staging_tiles * kStagingTile + 1024 + 256; }
 };
 
 // ------------------------------------------------------------------------------------------------ epilogue helpers
@@ -186,16 +196,17 @@ template <int BN>
 __global__ void __launch_bounds__(kNtThreads, 1)
 gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TileProg p) {
   using Cfg = NtCfg<BN>;
-  constexpr int S = Cfg::kStages;
+  const int S = p.stages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t staging_base = smem_base + S * Cfg::kStageBytes;
-  const uint32_t bar_base = staging_base + Cfg::kStagingBytes;
+  const uint32_t bar_base = staging_base + static_cast<uint32_t>(p.staging_tiles) * Cfg::kStagingTile;
   // barrier addresses
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
+  auto in_full = [&](int h) { return bar_base + 8u * (2 * S + 5 + h); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -213,6 +224,7 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
     if (p.tma_out) {
       tma_prefetch_desc(&maps.d);
       if (p.epi.aux_out) tma_prefetch_desc(&maps.aux);
+      if (p.tma_in) tma_prefetch_desc(&maps.in);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -223,6 +235,7 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 8);   // one arrive per epilogue warp
+      mbar_init(in_full(a), 1);
     }
     mbar_fence_init();
   }
@@ -244,8 +257,9 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles;
-        const int m_tile = tile / p.n_tiles;
+        const int m_tiles = p.batches * p.tiles_per_batch;
+        const int n_tile = p.m_fast ? tile / m_tiles : tile % p.n_tiles;
+        const int m_tile = p.m_fast ? tile % m_tiles : tile / p.n_tiles;
         const int b = m_tile / p.tiles_per_batch;
         const int t0 = (m_tile % p.tiles_per_batch) * kBM;
         const int n0 = n_tile * BN;
@@ -312,12 +326,29 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
     const int half = (warp - 4) >> 2;  // which half of the tile's columns
     constexpr int kHalfCols = (BN >= 64) ? BN / 2 : BN;
     const EpiDev& e = p.epi;
+    const int m_tiles = p.batches * p.tiles_per_batch;
+    const bool use_tma = BN >= 128 && p.tma_out;
+    const bool issuer = (q == 0);                                             // first warp of this column half
+    const uint32_t out_stage = staging_base + static_cast<uint32_t>(half) * (kBM * 128);
+    const uint32_t in_stage = staging_base + static_cast<uint32_t>(2 + half) * (kBM * 128);   // input tile, or the aux output tile
+    uint32_t in_phase = 0;
+    // epilogue input tile (aux_in / residual) of (tile, column chunk c) -> shared memory, by the elected issuer lane
+    auto issue_in = [&](int tile_, int c_) {
+      const int n_tile_ = p.m_fast ? tile_ / m_tiles : tile_ % p.n_tiles;
+      const int m_tile_ = p.m_fast ? tile_ % m_tiles : tile_ / p.n_tiles;
+      mbar_expect_tx(in_full(half), kBM * 128);
+      tma_load_3d(&maps.in, in_full(half), in_stage, n_tile_ * BN + half * kHalfCols + c_, (m_tile_ % p.tiles_per_batch) * kBM,
+                  p.in_batched ? m_tile_ / p.tiles_per_batch : 0);
+    };
+    if (use_tma && p.tma_in && issuer && blockIdx.x < total_tiles) {
+      if (elect_one()) issue_in(blockIdx.x, 0);
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
-      const int n_tile = tile % p.n_tiles;
-      const int m_tile = tile / p.n_tiles;
+      const int n_tile = p.m_fast ? tile / m_tiles : tile % p.n_tiles;
+      const int m_tile = p.m_fast ? tile % m_tiles : tile / p.n_tiles;
       const int b = m_tile / p.tiles_per_batch;
       const int t = (m_tile % p.tiles_per_batch) * kBM + q * 32 + lane;
       const int n0 = n_tile * BN;
@@ -328,7 +359,8 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
       tc_fence_after();
       // One 32-column slice of this thread's row: TMEM -> registers -> bias / scale / activation / residual.
       // `z_out` receives the pre-activation when NS_ACT_GELU has an aux output.
-      auto slice = [&](int c, int col0, int ncols, float (&x)[32], float (&z_out)[32]) {
+      // `zin` (16 packed bf16 pairs) carries this slice of the TMA-staged input tile when has_in.
+      auto slice = [&](int c, int col0, int ncols, float (&x)[32], float (&z_out)[32], const uint32_t (&zin)[16], bool has_in) {
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + half * kHalfCols + c), v);
         tmem_ld_wait();
@@ -358,44 +390,65 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
 #pragma unroll
           for (int j = 0; j < 32; ++j) { z_out[j] = x[j]; x[j] = gelu_fast(x[j]); }
         } else if (e.act == NS_ACT_DGELU) {
-          if (valid) {
+          if (has_in && p.tma_in == 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 zz = unpack_bf16x2(zin[j]);
+              x[2 * j] *= dgelu_fast(zz.x); x[2 * j + 1] *= dgelu_fast(zz.y);
+            }
+          } else if (valid) {
             float z[32];
             load32_bf16(reinterpret_cast<const __nv_bfloat16*>(e.aux_in) + row * e.ldaux + col0, p.vec_aux && full, ncols, z);
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] *= dgelu_fast(z[j]);
           }
         }
-        if (e.residual && valid) {
-          float r[32];
-          load32_bf16(reinterpret_cast<const __nv_bfloat16*>(e.residual) + res_row * e.ldr + col0, p.vec_res && full, ncols, r);
+        if (e.residual) {
+          if (has_in && p.tma_in == 2) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] += r[j];
+            for (int j = 0; j < 16; ++j) {
+              const float2 rr = unpack_bf16x2(zin[j]);
+              x[2 * j] += rr.x; x[2 * j + 1] += rr.y;
+            }
+          } else if (valid) {
+            float r[32];
+            load32_bf16(reinterpret_cast<const __nv_bfloat16*>(e.residual) + res_row * e.ldr + col0, p.vec_res && full, ncols, r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] += r[j];
+          }
         }
       };
-      if (BN >= 128 && p.tma_out) {
-        // ---- bf16 tiles leave through shared memory: each thread writes its 128-byte row slice (64 columns) into a
-        // 128B-swizzled [128 rows][64 columns] staging tile, then one thread per column half issues a TMA store.  The
-        // direct path below writes 16 bytes per lane into 32 different rows per instruction (LSU bound).
-        const uint32_t stage_row = staging_base + static_cast<uint32_t>(half) * (kBM * 128) + static_cast<uint32_t>(q * 32 + lane) * 128u;
+      if (use_tma) {
+        // ---- bf16 tiles travel through shared memory: each thread owns the 128-byte row slice (64 columns) of a
+        // 128B-swizzled [128 rows][64 columns] staging tile; one lane per column half issues the TMA loads / stores.  The
+        // direct path below moves 16 bytes per lane from / to 32 different rows per instruction (LSU bound).
+        const uint32_t row_off = static_cast<uint32_t>(q * 32 + lane) * 128u;
         const uint32_t sw = static_cast<uint32_t>(lane & 7);
         const int t_tile = (m_tile % p.tiles_per_batch) * kBM;
-        const bool issuer = (q == 0);                                         // first warp of this column half
-        auto stage_store = [&](const CUtensorMap* map, const uint32_t (&pk)[2][16], int col0) {
+        const bool has_aux = (e.act == NS_ACT_GELU && e.aux_out);
+        // With an aux output two store groups are in flight per chunk (aux tile, then output tile, each in its own staging
+        // tile): the tile about to be rewritten belongs to the OLDER of the two, so one group may stay pending.
+        auto stage_wait = [&]() {                                             // the previous store of this tile has read it
           if (issuer) {
-            if (elect_one()) bulk_wait_read0();                               // the previous store has read the staging tile
+            if (elect_one()) {
+              if (has_aux) bulk_wait_read1(); else bulk_wait_read0();
+            }
           }
           named_bar_sync(1 + half, 128);
+        };
+        auto stage_write = [&](uint32_t tile_addr, int sidx, const float (&y)[32]) {   // this thread's 32 columns -> 4 swizzled chunks
 #pragma unroll
-          for (int sidx = 0; sidx < 2; ++sidx)
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc)
-              st_shared_v4(stage_row + ((static_cast<uint32_t>(4 * sidx + cc) ^ sw) << 4), pk[sidx][4 * cc], pk[sidx][4 * cc + 1],
-                           pk[sidx][4 * cc + 2], pk[sidx][4 * cc + 3]);
+          for (int cc = 0; cc < 4; ++cc)
+            st_shared_v4(tile_addr + row_off + ((static_cast<uint32_t>(4 * sidx + cc) ^ sw) << 4), pack_bf16x2(y[8 * cc], y[8 * cc + 1]),
+                         pack_bf16x2(y[8 * cc + 2], y[8 * cc + 3]), pack_bf16x2(y[8 * cc + 4], y[8 * cc + 5]),
+                         pack_bf16x2(y[8 * cc + 6], y[8 * cc + 7]));
+        };
+        auto stage_commit = [&](const CUtensorMap* map, uint32_t tile_addr, int col0) {
           fence_proxy_async();
           named_bar_sync(1 + half, 128);
           if (issuer) {
             if (elect_one()) {
-              tma_store_3d(map, staging_base + static_cast<uint32_t>(half) * (kBM * 128), col0, t_tile, b);
+              tma_store_3d(map, tile_addr, col0, t_tile, b);
               bulk_commit();
             }
           }
@@ -403,27 +456,67 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
 #pragma unroll 1
         for (int c = 0; c < kHalfCols; c += 64) {
           const int col0 = n0 + half * kHalfCols + c;
-          if (col0 >= p.N) break;                                             // uniform over the 4 warps of this half
-          uint32_t pk_out[2][16], pk_aux[2][16];
+          if (c > 0 && col0 >= p.N) break;                                    // uniform over the 4 warps of this half
+          uint32_t zin[2][16];
+          if (p.tma_in) {
+            mbar_wait(in_full(half), in_phase);
+            in_phase ^= 1u;
 #pragma unroll
-          for (int sidx = 0; sidx < 2; ++sidx) {
-            const int cs = col0 + 32 * sidx;
-            float x[32], z[32];
-            if (cs < p.N) {
-              slice(c + 32 * sidx, cs, min(32, p.N - cs), x, z);
-            } else {
+            for (int sidx = 0; sidx < 2; ++sidx)
 #pragma unroll
-              for (int j = 0; j < 32; ++j) { x[j] = 0.f; z[j] = 0.f; }
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) pk_out[sidx][j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
-            if (e.act == NS_ACT_GELU && e.aux_out) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) pk_aux[sidx][j] = pack_bf16x2(z[2 * j], z[2 * j + 1]);
+              for (int cc = 0; cc < 4; ++cc)
+                ld_shared_v4(in_stage + row_off + ((static_cast<uint32_t>(4 * sidx + cc) ^ sw) << 4), zin[sidx][4 * cc], zin[sidx][4 * cc + 1],
+                             zin[sidx][4 * cc + 2], zin[sidx][4 * cc + 3]);
+            named_bar_sync(3 + half, 128);                                    // everyone has its slice: the tile may be refilled
+            if (issuer) {
+              if (elect_one()) {                                              // prefetch the next chunk (or the next tile's first)
+                const int c2 = c + 64;
+                if (c2 < kHalfCols && col0 + 64 < p.N) issue_in(tile, c2);
+                else if (tile + static_cast<int>(gridDim.x) < total_tiles) issue_in(tile + gridDim.x, 0);
+              }
             }
           }
-          if (e.act == NS_ACT_GELU && e.aux_out) stage_store(&maps.aux, pk_aux, col0);
-          stage_store(&maps.d, pk_out, col0);
+          stage_wait();
+          if (has_aux) {
+            // pre-activation tile -> its own staging tile and out; then the activated tile
+            uint32_t pk_out[2][16];
+#pragma unroll
+            for (int sidx = 0; sidx < 2; ++sidx) {
+              const int cs = col0 + 32 * sidx;
+              float x[32], z[32];
+              if (cs < p.N) {
+                slice(c + 32 * sidx, cs, min(32, p.N - cs), x, z, zin[sidx], false);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { x[j] = 0.f; z[j] = 0.f; }
+              }
+              stage_write(in_stage, sidx, z);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pk_out[sidx][j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+            }
+            stage_commit(&maps.aux, in_stage, col0);
+            stage_wait();
+#pragma unroll
+            for (int sidx = 0; sidx < 2; ++sidx)
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc)
+                st_shared_v4(out_stage + row_off + ((static_cast<uint32_t>(4 * sidx + cc) ^ sw) << 4), pk_out[sidx][4 * cc], pk_out[sidx][4 * cc + 1],
+                             pk_out[sidx][4 * cc + 2], pk_out[sidx][4 * cc + 3]);
+          } else {
+#pragma unroll
+            for (int sidx = 0; sidx < 2; ++sidx) {
+              const int cs = col0 + 32 * sidx;
+              float x[32], z[32];
+              if (cs < p.N) {
+                slice(c + 32 * sidx, cs, min(32, p.N - cs), x, z, zin[sidx], p.tma_in != 0);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = 0.f;
+              }
+              stage_write(out_stage, sidx, x);
+            }
+          }
+          stage_commit(&maps.d, out_stage, col0);
         }
       } else if (BN >= 64 || half == 0) {
 #pragma unroll 1
@@ -433,7 +526,8 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
           const int ncols = min(32, p.N - col0);
           const bool full = (ncols == 32);
           float x[32], z[32];
-          slice(c, col0, ncols, x, z);
+          const uint32_t no_in[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+          slice(c, col0, ncols, x, z, no_in, false);
           if (e.act == NS_ACT_GELU && e.aux_out && valid)
             store32_bf16(reinterpret_cast<__nv_bfloat16*>(e.aux_out) + row * e.ldaux + col0, p.vec_aux && full, ncols, z);
           if (valid) {
@@ -448,7 +542,7 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
-    if (BN >= 128 && p.tma_out && q == 0) {
+    if (use_tma && issuer) {
       if (elect_one()) bulk_wait0();                                          // outstanding tile stores of this thread
     }
   }
@@ -614,14 +708,20 @@ static int launch_nt(const Maps& maps, TileProg& prog, cudaStream_t st) {
   using Cfg = NtCfg<BN>;
   static bool attr_done = false;
   if (!attr_done) {
-    NS_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    NS_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kMaxSmem));
     attr_done = true;
   }
   prog.n_tiles = (prog.N + BN - 1) / BN;
+  // consecutive tiles should share the LARGER operand tile stream's counterpart: few M tiles and many N tiles (the tied
+  // vocabulary projection) -> walk M first so each weight tile is fetched once and reused from L2
+  prog.m_fast = (static_cast<long long>(prog.batches) * prog.tiles_per_batch * 4 < prog.n_tiles) ? 1 : 0;
   const long long total = static_cast<long long>(prog.batches) * prog.tiles_per_batch * prog.n_tiles;
   const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
   if (grid <= 0) return NS_OK;
-  gemm_nt_kernel<BN><<<grid, kNtThreads, Cfg::kSmemBytes, st>>>(maps, prog);
+  const bool has_aux = (prog.epi.act == NS_ACT_GELU && prog.epi.aux_out);
+  prog.staging_tiles = (BN >= 128 && prog.tma_out) ? ((has_aux || prog.tma_in) ? 4 : 2) : 0;
+  prog.stages = Cfg::stages_for(prog.staging_tiles);
+  gemm_nt_kernel<BN><<<grid, kNtThreads, Cfg::smem_bytes(prog.stages, prog.staging_tiles), st>>>(maps, prog);
   NS_LAUNCH_CHECK();
   count(C_GEMM_TC);
   return NS_OK;
@@ -650,7 +750,9 @@ static int setup_out_maps(Maps& maps, TileProg& prog) {
   const EpiDev& e = prog.epi;
   maps.d = maps.a[0];
   maps.aux = maps.a[0];
+  maps.in = maps.a[0];
   prog.tma_out = 0;
+  prog.tma_in = 0;
   static const bool disabled = getenv("NS_GEMM_NO_TMA_STORE") != nullptr;
   const bool has_aux = (e.act == NS_ACT_GELU && e.aux_out);
   if (disabled || e.out_f32 || prog.N <= 64 || !prog.vec_out || (has_aux && !prog.vec_aux)) return NS_OK;
@@ -665,6 +767,30 @@ static int setup_out_maps(Maps& maps, TileProg& prog) {
   if (r) return r;
   if (has_aux && (r = mk(&maps.aux, e.aux_out, e.ldaux))) return r;
   prog.tma_out = 1;
+  // one epilogue INPUT tile kind can ride the same way: the saved pre-activation of NS_ACT_DGELU, else the residual
+  maps.in = maps.a[0];
+  prog.tma_in = 0;
+  prog.in_batched = 1;
+  if (has_aux) {
+    // the second staging tile of each half carries the pre-activation output; a residual (conv C's position table) stays on
+    // the direct-load path
+  } else if (e.act == NS_ACT_DGELU && prog.vec_aux) {
+    if ((r = mk(&maps.in, const_cast<void*>(e.aux_in), e.ldaux))) return r;
+    prog.tma_in = 1;
+  } else if (e.residual && prog.vec_res) {
+    if (e.res_mod == 0) {
+      if ((r = mk(&maps.in, const_cast<void*>(e.residual), e.ldr))) return r;
+      prog.tma_in = 2;
+    } else if (prog.out_rs == 1 && prog.out_off == 0 && prog.tout <= e.res_mod) {
+      // position table (rows t of every batch read table row t): a tile never wraps, no batch coordinate
+      uint64_t dims[3] = {(uint64_t)prog.N, (uint64_t)e.res_mod, 1};
+      uint64_t str[2] = {(uint64_t)(e.ldr * 2), (uint64_t)(e.ldr * 2) * (uint64_t)e.res_mod};
+      uint32_t box[3] = {64, kBM, 1};
+      if ((r = make_map(&maps.in, e.residual, 3, dims, str, box))) return r;
+      prog.tma_in = 2;
+      prog.in_batched = 0;
+    }
+  }
   return NS_OK;
 }
 

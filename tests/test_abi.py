@@ -14,7 +14,7 @@ def declared_functions():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     out = {}
-    for m in re.finditer(r"(?:int|const char\*)\s+(ns_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"(?:long long|int|const char\*)\s+(ns_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
         args = m.group(2).strip()
         n = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
         out[m.group(1)] = n
@@ -32,7 +32,7 @@ def lib():
 
 def test_header_symbols_exported(lib):
     fns = declared_functions()
-    assert len(fns) >= 28
+    assert len(fns) >= 31
     for name in fns:
         assert hasattr(lib, name), f"{name} declared in include/neuspeech_b200.h but not exported"
 
