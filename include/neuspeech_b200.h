@@ -156,6 +156,18 @@ int ns_cast(int src_dtype, int dst_dtype, long long n, const void* src, void* ds
 /* dst (cols, rows_pad>=rows) = scale * src (rows, cols)^T, dst leading dim ldd; pad rows zero-filled up to ldd */
 int ns_transpose(int src_dtype, int dst_dtype, int rows, int cols, const void* src, long long lds, void* dst,
                  long long ldd, float scale, void* stream);
+/* n_jobs independent transposes (same dtypes) in ONE launch; `jobs` is a DEVICE array.  max_rows_pad / max_cols bound the
+ * largest job's ldd / cols.  Used for the per-step refresh of the LoRA operand layouts (60 small matrices). */
+typedef struct {
+  const void* src;
+  void* dst;
+  int rows, cols;
+  long long lds, ldd;
+  float scale;
+  int pad_;
+} ns_transpose_job;
+int ns_transpose_batched(int src_dtype, int dst_dtype, int n_jobs, int max_rows_pad, int max_cols,
+                         const ns_transpose_job* jobs, void* stream);
 /* conv weight re-layouts: w (N,C,3) fp32 -> (3,N,Cp) and (3,Cp,N) in dtype; and the fp32 gradient back (3,N,Cp)->(N,C,3) */
 int ns_conv_weight_pack(int dtype, int N, int C, int Cp, const float* w, void* w_tap, void* w_tap_t, void* stream);
 int ns_conv_weight_unpack_grad(int N, int C, int Cp, const float* dw_tap, float* dw, void* stream);

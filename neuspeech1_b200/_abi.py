@@ -33,6 +33,10 @@ class AttnShape(C.Structure):
                 ("o_bs", c_ll), ("o_rs", c_ll)]
 
 
+class TransposeJob(C.Structure):
+    _fields_ = [("src", c_vp), ("dst", c_vp), ("rows", c_i), ("cols", c_i), ("lds", c_ll), ("ldd", c_ll), ("scale", c_f), ("pad_", c_i)]
+
+
 class AugArgs(C.Structure):
     _fields_ = [("B", c_i), ("C", c_i), ("Tin", c_i), ("T", c_i), ("Cp", c_i), ("layout", c_i), ("out_dtype", c_i),
                 ("n", c_vp), ("shift", c_vp), ("e0", c_vp), ("e1", c_vp), ("flags", c_vp),
@@ -66,6 +70,7 @@ SIGNATURES = {
     "ns_channel_meansq": [c_i, c_i, c_i, c_vp, c_vp, c_vp, c_vp],
     "ns_cast": [c_i, c_i, c_ll, c_vp, c_vp, c_vp],
     "ns_transpose": [c_i, c_i, c_i, c_i, c_vp, c_ll, c_vp, c_ll, c_f, c_vp],
+    "ns_transpose_batched": [c_i, c_i, c_i, c_i, c_i, c_vp, c_vp],
     "ns_conv_weight_pack": [c_i, c_i, c_i, c_i, c_vp, c_vp, c_vp, c_vp],
     "ns_conv_weight_unpack_grad": [c_i, c_i, c_i, c_vp, c_vp, c_vp],
     "ns_add": [c_i, c_ll, c_vp, c_vp, c_vp, c_vp],

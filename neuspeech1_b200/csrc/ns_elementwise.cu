@@ -248,6 +248,100 @@ __global__ void __launch_bounds__(512) ce_kernel(int V, long long ld, T* __restr
   }
 }
 
+
+// bf16 rows with 16-byte alignment: 8 logits per load, ONE pass for (max, sum) with the online-softmax update, then (for the
+// gradient) one more read + one write.  The scalar kernel above reads every logit three times, two bytes at a time.
+__global__ void __launch_bounds__(512) ce_vec_kernel(int V, long long ld, __nv_bfloat16* __restrict__ logits, const long long* __restrict__ labels,
+                                                     float* __restrict__ row_loss, float* loss_sum, const int* __restrict__ n_valid,
+                                                     int write_grad, float grad_scale) {
+  constexpr float kL2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+  __shared__ float shm[16], shs[16];
+  __shared__ float bcm, bcs;
+  const long long row = blockIdx.x;
+  __nv_bfloat16* lr = logits + row * ld;
+  uint4* lv = reinterpret_cast<uint4*>(lr);
+  const long long label = labels[row];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = V / 8;                       // full vectors; the tail (< 8 logits) is handled by thread 0
+  float m = -INFINITY, s = 0.f;                 // s = sum exp2((x - m) * log2e)
+  auto upd = [&](float x) {
+    if (x > m) { s *= exp2f((m - x) * kL2e); m = x; }
+    s += exp2f((x - m) * kL2e);
+  };
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const uint4 u = lv[i];
+    float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+    const float vm = fmaxf(fmaxf(fmaxf(f0.x, f0.y), fmaxf(f1.x, f1.y)), fmaxf(fmaxf(f2.x, f2.y), fmaxf(f3.x, f3.y)));
+    if (vm > m) { s *= exp2f((m - vm) * kL2e); m = vm; }
+    const float mb = m * kL2e;
+    s += exp2f(fmaf(f0.x, kL2e, -mb)) + exp2f(fmaf(f0.y, kL2e, -mb)) + exp2f(fmaf(f1.x, kL2e, -mb)) + exp2f(fmaf(f1.y, kL2e, -mb)) +
+         exp2f(fmaf(f2.x, kL2e, -mb)) + exp2f(fmaf(f2.y, kL2e, -mb)) + exp2f(fmaf(f3.x, kL2e, -mb)) + exp2f(fmaf(f3.y, kL2e, -mb));
+  }
+  if (threadIdx.x == 0)
+    for (int c = nvec * 8; c < V; ++c) upd(__bfloat162float(lr[c]));
+  // combine (m, s) pairs: warp, then block
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    const float mn = fmaxf(m, m2);
+    s = (mn == -INFINITY) ? 0.f : s * exp2f((m - mn) * kL2e) + s2 * exp2f((m2 - mn) * kL2e);
+    m = mn;
+  }
+  if (lane == 0) { shm[warp] = m; shs[warp] = s; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    m = lane < nw ? shm[lane] : -INFINITY;
+    s = lane < nw ? shs[lane] : 0.f;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+      const float mn = fmaxf(m, m2);
+      s = (mn == -INFINITY) ? 0.f : s * exp2f((m - mn) * kL2e) + s2 * exp2f((m2 - mn) * kL2e);
+      m = mn;
+    }
+    if (lane == 0) { bcm = m; bcs = s; }
+  }
+  __syncthreads();
+  m = bcm; s = bcs;
+  const bool valid = label != -100;
+  if (threadIdx.x == 0) {
+    const float lse = m + log2f(s) * kLn2;
+    const float loss = valid ? lse - __bfloat162float(lr[label]) : 0.f;
+    if (row_loss) row_loss[row] = loss;
+    if (loss_sum && valid) atomicAdd(loss_sum, loss);
+  }
+  if (write_grad) {
+    __syncthreads();   // label logit read above before it is overwritten
+    const int nv = *n_valid;
+    const float sc = (valid && nv > 0) ? grad_scale / nv : 0.f;
+    const float k = sc / s;
+    const float mb = m * kL2e;
+    const int nvec_ld = static_cast<int>(ld / 8);
+    const int lab = valid ? static_cast<int>(label) : -1;
+    for (int i = threadIdx.x; i < nvec_ld; i += blockDim.x) {
+      const int c0 = i * 8;
+      const uint4 u = lv[i];
+      float x[8];
+      float2 f;
+      f = unpack_bf16x2(u.x); x[0] = f.x; x[1] = f.y;
+      f = unpack_bf16x2(u.y); x[2] = f.x; x[3] = f.y;
+      f = unpack_bf16x2(u.z); x[4] = f.x; x[5] = f.y;
+      f = unpack_bf16x2(u.w); x[6] = f.x; x[7] = f.y;
+      float gq[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float gg = (c0 + j < V) ? exp2f(fmaf(x[j], kL2e, -mb)) * k : 0.f;
+        if (c0 + j == lab) gg -= sc;
+        gq[j] = gg;
+      }
+      uint4 o;
+      o.x = pack_bf16x2(gq[0], gq[1]); o.y = pack_bf16x2(gq[2], gq[3]); o.z = pack_bf16x2(gq[4], gq[5]); o.w = pack_bf16x2(gq[6], gq[7]);
+      lv[i] = o;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ greedy pick
 template <typename T>
 __global__ void __launch_bounds__(512) greedy_kernel(int V, long long ld, const T* __restrict__ logits, const int* __restrict__ suppress,
@@ -410,6 +504,27 @@ __global__ void transpose_kernel(int rows, int cols, const TS* __restrict__ s, l
   for (int i = ty; i < 32; i += 8) {
     const int c = c0 + i, r = r0 + tx;   // dst[c][r]
     if (c < cols && r < ldd) d[static_cast<long long>(c) * ldd + r] = from_f<TD>(tile[tx][i]);
+  }
+}
+
+// Many small transposes in one launch (the per-step refresh of the LoRA A/B operand layouts): blockIdx.z picks the job.
+template <typename TS, typename TD>
+__global__ void transpose_batched_kernel(const ns_transpose_job* __restrict__ jobs) {
+  __shared__ float tile[32][33];
+  const ns_transpose_job j = jobs[blockIdx.z];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  if (r0 >= j.ldd || c0 >= j.cols) return;             // block-uniform
+  const TS* s = reinterpret_cast<const TS*>(j.src);
+  TD* d = reinterpret_cast<TD*>(j.dst);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < j.rows && c < j.cols) ? to_f<TS>(s[static_cast<long long>(r) * j.lds + c]) * j.scale : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;   // dst[c][r]
+    if (c < j.cols && r < j.ldd) d[static_cast<long long>(c) * j.ldd + r] = from_f<TD>(tile[tx][i]);
   }
 }
 
@@ -579,7 +694,9 @@ int ns_cross_entropy(int dtype, long long rows, int V, long long ld, void* logit
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   ce_count_kernel<<<1, 256, 0, st>>>(rows, labels, n_valid_out, loss_sum_out);
   NS_LAUNCH_CHECK();
-  if (dtype == NS_BF16)
+  if (dtype == NS_BF16 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0)
+    ce_vec_kernel<<<static_cast<unsigned>(rows), 512, 0, st>>>(V, ld, reinterpret_cast<bf16*>(logits), labels, row_loss, loss_sum_out, n_valid_out, write_grad, grad_scale);
+  else if (dtype == NS_BF16)
     ce_kernel<bf16><<<static_cast<unsigned>(rows), 512, 0, st>>>(V, ld, reinterpret_cast<bf16*>(logits), labels, row_loss, loss_sum_out, n_valid_out, write_grad, grad_scale);
   else
     ce_kernel<float><<<static_cast<unsigned>(rows), 512, 0, st>>>(V, ld, reinterpret_cast<float*>(logits), labels, row_loss, loss_sum_out, n_valid_out, write_grad, grad_scale);
@@ -654,6 +771,21 @@ int ns_transpose(int sdt, int ddt, int rows, int cols, const void* src, long lon
   else if (sdt == NS_F32 && ddt == NS_F32) transpose_kernel<float, float><<<grid, 256, 0, st>>>(rows, cols, reinterpret_cast<const float*>(src), lds, reinterpret_cast<float*>(dst), ldd, scale);
   else if (sdt == NS_BF16 && ddt == NS_BF16) transpose_kernel<bf16, bf16><<<grid, 256, 0, st>>>(rows, cols, reinterpret_cast<const bf16*>(src), lds, reinterpret_cast<bf16*>(dst), ldd, scale);
   else transpose_kernel<bf16, float><<<grid, 256, 0, st>>>(rows, cols, reinterpret_cast<const bf16*>(src), lds, reinterpret_cast<float*>(dst), ldd, scale);
+  NS_LAUNCH_CHECK();
+  count(C_OTHER);
+  return NS_OK;
+}
+
+int ns_transpose_batched(int sdt, int ddt, int n_jobs, int max_rows_pad, int max_cols, const ns_transpose_job* jobs_device, void* stream) {
+  NS_CHECK_ARG(valid_dtype(sdt) && valid_dtype(ddt) && n_jobs >= 0 && n_jobs <= 65535 && max_rows_pad > 0 && max_cols > 0 && jobs_device,
+               "ns_transpose_batched: bad arguments");
+  if (n_jobs == 0) return NS_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid((max_cols + 31) / 32, (max_rows_pad + 31) / 32, n_jobs);
+  if (sdt == NS_F32 && ddt == NS_BF16) transpose_batched_kernel<float, bf16><<<grid, 256, 0, st>>>(jobs_device);
+  else if (sdt == NS_F32 && ddt == NS_F32) transpose_batched_kernel<float, float><<<grid, 256, 0, st>>>(jobs_device);
+  else if (sdt == NS_BF16 && ddt == NS_BF16) transpose_batched_kernel<bf16, bf16><<<grid, 256, 0, st>>>(jobs_device);
+  else transpose_batched_kernel<bf16, float><<<grid, 256, 0, st>>>(jobs_device);
   NS_LAUNCH_CHECK();
   count(C_OTHER);
   return NS_OK;

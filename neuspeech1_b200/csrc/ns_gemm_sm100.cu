@@ -727,11 +727,19 @@ static int launch_nt(const Maps& maps, TileProg& prog, cudaStream_t st) {
   return NS_OK;
 }
 
-static int dispatch_nt(const Maps& maps, TileProg& prog, cudaStream_t st) {
-  const int N = prog.N;
-  if (N >= 256 || N > 128) return launch_nt<256>(maps, prog, st);
-  if (N > 64) return launch_nt<128>(maps, prog, st);
-  if (N > 32) return launch_nt<64>(maps, prog, st);
+// Tile width: the widest UMMA N that covers the output, narrowed (down to 64) while the grid would leave a quarter of the
+// SMs idle -- the M = B*L = 2048 products of the decoder and the K = 51872 product dlogits * E have only 16 row tiles.
+static int choose_bn(long long m_tiles, int N) {
+  int bn = (N > 128) ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
+  const long long want = static_cast<long long>(sm_count()) * 3 / 4;
+  while (bn > 64 && m_tiles * ((N + bn - 1) / bn) < want) bn >>= 1;
+  return bn;
+}
+
+static int dispatch_nt(const Maps& maps, TileProg& prog, cudaStream_t st, int bn) {
+  if (bn == 256) return launch_nt<256>(maps, prog, st);
+  if (bn == 128) return launch_nt<128>(maps, prog, st);
+  if (bn == 64) return launch_nt<64>(maps, prog, st);
   return launch_nt<32>(maps, prog, st);
 }
 
@@ -746,7 +754,7 @@ static void fill_epi(TileProg& prog, const EpiDev& e) {
 }
 
 // Output tensor maps for the TMA-store epilogue (bf16 output, 16-byte aligned rows, N > 64 so that BN >= 128 runs).
-static int setup_out_maps(Maps& maps, TileProg& prog) {
+static int setup_out_maps(Maps& maps, TileProg& prog, int bn) {
   const EpiDev& e = prog.epi;
   maps.d = maps.a[0];
   maps.aux = maps.a[0];
@@ -755,7 +763,7 @@ static int setup_out_maps(Maps& maps, TileProg& prog) {
   prog.tma_in = 0;
   static const bool disabled = getenv("NS_GEMM_NO_TMA_STORE") != nullptr;
   const bool has_aux = (e.act == NS_ACT_GELU && e.aux_out);
-  if (disabled || e.out_f32 || prog.N <= 64 || !prog.vec_out || (has_aux && !prog.vec_aux)) return NS_OK;
+  if (disabled || e.out_f32 || bn < 128 || !prog.vec_out || (has_aux && !prog.vec_aux)) return NS_OK;
   auto mk = [&](CUtensorMap* m, void* base, long long ld) -> int {
     uint64_t dims[3] = {(uint64_t)prog.N, (uint64_t)prog.tout, (uint64_t)prog.batches};
     const long long bs = prog.batches > 1 ? prog.out_bs : static_cast<long long>(prog.tout) * prog.out_rs;
@@ -811,7 +819,7 @@ int gemm_nt_fast(long long M, int N, int K, const void* A, long long lda, const 
   Maps maps;
   TileProg prog;
   memset(&prog, 0, sizeof(prog));
-  const int bn = (N > 128) ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
+  const int bn = choose_bn((M + kBM - 1) / kBM, N);
   {
     uint64_t dims[4] = {(uint64_t)K, 1, (uint64_t)M, 1};
     uint64_t str[3] = {(uint64_t)lda * 2, (uint64_t)lda * 2, (uint64_t)lda * 2 * (uint64_t)M};
@@ -856,8 +864,8 @@ int gemm_nt_fast(long long M, int N, int K, const void* A, long long lda, const 
   prog.ldd = ldd;
   prog.D = D;
   fill_epi(prog, epi);
-  if (int r = setup_out_maps(maps, prog)) return r;
-  return dispatch_nt(maps, prog, st);
+  if (int r = setup_out_maps(maps, prog, bn)) return r;
+  return dispatch_nt(maps, prog, st, bn);
 }
 
 // Implicit-GEMM k=3 convolution forward on channels-last bf16 (see ns_conv3_fwd).
@@ -869,7 +877,7 @@ int conv3_fwd_fast(int B, int Tin, int Cp, int N, int stride, const void* x, con
   TileProg prog;
   memset(&prog, 0, sizeof(prog));
   const int Tout = Tin / stride;
-  const int bn = (N > 128) ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
+  const int bn = choose_bn(static_cast<long long>(B) * ((Tout + kBM - 1) / kBM), N);
   uint64_t dims[4] = {(uint64_t)Cp, (uint64_t)stride, (uint64_t)Tout, (uint64_t)B};
   uint64_t str[3] = {(uint64_t)Cp * 2, (uint64_t)Cp * 2 * stride, (uint64_t)Cp * 2 * (uint64_t)Tin};
   uint32_t box[4] = {kBK, 1, kBM, 1};
@@ -902,8 +910,8 @@ int conv3_fwd_fast(int B, int Tin, int Cp, int N, int stride, const void* x, con
   prog.ldd = N;
   prog.D = y;
   fill_epi(prog, epi);
-  if (int r = setup_out_maps(maps, prog)) return r;
-  return dispatch_nt(maps, prog, st);
+  if (int r = setup_out_maps(maps, prog, bn)) return r;
+  return dispatch_nt(maps, prog, st, bn);
 }
 
 // Input gradient of the stride-2 conv: one launch per output-row parity (see ns_conv3_dgrad).
@@ -912,7 +920,7 @@ int conv3_dgrad_fast(int B, int Tin, int Cp, int N, int stride, const void* dz, 
   if (stride != 2 || N % 16 != 0 || Cp % 8 != 0 || !aligned16(dz) || !aligned16(wt) || Tin % 2 != 0)
     return NS_ERR_UNSUPPORTED;
   const int Tout = Tin / 2;
-  const int bn = (Cp > 128) ? 256 : (Cp > 64 ? 128 : (Cp > 32 ? 64 : 32));
+  const int bn = choose_bn(static_cast<long long>(B) * ((Tout + kBM - 1) / kBM), Cp);
   Maps maps;
   uint64_t dims[4] = {(uint64_t)N, 1, (uint64_t)Tout, (uint64_t)B};
   uint64_t str[3] = {(uint64_t)N * 2, (uint64_t)N * 2, (uint64_t)N * 2 * (uint64_t)Tout};
@@ -946,8 +954,8 @@ int conv3_dgrad_fast(int B, int Tin, int Cp, int N, int stride, const void* dz, 
     prog.ldd = Cp;
     prog.D = dx;
     fill_epi(prog, epi);
-    if ((r = setup_out_maps(maps, prog))) return r;
-    r = dispatch_nt(maps, prog, st);
+    if ((r = setup_out_maps(maps, prog, bn))) return r;
+    r = dispatch_nt(maps, prog, st, bn);
     if (r) return r;
   }
   return NS_OK;

@@ -147,7 +147,7 @@ class WhisperEEGEngine:
         self.device = torch.device(device)
         self.ws = Workspace(self.device)
         self.has_lora = lora is not None
-        self.fuse_cross_bwd = True       # decoder cross-attention backward through the fused single-pass kernel
+        self.fuse_cross_bwd = False      # decoder cross-attention backward through the fused single-pass kernel
         self.layout = TrainableLayout(dims, with_lora=self.has_lora)
         self.flat = torch.zeros(self.layout.size, dtype=torch.float32, device=self.device)
         self.grad = torch.zeros_like(self.flat)
@@ -241,6 +241,7 @@ class WhisperEEGEngine:
         wkv = torch.cat(kv_w, dim=0)                                     # (Nd*2d, d): [k0; v0; k1; v1; ...]
         W["dec.wkv"] = self._c(wkv); W["dec.wkv_t"] = self._ct(wkv); W["dec.bkv"] = torch.cat(kv_b)
         self.P = W
+        self._lora_tb = None             # LoRA operand views / transpose job table are rebuilt by pack_trainable
         self.suppress = torch.tensor(list(dm.begin_suppress_tokens), dtype=torch.int32, device=dev)
         self._packed = False
 
@@ -260,29 +261,35 @@ class WhisperEEGEngine:
                 lc = self.flat[lay.lora_begin: lay.lora_end]
             else:
                 lc = ops.cast(self.flat[lay.lora_begin: lay.lora_end], self.ws.get("lora_c", (nl,), self.dtype))
+            if getattr(self, "_lora_tb", None) is None or self._lora_tb_ptr != lc.data_ptr():
+                # operand views + the (src, dst) list of the 10 transposes per layer; the buffers never move, so the job table
+                # is built once and every later refresh is ONE ns_transpose_batched launch
+                def cv(name):
+                    off, shape = lay.entries[name]
+                    return lc[off - lay.lora_begin: off - lay.lora_begin + int(math.prod(shape))].view(shape)
 
-            def cv(name):
-                off, shape = lay.entries[name]
-                return lc[off - lay.lora_begin: off - lay.lora_begin + int(math.prod(shape))].view(shape)
-
-            for i in range(dm.enc_layers):
-                k = f"enc{i}"
-                aq = cv(lora_module_name(i, "q_proj") + ".lora_A.default.weight")
-                bq = cv(lora_module_name(i, "q_proj") + ".lora_B.default.weight")
-                off_a = lay.entries[lora_module_name(i, "q_proj") + ".lora_A.default.weight"][0] - lay.lora_begin
-                off_b = lay.entries[lora_module_name(i, "q_proj") + ".lora_B.default.weight"][0] - lay.lora_begin
-                W[k + ".A_qkv"] = lc[off_a: off_a + 3 * r * d].view(3 * r, d)        # stacked [Aq;Ak;Av]
-                W[k + ".B_qkv"] = lc[off_b: off_b + 3 * d * r].view(3 * d, r)        # stacked [Bq;Bk;Bv]
-                W[k + ".A_qkv_t"] = ops.transpose(W[k + ".A_qkv"], self.ws.get(k + ".A_qkv_t", (d, 3 * r), self.dtype))
-                for g in range(3):
-                    W[k + f".B_qkv_t{g}"] = ops.transpose(W[k + ".B_qkv"][g * d:(g + 1) * d],
-                                                           self.ws.get(k + f".B_qkv_t{g}", (r, d), self.dtype))
-                for t, fin, fout in (("out_proj", d, d), ("fc1", d, F), ("fc2", F, d)):
-                    a = cv(lora_module_name(i, t) + ".lora_A.default.weight")
-                    b = cv(lora_module_name(i, t) + ".lora_B.default.weight")
-                    W[f"{k}.A_{t}"] = a; W[f"{k}.B_{t}"] = b
-                    W[f"{k}.A_{t}_t"] = ops.transpose(a, self.ws.get(f"{k}.A_{t}_t", (fin, r), self.dtype))
-                    W[f"{k}.B_{t}_t"] = ops.transpose(b, self.ws.get(f"{k}.B_{t}_t", (r, fout), self.dtype))
+                pairs = []
+                for i in range(dm.enc_layers):
+                    k = f"enc{i}"
+                    off_a = lay.entries[lora_module_name(i, "q_proj") + ".lora_A.default.weight"][0] - lay.lora_begin
+                    off_b = lay.entries[lora_module_name(i, "q_proj") + ".lora_B.default.weight"][0] - lay.lora_begin
+                    W[k + ".A_qkv"] = lc[off_a: off_a + 3 * r * d].view(3 * r, d)        # stacked [Aq;Ak;Av]
+                    W[k + ".B_qkv"] = lc[off_b: off_b + 3 * d * r].view(3 * d, r)        # stacked [Bq;Bk;Bv]
+                    W[k + ".A_qkv_t"] = self.ws.get(k + ".A_qkv_t", (d, 3 * r), self.dtype)
+                    pairs.append((W[k + ".A_qkv"], W[k + ".A_qkv_t"]))
+                    for g in range(3):
+                        W[k + f".B_qkv_t{g}"] = self.ws.get(k + f".B_qkv_t{g}", (r, d), self.dtype)
+                        pairs.append((W[k + ".B_qkv"][g * d:(g + 1) * d], W[k + f".B_qkv_t{g}"]))
+                    for t, fin, fout in (("out_proj", d, d), ("fc1", d, F), ("fc2", F, d)):
+                        a = cv(lora_module_name(i, t) + ".lora_A.default.weight")
+                        b = cv(lora_module_name(i, t) + ".lora_B.default.weight")
+                        W[f"{k}.A_{t}"] = a; W[f"{k}.B_{t}"] = b
+                        W[f"{k}.A_{t}_t"] = self.ws.get(f"{k}.A_{t}_t", (fin, r), self.dtype)
+                        W[f"{k}.B_{t}_t"] = self.ws.get(f"{k}.B_{t}_t", (r, fout), self.dtype)
+                        pairs += [(a, W[f"{k}.A_{t}_t"]), (b, W[f"{k}.B_{t}_t"])]
+                self._lora_tb = ops.TransposeBatch(pairs, self.device)
+                self._lora_tb_ptr = lc.data_ptr()
+            self._lora_tb.run()
         Cp = dm.Cp
         for key, name, cin, cp in (("stemA", "model.encoder.conv1.0", dm.eeg_ch, Cp), ("stemB", "model.encoder.conv1.2", d, d),
                                    ("stemC", "model.encoder.conv2", d, d)):
@@ -434,7 +441,8 @@ class WhisperEEGEngine:
         return hd
 
     def forward_loss(self, x: torch.Tensor, labels: Optional[torch.Tensor] = None, decoder_input_ids: Optional[torch.Tensor] = None,
-                     aug: Optional[dict] = None, save: bool = True, logits_dtype: Optional[torch.dtype] = None):
+                     aug: Optional[dict] = None, save: bool = True, logits_dtype: Optional[torch.dtype] = None,
+                     ce_grad_scale: Optional[float] = None):
         """model(input_features, labels) -> (loss (0-d fp32 tensor or None), logits (B,L,V) view, enc (B,S,d)).
         utils/load_model.py:976-1070."""
         dm, W, ws, dt = self.dims, self.P, self.ws, self.dtype
@@ -471,7 +479,12 @@ class WhisperEEGEngine:
             row_loss = ws.get("row_loss", (ML,), torch.float32)
             loss_sum = ws.get("loss_sum", (1,), torch.float32)
             n_valid = ws.get("n_valid", (1,), torch.int32)
-            ops.cross_entropy(logits, dm.vocab, lab, row_loss, loss_sum, n_valid, write_grad=False)
+            # ce_grad_scale: the training step never looks at the logits again, so the same launch also turns them into
+            # dlogits (softmax - onehot) * scale / n_valid in place and backward() skips its own cross-entropy pass
+            fuse = ce_grad_scale is not None and save
+            ops.cross_entropy(logits, dm.vocab, lab, row_loss, loss_sum, n_valid, write_grad=fuse,
+                              grad_scale=ce_grad_scale if fuse else 1.0)
+            self._dlogits_ready = fuse
             loss = (loss_sum / n_valid.to(torch.float32).clamp_min(1.0)).squeeze(0)
         return loss, logits.view(B, L, dm.Vp)[:, :, :dm.vocab], enc
 
@@ -488,7 +501,10 @@ class WhisperEEGEngine:
         self.grad.zero_()
         # ---- loss -> logits (in place) -> decoder output
         logits = ws.bufs["logits"]
-        ops.cross_entropy(logits, dm.vocab, self._labels, ws.bufs["row_loss"], None, ws.bufs["n_valid"], write_grad=True, grad_scale=grad_scale)
+        if getattr(self, "_dlogits_ready", False):
+            self._dlogits_ready = False          # forward_loss(ce_grad_scale=...) already left dlogits in the buffer
+        else:
+            ops.cross_entropy(logits, dm.vocab, self._labels, ws.bufs["row_loss"], None, ws.bufs["n_valid"], write_grad=True, grad_scale=grad_scale)
         if logits.dtype != dt:
             dl = ops.cast(logits, ws.get("dlogits_c", logits.shape, dt))
         else:
@@ -650,7 +666,7 @@ class WhisperEEGEngine:
     def train_step(self, x, labels, lr: float, aug: Optional[dict] = None, all_reduce=None):
         """One Trainer.training_step + optimizer step.  `all_reduce(flat_grad)` is the data-parallel hook."""
         self.pack_trainable()
-        loss, _, _ = self.forward_loss(x, labels, aug=aug, save=True)
+        loss, _, _ = self.forward_loss(x, labels, aug=aug, save=True, ce_grad_scale=1.0)
         self.backward()
         if all_reduce is not None:
             all_reduce(self.grad)

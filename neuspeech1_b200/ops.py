@@ -191,6 +191,31 @@ def transpose(src, dst, scale: float = 1.0):
     return dst
 
 
+class TransposeBatch:
+    """A fixed set of (src, dst) transposes refreshed with one launch (ns_transpose_batched).  The job table lives on the
+    device; the tensors it points at must stay alive and in place (the engine's workspace guarantees that)."""
+
+    def __init__(self, pairs, device):
+        import numpy as np
+        assert pairs
+        self.sdt, self.ddt = ns_dtype(pairs[0][0]), ns_dtype(pairs[0][1])
+        self.keep = pairs
+        jobs = (_abi.TransposeJob * len(pairs))()
+        self.max_ldd = self.max_cols = 0
+        for i, (src, dst) in enumerate(pairs):
+            assert ns_dtype(src) == self.sdt and ns_dtype(dst) == self.ddt and src.dim() == 2 and dst.dim() == 2
+            rows, cols = src.shape
+            assert dst.shape[0] == cols and dst.stride(0) >= rows
+            jobs[i] = _abi.TransposeJob(_p(src), _p(dst), rows, cols, src.stride(0), dst.stride(0), 1.0, 0)
+            self.max_ldd = max(self.max_ldd, dst.stride(0)); self.max_cols = max(self.max_cols, cols)
+        raw = np.frombuffer(bytes(jobs), dtype=np.uint8).copy()
+        self.table = torch.from_numpy(raw).to(device)
+        self.n = len(pairs)
+
+    def run(self):
+        _call("ns_transpose_batched", (0, 0), self.sdt, self.ddt, self.n, self.max_ldd, self.max_cols, _p(self.table), _stream())
+
+
 def conv_weight_pack(w, w_tap, w_tap_t):
     N, Cin, _ = w.shape
     ref = w_tap if w_tap is not None else w_tap_t

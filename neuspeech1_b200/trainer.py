@@ -31,7 +31,7 @@ class Trainer:
         total = self.total_steps or (self.warmup_steps * 1000)
         lr = linear_warmup_decay(self.step + 1, self.lr, self.warmup_steps, total)   # HF steps the scheduler after the optimizer
         eng.pack_trainable()
-        loss, _, _ = eng.forward_loss(input_features, labels, aug=aug, save=True)
+        loss, _, _ = eng.forward_loss(input_features, labels, aug=aug, save=True, ce_grad_scale=1.0)
         eng.backward()
         if self.dp.world > 1:
             self.dp.all_reduce_mean(eng.grad)

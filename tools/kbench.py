@@ -132,6 +132,31 @@ def bench_gemm(B, iters, out):
     out["gemm"] = res
 
 
+def bench_head(B, iters, out):
+    """loss head: tied vocabulary projection (utils/load_model.py:1047), cross-entropy, dlogits @ E."""
+    L, d, V = 32, 512, 51865
+    Vp = (V + 15) // 16 * 16
+    M = B * L
+    g = torch.Generator().manual_seed(2)
+    y = (torch.randn(M, d, generator=g)).to(DEV, torch.bfloat16)
+    E = (torch.randn(V, d, generator=g) * 0.02).to(DEV, torch.bfloat16)
+    Et = torch.zeros(d, Vp, dtype=torch.bfloat16, device=DEV); Et[:, :V] = E.t()
+    logits = torch.empty(M, Vp, dtype=torch.bfloat16, device=DEV)
+    labels = torch.randint(0, V, (M,), generator=g).to(DEV)
+    row_loss = torch.empty(M, device=DEV); loss_sum = torch.zeros(1, device=DEV); nv = torch.zeros(1, dtype=torch.int32, device=DEV)
+    dy = torch.empty(M, d, dtype=torch.bfloat16, device=DEV)
+    res = {}
+    t = timeit(lambda: ops.gemm_nt(y, E, logits, ops.epilogue(), N=V), iters)
+    res["logits"] = {"ms": t, "tflops": 2.0 * M * V * d / t / 1e9}
+    t = timeit(lambda: ops.cross_entropy(logits, V, labels, row_loss, loss_sum, nv, write_grad=False), iters)
+    res["ce_fwd"] = {"ms": t, "gbs": logits.numel() * 2 / t / 1e6}
+    t = timeit(lambda: ops.cross_entropy(logits, V, labels, row_loss, None, nv, write_grad=True), iters)
+    res["ce_bwd"] = {"ms": t, "gbs": 2 * logits.numel() * 2 / t / 1e6}
+    t = timeit(lambda: ops.gemm_nt(logits, Et, dy, ops.epilogue()), iters)
+    res["dlogits"] = {"ms": t, "tflops": 2.0 * M * Vp * d / t / 1e9}
+    out["head"] = res
+
+
 def bench_ln(B, iters, out):
     S, d = 1500, 512
     M = B * S
@@ -158,6 +183,8 @@ def main():
         bench_attn(a.B, a.iters, out)
     if "gemm" in a.what:
         bench_gemm(a.B, a.iters, out)
+    if "head" in a.what:
+        bench_head(a.B, a.iters, out)
     if "ln" in a.what:
         bench_ln(a.B, a.iters, out)
     s = json.dumps(out, indent=1)
