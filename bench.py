@@ -252,12 +252,13 @@ def run_ours(args):
     e2e_value = world * B * 1e3 / ms_e2e
 
     line = None
+    # ---- per-kernel profile of one step (CUDA events around every ns_* launch on the launching stream).  Every rank runs the
+    # step (it contains the gradient all-reduce, a collective); only rank 0 keeps the record.
+    ops.profile_begin()
+    step_resident()
+    prof = ops.profile_end()
     if rank == 0:
         peaks = measured_peaks()
-        # ---- per-kernel profile of one step (CUDA events around every ns_* launch on the launching stream)
-        ops.profile_begin()
-        step_resident()
-        prof = ops.profile_end()
         fam = {}
         for r in prof:
             f = fam.setdefault(r["name"], dict(ms=0.0, flops=0.0, bytes=0.0, n=0))
