@@ -491,6 +491,7 @@ attn_bwd_dq_convert_kernel(long long rows, int Lq, int W, long long q_bs, long l
 // ---------------------------------------------------------------------------------------------------- host side
 static long long* g_attn_trace = nullptr;
 void set_attn_trace(long long* p) { g_attn_trace = p; }
+long long* get_attn_trace() { return g_attn_trace; }
 static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static int head_map128(CUtensorMap* m, const void* base, int H, int L, int B, long long bs, long long rs) {

@@ -22,6 +22,8 @@
 namespace ns {
 using namespace sm100;
 
+long long* get_attn_trace();   // ns_attention_bwd_fused.cu (developer aid)
+
 // ------------------------------------------------------------------------------------------------ tensor maps
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -112,6 +114,7 @@ struct TileProg {
   int tma_in;       // with tma_out: 1 = aux_in (NS_ACT_DGELU), 2 = residual tiles arrive through TMA + shared memory
   int in_batched;   // tma_in: the input tensor has a batch coordinate (0: one [rows][N] table shared by all batches)
   int m_fast;       // tile raster: 1 = consecutive tiles walk M first (small M, large N: the weight tile is the one to reuse)
+  long long* trace; // developer aid (ns_debug_attn_trace buffer): CTAs 0/1 record (tag, clock64) of producer / MMA events
   int stages;       // operand ring depth (what fits beside the staging tiles)
   int staging_tiles;  // 0, 2 (one output tile per column half) or 4 (+ one aux-output or input tile per half)
 };
@@ -129,8 +132,12 @@ constexpr int kBK = 64;
 constexpr int kABytes = kBM * kBK * 2;
 constexpr int kNtThreads = 384;
 
-template <int BN> struct NtCfg {
-  static constexpr int kBBytes = BN * kBK * 2;
+// CG = 2: the kernel runs as CTA pairs (clusters of 2, tcgen05 cta_group::2).  A pair owns a 256-row x BN tile: each CTA
+// stages its own 128 A rows and HALF of the weight tile (BN/2 rows), the leader issues M = 256 MMAs that read both halves,
+// and each CTA's TMEM receives its 128 accumulator rows.  Per MMA every SM then moves 8 KB through shared memory instead of
+// 12 KB and fetches a third less from L2 -- the two limits of the single-CTA kernel on the encoder shapes.
+template <int BN, int CG = 1> struct NtCfg {
+  static constexpr int kBBytes = (BN / CG) * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kMaxSmem = 232448 - 1024;      // 227 KB opt-in limit minus the 1 KB the runtime reserves per CTA
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
@@ -192,10 +199,10 @@ __device__ __forceinline__ void store32_f32(float* p, bool vec, int ncols, const
 }
 
 // ------------------------------------------------------------------------------------------------ NT kernel
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(kNtThreads, 1)
 gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TileProg p) {
-  using Cfg = NtCfg<BN>;
+  using Cfg = NtCfg<BN, CG>;
   const int S = p.stages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -212,7 +219,28 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.batches * p.tiles_per_batch * p.n_tiles;
+  // Work units.  CG = 1: one 128-row tile per CTA per step.  CG = 2: the pair walks "super tiles" of two consecutive row
+  // tiles (same column tile); this CTA takes row tile 2 * pair_index + rank.  An odd row-tile count leaves one phantom tile
+  // whose loads are all out of range (zero fill) and whose stores are clipped.
+  const int m_tiles_real = p.batches * p.tiles_per_batch;
+  const int m_units = (CG == 2) ? (m_tiles_real + 1) / 2 : m_tiles_real;
+  const int total_tiles = m_units * p.n_tiles;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int tile_first = (CG == 2) ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = (CG == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  int tr_n = 0;
+  auto trace = [&](int region, long long tag) {
+    if (p.trace != nullptr && blockIdx.x < 2 && tr_n < 512) {
+      p.trace[(region * 512 + tr_n) * 2] = tag;
+      p.trace[(region * 512 + tr_n) * 2 + 1] = clock64();
+      ++tr_n;
+    }
+  };
+  auto decode = [&](int tile, int& m_tile, int& n_tile) {
+    const int mu = p.m_fast ? tile % m_units : tile / p.n_tiles;
+    n_tile = p.m_fast ? tile / m_units : tile % p.n_tiles;
+    m_tile = (CG == 2) ? 2 * mu + static_cast<int>(cta_rank) : mu;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a[0]);
@@ -229,22 +257,22 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), 1);     // CG = 2: only the leader's copy is used; it counts the bytes of both CTAs
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8);   // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), 8 * CG);   // one arrive per epilogue warp (of both CTAs)
       mbar_init(in_full(a), 1);
     }
     mbar_fence_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (CG == 2) { tmem_alloc2(tmem_slot, Cfg::kTmemCols); tmem_relinquish2(); }
+    else { tmem_alloc(tmem_slot, Cfg::kTmemCols); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -256,10 +284,9 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tiles = p.batches * p.tiles_per_batch;
-        const int n_tile = p.m_fast ? tile / m_tiles : tile % p.n_tiles;
-        const int m_tile = p.m_fast ? tile % m_tiles : tile / p.n_tiles;
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+        int m_tile, n_tile;
+        decode(tile, m_tile, n_tile);
         const int b = m_tile / p.tiles_per_batch;
         const int t0 = (m_tile % p.tiles_per_batch) * kBM;
         const int n0 = n_tile * BN;
@@ -268,11 +295,22 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
           const int kbase = sg.a_ngrp > 0 ? (n0 / sg.a_ngrp) * sg.a_kstep : 0;
           for (int kb = 0; kb < sg.kblocks; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
+            trace(blockIdx.x == 0 ? 0 : 2, 100 + stage);
             const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
             const uint32_t sb = sa + kABytes;
-            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-            tma_load_4d(&maps.a[sg.a_map], full_bar(stage), sa, kbase + kb * kBK, sg.a_par, t0 + sg.a_off, b);
-            tma_load_3d(&maps.b[sg.b_map], full_bar(stage), sb, kb * kBK, n0, sg.b_tap);
+            if (CG == 2) {
+              // both CTAs' bytes are counted on the LEADER's barrier, which the leader arms with the pair's total.  The peer
+              // needs no arrive of its own: it cannot touch phase n+1 of a stage before the leader's MMAs of phase n have
+              // committed, and the phase cannot complete without the peer's bytes.
+              const uint32_t lead_full = mapa_cluster(full_bar(stage), 0);
+              if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+              tma_load_4d_2sm(&maps.a[sg.a_map], lead_full, sa, kbase + kb * kBK, sg.a_par, t0 + sg.a_off, b);
+              tma_load_3d_2sm(&maps.b[sg.b_map], lead_full, sb, kb * kBK, n0 + static_cast<int>(cta_rank) * (BN / 2), sg.b_tap);
+            } else {
+              mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+              tma_load_4d(&maps.a[sg.a_map], full_bar(stage), sa, kbase + kb * kBK, sg.a_par, t0 + sg.a_off, b);
+              tma_load_3d(&maps.b[sg.b_map], full_bar(stage), sb, kb * kBK, n0, sg.b_tap);
+            }
             if (++stage == S) { stage = 0; phase ^= 1u; }
           }
         }
@@ -281,11 +319,11 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
   } else if (warp == 1) {
     // ================================================================ MMA issuer
     setmaxnreg_dec<56>();
-    constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
+    constexpr uint32_t idesc = umma_idesc_bf16(kBM * CG, BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_first; tile < total_tiles && cta_rank == 0; tile += tile_step, ++it) {   // CG = 2: the leader issues
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -296,6 +334,7 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
         const Seg& sg = p.seg[s];
         for (int kb = 0; kb < sg.kblocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
+          if (lane == 0) trace(1, 200 + stage);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
@@ -305,16 +344,20 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
             const uint64_t bdesc = umma_smem_desc(sb, 16, 1024);
             for (int k = 0; k < ksteps; ++k) {
               // advance 16 elements (32 B) along K inside the 128B swizzle row: +2 in the (addr >> 4) field
-              umma_f16(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, accumulate);
+              if (CG == 2) umma_f16_cg2(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, accumulate);
+              else umma_f16(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, accumulate);
               accumulate = 1;
             }
-            umma_commit(empty_bar(stage));   // frees the smem stage when these MMAs have read it
+            // frees the smem stage (in both CTAs of a pair) when these MMAs have read it
+            if (CG == 2) umma_commit_mc2(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
           }
           __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
       }
-      if (elect_one()) umma_commit(tfull_bar(acc));
+      if (elect_one()) {
+        if (CG == 2) umma_commit_mc2(tfull_bar(acc), 3); else umma_commit(tfull_bar(acc));
+      }
       __syncwarp();
     }
   } else if (warp < 4) {
@@ -326,7 +369,6 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
     const int half = (warp - 4) >> 2;  // which half of the tile's columns
     constexpr int kHalfCols = (BN >= 64) ? BN / 2 : BN;
     const EpiDev& e = p.epi;
-    const int m_tiles = p.batches * p.tiles_per_batch;
     const bool use_tma = BN >= 128 && p.tma_out;
     const bool issuer = (q == 0);                                             // first warp of this column half
     const uint32_t out_stage = staging_base + static_cast<uint32_t>(half) * (kBM * 128);
@@ -334,25 +376,26 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
     uint32_t in_phase = 0;
     // epilogue input tile (aux_in / residual) of (tile, column chunk c) -> shared memory, by the elected issuer lane
     auto issue_in = [&](int tile_, int c_) {
-      const int n_tile_ = p.m_fast ? tile_ / m_tiles : tile_ % p.n_tiles;
-      const int m_tile_ = p.m_fast ? tile_ % m_tiles : tile_ / p.n_tiles;
+      int m_tile_, n_tile_;
+      decode(tile_, m_tile_, n_tile_);
       mbar_expect_tx(in_full(half), kBM * 128);
       tma_load_3d(&maps.in, in_full(half), in_stage, n_tile_ * BN + half * kHalfCols + c_, (m_tile_ % p.tiles_per_batch) * kBM,
                   p.in_batched ? m_tile_ / p.tiles_per_batch : 0);
     };
-    if (use_tma && p.tma_in && issuer && blockIdx.x < total_tiles) {
-      if (elect_one()) issue_in(blockIdx.x, 0);
+    if (use_tma && p.tma_in && issuer && tile_first < total_tiles) {
+      if (elect_one()) issue_in(tile_first, 0);
     }
+    const uint32_t lead_tempty0 = (CG == 2) ? mapa_cluster(tempty_bar(0), 0) : 0u;   // the leader's accumulator-free barriers
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
-      const int n_tile = p.m_fast ? tile / m_tiles : tile % p.n_tiles;
-      const int m_tile = p.m_fast ? tile % m_tiles : tile / p.n_tiles;
+      int m_tile, n_tile;
+      decode(tile, m_tile, n_tile);
       const int b = m_tile / p.tiles_per_batch;
       const int t = (m_tile % p.tiles_per_batch) * kBM + q * 32 + lane;
       const int n0 = n_tile * BN;
-      const bool valid = t < p.tout;
+      const bool valid = t < p.tout && m_tile < m_tiles_real;
       const long long row = static_cast<long long>(b) * p.out_bs + static_cast<long long>(t) * p.out_rs + p.out_off;
       const long long res_row = e.res_mod > 0 ? ((static_cast<long long>(t) * p.out_rs + p.out_off) % e.res_mod) : row;
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -472,7 +515,7 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
               if (elect_one()) {                                              // prefetch the next chunk (or the next tile's first)
                 const int c2 = c + 64;
                 if (c2 < kHalfCols && col0 + 64 < p.N) issue_in(tile, c2);
-                else if (tile + static_cast<int>(gridDim.x) < total_tiles) issue_in(tile + gridDim.x, 0);
+                else if (tile + tile_step < total_tiles) issue_in(tile + tile_step, 0);
               }
             }
           }
@@ -540,7 +583,9 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(lead_tempty0 + 8u * acc); else mbar_arrive(tempty_bar(acc));
+      }
     }
     if (use_tma && issuer) {
       if (elect_one()) bulk_wait0();                                          // outstanding tile stores of this thread
@@ -548,10 +593,10 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // nobody leaves while the peer may still signal / read this CTA
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CG == 2) tmem_dealloc2(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -703,25 +748,40 @@ gemm_tn_kernel(const __grid_constant__ TnMaps maps, const __grid_constant__ TnPr
 // ------------------------------------------------------------------------------------------------ host launchers
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <int BN>
+template <int BN, int CG>
 static int launch_nt(const Maps& maps, TileProg& prog, cudaStream_t st) {
-  using Cfg = NtCfg<BN>;
+  using Cfg = NtCfg<BN, CG>;
   static bool attr_done = false;
   if (!attr_done) {
-    NS_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kMaxSmem));
+    NS_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kMaxSmem));
     attr_done = true;
   }
   prog.n_tiles = (prog.N + BN - 1) / BN;
+  const long long m_tiles = static_cast<long long>(prog.batches) * prog.tiles_per_batch;
   // consecutive tiles should share the LARGER operand tile stream's counterpart: few M tiles and many N tiles (the tied
   // vocabulary projection) -> walk M first so each weight tile is fetched once and reused from L2
-  prog.m_fast = (static_cast<long long>(prog.batches) * prog.tiles_per_batch * 4 < prog.n_tiles) ? 1 : 0;
-  const long long total = static_cast<long long>(prog.batches) * prog.tiles_per_batch * prog.n_tiles;
-  const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
+  prog.m_fast = (m_tiles * 4 < prog.n_tiles) ? 1 : 0;
+  const long long units = ((CG == 2) ? (m_tiles + 1) / 2 : m_tiles) * prog.n_tiles;     // work units per CTA (pair)
+  int grid = static_cast<int>(units * CG < sm_count() ? units * CG : sm_count());
+  if (CG == 2) grid &= ~1;
   if (grid <= 0) return NS_OK;
   const bool has_aux = (prog.epi.act == NS_ACT_GELU && prog.epi.aux_out);
   prog.staging_tiles = (BN >= 128 && prog.tma_out) ? ((has_aux || prog.tma_in) ? 4 : 2) : 0;
   prog.stages = Cfg::stages_for(prog.staging_tiles);
-  gemm_nt_kernel<BN><<<grid, kNtThreads, Cfg::smem_bytes(prog.stages, prog.staging_tiles), st>>>(maps, prog);
+  prog.trace = get_attn_trace();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kNtThreads);
+  cfg.dynamicSmemBytes = Cfg::smem_bytes(prog.stages, prog.staging_tiles);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (CG == 2) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  NS_CUDA(cudaLaunchKernelEx(&cfg, gemm_nt_kernel<BN, CG>, maps, prog));
   NS_LAUNCH_CHECK();
   count(C_GEMM_TC);
   return NS_OK;
@@ -736,11 +796,19 @@ static int choose_bn(long long m_tiles, int N) {
   return bn;
 }
 
-static int dispatch_nt(const Maps& maps, TileProg& prog, cudaStream_t st, int bn) {
-  if (bn == 256) return launch_nt<256>(maps, prog, st);
-  if (bn == 128) return launch_nt<128>(maps, prog, st);
-  if (bn == 64) return launch_nt<64>(maps, prog, st);
-  return launch_nt<32>(maps, prog, st);
+// CTA pairs (cta_group::2) for the wide tiles when there is enough work to fill the pairs
+static int choose_cg(long long m_tiles, int N, int bn) {
+  static const bool disabled = getenv("NS_GEMM_NO_2CTA") != nullptr;
+  if (disabled || bn != 256) return 1;
+  const long long units = ((m_tiles + 1) / 2) * ((N + bn - 1) / bn);
+  return units * 2 >= static_cast<long long>(sm_count()) * 3 / 4 ? 2 : 1;
+}
+
+static int dispatch_nt(const Maps& maps, TileProg& prog, cudaStream_t st, int bn, int cg) {
+  if (bn == 256) return cg == 2 ? launch_nt<256, 2>(maps, prog, st) : launch_nt<256, 1>(maps, prog, st);
+  if (bn == 128) return launch_nt<128, 1>(maps, prog, st);
+  if (bn == 64) return launch_nt<64, 1>(maps, prog, st);
+  return launch_nt<32, 1>(maps, prog, st);
 }
 
 static void fill_epi(TileProg& prog, const EpiDev& e) {
@@ -820,6 +888,7 @@ int gemm_nt_fast(long long M, int N, int K, const void* A, long long lda, const 
   TileProg prog;
   memset(&prog, 0, sizeof(prog));
   const int bn = choose_bn((M + kBM - 1) / kBM, N);
+  const int cg = choose_cg((M + kBM - 1) / kBM, N, bn);
   {
     uint64_t dims[4] = {(uint64_t)K, 1, (uint64_t)M, 1};
     uint64_t str[3] = {(uint64_t)lda * 2, (uint64_t)lda * 2, (uint64_t)lda * 2 * (uint64_t)M};
@@ -828,7 +897,7 @@ int gemm_nt_fast(long long M, int N, int K, const void* A, long long lda, const 
     if (r) return r;
     uint64_t dimb[3] = {(uint64_t)K, (uint64_t)N, 1};
     uint64_t strb[2] = {(uint64_t)ldw * 2, (uint64_t)ldw * 2 * (uint64_t)N};
-    uint32_t boxb[3] = {kBK, (uint32_t)bn, 1};
+    uint32_t boxb[3] = {kBK, (uint32_t)(bn / cg), 1};
     r = make_map(&maps.b[0], W, 3, dimb, strb, boxb);
     if (r) return r;
   }
@@ -843,7 +912,7 @@ int gemm_nt_fast(long long M, int N, int K, const void* A, long long lda, const 
     if (r) return r;
     uint64_t dimb[3] = {(uint64_t)K2, (uint64_t)N, 1};
     uint64_t strb[2] = {(uint64_t)ldw2 * 2, (uint64_t)ldw2 * 2 * (uint64_t)N};
-    uint32_t boxb[3] = {kBK, (uint32_t)bn, 1};
+    uint32_t boxb[3] = {kBK, (uint32_t)(bn / cg), 1};
     r = make_map(&maps.b[1], W2, 3, dimb, strb, boxb);
     if (r) return r;
     prog.nseg = 2;
@@ -865,7 +934,7 @@ int gemm_nt_fast(long long M, int N, int K, const void* A, long long lda, const 
   prog.D = D;
   fill_epi(prog, epi);
   if (int r = setup_out_maps(maps, prog, bn)) return r;
-  return dispatch_nt(maps, prog, st, bn);
+  return dispatch_nt(maps, prog, st, bn, cg);
 }
 
 // Implicit-GEMM k=3 convolution forward on channels-last bf16 (see ns_conv3_fwd).
@@ -878,6 +947,7 @@ int conv3_fwd_fast(int B, int Tin, int Cp, int N, int stride, const void* x, con
   memset(&prog, 0, sizeof(prog));
   const int Tout = Tin / stride;
   const int bn = choose_bn(static_cast<long long>(B) * ((Tout + kBM - 1) / kBM), N);
+  const int cg = choose_cg(static_cast<long long>(B) * ((Tout + kBM - 1) / kBM), N, bn);
   uint64_t dims[4] = {(uint64_t)Cp, (uint64_t)stride, (uint64_t)Tout, (uint64_t)B};
   uint64_t str[3] = {(uint64_t)Cp * 2, (uint64_t)Cp * 2 * stride, (uint64_t)Cp * 2 * (uint64_t)Tin};
   uint32_t box[4] = {kBK, 1, kBM, 1};
@@ -885,7 +955,7 @@ int conv3_fwd_fast(int B, int Tin, int Cp, int N, int stride, const void* x, con
   if (r) return r;
   uint64_t dimb[3] = {(uint64_t)Cp, (uint64_t)N, 3};
   uint64_t strb[2] = {(uint64_t)Cp * 2, (uint64_t)Cp * 2 * (uint64_t)N};
-  uint32_t boxb[3] = {kBK, (uint32_t)bn, 1};
+  uint32_t boxb[3] = {kBK, (uint32_t)(bn / cg), 1};
   r = make_map(&maps.b[0], w, 3, dimb, strb, boxb);
   if (r) return r;
   maps.a[1] = maps.a[0];
@@ -911,7 +981,7 @@ int conv3_fwd_fast(int B, int Tin, int Cp, int N, int stride, const void* x, con
   prog.D = y;
   fill_epi(prog, epi);
   if (int r = setup_out_maps(maps, prog, bn)) return r;
-  return dispatch_nt(maps, prog, st, bn);
+  return dispatch_nt(maps, prog, st, bn, cg);
 }
 
 // Input gradient of the stride-2 conv: one launch per output-row parity (see ns_conv3_dgrad).
@@ -921,6 +991,7 @@ int conv3_dgrad_fast(int B, int Tin, int Cp, int N, int stride, const void* dz, 
     return NS_ERR_UNSUPPORTED;
   const int Tout = Tin / 2;
   const int bn = choose_bn(static_cast<long long>(B) * ((Tout + kBM - 1) / kBM), Cp);
+  const int cg = choose_cg(static_cast<long long>(B) * ((Tout + kBM - 1) / kBM), Cp, bn);
   Maps maps;
   uint64_t dims[4] = {(uint64_t)N, 1, (uint64_t)Tout, (uint64_t)B};
   uint64_t str[3] = {(uint64_t)N * 2, (uint64_t)N * 2, (uint64_t)N * 2 * (uint64_t)Tout};
@@ -929,7 +1000,7 @@ int conv3_dgrad_fast(int B, int Tin, int Cp, int N, int stride, const void* dz, 
   if (r) return r;
   uint64_t dimb[3] = {(uint64_t)N, (uint64_t)Cp, 3};
   uint64_t strb[2] = {(uint64_t)N * 2, (uint64_t)N * 2 * (uint64_t)Cp};
-  uint32_t boxb[3] = {kBK, (uint32_t)bn, 1};
+  uint32_t boxb[3] = {kBK, (uint32_t)(bn / cg), 1};
   r = make_map(&maps.b[0], wt, 3, dimb, strb, boxb);
   if (r) return r;
   maps.a[1] = maps.a[0];
@@ -955,7 +1026,7 @@ int conv3_dgrad_fast(int B, int Tin, int Cp, int N, int stride, const void* dz, 
     prog.D = dx;
     fill_epi(prog, epi);
     if ((r = setup_out_maps(maps, prog, bn))) return r;
-    r = dispatch_nt(maps, prog, st, bn);
+    r = dispatch_nt(maps, prog, st, bn, cg);
     if (r) return r;
   }
   return NS_OK;

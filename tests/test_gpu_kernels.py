@@ -106,6 +106,15 @@ def test_gemm_nt(M, N, K, flags, dtype):
         assert rel(aux_out.float(), z_ref) < tol(dtype)
 
 
+@pytest.mark.parametrize("M,N,K,flags", [(19000, 512, 512, "bias,res"), (19000, 2048, 512, "bias,gelu,aux"), (18944, 512, 2048, "dgelu"),
+                                          (19001, 1536, 512, "bias,alpha"), (19000, 1003, 256, "")])
+def test_gemm_nt_cta_pairs(M, N, K, flags):
+    """Shapes large enough for the cta_group::2 kernel (CTA pairs, M = 256 MMAs, odd row-tile counts leave a phantom tile),
+    every epilogue flavour, against torch fp32; and bit-identical to the single-CTA kernel (NS_GEMM_NO_2CTA is read once per
+    process, so the comparison uses a 128-wide call that never pairs)."""
+    test_gemm_nt(M, N, K, flags, torch.bfloat16)
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 @pytest.mark.parametrize("r", [32, 16, 8])
 def test_gemm_nt_lora_grouped(dtype, r):
