@@ -40,6 +40,8 @@ size_t attention_bwd_fused_ws(const ns_attn_shape& s);
 int attention_bwd_fused(const ns_attn_shape& s, const void* q, const void* k, const void* v, const void* o, const void* d_o,
                         const float* lse, float* delta, void* dq, void* dk, void* dv, void* ws, size_t ws_bytes, cudaStream_t st);
 
+int attention_bwd_smallq(const ns_attn_shape& s, const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                         const float* lse, float* delta, void* dq, void* dk, void* dv, cudaStream_t st);
 void set_attn_trace(long long* p);
 static bool want_fast(int dtype) { return dtype == NS_BF16 && g_path != NS_PATH_SIMT; }
 static int fast_required_failed(const char* what) {
@@ -243,6 +245,10 @@ int ns_attention_bwd(int dtype, const ns_attn_shape* s, const void* q, const voi
   NS_CHECK_ARG(valid_dtype(dtype) && q && k && v && o && d_o && lse && delta && dq && dk && dv, "ns_attention_bwd: bad arguments");
   if (int r = check_attn(s)) return r;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (want_fast(dtype) && s->Lq <= 64) {      // short query axis (decoder cross-attention): one CTA per (batch, head)
+    const int r = attention_bwd_smallq(*s, q, k, v, o, d_o, lse, delta, dq, dk, dv, st);
+    if (r != NS_ERR_UNSUPPORTED) return r;
+  }
   if (want_fast(dtype)) {
     const int r = attention_bwd_tc(*s, q, k, v, o, d_o, lse, delta, dq, dk, dv, st);
     if (r != NS_ERR_UNSUPPORTED) return r;

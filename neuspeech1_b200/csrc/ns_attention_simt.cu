@@ -286,8 +286,148 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_simt_kernel(const ns_attn_sh
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Tiny self-attention (Lq == Lk <= 32): the teacher-forced decoder self-attention of the training step (L = 32 label
+// positions, causal; utils/load_model.py:512-532).  ONE WARP per (batch, head), lane = query row; K / V (and in the
+// backward Q / dO, P / dS) live in shared memory and are read as broadcasts, so the softmax needs no cross-lane traffic.
+// The general kernels above spend ~30 us (forward) / ~120 us (backward, three launches) on this 32 x 32 problem.
+template <typename T, int DH>
+__global__ void __launch_bounds__(32) attn_tiny_fwd_kernel(const ns_attn_shape s, const T* __restrict__ q, const T* __restrict__ k,
+                                                           const T* __restrict__ v, T* __restrict__ o, float* __restrict__ lse) {
+  __shared__ float Ks[32][DH + 1];
+  __shared__ float Vs[32][DH + 1];
+  const int h = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;
+  const int L = s.Lq;
+  for (int e = lane; e < 32 * DH; e += 32) {
+    const int r = e / DH, d = e % DH;
+    float kv = 0.f, vv = 0.f;
+    if (r < L) {
+      kv = to_f<T>(k[b * s.k_bs + static_cast<long long>(r) * s.k_rs + h * DH + d]);
+      vv = to_f<T>(v[b * s.v_bs + static_cast<long long>(r) * s.v_rs + h * DH + d]);
+    }
+    Ks[r][d] = kv; Vs[r][d] = vv;
+  }
+  float qr[DH], acc[DH];
+  const bool act = lane < L;
+  const T* qp = q + b * s.q_bs + static_cast<long long>(act ? lane : 0) * s.q_rs + h * DH;
+#pragma unroll
+  for (int d = 0; d < DH; ++d) { qr[d] = act ? to_f<T>(qp[d]) : 0.f; acc[d] = 0.f; }
+  __syncwarp();
+  float m = -INFINITY, l = 0.f;
+  const int jend = s.causal ? lane + 1 : L;       // Lq == Lk: query i sees keys j <= i
+  for (int j = 0; j < L; ++j) {
+    float sc = 0.f;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) sc = fmaf(qr[d], Ks[j][d], sc);
+    if (j < jend && act) {
+      const float mn = fmaxf(m, sc);
+      const float corr = __expf(m - mn), pj = __expf(sc - mn);
+      l = l * corr + pj;
+      m = mn;
+#pragma unroll
+      for (int d = 0; d < DH; ++d) acc[d] = fmaf(pj, Vs[j][d], acc[d] * corr);
+    }
+  }
+  if (act) {
+    const float inv = 1.0f / l;
+    T* op = o + b * s.o_bs + static_cast<long long>(lane) * s.o_rs + h * DH;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) op[d] = from_f<T>(acc[d] * inv);
+    if (lse) lse[(static_cast<long long>(b) * s.H + h) * L + lane] = m + logf(l);
+  }
+}
+
+template <typename T, int DH>
+__global__ void __launch_bounds__(32) attn_tiny_bwd_kernel(const ns_attn_shape s, const T* __restrict__ q, const T* __restrict__ k,
+                                                           const T* __restrict__ v, const T* __restrict__ d_o, const float* __restrict__ lse,
+                                                           float* __restrict__ delta_out, T* __restrict__ dq, T* __restrict__ dk,
+                                                           T* __restrict__ dv) {
+  extern __shared__ float sm[];
+  float (*Ks)[DH + 1] = reinterpret_cast<float (*)[DH + 1]>(sm);
+  float (*Vs)[DH + 1] = Ks + 32;
+  float (*Qs)[DH + 1] = Vs + 32;
+  float (*Os)[DH + 1] = Qs + 32;                  // dO
+  float (*Ps)[33] = reinterpret_cast<float (*)[33]>(sm + 4 * 32 * (DH + 1));
+  float (*Ss)[33] = Ps + 32;                      // dS
+  const int h = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;
+  const int L = s.Lq;
+  for (int e = lane; e < 32 * DH; e += 32) {
+    const int r = e / DH, d = e % DH;
+    float kv = 0.f, vv = 0.f, qv = 0.f, ov = 0.f;
+    if (r < L) {
+      kv = to_f<T>(k[b * s.k_bs + static_cast<long long>(r) * s.k_rs + h * DH + d]);
+      vv = to_f<T>(v[b * s.v_bs + static_cast<long long>(r) * s.v_rs + h * DH + d]);
+      qv = to_f<T>(q[b * s.q_bs + static_cast<long long>(r) * s.q_rs + h * DH + d]);
+      ov = to_f<T>(d_o[b * s.o_bs + static_cast<long long>(r) * s.o_rs + h * DH + d]);
+    }
+    Ks[r][d] = kv; Vs[r][d] = vv; Qs[r][d] = qv; Os[r][d] = ov;
+  }
+  __syncwarp();
+  const bool act = lane < L;
+  const int jend = s.causal ? lane + 1 : L;
+  const float my_lse = act ? lse[(static_cast<long long>(b) * s.H + h) * L + lane] : 0.f;
+  // ---- phase A (lane = query i): P, dP rows; delta_i = sum_j p_ij dp_ij (= dO_i . O_i); dS; dq_i
+  float dlt = 0.f;
+  for (int j = 0; j < L; ++j) {
+    float sc = 0.f, dp = 0.f;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) {
+      sc = fmaf(Qs[lane][d], Ks[j][d], sc);
+      dp = fmaf(Os[lane][d], Vs[j][d], dp);
+    }
+    const float pj = (act && j < jend) ? __expf(sc - my_lse) : 0.f;
+    Ps[lane][j] = pj;
+    Ss[lane][j] = dp;
+    dlt = fmaf(pj, dp, dlt);
+  }
+  if (act && delta_out) delta_out[(static_cast<long long>(b) * s.H + h) * L + lane] = dlt;
+  float acc[DH];
+#pragma unroll
+  for (int d = 0; d < DH; ++d) acc[d] = 0.f;
+  for (int j = 0; j < L; ++j) {
+    const float ds = Ps[lane][j] * (Ss[lane][j] - dlt);
+    Ss[lane][j] = ds;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) acc[d] = fmaf(ds, Ks[j][d], acc[d]);
+  }
+  if (act) {
+    T* p = dq + b * s.q_bs + static_cast<long long>(lane) * s.q_rs + h * DH;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) p[d] = from_f<T>(acc[d]);
+  }
+  __syncwarp();
+  // ---- phase B (lane = key j): dv_j = sum_i p_ij dO_i ; dk_j = sum_i ds_ij q_i
+  float av[DH];
+#pragma unroll
+  for (int d = 0; d < DH; ++d) { acc[d] = 0.f; av[d] = 0.f; }
+  for (int i = 0; i < L; ++i) {
+    const float pij = Ps[i][lane], dsij = Ss[i][lane];
+#pragma unroll
+    for (int d = 0; d < DH; ++d) {
+      av[d] = fmaf(pij, Os[i][d], av[d]);
+      acc[d] = fmaf(dsij, Qs[i][d], acc[d]);
+    }
+  }
+  if (act) {
+    T* pk = dk + b * s.k_bs + static_cast<long long>(lane) * s.k_rs + h * DH;
+    T* pv = dv + b * s.v_bs + static_cast<long long>(lane) * s.v_rs + h * DH;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) { pk[d] = from_f<T>(acc[d]); pv[d] = from_f<T>(av[d]); }
+  }
+}
+
+template <typename T, int DH>
+static bool tiny_eligible(const ns_attn_shape& s) { return s.Lq == s.Lk && s.Lq <= 32 && s.H <= 65535 && s.B <= 65535; }
+
 template <typename T, int DH>
 static int attn_fwd_simt_t(const ns_attn_shape& s, const void* q, const void* k, const void* v, void* o, float* lse, cudaStream_t st) {
+  if (tiny_eligible<T, DH>(s)) {
+    attn_tiny_fwd_kernel<T, DH><<<dim3(s.H, s.B), 32, 0, st>>>(s, reinterpret_cast<const T*>(q), reinterpret_cast<const T*>(k),
+                                                             reinterpret_cast<const T*>(v), reinterpret_cast<T*>(o), lse);
+    NS_LAUNCH_CHECK();
+    count(C_ATTN_SIMT);
+    return NS_OK;
+  }
   dim3 grid((s.Lq + kQPB - 1) / kQPB, s.H, s.B);
   attn_fwd_simt_kernel<T, DH><<<grid, 256, 0, st>>>(s, reinterpret_cast<const T*>(q), reinterpret_cast<const T*>(k),
                                                     reinterpret_cast<const T*>(v), reinterpret_cast<T*>(o), lse);
@@ -299,6 +439,20 @@ static int attn_fwd_simt_t(const ns_attn_shape& s, const void* q, const void* k,
 template <typename T, int DH>
 static int attn_bwd_simt_t(const ns_attn_shape& s, const void* q, const void* k, const void* v, const void* o, const void* d_o,
                            const float* lse, float* delta, void* dq, void* dk, void* dv, cudaStream_t st) {
+  if (tiny_eligible<T, DH>(s)) {
+    constexpr int smem = (4 * 32 * (DH + 1) + 2 * 32 * 33) * 4;
+    static bool attr_done = false;
+    if (!attr_done) {
+      NS_CUDA(cudaFuncSetAttribute(attn_tiny_bwd_kernel<T, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr_done = true;
+    }
+    attn_tiny_bwd_kernel<T, DH><<<dim3(s.H, s.B), 32, smem, st>>>(s, reinterpret_cast<const T*>(q), reinterpret_cast<const T*>(k),
+                                                                 reinterpret_cast<const T*>(v), reinterpret_cast<const T*>(d_o), lse, delta,
+                                                                 reinterpret_cast<T*>(dq), reinterpret_cast<T*>(dk), reinterpret_cast<T*>(dv));
+    NS_LAUNCH_CHECK();
+    count(C_ATTN_SIMT);
+    return NS_OK;
+  }
   const long long total = static_cast<long long>(s.B) * s.H * s.Lq;
   attn_delta_kernel<T, DH><<<static_cast<unsigned>((total + 7) / 8), 256, 0, st>>>(s, reinterpret_cast<const T*>(o),
                                                                                     reinterpret_cast<const T*>(d_o), delta);

@@ -11,6 +11,8 @@
 #include "ns_common.cuh"
 #include "ns_sm100.cuh"
 
+#include <stdlib.h>
+
 namespace ns {
 using namespace sm100;
 
@@ -22,7 +24,10 @@ struct AttnFwdProg {
   long long o_bs, o_rs;
   __nv_bfloat16* o;
   float* lse;
+  long long* trace;     // developer aid (ns_debug_attn_trace): CTA (0,0,0) of the ping-pong kernel records (tag, clock64)
+  int take_turns;
 };
+long long* get_attn_trace();
 
 constexpr int kAtThreads = 192;
 constexpr int kTile = 128 * 64 * 2;                          // one [128][64] bf16 tile, 128B-swizzled
@@ -230,6 +235,273 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Forward, ping-pong variant for long query axes (the encoder: Lq = 1500).  One CTA per SM owns TWO 128-query tiles of one
+// (batch, head) and streams the key/value tiles once for both:
+//   warp 0        TMA producer : Q0, Q1 once; K / V tiles of 128 keys through 3-stage rings
+//   warp 1        MMA issuer   : one elected thread; S_w = Q_w K^T (SS, N = 128), O_w += P_w V (TS, N = 64) for w = 0, 1,
+//                                issued S0 S1 | PV0 S0' PV1 S1' | ... so that while softmax group 0 works on its tile the
+//                                tensor pipe serves group 1 and vice versa
+//   warps 4..7    softmax group 0 (query tile 0), warps 8..11 softmax group 1: one query row per thread
+// The exponentials (MUFU, 16 per clock per SM) bound this kernel at head_dim 64; with the two groups half a period apart
+// the MUFU pipe always has one group feeding it, instead of idling during every S / PV round trip.
+// TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384) P0 [384,448) P1 [448,512).
+constexpr int kF2Threads = 384;
+constexpr int kF2Stages = 3;
+constexpr int kF2Smem = kTile * (2 + 2 * kF2Stages) + 1024 + 256;
+
+__global__ void __launch_bounds__(kF2Threads, 1)
+attn_fwd2_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnFwdProg p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  auto sQ = [&](int w) { return smem_base + kTile * w; };
+  auto sK = [&](int s) { return smem_base + kTile * (2 + s); };
+  auto sV = [&](int s) { return smem_base + kTile * (2 + kF2Stages + s); };
+  const uint32_t bar = smem_base + kTile * (2 + 2 * kF2Stages);
+  const uint32_t q_full = bar;
+  auto k_full = [&](int s) { return bar + 8u * (1 + s); };
+  auto v_full = [&](int s) { return bar + 8u * (4 + s); };
+  auto k_empty = [&](int s) { return bar + 8u * (7 + s); };
+  auto v_empty = [&](int s) { return bar + 8u * (10 + s); };
+  auto s_full = [&](int w) { return bar + 8u * (13 + w); };
+  auto p_ready = [&](int w) { return bar + 8u * (15 + w); };
+  const uint32_t o_done = bar + 8u * 17;
+  const uint32_t tmem_slot = bar + 8u * 18;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+  const int n_kv = (p.Lk + 127) / 128;
+  const bool tr_on = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  int tr_n = 0;
+  auto trace = [&](int region, long long tag) {
+    if (tr_on && tr_n < 512) {
+      p.trace[(region * 512 + tr_n) * 2] = tag;
+      p.trace[(region * 512 + tr_n) * 2 + 1] = clock64();
+      ++tr_n;
+    }
+  };
+
+  if (warp == 0 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kF2Stages; ++s) { mbar_init(k_full(s), 1); mbar_init(v_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_empty(s), 1); }
+    for (int w = 0; w < 2; ++w) { mbar_init(s_full(w), 1); mbar_init(p_ready(w), 4); }
+    mbar_init(o_done, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&maps.q); tma_prefetch_desc(&maps.k); tma_prefetch_desc(&maps.v);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(q_full, 2 * kTile);
+      tma_load_3d(&maps.q, q_full, sQ(0), h * 64, q0, b);
+      tma_load_3d(&maps.q, q_full, sQ(1), h * 64, q0 + 128, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j % kF2Stages;
+        const uint32_t ph = ((j / kF2Stages) & 1u) ^ 1u;
+        mbar_wait(k_empty(s), ph);
+        mbar_expect_tx(k_full(s), kTile);
+        tma_load_3d(&maps.k, k_full(s), sK(s), h * 64, j * 128, b);
+        mbar_wait(v_empty(s), ph);
+        mbar_expect_tx(v_full(s), kTile);
+        tma_load_3d(&maps.v, v_full(s), sV(s), h * 64, j * 128, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idescS = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idescO = umma_idesc_bf16(128, 64, 0, 1);          // B = V is MN-major (keys x head_dim rows)
+      const uint64_t qd0 = umma_smem_desc(sQ(0), 16, 1024), qd1 = umma_smem_desc(sQ(1), 16, 1024);
+      const uint64_t kd0 = umma_smem_desc(sK(0), 16, 1024), vd0 = umma_smem_desc(sV(0), 8192, 1024);
+      auto issue_S = [&](int w, int j) {
+        const uint64_t kd = kd0 + 1024u * (j % kF2Stages);
+        const uint64_t qd = w ? qd1 : qd0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tmem + 128u * w, qd + 2u * k, kd + 2u * k, idescS, k > 0);
+        umma_commit(s_full(w));
+      };
+      auto issue_PV = [&](int w, int j) {
+        const uint64_t vd = vd0 + 1024u * (j % kF2Stages);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_f16_ts(tmem + 256u + 64u * w, tmem + 384u + 64u * w + 8u * k, vd + 128u * k, idescO, (j > 0 || k > 0) ? 1u : 0u);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(k_full(0), 0);
+      tc_fence_after();
+      issue_S(0, 0);
+      issue_S(1, 0);
+      umma_commit(k_empty(0));
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % kF2Stages;
+        const uint32_t ph = (j / kF2Stages) & 1u;
+        const bool more = j + 1 < n_kv;
+        const int st1 = (j + 1) % kF2Stages;
+        const uint32_t ph1 = ((j + 1) / kF2Stages) & 1u;
+        mbar_wait(p_ready(0), j & 1);
+        mbar_wait(v_full(st), ph);
+        trace(0, 100 + j);
+        tc_fence_after();
+        issue_PV(0, j);
+        if (more) {
+          mbar_wait(k_full(st1), ph1);
+          tc_fence_after();
+          issue_S(0, j + 1);
+        }
+        mbar_wait(p_ready(1), j & 1);
+        trace(0, 200 + j);
+        tc_fence_after();
+        issue_PV(1, j);
+        umma_commit(v_empty(st));
+        if (more) {
+          issue_S(1, j + 1);
+          umma_commit(k_empty(st1));
+        }
+      }
+      umma_commit(o_done);
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int w = (warp - 4) >> 2;                      // softmax group = query tile
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t tS = tmem + 128u * w, tO = tmem + 256u + 64u * w, tP = tmem + 384u + 64u * w;
+    float m_used = -INFINITY, l = 0.f;
+    // Optional strict alternation of the two groups' exponential phases (token through named barriers 4 / 5, the warpgroup
+    // ping-pong of FlashAttention-3).  Measured on B200 it LOSES here (627 us vs 543 us per encoder layer): one warp per
+    // scheduler cannot overlap its own MUFU issue windows (~14 issue cycles per element), two concurrent warps can; so the
+    // default lets both groups run together and only NS_ATTN_TAKE_TURNS=1 enables the token.
+    const bool take_turns = p.take_turns != 0;
+    if (take_turns && w == 1) named_bar_arrive(4, 256);
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(s_full(w), j & 1);
+      if (take_turns) named_bar_sync(4 + w, 256);
+      if (quarter == 0 && lane == 0) trace(2 + w, 100 + j);
+      tc_fence_after();
+      const int nvalid = min(128, p.Lk - j * 128);
+      const bool full = nvalid == 128;
+      uint32_t v[32];
+      if (j == 0) {                                   // first tile: the row max has to be known before the exponentials
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld32(tS + lane_addr + 32u * c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (full || c * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+        m_used = mx;
+      }
+      // One pass: p = exp2((s - m_used) * log2e) with the max of the PREVIOUS tiles, tracking this tile's max on the side.
+      // Only if some row's max grew by more than 8 (log2 units) the accumulator is rescaled and the pass is redone.
+      float l_tile = 0.f, mx = -INFINITY;
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        const float mb = m_used * kLog2e;
+        l_tile = 0.f;
+        // software pipeline over the four 32-column chunks: the tcgen05.ld of chunk c+1 is in flight while chunk c is
+        // exponentiated, so this warp (the only one of its group on this scheduler) keeps the MUFU pipe fed
+        uint32_t vb[2][32];
+        tmem_ld32(tS + lane_addr, vb[0]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < 3) tmem_ld32(tS + lane_addr + 32u * (c + 1), vb[(c + 1) & 1]);
+          const uint32_t (&vc)[32] = vb[c & 1];
+          uint32_t pk[16];
+          if (full) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float s0 = __uint_as_float(vc[2 * i]), s1 = __uint_as_float(vc[2 * i + 1]);
+              mx = fmaxf(mx, fmaxf(s0, s1));
+              const float p0 = fast_exp2(fmaf(s0, kLog2e, -mb)), p1 = fast_exp2(fmaf(s1, kLog2e, -mb));
+              l_tile += p0 + p1;
+              pk[i] = pack_bf16x2(p0, p1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const bool ok0 = c * 32 + 2 * i < nvalid, ok1 = c * 32 + 2 * i + 1 < nvalid;
+              const float s0 = __uint_as_float(vc[2 * i]), s1 = __uint_as_float(vc[2 * i + 1]);
+              if (ok0) mx = fmaxf(mx, s0);
+              if (ok1) mx = fmaxf(mx, s1);
+              const float p0 = ok0 ? fast_exp2(fmaf(s0, kLog2e, -mb)) : 0.f;
+              const float p1 = ok1 ? fast_exp2(fmaf(s1, kLog2e, -mb)) : 0.f;
+              l_tile += p0 + p1;
+              pk[i] = pack_bf16x2(p0, p1);
+            }
+          }
+          tmem_st16(tP + lane_addr + 16u * c, pk);
+          if (c < 3) tmem_ld_wait();
+        }
+        const bool need = mx > m_used + 5.545177f;     // 8 / log2(e)
+        if (attempt == 1 || !__any_sync(0xffffffffu, need)) break;
+        // s_full(j) was committed behind PV(j-1) of this tile, so the accumulator is quiescent here
+        const float m_new = fmaxf(m_used, mx);
+        const float sc = fast_exp2((m_used - m_new) * kLog2e);
+        tmem_st_wait();
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld32(tO + lane_addr + 32u * c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * sc);
+          tmem_st32(tO + lane_addr + 32u * c, v);
+        }
+        l *= sc;
+        m_used = m_new;
+      }
+      l += l_tile;
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready(w));
+      if (take_turns && (w == 0 || j + 1 < n_kv)) named_bar_arrive(5 - w, 256);
+      if (quarter == 0 && lane == 0) trace(2 + w, 200 + j);
+    }
+    mbar_wait(o_done, 0);
+    tc_fence_after();
+    const int qi = q0 + 128 * w + row;
+    const float inv = 1.0f / l;
+    __nv_bfloat16* orow = p.o + b * p.o_bs + static_cast<long long>(qi) * p.o_rs + h * 64;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tO + lane_addr + 32u * c, v);
+      tmem_ld_wait();
+      if (qi < p.Lq) {
+        uint4* dst = reinterpret_cast<uint4*>(orow + 32 * c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
+          dst[i] = u;
+        }
+      }
+    }
+    if (p.lse && qi < p.Lq) p.lse[(static_cast<long long>(b) * p.H + h) * p.Lq + qi] = m_used + logf(l);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static int head_map(CUtensorMap* m, const void* base, int H, int L, int B, long long bs, long long rs) {
@@ -257,7 +529,23 @@ int attention_fwd_tc(const ns_attn_shape& s, const void* q, const void* k, const
   if ((r = head_map(&maps.q, q, s.H, s.Lq, s.B, s.q_bs, s.q_rs))) return r;
   if ((r = head_map(&maps.k, k, s.H, s.Lk, s.B, s.k_bs, s.k_rs))) return r;
   if ((r = head_map(&maps.v, v, s.H, s.Lk, s.B, s.v_bs, s.v_rs))) return r;
-  AttnFwdProg prog{s.B, s.H, s.Lq, s.Lk, s.o_bs, s.o_rs, reinterpret_cast<__nv_bfloat16*>(o), lse};
+  AttnFwdProg prog{s.B, s.H, s.Lq, s.Lk, s.o_bs, s.o_rs, reinterpret_cast<__nv_bfloat16*>(o), lse, get_attn_trace(),
+                   getenv("NS_ATTN_TAKE_TURNS") != nullptr};
+  // two-query-tile kernel: same speed as the 2-CTAs-per-SM kernel below on B200 (543 us per encoder layer) with half the
+  // K/V traffic; opt-in until it wins
+  static const bool pingpong = getenv("NS_ATTN_PINGPONG") != nullptr;
+  if (s.Lq > 128 && pingpong) {
+    static bool attr2_done = false;
+    if (!attr2_done) {
+      NS_CUDA(cudaFuncSetAttribute(attn_fwd2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kF2Smem));
+      attr2_done = true;
+    }
+    dim3 grid2((s.Lq + 255) / 256, s.H, s.B);
+    attn_fwd2_tc_kernel<<<grid2, kF2Threads, kF2Smem, st>>>(maps, prog);
+    NS_LAUNCH_CHECK();
+    count(C_ATTN_TC);
+    return NS_OK;
+  }
   dim3 grid((s.Lq + 127) / 128, s.H, s.B);
   attn_fwd_tc_kernel<<<grid, kAtThreads, kAtSmem, st>>>(maps, prog);
   NS_LAUNCH_CHECK();
