@@ -291,48 +291,122 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_simt_kernel(const ns_attn_sh
 // positions, causal; utils/load_model.py:512-532).  ONE WARP per (batch, head), lane = query row; K / V (and in the
 // backward Q / dO, P / dS) live in shared memory and are read as broadcasts, so the softmax needs no cross-lane traffic.
 // The general kernels above spend ~30 us (forward) / ~120 us (backward, three launches) on this 32 x 32 problem.
+// shared-memory rows are DH floats (16-byte aligned) and always read as float4 BROADCASTS (every lane the same row), so one
+// LDS.128 feeds four FMAs; each lane's own q / dO row lives in registers.
+template <typename T, int DH>
+__device__ __forceinline__ void tiny_load_tile(float* dst, const T* __restrict__ src, long long rs, int L, int lane) {
+  // 16-byte loads, all issued before the first use (a single warp has nobody to hide a load latency behind)
+  constexpr int EPV = 16 / sizeof(T);              // elements per vector
+  constexpr int VPR = DH / EPV;                    // vectors per row
+  constexpr int NIT = 32 * VPR / 32;
+  uint4 buf[NIT];
+#pragma unroll
+  for (int i = 0; i < NIT; ++i) {
+    const int e = i * 32 + lane, r = e / VPR, c = e % VPR;
+    buf[i] = r < L ? __ldg(reinterpret_cast<const uint4*>(src + static_cast<long long>(r) * rs + c * EPV)) : make_uint4(0, 0, 0, 0);
+  }
+#pragma unroll
+  for (int i = 0; i < NIT; ++i) {
+    const int e = i * 32 + lane, r = e / VPR, c = e % VPR;
+    float* d = dst + r * DH + c * EPV;
+    if constexpr (sizeof(T) == 4) {
+      *reinterpret_cast<uint4*>(d) = buf[i];
+    } else {
+      float2 f;
+      f = unpack_bf16x2(buf[i].x); d[0] = f.x; d[1] = f.y;
+      f = unpack_bf16x2(buf[i].y); d[2] = f.x; d[3] = f.y;
+      f = unpack_bf16x2(buf[i].z); d[4] = f.x; d[5] = f.y;
+      f = unpack_bf16x2(buf[i].w); d[6] = f.x; d[7] = f.y;
+    }
+  }
+}
+template <typename T, int DH>
+__device__ __forceinline__ void tiny_store_row(T* __restrict__ p, const float (&a)[DH], float scale) {   // 16-byte stores
+  if constexpr (sizeof(T) == 4) {
+#pragma unroll
+    for (int d = 0; d < DH; d += 4) *reinterpret_cast<float4*>(p + d) = make_float4(a[d] * scale, a[d + 1] * scale, a[d + 2] * scale, a[d + 3] * scale);
+  } else {
+#pragma unroll
+    for (int d = 0; d < DH; d += 8) {
+      uint4 u;
+      u.x = pack_bf16x2(a[d] * scale, a[d + 1] * scale); u.y = pack_bf16x2(a[d + 2] * scale, a[d + 3] * scale);
+      u.z = pack_bf16x2(a[d + 4] * scale, a[d + 5] * scale); u.w = pack_bf16x2(a[d + 6] * scale, a[d + 7] * scale);
+      *reinterpret_cast<uint4*>(p + d) = u;
+    }
+  }
+}
+template <typename T, int DH>
+__device__ __forceinline__ void tiny_load_row(float (&a)[DH], const T* __restrict__ p) {
+  if constexpr (sizeof(T) == 4) {
+#pragma unroll
+    for (int d = 0; d < DH; d += 4) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(p + d));
+      a[d] = x.x; a[d + 1] = x.y; a[d + 2] = x.z; a[d + 3] = x.w;
+    }
+  } else {
+#pragma unroll
+    for (int d = 0; d < DH; d += 8) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(p + d));
+      float2 f;
+      f = unpack_bf16x2(u.x); a[d] = f.x; a[d + 1] = f.y;
+      f = unpack_bf16x2(u.y); a[d + 2] = f.x; a[d + 3] = f.y;
+      f = unpack_bf16x2(u.z); a[d + 4] = f.x; a[d + 5] = f.y;
+      f = unpack_bf16x2(u.w); a[d + 6] = f.x; a[d + 7] = f.y;
+    }
+  }
+}
+template <int DH>
+__device__ __forceinline__ float tiny_dot(const float (&a)[DH], const float* __restrict__ row) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int d = 0; d < DH; d += 8) {
+    const float4 x = *reinterpret_cast<const float4*>(row + d), y = *reinterpret_cast<const float4*>(row + d + 4);
+    s0 = fmaf(a[d], x.x, s0); s0 = fmaf(a[d + 1], x.y, s0); s0 = fmaf(a[d + 2], x.z, s0); s0 = fmaf(a[d + 3], x.w, s0);
+    s1 = fmaf(a[d + 4], y.x, s1); s1 = fmaf(a[d + 5], y.y, s1); s1 = fmaf(a[d + 6], y.z, s1); s1 = fmaf(a[d + 7], y.w, s1);
+  }
+  return s0 + s1;
+}
+template <int DH>
+__device__ __forceinline__ void tiny_axpy(float (&acc)[DH], float w, const float* __restrict__ row) {
+#pragma unroll
+  for (int d = 0; d < DH; d += 4) {
+    const float4 x = *reinterpret_cast<const float4*>(row + d);
+    acc[d] = fmaf(w, x.x, acc[d]); acc[d + 1] = fmaf(w, x.y, acc[d + 1]); acc[d + 2] = fmaf(w, x.z, acc[d + 2]); acc[d + 3] = fmaf(w, x.w, acc[d + 3]);
+  }
+}
+
 template <typename T, int DH>
 __global__ void __launch_bounds__(32) attn_tiny_fwd_kernel(const ns_attn_shape s, const T* __restrict__ q, const T* __restrict__ k,
                                                            const T* __restrict__ v, T* __restrict__ o, float* __restrict__ lse) {
-  __shared__ float Ks[32][DH + 1];
-  __shared__ float Vs[32][DH + 1];
+  __shared__ __align__(16) float Ks[32 * DH];
+  __shared__ __align__(16) float Vs[32 * DH];
   const int h = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;
   const int L = s.Lq;
-  for (int e = lane; e < 32 * DH; e += 32) {
-    const int r = e / DH, d = e % DH;
-    float kv = 0.f, vv = 0.f;
-    if (r < L) {
-      kv = to_f<T>(k[b * s.k_bs + static_cast<long long>(r) * s.k_rs + h * DH + d]);
-      vv = to_f<T>(v[b * s.v_bs + static_cast<long long>(r) * s.v_rs + h * DH + d]);
-    }
-    Ks[r][d] = kv; Vs[r][d] = vv;
-  }
+  tiny_load_tile<T, DH>(Ks, k + b * s.k_bs + h * DH, s.k_rs, L, lane);
+  tiny_load_tile<T, DH>(Vs, v + b * s.v_bs + h * DH, s.v_rs, L, lane);
   float qr[DH], acc[DH];
   const bool act = lane < L;
   const T* qp = q + b * s.q_bs + static_cast<long long>(act ? lane : 0) * s.q_rs + h * DH;
+  tiny_load_row<T, DH>(qr, qp);
 #pragma unroll
-  for (int d = 0; d < DH; ++d) { qr[d] = act ? to_f<T>(qp[d]) : 0.f; acc[d] = 0.f; }
+  for (int d = 0; d < DH; ++d) acc[d] = 0.f;
   __syncwarp();
   float m = -INFINITY, l = 0.f;
   const int jend = s.causal ? lane + 1 : L;       // Lq == Lk: query i sees keys j <= i
   for (int j = 0; j < L; ++j) {
-    float sc = 0.f;
+    const float sc = tiny_dot<DH>(qr, Ks + j * DH);
+    const bool on = j < jend && act;
+    const float mn = on ? fmaxf(m, sc) : m;
+    const float corr = on ? __expf(m - mn) : 1.f, pj = on ? __expf(sc - mn) : 0.f;
+    l = l * corr + pj;
+    m = mn;
 #pragma unroll
-    for (int d = 0; d < DH; ++d) sc = fmaf(qr[d], Ks[j][d], sc);
-    if (j < jend && act) {
-      const float mn = fmaxf(m, sc);
-      const float corr = __expf(m - mn), pj = __expf(sc - mn);
-      l = l * corr + pj;
-      m = mn;
-#pragma unroll
-      for (int d = 0; d < DH; ++d) acc[d] = fmaf(pj, Vs[j][d], acc[d] * corr);
-    }
+    for (int d = 0; d < DH; ++d) acc[d] *= corr;
+    tiny_axpy<DH>(acc, pj, Vs + j * DH);
   }
   if (act) {
     const float inv = 1.0f / l;
-    T* op = o + b * s.o_bs + static_cast<long long>(lane) * s.o_rs + h * DH;
-#pragma unroll
-    for (int d = 0; d < DH; ++d) op[d] = from_f<T>(acc[d] * inv);
+    tiny_store_row<T, DH>(o + b * s.o_bs + static_cast<long long>(lane) * s.o_rs + h * DH, acc, inv);
     if (lse) lse[(static_cast<long long>(b) * s.H + h) * L + lane] = m + logf(l);
   }
 }
@@ -342,86 +416,80 @@ __global__ void __launch_bounds__(32) attn_tiny_bwd_kernel(const ns_attn_shape s
                                                            const T* __restrict__ v, const T* __restrict__ d_o, const float* __restrict__ lse,
                                                            float* __restrict__ delta_out, T* __restrict__ dq, T* __restrict__ dk,
                                                            T* __restrict__ dv) {
-  extern __shared__ float sm[];
-  float (*Ks)[DH + 1] = reinterpret_cast<float (*)[DH + 1]>(sm);
-  float (*Vs)[DH + 1] = Ks + 32;
-  float (*Qs)[DH + 1] = Vs + 32;
-  float (*Os)[DH + 1] = Qs + 32;                  // dO
-  float (*Ps)[33] = reinterpret_cast<float (*)[33]>(sm + 4 * 32 * (DH + 1));
-  float (*Ss)[33] = Ps + 32;                      // dS
+  extern __shared__ __align__(16) float sm[];
+  float* Ks = sm;
+  float* Vs = Ks + 32 * DH;
+  float* Qs = Vs + 32 * DH;
+  float* Os = Qs + 32 * DH;                       // dO
+  float (*Ps)[33] = reinterpret_cast<float (*)[33]>(Os + 32 * DH);
+  float (*Ss)[33] = Ps + 32;                      // dP, then dS
   const int h = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;
   const int L = s.Lq;
-  for (int e = lane; e < 32 * DH; e += 32) {
-    const int r = e / DH, d = e % DH;
-    float kv = 0.f, vv = 0.f, qv = 0.f, ov = 0.f;
-    if (r < L) {
-      kv = to_f<T>(k[b * s.k_bs + static_cast<long long>(r) * s.k_rs + h * DH + d]);
-      vv = to_f<T>(v[b * s.v_bs + static_cast<long long>(r) * s.v_rs + h * DH + d]);
-      qv = to_f<T>(q[b * s.q_bs + static_cast<long long>(r) * s.q_rs + h * DH + d]);
-      ov = to_f<T>(d_o[b * s.o_bs + static_cast<long long>(r) * s.o_rs + h * DH + d]);
-    }
-    Ks[r][d] = kv; Vs[r][d] = vv; Qs[r][d] = qv; Os[r][d] = ov;
-  }
+  tiny_load_tile<T, DH>(Ks, k + b * s.k_bs + h * DH, s.k_rs, L, lane);
+  tiny_load_tile<T, DH>(Vs, v + b * s.v_bs + h * DH, s.v_rs, L, lane);
+  tiny_load_tile<T, DH>(Qs, q + b * s.q_bs + h * DH, s.q_rs, L, lane);
+  tiny_load_tile<T, DH>(Os, d_o + b * s.o_bs + h * DH, s.o_rs, L, lane);
   __syncwarp();
   const bool act = lane < L;
   const int jend = s.causal ? lane + 1 : L;
   const float my_lse = act ? lse[(static_cast<long long>(b) * s.H + h) * L + lane] : 0.f;
-  // ---- phase A (lane = query i): P, dP rows; delta_i = sum_j p_ij dp_ij (= dO_i . O_i); dS; dq_i
   float dlt = 0.f;
-  for (int j = 0; j < L; ++j) {
-    float sc = 0.f, dp = 0.f;
+  {
+    // ---- phase A1 (lane = query i): P and dP rows, delta_i = sum_j p_ij dp_ij (= dO_i . O_i)
+    float qr[DH], orow[DH];
 #pragma unroll
-    for (int d = 0; d < DH; ++d) {
-      sc = fmaf(Qs[lane][d], Ks[j][d], sc);
-      dp = fmaf(Os[lane][d], Vs[j][d], dp);
+    for (int d = 0; d < DH; d += 4) {
+      const float4 a = *reinterpret_cast<const float4*>(Qs + lane * DH + d), c = *reinterpret_cast<const float4*>(Os + lane * DH + d);
+      qr[d] = a.x; qr[d + 1] = a.y; qr[d + 2] = a.z; qr[d + 3] = a.w;
+      orow[d] = c.x; orow[d + 1] = c.y; orow[d + 2] = c.z; orow[d + 3] = c.w;
     }
-    const float pj = (act && j < jend) ? __expf(sc - my_lse) : 0.f;
-    Ps[lane][j] = pj;
-    Ss[lane][j] = dp;
-    dlt = fmaf(pj, dp, dlt);
+    for (int j = 0; j < L; ++j) {
+      const float sc = tiny_dot<DH>(qr, Ks + j * DH);
+      const float dp = tiny_dot<DH>(orow, Vs + j * DH);
+      const float pj = (act && j < jend) ? __expf(sc - my_lse) : 0.f;
+      Ps[lane][j] = pj;
+      Ss[lane][j] = dp;
+      dlt = fmaf(pj, dp, dlt);
+    }
   }
   if (act && delta_out) delta_out[(static_cast<long long>(b) * s.H + h) * L + lane] = dlt;
   float acc[DH];
 #pragma unroll
   for (int d = 0; d < DH; ++d) acc[d] = 0.f;
+  // ---- phase A2: dS row, dq_i = sum_j ds_ij k_j
   for (int j = 0; j < L; ++j) {
     const float ds = Ps[lane][j] * (Ss[lane][j] - dlt);
     Ss[lane][j] = ds;
-#pragma unroll
-    for (int d = 0; d < DH; ++d) acc[d] = fmaf(ds, Ks[j][d], acc[d]);
+    tiny_axpy<DH>(acc, ds, Ks + j * DH);
   }
-  if (act) {
-    T* p = dq + b * s.q_bs + static_cast<long long>(lane) * s.q_rs + h * DH;
-#pragma unroll
-    for (int d = 0; d < DH; ++d) p[d] = from_f<T>(acc[d]);
-  }
+  if (act) tiny_store_row<T, DH>(dq + b * s.q_bs + static_cast<long long>(lane) * s.q_rs + h * DH, acc, 1.0f);
   __syncwarp();
   // ---- phase B (lane = key j): dv_j = sum_i p_ij dO_i ; dk_j = sum_i ds_ij q_i
   float av[DH];
 #pragma unroll
   for (int d = 0; d < DH; ++d) { acc[d] = 0.f; av[d] = 0.f; }
   for (int i = 0; i < L; ++i) {
-    const float pij = Ps[i][lane], dsij = Ss[i][lane];
-#pragma unroll
-    for (int d = 0; d < DH; ++d) {
-      av[d] = fmaf(pij, Os[i][d], av[d]);
-      acc[d] = fmaf(dsij, Qs[i][d], acc[d]);
-    }
+    tiny_axpy<DH>(av, Ps[i][lane], Os + i * DH);
+    tiny_axpy<DH>(acc, Ss[i][lane], Qs + i * DH);
   }
   if (act) {
-    T* pk = dk + b * s.k_bs + static_cast<long long>(lane) * s.k_rs + h * DH;
-    T* pv = dv + b * s.v_bs + static_cast<long long>(lane) * s.v_rs + h * DH;
-#pragma unroll
-    for (int d = 0; d < DH; ++d) { pk[d] = from_f<T>(acc[d]); pv[d] = from_f<T>(av[d]); }
+    tiny_store_row<T, DH>(dk + b * s.k_bs + static_cast<long long>(lane) * s.k_rs + h * DH, acc, 1.0f);
+    tiny_store_row<T, DH>(dv + b * s.v_bs + static_cast<long long>(lane) * s.v_rs + h * DH, av, 1.0f);
   }
 }
 
 template <typename T, int DH>
-static bool tiny_eligible(const ns_attn_shape& s) { return s.Lq == s.Lk && s.Lq <= 32 && s.H <= 65535 && s.B <= 65535; }
+static bool tiny_eligible(const ns_attn_shape& s, const void* q, const void* k, const void* v, const void* o) {
+  constexpr long long epv = 16 / sizeof(T);
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return s.Lq == s.Lk && s.Lq <= 32 && s.H <= 65535 && s.B <= 65535 && al(q) && al(k) && al(v) && al(o) && s.q_rs % epv == 0 &&
+         s.k_rs % epv == 0 && s.v_rs % epv == 0 && s.o_rs % epv == 0 && s.q_bs % epv == 0 && s.k_bs % epv == 0 && s.v_bs % epv == 0 &&
+         s.o_bs % epv == 0;
+}
 
 template <typename T, int DH>
 static int attn_fwd_simt_t(const ns_attn_shape& s, const void* q, const void* k, const void* v, void* o, float* lse, cudaStream_t st) {
-  if (tiny_eligible<T, DH>(s)) {
+  if (tiny_eligible<T, DH>(s, q, k, v, o)) {
     attn_tiny_fwd_kernel<T, DH><<<dim3(s.H, s.B), 32, 0, st>>>(s, reinterpret_cast<const T*>(q), reinterpret_cast<const T*>(k),
                                                              reinterpret_cast<const T*>(v), reinterpret_cast<T*>(o), lse);
     NS_LAUNCH_CHECK();
@@ -439,8 +507,8 @@ static int attn_fwd_simt_t(const ns_attn_shape& s, const void* q, const void* k,
 template <typename T, int DH>
 static int attn_bwd_simt_t(const ns_attn_shape& s, const void* q, const void* k, const void* v, const void* o, const void* d_o,
                            const float* lse, float* delta, void* dq, void* dk, void* dv, cudaStream_t st) {
-  if (tiny_eligible<T, DH>(s)) {
-    constexpr int smem = (4 * 32 * (DH + 1) + 2 * 32 * 33) * 4;
+  if (tiny_eligible<T, DH>(s, q, k, v, d_o) && (reinterpret_cast<uintptr_t>(dq) & 15) == 0) {
+    constexpr int smem = (4 * 32 * DH + 2 * 32 * 33) * 4;
     static bool attr_done = false;
     if (!attr_done) {
       NS_CUDA(cudaFuncSetAttribute(attn_tiny_bwd_kernel<T, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
