@@ -56,7 +56,7 @@ class ClockSampler:
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -265,15 +265,22 @@ def run_ours(args):
             f["ms"] += r["ms"]; f["flops"] += r["flops"]; f["bytes"] += r["bytes"]; f["n"] += 1
         tot = sum(f["ms"] for f in fam.values())
         top_name, top = max(fam.items(), key=lambda kv: kv[1]["ms"])
+        # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/), null when not captured
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01b_traffic.json")))
+            traffic = tj.get(top_name, {}).get("dram_bytes_per_launch_avg")
+        except Exception:
+            traffic = None
         if top["flops"] > 0:
             ach = top["flops"] / (top["ms"] * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": top_name, "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["tf_sustained"], "traffic": None, "launches": top["n"], "share_of_step": top["ms"] / tot,
+                    "frac": ach / peaks["tf_sustained"], "traffic": traffic, "launches": top["n"], "share_of_step": top["ms"] / tot,
                     "peak_source": peaks["src"] + " (sustained bf16: kernel timed inside a long step)"}
         else:
             ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": top_name, "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
-                    "traffic": None, "launches": top["n"], "share_of_step": top["ms"] / tot, "peak_source": peaks["src"]}
+                    "traffic": traffic, "launches": top["n"], "share_of_step": top["ms"] / tot, "peak_source": peaks["src"]}
         step_tf = value / world * FLOP_PER_SAMPLE.get(args.eeg_ch, 267.92e9) / 1e12
         shares = {k: round(v["ms"] / tot, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])[:8]}
         cpu = None
