@@ -232,7 +232,7 @@ int ns_attention_fwd(int dtype, const ns_attn_shape* s, const void* q, const voi
   NS_CHECK_ARG(valid_dtype(dtype) && q && k && v && o, "ns_attention_fwd: bad arguments");
   if (int r = check_attn(s)) return r;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (want_fast(dtype)) {
+  if (want_fast(dtype) && s->Lq > 1) {       // single-query (decode) attention is a streaming kernel on the SIMT side
     const int r = attention_fwd_tc(*s, q, k, v, o, lse, st);
     if (r != NS_ERR_UNSUPPORTED) return r;
     if (g_path == NS_PATH_FAST) return fast_required_failed("ns_attention_fwd");

@@ -487,8 +487,125 @@ static bool tiny_eligible(const ns_attn_shape& s, const void* q, const void* k, 
          s.o_bs % epv == 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Single-query attention (Lq == 1): the per-token decoder step of greedy generation against the self-attention cache
+// (Lk = t <= 448) and the cross-attention cache (Lk = 1500) -- utils/load_model.py:1332-1351, HF modeling_whisper.py:314-336.
+// Pure streaming: every K and V row is read once with 16-byte loads (8 lanes per 128-byte bf16 row, 4 keys per warp
+// instruction), scores / weights stay in registers, one online-softmax state per warp, partial results of the 8 warps are
+// merged in shared memory.  HBM-bound by construction: B*H*Lk*Dh*2 elements per call.
+template <typename T, int DH>
+__global__ void __launch_bounds__(256) attn_decode_kernel(const ns_attn_shape s, const T* __restrict__ q, const T* __restrict__ k,
+                                                          const T* __restrict__ v, T* __restrict__ o, float* __restrict__ lse) {
+  constexpr int EPV = 16 / sizeof(T);              // elements per 16-byte vector
+  constexpr int CPR = DH / EPV;                    // vectors (lanes) per row
+  constexpr int KPW = 32 / CPR;                    // keys per warp instruction
+  __shared__ float sm_m[8], sm_l[8];
+  __shared__ __align__(16) float sm_o[8][DH];
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = lane % CPR, kk = lane / CPR;
+  float qv[EPV];
+  {
+    const T* qp = q + b * s.q_bs + h * DH + c * EPV;       // Lq == 1: row 0
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) qv[e] = to_f<T>(qp[e]);
+  }
+  float m = -INFINITY, l = 0.f, acc[EPV];
+#pragma unroll
+  for (int e = 0; e < EPV; ++e) acc[e] = 0.f;
+  const T* kb = k + b * s.k_bs + h * DH + c * EPV;
+  const T* vb = v + b * s.v_bs + h * DH + c * EPV;
+  // UNR key groups per loop trip, all their 16-byte loads issued before the first use (memory-level parallelism is the whole
+  // game here: ~64 KB must be in flight per SM to cover the HBM latency)
+  constexpr int UNR = 4;
+  for (int j0 = warp * KPW; j0 < s.Lk; j0 += 8 * KPW * UNR) {
+    uint4 ku[UNR], vu[UNR];
+    bool ok[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int j = j0 + u * 8 * KPW + kk;
+      ok[u] = j < s.Lk;
+      ku[u] = ok[u] ? __ldg(reinterpret_cast<const uint4*>(kb + static_cast<long long>(j) * s.k_rs)) : make_uint4(0, 0, 0, 0);
+      vu[u] = ok[u] ? __ldg(reinterpret_cast<const uint4*>(vb + static_cast<long long>(j) * s.v_rs)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (j0 + u * 8 * KPW >= s.Lk) break;           // warp-uniform: this group has no valid key
+      float kx[EPV], vx[EPV];
+      if constexpr (sizeof(T) == 4) {
+        kx[0] = __uint_as_float(ku[u].x); kx[1] = __uint_as_float(ku[u].y); kx[2] = __uint_as_float(ku[u].z); kx[3] = __uint_as_float(ku[u].w);
+        vx[0] = __uint_as_float(vu[u].x); vx[1] = __uint_as_float(vu[u].y); vx[2] = __uint_as_float(vu[u].z); vx[3] = __uint_as_float(vu[u].w);
+      } else {
+        float2 f;
+        f = unpack_bf16x2(ku[u].x); kx[0] = f.x; kx[1] = f.y; f = unpack_bf16x2(ku[u].y); kx[2] = f.x; kx[3] = f.y;
+        f = unpack_bf16x2(ku[u].z); kx[4] = f.x; kx[5] = f.y; f = unpack_bf16x2(ku[u].w); kx[6] = f.x; kx[7] = f.y;
+        f = unpack_bf16x2(vu[u].x); vx[0] = f.x; vx[1] = f.y; f = unpack_bf16x2(vu[u].y); vx[2] = f.x; vx[3] = f.y;
+        f = unpack_bf16x2(vu[u].z); vx[4] = f.x; vx[5] = f.y; f = unpack_bf16x2(vu[u].w); vx[6] = f.x; vx[7] = f.y;
+      }
+      float sc = 0.f;
+#pragma unroll
+      for (int e = 0; e < EPV; ++e) sc = fmaf(qv[e], kx[e], sc);
+#pragma unroll
+      for (int off = CPR / 2; off > 0; off >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, off);   // over the lanes of one row
+      if (!ok[u]) sc = -INFINITY;
+      float mt = sc;                                                                             // max over the KPW keys
+#pragma unroll
+      for (int off = CPR; off < 32; off <<= 1) mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, off));
+      const float mn = fmaxf(m, mt);               // finite: the first key of this group is valid
+      const float corr = __expf(m - mn), pj = __expf(sc - mn);
+      m = mn;
+      l = l * corr + pj;                           // per key group; groups are summed at the end
+#pragma unroll
+      for (int e = 0; e < EPV; ++e) acc[e] = fmaf(pj, vx[e], acc[e] * corr);
+    }
+  }
+  // merge the KPW key groups of this warp (they share m), then the 8 warps
+#pragma unroll
+  for (int off = CPR; off < 32; off <<= 1) {
+    l += __shfl_xor_sync(0xffffffffu, l, off);
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], off);
+  }
+  if (kk == 0) {
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) sm_o[warp][c * EPV + e] = acc[e];
+    if (c == 0) { sm_m[warp] = m; sm_l[warp] = l; }
+  }
+  __syncthreads();
+  if (threadIdx.x < DH) {
+    float mg = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) mg = fmaxf(mg, sm_m[w]);
+    float lg = 0.f, og = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float sc = sm_m[w] == -INFINITY ? 0.f : __expf(sm_m[w] - mg);
+      lg = fmaf(sm_l[w], sc, lg);
+      og = fmaf(sm_o[w][threadIdx.x], sc, og);
+    }
+    o[b * s.o_bs + h * DH + threadIdx.x] = from_f<T>(og / lg);
+    if (lse && threadIdx.x == 0) lse[static_cast<long long>(b) * s.H + h] = mg + logf(lg);
+  }
+}
+
+template <typename T, int DH>
+static bool decode_eligible(const ns_attn_shape& s, const void* q, const void* k, const void* v) {
+  constexpr long long epv = 16 / sizeof(T);
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  // Lq == 1: with or without the causal flag the query sees every key (j <= 0 + Lk - 1)
+  return s.Lq == 1 && s.Lk >= 1 && s.H <= 65535 && s.B <= 65535 && al(k) && al(v) && s.k_rs % epv == 0 && s.v_rs % epv == 0 &&
+         s.k_bs % epv == 0 && s.v_bs % epv == 0 && q != nullptr;
+}
+
 template <typename T, int DH>
 static int attn_fwd_simt_t(const ns_attn_shape& s, const void* q, const void* k, const void* v, void* o, float* lse, cudaStream_t st) {
+  if (decode_eligible<T, DH>(s, q, k, v)) {
+    attn_decode_kernel<T, DH><<<dim3(s.H, s.B), 256, 0, st>>>(s, reinterpret_cast<const T*>(q), reinterpret_cast<const T*>(k),
+                                                            reinterpret_cast<const T*>(v), reinterpret_cast<T*>(o), lse);
+    NS_LAUNCH_CHECK();
+    count(C_ATTN_SIMT);
+    return NS_OK;
+  }
   if (tiny_eligible<T, DH>(s, q, k, v, o)) {
     attn_tiny_fwd_kernel<T, DH><<<dim3(s.H, s.B), 32, 0, st>>>(s, reinterpret_cast<const T*>(q), reinterpret_cast<const T*>(k),
                                                              reinterpret_cast<const T*>(v), reinterpret_cast<T*>(o), lse);

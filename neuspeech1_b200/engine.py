@@ -122,6 +122,7 @@ class Workspace:
     def __init__(self, device):
         self.device = device
         self.bufs: Dict[str, torch.Tensor] = {}
+        self.gen = 0          # bumped on every (re)allocation: captured CUDA graphs are only replayed while it stands still
 
     def get(self, name: str, shape, dtype, zero: bool = False) -> torch.Tensor:
         shape = tuple(int(s) for s in shape)
@@ -129,6 +130,7 @@ class Workspace:
         if t is None or t.shape != shape or t.dtype != dtype:
             t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
             self.bufs[name] = t
+            self.gen += 1
         return t
 
     def bytes(self) -> int:
@@ -241,6 +243,8 @@ class WhisperEEGEngine:
         wkv = torch.cat(kv_w, dim=0)                                     # (Nd*2d, d): [k0; v0; k1; v1; ...]
         W["dec.wkv"] = self._c(wkv); W["dec.wkv_t"] = self._ct(wkv); W["dec.bkv"] = torch.cat(kv_b)
         self.P = W
+        self._decode_graphs = {}
+        self._weights_version = getattr(self, "_weights_version", 0) + 1
         self._lora_tb = None             # LoRA operand views / transpose job table are rebuilt by pack_trainable
         self.suppress = torch.tensor(list(dm.begin_suppress_tokens), dtype=torch.int32, device=dev)
         self._packed = False
@@ -675,7 +679,8 @@ class WhisperEEGEngine:
 
     # ------------------------------------------------------------------ greedy decode with KV cache
     @torch.no_grad()
-    def greedy(self, x: torch.Tensor, max_length: int, prompt: Optional[torch.Tensor] = None, aug: Optional[dict] = None) -> torch.Tensor:
+    def greedy(self, x: torch.Tensor, max_length: int, prompt: Optional[torch.Tensor] = None, aug: Optional[dict] = None,
+               use_graphs: bool = False) -> torch.Tensor:
         """Batched greedy generate (utils/load_model.py:1072-1351 -> GenerationMixin greedy): encoder once, cross-K/V once,
         then one-token decoder steps against the self-attention cache.  Returns the generated suffix (B, n_new) int64;
         rows that hit EOS emit pad afterwards; begin_suppress_tokens are masked at the first generated position."""
@@ -695,16 +700,18 @@ class WhisperEEGEngine:
         if Tmax > dm.max_target_positions:
             raise ValueError(f"max_length {Tmax} exceeds max_target_positions {dm.max_target_positions}")
         n_new = Tmax - L0
-        out = torch.empty((B, max(n_new, 0)), dtype=torch.long, device=self.device)
         if n_new <= 0:
-            return out
+            return torch.empty((B, 0), dtype=torch.long, device=self.device)
         cache = [ws.get(f"g_qkv.{i}", (B, Tmax, 3 * d), dt) for i in range(dm.dec_layers)]
         finished = ws.get("g_fin", (B,), torch.uint8); finished.zero_()
         nxt = ws.get("g_next", (B,), torch.long)
         logits = ws.get("g_logits", (B, dm.Vp), torch.float32 if dt == torch.float32 else dt)
-        ids = prompt
-        pos = 0
-        for step in range(n_new):
+        out = ws.get(f"g_out.{n_new}", (B, n_new), torch.long)
+        ids0 = ws.get(f"g_ids0.{L0}", (B, L0), torch.long)
+        ids0.copy_(prompt)
+
+        def decode_step(step: int, ids: torch.Tensor, pos: int):
+            """One decoder pass over `ids` (B, Lq) at cache position `pos` -> next token in `nxt`, appended to out[:, step]."""
             Lq = ids.shape[1]
             MLq = B * Lq
             hd = ws.get(f"g_h0.{Lq}", (MLq, d), dt)
@@ -747,6 +754,26 @@ class WhisperEEGEngine:
             ops.gemm_nt(y_last, W["dec.E"], logits, self._ep(out_dtype=ops.ns_dtype(logits)), N=dm.vocab, M=B, K=d)
             ops.greedy_pick(logits, dm.vocab, self.suppress if step == 0 else None, dm.eos_token_id, dm.pad_token_id, finished, nxt)
             out[:, step].copy_(nxt)
-            pos += Lq
-            ids = nxt.view(B, 1)
-        return out
+
+        # The ~150 launches of a decode step are latency-bound at M = B: each step is captured once into a CUDA graph (keyed by
+        # batch / prompt length / position, all buffers live in the persistent workspace) and replayed afterwards.
+        graphs = self._decode_graphs if use_graphs else None
+        pos = 0
+        for step in range(n_new):
+            ids = ids0 if step == 0 else nxt.view(B, 1)
+            key = (B, Tmax, L0, step, self._weights_version)
+            if graphs is None:
+                decode_step(step, ids, pos)
+            else:
+                ent = graphs.get(key)
+                if ent is None or ent[1] != ws.gen:
+                    decode_step(step, ids, pos)                       # eager once: allocates this step's workspace buffers
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):                         # capture only records; state stays as after the eager run
+                        decode_step(step, ids, pos)
+                    graphs[key] = (g, ws.gen)
+                else:
+                    ent[0].replay()
+            pos += ids.shape[1]
+        return out.clone()

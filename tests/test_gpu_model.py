@@ -135,3 +135,29 @@ def test_whisper_base_fp32_greedy_identical(golden_dir):
     assert abs(float(loss) - float(g["loss"])) < 1e-3 * float(g["loss"])
     ids = eng.greedy(x.to(DEV), max_length=13)
     assert torch.equal(ids.cpu(), torch.from_numpy(g["greedy"]))
+
+
+def test_greedy_cuda_graph_replay_matches_eager():
+    """The per-position CUDA graphs of the decode loop (engine.greedy(use_graphs=True)) reproduce the eager launches token for
+    token: first call captures, second call re-captures the early steps once (their workspace allocations bump the
+    generation), third call is pure replay; a different batch in between must not leave stale graphs behind."""
+    dims = O.Dims(d_model=256, enc_layers=2, dec_layers=2, enc_heads=4, dec_heads=4, enc_ffn=512, dec_ffn=512, vocab=2000,
+                  max_source_positions=160, max_target_positions=32, eeg_ch=24, pad_token_id=1997, eos_token_id=1997,
+                  decoder_start_token_id=1998, begin_suppress_tokens=(220, 1996), lora_r=32, lora_alpha=64)
+    P = O.init_params(dims, seed=0)
+    x, _ = O.synthetic_batch(dims, B=3, L=8, seed=1)
+    x2, _ = O.synthetic_batch(dims, B=3, L=8, seed=2)
+    eng = WhisperEEGEngine(ModelDims.from_any(dims), P, None, dtype=torch.float32, device=DEV)
+    ref = eng.greedy(x.to(DEV), max_length=14)
+    ref2 = eng.greedy(x2.to(DEV), max_length=14)
+    for _ in range(3):
+        assert torch.equal(eng.greedy(x.to(DEV), max_length=14, use_graphs=True), ref)
+    assert torch.equal(eng.greedy(x2.to(DEV), max_length=14, use_graphs=True), ref2)
+    xb, _ = O.synthetic_batch(dims, B=5, L=8, seed=3)                       # another batch size reallocates the workspace
+    refb = eng.greedy(xb.to(DEV), max_length=14)
+    assert torch.equal(eng.greedy(xb.to(DEV), max_length=14, use_graphs=True), refb)
+    assert torch.equal(eng.greedy(x.to(DEV), max_length=14, use_graphs=True), ref)
+    prompt = torch.tensor([[1998, 5, 7, 9]] * 3)
+    refp = eng.greedy(x.to(DEV), max_length=14, prompt=prompt)
+    for _ in range(2):
+        assert torch.equal(eng.greedy(x.to(DEV), max_length=14, prompt=prompt, use_graphs=True), refp)
