@@ -161,3 +161,34 @@ def test_greedy_cuda_graph_replay_matches_eager():
     refp = eng.greedy(x.to(DEV), max_length=14, prompt=prompt)
     for _ in range(2):
         assert torch.equal(eng.greedy(x.to(DEV), max_length=14, prompt=prompt, use_graphs=True), refp)
+
+
+# BASELINE.json configs[2] / configs[4] shapes at reduced depth / sequence: the Schoffelen channel count (273 -> padded to 288
+# channels-last, K = 3*288 for stem conv A) and the large-v3 widths (d = 1280 = 5 x 256 column tiles, 20 heads of 64, F = 5120).
+WIDE = O.Dims(d_model=1280, enc_layers=1, dec_layers=1, enc_heads=20, dec_heads=20, enc_ffn=5120, dec_ffn=5120, vocab=3000,
+              max_source_positions=192, max_target_positions=32, eeg_ch=273, pad_token_id=2997, eos_token_id=2997,
+              decoder_start_token_id=2998, begin_suppress_tokens=(220, 2996), lora_r=32, lora_alpha=64)
+SCHOF = O.Dims(d_model=256, enc_layers=2, dec_layers=2, enc_heads=4, dec_heads=4, enc_ffn=512, dec_ffn=512, vocab=2000,
+               max_source_positions=160, max_target_positions=48, eeg_ch=273, pad_token_id=1997, eos_token_id=1997,
+               decoder_start_token_id=1998, begin_suppress_tokens=(220, 1996), lora_r=32, lora_alpha=64)
+
+
+@pytest.mark.parametrize("dims_name,dtype", [("SCHOF", torch.float32), ("SCHOF", torch.bfloat16), ("WIDE", torch.bfloat16)])
+def test_schoffelen_channels_and_large_v3_widths(dims_name, dtype):
+    dims = {"SCHOF": SCHOF, "WIDE": WIDE}[dims_name]
+    P, lora, eng = build(dims, dtype)
+    B = 2 if dims_name == "WIDE" else 3
+    x, labels = O.synthetic_batch(dims, B=B, L=8, seed=5)
+    loss_ref, grads_ref, enc_ref = O.grads(x, labels, P, dims, lora)
+    _abi.reset_counters()
+    loss, logits, enc = eng.forward_loss(x.to(DEV), labels.to(DEV))
+    eng.backward()
+    torch.cuda.synchronize()
+    tol_e, tol_g = (1e-3, 2e-3) if dtype == torch.float32 else (2e-2, 6e-2)
+    assert rel(enc, enc_ref) < tol_e, rel(enc, enc_ref)
+    assert abs(float(loss) - float(loss_ref)) < tol_e * float(loss_ref)
+    worst = max(rel(eng.trainable_grad(n), g) for n, g in grads_ref.items())
+    assert worst < tol_g, worst
+    if dtype == torch.bfloat16:
+        c = _abi.counters()
+        assert c["gemm_tcgen05"] > 0 and c["attn_tc"] > 0, c
