@@ -213,7 +213,7 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
   auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
-  auto in_full = [&](int h) { return bar_base + 8u * (2 * S + 5 + h); };
+  auto in_full = [&](int w) { return bar_base + 8u * (2 * S + 5 + w); };    // one per epilogue warp (8)
   const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -263,8 +263,8 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 8 * CG);   // one arrive per epilogue warp (of both CTAs)
-      mbar_init(in_full(a), 1);
     }
+    for (int w = 0; w < 8; ++w) mbar_init(in_full(w), 1);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -280,7 +280,7 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
   // each role branch so that ptxas allocates every role under its own limit
   if (warp == 0) {
     // ================================================================ TMA producer
-    setmaxnreg_dec<56>();
+    setmaxnreg_dec<40>();
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
@@ -318,7 +318,7 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
-    setmaxnreg_dec<56>();
+    setmaxnreg_dec<40>();
     constexpr uint32_t idesc = umma_idesc_bf16(kBM * CG, BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
@@ -361,28 +361,32 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
       __syncwarp();
     }
   } else if (warp < 4) {
-    setmaxnreg_dec<56>();
+    setmaxnreg_dec<40>();
   } else {
     // ================================================================ epilogue
-    setmaxnreg_inc<216>();
+    setmaxnreg_inc<232>();
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;  // which half of the tile's columns
     constexpr int kHalfCols = (BN >= 64) ? BN / 2 : BN;
     const EpiDev& e = p.epi;
     const bool use_tma = BN >= 128 && p.tma_out;
-    const bool issuer = (q == 0);                                             // first warp of this column half
+    // Every epilogue warp moves its OWN 32-row slice of the staging tiles (TMA boxes of 64 columns x 32 rows, a per-warp
+    // input barrier, per-lane bulk groups): no named barrier anywhere in the epilogue.  With one issuer per column half the
+    // four warps met at 4 barriers per 64-column chunk and ncu showed 2 barrier-stall cycles per issued instruction.
+    const int ew = warp - 4;
+    const uint32_t slice_off = static_cast<uint32_t>(q) * 32u * 128u;
     const uint32_t out_stage = staging_base + static_cast<uint32_t>(half) * (kBM * 128);
     const uint32_t in_stage = staging_base + static_cast<uint32_t>(2 + half) * (kBM * 128);   // input tile, or the aux output tile
     uint32_t in_phase = 0;
-    // epilogue input tile (aux_in / residual) of (tile, column chunk c) -> shared memory, by the elected issuer lane
+    // this warp's slice of the epilogue input tile (aux_in / residual) of (tile, column chunk c) -> shared memory
     auto issue_in = [&](int tile_, int c_) {
       int m_tile_, n_tile_;
       decode(tile_, m_tile_, n_tile_);
-      mbar_expect_tx(in_full(half), kBM * 128);
-      tma_load_3d(&maps.in, in_full(half), in_stage, n_tile_ * BN + half * kHalfCols + c_, (m_tile_ % p.tiles_per_batch) * kBM,
-                  p.in_batched ? m_tile_ / p.tiles_per_batch : 0);
+      mbar_expect_tx(in_full(ew), 32 * 128);
+      tma_load_3d(&maps.in, in_full(ew), in_stage + slice_off, n_tile_ * BN + half * kHalfCols + c_,
+                  (m_tile_ % p.tiles_per_batch) * kBM + q * 32, p.in_batched ? m_tile_ / p.tiles_per_batch : 0);
     };
-    if (use_tma && p.tma_in && issuer && tile_first < total_tiles) {
+    if (use_tma && p.tma_in && tile_first < total_tiles) {
       if (elect_one()) issue_in(tile_first, 0);
     }
     const uint32_t lead_tempty0 = (CG == 2) ? mapa_cluster(tempty_bar(0), 0) : 0u;   // the leader's accumulator-free barriers
@@ -471,13 +475,11 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
         const bool has_aux = (e.act == NS_ACT_GELU && e.aux_out);
         // With an aux output two store groups are in flight per chunk (aux tile, then output tile, each in its own staging
         // tile): the tile about to be rewritten belongs to the OLDER of the two, so one group may stay pending.
-        auto stage_wait = [&]() {                                             // the previous store of this tile has read it
-          if (issuer) {
-            if (elect_one()) {
-              if (has_aux) bulk_wait_read1(); else bulk_wait_read0();
-            }
+        auto stage_wait = [&]() {                                             // the previous store of this slice has read it
+          if (elect_one()) {
+            if (has_aux) bulk_wait_read1(); else bulk_wait_read0();
           }
-          named_bar_sync(1 + half, 128);
+          __syncwarp();
         };
         auto stage_write = [&](uint32_t tile_addr, int sidx, const float (&y)[32]) {   // this thread's 32 columns -> 4 swizzled chunks
 #pragma unroll
@@ -488,12 +490,10 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
         };
         auto stage_commit = [&](const CUtensorMap* map, uint32_t tile_addr, int col0) {
           fence_proxy_async();
-          named_bar_sync(1 + half, 128);
-          if (issuer) {
-            if (elect_one()) {
-              tma_store_3d(map, tile_addr, col0, t_tile, b);
-              bulk_commit();
-            }
+          __syncwarp();
+          if (elect_one()) {
+            tma_store_3d(map, tile_addr + slice_off, col0, t_tile + q * 32, b);
+            bulk_commit();
           }
         };
 #pragma unroll 1
@@ -502,7 +502,7 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
           if (c > 0 && col0 >= p.N) break;                                    // uniform over the 4 warps of this half
           uint32_t zin[2][16];
           if (p.tma_in) {
-            mbar_wait(in_full(half), in_phase);
+            mbar_wait(in_full(ew), in_phase);
             in_phase ^= 1u;
 #pragma unroll
             for (int sidx = 0; sidx < 2; ++sidx)
@@ -510,13 +510,11 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
               for (int cc = 0; cc < 4; ++cc)
                 ld_shared_v4(in_stage + row_off + ((static_cast<uint32_t>(4 * sidx + cc) ^ sw) << 4), zin[sidx][4 * cc], zin[sidx][4 * cc + 1],
                              zin[sidx][4 * cc + 2], zin[sidx][4 * cc + 3]);
-            named_bar_sync(3 + half, 128);                                    // everyone has its slice: the tile may be refilled
-            if (issuer) {
-              if (elect_one()) {                                              // prefetch the next chunk (or the next tile's first)
-                const int c2 = c + 64;
-                if (c2 < kHalfCols && col0 + 64 < p.N) issue_in(tile, c2);
-                else if (tile + tile_step < total_tiles) issue_in(tile + tile_step, 0);
-              }
+            __syncwarp();                                                     // every lane has its row: the slice may be refilled
+            if (elect_one()) {                                                // prefetch the next chunk (or the next tile's first)
+              const int c2 = c + 64;
+              if (c2 < kHalfCols && col0 + 64 < p.N) issue_in(tile, c2);
+              else if (tile + tile_step < total_tiles) issue_in(tile + tile_step, 0);
             }
           }
           stage_wait();
@@ -587,7 +585,7 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
         if (CG == 2) mbar_arrive_cluster(lead_tempty0 + 8u * acc); else mbar_arrive(tempty_bar(acc));
       }
     }
-    if (use_tma && issuer) {
+    if (use_tma) {
       if (elect_one()) bulk_wait0();                                          // outstanding tile stores of this thread
     }
   }
@@ -836,7 +834,7 @@ static int setup_out_maps(Maps& maps, TileProg& prog, int bn) {
     uint64_t dims[3] = {(uint64_t)prog.N, (uint64_t)prog.tout, (uint64_t)prog.batches};
     const long long bs = prog.batches > 1 ? prog.out_bs : static_cast<long long>(prog.tout) * prog.out_rs;
     uint64_t str[2] = {(uint64_t)(prog.out_rs * ld * 2), (uint64_t)(bs * ld * 2)};
-    uint32_t box[3] = {64, kBM, 1};
+    uint32_t box[3] = {64, 32, 1};           // one epilogue warp's slice
     return make_map(m, reinterpret_cast<char*>(base) + prog.out_off * ld * 2, 3, dims, str, box);
   };
   int r = mk(&maps.d, prog.D, prog.ldd);
@@ -861,7 +859,7 @@ static int setup_out_maps(Maps& maps, TileProg& prog, int bn) {
       // position table (rows t of every batch read table row t): a tile never wraps, no batch coordinate
       uint64_t dims[3] = {(uint64_t)prog.N, (uint64_t)e.res_mod, 1};
       uint64_t str[2] = {(uint64_t)(e.ldr * 2), (uint64_t)(e.ldr * 2) * (uint64_t)e.res_mod};
-      uint32_t box[3] = {64, kBM, 1};
+      uint32_t box[3] = {64, 32, 1};
       if ((r = make_map(&maps.in, e.residual, 3, dims, str, box))) return r;
       prog.tma_in = 2;
       prog.in_batched = 0;
