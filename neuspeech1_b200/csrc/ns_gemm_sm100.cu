@@ -18,6 +18,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <type_traits>
 
 namespace ns {
 using namespace sm100;
@@ -102,6 +103,25 @@ struct Seg {
   int a_kstep;
 };
 
+// n / d for 0 <= n < 2^31 as one multiply-high and a shift (the tile decode ran five integer divisions per tile and role)
+struct FastDiv {
+  uint32_t mul, shr, d;
+  __device__ __forceinline__ int div(int n) const { return d == 1u ? n : static_cast<int>(__umulhi(static_cast<uint32_t>(n), mul) >> shr); }
+};
+static FastDiv make_fastdiv(long long dd) {
+  FastDiv f;
+  const uint32_t d = dd < 1 ? 1u : static_cast<uint32_t>(dd);
+  f.d = d; f.mul = 0; f.shr = 0;
+  if (d > 1) {
+    uint32_t lg = 0;
+    while ((1ull << lg) < d) ++lg;
+    const uint32_t pw = 31 + lg;
+    f.mul = static_cast<uint32_t>(((1ull << pw) + d - 1) / d);
+    f.shr = pw - 32;
+  }
+  return f;
+}
+
 struct TileProg {
   int nseg;
   Seg seg[4];
@@ -117,6 +137,8 @@ struct TileProg {
   long long* trace; // developer aid (ns_debug_attn_trace buffer): CTAs 0/1 record (tag, clock64) of producer / MMA events
   int stages;       // operand ring depth (what fits beside the staging tiles)
   int staging_tiles;  // 0, 2 (one output tile per column half) or 4 (+ one aux-output or input tile per half)
+  int epi_mode;     // which compiled copy of the epilogue loop runs (see gemm_nt_kernel)
+  FastDiv fd_units, fd_ntiles, fd_tpb;   // m_units (row tiles, or row-tile pairs with CG = 2), n_tiles, tiles_per_batch
 };
 
 struct Maps {
@@ -139,15 +161,16 @@ constexpr int kNtThreads = 384;
 template <int BN, int CG = 1> struct NtCfg {
   static constexpr int kBBytes = (BN / CG) * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kMaxSmem = 232448 - 1024;      // 227 KB opt-in limit minus the 1 KB the runtime reserves per CTA
+  static constexpr int kMaxSmem = 232448;             // the 227 KB opt-in limit (the runtime's 1 KB per CTA is outside it)
+  static constexpr int kTailBytes = 256 + 2048;       // barriers + the epilogue's bias rows (2 column halves x 2 tile parities)
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
   // staging for the TMA epilogue: [128 rows][64 columns] bf16 tiles (128B swizzle), see TileProg::staging_tiles
   static constexpr int kStagingTile = kBM * 128;
   static int stages_for(int staging_tiles) {
-    const int s = (kMaxSmem - 1024 - 256 - staging_tiles * kStagingTile) / kStageBytes;
+    const int s = (kMaxSmem - kTailBytes - staging_tiles * kStagingTile) / kStageBytes;
     return s > 8 ? 8 : s;
   }
-  static int smem_bytes(int stages, int staging_tiles) { return stages * kStageBytes + staging_tiles * kStagingTile + 1024 + 256; }
+  static int smem_bytes(int stages, int staging_tiles) { return stages * kStageBytes + staging_tiles * kStagingTile + kTailBytes; }
 };
 
 // ------------------------------------------------------------------------------------------------ epilogue helpers
@@ -199,13 +222,21 @@ __device__ __forceinline__ void store32_f32(float* p, bool vec, int ncols, const
 }
 
 // ------------------------------------------------------------------------------------------------ NT kernel
+// Epilogue timeline of warp 4 of CTA 0 (tools/gemm_epi_trace.py): compiled in only with -DNS_GEMM_EPI_TRACE, the probes
+// cost ~5 % on the short-K shapes even when no trace buffer is set.
+#ifdef NS_GEMM_EPI_TRACE
+#define NS_EPI_TRACE(tag) do { if (ew == 0 && lane == 0 && blockIdx.x == 0) trace(3, tag); } while (0)
+#else
+#define NS_EPI_TRACE(tag) do { } while (0)
+#endif
 template <int BN, int CG>
 __global__ void __launch_bounds__(kNtThreads, 1)
 gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TileProg p) {
   using Cfg = NtCfg<BN, CG>;
   const int S = p.stages;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);      // 128B-swizzled tiles need 1 KB alignment: no static shared memory here,
+  if (smem_base & 1023u) __trap();                    // so the dynamic window starts aligned (and every byte of it is budgeted)
   const uint32_t staging_base = smem_base + S * Cfg::kStageBytes;
   const uint32_t bar_base = staging_base + static_cast<uint32_t>(p.staging_tiles) * Cfg::kStagingTile;
   // barrier addresses
@@ -214,6 +245,7 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
   auto in_full = [&](int w) { return bar_base + 8u * (2 * S + 5 + w); };    // one per epilogue warp (8)
+  const uint32_t bias_base = bar_base + 256u;         // [tile parity][column half][128] floats
   const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -237,8 +269,9 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
     }
   };
   auto decode = [&](int tile, int& m_tile, int& n_tile) {
-    const int mu = p.m_fast ? tile % m_units : tile / p.n_tiles;
-    n_tile = p.m_fast ? tile / m_units : tile % p.n_tiles;
+    int mu;
+    if (p.m_fast) { n_tile = p.fd_units.div(tile); mu = tile - n_tile * m_units; }
+    else { mu = p.fd_ntiles.div(tile); n_tile = tile - mu * p.n_tiles; }
     m_tile = (CG == 2) ? 2 * mu + static_cast<int>(cta_rank) : mu;
   };
 
@@ -287,8 +320,8 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
       for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
         int m_tile, n_tile;
         decode(tile, m_tile, n_tile);
-        const int b = m_tile / p.tiles_per_batch;
-        const int t0 = (m_tile % p.tiles_per_batch) * kBM;
+        const int b = p.fd_tpb.div(m_tile);
+        const int t0 = (m_tile - b * p.tiles_per_batch) * kBM;
         const int n0 = n_tile * BN;
         for (int s = 0; s < p.nseg; ++s) {
           const Seg& sg = p.seg[s];
@@ -383,48 +416,90 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
       int m_tile_, n_tile_;
       decode(tile_, m_tile_, n_tile_);
       mbar_expect_tx(in_full(ew), 32 * 128);
+      const int b_ = p.fd_tpb.div(m_tile_);
       tma_load_3d(&maps.in, in_full(ew), in_stage + slice_off, n_tile_ * BN + half * kHalfCols + c_,
-                  (m_tile_ % p.tiles_per_batch) * kBM + q * 32, p.in_batched ? m_tile_ / p.tiles_per_batch : 0);
+                  (m_tile_ - b_ * p.tiles_per_batch) * kBM + q * 32, p.in_batched ? b_ : 0);
     };
     if (use_tma && p.tma_in && tile_first < total_tiles) {
       if (elect_one()) issue_in(tile_first, 0);
     }
     const uint32_t lead_tempty0 = (CG == 2) ? mapa_cluster(tempty_bar(0), 0) : 0u;   // the leader's accumulator-free barriers
+    // Bias: global loads in the column loop cost an L2 round trip per 32-column slice (~500 cycles, measured: the
+    // 227 KB carve-out leaves next to no L1).  Each lane fetches 4 of its half's columns one tile AHEAD into registers, the
+    // warp parks them in shared memory after the accumulator-full wait and the slices read them back as broadcasts.  The
+    // four warps of a half write identical rows; two tile parities keep a warp that runs ahead off the row a slower one
+    // still reads (warps drift by at most one tile: the accumulator stage is recycled only after all of them arrived).
+    constexpr int kBiasLanes = kHalfCols / 4;
+    float4 bias_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto fetch_bias = [&](int tile_) {
+      if (e.bias == nullptr || lane >= kBiasLanes) return;
+      int m_tile_, n_tile_;
+      decode(tile_, m_tile_, n_tile_);
+      const int col = n_tile_ * BN + half * kHalfCols + 4 * lane;
+      if (p.vec_bias && col + 3 < p.N) {
+        bias_next = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+      } else {
+        bias_next.x = col < p.N ? __ldg(e.bias + col) : 0.f;
+        bias_next.y = col + 1 < p.N ? __ldg(e.bias + col + 1) : 0.f;
+        bias_next.z = col + 2 < p.N ? __ldg(e.bias + col + 2) : 0.f;
+        bias_next.w = col + 3 < p.N ? __ldg(e.bias + col + 3) : 0.f;
+      }
+    };
+    if (tile_first < total_tiles) fetch_bias(tile_first);
+    // The tile loop is compiled once per epilogue SHAPE (p.epi_mode, chosen on the host): with everything decided at run
+    // time a plain bias epilogue executed ~1400 warp instructions per tile and warp for ~250 useful ones (branches over
+    // the unused variants, register moves between them), spread over 90 KB of code.
+    //   0 = generic (any epilogue, direct or TMA stores)   1 = TMA store, no activation / residual
+    //   2 = GELU   3 = GELU + pre-activation output   4 = dGELU with the TMA-staged pre-activation   5 = TMA-staged residual
+    auto run_tiles = [&](auto mode_c) {
+    constexpr int MODE = decltype(mode_c)::value;
+    const int act = MODE == 0 ? e.act : ((MODE == 2 || MODE == 3) ? NS_ACT_GELU : (MODE == 4 ? NS_ACT_DGELU : NS_ACT_NONE));
+    const bool use_tma_m = MODE == 0 ? use_tma : true;
+    const int tma_in = MODE == 0 ? p.tma_in : (MODE == 4 ? 1 : (MODE == 5 ? 2 : 0));
+    const bool has_aux = MODE == 0 ? (e.act == NS_ACT_GELU && e.aux_out != nullptr) : (MODE == 3);
+    const bool has_res = MODE == 0 ? (e.residual != nullptr) : (MODE == 5);
     int it = 0;
     for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       int m_tile, n_tile;
       decode(tile, m_tile, n_tile);
-      const int b = m_tile / p.tiles_per_batch;
-      const int t = (m_tile % p.tiles_per_batch) * kBM + q * 32 + lane;
+      const int b = p.fd_tpb.div(m_tile);
+      const int t_tile = (m_tile - b * p.tiles_per_batch) * kBM;
+      const int t = t_tile + q * 32 + lane;
       const int n0 = n_tile * BN;
       const bool valid = t < p.tout && m_tile < m_tiles_real;
       const long long row = static_cast<long long>(b) * p.out_bs + static_cast<long long>(t) * p.out_rs + p.out_off;
       const long long res_row = e.res_mod > 0 ? ((static_cast<long long>(t) * p.out_rs + p.out_off) % e.res_mod) : row;
+      NS_EPI_TRACE(380);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      NS_EPI_TRACE(300);
+      const uint32_t bias_row = bias_base + static_cast<uint32_t>(((it & 1) * 2 + half) * 512);
+      if (e.bias) {
+        if (lane < kBiasLanes)
+          st_shared_v4(bias_row + 16u * lane, __float_as_uint(bias_next.x), __float_as_uint(bias_next.y), __float_as_uint(bias_next.z),
+                       __float_as_uint(bias_next.w));
+        __syncwarp();
+        if (tile + tile_step < total_tiles) fetch_bias(tile + tile_step);
+      }
       // One 32-column slice of this thread's row: TMEM -> registers -> bias / scale / activation / residual.
       // `z_out` receives the pre-activation when NS_ACT_GELU has an aux output.
       // `zin` (16 packed bf16 pairs) carries this slice of the TMA-staged input tile when has_in.
-      auto slice = [&](int c, int col0, int ncols, float (&x)[32], float (&z_out)[32], const uint32_t (&zin)[16], bool has_in) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + half * kHalfCols + c), v);
-        tmem_ld_wait();
+      const uint32_t acc_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + half * kHalfCols);
+      // `v`: the 32 accumulator columns [c, c + 32) of this half, already read from TMEM (the caller keeps several loads in
+      // flight behind one wait).
+      auto slice = [&](const uint32_t (&v)[32], int c, int col0, int ncols, float (&x)[32], float (&z_out)[32], const uint32_t (&zin)[16],
+                       bool has_in) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-        if (e.bias) {
-          if (ncols == 32 && p.vec_bias) {
-            const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);   // col0 % 32 == 0, bias 16B-aligned (checked on host)
+        if (e.bias) {                                     // columns past N hold zeros
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 bb = __ldg(b4 + j);
-              x[4 * j] += bb.x; x[4 * j + 1] += bb.y; x[4 * j + 2] += bb.z; x[4 * j + 3] += bb.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) x[j] += __ldg(e.bias + col0 + j);
+          for (int j = 0; j < 8; ++j) {
+            uint32_t b0, b1, b2, b3;
+            ld_shared_v4(bias_row + 4u * static_cast<uint32_t>(c) + 16u * j, b0, b1, b2, b3);
+            x[4 * j] += __uint_as_float(b0); x[4 * j + 1] += __uint_as_float(b1);
+            x[4 * j + 2] += __uint_as_float(b2); x[4 * j + 3] += __uint_as_float(b3);
           }
         }
         if (col0 < e.alpha_cols) {
@@ -433,11 +508,11 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
             if (col0 + j < e.alpha_cols) x[j] *= e.alpha;
         }
         const bool full = (ncols == 32);
-        if (e.act == NS_ACT_GELU) {
+        if (act == NS_ACT_GELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) { z_out[j] = x[j]; x[j] = gelu_fast(x[j]); }
-        } else if (e.act == NS_ACT_DGELU) {
-          if (has_in && p.tma_in == 1) {
+        } else if (act == NS_ACT_DGELU) {
+          if (has_in && tma_in == 1) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float2 zz = unpack_bf16x2(zin[j]);
@@ -450,8 +525,8 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
             for (int j = 0; j < 32; ++j) x[j] *= dgelu_fast(z[j]);
           }
         }
-        if (e.residual) {
-          if (has_in && p.tma_in == 2) {
+        if (has_res) {
+          if (has_in && tma_in == 2) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float2 rr = unpack_bf16x2(zin[j]);
@@ -465,14 +540,12 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
           }
         }
       };
-      if (use_tma) {
+      if (use_tma_m) {
         // ---- bf16 tiles travel through shared memory: each thread owns the 128-byte row slice (64 columns) of a
         // 128B-swizzled [128 rows][64 columns] staging tile; one lane per column half issues the TMA loads / stores.  The
         // direct path below moves 16 bytes per lane from / to 32 different rows per instruction (LSU bound).
         const uint32_t row_off = static_cast<uint32_t>(q * 32 + lane) * 128u;
         const uint32_t sw = static_cast<uint32_t>(lane & 7);
-        const int t_tile = (m_tile % p.tiles_per_batch) * kBM;
-        const bool has_aux = (e.act == NS_ACT_GELU && e.aux_out);
         // With an aux output two store groups are in flight per chunk (aux tile, then output tile, each in its own staging
         // tile): the tile about to be rewritten belongs to the OLDER of the two, so one group may stay pending.
         auto stage_wait = [&]() {                                             // the previous store of this slice has read it
@@ -488,6 +561,12 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
                          pack_bf16x2(y[8 * cc + 2], y[8 * cc + 3]), pack_bf16x2(y[8 * cc + 4], y[8 * cc + 5]),
                          pack_bf16x2(y[8 * cc + 6], y[8 * cc + 7]));
         };
+        auto stage_write_packed = [&](uint32_t tile_addr, int sidx, const uint32_t (&y)[16]) {
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc)
+            st_shared_v4(tile_addr + row_off + ((static_cast<uint32_t>(4 * sidx + cc) ^ sw) << 4), y[4 * cc], y[4 * cc + 1], y[4 * cc + 2],
+                         y[4 * cc + 3]);
+        };
         auto stage_commit = [&](const CUtensorMap* map, uint32_t tile_addr, int col0) {
           fence_proxy_async();
           __syncwarp();
@@ -501,7 +580,7 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
           const int col0 = n0 + half * kHalfCols + c;
           if (c > 0 && col0 >= p.N) break;                                    // uniform over the 4 warps of this half
           uint32_t zin[2][16];
-          if (p.tma_in) {
+          if (tma_in) {
             mbar_wait(in_full(ew), in_phase);
             in_phase ^= 1u;
 #pragma unroll
@@ -517,16 +596,20 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
               else if (tile + tile_step < total_tiles) issue_in(tile + tile_step, 0);
             }
           }
-          stage_wait();
+          NS_EPI_TRACE(310);
           if (has_aux) {
             // pre-activation tile -> its own staging tile and out; then the activated tile
+            stage_wait();
             uint32_t pk_out[2][16];
 #pragma unroll
             for (int sidx = 0; sidx < 2; ++sidx) {
               const int cs = col0 + 32 * sidx;
               float x[32], z[32];
               if (cs < p.N) {
-                slice(c + 32 * sidx, cs, min(32, p.N - cs), x, z, zin[sidx], false);
+                uint32_t v[32];
+                tmem_ld32(acc_addr + static_cast<uint32_t>(c + 32 * sidx), v);
+                tmem_ld_wait();
+                slice(v, c + 32 * sidx, cs, min(32, p.N - cs), x, z, zin[sidx], false);
               } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) { x[j] = 0.f; z[j] = 0.f; }
@@ -535,29 +618,43 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
 #pragma unroll
               for (int j = 0; j < 16; ++j) pk_out[sidx][j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
             }
+            NS_EPI_TRACE(330);
             stage_commit(&maps.aux, in_stage, col0);
             stage_wait();
+            NS_EPI_TRACE(340);
 #pragma unroll
-            for (int sidx = 0; sidx < 2; ++sidx)
-#pragma unroll
-              for (int cc = 0; cc < 4; ++cc)
-                st_shared_v4(out_stage + row_off + ((static_cast<uint32_t>(4 * sidx + cc) ^ sw) << 4), pk_out[sidx][4 * cc], pk_out[sidx][4 * cc + 1],
-                             pk_out[sidx][4 * cc + 2], pk_out[sidx][4 * cc + 3]);
+            for (int sidx = 0; sidx < 2; ++sidx) stage_write_packed(out_stage, sidx, pk_out[sidx]);
           } else {
+            // both 32-column slices of the chunk: two TMEM loads in flight behind one wait, then the arithmetic -- all of it
+            // while the previous chunk's TMA store still reads this warp's staging slice; the wait for that store sits right
+            // before the slice is rewritten.
+            uint32_t v[2][32], pk[2][16];
+            tmem_ld32(acc_addr + static_cast<uint32_t>(c), v[0]);
+            tmem_ld32(acc_addr + static_cast<uint32_t>(c + 32), v[1]);
+            tmem_ld_wait();
+            NS_EPI_TRACE(322);
 #pragma unroll
             for (int sidx = 0; sidx < 2; ++sidx) {
               const int cs = col0 + 32 * sidx;
               float x[32], z[32];
               if (cs < p.N) {
-                slice(c + 32 * sidx, cs, min(32, p.N - cs), x, z, zin[sidx], p.tma_in != 0);
+                slice(v[sidx], c + 32 * sidx, cs, min(32, p.N - cs), x, z, zin[sidx], tma_in != 0);
               } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) x[j] = 0.f;
               }
-              stage_write(out_stage, sidx, x);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pk[sidx][j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
             }
+            NS_EPI_TRACE(323);
+            stage_wait();
+            NS_EPI_TRACE(320);
+#pragma unroll
+            for (int sidx = 0; sidx < 2; ++sidx) stage_write_packed(out_stage, sidx, pk[sidx]);
           }
+          NS_EPI_TRACE(350);
           stage_commit(&maps.d, out_stage, col0);
+          NS_EPI_TRACE(360);
         }
       } else if (BN >= 64 || half == 0) {
 #pragma unroll 1
@@ -568,8 +665,11 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
           const bool full = (ncols == 32);
           float x[32], z[32];
           const uint32_t no_in[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-          slice(c, col0, ncols, x, z, no_in, false);
-          if (e.act == NS_ACT_GELU && e.aux_out && valid)
+          uint32_t v[32];
+          tmem_ld32(acc_addr + static_cast<uint32_t>(c), v);
+          tmem_ld_wait();
+          slice(v, c, col0, ncols, x, z, no_in, false);
+          if (act == NS_ACT_GELU && e.aux_out && valid)
             store32_bf16(reinterpret_cast<__nv_bfloat16*>(e.aux_out) + row * e.ldaux + col0, p.vec_aux && full, ncols, z);
           if (valid) {
             if (e.out_f32)
@@ -584,6 +684,20 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
       if (lane == 0) {
         if (CG == 2) mbar_arrive_cluster(lead_tempty0 + 8u * acc); else mbar_arrive(tempty_bar(acc));
       }
+      NS_EPI_TRACE(370);
+    }
+    };
+    if constexpr (BN >= 128) {
+      switch (p.epi_mode) {
+        case 1: run_tiles(std::integral_constant<int, 1>{}); break;
+        case 2: run_tiles(std::integral_constant<int, 2>{}); break;
+        case 3: run_tiles(std::integral_constant<int, 3>{}); break;
+        case 4: run_tiles(std::integral_constant<int, 4>{}); break;
+        case 5: run_tiles(std::integral_constant<int, 5>{}); break;
+        default: run_tiles(std::integral_constant<int, 0>{}); break;
+      }
+    } else {
+      run_tiles(std::integral_constant<int, 0>{});
     }
     if (use_tma) {
       if (elect_one()) bulk_wait0();                                          // outstanding tile stores of this thread
@@ -764,8 +878,21 @@ static int launch_nt(const Maps& maps, TileProg& prog, cudaStream_t st) {
   if (CG == 2) grid &= ~1;
   if (grid <= 0) return NS_OK;
   const bool has_aux = (prog.epi.act == NS_ACT_GELU && prog.epi.aux_out);
+  prog.fd_units = make_fastdiv((CG == 2) ? (m_tiles + 1) / 2 : m_tiles);
+  prog.fd_ntiles = make_fastdiv(prog.n_tiles);
+  prog.fd_tpb = make_fastdiv(prog.tiles_per_batch);
   prog.staging_tiles = (BN >= 128 && prog.tma_out) ? ((has_aux || prog.tma_in) ? 4 : 2) : 0;
   prog.stages = Cfg::stages_for(prog.staging_tiles);
+  prog.epi_mode = 0;
+  if (BN >= 128 && prog.tma_out) {
+    const EpiDev& e = prog.epi;
+    if (e.act == NS_ACT_NONE && !e.residual && !prog.tma_in) prog.epi_mode = 1;
+    else if (e.act == NS_ACT_GELU && !e.residual && !prog.tma_in) prog.epi_mode = e.aux_out ? 3 : 2;
+    else if (e.act == NS_ACT_DGELU && !e.residual && prog.tma_in == 1) prog.epi_mode = 4;
+    else if (e.act == NS_ACT_NONE && e.residual && prog.tma_in == 2) prog.epi_mode = 5;
+  }
+  static const bool generic_only = getenv("NS_GEMM_GENERIC_EPILOGUE") != nullptr;
+  if (generic_only) prog.epi_mode = 0;
   prog.trace = get_attn_trace();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);

@@ -177,7 +177,11 @@ def main():
     ap.add_argument("--B", type=int, default=64)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--lib", default=None, help="A/B aid: load this build of the shared library instead of the in-tree one")
     a = ap.parse_args()
+    if a.lib:
+        from neuspeech1_b200 import _abi
+        _abi.LIB_PATH = os.path.abspath(a.lib)
     out = {}
     if "attn" in a.what:
         bench_attn(a.B, a.iters, out)
@@ -189,6 +193,9 @@ def main():
         bench_ln(a.B, a.iters, out)
     s = json.dumps(out, indent=1)
     print(s)
+    for fam, d in out.items():   # compact one-line-per-kernel summary (what gets read back from a gpurun tail)
+        for k, v in d.items():
+            print(f"## {fam:6s} {k:28s} {v['ms'] * 1e3:8.1f} us" + (f" {v['tflops']:7.0f} TF/s" if "tflops" in v else ""))
     if a.out:
         open(a.out, "w").write(s)
 
