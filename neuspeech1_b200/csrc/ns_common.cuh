@@ -82,6 +82,38 @@ __device__ __forceinline__ float dgelu_fast(float z) {
   return fmaf(0.5f * z * s, up, fmaf(0.5f, T, 0.5f));
 }
 
+// Packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): the same fp32 arithmetic in half the issue slots -- the GEMM epilogues
+// are bound by instruction issue, not by the FMA pipe.
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t f2_splat(float v) { return f2_pack(v, v); }
+// tanh(u(z)) of a pair and the clamped z^2 it was built from: the part gelu_fast and dgelu_fast share
+__device__ __forceinline__ uint64_t gelu_tanh2(uint64_t z, uint64_t& t) {
+  float t0, t1, u0, u1;
+  f2_unpack(f2_mul(z, z), t0, t1);
+  t = f2_pack(fminf(t0, 36.0f), fminf(t1, 36.0f));
+  const uint64_t pz = f2_fma(t, f2_fma(t, f2_splat(kGeluC), f2_splat(kGeluB)), f2_splat(kGeluA));
+  f2_unpack(f2_mul(z, pz), u0, u1);
+  return f2_pack(tanh_approx(u0), tanh_approx(u1));
+}
+// gelu_fast / dgelu_fast on a pair: bit-identical to the scalar forms (same operations, same order, same rounding)
+__device__ __forceinline__ uint64_t gelu_fast2(uint64_t z) {
+  uint64_t t;
+  const uint64_t T = gelu_tanh2(z, t);
+  const uint64_t hz = f2_mul(z, f2_splat(0.5f));
+  return f2_fma(hz, T, hz);
+}
+__device__ __forceinline__ uint64_t dgelu_fast2(uint64_t z) {
+  uint64_t t;
+  const uint64_t T = gelu_tanh2(z, t);
+  const uint64_t up = f2_fma(t, f2_fma(t, f2_splat(5.0f * kGeluC), f2_splat(3.0f * kGeluB)), f2_splat(kGeluA));
+  const uint64_t s = f2_fma(f2_mul(T, f2_splat(-1.0f)), T, f2_splat(1.0f));
+  return f2_fma(f2_mul(f2_mul(z, f2_splat(0.5f)), s), up, f2_fma(f2_splat(0.5f), T, f2_splat(0.5f)));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

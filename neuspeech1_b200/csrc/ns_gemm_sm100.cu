@@ -498,8 +498,9 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
           for (int j = 0; j < 8; ++j) {
             uint32_t b0, b1, b2, b3;
             ld_shared_v4(bias_row + 4u * static_cast<uint32_t>(c) + 16u * j, b0, b1, b2, b3);
-            x[4 * j] += __uint_as_float(b0); x[4 * j + 1] += __uint_as_float(b1);
-            x[4 * j + 2] += __uint_as_float(b2); x[4 * j + 3] += __uint_as_float(b3);
+            f2_unpack(f2_add(f2_pack(x[4 * j], x[4 * j + 1]), f2_pack(__uint_as_float(b0), __uint_as_float(b1))), x[4 * j], x[4 * j + 1]);
+            f2_unpack(f2_add(f2_pack(x[4 * j + 2], x[4 * j + 3]), f2_pack(__uint_as_float(b2), __uint_as_float(b3))), x[4 * j + 2],
+                      x[4 * j + 3]);
           }
         }
         if (col0 < e.alpha_cols) {
@@ -510,13 +511,16 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
         const bool full = (ncols == 32);
         if (act == NS_ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { z_out[j] = x[j]; x[j] = gelu_fast(x[j]); }
+          for (int j = 0; j < 16; ++j) {
+            z_out[2 * j] = x[2 * j]; z_out[2 * j + 1] = x[2 * j + 1];
+            f2_unpack(gelu_fast2(f2_pack(x[2 * j], x[2 * j + 1])), x[2 * j], x[2 * j + 1]);
+          }
         } else if (act == NS_ACT_DGELU) {
           if (has_in && tma_in == 1) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float2 zz = unpack_bf16x2(zin[j]);
-              x[2 * j] *= dgelu_fast(zz.x); x[2 * j + 1] *= dgelu_fast(zz.y);
+              f2_unpack(f2_mul(f2_pack(x[2 * j], x[2 * j + 1]), dgelu_fast2(f2_pack(zz.x, zz.y))), x[2 * j], x[2 * j + 1]);
             }
           } else if (valid) {
             float z[32];
@@ -530,7 +534,7 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float2 rr = unpack_bf16x2(zin[j]);
-              x[2 * j] += rr.x; x[2 * j + 1] += rr.y;
+              f2_unpack(f2_add(f2_pack(x[2 * j], x[2 * j + 1]), f2_pack(rr.x, rr.y)), x[2 * j], x[2 * j + 1]);
             }
           } else if (valid) {
             float r[32];
@@ -598,26 +602,34 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
           }
           NS_EPI_TRACE(310);
           if (has_aux) {
-            // pre-activation tile -> its own staging tile and out; then the activated tile
-            stage_wait();
-            uint32_t pk_out[2][16];
+            // pre-activation tile -> its own staging tile and out; then the activated tile.  Loads and arithmetic of both
+            // slices first (the previous chunk's two stores drain meanwhile), then wait / write / commit per tile.
+            uint32_t pk_z[2][16], pk_out[2][16];
+            {
+              uint32_t v[2][32];
+              tmem_ld32(acc_addr + static_cast<uint32_t>(c), v[0]);
+              tmem_ld32(acc_addr + static_cast<uint32_t>(c + 32), v[1]);
+              tmem_ld_wait();
 #pragma unroll
-            for (int sidx = 0; sidx < 2; ++sidx) {
-              const int cs = col0 + 32 * sidx;
-              float x[32], z[32];
-              if (cs < p.N) {
-                uint32_t v[32];
-                tmem_ld32(acc_addr + static_cast<uint32_t>(c + 32 * sidx), v);
-                tmem_ld_wait();
-                slice(v, c + 32 * sidx, cs, min(32, p.N - cs), x, z, zin[sidx], false);
-              } else {
+              for (int sidx = 0; sidx < 2; ++sidx) {
+                const int cs = col0 + 32 * sidx;
+                float x[32], z[32];
+                if (cs < p.N) {
+                  slice(v[sidx], c + 32 * sidx, cs, min(32, p.N - cs), x, z, zin[sidx], false);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) { x[j] = 0.f; z[j] = 0.f; }
+                  for (int j = 0; j < 32; ++j) { x[j] = 0.f; z[j] = 0.f; }
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  pk_z[sidx][j] = pack_bf16x2(z[2 * j], z[2 * j + 1]);
+                  pk_out[sidx][j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+                }
               }
-              stage_write(in_stage, sidx, z);
-#pragma unroll
-              for (int j = 0; j < 16; ++j) pk_out[sidx][j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
             }
+            stage_wait();
+#pragma unroll
+            for (int sidx = 0; sidx < 2; ++sidx) stage_write_packed(in_stage, sidx, pk_z[sidx]);
             NS_EPI_TRACE(330);
             stage_commit(&maps.aux, in_stage, col0);
             stage_wait();
