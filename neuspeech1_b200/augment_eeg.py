@@ -95,17 +95,24 @@ class BatchAugmenter:
     def plan(self, shapes: Sequence[Sequence[int]], device) -> dict:
         """Draw the batch's random decisions -> keyword arguments of ops.aug_pass / engine.encode(aug=...)."""
         plans = [self._draw(s) for s in shapes]
-        i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=device)
-        kw = dict(n=i32([p.n for p in plans]), shift=i32([p.shift for p in plans]), e0=i32([p.e0 for p in plans]),
-                  e1=i32([p.e1 for p in plans]), flags=i32([p.flags for p in plans]))
-        if any(p.grid is not None for p in plans):
+        B = len(plans)
+        has_grid = any(p.grid is not None for p in plans)
+        # All per-sample integers travel in ONE pinned staging buffer and one asynchronous copy (a pageable
+        # torch.tensor(..., device=...) per field is a synchronous memcpy on the compute stream: it drains the GPU every step).
+        rows = [[p.n for p in plans], [p.shift for p in plans], [p.e0 for p in plans], [p.e1 for p in plans], [p.flags for p in plans]]
+        if has_grid:
+            rows += [[p.grid.shape[1] if p.grid is not None else 1 for p in plans], [p.rep_c for p in plans], [p.rep_t for p in plans]]
+        host = torch.empty(len(rows), B, dtype=torch.int32, pin_memory=torch.cuda.is_available())
+        host.copy_(torch.tensor(rows, dtype=torch.int32))
+        devt = host.to(device, non_blocking=True)
+        kw = dict(n=devt[0], shift=devt[1], e0=devt[2], e1=devt[3], flags=devt[4])
+        if has_grid:
             gmax = max(p.grid.numel() for p in plans if p.grid is not None)
-            grid = torch.ones(len(plans), gmax, dtype=torch.uint8)
+            grid = torch.ones(B, gmax, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
             for b, p in enumerate(plans):
                 if p.grid is not None:
                     grid[b, :p.grid.numel()] = p.grid.reshape(-1)
-            kw.update(grid=grid.to(device), grid_stride=gmax, gl=i32([p.grid.shape[1] if p.grid is not None else 1 for p in plans]),
-                      rep_c=i32([p.rep_c for p in plans]), rep_t=i32([p.rep_t for p in plans]))
+            kw.update(grid=grid.to(device, non_blocking=True), grid_stride=gmax, gl=devt[5], rep_c=devt[6], rep_t=devt[7])
         self._plans = plans
         return kw
 
