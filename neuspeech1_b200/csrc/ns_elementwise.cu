@@ -387,6 +387,15 @@ __global__ void __launch_bounds__(512) greedy_kernel(int V, long long ld, const 
 }
 
 // ------------------------------------------------------------------------------------------------ augmentation pass
+__device__ __forceinline__ void store8(__nv_bfloat16* dst, float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7) {
+  uint4 u;
+  u.x = pack_bf16x2(a0, a1); u.y = pack_bf16x2(a2, a3); u.z = pack_bf16x2(a4, a5); u.w = pack_bf16x2(a6, a7);
+  *reinterpret_cast<uint4*>(dst) = u;
+}
+__device__ __forceinline__ void store8(float* dst, float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7) {
+  reinterpret_cast<float4*>(dst)[0] = make_float4(a0, a1, a2, a3);
+  reinterpret_cast<float4*>(dst)[1] = make_float4(a4, a5, a6, a7);
+}
 __device__ __forceinline__ uint32_t mulhilo(uint32_t a, uint32_t b, uint32_t* hi) {
   const unsigned long long p = static_cast<unsigned long long>(a) * b;
   *hi = static_cast<uint32_t>(p >> 32);
@@ -446,24 +455,83 @@ __global__ void aug_bct_kernel(const AugDev a, const float* __restrict__ x, TO* 
   y[(static_cast<long long>(b) * a.C + c) * a.T + tau] = from_f<TO>(aug_value(a, x, b, c, tau));
 }
 
-// layout 1: (B,C,T) -> (B,T,Cp) channels-last through a 32(t) x 64(c) shared tile; pad channels written as zero
+// layout 1: (B,C,T) -> (B,T,Cp) channels-last through a 128(t) x 64(c) shared tile; pad channels written as zero.
+// HBM-bound (4 B in + 2 B out per element): every lane reads 16 bytes (four consecutive samples of one channel, a warp covers
+// 512 contiguous bytes) and writes 16 bytes (eight channels of one sample).  The per-sample decisions (length, shift, edge
+// zeroing, mask grid geometry) are read once per block; the grid cell is looked up once per run of samples inside it.
+constexpr int kAugTT = 128, kAugTC = 64;
 template <typename TO>
 __global__ void __launch_bounds__(256) aug_btc_kernel(const AugDev a, const float* __restrict__ x, TO* __restrict__ y) {
-  __shared__ float tile[64][33];
+  // tile[channel][sample], 16-byte groups of 4 samples XOR-swizzled with (channel / 8): the 16-byte stores of the read phase
+  // and the scalar reads of the write phase (lanes = 4 samples x 8 channel groups) are both bank-conflict free
+  __shared__ __align__(16) float tile[kAugTC][kAugTT];
+  auto at = [&](int cc, int t) -> float& { return tile[cc][((((t >> 2) ^ (cc >> 3)) & 31) << 2) | (t & 3)]; };
   const int b = blockIdx.z;
-  const int c0 = blockIdx.y * 64;
-  const int t0 = blockIdx.x * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-  for (int cc = ty; cc < 64; cc += 8) {
-    const int c = c0 + cc, tau = t0 + tx;
-    tile[cc][tx] = (c < a.C && tau < a.T) ? aug_value(a, x, b, c, tau) : 0.f;
+  const int c0 = blockIdx.y * kAugTC;
+  const int t0 = blockIdx.x * kAugTT;
+  const int sh = a.shift ? a.shift[b] : 0;
+  const int n = a.n ? min(a.n[b], a.Tin) : a.Tin;
+  const int fl = a.flags ? a.flags[b] : 0;
+  const int e0 = a.e0 ? a.e0[b] : 0, e1 = a.e1 ? a.e1[b] : 0;
+  const int lo = max(e0, 0), hi = min(n, n - e1);            // samples outside [lo, hi) of the source are zero
+  const bool masked = (fl & 1) && a.grid && n > 0;
+  const int rep_c = masked ? a.rep_c[b] : 1, rep_t = masked ? a.rep_t[b] : 1, gl = masked ? a.gl[b] : 1;
+  const unsigned char* grid = masked ? a.grid + b * a.grid_stride : nullptr;
+  // 16-byte loads need the SOURCE index t = tau - shift of a lane's first sample to be a multiple of 4 (rows are Tin floats)
+  const bool vec = ((sh & 3) == 0) && ((a.Tin & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  for (int e = threadIdx.x; e < kAugTC * (kAugTT / 4); e += 256) {
+    const int cc = e / (kAugTT / 4), t4 = (e % (kAugTT / 4)) * 4;
+    const int c = c0 + cc, tau = t0 + t4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    const int t = tau - sh;
+    if (c < a.C && t + 3 >= lo && t < hi) {
+      const float* xr = x + (static_cast<long long>(b) * a.C + c) * a.Tin;
+      if (vec && t >= 0 && t + 3 < a.Tin) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(xr + t));
+        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (t + k >= 0 && t + k < n) v[k] = __ldg(xr + t + k);
+      }
+      if (fl & 2) {   // gaussian noise: the reference returns signal + (signal + noise)
+        const float sg = a.sigma[static_cast<long long>(b) * a.C + c];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (t + k >= 0 && t + k < n)
+            v[k] = 2.0f * v[k] + sg * philox_normal(a.seed, (static_cast<unsigned long long>(b) * a.C + c) * a.Tin + (t + k));
+      }
+      if (masked) {
+        const unsigned char* grow = grid + static_cast<long long>(c / rep_c) * gl;
+        const int tb = max(t, 0);
+        int gq = tb / rep_t, gr = tb - gq * rep_t;
+        bool keep = grow[gq] != 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (t + k < tb) continue;                           // before the signal starts: already zero
+          if (t + k > tb) { if (++gr == rep_t) { gr = 0; ++gq; keep = (t + k < n) ? grow[gq] != 0 : false; } }
+          if (!keep) v[k] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (t + k < lo || t + k >= hi) v[k] = 0.f;
+    }
+    *reinterpret_cast<float4*>(&at(cc, t4)) = make_float4(v[0], v[1], v[2], v[3]);
   }
   __syncthreads();
-  // write: each thread 1 channel-pair column... 64 channels contiguous per time row
-  for (int e = threadIdx.x; e < 32 * 64; e += 256) {
-    const int tt = e >> 6, cc = e & 63;
-    const int c = c0 + cc, tau = t0 + tt;
-    if (c < a.Cp && tau < a.T) y[(static_cast<long long>(b) * a.T + tau) * a.Cp + c] = from_f<TO>(tile[cc][tt]);
+  // write: 8 channels (16 bytes of bf16, 32 of fp32) of one sample per lane; the 64 channels of a sample are contiguous
+  const bool vec_out = (a.Cp % 8 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+  for (int e = threadIdx.x; e < kAugTT * (kAugTC / 8); e += 256) {
+    const int tt = e / (kAugTC / 8), ch = (e % (kAugTC / 8)) * 8;
+    const int c = c0 + ch, tau = t0 + tt;
+    if (tau >= a.T || c >= a.Cp) continue;
+    TO* dst = y + (static_cast<long long>(b) * a.T + tau) * a.Cp + c;
+    if (vec_out && c + 8 <= a.Cp) {
+      store8(dst, at(ch, tt), at(ch + 1, tt), at(ch + 2, tt), at(ch + 3, tt), at(ch + 4, tt), at(ch + 5, tt), at(ch + 6, tt), at(ch + 7, tt));
+    } else {
+      for (int k = 0; k < 8 && c + k < a.Cp; ++k) dst[k] = from_f<TO>(at(ch + k, tt));
+    }
   }
 }
 
@@ -732,7 +800,7 @@ int ns_aug_pass(const ns_aug_args* a, const float* x, void* y, void* stream) {
     if (a->out_dtype == NS_BF16) aug_bct_kernel<bf16><<<grid, 256, 0, st>>>(d, x, reinterpret_cast<bf16*>(y));
     else aug_bct_kernel<float><<<grid, 256, 0, st>>>(d, x, reinterpret_cast<float*>(y));
   } else {
-    dim3 grid((a->T + 31) / 32, (a->Cp + 63) / 64, a->B);
+    dim3 grid((a->T + kAugTT - 1) / kAugTT, (a->Cp + kAugTC - 1) / kAugTC, a->B);
     if (a->out_dtype == NS_BF16) aug_btc_kernel<bf16><<<grid, 256, 0, st>>>(d, x, reinterpret_cast<bf16*>(y));
     else aug_btc_kernel<float><<<grid, 256, 0, st>>>(d, x, reinterpret_cast<float*>(y));
   }

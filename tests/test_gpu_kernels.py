@@ -459,6 +459,19 @@ def test_aug_pass_matches_oracle():
     for b, p in enumerate(plans):
         pad[b, :, p.n:] = 0
     assert torch.equal(y2[:, :, :C].cpu(), pad.permute(0, 2, 1))
+    # the 16-byte load path of the channels-last kernel (source rows of 4k floats, shifts that are multiples of 4), with
+    # noise + mask + edge zeroing on: bit-identical to the elementwise (B,C,T) kernel checked against the oracle above
+    Tin4 = (Tin + 3) // 4 * 4
+    xb4 = torch.zeros(B, C, Tin4); xb4[:, :, :Tin] = xb
+    kw4 = dict(kw); kw4["shift"] = (kw["shift"] // 4) * 4
+    kw4["flags"] = i32([3, 1, 3, 0])
+    kw4["sigma"] = torch.full((B, C), 0.1, device=DEV); kw4["seed"] = 77
+    ya = torch.empty(B, C, T, device=DEV)
+    ops.aug_pass(xb4.to(DEV), ya, 0, **kw4)
+    yb = torch.full((B, T, Cp), 5.0, dtype=torch.float32, device=DEV)
+    ops.aug_pass(xb4.to(DEV), yb, 1, **kw4)
+    assert torch.equal(yb[:, :, :C], ya.permute(0, 2, 1)) and bool((yb[:, :, C:] == 0).all())
+    assert bool((ya[0] != ya[1]).any())
 
 
 def test_aug_noise_statistics():

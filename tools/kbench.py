@@ -164,11 +164,39 @@ def bench_ln(B, iters, out):
     y = torch.empty_like(x); dx = torch.empty_like(x)
     gm = torch.ones(d, device=DEV); bt = torch.zeros(d, device=DEV)
     mean = torch.empty(M, device=DEV); rstd = torch.empty(M, device=DEV)
+    res = {}
     t = timeit(lambda: ops.layernorm_fwd(x, gm, bt, y, mean, rstd), iters)
-    res = {"fwd_ms": t, "fwd_gbs": 2.0 * M * d * 2 / t / 1e6}
+    res["fwd"] = {"ms": t, "gbs": 2.0 * M * d * 2 / t / 1e6}
     t = timeit(lambda: ops.layernorm_bwd(y, x, gm, mean, rstd, dx, dres=x), iters)
-    res["bwd_ms"] = t; res["bwd_gbs"] = 4.0 * M * d * 2 / t / 1e6
+    res["bwd"] = {"ms": t, "gbs": 4.0 * M * d * 2 / t / 1e6}
     out["ln"] = res
+
+
+def bench_aug(B, iters, out):
+    """K0: (B, C, 6000) fp32 -> (B, 6000, Cp) bf16 channels-last; algorithmic bytes B*C*T*(4 + 2)."""
+    C, T = 208, 6000
+    g = torch.Generator().manual_seed(5)
+    x = (0.3 * torch.randn(B, C, T, generator=g)).clamp_(-1, 1)
+    lens = torch.randint(400, 5000, (B,), generator=g)
+    for b in range(B):
+        x[b, :, int(lens[b]):] = 0
+    x = x.to(DEV)
+    y = torch.empty(B, T, C, dtype=torch.bfloat16, device=DEV)
+    n = lens.to(torch.int32).to(DEV)
+    res = {}
+    byts = B * C * T * 6.0
+    t = timeit(lambda: ops.aug_pass(x, y, 1), iters)
+    res["identity, full length"] = {"ms": t, "gbs": byts / t / 1e6}
+    t = timeit(lambda: ops.aug_pass(x, y, 1, n=n), iters)
+    res["identity, ragged lengths"] = {"ms": t, "gbs": byts / t / 1e6}
+    gl = (lens + 39) // 40
+    gmax = int(gl.max()) * C
+    grid = (torch.rand(B, gmax, generator=g) >= 0.25).to(torch.uint8).to(DEV)
+    i32 = lambda v: v.to(torch.int32).to(DEV)
+    kw = dict(n=n, flags=i32(torch.ones(B)), grid=grid, grid_stride=gmax, gl=i32(gl), rep_c=i32(torch.ones(B)), rep_t=i32(torch.full((B,), 40)))
+    t = timeit(lambda: ops.aug_pass(x, y, 1, **kw), iters)
+    res["block mask"] = {"ms": t, "gbs": byts / t / 1e6}
+    out["aug"] = res
 
 
 def main():
@@ -191,11 +219,14 @@ def main():
         bench_head(a.B, a.iters, out)
     if "ln" in a.what:
         bench_ln(a.B, a.iters, out)
+    if "aug" in a.what:
+        bench_aug(a.B, a.iters, out)
     s = json.dumps(out, indent=1)
     print(s)
     for fam, d in out.items():   # compact one-line-per-kernel summary (what gets read back from a gpurun tail)
         for k, v in d.items():
-            print(f"## {fam:6s} {k:28s} {v['ms'] * 1e3:8.1f} us" + (f" {v['tflops']:7.0f} TF/s" if "tflops" in v else ""))
+            print(f"## {fam:6s} {k:28s} {v['ms'] * 1e3:8.1f} us" + (f" {v['tflops']:7.0f} TF/s" if "tflops" in v else "")
+                  + (f" {v['gbs']:7.0f} GB/s" if "gbs" in v else ""))
     if a.out:
         open(a.out, "w").write(s)
 
