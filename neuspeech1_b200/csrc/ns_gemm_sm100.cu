@@ -18,6 +18,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <utility>
 #include <type_traits>
 
 namespace ns {
@@ -735,29 +736,30 @@ struct TnProg {
   long long si, sj, stap;     // output strides
   float* G;
   float alpha;
-  int stage_bytes;            // 16 KB (X) + 8 KB per 64 columns of Y
+  int stage_bytes;            // icta x 16 KB (X) + 8 KB per 64 columns of Y
+  int icta;                   // 128-row output tiles per CTA (1..4): with a narrow Y (J <= 64) one CTA streams up to 512
+                              // contiguous X columns per contraction row and keeps icta accumulators (icta * bj TMEM columns)
+  int stages;                 // operand ring depth
 };
 struct TnMaps {
   CUtensorMap x;
   CUtensorMap y;
 };
 constexpr int kTnThreads = 256;
-constexpr int kTnStages = 4;
-constexpr int kTnABytes = 128 * 64 * 2;        // two [64 m][64 i] boxes
-constexpr int kTnBBytes = 256 * 64 * 2;        // up to four [64 m][64 j] boxes
-constexpr int kTnStageBytes = kTnABytes + kTnBBytes;
-constexpr int kTnSmemBytes = kTnStages * kTnStageBytes + 1024 + 256;
+constexpr int kTnMaxStages = 4;
+constexpr int kTnABytes = 128 * 64 * 2;        // two [64 m][64 i] boxes per output row tile
+constexpr int kTnSmemMax = 232448;
 
 __global__ void __launch_bounds__(kTnThreads, 1)
 gemm_tn_kernel(const __grid_constant__ TnMaps maps, const __grid_constant__ TnProg p) {
-  constexpr int S = kTnStages;
+  const int S = p.stages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + S * p.stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
-  const uint32_t tfull_bar = bar_base + 8u * (2 * S);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 1);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kTnMaxStages + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * kTnMaxStages);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kTnMaxStages + 1);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
@@ -772,10 +774,11 @@ gemm_tn_kernel(const __grid_constant__ TnMaps maps, const __grid_constant__ TnPr
   const int blk0 = split * p.blocks_per_split;
   const int blk1 = min(p.total_blocks, blk0 + p.blocks_per_split);
   const int nblk = max(0, blk1 - blk0);
-  const int i0 = i_tile * 128;
+  const int i0 = i_tile * 128 * p.icta;         // i_tile counts groups of icta row tiles
   const int j0 = j_tile * 256;
   const int jboxes = (p.bj + 63) / 64;
-  const uint32_t stage_tx = kTnABytes + static_cast<uint32_t>(jboxes) * 8192u;
+  const uint32_t a_bytes = static_cast<uint32_t>(p.icta) * kTnABytes;
+  const uint32_t stage_tx = a_bytes + static_cast<uint32_t>(jboxes) * 8192u;
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < S; ++s) {
@@ -803,10 +806,10 @@ gemm_tn_kernel(const __grid_constant__ TnMaps maps, const __grid_constant__ TnPr
         const int t0 = (blk % p.blocks_per_batch) * 64;
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sa = smem_base + stage * p.stage_bytes;
-        const uint32_t sb = sa + kTnABytes;
+        const uint32_t sb = sa + a_bytes;
         mbar_expect_tx(full_bar(stage), stage_tx);
-        tma_load_4d(&maps.x, full_bar(stage), sa, i0, 0, t0, b);
-        tma_load_4d(&maps.x, full_bar(stage), sa + 8192u, i0 + 64, 0, t0, b);
+        for (int g = 0; g < 2 * p.icta; ++g)                  // boxes past I arrive zero-filled
+          tma_load_4d(&maps.x, full_bar(stage), sa + 8192u * g, i0 + 64 * g, 0, t0, b);
         for (int g = 0; g < jboxes; ++g)
           tma_load_4d(&maps.y, full_bar(stage), sb + 8192u * g, j0 + 64 * g, p.y_par[tap], t0 + p.y_off[tap], b);
         if (++stage == S) { stage = 0; phase ^= 1u; }
@@ -822,16 +825,17 @@ gemm_tn_kernel(const __grid_constant__ TnMaps maps, const __grid_constant__ TnPr
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sa = smem_base + stage * p.stage_bytes;
-        const uint32_t sb = sa + kTnABytes;
+        const uint32_t sb = sa + a_bytes;
         // MN-major: LBO = distance between 64-element MN groups (8192 B), SBO = distance between 8-row K groups (1024 B)
-        const uint64_t adesc = umma_smem_desc(sa, 8192, 1024);
         const uint64_t bdesc = umma_smem_desc(sb, 8192, 1024);
+        for (int it = 0; it < p.icta; ++it) {
+          const uint64_t adesc = umma_smem_desc(sa + static_cast<uint32_t>(it) * kTnABytes, 8192, 1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          // 16 contraction rows = 2048 B  -> +128 in the (addr >> 4) field
-          umma_f16(tmem_base, adesc + static_cast<uint64_t>(128 * k), bdesc + static_cast<uint64_t>(128 * k), idesc, accumulate);
-          accumulate = 1;
+          for (int k = 0; k < 4; ++k)   // 16 contraction rows = 2048 B  -> +128 in the (addr >> 4) field
+            umma_f16(tmem_base + static_cast<uint32_t>(it * p.bj), adesc + static_cast<uint64_t>(128 * k),
+                     bdesc + static_cast<uint64_t>(128 * k), idesc, (accumulate | (k > 0)) ? 1u : 0u);
         }
+        accumulate = 1;
         umma_commit(empty_bar(stage));
       }
       __syncwarp();
@@ -844,18 +848,33 @@ gemm_tn_kernel(const __grid_constant__ TnMaps maps, const __grid_constant__ TnPr
     if (nblk > 0) {
       mbar_wait(tfull_bar, 0);
       tc_fence_after();
-      const int i = i0 + q * 32 + lane;
-      float* g_row = p.G + static_cast<long long>(tap) * p.stap + static_cast<long long>(i) * p.si;
 #pragma unroll 1
-      for (int c = 0; c < p.bj; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c), v);
-        tmem_ld_wait();
-        if (i < p.I) {
+      for (int it = 0; it < p.icta; ++it) {
+        const int i = i0 + it * 128 + q * 32 + lane;
+        float* g_row = p.G + static_cast<long long>(tap) * p.stap + static_cast<long long>(i) * p.si;
+#pragma unroll 1
+        for (int c = 0; c < p.bj; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(it * p.bj + c), v);
+          tmem_ld_wait();
+          if (i < p.I) {
+            float* g0 = g_row + static_cast<long long>(j0 + c) * p.sj;
+            if (p.sj == 1 && j0 + c + 32 <= p.J && (reinterpret_cast<uintptr_t>(g0) & 15) == 0) {
+              // this thread's 32 columns are contiguous: eight 16-byte reductions instead of 32 scalar ones to 32 different
+              // lines per warp instruction (the split-K tail was a third of the kernel at the LoRA shapes)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int jj = j0 + c + j;
-            if (jj < p.J) atomicAdd(g_row + static_cast<long long>(jj) * p.sj, p.alpha * __uint_as_float(v[j]));
+              for (int j = 0; j < 32; j += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g0 + j), "f"(p.alpha * __uint_as_float(v[j])),
+                             "f"(p.alpha * __uint_as_float(v[j + 1])), "f"(p.alpha * __uint_as_float(v[j + 2])),
+                             "f"(p.alpha * __uint_as_float(v[j + 3]))
+                             : "memory");
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int jj = j0 + c + j;
+                if (jj < p.J) atomicAdd(g_row + static_cast<long long>(jj) * p.sj, p.alpha * __uint_as_float(v[j]));
+              }
+            }
           }
         }
       }
@@ -1172,24 +1191,39 @@ int conv3_dgrad_fast(int B, int Tin, int Cp, int N, int stride, const void* dz, 
 static int launch_tn(const TnMaps& maps, TnProg& p, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    NS_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTnSmemBytes));
+    NS_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTnSmemMax));
     attr_done = true;
   }
   p.blocks_per_batch = (p.tout + 63) / 64;
   p.total_blocks = p.batches * p.blocks_per_batch;
-  p.i_tiles = (p.I + 127) / 128;
-  p.j_tiles = (p.J + 255) / 256;
   const int jt = p.J < 256 ? p.J : 256;   // all j tiles use the same UMMA N (tail columns masked in the epilogue)
   p.bj = (jt + 15) / 16 * 16;
+  // narrow Y (the LoRA rank): one CTA takes up to four row tiles, i.e. up to 1 KB of every X row it streams
+  static const bool no_wide = getenv("NS_TN_NO_WIDE") != nullptr;
+  p.icta = 1;
+  if (!no_wide && p.ntaps == 1 && p.bj <= 64) {
+    const int it = (p.I + 127) / 128;
+    p.icta = it >= 4 ? 4 : it;
+  }
+  p.i_tiles = (p.I + 128 * p.icta - 1) / (128 * p.icta);
+  p.j_tiles = (p.J + 255) / 256;
+  p.stage_bytes = p.icta * kTnABytes + ((p.bj + 63) / 64) * 8192;
   const int tiles = p.i_tiles * p.j_tiles * p.ntaps;
-  int nsplit = (2 * sm_count() + tiles - 1) / tiles;
+  int nsplit;
+  if (p.icta == 1) {                                         // 4 stages of <= 48 KB; two CTAs per SM when they fit
+    p.stages = kTnMaxStages;
+    nsplit = (2 * sm_count() + tiles - 1) / tiles;
+  } else {                                                   // wide stages (up to 72 KB): one CTA per SM, 3 stages
+    p.stages = (kTnSmemMax - 1024 - 256) / p.stage_bytes;
+    if (p.stages > kTnMaxStages) p.stages = kTnMaxStages;
+    nsplit = (sm_count() + tiles - 1) / tiles;
+  }
   const int max_split = (p.total_blocks + 3) / 4;           // at least 4 contraction blocks per CTA
   if (nsplit > max_split) nsplit = max_split;
   if (nsplit < 1) nsplit = 1;
   p.blocks_per_split = (p.total_blocks + nsplit - 1) / nsplit;
   p.nsplit = (p.total_blocks + p.blocks_per_split - 1) / p.blocks_per_split;
-  p.stage_bytes = kTnABytes + ((p.bj + 63) / 64) * 8192;
-  const int smem = kTnStages * p.stage_bytes + 1024 + 256;
+  const int smem = p.stages * p.stage_bytes + 1024 + 256;
   gemm_tn_kernel<<<tiles * p.nsplit, kTnThreads, smem, st>>>(maps, p);
   NS_LAUNCH_CHECK();
   count(C_WGRAD_TC);
@@ -1200,6 +1234,11 @@ int gemm_tn_fast(long long M, int I, int J, const void* X, long long ldx, const 
                  long long si, long long sj, float alpha, cudaStream_t st) {
   if (ldx % 8 != 0 || ldy % 8 != 0 || !aligned16(X) || !aligned16(Y) || M > 0x7fffffffLL) return NS_ERR_UNSUPPORTED;
   if (I % 8 != 0 || J % 8 != 0) return NS_ERR_UNSUPPORTED;
+  // G^T = Y^T X is the same sum: put the WIDE operand on the X side (rows of the MMA, several row tiles per CTA) and the
+  // LoRA-rank-wide one on the Y side
+  if (I <= 64 && J >= 128) {
+    std::swap(I, J); std::swap(X, Y); std::swap(ldx, ldy); std::swap(si, sj);
+  }
   TnMaps maps;
   uint64_t dx[4] = {(uint64_t)I, 1, (uint64_t)M, 1};
   uint64_t sx[3] = {(uint64_t)ldx * 2, (uint64_t)ldx * 2, (uint64_t)ldx * 2 * (uint64_t)M};

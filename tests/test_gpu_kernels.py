@@ -158,7 +158,8 @@ def test_fast_path_required_fails_loudly():
 
 # ------------------------------------------------------------------------------------------------ GEMM TN (wgrad)
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
-@pytest.mark.parametrize("M,I,J", [(64, 128, 32), (128, 128, 64), (1000, 512, 32), (4096, 2048, 32), (3001, 512, 96), (2000, 512, 208), (1500, 256, 512)])
+@pytest.mark.parametrize("M,I,J", [(64, 128, 32), (128, 128, 64), (1000, 512, 32), (4096, 2048, 32), (3001, 512, 96), (2000, 512, 208), (1500, 256, 512),
+                                   (2000, 32, 512), (1111, 32, 2048), (700, 64, 384), (5000, 1280, 32)])
 def test_gemm_tn(M, I, J, dtype):
     x = rnd(M, I, dtype=dtype, seed=1); y = rnd(M, J, dtype=dtype, seed=2)
     ref = 0.5 * (x.float().t() @ y.float())

@@ -129,6 +129,9 @@ def bench_gemm(B, iters, out):
     G2 = torch.zeros(F * r, device=DEV)
     t = timeit(lambda: ops.gemm_tn(x2048, t32, G2, r, 1), iters)
     res["wgrad 2048x32"] = {"ms": t, "tflops": 2.0 * M * F * r / t / 1e9}
+    G3 = torch.zeros(r * d, device=DEV)
+    t = timeit(lambda: ops.gemm_tn(t32, x512, G3, d, 1), iters)
+    res["wgrad 32x512 (dA)"] = {"ms": t, "tflops": 2.0 * M * d * r / t / 1e9}
     out["gemm"] = res
 
 
