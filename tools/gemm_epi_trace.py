@@ -3,7 +3,9 @@ usage: gemm_epi_trace.py [plain|gelu|gelu_aux|dgelu] [n_events]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from neuspeech1_b200 import ops
+from neuspeech1_b200 import ops, _abi
+if os.environ.get("NS_LIB"):      # a build with -DNS_GEMM_EPI_TRACE (the probes are compiled out of the product library)
+    _abi.LIB_PATH = os.path.abspath(os.environ["NS_LIB"])
 DEV = torch.device("cuda")
 kind = sys.argv[1] if len(sys.argv) > 1 else "gelu"
 M, N, K = 96000, 2048, 512
