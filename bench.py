@@ -268,7 +268,7 @@ def run_ours(args):
         # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/), null when not captured
         traffic = None
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01b_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01c_traffic.json")))
             traffic = tj.get(top_name, {}).get("dram_bytes_per_launch_avg")
         except Exception:
             traffic = None
