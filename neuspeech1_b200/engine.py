@@ -244,6 +244,8 @@ class WhisperEEGEngine:
         W["dec.wkv"] = self._c(wkv); W["dec.wkv_t"] = self._ct(wkv); W["dec.bkv"] = torch.cat(kv_b)
         self.P = W
         self._decode_graphs = {}
+        self._train_graphs = {}
+        self.graph_launches = getattr(self, "graph_launches", 0)   # ns_* launches executed through CUDA-graph replays
         self._weights_version = getattr(self, "_weights_version", 0) + 1
         self._lora_tb = None             # LoRA operand views / transpose job table are rebuilt by pack_trainable
         self.suppress = torch.tensor(list(dm.begin_suppress_tokens), dtype=torch.int32, device=dev)
@@ -667,14 +669,72 @@ class WhisperEEGEngine:
         self._packed = False
         return self.sumsq
 
-    def train_step(self, x, labels, lr: float, aug: Optional[dict] = None, all_reduce=None):
-        """One Trainer.training_step + optimizer step.  `all_reduce(flat_grad)` is the data-parallel hook."""
-        self.pack_trainable()
-        loss, _, _ = self.forward_loss(x, labels, aug=aug, save=True, ce_grad_scale=1.0)
-        self.backward()
+    def train_step(self, x, labels, lr: float, aug: Optional[dict] = None, all_reduce=None, use_graph: bool = True):
+        """One Trainer.training_step + optimizer step.  `all_reduce(flat_grad)` is the data-parallel hook.
+
+        use_graph: the ~380 launches of pack + forward + backward are replayed as ONE CUDA graph when the step is called
+        again on the same input buffers (same addresses and shapes: a double-buffered loader, or device-resident data).
+        Launched one by one the kernels leave ~1.3 ms of gaps in a 31 ms step.  The first call on a buffer pair runs
+        eagerly (it also warms the workspace up), the second one captures, later ones replay; anything else -- new
+        addresses every step, a workspace that grew, reloaded weights -- simply keeps running eagerly.  The gradient
+        all-reduce and the three optimizer launches stay outside the graph (learning rate and step count are host values).
+        The returned loss is the graph's own output tensor: read it before the next step overwrites it."""
+        loss = None
+        if (use_graph and not getattr(self, "_graphs_off", False) and ops._prof is None and x.is_cuda and x.is_contiguous()
+                and labels.is_cuda and labels.is_contiguous() and labels.dtype == torch.long):
+            loss = self._fwd_bwd_graph(x, labels, aug)
+        if loss is None:
+            self.pack_trainable()
+            loss, _, _ = self.forward_loss(x, labels, aug=aug, save=True, ce_grad_scale=1.0)
+            self.backward()
         if all_reduce is not None:
             all_reduce(self.grad)
         self.optimizer_step(lr)
+        return loss
+
+    def _fwd_bwd_graph(self, x, labels, aug):
+        """Replay (or capture) the graph of pack_trainable + forward_loss + backward for these buffers; None = run eagerly."""
+        from . import _abi
+        akey = tuple(sorted((k, v.data_ptr() if torch.is_tensor(v) else v) for k, v in (aug or {}).items()))
+        key = (x.data_ptr(), tuple(x.shape), x.dtype, labels.data_ptr(), tuple(labels.shape), akey)
+        stamp = (self.ws.gen, self._weights_version)
+        graphs = self.__dict__.setdefault("_train_graphs", {})
+        ent = graphs.get(key)
+        if ent is not None and ent[0] is not None and ent[3] == stamp:
+            ent[0].replay()
+            self.graph_launches += ent[2]
+            self._packed = False
+            return ent[1]
+        if ent is None or ent[3] != stamp:
+            if len(graphs) >= 4:                      # a loader that never reuses a buffer must not pile graphs up
+                graphs.pop(next(iter(graphs)))
+            graphs[key] = (None, None, 0, stamp)     # seen once: eager now, capture if it comes back unchanged
+            return None
+        self._packed = False
+        torch.cuda.synchronize()
+        before = sum(_abi.counters().values())
+        g = torch.cuda.CUDAGraph()
+        try:
+            with torch.cuda.graph(g):
+                self.pack_trainable()
+                loss, _, _ = self.forward_loss(x, labels, aug=aug, save=True, ce_grad_scale=1.0)
+                self.backward()
+        except Exception as e:                          # something on this path is not capturable: stay eager from now on
+            import warnings
+            warnings.warn(f"neuspeech1_b200: CUDA-graph capture of the training step failed ({e}); running eagerly")
+            self._graphs_off = True
+            graphs.pop(key, None)
+            torch.cuda.synchronize()
+            self._packed = False
+            return None
+        n = sum(_abi.counters().values()) - before
+        if (self.ws.gen, self._weights_version) != stamp:   # the capture itself allocated: do not trust it
+            graphs.pop(key, None)
+            return None
+        graphs[key] = (g, loss, n, stamp)
+        g.replay()
+        self.graph_launches += n
+        self._packed = False
         return loss
 
     # ------------------------------------------------------------------ greedy decode with KV cache

@@ -302,10 +302,11 @@ class WhisperEEGForConditionalGeneration(nn.Module):
                 loss = loss.clone() if loss is not None else None
         return Seq2SeqLMOutput(loss=loss, logits=logits, encoder_last_hidden_state=enc)
 
-    def training_step(self, input_features, labels, lr: float, all_reduce=None, aug: Optional[dict] = None):
-        """Fused Trainer.training_step + clip + AdamW (HF trainer.py:1867-1934, finetune.py:231-253) without autograd."""
+    def training_step(self, input_features, labels, lr: float, all_reduce=None, aug: Optional[dict] = None, use_graph: bool = True):
+        """Fused Trainer.training_step + clip + AdamW (HF trainer.py:1867-1934, finetune.py:231-253) without autograd.
+        use_graph: see WhisperEEGEngine.train_step (CUDA-graph replay when the same input buffers come back)."""
         eng = self._engine()
-        loss = eng.train_step(input_features, labels, lr=lr, aug=aug, all_reduce=all_reduce)
+        loss = eng.train_step(input_features, labels, lr=lr, aug=aug, all_reduce=all_reduce, use_graph=use_graph)
         return Seq2SeqLMOutput(loss=loss)
 
     @torch.no_grad()

@@ -163,6 +163,32 @@ def test_greedy_cuda_graph_replay_matches_eager():
         assert torch.equal(eng.greedy(x.to(DEV), max_length=14, prompt=prompt, use_graphs=True), refp)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_train_step_graph_replay_matches_eager(dtype):
+    """train_step replays pack + forward + backward as one CUDA graph once the same input buffers come back (first call eager,
+    second captures, later ones replay).  Same losses and the same weights as the launch-by-launch path (up to the order of the
+    fp32 reductions in the split-K weight gradients); new buffers or a different batch fall back to eager launches."""
+    dims = O.Dims(d_model=256, enc_layers=2, dec_layers=2, enc_heads=4, dec_heads=4, enc_ffn=512, dec_ffn=512, vocab=2000,
+                  max_source_positions=160, max_target_positions=32, eeg_ch=24, pad_token_id=1997, eos_token_id=1997,
+                  decoder_start_token_id=1998, begin_suppress_tokens=(220, 1996), lora_r=32, lora_alpha=64)
+    P = O.init_params(dims, seed=0)
+    lora = O.init_lora(dims, seed=1, b_std=0.05)
+    x, labels = O.synthetic_batch(dims, B=3, L=8, seed=1)
+    x2, labels2 = O.synthetic_batch(dims, B=3, L=8, seed=2)
+    xd, ld, xd2, ld2 = x.to(DEV), labels.to(DEV), x2.to(DEV), labels2.to(DEV)
+    e_graph = WhisperEEGEngine(ModelDims.from_any(dims), P, lora, dtype=dtype, device=DEV)
+    e_eager = WhisperEEGEngine(ModelDims.from_any(dims), P, lora, dtype=dtype, device=DEV)
+    tol_l = 2e-3 if dtype == torch.bfloat16 else 1e-5
+    seq = [(xd, ld)] * 4 + [(xd2, ld2)] + [(xd, ld)] * 2
+    for i, (a, b) in enumerate(seq):
+        lg = float(e_graph.train_step(a, b, lr=1e-3 * (1 + i)))           # the learning rate changes every step
+        le = float(e_eager.train_step(a, b, lr=1e-3 * (1 + i), use_graph=False))
+        assert abs(lg - le) <= tol_l * abs(le), (i, lg, le)
+    assert e_graph.graph_launches > 0 and e_eager.graph_launches == 0
+    assert rel(e_graph.flat, e_eager.flat) < (2e-3 if dtype == torch.bfloat16 else 1e-5)
+    assert e_graph.opt_step == e_eager.opt_step == len(seq)
+
+
 # BASELINE.json configs[2] / configs[4] shapes at reduced depth / sequence: the Schoffelen channel count (273 -> padded to 288
 # channels-last, K = 3*288 for stem conv A) and the large-v3 widths (d = 1280 = 5 x 256 column tiles, 20 heads of 64, F = 5120).
 WIDE = O.Dims(d_model=1280, enc_layers=1, dec_layers=1, enc_heads=20, dec_heads=20, enc_ffn=5120, dec_ffn=5120, vocab=3000,
