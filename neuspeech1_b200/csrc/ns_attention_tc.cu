@@ -237,6 +237,225 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
 
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Forward with a DOUBLE-BUFFERED score tile (the default).  Same CTA shape as attn_fwd_tc_kernel (one 128-query tile, two CTAs
+// per SM, 256 TMEM columns) but the key axis advances in HALF tiles of 64 keys:
+//   TMEM columns: [0,64) S buffer 0, [64,128) S buffer 1, [128,192) O.  bf16 P overwrites the first 32 columns of its own S
+//   buffer (every score of the half tile is in registers by then).
+//   The MMA thread keeps S two half tiles ahead: S(0) S(1) | PV(0) S(2) | PV(1) S(3) | ...  so the softmax warps find their
+//   next scores ready when they finish a half tile -- in the single-buffer kernel they sat out PV(j) + S(j+1) + two barrier
+//   round trips per tile and the MUFU pipe was busy 52 % of the time.
+//   Softmax per half tile: both 32-column TMEM loads behind one wait, exact row max, then the exponentials (packed FFMA2 for the
+//   argument, FADD2 for the row sum).  The running max moves only when a row's new max exceeds it by > 8 (log2 units, P stays
+//   below 2^8); O is then rescaled after PV(h-1) has finished (pv_done), before P(h) is published.
+constexpr int kDbThreads = 192;
+__global__ void __launch_bounds__(kDbThreads, 2)
+attn_fwd_db_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnFwdProg p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = smem_base;
+  auto sK = [&](int s) { return smem_base + kTile * (1 + s); };
+  auto sV = [&](int s) { return smem_base + kTile * (3 + s); };
+  const uint32_t bar = smem_base + kTile * 5;
+  const uint32_t q_full = bar;
+  auto k_full = [&](int s) { return bar + 8u * (1 + s); };
+  auto v_full = [&](int s) { return bar + 8u * (3 + s); };
+  auto k_empty = [&](int s) { return bar + 8u * (5 + s); };
+  auto v_empty = [&](int s) { return bar + 8u * (7 + s); };
+  auto s_full = [&](int b_) { return bar + 8u * (9 + b_); };
+  auto p_full = [&](int b_) { return bar + 8u * (11 + b_); };
+  auto pv_done = [&](int b_) { return bar + 8u * (13 + b_); };
+  const uint32_t o_full = bar + 8u * 15;
+  const uint32_t tmem_slot = bar + 8u * 16;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int n_kv = (p.Lk + 127) / 128;
+  const int nh = (p.Lk + 63) / 64;               // half tiles of 64 keys
+
+  if (warp == 0 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(k_full(s), 1); mbar_init(v_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_empty(s), 1);
+      mbar_init(s_full(s), 1); mbar_init(p_full(s), 4); mbar_init(pv_done(s), 1);
+    }
+    mbar_init(o_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  auto tS = [&](int b_) { return tmem + 64u * static_cast<uint32_t>(b_); };
+  const uint32_t tO = tmem + 128;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(q_full, kTile);
+      tma_load_3d(&maps.q, q_full, sQ, h * 64, q0, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1u;
+        mbar_wait(k_empty(s), ph ^ 1u);
+        mbar_expect_tx(k_full(s), kTile);
+        tma_load_3d(&maps.k, k_full(s), sK(s), h * 64, j * 128, b);
+        mbar_wait(v_empty(s), ph ^ 1u);
+        mbar_expect_tx(v_full(s), kTile);
+        tma_load_3d(&maps.v, v_full(s), sV(s), h * 64, j * 128, b);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idescS = umma_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t idescO = umma_idesc_bf16(128, 64, 0, 1);          // B = V is MN-major (keys x head_dim rows)
+    mbar_wait(q_full, 0);
+    // S(hf) = Q K_half^T into score buffer hf & 1 (keys 64 * half .. of key tile hf >> 1: 64 rows of 128 B = +8 KB)
+    auto issue_qk = [&](int hf) {
+      const int j = hf >> 1, s = j & 1, half = hf & 1;
+      if (half == 0) {
+        mbar_wait(k_full(s), (j >> 1) & 1u);
+        tc_fence_after();
+      }
+      if (elect_one()) {
+        const uint64_t qd = umma_smem_desc(sQ, 16, 1024), kd = umma_smem_desc(sK(s) + 8192u * half, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tS(hf & 1), qd + 2u * k, kd + 2u * k, idescS, k > 0);
+        if (half == 1 || hf == nh - 1) umma_commit(k_empty(s));
+        umma_commit(s_full(hf & 1));
+      }
+      __syncwarp();
+    };
+    issue_qk(0);
+    if (nh > 1) issue_qk(1);
+    for (int hf = 0; hf < nh; ++hf) {
+      const int j = hf >> 1, s = j & 1, half = hf & 1, buf = hf & 1;
+      mbar_wait(p_full(buf), (hf >> 1) & 1u);
+      tc_fence_after();
+      if (half == 0) {
+        mbar_wait(v_full(s), (j >> 1) & 1u);
+        tc_fence_after();
+      }
+      if (elect_one()) {
+        const uint64_t vd = umma_smem_desc(sV(s), 8192, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)       // 16 keys per MMA: 8 TMEM columns of bf16 pairs, 2 KB of V rows
+          umma_f16_ts(tO, tS(buf) + 8u * k, vd + 128u * (4 * half + k), idescO, (hf > 0 || k > 0) ? 1u : 0u);
+        if (half == 1 || hf == nh - 1) umma_commit(v_empty(s));
+        umma_commit(pv_done(buf));
+        if (hf == nh - 1) umma_commit(o_full);
+      }
+      __syncwarp();
+      if (hf + 2 < nh) issue_qk(hf + 2);    // in order behind PV(hf): it may overwrite the buffer PV(hf) reads P from
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    float m_used = -INFINITY, l = 0.f;
+    for (int hf = 0; hf < nh; ++hf) {
+      const int buf = hf & 1;
+      mbar_wait(s_full(buf), (hf >> 1) & 1u);
+      tc_fence_after();
+      const int nvalid = min(64, p.Lk - hf * 64);
+      uint32_t v[2][32];
+      tmem_ld32(tS(buf) + lane_addr, v[0]);
+      tmem_ld32(tS(buf) + lane_addr + 32u, v[1]);
+      tmem_ld_wait();
+      if (nvalid < 64) {                              // keys past Lk: exp2(-inf) = 0 and they never win the max
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= nvalid) v[c][i] = 0xff800000u;
+      }
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};     // four chains instead of one 32-deep one
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 2)
+          mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])));
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      if (hf == 0) {
+        m_used = mx;
+      } else if (__any_sync(0xffffffffu, mx > m_used + 5.545177f)) {     // 8 / log2(e)
+        const float m_new = fmaxf(m_used, mx);
+        const float sc = fast_exp2((m_used - m_new) * kLog2e);
+        mbar_wait(pv_done((hf - 1) & 1), ((hf - 1) >> 1) & 1u);          // nobody accumulates into O right now
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tO + lane_addr + 32u * c, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * sc);
+          tmem_st32(tO + lane_addr + 32u * c, o);
+        }
+        l *= sc;
+        m_used = m_new;
+      }
+      // (fetching the next half tile's scores here, behind the exponentials, was tried: 574 us vs 444 us -- 168 registers
+      // with spills under the two-CTAs-per-SM cap)
+      const uint64_t nmb = f2_splat(-m_used * kLog2e), l2e = f2_splat(kLog2e);
+      uint64_t acc0 = f2_splat(0.f), acc1 = f2_splat(0.f);
+      uint32_t pk[32];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float x0, x1;
+          f2_unpack(f2_fma(f2_pack(__uint_as_float(v[c][2 * i]), __uint_as_float(v[c][2 * i + 1])), l2e, nmb), x0, x1);
+          const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+          if (i & 1) acc1 = f2_add(acc1, f2_pack(p0, p1)); else acc0 = f2_add(acc0, f2_pack(p0, p1));
+          pk[16 * c + i] = pack_bf16x2(p0, p1);
+        }
+      }
+      tmem_st32(tS(buf) + lane_addr, pk);             // P over the first 32 columns of its own score buffer
+      float a0, a1, a2, a3;
+      f2_unpack(acc0, a0, a1); f2_unpack(acc1, a2, a3);
+      l += (a0 + a1) + (a2 + a3);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full(buf));
+    }
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const int qi = q0 + row;
+    const float inv = 1.0f / l;
+    __nv_bfloat16* orow = p.o + b * p.o_bs + static_cast<long long>(qi) * p.o_rs + h * 64;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tO + lane_addr + 32u * c, v);
+      tmem_ld_wait();
+      if (qi < p.Lq) {
+        uint4* dst = reinterpret_cast<uint4*>(orow + 32 * c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
+          dst[i] = u;
+        }
+      }
+    }
+    if (p.lse && qi < p.Lq) p.lse[(static_cast<long long>(b) * p.H + h) * p.Lq + qi] = m_used + logf(l);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Forward, ping-pong variant for long query axes (the encoder: Lq = 1500).  One CTA per SM owns TWO 128-query tiles of one
 // (batch, head) and streams the key/value tiles once for both:
 //   warp 0        TMA producer : Q0, Q1 once; K / V tiles of 128 keys through 3-stage rings
@@ -547,7 +766,17 @@ int attention_fwd_tc(const ns_attn_shape& s, const void* q, const void* k, const
     return NS_OK;
   }
   dim3 grid((s.Lq + 127) / 128, s.H, s.B);
-  attn_fwd_tc_kernel<<<grid, kAtThreads, kAtSmem, st>>>(maps, prog);
+  static const bool single_buffer = getenv("NS_ATTN_FWD_SINGLE") != nullptr;     // the first kernel, kept for A/B runs
+  if (single_buffer) {
+    attn_fwd_tc_kernel<<<grid, kAtThreads, kAtSmem, st>>>(maps, prog);
+  } else {
+    static bool attr3_done = false;
+    if (!attr3_done) {
+      NS_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+      attr3_done = true;
+    }
+    attn_fwd_db_kernel<<<grid, kDbThreads, kAtSmem, st>>>(maps, prog);
+  }
   NS_LAUNCH_CHECK();
   count(C_ATTN_TC);
   return NS_OK;

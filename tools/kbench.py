@@ -228,6 +228,12 @@ def main():
     print(s)
     for fam, d in out.items():   # compact one-line-per-kernel summary (what gets read back from a gpurun tail)
         for k, v in d.items():
+            if not isinstance(v, dict):
+                if k.endswith("_ms"):
+                    print(f"## {fam:6s} {k[:-3]:28s} {v * 1e3:8.1f} us {d.get(k[:-3] + '_tflops', 0):7.0f} TF/s")
+                else:
+                    if not k.endswith("_tflops"): print(f"## {fam:6s} {k:28s} {v:.3e}")
+                continue
             print(f"## {fam:6s} {k:28s} {v['ms'] * 1e3:8.1f} us" + (f" {v['tflops']:7.0f} TF/s" if "tflops" in v else "")
                   + (f" {v['gbs']:7.0f} GB/s" if "gbs" in v else ""))
     if a.out:
