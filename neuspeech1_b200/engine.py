@@ -17,6 +17,7 @@ Data layout in HBM (row-major, activations in `dtype` = bf16 or fp32, statistics
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -25,6 +26,7 @@ import torch
 from . import ops
 from ._abi import ACT_DGELU, ACT_GELU, ACT_NONE, NS_BF16, NS_F32
 
+_NO_TRAIN_GRAPH = bool(os.environ.get("NS_NO_TRAIN_GRAPH"))     # developer switch: launch every kernel of train_step one by one
 ENC_LORA_TARGETS = ("q_proj", "k_proj", "v_proj", "out_proj", "fc1", "fc2")
 
 
@@ -680,7 +682,7 @@ class WhisperEEGEngine:
         all-reduce and the three optimizer launches stay outside the graph (learning rate and step count are host values).
         The returned loss is the graph's own output tensor: read it before the next step overwrites it."""
         loss = None
-        if (use_graph and not getattr(self, "_graphs_off", False) and ops._prof is None and x.is_cuda and x.is_contiguous()
+        if (use_graph and not getattr(self, "_graphs_off", False) and not _NO_TRAIN_GRAPH and ops._prof is None and x.is_cuda and x.is_contiguous()
                 and labels.is_cuda and labels.is_contiguous() and labels.dtype == torch.long):
             loss = self._fwd_bwd_graph(x, labels, aug)
         if loss is None:
