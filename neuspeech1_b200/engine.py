@@ -679,8 +679,7 @@ class WhisperEEGEngine:
         Launched one by one the kernels leave ~1.3 ms of gaps in a 31 ms step.  The first call on a buffer pair runs
         eagerly (it also warms the workspace up), the second one captures, later ones replay; anything else -- new
         addresses every step, a workspace that grew, reloaded weights -- simply keeps running eagerly.  The gradient
-        all-reduce and the three optimizer launches stay outside the graph (learning rate and step count are host values).
-        The returned loss is the graph's own output tensor: read it before the next step overwrites it."""
+        all-reduce and the three optimizer launches stay outside the graph (learning rate and step count are host values)."""
         loss = None
         if (use_graph and not getattr(self, "_graphs_off", False) and not _NO_TRAIN_GRAPH and ops._prof is None and x.is_cuda and x.is_contiguous()
                 and labels.is_cuda and labels.is_contiguous() and labels.dtype == torch.long):
@@ -706,7 +705,7 @@ class WhisperEEGEngine:
             ent[0].replay()
             self.graph_launches += ent[2]
             self._packed = False
-            return ent[1]
+            return ent[1].clone()                     # the graph's own output buffer is overwritten by the next replay
         if ent is None or ent[3] != stamp:
             if len(graphs) >= 4:                      # a loader that never reuses a buffer must not pile graphs up
                 graphs.pop(next(iter(graphs)))
@@ -717,7 +716,7 @@ class WhisperEEGEngine:
         before = sum(_abi.counters().values())
         g = torch.cuda.CUDAGraph()
         try:
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):   # loader threads may pin memory meanwhile
                 self.pack_trainable()
                 loss, _, _ = self.forward_loss(x, labels, aug=aug, save=True, ce_grad_scale=1.0)
                 self.backward()
@@ -737,7 +736,7 @@ class WhisperEEGEngine:
         g.replay()
         self.graph_launches += n
         self._packed = False
-        return loss
+        return loss.clone()
 
     # ------------------------------------------------------------------ greedy decode with KV cache
     @torch.no_grad()
