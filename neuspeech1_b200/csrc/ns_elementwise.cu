@@ -5,36 +5,50 @@
 namespace ns {
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
-// One warp per row.  NV = number of 8-element vectors per lane (bf16, d = 256*NV) for the register-resident fast path.
+// One warp per PAIR of rows (both rows' 16-byte loads are in flight together: with one row per warp the kernel ran at
+// 4.5 TB/s, latency-bound).  NV = number of 8-element vectors per lane (bf16, d = 256*NV), register-resident.
 template <int NV>
 __global__ void __launch_bounds__(256) ln_fwd_bf16_kernel(long long rows, const __nv_bfloat16* __restrict__ x,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
                                                           float* __restrict__ rstd_out, float eps) {
   constexpr int d = NV * 256;
-  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const long long row0 = (static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5)) * 2;
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const uint4* xr = reinterpret_cast<const uint4*>(x + row * d);
-  float v[NV * 8];
-  float s = 0.f;
+  if (row0 >= rows) return;
+  const bool two = row0 + 1 < rows;
+  uint4 u[2][NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const uint4 u = __ldg(xr + i * 32 + lane);
-    float2 f;
-    f = unpack_bf16x2(u.x); v[8 * i + 0] = f.x; v[8 * i + 1] = f.y;
-    f = unpack_bf16x2(u.y); v[8 * i + 2] = f.x; v[8 * i + 3] = f.y;
-    f = unpack_bf16x2(u.z); v[8 * i + 4] = f.x; v[8 * i + 5] = f.y;
-    f = unpack_bf16x2(u.w); v[8 * i + 6] = f.x; v[8 * i + 7] = f.y;
+  for (int r = 0; r < 2; ++r) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (row0 + ((r == 1 && two) ? 1 : 0)) * d);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s += v[8 * i + j];
+    for (int i = 0; i < NV; ++i) u[r][i] = __ldg(xr + i * 32 + lane);
   }
-  const float mean = warp_sum(s) * (1.0f / d);
-  float q = 0.f;
+  float v[2][NV * 8], s[2] = {0.f, 0.f};
 #pragma unroll
-  for (int i = 0; i < NV * 8; ++i) { const float c = v[i] - mean; q = fmaf(c, c, q); }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / d) + eps);
-  uint4* yr = reinterpret_cast<uint4*>(y + row * d);
+  for (int r = 0; r < 2; ++r) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float2 f;
+      f = unpack_bf16x2(u[r][i].x); v[r][8 * i + 0] = f.x; v[r][8 * i + 1] = f.y;
+      f = unpack_bf16x2(u[r][i].y); v[r][8 * i + 2] = f.x; v[r][8 * i + 3] = f.y;
+      f = unpack_bf16x2(u[r][i].z); v[r][8 * i + 4] = f.x; v[r][8 * i + 5] = f.y;
+      f = unpack_bf16x2(u[r][i].w); v[r][8 * i + 6] = f.x; v[r][8 * i + 7] = f.y;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[r] += v[r][8 * i + j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s[0] += __shfl_xor_sync(0xffffffffu, s[0], o); s[1] += __shfl_xor_sync(0xffffffffu, s[1], o); }
+  const float mean[2] = {s[0] * (1.0f / d), s[1] * (1.0f / d)};
+  float q[2] = {0.f, 0.f};
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int i = 0; i < NV * 8; ++i) { const float c = v[r][i] - mean[r]; q[r] = fmaf(c, c, q[r]); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { q[0] += __shfl_xor_sync(0xffffffffu, q[0], o); q[1] += __shfl_xor_sync(0xffffffffu, q[1], o); }
+  const float rstd[2] = {rsqrtf(q[0] * (1.0f / d) + eps), rsqrtf(q[1] * (1.0f / d) + eps)};
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c0 = (i * 32 + lane) * 8;
@@ -42,18 +56,22 @@ __global__ void __launch_bounds__(256) ln_fwd_bf16_kernel(long long rows, const 
     const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0));
     const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
-    float o[8];
-    o[0] = (v[8 * i + 0] - mean) * rstd * g0.x + b0.x; o[1] = (v[8 * i + 1] - mean) * rstd * g0.y + b0.y;
-    o[2] = (v[8 * i + 2] - mean) * rstd * g0.z + b0.z; o[3] = (v[8 * i + 3] - mean) * rstd * g0.w + b0.w;
-    o[4] = (v[8 * i + 4] - mean) * rstd * g1.x + b1.x; o[5] = (v[8 * i + 5] - mean) * rstd * g1.y + b1.y;
-    o[6] = (v[8 * i + 6] - mean) * rstd * g1.z + b1.z; o[7] = (v[8 * i + 7] - mean) * rstd * g1.w + b1.w;
-    uint4 u;
-    u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]); u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
-    yr[i * 32 + lane] = u;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      if (r == 1 && !two) break;
+      float o[8];
+      o[0] = (v[r][8 * i + 0] - mean[r]) * rstd[r] * g0.x + b0.x; o[1] = (v[r][8 * i + 1] - mean[r]) * rstd[r] * g0.y + b0.y;
+      o[2] = (v[r][8 * i + 2] - mean[r]) * rstd[r] * g0.z + b0.z; o[3] = (v[r][8 * i + 3] - mean[r]) * rstd[r] * g0.w + b0.w;
+      o[4] = (v[r][8 * i + 4] - mean[r]) * rstd[r] * g1.x + b1.x; o[5] = (v[r][8 * i + 5] - mean[r]) * rstd[r] * g1.y + b1.y;
+      o[6] = (v[r][8 * i + 6] - mean[r]) * rstd[r] * g1.z + b1.z; o[7] = (v[r][8 * i + 7] - mean[r]) * rstd[r] * g1.w + b1.w;
+      uint4 w;
+      w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]); w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+      reinterpret_cast<uint4*>(y + (row0 + r) * d)[i * 32 + lane] = w;
+    }
   }
   if (lane == 0) {
-    if (mean_out) mean_out[row] = mean;
-    if (rstd_out) rstd_out[row] = rstd;
+    if (mean_out) { mean_out[row0] = mean[0]; if (two) mean_out[row0 + 1] = mean[1]; }
+    if (rstd_out) { rstd_out[row0] = rstd[0]; if (two) rstd_out[row0 + 1] = rstd[1]; }
   }
 }
 
@@ -691,6 +709,7 @@ int ns_layernorm_fwd(int dtype, long long rows, int d, const void* x, const floa
   if (dtype == NS_BF16 && al && d % 256 == 0 && d <= 1280) {
     const bf16* xi = reinterpret_cast<const bf16*>(x);
     bf16* yo = reinterpret_cast<bf16*>(y);
+    const unsigned grid = static_cast<unsigned>((rows + 15) / 16);    // 8 warps x 2 rows per block
     switch (d / 256) {
       case 1: ln_fwd_bf16_kernel<1><<<grid, 256, 0, st>>>(rows, xi, gamma, beta, yo, mean, rstd, eps); break;
       case 2: ln_fwd_bf16_kernel<2><<<grid, 256, 0, st>>>(rows, xi, gamma, beta, yo, mean, rstd, eps); break;
