@@ -79,6 +79,10 @@ def lora_inject(model: nn.Module, r: int = 32, lora_alpha: int = 64, lora_dropou
                 target_modules: Optional[Iterable[str]] = None, modules_to_save: Optional[Iterable[str]] = None,
                 state: Optional[Dict[str, torch.Tensor]] = None):
     """In-place equivalent of get_peft_model for the reference's configuration (finetune.py:194-212)."""
+    if lora_dropout > 0:
+        import warnings
+        warnings.warn(f"neuspeech1_b200: lora_dropout={lora_dropout} is recorded but NOT applied by the B200 engine yet "
+                      "(the LoRA branch sees the undropped input; DESIGN.md section 6). Training proceeds without it.")
     if target_modules is None:
         target_modules = match_modules_string(model.named_modules(), ["model.encoder"], list(ENC_TARGETS))
     for name in list(target_modules):
