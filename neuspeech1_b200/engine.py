@@ -738,6 +738,97 @@ class WhisperEEGEngine:
         self._packed = False
         return loss.clone()
 
+    # ------------------------------------------------------------------ one decoder pass with KV cache
+    def _decode_logits(self, ids: torch.Tensor, pos: int, cache, kv_all: torch.Tensor, logits: torch.Tensor, Tmax: int):
+        """Decoder pass over `ids` (B, Lq) at cache position `pos` (utils/load_model.py:624,704,740-741, HF
+        modeling_whisper.py:314-336): self-attention K/V appended to `cache[i]` (B, Tmax, 3d), cross-attention over the
+        precomputed `kv_all` (B*S, N_dec*2d); logits of the LAST position -> `logits` (B, Vp)."""
+        dm, W, ws, dt = self.dims, self.P, self.ws, self.dtype
+        d, S, F, H = dm.d_model, dm.max_source_positions, dm.dec_ffn, dm.dec_heads
+        Dh = d // H
+        nkv = dm.dec_layers * 2 * d
+        B, Lq = ids.shape
+        MLq = B * Lq
+        tag = f"{B}.{Lq}"
+        hd = ws.get(f"g_h0.{tag}", (MLq, d), dt)
+        ops.embed(ids, W["dec.E"], W["dec.pos"], pos, hd)
+        for i in range(dm.dec_layers):
+            k = f"dec{i}"
+            u = ws.get(f"g_u.{tag}", (MLq, d), dt)
+            ops.layernorm_fwd(hd, W[k + ".ln1.g"], W[k + ".ln1.b"], u)
+            qkv_new = cache[i][:, pos:pos + Lq]                     # rows (b, pos..pos+Lq) of the cache, written in place
+            if Lq == 1:
+                ops.gemm_nt(u, W[k + ".wqkv"], qkv_new.view(B, 3 * d) if Tmax == 1 else qkv_new.squeeze(1),
+                            self._ep(bias=W[k + ".bqkv"], alpha=Dh ** -0.5, alpha_cols=d))
+            else:
+                tmp = ws.get(f"g_qkvtmp.{tag}", (MLq, 3 * d), dt)
+                ops.gemm_nt(u, W[k + ".wqkv"], tmp, self._ep(bias=W[k + ".bqkv"], alpha=Dh ** -0.5, alpha_cols=d))
+                qkv_new.copy_(tmp.view(B, Lq, 3 * d))
+            Lk = pos + Lq
+            shp_s = ops.attn_shape(B, H, Lq, Lk, Dh, True, Tmax * 3 * d, 3 * d, Tmax * 3 * d, 3 * d, Tmax * 3 * d, 3 * d, Lq * d, d)
+            o = ws.get(f"g_o.{tag}", (MLq, d), dt)
+            c = cache[i]
+            ops.attention_fwd(shp_s, c[:, pos:], c[:, :, d:], c[:, :, 2 * d:], o)
+            h1 = ws.get(f"g_h1.{tag}", (MLq, d), dt)
+            ops.gemm_nt(o, W[k + ".wo"], h1, self._ep(bias=W[k + ".bo"], residual=hd, ldr=d))
+            ops.layernorm_fwd(h1, W[k + ".ln2.g"], W[k + ".ln2.b"], u)
+            qc = ws.get(f"g_qc.{tag}", (MLq, d), dt)
+            ops.gemm_nt(u, W[k + ".wqc"], qc, self._ep(bias=W[k + ".bqc"], alpha=Dh ** -0.5, alpha_cols=d))
+            shp_c = ops.attn_shape(B, H, Lq, S, Dh, False, Lq * d, d, S * nkv, nkv, S * nkv, nkv, Lq * d, d)
+            ops.attention_fwd(shp_c, qc, kv_all[:, i * 2 * d:], kv_all[:, i * 2 * d + d:], o)
+            h2 = ws.get(f"g_h2.{tag}", (MLq, d), dt)
+            ops.gemm_nt(o, W[k + ".woc"], h2, self._ep(bias=W[k + ".boc"], residual=h1, ldr=d))
+            ops.layernorm_fwd(h2, W[k + ".ln3.g"], W[k + ".ln3.b"], u)
+            mm = ws.get(f"g_m.{tag}", (MLq, F), dt)
+            ops.gemm_nt(u, W[k + ".w1"], mm, self._ep(bias=W[k + ".b1"], act=ACT_GELU))
+            hd2 = ws.get(f"g_h3.{tag}.{i % 2}", (MLq, d), dt)
+            ops.gemm_nt(mm, W[k + ".w2"], hd2, self._ep(bias=W[k + ".b2"], residual=h2, ldr=d))
+            hd = hd2
+        y = ws.get(f"g_y.{tag}", (MLq, d), dt)
+        ops.layernorm_fwd(hd, W["dec.lnf.g"], W["dec.lnf.b"], y)
+        y_last = y.view(B, Lq, d)[:, Lq - 1]                          # (B, d) view, row stride Lq*d
+        ops.gemm_nt(y_last, W["dec.E"], logits, self._ep(out_dtype=ops.ns_dtype(logits)), N=dm.vocab, M=B, K=d)
+
+    # ------------------------------------------------------------------ beam search (evaluation.py:370-385)
+    @torch.no_grad()
+    def beam_search(self, x: torch.Tensor, max_length: int, num_beams: int = 5, repetition_penalty: float = 1.0,
+                    no_repeat_ngram_size: int = 0, prompt: Optional[torch.Tensor] = None, aug: Optional[dict] = None,
+                    length_penalty: float = 1.0) -> torch.Tensor:
+        """`generate(num_beams=K, repetition_penalty, no_repeat_ngram_size)`: the beams ride in the batch dimension of the
+        decoder pass (rows b*K + k; cross-attention K/V of a sample repeated for its beams, self-attention cache gathered
+        after every step like `_reorder_cache`, utils/load_model.py:1353-1360); the scoring loop is
+        neuspeech1_b200/generation.py.  Returns the generated suffix (B, <= max_length - prompt_len), pad after EOS."""
+        from .generation import beam_search as run_beams
+        dm, W, ws, dt = self.dims, self.P, self.ws, self.dtype
+        d, S = dm.d_model, dm.max_source_positions
+        B, K = x.shape[0], num_beams
+        if max_length > dm.max_target_positions:
+            raise ValueError(f"max_length {max_length} exceeds max_target_positions {dm.max_target_positions}")
+        enc = self.encode(x, aug=aug, save=False)
+        nkv = dm.dec_layers * 2 * d
+        kv_all = ws.get("kv_all", (B * S, nkv), dt)
+        ops.gemm_nt(enc.view(B * S, d), W["dec.wkv"], kv_all, self._ep(bias=W["dec.bkv"]))
+        kv_beams = ws.get(f"bs_kv.{K}", (B * K * S, nkv), dt)
+        kv_beams.view(B, K, S, nkv).copy_(kv_all.view(B, 1, S, nkv).expand(B, K, S, nkv))
+        if prompt is None:
+            prompt = torch.full((B, 1), dm.decoder_start_token_id, dtype=torch.long, device=self.device)
+        prompt = prompt.to(self.device, torch.long).contiguous()
+        L0 = prompt.shape[1]
+        cache = [ws.get(f"bs_qkv.{K}.{i}", (B * K, max_length, 3 * d), dt) for i in range(dm.dec_layers)]
+        logits = ws.get(f"bs_logits.{K}", (B * K, dm.Vp), torch.float32 if dt == torch.float32 else dt)
+
+        def step_fn(tokens: torch.Tensor, pos: int) -> torch.Tensor:
+            self._decode_logits(tokens.contiguous(), pos, cache, kv_beams, logits, max_length)
+            return logits
+
+        def reorder_fn(beam_idx: torch.Tensor):
+            for c in cache:
+                c.copy_(c.index_select(0, beam_idx))
+
+        out = run_beams(step_fn, reorder_fn, prompt, K, max_length, dm.vocab, dm.eos_token_id, dm.pad_token_id,
+                        dm.begin_suppress_tokens, repetition_penalty, no_repeat_ngram_size, length_penalty)
+        return out[:, L0:].contiguous()
+
     # ------------------------------------------------------------------ greedy decode with KV cache
     @torch.no_grad()
     def greedy(self, x: torch.Tensor, max_length: int, prompt: Optional[torch.Tensor] = None, aug: Optional[dict] = None,
@@ -773,46 +864,7 @@ class WhisperEEGEngine:
 
         def decode_step(step: int, ids: torch.Tensor, pos: int):
             """One decoder pass over `ids` (B, Lq) at cache position `pos` -> next token in `nxt`, appended to out[:, step]."""
-            Lq = ids.shape[1]
-            MLq = B * Lq
-            hd = ws.get(f"g_h0.{Lq}", (MLq, d), dt)
-            ops.embed(ids, W["dec.E"], W["dec.pos"], pos, hd)
-            for i in range(dm.dec_layers):
-                k = f"dec{i}"
-                u = ws.get(f"g_u.{Lq}", (MLq, d), dt)
-                ops.layernorm_fwd(hd, W[k + ".ln1.g"], W[k + ".ln1.b"], u)
-                qkv_new = cache[i][:, pos:pos + Lq]                     # rows (b, pos..pos+Lq) of the cache, written in place
-                if Lq == 1:
-                    ops.gemm_nt(u, W[k + ".wqkv"], qkv_new.view(B, 3 * d) if Tmax == 1 else qkv_new.squeeze(1),
-                                self._ep(bias=W[k + ".bqkv"], alpha=Dh ** -0.5, alpha_cols=d))
-                else:
-                    tmp = ws.get(f"g_qkvtmp.{Lq}", (MLq, 3 * d), dt)
-                    ops.gemm_nt(u, W[k + ".wqkv"], tmp, self._ep(bias=W[k + ".bqkv"], alpha=Dh ** -0.5, alpha_cols=d))
-                    qkv_new.copy_(tmp.view(B, Lq, 3 * d))
-                Lk = pos + Lq
-                shp_s = ops.attn_shape(B, H, Lq, Lk, Dh, True, Tmax * 3 * d, 3 * d, Tmax * 3 * d, 3 * d, Tmax * 3 * d, 3 * d, Lq * d, d)
-                o = ws.get(f"g_o.{Lq}", (MLq, d), dt)
-                c = cache[i]
-                ops.attention_fwd(shp_s, c[:, pos:], c[:, :, d:], c[:, :, 2 * d:], o)
-                h1 = ws.get(f"g_h1.{Lq}", (MLq, d), dt)
-                ops.gemm_nt(o, W[k + ".wo"], h1, self._ep(bias=W[k + ".bo"], residual=hd, ldr=d))
-                ops.layernorm_fwd(h1, W[k + ".ln2.g"], W[k + ".ln2.b"], u)
-                qc = ws.get(f"g_qc.{Lq}", (MLq, d), dt)
-                ops.gemm_nt(u, W[k + ".wqc"], qc, self._ep(bias=W[k + ".bqc"], alpha=Dh ** -0.5, alpha_cols=d))
-                shp_c = ops.attn_shape(B, H, Lq, S, Dh, False, Lq * d, d, S * nkv, nkv, S * nkv, nkv, Lq * d, d)
-                ops.attention_fwd(shp_c, qc, kv_all[:, i * 2 * d:], kv_all[:, i * 2 * d + d:], o)
-                h2 = ws.get(f"g_h2.{Lq}", (MLq, d), dt)
-                ops.gemm_nt(o, W[k + ".woc"], h2, self._ep(bias=W[k + ".boc"], residual=h1, ldr=d))
-                ops.layernorm_fwd(h2, W[k + ".ln3.g"], W[k + ".ln3.b"], u)
-                mm = ws.get(f"g_m.{Lq}", (MLq, F), dt)
-                ops.gemm_nt(u, W[k + ".w1"], mm, self._ep(bias=W[k + ".b1"], act=ACT_GELU))
-                hd2 = ws.get(f"g_h3.{Lq}.{i % 2}", (MLq, d), dt)
-                ops.gemm_nt(mm, W[k + ".w2"], hd2, self._ep(bias=W[k + ".b2"], residual=h2, ldr=d))
-                hd = hd2
-            y = ws.get(f"g_y.{Lq}", (MLq, d), dt)
-            ops.layernorm_fwd(hd, W["dec.lnf.g"], W["dec.lnf.b"], y)
-            y_last = y.view(B, Lq, d)[:, Lq - 1]                          # (B, d) view, row stride Lq*d
-            ops.gemm_nt(y_last, W["dec.E"], logits, self._ep(out_dtype=ops.ns_dtype(logits)), N=dm.vocab, M=B, K=d)
+            self._decode_logits(ids, pos, cache, kv_all, logits, Tmax)
             ops.greedy_pick(logits, dm.vocab, self.suppress if step == 0 else None, dm.eos_token_id, dm.pad_token_id, finished, nxt)
             out[:, step].copy_(nxt)
 

@@ -313,16 +313,24 @@ class WhisperEEGForConditionalGeneration(nn.Module):
     def generate(self, input_features=None, do_sample: bool = False, num_beams: int = 1, max_length: Optional[int] = None,
                  max_new_tokens: Optional[int] = None, decoder_input_ids=None, repetition_penalty: float = 1.0,
                  no_repeat_ngram_size: int = 0, **unused):
-        """Greedy decode with KV cache (utils/process_str.py:54-55).  evaluation.py's beam-5 + penalties configuration is a
-        'next' row and is refused loudly rather than approximated."""
-        if do_sample or num_beams != 1 or repetition_penalty != 1.0 or no_repeat_ngram_size:
-            raise NotImplementedError("neuspeech1_b200.generate implements greedy decoding (num_beams=1, no penalties)")
+        """`generate` as the reference calls it: greedy with KV cache (utils/process_str.py:54-55) and the beam search of
+        evaluation.py:370-385 (`num_beams=5, repetition_penalty=5.0, no_repeat_ngram_size=2`).  Sampling, beam groups and
+        sequence_bias are refused loudly rather than approximated.  Returns the generated suffix like HF's Whisper wrapper."""
+        if do_sample or unused.get("num_beam_groups", 1) != 1 or unused.get("sequence_bias") is not None:
+            raise NotImplementedError("neuspeech1_b200.generate implements greedy and plain beam search (no sampling, "
+                                      "beam groups or sequence_bias)")
         L0 = 1 if decoder_input_ids is None else decoder_input_ids.shape[1]
         if max_new_tokens is not None:
             max_length = L0 + max_new_tokens
         if max_length is None:
             max_length = self.dims.max_target_positions
-        return self._engine().greedy(input_features.to(self.device_), max_length=max_length, prompt=decoder_input_ids)
+        eng = self._engine()
+        x = input_features.to(self.device_)
+        if num_beams == 1 and repetition_penalty == 1.0 and not no_repeat_ngram_size:
+            return eng.greedy(x, max_length=max_length, prompt=decoder_input_ids)
+        return eng.beam_search(x, max_length=max_length, num_beams=num_beams, repetition_penalty=repetition_penalty,
+                               no_repeat_ngram_size=no_repeat_ngram_size, prompt=decoder_input_ids,
+                               length_penalty=float(unused.get("length_penalty", 1.0)))
 
     def prepare_inputs_for_generation(self, decoder_input_ids, past_key_values=None, use_cache=None, encoder_outputs=None, **kw):
         if past_key_values is not None:                      # utils/load_model.py:1332-1351: feed only the last token

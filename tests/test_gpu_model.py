@@ -163,6 +163,42 @@ def test_greedy_cuda_graph_replay_matches_eager():
         assert torch.equal(eng.greedy(x.to(DEV), max_length=14, prompt=prompt, use_graphs=True), refp)
 
 
+def test_beam_search_matches_oracle_loop_fp32():
+    """evaluation.py:370-385 (num_beams=5, repetition_penalty=5.0, no_repeat_ngram_size=2) on the B200 decoder step, fp32: the
+    same token ids as the same scoring loop over the oracle's decoder (that loop is pinned to stock transformers generate in
+    tests/test_generation_cpu.py), with and without a decoder prompt, beam widths 5 and 3."""
+    from neuspeech1_b200.generation import beam_search
+    dims = O.Dims(d_model=256, enc_layers=2, dec_layers=2, enc_heads=4, dec_heads=4, enc_ffn=512, dec_ffn=512, vocab=120,
+                  max_source_positions=160, max_target_positions=32, eeg_ch=24, pad_token_id=117, eos_token_id=117,
+                  decoder_start_token_id=118, begin_suppress_tokens=(20, 116), lora_r=32, lora_alpha=64)
+    P = O.init_params(dims, seed=0, std=0.12)
+    x, _ = O.synthetic_batch(dims, B=3, L=8, seed=1)
+    eng = WhisperEEGEngine(ModelDims.from_any(dims), P, None, dtype=torch.float32, device=DEV)
+    enc = O.encoder(x, P, dims, None)
+    for K, pen, ngram, L0 in ((5, 5.0, 2, 1), (3, 1.3, 3, 4)):
+        prompt = torch.full((3, 1), dims.decoder_start_token_id, dtype=torch.long)
+        if L0 > 1:
+            prompt = torch.cat([prompt, torch.tensor([[5, 7, 9], [1, 2, 3], [30, 31, 32]])], dim=1)
+        state = {}
+
+        def step_fn(tokens, pos):
+            if pos == 0:
+                state["enc"] = enc.repeat_interleave(K, 0); state["past"] = None
+            y, state["past"] = O.decoder(tokens, state["enc"], P, dims, state["past"])
+            return y[:, -1] @ P["model.decoder.embed_tokens.weight"].t()
+
+        def reorder_fn(idx):
+            state["past"] = [tuple(t.index_select(0, idx) for t in layer) if isinstance(layer, (tuple, list)) else layer.index_select(0, idx)
+                             for layer in state["past"]]
+
+        ref = beam_search(step_fn, reorder_fn, prompt, K, 20, dims.vocab, dims.eos_token_id, dims.pad_token_id,
+                          dims.begin_suppress_tokens, pen, ngram)[:, L0:]
+        got = eng.beam_search(x.to(DEV), max_length=20, num_beams=K, repetition_penalty=pen, no_repeat_ngram_size=ngram,
+                              prompt=prompt if L0 > 1 else None).cpu()
+        assert got.shape == ref.shape and torch.equal(got, ref), (K, L0, got, ref)
+        assert len({tuple(r.tolist()) for r in ref}) > 1
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 def test_train_step_graph_replay_matches_eager(dtype):
     """train_step replays pack + forward + backward as one CUDA graph once the same input buffers come back (first call eager,

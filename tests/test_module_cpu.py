@@ -95,4 +95,6 @@ def test_forward_argument_errors():
     with pytest.raises(ValueError):
         m.forward(input_features=torch.zeros(1, 16, 256))
     with pytest.raises(NotImplementedError):
-        m.generate(torch.zeros(1, 16, 256), num_beams=5)
+        m.generate(torch.zeros(1, 16, 256), do_sample=True)
+    with pytest.raises(NotImplementedError):
+        m.generate(torch.zeros(1, 16, 256), num_beams=4, num_beam_groups=2)
