@@ -13,6 +13,8 @@ from neuspeech1_b200.weights import random_params
 ap = argparse.ArgumentParser()
 ap.add_argument("--B", type=int, default=128); ap.add_argument("--eeg-ch", dest="eeg_ch", type=int, default=273)
 ap.add_argument("--max-length", dest="max_length", type=int, default=448); ap.add_argument("--batches", type=int, default=3)
+ap.add_argument("--beams", type=int, default=0, help="also time evaluation.py's beam search (num_beams, penalty 5.0, no-repeat 2) at --beam-B")
+ap.add_argument("--beam-B", dest="beam_B", type=int, default=32)
 a = ap.parse_args()
 dev = torch.device("cuda")
 dims = ModelDims(eeg_ch=a.eeg_ch)
@@ -35,6 +37,19 @@ for name, graphs in (("eager", False), ("cuda_graphs", True)):
                  "ms_per_token_step": p50 / out.shape[1], "new_tokens": int(out.shape[1])}
     res[name + "_ids_head"] = out[0, :8].tolist()
 res["graphs_match_eager"] = res["eager_ids_head"] == res["cuda_graphs_ids_head"]
+if a.beams > 1:
+    xb = x[:a.beam_B]
+    run = lambda: eng.beam_search(xb, max_length=a.max_length, num_beams=a.beams, repetition_penalty=5.0, no_repeat_ngram_size=2)
+    out = run(); torch.cuda.synchronize()
+    lat = []
+    for _ in range(a.batches):
+        s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+        s.record(); out = run(); e.record()
+        torch.cuda.synchronize(); lat.append(s.elapsed_time(e))
+    p50 = statistics.median(lat)
+    res[f"beam{a.beams}"] = {"B": a.beam_B, "p50_ms_per_batch": p50, "samples_per_s": a.beam_B * 1e3 / p50, "new_tokens": int(out.shape[1]),
+                             "ms_per_token_step": p50 / max(int(out.shape[1]), 1),
+                             "note": "beams in the batch dimension, scoring loop in torch ops, cache gathered by copy"}
 if os.environ.get("NS_DECODE_PROFILE"):
     from neuspeech1_b200 import ops
     ops.profile_begin()
