@@ -739,10 +739,14 @@ class WhisperEEGEngine:
         return loss.clone()
 
     # ------------------------------------------------------------------ one decoder pass with KV cache
-    def _decode_logits(self, ids: torch.Tensor, pos: int, cache, kv_all: torch.Tensor, logits: torch.Tensor, Tmax: int):
+    def _decode_logits(self, ids: torch.Tensor, pos: int, cache, kv_all: torch.Tensor, logits: torch.Tensor, Tmax: int,
+                       beams: int = 1):
         """Decoder pass over `ids` (B, Lq) at cache position `pos` (utils/load_model.py:624,704,740-741, HF
         modeling_whisper.py:314-336): self-attention K/V appended to `cache[i]` (B, Tmax, 3d), cross-attention over the
-        precomputed `kv_all` (B*S, N_dec*2d); logits of the LAST position -> `logits` (B, Vp)."""
+        precomputed `kv_all` ((B / beams)*S, N_dec*2d); logits of the LAST position -> `logits` (B, Vp).
+        beams > 1: rows b*beams + k are the beams of sample b.  They ride in the batch dimension of the self-attention and in
+        the QUERY dimension of the cross-attention (beams * Lq independent queries per sample), so a sample's encoder K/V are
+        read once per step for all its beams and never copied."""
         dm, W, ws, dt = self.dims, self.P, self.ws, self.dtype
         d, S, F, H = dm.d_model, dm.max_source_positions, dm.dec_ffn, dm.dec_heads
         Dh = d // H
@@ -774,7 +778,8 @@ class WhisperEEGEngine:
             ops.layernorm_fwd(h1, W[k + ".ln2.g"], W[k + ".ln2.b"], u)
             qc = ws.get(f"g_qc.{tag}", (MLq, d), dt)
             ops.gemm_nt(u, W[k + ".wqc"], qc, self._ep(bias=W[k + ".bqc"], alpha=Dh ** -0.5, alpha_cols=d))
-            shp_c = ops.attn_shape(B, H, Lq, S, Dh, False, Lq * d, d, S * nkv, nkv, S * nkv, nkv, Lq * d, d)
+            Lc = beams * Lq
+            shp_c = ops.attn_shape(B // beams, H, Lc, S, Dh, False, Lc * d, d, S * nkv, nkv, S * nkv, nkv, Lc * d, d)
             ops.attention_fwd(shp_c, qc, kv_all[:, i * 2 * d:], kv_all[:, i * 2 * d + d:], o)
             h2 = ws.get(f"g_h2.{tag}", (MLq, d), dt)
             ops.gemm_nt(o, W[k + ".woc"], h2, self._ep(bias=W[k + ".boc"], residual=h1, ldr=d))
@@ -795,8 +800,8 @@ class WhisperEEGEngine:
                     no_repeat_ngram_size: int = 0, prompt: Optional[torch.Tensor] = None, aug: Optional[dict] = None,
                     length_penalty: float = 1.0) -> torch.Tensor:
         """`generate(num_beams=K, repetition_penalty, no_repeat_ngram_size)`: the beams ride in the batch dimension of the
-        decoder pass (rows b*K + k; cross-attention K/V of a sample repeated for its beams, self-attention cache gathered
-        after every step like `_reorder_cache`, utils/load_model.py:1353-1360); the scoring loop is
+        decoder pass (rows b*K + k) and in the query dimension of its cross-attention; the self-attention cache is gathered
+        after every step like `_reorder_cache` (utils/load_model.py:1353-1360); the scoring loop is
         neuspeech1_b200/generation.py.  Returns the generated suffix (B, <= max_length - prompt_len), pad after EOS."""
         from .generation import beam_search as run_beams
         dm, W, ws, dt = self.dims, self.P, self.ws, self.dtype
@@ -808,8 +813,6 @@ class WhisperEEGEngine:
         nkv = dm.dec_layers * 2 * d
         kv_all = ws.get("kv_all", (B * S, nkv), dt)
         ops.gemm_nt(enc.view(B * S, d), W["dec.wkv"], kv_all, self._ep(bias=W["dec.bkv"]))
-        kv_beams = ws.get(f"bs_kv.{K}", (B * K * S, nkv), dt)
-        kv_beams.view(B, K, S, nkv).copy_(kv_all.view(B, 1, S, nkv).expand(B, K, S, nkv))
         if prompt is None:
             prompt = torch.full((B, 1), dm.decoder_start_token_id, dtype=torch.long, device=self.device)
         prompt = prompt.to(self.device, torch.long).contiguous()
@@ -818,7 +821,7 @@ class WhisperEEGEngine:
         logits = ws.get(f"bs_logits.{K}", (B * K, dm.Vp), torch.float32 if dt == torch.float32 else dt)
 
         def step_fn(tokens: torch.Tensor, pos: int) -> torch.Tensor:
-            self._decode_logits(tokens.contiguous(), pos, cache, kv_beams, logits, max_length)
+            self._decode_logits(tokens.contiguous(), pos, cache, kv_all, logits, max_length, beams=K)
             return logits
 
         def reorder_fn(beam_idx: torch.Tensor):
