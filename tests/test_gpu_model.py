@@ -163,6 +163,56 @@ def test_greedy_cuda_graph_replay_matches_eager():
         assert torch.equal(eng.greedy(x.to(DEV), max_length=14, prompt=prompt, use_graphs=True), refp)
 
 
+@pytest.mark.skipif(not os.environ.get("NS_TEST_ADALORA"), reason="AdaLoRA adapter: not yet verified on a B200 (set NS_TEST_ADALORA=1)")
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_adalora_adapter_matches_oracle_autograd(dtype):
+    """finetune.py:205-208 (AdaLoRA, the CLI default): y = base(x) + x (A*E)^T B^T alpha/(r+1e-5), loss += 0.5 * mean orthogonality
+    norm.  The adapter trains the engine on effective rank-16 operands; loss and the gradients of the MASTER A, E, B (and of
+    the stem) must match autograd through the oracle with the same parametrisation, and two optimizer steps must track it."""
+    from neuspeech1_b200.adalora import AdaLoraAdapter
+    dims = O.Dims(d_model=256, enc_layers=2, dec_layers=2, enc_heads=4, dec_heads=4, enc_ffn=512, dec_ffn=512, vocab=2000,
+                  max_source_positions=160, max_target_positions=32, eeg_ch=24, pad_token_id=1997, eos_token_id=1997,
+                  decoder_start_token_id=1998, begin_suppress_tokens=(220, 1996), lora_r=12, lora_alpha=32)
+    P = O.init_params(dims, seed=0)
+    x, labels = O.synthetic_batch(dims, B=2, L=8, seed=1)
+    ad = AdaLoraAdapter(ModelDims.from_any(dims), P, init_r=12, lora_alpha=32, orth_reg_weight=0.5, dtype=dtype, device=DEV, seed=3)
+    g = torch.Generator().manual_seed(5)
+    for name, _, _ in ad.modules:                                   # E = 0 at init would hide dA: give it values
+        ad.param(name + ".lora_E.default").copy_(torch.randn(12, 1, generator=g) * 0.5)
+        ad.param(name + ".lora_B.default").copy_(torch.randn(ad.param(name + ".lora_B.default").shape, generator=g) * 0.05)
+    sd = {k: v.cpu() for k, v in ad.state_dict().items()}
+
+    def oracle_loss(master):
+        eff = {}
+        for name, _, _ in ad.modules:
+            eff[name + ".lora_A.default.weight"] = master[name + ".lora_A.default"] * master[name + ".lora_E.default"]
+            eff[name + ".lora_B.default.weight"] = master[name + ".lora_B.default"]
+        od = O.Dims(**{**dims.__dict__, "lora_r": 12, "lora_alpha": 32 * 12 / (12 + 1e-5)})
+        ce, _, _ = O.forward_loss(x, labels, master["P"], od, eff)
+        eye = torch.eye(12)
+        reg = sum(torch.norm(master[n + ".lora_A.default"] @ master[n + ".lora_A.default"].T - eye, p="fro")
+                  + torch.norm(master[n + ".lora_B.default"].T @ master[n + ".lora_B.default"] - eye, p="fro") for n, _, _ in ad.modules)
+        return ce + 0.5 * reg / (2 * len(ad.modules))
+
+    stem_names = [k for k in P if k.startswith("model.encoder.conv")]
+    master = {k: v.clone().requires_grad_(True) for k, v in sd.items() if "ranknum" not in k}
+    Pg = {k: (v.clone().requires_grad_(True) if k in stem_names else v) for k, v in P.items()}
+    master["P"] = Pg
+    ref = oracle_loss(master)
+    ref.backward()
+    loss = ad.loss_and_grads(x.to(DEV), labels.to(DEV))
+    t = 1e-3 if dtype == torch.float32 else 2e-2
+    assert abs(float(loss) - float(ref)) < t * abs(float(ref)), (float(loss), float(ref))
+    for key in ad.entries:
+        assert rel(ad.param_grad(key).cpu(), master[key].grad) < (2e-3 if dtype == torch.float32 else 6e-2), key
+    for k in stem_names:
+        assert rel(ad.engine.trainable_grad(k).cpu(), Pg[k].grad) < (2e-3 if dtype == torch.float32 else 6e-2), k
+    l0 = float(ad.train_step(x.to(DEV), labels.to(DEV), lr=1e-3))
+    for _ in range(3):
+        l1 = float(ad.train_step(x.to(DEV), labels.to(DEV), lr=1e-3))
+    assert l1 < l0                                                  # same batch four times: the loss goes down
+
+
 def test_beam_search_matches_oracle_loop_fp32():
     """evaluation.py:370-385 (num_beams=5, repetition_penalty=5.0, no_repeat_ngram_size=2) on the B200 decoder step, fp32: the
     same token ids as the same scoring loop over the oracle's decoder (that loop is pinned to stock transformers generate in
