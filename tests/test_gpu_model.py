@@ -163,7 +163,6 @@ def test_greedy_cuda_graph_replay_matches_eager():
         assert torch.equal(eng.greedy(x.to(DEV), max_length=14, prompt=prompt, use_graphs=True), refp)
 
 
-@pytest.mark.skipif(not os.environ.get("NS_TEST_ADALORA"), reason="AdaLoRA adapter: not yet verified on a B200 (set NS_TEST_ADALORA=1)")
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_adalora_adapter_matches_oracle_autograd(dtype):
     """finetune.py:205-208 (AdaLoRA, the CLI default): y = base(x) + x (A*E)^T B^T alpha/(r+1e-5), loss += 0.5 * mean orthogonality
