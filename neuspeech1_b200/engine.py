@@ -798,11 +798,13 @@ class WhisperEEGEngine:
     @torch.no_grad()
     def beam_search(self, x: torch.Tensor, max_length: int, num_beams: int = 5, repetition_penalty: float = 1.0,
                     no_repeat_ngram_size: int = 0, prompt: Optional[torch.Tensor] = None, aug: Optional[dict] = None,
-                    length_penalty: float = 1.0) -> torch.Tensor:
+                    length_penalty: float = 1.0, use_graphs: bool = False) -> torch.Tensor:
         """`generate(num_beams=K, repetition_penalty, no_repeat_ngram_size)`: the beams ride in the batch dimension of the
         decoder pass (rows b*K + k) and in the query dimension of its cross-attention; the self-attention cache is gathered
         after every step like `_reorder_cache` (utils/load_model.py:1353-1360); the scoring loop is
-        neuspeech1_b200/generation.py.  Returns the generated suffix (B, <= max_length - prompt_len), pad after EOS."""
+        neuspeech1_b200/generation.py.  use_graphs: the decoder pass of every position is captured once into a CUDA graph and
+        replayed by later calls of the same shape (as in `greedy`).  Returns the generated suffix (B, <= max_length -
+        prompt_len), pad after EOS."""
         from .generation import beam_search as run_beams
         dm, W, ws, dt = self.dims, self.P, self.ws, self.dtype
         d, S = dm.d_model, dm.max_source_positions
@@ -820,8 +822,26 @@ class WhisperEEGEngine:
         cache = [ws.get(f"bs_qkv.{K}.{i}", (B * K, max_length, 3 * d), dt) for i in range(dm.dec_layers)]
         logits = ws.get(f"bs_logits.{K}", (B * K, dm.Vp), torch.float32 if dt == torch.float32 else dt)
 
+        graphs = self._decode_graphs if use_graphs else None
+
         def step_fn(tokens: torch.Tensor, pos: int) -> torch.Tensor:
-            self._decode_logits(tokens.contiguous(), pos, cache, kv_all, logits, max_length, beams=K)
+            Lq = tokens.shape[1]
+            ids = ws.get(f"bs_ids.{K}.{Lq}", (B * K, Lq), torch.long)       # static buffer: the pass below may be a graph replay
+            ids.copy_(tokens)
+            if graphs is None:
+                self._decode_logits(ids, pos, cache, kv_all, logits, max_length, beams=K)
+                return logits
+            key = ("beam", B, K, max_length, Lq, pos, self._weights_version)
+            ent = graphs.get(key)
+            if ent is None or ent[1] != ws.gen:
+                self._decode_logits(ids, pos, cache, kv_all, logits, max_length, beams=K)   # eager once: sizes the workspace
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._decode_logits(ids, pos, cache, kv_all, logits, max_length, beams=K)
+                graphs[key] = (g, ws.gen)
+            else:
+                ent[0].replay()
             return logits
 
         def reorder_fn(beam_idx: torch.Tensor):

@@ -246,6 +246,10 @@ def test_beam_search_matches_oracle_loop_fp32():
                               prompt=prompt if L0 > 1 else None).cpu()
         assert got.shape == ref.shape and torch.equal(got, ref), (K, L0, got, ref)
         assert len({tuple(r.tolist()) for r in ref}) > 1
+        for _ in range(3):                                   # capture, re-capture of the early positions, pure replay
+            got = eng.beam_search(x.to(DEV), max_length=20, num_beams=K, repetition_penalty=pen, no_repeat_ngram_size=ngram,
+                                  prompt=prompt if L0 > 1 else None, use_graphs=True).cpu()
+            assert torch.equal(got, ref)
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
