@@ -92,29 +92,60 @@ class BatchAugmenter:
             p.shift = int(np.random.randint(max_shift, size=None))
         return p
 
-    def plan(self, shapes: Sequence[Sequence[int]], device) -> dict:
-        """Draw the batch's random decisions -> keyword arguments of ops.aug_pass / engine.encode(aug=...)."""
+    def plan(self, shapes: Sequence[Sequence[int]], device, static: Optional[dict] = None) -> dict:
+        """Draw the batch's random decisions -> keyword arguments of ops.aug_pass / engine.encode(aug=...).
+
+        static: a dict made by `static_buffers(B, grid_cap, device)`.  The decisions are then written INTO those persistent
+        device tensors and the returned tensors are views of them, so that the arguments keep their addresses from step to step
+        (what `engine.train_step(use_graph=True)` keys its CUDA graphs on).  Without it fresh tensors are returned."""
         plans = [self._draw(s) for s in shapes]
         B = len(plans)
         has_grid = any(p.grid is not None for p in plans)
+        pin = torch.cuda.is_available() and torch.device(device).type == "cuda"
         # All per-sample integers travel in ONE pinned staging buffer and one asynchronous copy (a pageable
         # torch.tensor(..., device=...) per field is a synchronous memcpy on the compute stream: it drains the GPU every step).
         rows = [[p.n for p in plans], [p.shift for p in plans], [p.e0 for p in plans], [p.e1 for p in plans], [p.flags for p in plans]]
-        if has_grid:
+        if has_grid or static is not None:
             rows += [[p.grid.shape[1] if p.grid is not None else 1 for p in plans], [p.rep_c for p in plans], [p.rep_t for p in plans]]
-        host = torch.empty(len(rows), B, dtype=torch.int32, pin_memory=torch.cuda.is_available())
+        host = torch.empty(len(rows), B, dtype=torch.int32, pin_memory=pin)
         host.copy_(torch.tensor(rows, dtype=torch.int32))
-        devt = host.to(device, non_blocking=True)
+        if static is not None:
+            devt = static["ints"][:, :B]
+            devt.copy_(host, non_blocking=True)
+        else:
+            devt = host.to(device, non_blocking=True)
         kw = dict(n=devt[0], shift=devt[1], e0=devt[2], e1=devt[3], flags=devt[4])
-        if has_grid:
-            gmax = max(p.grid.numel() for p in plans if p.grid is not None)
-            grid = torch.ones(B, gmax, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+        if has_grid or static is not None:
+            gmax = max([p.grid.numel() for p in plans if p.grid is not None] + [1])
+            if static is not None:
+                cap = static["grid"].shape[1]
+                if gmax > cap:
+                    raise ValueError(f"mask grid of {gmax} cells exceeds the static buffer ({cap}); size it with static_buffers()")
+                gmax = cap
+            grid = torch.ones(B, gmax, dtype=torch.uint8, pin_memory=pin)
             for b, p in enumerate(plans):
                 if p.grid is not None:
                     grid[b, :p.grid.numel()] = p.grid.reshape(-1)
-            kw.update(grid=grid.to(device, non_blocking=True), grid_stride=gmax, gl=devt[5], rep_c=devt[6], rep_t=devt[7])
+            if static is not None:
+                gdev = static["grid"][:B]
+                gdev.copy_(grid, non_blocking=True)
+            else:
+                gdev = grid.to(device, non_blocking=True)
+            kw.update(grid=gdev, grid_stride=gmax, gl=devt[5], rep_c=devt[6], rep_t=devt[7])
         self._plans = plans
         return kw
+
+    def static_buffers(self, B: int, n_channels: int, device) -> dict:
+        """Persistent device tensors for `plan(..., static=...)`, sized for the finest mask grid the configuration can draw
+        (ceil(C / unit_c) x ceil(max_length / unit_t) cells; a full row / column unit for random_type 2 / 3)."""
+        cap = 1
+        if "mask" in self.cfg:
+            m = RandomShapeMasker(**self.cfg["mask"]["kwargs"])
+            uc, ut = m.unit
+            gc = 1 if m.random_type == 2 else int(np.ceil(n_channels / uc))
+            gt = 1 if m.random_type == 3 else int(np.ceil(self.max_length / ut))
+            cap = gc * gt
+        return {"ints": torch.zeros(8, B, dtype=torch.int32, device=device), "grid": torch.ones(B, cap, dtype=torch.uint8, device=device)}
 
     def __call__(self, samples: List[np.ndarray], out: torch.Tensor, layout: int = 1, seed: int = 0) -> torch.Tensor:
         """samples: list of (C, n_b) arrays -> `out` ((B,T,Cp) channels-last for layout 1, (B,C,T) for layout 0) on the device."""

@@ -1,0 +1,152 @@
+"""On-device input pipeline: `.npy` recording -> channel selection / channel padding -> pinned staging
+-> asynchronous copy into one of TWO persistent device batches -> the augmentation pass pads to 30 s, casts and lays the batch
+out channels-last on the device.
+
+Reference behaviour restated: `utils/reader.py:253-303` (`np.load`; Schoffelen recordings keep rows 28:301, Gwilliams rows :208,
+anything else rows :modal_ch; fewer channels than `modal_ch` are zero-padded at the END, `:508-516`), `:496-506` (crop to
+30 s x 200 Hz; the zero tail is written by `ns_aug_pass`, not on the host), and the collator `utils/data_utils.py:185-221`
+(labels right-padded with -100; a leading BOS shared by every row is cut).  Tokenisation stays with the caller: items carry
+token ids.
+
+The reference ships padded fp32 batches (5 MB per sample at C = 208) from 16 numpy workers; here the host only touches the
+UNPADDED samples (mean length ~2700 of 6000), and because batches land in two fixed device buffers the training step can be
+replayed as a CUDA graph (`engine.train_step(use_graph=True)` keys its graphs on the buffer addresses).
+"""
+from __future__ import annotations
+
+import queue
+import threading
+from typing import Dict, Iterable, Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .augment_eeg import BatchAugmenter
+
+
+def select_channels(sample: np.ndarray, path: str, modal_ch: int) -> np.ndarray:
+    """(C_file, n) -> (modal_ch, n): dataset-specific row window, then zero rows appended up to modal_ch (reader.py:270-282)."""
+    if "schoffelen" in path:
+        sample = sample[28:301]
+    elif "gwilliams" in path:
+        sample = sample[:208]
+    else:
+        sample = sample[:modal_ch]
+    if sample.shape[0] > modal_ch:
+        raise ValueError(f"{path}: {sample.shape[0]} channels selected but the stem takes {modal_ch}")
+    if sample.shape[0] < modal_ch:
+        sample = np.pad(sample, ((0, modal_ch - sample.shape[0]), (0, 0)))
+    return sample
+
+
+def collate_labels(labels: Sequence[Sequence[int]], bos_token_id: Optional[int] = None) -> torch.Tensor:
+    """Right-pad with -100; drop the first column when every row starts with BOS (data_utils.py:198-219)."""
+    L = max(len(l) for l in labels)
+    out = torch.full((len(labels), L), -100, dtype=torch.long)
+    for i, l in enumerate(labels):
+        out[i, :len(l)] = torch.as_tensor(list(l), dtype=torch.long)
+    if bos_token_id is not None and bool((out[:, 0] == bos_token_id).all()):
+        out = out[:, 1:]
+    return out
+
+
+class DeviceBatchLoader:
+    """Iterate `(input_features, labels, aug)` batches that live on `device`.
+
+    items: sequence of dicts `{"path": <.npy file> | "array": (C, n) ndarray, "labels": [token ids]}`.
+    `input_features` is one of two persistent (B, modal_ch, max_samples) fp32 device buffers holding the unpadded samples (rows
+    beyond a sample's length are stale: `aug["n"]` carries the lengths and `ns_aug_pass` writes the zero tail), `labels` one of two
+    persistent (B, max_label_len) int64 buffers (-100 padded; longer label rows are truncated, the reference filters them by
+    `max_label_length`), `aug` the keyword arguments of `engine.train_step(..., aug=aug)` (augmentation decisions drawn per sample
+    with the reference's RNG calls when `augment_configs` is given), written into persistent per-slot tensors as well: every
+    address a training step sees repeats every second batch, which is what CUDA-graph replay of the step needs.
+    A background thread reads and stages batch i+1 while batch i trains; the device copy runs on its own stream."""
+
+    def __init__(self, items: Sequence[Dict], batch_size: int, modal_ch: int, device, augment_configs: Optional[Dict] = None,
+                 max_duration: float = 30.0, sample_rate: int = 200, max_label_len: int = 64, bos_token_id: Optional[int] = None,
+                 order: Optional[Iterable[int]] = None, drop_last: bool = True, train: bool = True):
+        self.items, self.B, self.C = items, batch_size, modal_ch
+        self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
+        self.T = int(max_duration * sample_rate)
+        self.Lmax = max_label_len
+        self.bos = bos_token_id
+        self.order = list(order) if order is not None else list(range(len(items)))
+        self.drop_last = drop_last
+        self.aug = BatchAugmenter(augment_configs or {}, max_duration=max_duration, sample_rate=sample_rate, train=train)
+        self.x_dev = [torch.zeros(batch_size, modal_ch, self.T, dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.y_dev = [torch.full((batch_size, max_label_len), -100, dtype=torch.long, device=self.device) for _ in range(2)]
+        self.x_host = [torch.zeros(batch_size, modal_ch, self.T, dtype=torch.float32, pin_memory=self.cuda) for _ in range(2)]
+        self.aug_static = [self.aug.static_buffers(batch_size, modal_ch, self.device) for _ in range(2)]
+        self.stream = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self.free = [torch.cuda.Event() for _ in range(2)] if self.cuda else None     # device side: the step that read the slot was launched
+        self.h2d_done = [torch.cuda.Event() for _ in range(2)] if self.cuda else None # host side: the pinned slot may be refilled
+
+    def __len__(self) -> int:
+        n = len(self.order)
+        return n // self.B if self.drop_last else (n + self.B - 1) // self.B
+
+    def _stage(self, idxs: List[int], slot: int):
+        """Host side of one batch (worker thread): read, select channels, crop to 30 s, copy into the pinned buffer."""
+        lens, labels = [], []
+        xh = self.x_host[slot]
+        if self.cuda:
+            self.h2d_done[slot].synchronize()           # the copy of the batch staged here two batches ago has left the pinned buffer
+        for b, i in enumerate(idxs):
+            it = self.items[i]
+            s = it["array"] if "array" in it else np.load(it["path"])
+            s = select_channels(np.asarray(s), it.get("path", ""), self.C)[:, :self.T]
+            n = s.shape[1]
+            xh[b, :, :n] = torch.from_numpy(np.ascontiguousarray(s, dtype=np.float32))
+            lens.append(n); labels.append(list(it["labels"])[:self.Lmax])
+        return lens, collate_labels(labels, self.bos)
+
+    def release(self, slot: int):
+        """The work that reads `slot` has been launched on the current stream: its device buffers may be overwritten after it.
+        Called automatically when the next batch is requested."""
+        if self.cuda:
+            self.free[slot].record(torch.cuda.current_stream(self.device))
+
+    def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor, dict, int]]:
+        batches = [self.order[k:k + self.B] for k in range(0, len(self.order), self.B)]
+        if self.drop_last:
+            batches = [b for b in batches if len(b) == self.B]
+        q: "queue.Queue" = queue.Queue(maxsize=1)
+
+        def worker():
+            for k, idxs in enumerate(batches):
+                q.put((k, idxs, self._stage(idxs, k & 1)))
+            q.put(None)
+
+        th = threading.Thread(target=worker, daemon=True)
+        th.start()
+        prev_slot = None
+        while True:
+            got = q.get()
+            if prev_slot is not None:
+                self.release(prev_slot)                 # the consumer launched its step on the previous batch before asking again
+            if got is None:
+                break
+            k, idxs, (lens, labels) = got
+            slot = k & 1
+            nb = len(idxs)
+            xd, yd = self.x_dev[slot], self.y_dev[slot]
+            lab = torch.full((nb, self.Lmax), -100, dtype=torch.long, pin_memory=self.cuda)
+            lab[:, :labels.shape[1]] = labels
+            shapes = [(self.C, n) for n in lens]
+            if self.cuda:
+                with torch.cuda.stream(self.stream):
+                    self.stream.wait_event(self.free[slot])
+                    xd[:nb].copy_(self.x_host[slot][:nb], non_blocking=True)      # whole rows: one contiguous pinned -> device copy
+                    yd[:nb].copy_(lab, non_blocking=True)
+                    plan = self.aug.plan(shapes, self.device, static=self.aug_static[slot])
+                    self.h2d_done[slot].record(self.stream)
+                torch.cuda.current_stream(self.device).wait_stream(self.stream)
+            else:
+                xd[:nb].copy_(self.x_host[slot][:nb])
+                yd[:nb].copy_(lab)
+                plan = self.aug.plan(shapes, self.device, static=self.aug_static[slot])
+            # fixed-shape views of the persistent buffers: the label width is the widest batch the loader may ever yield
+            prev_slot = slot
+            yield xd[:nb], yd[:nb], plan, slot
+        th.join()

@@ -1,0 +1,52 @@
+"""Host logic of the on-device input pipeline (neuspeech1_b200/reader.py) on the CPU device: channel selection like
+utils/reader.py:270-282 / :508-516, label collation like utils/data_utils.py:198-219, double-buffered batches with stable
+addresses, lengths handed to the augmentation pass."""
+import numpy as np
+import pytest
+import torch
+
+from neuspeech1_b200.reader import DeviceBatchLoader, collate_labels, select_channels
+
+
+def test_select_channels_follows_the_reference_windows():
+    s = np.arange(320 * 5, dtype=np.float32).reshape(320, 5)
+    assert np.array_equal(select_channels(s, "/data/schoffelen/sub-A2002/x.npy", 273), s[28:301])
+    assert np.array_equal(select_channels(s, "/data/gwilliams2023/x.npy", 208), s[:208])
+    assert np.array_equal(select_channels(s, "/data/other/x.npy", 64), s[:64])
+    padded = select_channels(s, "/data/gwilliams2023/x.npy", 273)            # combined-dataset run: zero rows appended
+    assert padded.shape == (273, 5) and np.array_equal(padded[:208], s[:208]) and not padded[208:].any()
+    with pytest.raises(ValueError):
+        select_channels(s, "/data/schoffelen/x.npy", 208)                    # 273 selected rows do not fit a 208-channel stem
+
+
+def test_collate_labels():
+    out = collate_labels([[7, 1, 2, 3], [7, 5]], bos_token_id=7)
+    assert out.tolist() == [[1, 2, 3], [5, -100, -100]]
+    out = collate_labels([[7, 1, 2, 3], [8, 5]], bos_token_id=7)             # not every row starts with BOS: nothing is cut
+    assert out.tolist() == [[7, 1, 2, 3], [8, 5, -100, -100]]
+
+
+def test_loader_double_buffers_and_lengths():
+    rng = np.random.RandomState(0)
+    items = []
+    for i in range(5):
+        n = int(rng.randint(50, 400))
+        items.append({"array": rng.randn(12, n).astype(np.float32), "path": f"/x/other/{i}.npy", "labels": list(range(3 + i))})
+    cfg = {"mask": {"prob": 1.0, "kwargs": {"unit": [1, 40], "mask_prob": 0.25, "random_type": 1}}}
+    ld = DeviceBatchLoader(items, batch_size=2, modal_ch=16, device="cpu", augment_configs=cfg, max_duration=2.0, sample_rate=200,
+                           max_label_len=8)
+    assert len(ld) == 2
+    seen, ptrs = [], []
+    for k, (x, y, aug, slot) in enumerate(ld):
+        assert slot == k % 2 and x.shape == (2, 16, 400) and y.shape == (2, 8)
+        for b in range(2):
+            it = items[2 * k + b]
+            n = it["array"].shape[1]
+            assert int(aug["n"][b]) == n
+            assert torch.equal(x[b, :12, :n], torch.from_numpy(it["array"])) and not x[b, 12:, :n].any()
+            assert y[b, :len(it["labels"])].tolist() == it["labels"] and bool((y[b, len(it["labels"]):] == -100).all())
+        assert aug["grid"].shape[1] == aug["grid_stride"] == 16 * 10 and int(aug["flags"][0]) == 1
+        seen.append(k); ptrs.append((x.data_ptr(), y.data_ptr(), aug["n"].data_ptr(), aug["grid"].data_ptr()))
+    assert seen == [0, 1] and ptrs[0] != ptrs[1]
+    ptrs2 = [(x.data_ptr(), y.data_ptr(), aug["n"].data_ptr(), aug["grid"].data_ptr()) for x, y, aug, _ in ld]
+    assert ptrs2 == ptrs                                    # a second epoch lands in the same buffers
