@@ -127,6 +127,11 @@ def cpu_train_steps(B, L, steps, warmup, eeg_ch=208, threads=None):
     return B * steps / dt, threads, dt / max(steps, 1)
 
 
+def workload_name(eeg_ch, B, L):
+    return (f"Gwilliams-shaped LoRA fine-tune step: Whisper-base, eeg_ch={eeg_ch}, B={B}/GPU, L={L}, "
+            f"LoRA r=32 on 36 encoder linears + 3 stem convs, augmentation1 (identity) pass")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -138,7 +143,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"Whisper-base EEG LoRA fine-tune step, eeg_ch={args.eeg_ch}, L={args.labels}, CPU sample B={B}"},
+        "config": {"workload": workload_name(args.eeg_ch, args.batch, args.labels), "parallelism": "host cores",
+                   "sample": f"each step is a bounded sample of that workload: B={B} instead of {args.batch} per step"},
         "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} training steps of B={B} (oracle port of the reference path; PEFT/accelerate absent)"},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -295,8 +301,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": f"Gwilliams-shaped LoRA fine-tune step: Whisper-base, eeg_ch={args.eeg_ch}, B={B}/GPU, L={L}, "
-                                   f"LoRA r=32 on 36 encoder linears + 3 stem convs, augmentation1 (identity) pass",
+            "config": {"workload": workload_name(args.eeg_ch, B, L),
                        "parallelism": f"dp{world}", "l2": "inputs and activations per step (>10 GB) exceed the 126 MB L2",
                        "launch": "pack + forward + backward replayed as one CUDA graph per input buffer, all-reduce and optimizer launched eagerly"},
             "clocks": clocks, "gpu_launches": launches,
