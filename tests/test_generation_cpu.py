@@ -75,6 +75,34 @@ def test_beam_search_matches_transformers(seed):
     assert len({tuple(r.tolist()) for r in ref}) > 1           # the inputs matter: not one sequence for every sample
 
 
+@pytest.mark.parametrize("case", [(2.0, 4, 18), (0.5, 5, 18), (1.0, 2, 12), (0.0, 5, 16), (1.0, 5, 6), (1.5, 3, 24)])
+def test_beam_search_length_penalties_match_transformers(case):
+    """length_penalty (finished-hypothesis score = sum-logprob / generated_length ** lp, also in the stop heuristic), narrow and
+    wide beams, a length limit a few tokens after the prompt."""
+    import transformers
+    transformers.logging.set_verbosity_error()
+    lp, K, max_length = case
+    V = 40
+    dims = O.Dims(d_model=64, enc_layers=1, dec_layers=2, enc_heads=2, dec_heads=2, enc_ffn=128, dec_ffn=128, vocab=V,
+                  max_source_positions=40, max_target_positions=24, eeg_ch=6, pad_token_id=V - 3, eos_token_id=V - 3,
+                  decoder_start_token_id=V - 2, begin_suppress_tokens=(20, V - 4), lora_r=4, lora_alpha=8)
+    seed = int(lp * 10) + K
+    P = O.init_params(dims, seed=seed + 20, std=0.5)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(4, dims.eeg_ch, dims.T, generator=g) * 2
+    prompt = torch.full((4, 1), dims.decoder_start_token_id, dtype=torch.long)
+    m = build_hf(dims, P)
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = m.generate(x, do_sample=False, num_beams=K, repetition_penalty=5.0, no_repeat_ngram_size=2, max_length=max_length,
+                         length_penalty=lp)
+    step_fn, reorder_fn = _oracle_step_fns(dims, P, O.encoder(x, P, dims, None), K)
+    out = beam_search(step_fn, reorder_fn, prompt, K, max_length, dims.vocab, dims.eos_token_id, dims.pad_token_id,
+                      dims.begin_suppress_tokens, 5.0, 2, length_penalty=lp)
+    for b in range(4):
+        assert _strip(out[b, 1:], dims.pad_token_id) == _strip(ref[b], dims.pad_token_id), (b, out[b], ref[b])
+
+
 def test_logit_processors():
     scores = torch.log_softmax(torch.arange(12, dtype=torch.float32).view(2, 6), dim=-1)
     seqs = torch.tensor([[1, 2, 1], [0, 0, 3]])
