@@ -18,7 +18,7 @@ oracle's decoder as step function); `tests/test_gpu_model.py` then runs it over 
 """
 from __future__ import annotations
 
-from typing import Callable, Optional, Sequence
+from typing import Callable, Sequence
 
 import torch
 
