@@ -166,11 +166,37 @@ def trainable_names(P: Dict[str, Tensor], lora: Dict[str, Tensor]) -> List[str]:
 
 # --------------------------------------------------------------------------- forward pieces
 
+def lora_dropout_keep(seed: int, name: str, rows: int, cols: int, p: float) -> Tensor:
+    """Keep mask (rows, cols) of the LoRA-branch dropout of module `name` (finetune.py:210 lora_dropout=0.05): a counter hash
+    of (seed ^ crc32(name), row, column) so that a device kernel can recompute any element without storing the mask --
+        x = row * 0x9E3779B1 ^ col * 0x85EBCA77 ^ module_seed;  x ^= x >> 16;  x *= 0x7FEB352D;  x ^= x >> 15;
+        x *= 0x846CA68B;  x ^= x >> 16;            (all mod 2^32)        dropped  <=>  x < floor(p * 2^32)
+    This is the specification the planned B200 kernels are to follow; PEFT itself draws from torch's
+    generator, so with dropout on parity with the reference is statistical by construction."""
+    import zlib
+    import numpy as np
+    m = np.uint64(0xFFFFFFFF)
+    ms = np.uint64((seed ^ zlib.crc32(name.encode())) & 0xFFFFFFFF)
+    r = np.arange(rows, dtype=np.uint64)[:, None]
+    c = np.arange(cols, dtype=np.uint64)[None, :]
+    x = ((r * np.uint64(0x9E3779B1)) ^ (c * np.uint64(0x85EBCA77)) ^ ms) & m
+    x ^= x >> np.uint64(16); x = (x * np.uint64(0x7FEB352D)) & m
+    x ^= x >> np.uint64(15); x = (x * np.uint64(0x846CA68B)) & m
+    x ^= x >> np.uint64(16)
+    return torch.from_numpy(x >= np.uint64(int(p * 4294967296.0)))
+
+
 def linear(x: Tensor, P, name: str, lora=None, scale: float = 0.0) -> Tensor:
     y = F.linear(x, P[name + ".weight"], P.get(name + ".bias"))
     if lora is not None and (name + ".lora_A.default.weight") in lora:
         a = lora[name + ".lora_A.default.weight"]; b = lora[name + ".lora_B.default.weight"]
-        y = y + scale * F.linear(F.linear(x, a), b)
+        xin = x
+        if "__dropout__" in lora:                       # (p, seed): training-mode dropout on the LoRA branch input only
+            pdrop, seed = lora["__dropout__"]
+            if pdrop > 0:
+                keep = lora_dropout_keep(seed, name, x.numel() // x.shape[-1], x.shape[-1], pdrop).view(x.shape)
+                xin = x * keep.to(x.dtype) / (1.0 - pdrop)
+        y = y + scale * F.linear(F.linear(xin, a), b)
     return y
 
 

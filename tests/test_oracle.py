@@ -115,3 +115,30 @@ def test_adamw_matches_torch():
         assert abs(n - float(n_ref)) < 1e-5 * n
         for k in p:
             assert rel(p[k], q[k].detach()) < 1e-6
+
+
+def test_lora_dropout_mask_spec():
+    """The counter-hash keep mask of the LoRA-branch dropout (oracle.lora_dropout_keep, the specification for the device kernels):
+    rate, independence between modules and seeds, p = 0 identical to no dropout, gradients flow through the kept elements."""
+    import torch
+    from oracle import whisper_eeg as O
+    k1 = O.lora_dropout_keep(7, "model.encoder.layers.0.fc1", 4096, 512, 0.05)
+    k2 = O.lora_dropout_keep(7, "model.encoder.layers.0.fc2", 4096, 512, 0.05)
+    k3 = O.lora_dropout_keep(8, "model.encoder.layers.0.fc1", 4096, 512, 0.05)
+    for k in (k1, k2, k3):
+        assert abs(1.0 - k.float().mean().item() - 0.05) < 2e-3
+    assert abs((k1 ^ k2).float().mean().item() - 2 * 0.05 * 0.95) < 3e-3 and abs((k1 ^ k3).float().mean().item() - 0.095) < 3e-3
+    assert abs(k1.float().mean(dim=0).std().item() - (0.05 * 0.95 / 4096) ** 0.5) < 1e-3      # no column structure
+    assert bool(O.lora_dropout_keep(7, "x", 64, 64, 0.0).all())
+    dims = O.TINY
+    P = O.init_params(dims, seed=0)
+    lora = O.init_lora(dims, seed=1, b_std=0.05)
+    x, labels = O.synthetic_batch(dims, B=2, L=8, seed=1)
+    base, _, _ = O.forward_loss(x, labels, P, dims, lora)
+    same, _, _ = O.forward_loss(x, labels, P, dims, {**lora, "__dropout__": (0.0, 3)})
+    assert torch.equal(base, same)
+    la = {k: v.clone().requires_grad_(True) for k, v in lora.items()}
+    dropped, _, _ = O.forward_loss(x, labels, P, dims, {**la, "__dropout__": (0.3, 3)})
+    assert abs(float(dropped) - float(base)) > 1e-6
+    dropped.backward()
+    assert all(v.grad is not None and torch.isfinite(v.grad).all() for v in la.values())
