@@ -177,6 +177,32 @@ int ns_add(int dtype, long long n, const void* a, const void* b, void* y, void* 
  * path whose backward cannot ride in a GEMM epilogue) */
 int ns_dgelu_mul(int dtype, long long n, const void* dy, const void* z, void* dz, void* stream);
 
+/* ---- LoRA branch: dropout and the rank-r products around it.
+ * Replaces PEFT lora.Linear's  result += lora_B(lora_A(lora_dropout(x))) * scaling  (finetune.py:206-212: lora_dropout 0.05,
+ * 0.1 for AdaLoRA) and its autograd backward.  The keep mask is a counter hash of (row pair, column, *seed ^ salt) that every
+ * kernel recomputes (never stored): element (row, col) is dropped iff the 16-bit half (row & 1) of
+ *   lowbias32(((row >> 1) * 0x9E3779B1) ^ (col * 0x85EBCA77) ^ *seed ^ salt)   is  < round(p * 65536).
+ * `seed` is a DEVICE word (one per training step, advanced on the device so a replayed CUDA graph draws a new mask); `salt` /
+ * `salts[g]` identify the module (crc32 of its name).  The kernels use the UNSCALED masked input: the caller folds 1/(1-p)
+ * into alpha (t) and into dt.  G = number of adapters stacked on the same input (1, or 3 for q/k/v), r = LoRA rank. */
+int ns_seed_advance(unsigned int* seed, void* stream);                          /* *seed = lowbias32(*seed + 0x9E3779B9) */
+/* y = x with dropped elements zeroed (materialised masked input: fp32 parity mode and tests) */
+int ns_dropout_apply(int dtype, long long rows, int cols, const void* x, long long ldx, void* y, long long ldy,
+                     const unsigned int* seed, unsigned int salt, float p, void* stream);
+/* t[M, G*r] = alpha * (x . keep_g) * A_g^T for the G stacked adapters A = [A_0; ..; A_{G-1}] (G*r, K), bf16 storage.  p == 0
+ * (evaluation, parity runs): plain t = alpha * x * A^T.  HBM-bound: x is read once. */
+int ns_lora_down(long long M, int K, int G, int r, const void* x, long long ldx, const void* A, long long lda, void* t,
+                 long long ldt, float alpha, const unsigned int* seed, const unsigned int* salts, float p, void* stream);
+/* dA[G*r, K] (fp32, row stride ldg) += dt_g^T * (x . keep_g): gradient of the stacked A_g, bf16 activations, x read once */
+int ns_lora_da(long long M, int K, int G, int r, const void* x, long long ldx, const void* dt, long long lddt, float* dA,
+               long long ldg, const unsigned int* seed, const unsigned int* salts, float p, void* stream);
+/* dx[m,k] -= sum_g dropped_g(m,k) * (dt_g[m,:] . At[k, g*r:(g+1)*r]) (* gelu'(z[m,k]) when z != NULL), in place: the input-
+ * gradient GEMM carries the LoRA product as a K-segment as if nothing had been dropped; this removes the dropped terms.
+ * At = A^T (K, ldat >= G*r) in the activation dtype. */
+int ns_lora_dx_fix(int dtype, long long rows, int K, int G, int r, void* dx, long long lddx, const void* dt, long long lddt,
+                   const void* At, long long ldat, const unsigned int* seed, const unsigned int* salts, float p, const void* z,
+                   long long ldz, void* stream);
+
 /* ---- fused clip + AdamW over one flat fp32 parameter/gradient buffer (HF trainer.py:2493,1760; finetune.py:236-247).
  *  Step 1: ns_sumsq accumulates sum(g^2) into *out (caller zeroes).  Step 2: ns_adamw_clip reads *sumsq on device,
  *  scales g by min(1, max_norm/(sqrt(sumsq*gscale^2)+1e-6))*gscale and applies torch.optim.AdamW semantics. */

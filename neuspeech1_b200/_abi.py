@@ -75,6 +75,11 @@ SIGNATURES = {
     "ns_conv_weight_unpack_grad": [c_i, c_i, c_i, c_vp, c_vp, c_vp],
     "ns_add": [c_i, c_ll, c_vp, c_vp, c_vp, c_vp],
     "ns_dgelu_mul": [c_i, c_ll, c_vp, c_vp, c_vp, c_vp],
+    "ns_seed_advance": [c_vp, c_vp],
+    "ns_dropout_apply": [c_i, c_ll, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, C.c_uint, c_f, c_vp],
+    "ns_lora_down": [c_ll, c_i, c_i, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_f, c_vp, c_vp, c_f, c_vp],
+    "ns_lora_da": [c_ll, c_i, c_i, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_vp, c_f, c_vp],
+    "ns_lora_dx_fix": [c_i, c_ll, c_i, c_i, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_vp, c_f, c_vp, c_ll, c_vp],
     "ns_sumsq": [c_ll, c_vp, c_vp, c_vp],
     "ns_adamw_clip": [c_ll, c_vp, c_vp, c_vp, c_vp, c_vp, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_vp],
 }

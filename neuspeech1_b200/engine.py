@@ -139,9 +139,24 @@ class Workspace:
         return sum(t.numel() * t.element_size() for t in self.bufs.values())
 
 
+def _on_device(fn):
+    """Run an engine entry point with the engine's GPU current: every ns_* call launches on the CURRENT device's current stream
+    (ops._stream), so an engine built for cuda:N in a process whose current device is cuda:0 would otherwise launch on GPU 0
+    with GPU N pointers."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **kw):
+        if torch.cuda.current_device() == self.device.index:
+            return fn(self, *a, **kw)
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **kw)
+    return wrapped
+
+
 class WhisperEEGEngine:
     def __init__(self, dims: ModelDims, params: Dict[str, torch.Tensor], lora: Optional[Dict[str, torch.Tensor]] = None,
-                 dtype: torch.dtype = torch.bfloat16, device="cuda"):
+                 dtype: torch.dtype = torch.bfloat16, device="cuda", lora_dropout: float = 0.0, dropout_seed: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError("neuspeech1_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         ops.lib()
@@ -149,6 +164,8 @@ class WhisperEEGEngine:
         self.dtype = dtype
         self.ns = ops.ns_dtype(dtype)
         self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.ws = Workspace(self.device)
         self.has_lora = lora is not None
         self.fuse_cross_bwd = False      # decoder cross-attention backward through the fused single-pass kernel
@@ -159,8 +176,65 @@ class WhisperEEGEngine:
         self.adam_v = torch.zeros_like(self.flat)
         self.opt_step = 0
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
+        # LoRA-branch dropout (finetune.py:210 lora_dropout=0.05): applied by training forwards (save=True) while `training`;
+        # the step seed is a device word that train_step advances on the device (a replayed CUDA graph draws a new mask)
+        if not 0.0 <= lora_dropout < 1.0:
+            raise ValueError(f"lora_dropout must be in [0, 1), got {lora_dropout}")
+        self.lora_dropout = float(lora_dropout)
+        self.training = True
+        self.drop_seed = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._drop_p = 0.0
+        self.use_lora_kernels = dtype == torch.bfloat16      # ns_lora_down / ns_lora_da (bf16 storage); else the GEMM kernels
+        self.set_dropout_seed(dropout_seed)
         self.P: Dict[str, torch.Tensor] = {}
-        self.load_params(params, lora)
+        with torch.cuda.device(self.device):
+            self.load_params(params, lora)
+
+    def set_dropout_seed(self, seed: int):
+        """Step seed of the LoRA-branch dropout mask (the next train_step advances it first: oracle.next_dropout_seed)."""
+        seed &= 0xFFFFFFFF
+        self.drop_seed.fill_(seed - (1 << 32) if seed >= (1 << 31) else seed)
+
+    def _salts(self, layer: int, targets) -> List[int]:
+        import zlib
+        return [zlib.crc32(lora_module_name(layer, t).encode()) & 0xFFFFFFFF for t in targets]
+
+    def _lora_down(self, x: torch.Tensor, A: torch.Tensor, t: torch.Tensor, layer: int, targets):
+        """t[:, g*r:(g+1)*r] = alpha' * dropout_g(x) A_g^T for the adapters `targets` stacked in A (PEFT lora.Linear:
+        lora_A(lora_dropout(x)) * scaling); alpha' = (alpha/r) / (1 - p)."""
+        p, r, G = self._drop_p, self.dims.lora_r, len(targets)
+        a = self.dims.lora_scale / (1.0 - p)
+        K = x.shape[1]
+        if self.use_lora_kernels and K % 32 == 0 and r in (8, 16, 32) and G * r * (2 * K + 64) <= 220 * 1024:
+            ops.lora_down(x, A, t, a, G, self.drop_seed, self._salts(layer, targets), p)
+        elif p == 0.0:
+            ops.gemm_nt(x, A, t, self._ep(alpha=a, alpha_cols=G * r))
+        else:
+            xm = self.ws.get(f"xm.{K}", x.shape, self.dtype)
+            for g, salt in enumerate(self._salts(layer, targets)):
+                ops.dropout_apply(x, xm, self.drop_seed, salt, p)
+                ops.gemm_nt(xm, A[g * r:(g + 1) * r], t[:, g * r:(g + 1) * r], self._ep(alpha=a, alpha_cols=r))
+
+    def _lora_da(self, x: torch.Tensor, dt: torch.Tensor, layer: int, targets):
+        """dA_g += dt_g^T dropout_g(x) into the flat gradient buffer (the A gradients of `targets` are contiguous)."""
+        p, r, G = self._drop_p, self.dims.lora_r, len(targets)
+        K = x.shape[1]
+        off, _ = self.layout.entries[lora_module_name(layer, targets[0]) + ".lora_A.default.weight"]
+        gA = self.grad[off: off + G * r * K].view(G * r, K)
+        if self.use_lora_kernels and K % 8 == 0 and r in (8, 16, 32):
+            ops.lora_da(x, dt, gA, G, self.drop_seed, self._salts(layer, targets), p)
+        elif p == 0.0:
+            ops.gemm_tn(x, dt, gA, 1, K)
+        else:
+            xm = self.ws.get(f"xm.{K}", x.shape, self.dtype)
+            for g, salt in enumerate(self._salts(layer, targets)):
+                ops.dropout_apply(x, xm, self.drop_seed, salt, p)
+                ops.gemm_tn(xm, dt[:, g * r:(g + 1) * r], gA[g * r:(g + 1) * r], 1, K)
+
+    def _lora_fix(self, dx: torch.Tensor, dt: torch.Tensor, At: torch.Tensor, layer: int, targets, z: Optional[torch.Tensor] = None):
+        """The input-gradient GEMM added dt' A for every element; take the dropped ones out again (no-op without dropout)."""
+        if self._drop_p > 0.0:
+            ops.lora_dx_fix(dx, dt, At, self.drop_seed, self._salts(layer, targets), self._drop_p, len(targets), z)
 
     # ------------------------------------------------------------------ parameters
     def _c(self, t: torch.Tensor) -> torch.Tensor:
@@ -178,6 +252,7 @@ class WhisperEEGEngine:
         out = torch.empty((cols, pad_to or rows), dtype=self.dtype, device=self.device)
         return ops.transpose(t, out, scale)
 
+    @_on_device
     def load_params(self, params: Dict[str, torch.Tensor], lora: Optional[Dict[str, torch.Tensor]] = None):
         """(Re)load weights.  `params`: HF-named fp32 tensors (see oracle.init_params / state_dict of the HF model)."""
         dm = self.dims
@@ -259,6 +334,7 @@ class WhisperEEGEngine:
     def trainable_grad(self, name: str) -> torch.Tensor:
         return self.layout.view(self.grad, name)
 
+    @_on_device
     def pack_trainable(self):
         """Refresh the compute-dtype copies of the trainable weights (LoRA A/B + transposes, stem tap layouts)."""
         dm, lay, W = self.dims, self.layout, self.P
@@ -324,6 +400,7 @@ class WhisperEEGEngine:
         ops.aug_pass(x, y, layout=1, **(aug or {}))
         return y
 
+    @_on_device
     def encode(self, x: torch.Tensor, aug: Optional[dict] = None, save: bool = False) -> torch.Tensor:
         """input_features (B, eeg_ch, T) -> encoder_last_hidden_state (B, S, d).  utils/load_model.py:371-476."""
         dm, W, ws, dt = self.dims, self.P, self.ws, self.dtype
@@ -334,7 +411,7 @@ class WhisperEEGEngine:
         B = x.shape[0]
         d, S, T, F, r, H = dm.d_model, dm.max_source_positions, dm.T, dm.enc_ffn, dm.lora_r, dm.enc_heads
         M = B * S
-        s = dm.lora_scale
+        self._drop_p = self.lora_dropout if (save and self.training and self.has_lora) else 0.0
         xcl = self.input_to_channels_last(x, aug)
         zA = ws.get("zA", (B, T, d), dt); aA = ws.get("aA", (B, T, d), dt)
         ops.conv3_fwd(xcl, W["stemA.w"], aA, 1, self._ep(bias=W["stemA.b"], act=ACT_GELU, aux_out=zA if save else None, ldaux=d))
@@ -355,7 +432,7 @@ class WhisperEEGEngine:
             qkv = ws.get("qkv" + sfx, (M, 3 * d), dt)
             if self.has_lora:
                 t_qkv = ws.get("t_qkv" + sfx, (M, 3 * r), dt)
-                ops.gemm_nt(u1, W[k + ".A_qkv"], t_qkv, self._ep(alpha=s, alpha_cols=3 * r))
+                self._lora_down(u1, W[k + ".A_qkv"], t_qkv, i, ("q_proj", "k_proj", "v_proj"))
                 ops.gemm_nt(u1, W[k + ".wqkv"], qkv, self._ep(bias=W[k + ".bqkv"], alpha=Dh ** -0.5, alpha_cols=d, a2_group_cols=d),
                             a2=t_qkv, w2=W[k + ".B_qkv"], k2=r)
             else:
@@ -366,7 +443,7 @@ class WhisperEEGEngine:
             hm = ws.get("hm" + sfx, (M, d), dt)
             if self.has_lora:
                 t_o = ws.get("t_o" + sfx, (M, r), dt)
-                ops.gemm_nt(o, W[k + ".A_out_proj"], t_o, self._ep(alpha=s, alpha_cols=r))
+                self._lora_down(o, W[k + ".A_out_proj"], t_o, i, ("out_proj",))
                 ops.gemm_nt(o, W[k + ".wo"], hm, self._ep(bias=W[k + ".bo"], residual=h, ldr=d), a2=t_o, w2=W[k + ".B_out_proj"], k2=r)
             else:
                 ops.gemm_nt(o, W[k + ".wo"], hm, self._ep(bias=W[k + ".bo"], residual=h, ldr=d))
@@ -377,14 +454,14 @@ class WhisperEEGEngine:
             m = ws.get("m" + sfx, (M, F), dt)
             if self.has_lora:
                 t_1 = ws.get("t_1" + sfx, (M, r), dt)
-                ops.gemm_nt(u2, W[k + ".A_fc1"], t_1, self._ep(alpha=s, alpha_cols=r))
+                self._lora_down(u2, W[k + ".A_fc1"], t_1, i, ("fc1",))
                 ops.gemm_nt(u2, W[k + ".w1"], m, self._ep(bias=W[k + ".b1"], act=ACT_GELU, aux_out=z1, ldaux=F), a2=t_1, w2=W[k + ".B_fc1"], k2=r)
             else:
                 ops.gemm_nt(u2, W[k + ".w1"], m, self._ep(bias=W[k + ".b1"], act=ACT_GELU, aux_out=z1, ldaux=F))
             hn = ws.get(f"h{i + 1}" if save else f"h{(i + 1) % 2 + 1}", (M, d), dt)
             if self.has_lora:
                 t_2 = ws.get("t_2" + sfx, (M, r), dt)
-                ops.gemm_nt(m, W[k + ".A_fc2"], t_2, self._ep(alpha=s, alpha_cols=r))
+                self._lora_down(m, W[k + ".A_fc2"], t_2, i, ("fc2",))
                 ops.gemm_nt(m, W[k + ".w2"], hn, self._ep(bias=W[k + ".b2"], residual=hm, ldr=d), a2=t_2, w2=W[k + ".B_fc2"], k2=r)
             else:
                 ops.gemm_nt(m, W[k + ".w2"], hn, self._ep(bias=W[k + ".b2"], residual=hm, ldr=d))
@@ -448,6 +525,7 @@ class WhisperEEGEngine:
             hd = h3
         return hd
 
+    @_on_device
     def forward_loss(self, x: torch.Tensor, labels: Optional[torch.Tensor] = None, decoder_input_ids: Optional[torch.Tensor] = None,
                      aug: Optional[dict] = None, save: bool = True, logits_dtype: Optional[torch.dtype] = None,
                      ce_grad_scale: Optional[float] = None):
@@ -497,6 +575,7 @@ class WhisperEEGEngine:
         return loss, logits.view(B, L, dm.Vp)[:, :, :dm.vocab], enc
 
     # ------------------------------------------------------------------ backward
+    @_on_device
     def backward(self, grad_scale: float = 1.0):
         """Gradients of the mean token cross-entropy w.r.t. the trainable set into self.grad (flat fp32).
         Must follow forward_loss(..., labels=..., save=True).  Mirrors autograd through utils/load_model.py:976-1070 with
@@ -505,7 +584,7 @@ class WhisperEEGEngine:
         d, S, T, F, r, H = dm.d_model, dm.max_source_positions, dm.T, dm.enc_ffn, dm.lora_r, dm.enc_heads
         B, L = self._B, self._L
         M, ML = B * S, B * L
-        s = dm.lora_scale
+        s = dm.lora_scale / (1.0 - self._drop_p)         # dt' = alpha' g B (the 1/(1-p) of the dropped branch input lives here)
         self.grad.zero_()
         # ---- loss -> logits (in place) -> decoder output
         logits = ws.bufs["logits"]
@@ -578,8 +657,9 @@ class WhisperEEGEngine:
                 dt2 = ws.get("dt_r", (M, r), dt)
                 ops.gemm_nt(dh, W[k + ".B_fc2_t"], dt2, self._ep(alpha=s, alpha_cols=r))
                 ops.gemm_tn(dh, g("t_2"), G("fc2", "B"), r, 1)
-                ops.gemm_tn(g("m"), dt2, G("fc2", "A"), 1, F)
+                self._lora_da(g("m"), dt2, i, ("fc2",))
                 ops.gemm_nt(dh, W[k + ".w2_t"], dz1, self._ep(act=ACT_DGELU, aux_in=g("z1"), ldaux=F), a2=dt2, w2=W[k + ".A_fc2_t"], k2=r)
+                self._lora_fix(dz1, dt2, W[k + ".A_fc2_t"], i, ("fc2",), z=g("z1"))
             else:
                 ops.gemm_nt(dh, W[k + ".w2_t"], dz1, self._ep(act=ACT_DGELU, aux_in=g("z1"), ldaux=F))
             # fc1
@@ -588,8 +668,9 @@ class WhisperEEGEngine:
                 dt1 = ws.get("dt_r", (M, r), dt)
                 ops.gemm_nt(dz1, W[k + ".B_fc1_t"], dt1, self._ep(alpha=s, alpha_cols=r))
                 ops.gemm_tn(dz1, g("t_1"), G("fc1", "B"), r, 1)
-                ops.gemm_tn(g("u2"), dt1, G("fc1", "A"), 1, d)
+                self._lora_da(g("u2"), dt1, i, ("fc1",))
                 ops.gemm_nt(dz1, W[k + ".w1_t"], du2, self._ep(), a2=dt1, w2=W[k + ".A_fc1_t"], k2=r)
+                self._lora_fix(du2, dt1, W[k + ".A_fc1_t"], i, ("fc1",))
             else:
                 ops.gemm_nt(dz1, W[k + ".w1_t"], du2, self._ep())
             dhm = ws.get("dh_b", (M, d), dt)
@@ -600,8 +681,9 @@ class WhisperEEGEngine:
                 dto = ws.get("dt_r", (M, r), dt)
                 ops.gemm_nt(dhm, W[k + ".B_out_proj_t"], dto, self._ep(alpha=s, alpha_cols=r))
                 ops.gemm_tn(dhm, g("t_o"), G("out_proj", "B"), r, 1)
-                ops.gemm_tn(g("o"), dto, G("out_proj", "A"), 1, d)
+                self._lora_da(g("o"), dto, i, ("out_proj",))
                 ops.gemm_nt(dhm, W[k + ".wo_t"], do, self._ep(), a2=dto, w2=W[k + ".A_out_proj_t"], k2=r)
+                self._lora_fix(do, dto, W[k + ".A_out_proj_t"], i, ("out_proj",))
             else:
                 ops.gemm_nt(dhm, W[k + ".wo_t"], do, self._ep())
             # attention
@@ -620,8 +702,9 @@ class WhisperEEGEngine:
                                 self._ep(alpha=s * sc, alpha_cols=r))
                     ops.gemm_tn(dqkv[:, gi * d:(gi + 1) * d], t_qkv[:, gi * r:(gi + 1) * r], G(tname, "B"), r, 1, alpha=sc)
                 # dA for q,k,v in one launch: the three (r,d) gradients are contiguous = one (3r, d) matrix
-                ops.gemm_tn(g("u1"), dtq, G("q_proj", "A"), 1, d)
+                self._lora_da(g("u1"), dtq, i, ("q_proj", "k_proj", "v_proj"))
                 ops.gemm_nt(dqkv, W[k + ".wqkv_t"], du1, self._ep(), a2=dtq, w2=W[k + ".A_qkv_t"], k2=3 * r)
+                self._lora_fix(du1, dtq, W[k + ".A_qkv_t"], i, ("q_proj", "k_proj", "v_proj"))
             else:
                 ops.gemm_nt(dqkv, W[k + ".wqkv_t"], du1, self._ep())
             ops.layernorm_bwd(du1, self._saved_h[i], W[k + ".ln1.g"], g("mean1"), g("rstd1"), dh, dres=dhm)
@@ -659,6 +742,7 @@ class WhisperEEGEngine:
         ops.conv_weight_unpack_grad(dwt, self.trainable_grad(name + ".weight"))
 
     # ------------------------------------------------------------------ optimizer
+    @_on_device
     def optimizer_step(self, lr: float, max_grad_norm: float = 1.0, betas=(0.9, 0.999), eps: float = 1e-8,
                        weight_decay: float = 0.0, grad_scale: float = 1.0):
         """clip_grad_norm_(max_grad_norm) + AdamW over the flat buffer (HF trainer.py:2493,1760; finetune.py:236-247).
@@ -671,6 +755,7 @@ class WhisperEEGEngine:
         self._packed = False
         return self.sumsq
 
+    @_on_device
     def train_step(self, x, labels, lr: float, aug: Optional[dict] = None, all_reduce=None, use_graph: bool = True):
         """One Trainer.training_step + optimizer step.  `all_reduce(flat_grad)` is the data-parallel hook.
 
@@ -685,6 +770,7 @@ class WhisperEEGEngine:
                 and labels.is_cuda and labels.is_contiguous() and labels.dtype == torch.long):
             loss = self._fwd_bwd_graph(x, labels, aug)
         if loss is None:
+            self._advance_seed()
             self.pack_trainable()
             loss, _, _ = self.forward_loss(x, labels, aug=aug, save=True, ce_grad_scale=1.0)
             self.backward()
@@ -693,12 +779,16 @@ class WhisperEEGEngine:
         self.optimizer_step(lr)
         return loss
 
+    def _advance_seed(self):
+        if self.lora_dropout > 0.0 and self.training and self.has_lora:
+            ops.seed_advance(self.drop_seed)
+
     def _fwd_bwd_graph(self, x, labels, aug):
         """Replay (or capture) the graph of pack_trainable + forward_loss + backward for these buffers; None = run eagerly."""
         from . import _abi
         akey = tuple(sorted((k, v.data_ptr() if torch.is_tensor(v) else v) for k, v in (aug or {}).items()))
         key = (x.data_ptr(), tuple(x.shape), x.dtype, labels.data_ptr(), tuple(labels.shape), akey)
-        stamp = (self.ws.gen, self._weights_version)
+        stamp = (self.ws.gen, self._weights_version, self.lora_dropout, self.training)
         graphs = self.__dict__.setdefault("_train_graphs", {})
         ent = graphs.get(key)
         if ent is not None and ent[0] is not None and ent[3] == stamp:
@@ -717,6 +807,7 @@ class WhisperEEGEngine:
         g = torch.cuda.CUDAGraph()
         try:
             with torch.cuda.graph(g, capture_error_mode="thread_local"):   # loader threads may pin memory meanwhile
+                self._advance_seed()
                 self.pack_trainable()
                 loss, _, _ = self.forward_loss(x, labels, aug=aug, save=True, ce_grad_scale=1.0)
                 self.backward()
@@ -729,7 +820,7 @@ class WhisperEEGEngine:
             self._packed = False
             return None
         n = sum(_abi.counters().values()) - before
-        if (self.ws.gen, self._weights_version) != stamp:   # the capture itself allocated: do not trust it
+        if (self.ws.gen, self._weights_version, self.lora_dropout, self.training) != stamp:   # the capture itself allocated: do not trust it
             graphs.pop(key, None)
             return None
         graphs[key] = (g, loss, n, stamp)
@@ -795,6 +886,7 @@ class WhisperEEGEngine:
         ops.gemm_nt(y_last, W["dec.E"], logits, self._ep(out_dtype=ops.ns_dtype(logits)), N=dm.vocab, M=B, K=d)
 
     # ------------------------------------------------------------------ beam search (evaluation.py:370-385)
+    @_on_device
     @torch.no_grad()
     def beam_search(self, x: torch.Tensor, max_length: int, num_beams: int = 5, repetition_penalty: float = 1.0,
                     no_repeat_ngram_size: int = 0, prompt: Optional[torch.Tensor] = None, aug: Optional[dict] = None,
@@ -853,6 +945,7 @@ class WhisperEEGEngine:
         return out[:, L0:].contiguous()
 
     # ------------------------------------------------------------------ greedy decode with KV cache
+    @_on_device
     @torch.no_grad()
     def greedy(self, x: torch.Tensor, max_length: int, prompt: Optional[torch.Tensor] = None, aug: Optional[dict] = None,
                use_graphs: bool = False) -> torch.Tensor:

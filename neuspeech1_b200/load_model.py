@@ -243,7 +243,9 @@ class WhisperEEGForConditionalGeneration(nn.Module):
                 self.dims = ModelDims(**{**self.dims.__dict__, "eeg_ch": stem_ch})
             if lora is not None and self._lora_cfg is not None:
                 self.dims = ModelDims(**{**self.dims.__dict__, "lora_r": self._lora_cfg["r"], "lora_alpha": self._lora_cfg["lora_alpha"]})
-            self._eng = WhisperEEGEngine(self.dims, params, lora, dtype=self.compute_dtype, device=self.device_)
+            drop = float((self._lora_cfg or {}).get("lora_dropout", 0.0)) if lora is not None else 0.0
+            self._eng = WhisperEEGEngine(self.dims, params, lora, dtype=self.compute_dtype, device=self.device_, lora_dropout=drop,
+                                         dropout_seed=int(torch.initial_seed()) & 0xFFFFFFFF)
             self._alias_trainables()
         return self._eng
 
@@ -270,7 +272,13 @@ class WhisperEEGForConditionalGeneration(nn.Module):
             self._trainable_params.append(p)
 
     def _sync_trainables_to_engine(self):
-        self._eng._packed = False       # parameters may have been updated by an external optimizer
+        """An external optimizer (HF Trainer's AdamW) updates the aliased flat master buffer in place: the engine's bf16 LoRA
+        copies / packed stem taps are stale then.  Detected through the Parameters' version counters, so evaluation and
+        generate() right after optimizer.step() never run one step behind."""
+        ver = tuple(p._version for p in self._trainable_params)
+        if ver != getattr(self, "_trainable_versions", None):
+            self._trainable_versions = ver
+            self._eng._packed = False
 
     def _stem_swapped(self):
         self._eng = None
@@ -290,13 +298,14 @@ class WhisperEEGForConditionalGeneration(nn.Module):
     def forward(self, input_features=None, labels=None, decoder_input_ids=None, return_dict=True, **unused):
         if decoder_input_ids is None and labels is None:
             raise ValueError("You have to specify either decoder_input_ids or decoder_inputs_embeds")   # utils/load_model.py:613-614
-        self._engine()
+        self._engine().training = self.training          # nn.Dropout semantics: the LoRA-branch dropout is off under model.eval()
         x = input_features.to(self.device_)
         train_params = self._trainable_params if torch.is_grad_enabled() else []
         need_grad = labels is not None and torch.is_grad_enabled() and any(p.requires_grad for p in train_params)
         if need_grad:
             loss, logits, enc = _HotPath.apply(self, x, labels, decoder_input_ids, *train_params)
         else:
+            self._sync_trainables_to_engine()
             with torch.no_grad():
                 loss, logits, enc = self._eng.forward_loss(x, labels, decoder_input_ids=decoder_input_ids, save=False)
                 loss = loss.clone() if loss is not None else None
@@ -306,6 +315,7 @@ class WhisperEEGForConditionalGeneration(nn.Module):
         """Fused Trainer.training_step + clip + AdamW (HF trainer.py:1867-1934, finetune.py:231-253) without autograd.
         use_graph: see WhisperEEGEngine.train_step (CUDA-graph replay when the same input buffers come back)."""
         eng = self._engine()
+        eng.training = True
         loss = eng.train_step(input_features, labels, lr=lr, aug=aug, all_reduce=all_reduce, use_graph=use_graph)
         return Seq2SeqLMOutput(loss=loss)
 

@@ -5,8 +5,8 @@ to the module tree at finetune.py:194-212, so that parameter names match PEFT ch
     <module>.base_layer.weight / <module>.lora_A.default.weight (r,in) / <module>.lora_B.default.weight (out,r)
     model.encoder.conv1.modules_to_save.default.* (trainable copy) and .original_module.* (frozen)
 The forward arithmetic  y = base(x) + (alpha/r) * B(A(dropout(x)))  runs fused in the tcgen05 GEMM epilogue path
-(engine.py); these modules only own the fp32 master parameters.  lora_dropout is accepted for API parity and must be 0
-for bit-parity runs (the engine applies no dropout on the LoRA branch yet -- listed in DESIGN.md).
+(engine.py); these modules only own the fp32 master parameters.  lora_dropout (finetune.py:210: 0.05) is applied by the engine
+in training mode as a counter-hash keep mask on the LoRA-branch input (csrc/ns_lora.cu); `model.eval()` switches it off.
 """
 from __future__ import annotations
 
@@ -79,10 +79,6 @@ def lora_inject(model: nn.Module, r: int = 32, lora_alpha: int = 64, lora_dropou
                 target_modules: Optional[Iterable[str]] = None, modules_to_save: Optional[Iterable[str]] = None,
                 state: Optional[Dict[str, torch.Tensor]] = None):
     """In-place equivalent of get_peft_model for the reference's configuration (finetune.py:194-212)."""
-    if lora_dropout > 0:
-        import warnings
-        warnings.warn(f"neuspeech1_b200: lora_dropout={lora_dropout} is recorded but NOT applied by the B200 engine yet "
-                      "(the LoRA branch sees the undropped input; DESIGN.md section 6). Training proceeds without it.")
     if target_modules is None:
         target_modules = match_modules_string(model.named_modules(), ["model.encoder"], list(ENC_TARGETS))
     for name in list(target_modules):
@@ -128,29 +124,100 @@ def merge_and_unload(model: nn.Module):
     return model
 
 
+PEFT_PREFIX = "base_model.model."      # PeftModel.base_model (LoraModel) .model (the wrapped WhisperForConditionalGeneration)
+
+
 def adapter_state_dict(model: nn.Module) -> Dict[str, torch.Tensor]:
-    """PEFT-format adapter checkpoint content: LoRA A/B + modules_to_save copies, `base_model.model.` prefixed."""
+    """What PEFT's `get_peft_model_state_dict` puts into `adapter_model.safetensors` / `.bin` (finetune.py:282 `save_pretrained`,
+    utils/callback.py:11-22): LoRA A/B and the modules_to_save copies, keys prefixed `base_model.model.`, with the ADAPTER NAME
+    STRIPPED -- `...q_proj.lora_A.weight` (not `.lora_A.default.weight`) and `...encoder.conv1.0.weight` (not
+    `...conv1.modules_to_save.default.0.weight`).  (PEFT itself is absent from this image: layout restated, SURVEY appendix D.)"""
     out = {}
     for k, v in model.state_dict().items():
-        if ".lora_A." in k or ".lora_B." in k or ".modules_to_save." in k:
-            out["base_model.model." + k] = v.detach().cpu().clone()
+        if ".lora_A." in k or ".lora_B." in k:
+            out[PEFT_PREFIX + k.replace(".default.", ".")] = v.detach().cpu().clone().contiguous()
+        elif ".modules_to_save.default." in k:
+            out[PEFT_PREFIX + k.replace("modules_to_save.default.", "")] = v.detach().cpu().clone().contiguous()
     return out
 
 
-def save_adapter(model: nn.Module, path: str):
-    os.makedirs(path, exist_ok=True)
-    torch.save(adapter_state_dict(model), os.path.join(path, "adapter_model.bin"))
+def _adapter_config(model: nn.Module) -> Dict:
+    cfg = model._lora_cfg or {}
+    targets = [n for n, m in model.named_modules() if isinstance(m, LoraLinear)]
+    saves = [n for n, m in model.named_modules() if isinstance(m, ModulesToSaveWrapper)]
+    return {"peft_type": "LORA", "task_type": None, "base_model_name_or_path": getattr(model, "name_or_path", None),
+            "r": cfg.get("r", 32), "lora_alpha": cfg.get("lora_alpha", 64), "lora_dropout": cfg.get("lora_dropout", 0.0),
+            "bias": "none", "fan_in_fan_out": False, "inference_mode": True, "init_lora_weights": True,
+            "target_modules": targets,                 # full module names, as finetune.py:194-202 passes them
+            "modules_to_save": saves}
+
+
+def save_adapter(model: nn.Module, path: str, safe_serialization: bool = True):
+    """`PeftModel.save_pretrained(path)`: adapter_config.json + adapter_model.safetensors (or .bin for PEFT < 0.7 readers)."""
     import json
-    json.dump({"peft_type": "LORA", **(model._lora_cfg or {}), "target_modules": list(ENC_TARGETS),
-               "modules_to_save": ["model.encoder.conv1", "model.encoder.conv2"]}, open(os.path.join(path, "adapter_config.json"), "w"))
+    os.makedirs(path, exist_ok=True)
+    sd = adapter_state_dict(model)
+    if safe_serialization:
+        from safetensors.torch import save_file
+        save_file(sd, os.path.join(path, "adapter_model.safetensors"), metadata={"format": "pt"})
+    else:
+        torch.save(sd, os.path.join(path, "adapter_model.bin"))
+    json.dump(_adapter_config(model), open(os.path.join(path, "adapter_config.json"), "w"), indent=2)
 
 
-def load_adapter(model: nn.Module, path: str):
-    sd = torch.load(os.path.join(path, "adapter_model.bin"), map_location="cpu", weights_only=True)
+def _own_key(k: str, own: Dict[str, torch.Tensor]) -> str:
+    """Map a checkpoint key (PEFT's stripped layout, or this package's round-1 `.default.` layout) to a parameter name here."""
+    if k.startswith(PEFT_PREFIX):
+        k = k[len(PEFT_PREFIX):]
+    if k in own:
+        return k
+    if ".lora_A." in k or ".lora_B." in k:
+        if ".default." not in k:
+            k = k.replace(".lora_A.", ".lora_A.default.").replace(".lora_B.", ".lora_B.default.")
+        return k
+    # modules_to_save: `<module>.<rest>` -> `<module>.modules_to_save.default.<rest>` for the wrapped module that prefixes the key
+    parts = k.split(".")
+    for cut in range(len(parts) - 1, 0, -1):
+        cand = ".".join(parts[:cut]) + ".modules_to_save.default." + ".".join(parts[cut:])
+        if cand in own:
+            return cand
+    return k
+
+
+def load_adapter(model: nn.Module, path: str, is_trainable: bool = True):
+    """`PeftModel.from_pretrained(model, path)` (finetune.py:182-185, evaluation.py:88, merge_lora.py:43): reads PEFT's on-disk
+    layout (adapter_config.json + adapter_model.safetensors | adapter_model.bin); wraps the target linears / modules_to_save first
+    when the model is still plain.  Raises KeyError on a tensor that has no home (never drops one silently)."""
+    import json
+    cfg_path = os.path.join(path, "adapter_config.json")
+    cfg = json.load(open(cfg_path)) if os.path.exists(cfg_path) else {}
+    if cfg.get("peft_type", "LORA") != "LORA":
+        raise NotImplementedError(f"adapter type {cfg.get('peft_type')}: load_adapter reads plain LoRA adapters "
+                                  "(AdaLoRA state lives in neuspeech1_b200.adalora)")
+    if not any(isinstance(m, LoraLinear) for m in model.modules()):
+        tm = cfg.get("target_modules")
+        if isinstance(tm, (list, tuple)) and tm and all("." not in t for t in tm):   # suffix list: the reference adapts the encoder only
+            tm = match_modules_string(model.named_modules(), ["model.encoder"], list(tm))
+        lora_inject(model, r=cfg.get("r", 32), lora_alpha=cfg.get("lora_alpha", 64), lora_dropout=cfg.get("lora_dropout", 0.0),
+                    target_modules=tm, modules_to_save=cfg.get("modules_to_save") or ())
+    st = os.path.join(path, "adapter_model.safetensors")
+    if os.path.exists(st):
+        from safetensors.torch import load_file
+        sd = load_file(st)
+    else:
+        sd = torch.load(os.path.join(path, "adapter_model.bin"), map_location="cpu", weights_only=True)
     own = dict(model.named_parameters())
     for k, v in sd.items():
-        k = k[len("base_model.model."):] if k.startswith("base_model.model.") else k
-        own[k].data.copy_(v)
+        name = _own_key(k, own)
+        if name not in own:
+            raise KeyError(f"adapter tensor {k!r} matches no parameter of the model (looked for {name!r})")
+        if own[name].shape != v.shape:
+            raise ValueError(f"adapter tensor {k!r}: shape {tuple(v.shape)} vs parameter {tuple(own[name].shape)}")
+        own[name].data.copy_(v)
+    if not is_trainable:
+        for m in model.modules():
+            if isinstance(m, (LoraLinear, ModulesToSaveWrapper)):
+                m.requires_grad_(False)
     if hasattr(model, "invalidate_engine"):
         model.invalidate_engine()
     return model

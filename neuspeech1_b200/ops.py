@@ -238,6 +238,49 @@ def dgelu_mul(dy, z, dz):
     return dz
 
 
+def seed_advance(seed: torch.Tensor):
+    """seed (1,) int32 device word <- lowbias32(seed + 0x9E3779B9): one new dropout mask per (replayed) training step."""
+    _call("ns_seed_advance", (0, 0), _p(seed), _stream())
+
+
+def _salts(salts):
+    return (C.c_uint * 3)(*([int(s) & 0xFFFFFFFF for s in salts] + [0] * (3 - len(salts))))
+
+
+def dropout_apply(x, y, seed, salt: int, p: float):
+    """y = x with the dropped elements of module `salt` zeroed (unscaled); x, y 2-D views (rows, cols)."""
+    _call("ns_dropout_apply", (0, 2.0 * x.numel() * x.element_size()), ns_dtype(x), x.shape[0], x.shape[1], _p(x), x.stride(0), _p(y),
+          y.stride(0), _p(seed), int(salt) & 0xFFFFFFFF, float(p), _stream())
+    return y
+
+
+def lora_down(x, A, t, alpha: float, G: int = 1, seed=None, salts=(), p: float = 0.0):
+    """t[M, G*r] = alpha * (x . keep_g) A_g^T, A = stacked (G*r, K) bf16."""
+    M, K = x.shape
+    r = A.shape[0] // G
+    _call("ns_lora_down", (2.0 * M * K * G * r, float(x.numel() * 2)), M, K, G, r, _p(x), x.stride(0), _p(A), A.stride(0), _p(t), t.stride(0),
+          float(alpha), _p(seed), _salts(salts) if p > 0 else None, float(p), _stream())
+    return t
+
+
+def lora_da(x, dt, dA, G: int = 1, seed=None, salts=(), p: float = 0.0):
+    """dA[G*r, K] (fp32) += dt_g^T (x . keep_g)."""
+    M, K = x.shape
+    r = dA.shape[0] // G
+    _call("ns_lora_da", (2.0 * M * K * G * r, float(x.numel() * 2)), M, K, G, r, _p(x), x.stride(0), _p(dt), dt.stride(0), _p(dA), dA.stride(0),
+          _p(seed), _salts(salts) if p > 0 else None, float(p), _stream())
+    return dA
+
+
+def lora_dx_fix(dx, dt, At, seed, salts, p: float, G: int = 1, z=None):
+    """dx -= dropped_g * (dt_g . At[k, g]) (* gelu'(z)), in place (see include/neuspeech_b200.h)."""
+    M, K = dx.shape
+    r = At.shape[1] // G
+    _call("ns_lora_dx_fix", (0, 2.0 * dx.numel() * dx.element_size()), ns_dtype(dx), M, K, G, r, _p(dx), dx.stride(0), _p(dt), dt.stride(0),
+          _p(At), At.stride(0), _p(seed), _salts(salts), float(p), _p(z), z.stride(0) if z is not None else 0, _stream())
+    return dx
+
+
 def sumsq(g, out):
     _call("ns_sumsq", (0, 0), g.numel(), _p(g), _p(out), _stream())
 

@@ -81,6 +81,10 @@ class DeviceBatchLoader:
         self.stream = torch.cuda.Stream(device=self.device) if self.cuda else None
         self.free = [torch.cuda.Event() for _ in range(2)] if self.cuda else None     # device side: the step that read the slot was launched
         self.h2d_done = [torch.cuda.Event() for _ in range(2)] if self.cuda else None # host side: the pinned slot may be refilled
+        # host-side handshake per pinned slot: the consumer hands the slot back only AFTER it has enqueued the copy out of it and
+        # recorded h2d_done (an event that was never recorded, or was recorded for an older batch, synchronises at once)
+        self.host_free = [threading.Semaphore(1) for _ in range(2)]
+        self._consumer_delay = 0.0                     # tests: sleep this long between q.get() and the copy (widens the old race)
 
     def __len__(self) -> int:
         n = len(self.order)
@@ -90,8 +94,9 @@ class DeviceBatchLoader:
         """Host side of one batch (worker thread): read, select channels, crop to 30 s, copy into the pinned buffer."""
         lens, labels = [], []
         xh = self.x_host[slot]
+        self.host_free[slot].acquire()                  # the consumer has issued the copy of the batch staged here two batches ago
         if self.cuda:
-            self.h2d_done[slot].synchronize()           # the copy of the batch staged here two batches ago has left the pinned buffer
+            self.h2d_done[slot].synchronize()           # ... and that copy has left the pinned buffer
         for b, i in enumerate(idxs):
             it = self.items[i]
             s = it["array"] if "array" in it else np.load(it["path"])
@@ -118,11 +123,18 @@ class DeviceBatchLoader:
                 q.put((k, idxs, self._stage(idxs, k & 1)))
             q.put(None)
 
+        for sem in self.host_free:                      # a previous, abandoned iteration may have left a slot taken
+            while sem.acquire(blocking=False):
+                pass
+            sem.release()
         th = threading.Thread(target=worker, daemon=True)
         th.start()
         prev_slot = None
         while True:
             got = q.get()
+            if self._consumer_delay:
+                import time
+                time.sleep(self._consumer_delay)
             if prev_slot is not None:
                 self.release(prev_slot)                 # the consumer launched its step on the previous batch before asking again
             if got is None:
@@ -146,6 +158,7 @@ class DeviceBatchLoader:
                 xd[:nb].copy_(self.x_host[slot][:nb])
                 yd[:nb].copy_(lab)
                 plan = self.aug.plan(shapes, self.device, static=self.aug_static[slot])
+            self.host_free[slot].release()              # copy enqueued, h2d_done recorded: the worker may wait on it and refill
             # fixed-shape views of the persistent buffers: the label width is the widest batch the loader may ever yield
             prev_slot = slot
             yield xd[:nb], yd[:nb], plan, slot

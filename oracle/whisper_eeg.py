@@ -161,29 +161,49 @@ def init_lora(dims: Dims, seed: int = 1, b_std: float = 0.0) -> Dict[str, Tensor
 def trainable_names(P: Dict[str, Tensor], lora: Dict[str, Tensor]) -> List[str]:
     """Trainable set of finetune.py:176-212: LoRA A/B + modules_to_save conv1 (stem A,B) and conv2 (stem C)."""
     stem = [k for k in P if k.startswith("model.encoder.conv1.") or k.startswith("model.encoder.conv2.")]
-    return sorted(lora.keys()) + sorted(stem)
+    return sorted(k for k in lora if not k.startswith("__")) + sorted(stem)
 
 
 # --------------------------------------------------------------------------- forward pieces
 
-def lora_dropout_keep(seed: int, name: str, rows: int, cols: int, p: float) -> Tensor:
-    """Keep mask (rows, cols) of the LoRA-branch dropout of module `name` (finetune.py:210 lora_dropout=0.05): a counter hash
-    of (seed ^ crc32(name), row, column) so that a device kernel can recompute any element without storing the mask --
-        x = row * 0x9E3779B1 ^ col * 0x85EBCA77 ^ module_seed;  x ^= x >> 16;  x *= 0x7FEB352D;  x ^= x >> 15;
-        x *= 0x846CA68B;  x ^= x >> 16;            (all mod 2^32)        dropped  <=>  x < floor(p * 2^32)
-    This is the specification the planned B200 kernels are to follow; PEFT itself draws from torch's
-    generator, so with dropout on parity with the reference is statistical by construction."""
-    import zlib
+def lowbias32(x):
+    """The 32-bit mixer of the dropout mask / seed sequence (numpy uint64 arithmetic, masked to 32 bits)."""
     import numpy as np
     m = np.uint64(0xFFFFFFFF)
-    ms = np.uint64((seed ^ zlib.crc32(name.encode())) & 0xFFFFFFFF)
-    r = np.arange(rows, dtype=np.uint64)[:, None]
-    c = np.arange(cols, dtype=np.uint64)[None, :]
-    x = ((r * np.uint64(0x9E3779B1)) ^ (c * np.uint64(0x85EBCA77)) ^ ms) & m
+    x = x & m
     x ^= x >> np.uint64(16); x = (x * np.uint64(0x7FEB352D)) & m
     x ^= x >> np.uint64(15); x = (x * np.uint64(0x846CA68B)) & m
     x ^= x >> np.uint64(16)
-    return torch.from_numpy(x >= np.uint64(int(p * 4294967296.0)))
+    return x
+
+
+def next_dropout_seed(seed: int) -> int:
+    """The step-seed sequence of the training step: seed <- lowbias32(seed + 0x9E3779B9)  (ns_seed_advance)."""
+    import numpy as np
+    return int(lowbias32(np.uint64((seed + 0x9E3779B9) & 0xFFFFFFFF)))
+
+
+def module_salt(name: str) -> int:
+    import zlib
+    return zlib.crc32(name.encode()) & 0xFFFFFFFF
+
+
+def lora_dropout_keep(seed: int, name: str, rows: int, cols: int, p: float) -> Tensor:
+    """Keep mask (rows, cols) of the LoRA-branch dropout of module `name` (finetune.py:210 lora_dropout=0.05; PEFT lora.Linear
+    applies nn.Dropout to the LoRA branch input only).  A counter hash, so that the device kernels recompute any element
+    without storing the mask (include/neuspeech_b200.h, csrc/ns_lora.cu):
+        w = lowbias32(((row >> 1) * 0x9E3779B1) ^ (col * 0x85EBCA77) ^ seed ^ crc32(name))      (all mod 2^32)
+        half = (row & 1) ? w >> 16 : w & 0xFFFF ;      dropped  <=>  half < round(p * 65536)
+    One 32-bit word serves the two rows of a row pair.  PEFT itself draws from torch's generator, so with dropout on, parity
+    with the reference is statistical by construction; between this oracle and the CUDA path it is exact."""
+    import numpy as np
+    ms = np.uint64((seed ^ module_salt(name)) & 0xFFFFFFFF)
+    r = np.arange(rows, dtype=np.uint64)[:, None]
+    c = np.arange(cols, dtype=np.uint64)[None, :]
+    w = lowbias32((((r >> np.uint64(1)) * np.uint64(0x9E3779B1)) ^ (c * np.uint64(0x85EBCA77)) ^ ms))
+    half = np.where((r & np.uint64(1)) == 1, w >> np.uint64(16), w & np.uint64(0xFFFF))
+    thr = min(65535, int(p * 65536.0 + 0.5))
+    return torch.from_numpy(half >= np.uint64(thr))
 
 
 def linear(x: Tensor, P, name: str, lora=None, scale: float = 0.0) -> Tensor:
@@ -195,7 +215,7 @@ def linear(x: Tensor, P, name: str, lora=None, scale: float = 0.0) -> Tensor:
             pdrop, seed = lora["__dropout__"]
             if pdrop > 0:
                 keep = lora_dropout_keep(seed, name, x.numel() // x.shape[-1], x.shape[-1], pdrop).view(x.shape)
-                xin = x * keep.to(x.dtype) / (1.0 - pdrop)
+                xin = x * keep.to(device=x.device, dtype=x.dtype) / (1.0 - pdrop)
         y = y + scale * F.linear(F.linear(xin, a), b)
     return y
 
@@ -221,7 +241,7 @@ def mha(q: Tensor, k: Tensor, v: Tensor, heads: int, causal: bool = False) -> Te
     w = q @ k.transpose(2, 3)
     if causal:
         off = Lk - Lq
-        m = torch.ones(Lq, Lk, dtype=torch.bool).tril(off)
+        m = torch.ones(Lq, Lk, dtype=torch.bool, device=q.device).tril(off)
         w = w.masked_fill(~m, float("-inf"))
     w = w.softmax(dim=-1)
     return (w @ v).transpose(1, 2).reshape(B, Lq, d)
@@ -375,7 +395,7 @@ def clip_and_adamw(params: Dict[str, Tensor], g: Dict[str, Tensor], st: AdamWSta
 
 def train_step(x, labels, P, dims, lora, st: AdamWState, lr: float = 1e-3):
     loss, g, _ = grads(x, labels, P, dims, lora)
-    both = {**{k: lora[k] for k in lora}, **{k: P[k] for k in g if k in P}}
+    both = {**{k: lora[k] for k in lora if not k.startswith("__")}, **{k: P[k] for k in g if k in P}}
     norm = clip_and_adamw(both, g, st, lr)
     return float(loss), norm
 

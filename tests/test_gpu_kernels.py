@@ -490,3 +490,92 @@ def test_aug_noise_statistics():
     got_db = 10 * torch.log10((x ** 2).mean(-1) / (resid ** 2).mean(-1))
     assert float((got_db - snr_db).abs().max()) < 0.5
     assert abs(float(resid.mean())) < 0.01
+
+
+# ------------------------------------------------------------------------------------------------ LoRA branch: dropout + rank-r products
+def _keep(seed, name, rows, cols, p):
+    from oracle import whisper_eeg as O
+    return O.lora_dropout_keep(seed, name, rows, cols, p).to(DEV)
+
+
+def _seed_tensor(seed):
+    return torch.tensor([seed - (1 << 32) if seed >= (1 << 31) else seed], dtype=torch.int32, device=DEV)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_dropout_mask_bit_exact_and_seed_sequence(dtype):
+    """ns_dropout_apply == oracle.lora_dropout_keep element for element (odd row count, ragged leading dimension), and
+    ns_seed_advance follows oracle.next_dropout_seed."""
+    from oracle import whisper_eeg as O
+    rows, cols, p = 1501, 520, 0.05
+    x = rnd(rows, cols + 8, dtype=dtype, seed=1)[:, :cols]
+    x = torch.where(x == 0, torch.ones_like(x), x)
+    for seed, name in ((7, "model.encoder.layers.0.fc1"), (0xDEADBEEF, "model.encoder.layers.3.self_attn.q_proj")):
+        y = torch.empty(rows, cols, dtype=dtype, device=DEV)
+        ops.dropout_apply(x, y, _seed_tensor(seed), O.module_salt(name), p)
+        keep = _keep(seed, name, rows, cols, p)
+        assert torch.equal(y != 0, keep)
+        assert torch.equal(y[keep], x[keep])
+        assert abs(float(keep.float().mean()) - 0.95) < 2e-3
+    s = _seed_tensor(12345)
+    ref = 12345
+    for _ in range(3):
+        ops.seed_advance(s)
+        ref = O.next_dropout_seed(ref)
+        assert (int(s.item()) & 0xFFFFFFFF) == ref
+
+
+LORA_CASES = [(3000, 512, 1, 32), (3000, 512, 3, 32), (1000, 2048, 1, 32), (333, 128, 1, 8), (333, 128, 3, 8), (640, 256, 3, 16),
+              (96001, 512, 3, 32)]
+
+
+@pytest.mark.parametrize("p", [0.0, 0.05])
+@pytest.mark.parametrize("M,K,G,r", LORA_CASES)
+def test_lora_down_and_da(M, K, G, r, p):
+    """t = alpha (x . keep_g) A_g^T and dA_g += dt_g^T (x . keep_g) against fp32 torch on the same bf16 operands and the oracle's
+    mask (3 stacked adapters = q/k/v on one input; an odd / ragged row count exercises the row-pair and tile tails)."""
+    from oracle import whisper_eeg as O
+    names = [f"model.encoder.layers.2.self_attn.{n}" for n in ("q_proj", "k_proj", "v_proj")][:G]
+    salts = [O.module_salt(n) for n in names]
+    seed = 424242
+    x = rnd(M, K, dtype=torch.bfloat16, seed=2)
+    A = rnd(G * r, K, dtype=torch.bfloat16, scale=K ** -0.5, seed=3)
+    dt = rnd(M, G * r, dtype=torch.bfloat16, scale=0.1, seed=4)
+    t = torch.empty(M, G * r, dtype=torch.bfloat16, device=DEV)
+    alpha = 2.0 / (1.0 - p)
+    ops.lora_down(x, A, t, alpha, G, _seed_tensor(seed), salts, p)
+    dA = torch.full((G * r, K), 0.25, dtype=torch.float32, device=DEV)
+    ops.lora_da(x, dt, dA, G, _seed_tensor(seed), salts, p)
+    for g in range(G):
+        xm = x.float() * (_keep(seed, names[g], M, K, p).float() if p > 0 else 1.0)
+        t_ref = alpha * xm @ A[g * r:(g + 1) * r].float().t()
+        assert rel(t[:, g * r:(g + 1) * r].float(), t_ref) < 1e-2, (g, rel(t[:, g * r:(g + 1) * r].float(), t_ref))
+        dA_ref = dt[:, g * r:(g + 1) * r].float().t() @ xm + 0.25
+        assert rel(dA[g * r:(g + 1) * r], dA_ref) < 2e-3, (g, rel(dA[g * r:(g + 1) * r], dA_ref))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("M,K,G,r,with_z", [(1001, 512, 3, 32, False), (700, 2048, 1, 32, True), (333, 128, 1, 8, False)])
+def test_lora_dx_fix(M, K, G, r, with_z, dtype):
+    """dx - dropped_g * (dt_g . A_g[:, k]) * gelu'(z): the sparse correction after the input-gradient GEMM."""
+    from oracle import whisper_eeg as O
+    names = [f"model.encoder.layers.1.self_attn.{n}" for n in ("q_proj", "k_proj", "v_proj")][:G]
+    seed, p = 99, 0.05
+    dx0 = rnd(M, K, dtype=dtype, seed=5)
+    dt = rnd(M, G * r, dtype=dtype, scale=0.3, seed=6)
+    At = rnd(K, G * r, dtype=dtype, scale=0.2, seed=7)
+    z = rnd(M, K, dtype=dtype, seed=8) if with_z else None
+    dx = dx0.clone()
+    ops.lora_dx_fix(dx, dt, At, _seed_tensor(seed), [O.module_salt(n) for n in names], p, G, z)
+    ref = dx0.float()
+    for g in range(G):
+        drop = ~_keep(seed, names[g], M, K, p)
+        full = dt[:, g * r:(g + 1) * r].float() @ At[:, g * r:(g + 1) * r].float().t()
+        if with_z:
+            full = full * gelu_grad(z.float())
+        ref = ref - full * drop.float()
+    changed = (dx.float() != dx0.float())
+    assert float(changed.float().mean()) < 0.06 * G + 0.01
+    assert rel(dx.float(), ref) < (1e-2 if dtype == torch.bfloat16 else 1e-5)
+    sel = (ref != dx0.float())
+    assert rel(dx.float()[sel], ref[sel]) < (2e-2 if dtype == torch.bfloat16 else 1e-4)

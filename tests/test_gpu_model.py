@@ -75,7 +75,7 @@ def test_bf16_forward_loss_grads(dims_name):
     c = _abi.counters()
     assert c["gemm_tcgen05"] > 0, c
     errs = {name: rel(eng.trainable_grad(name), g) for name, g in grads_ref.items()}
-    bad = {k: v for k, v in errs.items() if v > 6e-2}
+    bad = {k: v for k, v in errs.items() if v > 2e-2}          # LoRA/stem grads at the bf16 tolerance of the states
     assert not bad, bad
     # whole-gradient direction: cosine over the flat trainable vector
     ref_flat = torch.cat([grads_ref[n].reshape(-1) for n in sorted(grads_ref)])
@@ -107,9 +107,8 @@ def test_wrong_length_raises():
         eng.encode(x[..., :-4].to(DEV))
 
 
-def test_whisper_base_bf16_against_golden_and_oracle(golden_dir):
-    """Config #1 shape (Whisper-base, eeg_ch=208): bf16 CUDA path vs the reference-pinned golden (no LoRA) and vs the oracle
-    with LoRA (loss + a few gradients)."""
+def test_whisper_base_bf16_against_golden(golden_dir):
+    """Config #1 shape (Whisper-base, eeg_ch=208): bf16 CUDA path vs the reference-pinned golden (no LoRA)."""
     dims = O.WHISPER_BASE
     P = O.init_params(dims, seed=0)
     x, labels = O.synthetic_batch(dims, B=2, L=32, seed=1)
@@ -121,6 +120,39 @@ def test_whisper_base_bf16_against_golden_and_oracle(golden_dir):
     ids = eng.greedy(x.to(DEV), max_length=13)
     agree = float((ids.cpu() == torch.from_numpy(g["greedy"])).float().mean())
     assert agree >= 0.75, agree          # bf16: identity is only required in fp32 (north_star); random-init margins are small
+
+
+def test_whisper_base_bf16_lora_fwd_bwd_at_the_benchmark_shape():
+    """The shape bench.py times (Whisper-base, eeg_ch=208, S=1500, LoRA r=32 with non-zero B, L=32), B=3, bf16: the CTA-pair
+    GEMMs, the fused attention forward/backward, the split-K weight gradients and the stem run TOGETHER here.  Encoder states
+    and loss within 2e-2 of the fp32 oracle, EVERY LoRA / stem gradient within 2e-2, and the same again after the
+    step has gone through `train_step`'s CUDA-graph capture and replay (lr = 0: the weights stand still)."""
+    dims = O.WHISPER_BASE
+    P, lora, eng = build(dims, torch.bfloat16)
+    x, labels = O.synthetic_batch(dims, B=3, L=32, seed=1)
+    loss_ref, grads_ref, enc_ref = O.grads(x, labels, P, dims, lora)
+    xd, ld = x.to(DEV), labels.to(DEV)
+    _abi.reset_counters()
+    loss, logits, enc = eng.forward_loss(xd, ld)
+    assert rel(enc, enc_ref) < 2e-2, rel(enc, enc_ref)
+    assert abs(float(loss) - float(loss_ref)) < 2e-2 * float(loss_ref)
+    eng.backward()
+    c = _abi.counters()
+    assert c["gemm_tcgen05"] > 0 and c["attn_tc"] > 0 and c["wgrad_tcgen05"] > 0, c
+
+    def check(tag):
+        errs = {n: rel(eng.trainable_grad(n), g) for n, g in grads_ref.items()}
+        bad = {k: v for k, v in errs.items() if v > 2e-2}
+        assert not bad, (tag, bad)
+        assert len(errs) == 6 * 6 * 2 + 6
+
+    check("eager")
+    before = eng.graph_launches
+    for i in range(4):                                            # eager, capture, replay, replay
+        l = float(eng.train_step(xd, ld, lr=0.0))
+        assert abs(l - float(loss_ref)) < 2e-2 * float(loss_ref), (i, l)
+    assert eng.graph_launches > before
+    check("graph replay")
 
 
 def test_whisper_base_fp32_greedy_identical(golden_dir):
@@ -203,9 +235,9 @@ def test_adalora_adapter_matches_oracle_autograd(dtype):
     t = 1e-3 if dtype == torch.float32 else 2e-2
     assert abs(float(loss) - float(ref)) < t * abs(float(ref)), (float(loss), float(ref))
     for key in ad.entries:
-        assert rel(ad.param_grad(key).cpu(), master[key].grad) < (2e-3 if dtype == torch.float32 else 6e-2), key
+        assert rel(ad.param_grad(key).cpu(), master[key].grad) < (2e-3 if dtype == torch.float32 else 2e-2), key
     for k in stem_names:
-        assert rel(ad.engine.trainable_grad(k).cpu(), Pg[k].grad) < (2e-3 if dtype == torch.float32 else 6e-2), k
+        assert rel(ad.engine.trainable_grad(k).cpu(), Pg[k].grad) < (2e-3 if dtype == torch.float32 else 2e-2), k
     l0 = float(ad.train_step(x.to(DEV), labels.to(DEV), lr=1e-3))
     for _ in range(3):
         l1 = float(ad.train_step(x.to(DEV), labels.to(DEV), lr=1e-3))
@@ -335,7 +367,7 @@ def test_schoffelen_channels_and_large_v3_widths(dims_name, dtype):
     loss, logits, enc = eng.forward_loss(x.to(DEV), labels.to(DEV))
     eng.backward()
     torch.cuda.synchronize()
-    tol_e, tol_g = (1e-3, 2e-3) if dtype == torch.float32 else (2e-2, 6e-2)
+    tol_e, tol_g = (1e-3, 2e-3) if dtype == torch.float32 else (2e-2, 2e-2)
     assert rel(enc, enc_ref) < tol_e, rel(enc, enc_ref)
     assert abs(float(loss) - float(loss_ref)) < tol_e * float(loss_ref)
     worst = max(rel(eng.trainable_grad(n), g) for n, g in grads_ref.items())
@@ -343,3 +375,112 @@ def test_schoffelen_channels_and_large_v3_widths(dims_name, dtype):
     if dtype == torch.bfloat16:
         c = _abi.counters()
         assert c["gemm_tcgen05"] > 0 and c["attn_tc"] > 0, c
+
+
+def test_config4_c273_merged_greedy_ids_identical_fp32():
+    """BASELINE.json configs[3] (evaluation decode: Whisper-base, eeg_ch=273, merged LoRA weights, greedy with KV cache) as a
+    parity test at a real batch: B=8, 36 positions, fp32 -> token ids identical to the oracle's greedy loop, with and without
+    the 4-token decoder prompt of evaluation.py:357-359, launched eagerly and through the per-position CUDA graphs."""
+    from neuspeech1_b200.weights import merge_lora
+    dims = O.Dims(eeg_ch=273)
+    P0 = O.init_params(dims, seed=0, std=0.1)                     # std 0.1: the ids depend on the input (0.02 gives one sequence)
+    lora = O.init_lora(dims, seed=1, b_std=0.05)
+    P = merge_lora(P0, lora, dims.lora_scale)                     # evaluation.py:88-89 merge_and_unload
+    B, Tmax = 8, 36
+    x, _ = O.synthetic_batch(dims, B=B, L=8, seed=4)
+    eng = WhisperEEGEngine(ModelDims.from_any(dims), P, None, dtype=torch.float32, device=DEV)
+    ref = O.greedy_decode(x, P, dims, max_length=Tmax)
+    # merged weights == unmerged adapter (same function): the oracle with the LoRA branch gives the same ids
+    ref_unmerged = O.greedy_decode(x[:2], P0, dims, max_length=12, lora=lora)
+    assert torch.equal(ref[:2, :11], ref_unmerged)
+    got = eng.greedy(x.to(DEV), max_length=Tmax).cpu()
+    assert got.shape == (B, Tmax - 1) and torch.equal(got[:, :ref.shape[1]], ref)
+    g = torch.Generator().manual_seed(9)
+    prompt = torch.cat([torch.full((B, 1), dims.decoder_start_token_id), torch.randint(0, 50000, (B, 3), generator=g)], dim=1)
+    refp = O.greedy_decode(x, P, dims, max_length=Tmax, prompt=prompt)
+    gotp = eng.greedy(x.to(DEV), max_length=Tmax, prompt=prompt).cpu()
+    assert gotp.shape == (B, Tmax - 4) and torch.equal(gotp[:, :refp.shape[1]], refp)
+    for _ in range(3):                                            # capture, re-capture, replay
+        assert torch.equal(eng.greedy(x.to(DEV), max_length=Tmax, use_graphs=True).cpu(), got)
+        assert torch.equal(eng.greedy(x.to(DEV), max_length=Tmax, prompt=prompt, use_graphs=True).cpu(), gotp)
+    assert len({tuple(r.tolist()) for r in ref}) > 1              # the samples do decode differently
+
+
+# ------------------------------------------------------------------------------------------------ LoRA-branch dropout (finetune.py:210)
+@pytest.mark.parametrize("dims_name,dtype,p", [("TINY", torch.float32, 0.05), ("MID", torch.float32, 0.1), ("TINY", torch.bfloat16, 0.05),
+                                               ("MID", torch.bfloat16, 0.05), ("SCHOF", torch.bfloat16, 0.1)])
+def test_lora_dropout_forward_backward_matches_oracle(dims_name, dtype, p):
+    """LoraConfig(lora_dropout=0.05) (0.1: the AdaLoRA branch): training forward + all gradients with the LoRA-branch input
+    dropped by the counter-hash mask, against oracle autograd with the same mask (`lora["__dropout__"] = (p, seed)`): fp32
+    <= 1e-3 / 2e-3, bf16 <= 2e-2.  Evaluation mode (`training = False`) is the undropped function."""
+    dims = {"TINY": O.TINY, "MID": MID, "SCHOF": SCHOF}[dims_name]
+    seed = 0x9E3779B9
+    P = O.init_params(dims, seed=0)
+    lora = O.init_lora(dims, seed=1, b_std=0.05)
+    eng = WhisperEEGEngine(ModelDims.from_any(dims), P, lora, dtype=dtype, device=DEV, lora_dropout=p, dropout_seed=seed)
+    x, labels = O.synthetic_batch(dims, B=3, L=8, seed=1)
+    lo = {**lora, "__dropout__": (p, seed)}
+    loss_ref, grads_ref, enc_ref = O.grads(x, labels, P, dims, lo)
+    loss_nodrop, _, enc_nodrop = O.grads(x, labels, P, dims, lora)
+    assert rel(enc_ref, enc_nodrop) > 1e-3                       # the mask does change the function
+    te, tg = (1e-3, 2e-3) if dtype == torch.float32 else (2e-2, 2e-2)
+    loss, _, enc = eng.forward_loss(x.to(DEV), labels.to(DEV))
+    assert rel(enc, enc_ref) < te, rel(enc, enc_ref)
+    assert abs(float(loss) - float(loss_ref)) < te * float(loss_ref)
+    if dtype == torch.float32:
+        assert rel(enc, enc_nodrop) > 5 * rel(enc, enc_ref)
+    eng.backward()
+    errs = {n: rel(eng.trainable_grad(n), g) for n, g in grads_ref.items()}
+    bad = {k: v for k, v in errs.items() if v > tg}
+    assert not bad, bad
+    eng.training = False                                          # model.eval(): nn.Dropout is the identity
+    loss_e, _, enc_e = eng.forward_loss(x.to(DEV), labels.to(DEV))
+    assert rel(enc_e, enc_nodrop) < te and abs(float(loss_e) - float(loss_nodrop)) < te * float(loss_nodrop)
+
+
+def test_train_steps_with_lora_dropout_match_oracle_fp32():
+    """Three optimizer steps with lora_dropout = 0.05: the device seed sequence (ns_seed_advance at the start of every step)
+    follows oracle.next_dropout_seed, losses and weights track the oracle's training step with the same masks."""
+    dims = O.TINY
+    P, lora, _ = build(dims, torch.float32)
+    eng = WhisperEEGEngine(ModelDims.from_any(dims), P, lora, dtype=torch.float32, device=DEV, lora_dropout=0.05, dropout_seed=77)
+    P = {k: v.clone() for k, v in P.items()}; lora = {k: v.clone() for k, v in lora.items()}
+    st = O.AdamWState()
+    seed = 77
+    for step in range(3):
+        x, labels = O.synthetic_batch(dims, B=2, L=6, seed=10 + step)
+        seed = O.next_dropout_seed(seed)
+        lora["__dropout__"] = (0.05, seed)
+        loss_ref, _ = O.train_step(x, labels, P, dims, lora, st, lr=1e-3)
+        loss = eng.train_step(x.to(DEV), labels.to(DEV), lr=1e-3)
+        assert abs(float(loss) - loss_ref) < 2e-3 * loss_ref, (step, float(loss), loss_ref)
+        assert (int(eng.drop_seed.item()) & 0xFFFFFFFF) == seed
+    for name in O.trainable_names(P, lora):
+        ref = lora[name] if name in lora else P[name]
+        assert rel(eng.trainable(name), ref) < 2e-3, name
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_train_step_graph_replay_with_dropout_draws_new_masks(dtype):
+    """The captured training step advances the dropout seed ON THE DEVICE: graph replays and launch-by-launch stepping see the
+    same seed sequence, hence the same masks, losses and weights; consecutive steps on the same batch see different masks."""
+    P = O.init_params(MID, seed=0)
+    lora = O.init_lora(MID, seed=1, b_std=0.05)
+    x, labels = O.synthetic_batch(MID, B=3, L=8, seed=1)
+    xd, ld = x.to(DEV), labels.to(DEV)
+    mk = lambda: WhisperEEGEngine(ModelDims.from_any(MID), P, lora, dtype=dtype, device=DEV, lora_dropout=0.1, dropout_seed=5)
+    e_graph, e_eager = mk(), mk()
+    tol_l = 1e-2 if dtype == torch.bfloat16 else 1e-5
+    losses = []
+    for i in range(5):
+        lg = float(e_graph.train_step(xd, ld, lr=0.0))
+        le = float(e_eager.train_step(xd, ld, lr=0.0, use_graph=False))
+        assert abs(lg - le) <= tol_l * abs(le), (i, lg, le)
+        assert int(e_graph.drop_seed.item()) == int(e_eager.drop_seed.item())
+        losses.append(le)
+    assert e_graph.graph_launches > 0
+    assert len({round(l, 6) for l in losses}) == len(losses)      # lr = 0, same batch: only the mask differs between steps
+    seed = 5
+    for _ in range(5):
+        seed = O.next_dropout_seed(seed)
+    assert (int(e_graph.drop_seed.item()) & 0xFFFFFFFF) == seed

@@ -50,3 +50,19 @@ def test_loader_double_buffers_and_lengths():
     assert seen == [0, 1] and ptrs[0] != ptrs[1]
     ptrs2 = [(x.data_ptr(), y.data_ptr(), aug["n"].data_ptr(), aug["grid"].data_ptr()) for x, y, aug, _ in ld]
     assert ptrs2 == ptrs                                    # a second epoch lands in the same buffers
+
+
+def test_loader_slow_consumer_never_sees_a_later_batch():
+    """Stress of the pinned-slot handshake: with a consumer that dawdles between taking a batch off the queue and copying it, the
+    worker used to refill the slot with batch k+2 first (batch k then carried batch k+2's samples with batch k's labels)."""
+    rng = np.random.RandomState(1)
+    items = [{"array": np.full((4, 20 + i), float(i + 1), dtype=np.float32), "path": f"/x/other/{i}.npy", "labels": [i]}
+             for i in range(16)]
+    ld = DeviceBatchLoader(items, batch_size=2, modal_ch=4, device="cpu", augment_configs={}, max_duration=0.5, sample_rate=200,
+                           max_label_len=2)
+    ld._consumer_delay = 0.05
+    for epoch in range(2):
+        for k, (x, y, aug, slot) in enumerate(ld):
+            for b in range(2):
+                i = 2 * k + b
+                assert float(x[b, 0, 0]) == float(i + 1) and int(y[b, 0]) == i and int(aug["n"][b]) == 20 + i, (epoch, k, b)

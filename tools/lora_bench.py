@@ -1,0 +1,63 @@
+"""Times of the LoRA side kernels at the benchmark shapes (M = 64*1500 rows) next to the GEMM-kernel passes they replace.
+Developer tool: python tools/lora_bench.py -> gpurun_out/lora_bench.json"""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from neuspeech1_b200 import ops
+
+DEV = torch.device("cuda")
+M, r = 96000, 32
+
+
+def timeit(fn, n=20, flush=None):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(n):
+        if flush is not None:
+            flush.zero_()
+        s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record()
+        torch.cuda.synchronize()
+        tot += s.elapsed_time(e)
+    return tot / n * 1000.0   # us
+
+
+def main():
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    seed = torch.tensor([1234], dtype=torch.int32, device=DEV)
+    out = {}
+    for K, G in ((512, 1), (512, 3), (2048, 1)):
+        x = torch.randn(M, K, device=DEV).to(torch.bfloat16)
+        A = (torch.randn(G * r, K, device=DEV) * K ** -0.5).to(torch.bfloat16)
+        At = A.t().contiguous()
+        t = torch.empty(M, G * r, dtype=torch.bfloat16, device=DEV)
+        dt = (torch.randn(M, G * r, device=DEV) * 0.1).to(torch.bfloat16)
+        dA = torch.zeros(G * r, K, dtype=torch.float32, device=DEV)
+        dx = torch.randn(M, K, device=DEV).to(torch.bfloat16)
+        z = torch.randn(M, K, device=DEV).to(torch.bfloat16)
+        salts = [11, 22, 33][:G]
+        key = f"K{K}_G{G}"
+        out[key] = {
+            "gemm_nt_thin": timeit(lambda: ops.gemm_nt(x, A, t, ops.epilogue(alpha=2.0, alpha_cols=G * r)), flush=flush),
+            "lora_down_p0": timeit(lambda: ops.lora_down(x, A, t, 2.0, G), flush=flush),
+            "lora_down_p05": timeit(lambda: ops.lora_down(x, A, t, 2.0, G, seed, salts, 0.05), flush=flush),
+            "gemm_tn_dA": timeit(lambda: ops.gemm_tn(x, dt, dA, 1, K), flush=flush),
+            "lora_da_p0": timeit(lambda: ops.lora_da(x, dt, dA, G), flush=flush),
+            "lora_da_p05": timeit(lambda: ops.lora_da(x, dt, dA, G, seed, salts, 0.05), flush=flush),
+            "dx_fix_p05": timeit(lambda: ops.lora_dx_fix(dx, dt, At, seed, salts, 0.05, G), flush=flush),
+            "dx_fix_p05_gelu": timeit(lambda: ops.lora_dx_fix(dx, dt, At, seed, salts, 0.05, G, z), flush=flush),
+            "x_MB": M * K * 2 / 1e6,
+        }
+        print(key, {k: round(v, 1) for k, v in out[key].items()})
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(out, open("gpurun_out/lora_bench.json", "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
