@@ -108,8 +108,9 @@ def synthetic_host_batch(dims, B, L, seed):
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline (oracle)
-def cpu_train_steps(B, L, steps, warmup, eeg_ch=208, threads=None):
-    """Times oracle.train_step (fwd + loss + autograd bwd + clip + AdamW, LoRA r=32) on the host.  -> (samples/s, cores)"""
+def cpu_train_steps(B, L, steps, warmup, eeg_ch=208, threads=None, lora_dropout=0.05):
+    """Times oracle.train_step (fwd + loss + autograd bwd + clip + AdamW, LoRA r=32, LoRA-branch dropout) on the host.
+    -> (samples/s, cores, s/step)"""
     from oracle import whisper_eeg as O
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
@@ -118,32 +119,41 @@ def cpu_train_steps(B, L, steps, warmup, eeg_ch=208, threads=None):
     lora = O.init_lora(dims, seed=1)
     st = O.AdamWState()
     x, labels = O.synthetic_batch(dims, B=B, L=L, seed=1)
-    for _ in range(warmup):
+    seed = 1
+
+    def one():
+        nonlocal seed
+        if lora_dropout > 0:
+            seed = O.next_dropout_seed(seed)
+            lora["__dropout__"] = (lora_dropout, seed)
         O.train_step(x, labels, P, dims, lora, st, lr=1e-3)
+
+    for _ in range(warmup):
+        one()
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.train_step(x, labels, P, dims, lora, st, lr=1e-3)
+        one()
     dt = time.perf_counter() - t0
     return B * steps / dt, threads, dt / max(steps, 1)
 
 
-def workload_name(eeg_ch, B, L):
+def workload_name(eeg_ch, B, L, p=0.05):
     return (f"Gwilliams-shaped LoRA fine-tune step: Whisper-base, eeg_ch={eeg_ch}, B={B}/GPU, L={L}, "
-            f"LoRA r=32 on 36 encoder linears + 3 stem convs, augmentation1 (identity) pass")
+            f"LoRA r=32 alpha=64 lora_dropout={p:g} on 36 encoder linears + 3 stem convs, augmentation1 (identity) pass")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B = 2                                                   # bounded sample of the B=64 workload
+    B = 4                                                   # bounded sample of the B=64 workload (about 1 s of host time per step)
     warm = min(args.warmup, 1)
-    sps, cores, sec = cpu_train_steps(B, args.labels, args.steps, warm, args.eeg_ch)
+    sps, cores, sec = cpu_train_steps(B, args.labels, args.steps, warm, args.eeg_ch, lora_dropout=args.lora_dropout)
     line = {
         "impl": "reference", "metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.eeg_ch, args.batch, args.labels), "parallelism": "host cores",
+        "config": {"workload": workload_name(args.eeg_ch, args.batch, args.labels, args.lora_dropout), "parallelism": "host cores",
                    "sample": f"each step is a bounded sample of that workload: B={B} instead of {args.batch} per step"},
         "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} training steps of B={B} (oracle port of the reference path; PEFT/accelerate absent)"},
@@ -172,7 +182,8 @@ def run_ours(args):
     dims = ModelDims(eeg_ch=args.eeg_ch)
     B, L = args.batch, args.labels
     model = WhisperEEGForConditionalGeneration(dims, random_params(dims, seed=0), random_lora(dims, seed=1, b_std=0.01),
-                                               dtype=torch.bfloat16, device=dev)
+                                               dtype=torch.bfloat16, device=dev, lora_dropout=args.lora_dropout)
+    model.train()
     eng = model.engine
     x_host, labels_host = synthetic_host_batch(dims, B, L, seed=100 + rank)
     x_host = x_host.pin_memory(); labels_host = labels_host.pin_memory()
@@ -294,14 +305,14 @@ def run_ours(args):
         shares = {k: round(v["ms"] / tot, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])[:8]}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            sps, cores, sec = cpu_train_steps(4, L, 2, 1, args.eeg_ch)
+            sps, cores, sec = cpu_train_steps(4, L, 2, 1, args.eeg_ch, lora_dropout=args.lora_dropout)
             cpu = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
                    "sample": "2 training steps of B=4 after 1 warm-up (oracle port of the reference path, fp32, all host threads)"}
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": workload_name(args.eeg_ch, B, L),
+            "config": {"workload": workload_name(args.eeg_ch, B, L, args.lora_dropout),
                        "parallelism": f"dp{world}", "l2": "inputs and activations per step (>10 GB) exceed the 126 MB L2",
                        "launch": "pack + forward + backward replayed as one CUDA graph per input buffer, all-reduce and optimizer launched eagerly"},
             "clocks": clocks, "gpu_launches": launches,
@@ -331,6 +342,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--labels", type=int, default=32)
     ap.add_argument("--eeg-ch", dest="eeg_ch", type=int, default=208)
+    ap.add_argument("--lora-dropout", dest="lora_dropout", type=float, default=0.05)     # finetune.py:210
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None)
     args = ap.parse_args()

@@ -179,29 +179,35 @@ int ns_dgelu_mul(int dtype, long long n, const void* dy, const void* z, void* dz
 
 /* ---- LoRA branch: dropout and the rank-r products around it.
  * Replaces PEFT lora.Linear's  result += lora_B(lora_A(lora_dropout(x))) * scaling  (finetune.py:206-212: lora_dropout 0.05,
- * 0.1 for AdaLoRA) and its autograd backward.  The keep mask is a counter hash of (row pair, column, *seed ^ salt) that every
- * kernel recomputes (never stored): element (row, col) is dropped iff the 16-bit half (row & 1) of
- *   lowbias32(((row >> 1) * 0x9E3779B1) ^ (col * 0x85EBCA77) ^ *seed ^ salt)   is  < round(p * 65536).
- * `seed` is a DEVICE word (one per training step, advanced on the device so a replayed CUDA graph draws a new mask); `salt` /
- * `salts[g]` identify the module (crc32 of its name).  The kernels use the UNSCALED masked input: the caller folds 1/(1-p)
- * into alpha (t) and into dt.  G = number of adapters stacked on the same input (1, or 3 for q/k/v), r = LoRA rank. */
+ * 0.1 for AdaLoRA) and its autograd backward.  The keep mask of a module is a counter-based bit plane, drawn once per step:
+ *   bits[g][(rows+1)/2][(cols+15)/16] (32-bit words); bit 2*(col % 16) + (row & 1) of word (g, rp = row >> 1, w = col / 16) set
+ *   <=> element (row, col) of adapter g is dropped.  The 32 flags of a word are drawn together from 16 hashed words
+ *   R_i = lowbias32((rp * 0x9E3779B1) ^ (w * 0x85EBCA77) ^ (i * 0xC2B2AE35) ^ *seed ^ salts[g]), combined along the binary
+ *   expansion of thr = round(p * 65536), least significant bit first: D = bit_i(thr) ? (D | R_i) : (D & R_i)  (P(flag) = thr/65536).
+ * `seed` is a DEVICE word (one per training step, advanced on the device so a replayed CUDA graph draws a new mask); `salts[g]`
+ * identify the modules (crc32 of their names).  The kernels use the UNSCALED masked input: the caller folds 1/(1-p) into alpha
+ * (t) and into dt.  G = adapters stacked on the same input (1, or 3 for q/k/v), r = rank. */
 int ns_seed_advance(unsigned int* seed, void* stream);                          /* *seed = lowbias32(*seed + 0x9E3779B9) */
-/* y = x with dropped elements zeroed (materialised masked input: fp32 parity mode and tests) */
+long long ns_dropout_bits_words(long long rows, int cols);                      /* words per adapter of the bit plane */
+int ns_dropout_bits(long long rows, int cols, int G, const unsigned int* seed, const unsigned int* salts, float p,
+                    unsigned int* bits, void* stream);
+/* y = x with the dropped elements of ONE adapter's plane zeroed (materialised masked input: fp32 parity mode and tests) */
 int ns_dropout_apply(int dtype, long long rows, int cols, const void* x, long long ldx, void* y, long long ldy,
-                     const unsigned int* seed, unsigned int salt, float p, void* stream);
-/* t[M, G*r] = alpha * (x . keep_g) * A_g^T for the G stacked adapters A = [A_0; ..; A_{G-1}] (G*r, K), bf16 storage.  p == 0
- * (evaluation, parity runs): plain t = alpha * x * A^T.  HBM-bound: x is read once. */
+                     const unsigned int* bits, void* stream);
+/* t[M, G*r] = alpha * (x . keep_g) * A_g^T for the G stacked adapters A = [A_0; ..; A_{G-1}] (G*r, K), bf16 storage.
+ * bits == NULL (evaluation, parity runs): plain t = alpha * x * A^T.  HBM-bound: x is read once. */
 int ns_lora_down(long long M, int K, int G, int r, const void* x, long long ldx, const void* A, long long lda, void* t,
-                 long long ldt, float alpha, const unsigned int* seed, const unsigned int* salts, float p, void* stream);
-/* dA[G*r, K] (fp32, row stride ldg) += dt_g^T * (x . keep_g): gradient of the stacked A_g, bf16 activations, x read once */
+                 long long ldt, float alpha, const unsigned int* bits, void* stream);
+/* dA[G*r, K] (fp32, row stride ldg) += dt_g^T * (x . keep_g): gradient of the stacked A_g, bf16 activations, x read once.
+ * With dx != NULL the same pass also removes the dropped terms from the input gradient,
+ *   dx[m,k] -= sum_g dropped_g(m,k) * (dt_g[m,:] . At[k, g*r:(g+1)*r]) (* gelu'(z[m,k]) when z != NULL),
+ * which the input-gradient GEMM added as a K-segment as if nothing had been dropped (At = A^T, (K, ldat >= G*r), bf16). */
 int ns_lora_da(long long M, int K, int G, int r, const void* x, long long ldx, const void* dt, long long lddt, float* dA,
-               long long ldg, const unsigned int* seed, const unsigned int* salts, float p, void* stream);
-/* dx[m,k] -= sum_g dropped_g(m,k) * (dt_g[m,:] . At[k, g*r:(g+1)*r]) (* gelu'(z[m,k]) when z != NULL), in place: the input-
- * gradient GEMM carries the LoRA product as a K-segment as if nothing had been dropped; this removes the dropped terms.
- * At = A^T (K, ldat >= G*r) in the activation dtype. */
+               long long ldg, const unsigned int* bits, void* dx, long long lddx, const void* At, long long ldat, const void* z,
+               long long ldz, void* stream);
+/* the dx correction alone, any storage dtype (fp32 parity mode) */
 int ns_lora_dx_fix(int dtype, long long rows, int K, int G, int r, void* dx, long long lddx, const void* dt, long long lddt,
-                   const void* At, long long ldat, const unsigned int* seed, const unsigned int* salts, float p, const void* z,
-                   long long ldz, void* stream);
+                   const void* At, long long ldat, const unsigned int* bits, const void* z, long long ldz, void* stream);
 
 /* ---- fused clip + AdamW over one flat fp32 parameter/gradient buffer (HF trainer.py:2493,1760; finetune.py:236-247).
  *  Step 1: ns_sumsq accumulates sum(g^2) into *out (caller zeroes).  Step 2: ns_adamw_clip reads *sumsq on device,

@@ -76,15 +76,17 @@ SIGNATURES = {
     "ns_add": [c_i, c_ll, c_vp, c_vp, c_vp, c_vp],
     "ns_dgelu_mul": [c_i, c_ll, c_vp, c_vp, c_vp, c_vp],
     "ns_seed_advance": [c_vp, c_vp],
-    "ns_dropout_apply": [c_i, c_ll, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, C.c_uint, c_f, c_vp],
-    "ns_lora_down": [c_ll, c_i, c_i, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_f, c_vp, c_vp, c_f, c_vp],
-    "ns_lora_da": [c_ll, c_i, c_i, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_vp, c_f, c_vp],
-    "ns_lora_dx_fix": [c_i, c_ll, c_i, c_i, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_vp, c_f, c_vp, c_ll, c_vp],
+    "ns_dropout_apply": [c_i, c_ll, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, c_vp],
+    "ns_lora_down": [c_ll, c_i, c_i, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_f, c_vp, c_vp],
+    "ns_lora_da": [c_ll, c_i, c_i, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp],
+    "ns_lora_dx_fix": [c_i, c_ll, c_i, c_i, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_vp, c_ll, c_vp],
+    "ns_dropout_bits_words": [c_ll, c_i],
+    "ns_dropout_bits": [c_ll, c_i, c_i, c_vp, c_vp, c_f, c_vp, c_vp],
     "ns_sumsq": [c_ll, c_vp, c_vp, c_vp],
     "ns_adamw_clip": [c_ll, c_vp, c_vp, c_vp, c_vp, c_vp, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_vp],
 }
 
-RESTYPES = {"ns_attention_bwd_workspace_bytes": c_ll}      # everything else returns an int status
+RESTYPES = {"ns_attention_bwd_workspace_bytes": c_ll, "ns_dropout_bits_words": c_ll}      # everything else returns an int status
 
 _lib = None
 

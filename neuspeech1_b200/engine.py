@@ -199,42 +199,54 @@ class WhisperEEGEngine:
         import zlib
         return [zlib.crc32(lora_module_name(layer, t).encode()) & 0xFFFFFFFF for t in targets]
 
+    def _fast_lora(self, K: int, G: int) -> bool:
+        r = self.dims.lora_r
+        return self.use_lora_kernels and K % 64 == 0 and r in (8, 16, 32) and G * r * (2 * K + 64) <= 220 * 1024
+
+    def _bits(self, layer: int, targets, M: int, K: int) -> torch.Tensor:
+        """Bit plane of the dropped elements of `targets`: drawn in the forward, kept for the backward consumers."""
+        return self.ws.get(f"dropbits.{layer}.{targets[0]}", (len(targets), (M + 1) // 2, (K + 15) // 16), torch.int32)
+
     def _lora_down(self, x: torch.Tensor, A: torch.Tensor, t: torch.Tensor, layer: int, targets):
         """t[:, g*r:(g+1)*r] = alpha' * dropout_g(x) A_g^T for the adapters `targets` stacked in A (PEFT lora.Linear:
-        lora_A(lora_dropout(x)) * scaling); alpha' = (alpha/r) / (1 - p)."""
+        lora_A(lora_dropout(x)) * scaling); alpha' = (alpha/r) / (1 - p).  Without dropout this is the thin tcgen05 GEMM; with
+        it the mask is drawn once into a bit plane and (bf16) ns_lora_down applies it on the way from HBM to the MMA."""
         p, r, G = self._drop_p, self.dims.lora_r, len(targets)
         a = self.dims.lora_scale / (1.0 - p)
-        K = x.shape[1]
-        if self.use_lora_kernels and K % 32 == 0 and r in (8, 16, 32) and G * r * (2 * K + 64) <= 220 * 1024:
-            ops.lora_down(x, A, t, a, G, self.drop_seed, self._salts(layer, targets), p)
-        elif p == 0.0:
+        M, K = x.shape
+        if p == 0.0:
             ops.gemm_nt(x, A, t, self._ep(alpha=a, alpha_cols=G * r))
+            return
+        bits = ops.dropout_bits(M, K, self.drop_seed, self._salts(layer, targets), p, self._bits(layer, targets, M, K))
+        if self._fast_lora(K, G):
+            ops.lora_down(x, A, t, a, G, bits)
         else:
             xm = self.ws.get(f"xm.{K}", x.shape, self.dtype)
-            for g, salt in enumerate(self._salts(layer, targets)):
-                ops.dropout_apply(x, xm, self.drop_seed, salt, p)
+            for g in range(G):
+                ops.dropout_apply(x, xm, bits[g])
                 ops.gemm_nt(xm, A[g * r:(g + 1) * r], t[:, g * r:(g + 1) * r], self._ep(alpha=a, alpha_cols=r))
 
-    def _lora_da(self, x: torch.Tensor, dt: torch.Tensor, layer: int, targets):
-        """dA_g += dt_g^T dropout_g(x) into the flat gradient buffer (the A gradients of `targets` are contiguous)."""
+    def _lora_da_fix(self, x: torch.Tensor, dt: torch.Tensor, dx: torch.Tensor, At: torch.Tensor, layer: int, targets,
+                     z: Optional[torch.Tensor] = None):
+        """dA_g += dt_g^T dropout_g(x) into the flat gradient buffer (the A gradients of `targets` are contiguous) and, under
+        dropout, the correction of the input gradient: the GEMM that produced `dx` added dt' A for EVERY element (K-segment);
+        the dropped ones are taken out again (times gelu'(z) where dx went through the GELU backward)."""
         p, r, G = self._drop_p, self.dims.lora_r, len(targets)
-        K = x.shape[1]
+        M, K = x.shape
         off, _ = self.layout.entries[lora_module_name(layer, targets[0]) + ".lora_A.default.weight"]
         gA = self.grad[off: off + G * r * K].view(G * r, K)
-        if self.use_lora_kernels and K % 8 == 0 and r in (8, 16, 32):
-            ops.lora_da(x, dt, gA, G, self.drop_seed, self._salts(layer, targets), p)
-        elif p == 0.0:
+        if p == 0.0:
             ops.gemm_tn(x, dt, gA, 1, K)
+            return
+        bits = self._bits(layer, targets, M, K)
+        if self._fast_lora(K, G):
+            ops.lora_da(x, dt, gA, G, bits, dx=dx, At=At, z=z)
         else:
             xm = self.ws.get(f"xm.{K}", x.shape, self.dtype)
-            for g, salt in enumerate(self._salts(layer, targets)):
-                ops.dropout_apply(x, xm, self.drop_seed, salt, p)
+            for g in range(G):
+                ops.dropout_apply(x, xm, bits[g])
                 ops.gemm_tn(xm, dt[:, g * r:(g + 1) * r], gA[g * r:(g + 1) * r], 1, K)
-
-    def _lora_fix(self, dx: torch.Tensor, dt: torch.Tensor, At: torch.Tensor, layer: int, targets, z: Optional[torch.Tensor] = None):
-        """The input-gradient GEMM added dt' A for every element; take the dropped ones out again (no-op without dropout)."""
-        if self._drop_p > 0.0:
-            ops.lora_dx_fix(dx, dt, At, self.drop_seed, self._salts(layer, targets), self._drop_p, len(targets), z)
+            ops.lora_dx_fix(dx, dt, At, bits, G, z)
 
     # ------------------------------------------------------------------ parameters
     def _c(self, t: torch.Tensor) -> torch.Tensor:
@@ -657,9 +669,8 @@ class WhisperEEGEngine:
                 dt2 = ws.get("dt_r", (M, r), dt)
                 ops.gemm_nt(dh, W[k + ".B_fc2_t"], dt2, self._ep(alpha=s, alpha_cols=r))
                 ops.gemm_tn(dh, g("t_2"), G("fc2", "B"), r, 1)
-                self._lora_da(g("m"), dt2, i, ("fc2",))
                 ops.gemm_nt(dh, W[k + ".w2_t"], dz1, self._ep(act=ACT_DGELU, aux_in=g("z1"), ldaux=F), a2=dt2, w2=W[k + ".A_fc2_t"], k2=r)
-                self._lora_fix(dz1, dt2, W[k + ".A_fc2_t"], i, ("fc2",), z=g("z1"))
+                self._lora_da_fix(g("m"), dt2, dz1, W[k + ".A_fc2_t"], i, ("fc2",), z=g("z1"))
             else:
                 ops.gemm_nt(dh, W[k + ".w2_t"], dz1, self._ep(act=ACT_DGELU, aux_in=g("z1"), ldaux=F))
             # fc1
@@ -668,9 +679,8 @@ class WhisperEEGEngine:
                 dt1 = ws.get("dt_r", (M, r), dt)
                 ops.gemm_nt(dz1, W[k + ".B_fc1_t"], dt1, self._ep(alpha=s, alpha_cols=r))
                 ops.gemm_tn(dz1, g("t_1"), G("fc1", "B"), r, 1)
-                self._lora_da(g("u2"), dt1, i, ("fc1",))
                 ops.gemm_nt(dz1, W[k + ".w1_t"], du2, self._ep(), a2=dt1, w2=W[k + ".A_fc1_t"], k2=r)
-                self._lora_fix(du2, dt1, W[k + ".A_fc1_t"], i, ("fc1",))
+                self._lora_da_fix(g("u2"), dt1, du2, W[k + ".A_fc1_t"], i, ("fc1",))
             else:
                 ops.gemm_nt(dz1, W[k + ".w1_t"], du2, self._ep())
             dhm = ws.get("dh_b", (M, d), dt)
@@ -681,9 +691,8 @@ class WhisperEEGEngine:
                 dto = ws.get("dt_r", (M, r), dt)
                 ops.gemm_nt(dhm, W[k + ".B_out_proj_t"], dto, self._ep(alpha=s, alpha_cols=r))
                 ops.gemm_tn(dhm, g("t_o"), G("out_proj", "B"), r, 1)
-                self._lora_da(g("o"), dto, i, ("out_proj",))
                 ops.gemm_nt(dhm, W[k + ".wo_t"], do, self._ep(), a2=dto, w2=W[k + ".A_out_proj_t"], k2=r)
-                self._lora_fix(do, dto, W[k + ".A_out_proj_t"], i, ("out_proj",))
+                self._lora_da_fix(g("o"), dto, do, W[k + ".A_out_proj_t"], i, ("out_proj",))
             else:
                 ops.gemm_nt(dhm, W[k + ".wo_t"], do, self._ep())
             # attention
@@ -702,9 +711,8 @@ class WhisperEEGEngine:
                                 self._ep(alpha=s * sc, alpha_cols=r))
                     ops.gemm_tn(dqkv[:, gi * d:(gi + 1) * d], t_qkv[:, gi * r:(gi + 1) * r], G(tname, "B"), r, 1, alpha=sc)
                 # dA for q,k,v in one launch: the three (r,d) gradients are contiguous = one (3r, d) matrix
-                self._lora_da(g("u1"), dtq, i, ("q_proj", "k_proj", "v_proj"))
                 ops.gemm_nt(dqkv, W[k + ".wqkv_t"], du1, self._ep(), a2=dtq, w2=W[k + ".A_qkv_t"], k2=3 * r)
-                self._lora_fix(du1, dtq, W[k + ".A_qkv_t"], i, ("q_proj", "k_proj", "v_proj"))
+                self._lora_da_fix(g("u1"), dtq, du1, W[k + ".A_qkv_t"], i, ("q_proj", "k_proj", "v_proj"))
             else:
                 ops.gemm_nt(dqkv, W[k + ".wqkv_t"], du1, self._ep())
             ops.layernorm_bwd(du1, self._saved_h[i], W[k + ".ln1.g"], g("mean1"), g("rstd1"), dh, dres=dhm)

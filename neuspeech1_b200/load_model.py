@@ -152,7 +152,7 @@ class WhisperEEGForConditionalGeneration(nn.Module):
     main_input_name = "input_features"
 
     def __init__(self, dims: ModelDims, params: Optional[Dict[str, torch.Tensor]] = None, lora: Optional[Dict[str, torch.Tensor]] = None,
-                 dtype: torch.dtype = torch.bfloat16, device="cuda"):
+                 dtype: torch.dtype = torch.bfloat16, device="cuda", lora_dropout: float = 0.0):
         super().__init__()
         self.dims = dims
         self.compute_dtype = dtype
@@ -181,7 +181,7 @@ class WhisperEEGForConditionalGeneration(nn.Module):
             p.requires_grad_(True)                                              # modules_to_save (finetune.py:202)
         if lora is not None:
             from .lora import lora_inject
-            lora_inject(self, r=dims.lora_r, lora_alpha=dims.lora_alpha, state=lora)
+            lora_inject(self, r=dims.lora_r, lora_alpha=dims.lora_alpha, lora_dropout=lora_dropout, state=lora)
 
     # ---- construction helpers -------------------------------------------------------------------------------------
     @classmethod

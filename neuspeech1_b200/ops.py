@@ -247,37 +247,49 @@ def _salts(salts):
     return (C.c_uint * 3)(*([int(s) & 0xFFFFFFFF for s in salts] + [0] * (3 - len(salts))))
 
 
-def dropout_apply(x, y, seed, salt: int, p: float):
-    """y = x with the dropped elements of module `salt` zeroed (unscaled); x, y 2-D views (rows, cols)."""
+def dropout_apply(x, y, bits):
+    """y = x with the dropped elements of one adapter's bit plane zeroed (unscaled); x, y 2-D views (rows, cols)."""
     _call("ns_dropout_apply", (0, 2.0 * x.numel() * x.element_size()), ns_dtype(x), x.shape[0], x.shape[1], _p(x), x.stride(0), _p(y),
-          y.stride(0), _p(seed), int(salt) & 0xFFFFFFFF, float(p), _stream())
+          y.stride(0), _p(bits), _stream())
     return y
 
 
-def lora_down(x, A, t, alpha: float, G: int = 1, seed=None, salts=(), p: float = 0.0):
-    """t[M, G*r] = alpha * (x . keep_g) A_g^T, A = stacked (G*r, K) bf16."""
+def dropout_bits_words(rows: int, cols: int) -> int:
+    return ((rows + 1) // 2) * ((cols + 15) // 16)
+
+
+def dropout_bits(rows: int, cols: int, seed, salts, p: float, bits):
+    """bits (G, (rows+1)//2, (cols+15)//16) int32 <- the dropped-element bit plane of the G modules `salts` (hashed once per step)."""
+    _call("ns_dropout_bits", (0, float(bits.numel() * 4)), rows, cols, len(salts), _p(seed), _salts(salts), float(p), _p(bits), _stream())
+    return bits
+
+
+def lora_down(x, A, t, alpha: float, G: int = 1, bits=None):
+    """t[M, G*r] = alpha * (x . keep_g) A_g^T, A = stacked (G*r, K) bf16; bits = dropout_bits(...) or None."""
     M, K = x.shape
     r = A.shape[0] // G
     _call("ns_lora_down", (2.0 * M * K * G * r, float(x.numel() * 2)), M, K, G, r, _p(x), x.stride(0), _p(A), A.stride(0), _p(t), t.stride(0),
-          float(alpha), _p(seed), _salts(salts) if p > 0 else None, float(p), _stream())
+          float(alpha), _p(bits), _stream())
     return t
 
 
-def lora_da(x, dt, dA, G: int = 1, seed=None, salts=(), p: float = 0.0):
-    """dA[G*r, K] (fp32) += dt_g^T (x . keep_g)."""
+def lora_da(x, dt, dA, G: int = 1, bits=None, dx=None, At=None, z=None):
+    """dA[G*r, K] (fp32) += dt_g^T (x . keep_g); with dx (and At = A^T, optionally z) the same pass takes the dropped terms of
+    the LoRA product out of the input gradient (see include/neuspeech_b200.h)."""
     M, K = x.shape
     r = dA.shape[0] // G
-    _call("ns_lora_da", (2.0 * M * K * G * r, float(x.numel() * 2)), M, K, G, r, _p(x), x.stride(0), _p(dt), dt.stride(0), _p(dA), dA.stride(0),
-          _p(seed), _salts(salts) if p > 0 else None, float(p), _stream())
+    _call("ns_lora_da", (2.0 * M * K * G * r * (2 if dx is not None else 1), float(x.numel() * 2)), M, K, G, r, _p(x), x.stride(0), _p(dt),
+          dt.stride(0), _p(dA), dA.stride(0), _p(bits), _p(dx), dx.stride(0) if dx is not None else 0, _p(At),
+          At.stride(0) if At is not None else 0, _p(z), z.stride(0) if z is not None else 0, _stream())
     return dA
 
 
-def lora_dx_fix(dx, dt, At, seed, salts, p: float, G: int = 1, z=None):
-    """dx -= dropped_g * (dt_g . At[k, g]) (* gelu'(z)), in place (see include/neuspeech_b200.h)."""
+def lora_dx_fix(dx, dt, At, bits, G: int = 1, z=None):
+    """dx -= dropped_g * (dt_g . At[k, g]) (* gelu'(z)), in place, any storage dtype."""
     M, K = dx.shape
     r = At.shape[1] // G
     _call("ns_lora_dx_fix", (0, 2.0 * dx.numel() * dx.element_size()), ns_dtype(dx), M, K, G, r, _p(dx), dx.stride(0), _p(dt), dt.stride(0),
-          _p(At), At.stride(0), _p(seed), _salts(salts), float(p), _p(z), z.stride(0) if z is not None else 0, _stream())
+          _p(At), At.stride(0), _p(bits), _p(z), z.stride(0) if z is not None else 0, _stream())
     return dx
 
 

@@ -188,22 +188,40 @@ def module_salt(name: str) -> int:
     return zlib.crc32(name.encode()) & 0xFFFFFFFF
 
 
+def lora_dropout_plane(seed: int, name: str, rows: int, cols: int, p: float):
+    """The dropped-element bit plane of module `name` as the device draws it (include/neuspeech_b200.h, csrc/ns_lora.cu):
+    uint32 array ((rows+1)//2, (cols+15)//16); bit 2*(col % 16) + (row & 1) of word (row >> 1, col // 16) set <=> dropped.
+    The 32 flags of a word come from 16 hashed words R_i = lowbias32((rp * 0x9E3779B1) ^ (w * 0x85EBCA77) ^ (i * 0xC2B2AE35) ^
+    seed ^ crc32(name)) combined along the binary expansion of thr = round(p * 65536), least significant bit first:
+    D = bit_i(thr) ? (D | R_i) : (D & R_i), i.e. flag_b = [U_b < thr] for the 16-bit number U_b made of bit b of R_15..R_0."""
+    import numpy as np
+    m = np.uint64(0xFFFFFFFF)
+    ms = np.uint64((seed ^ module_salt(name)) & 0xFFFFFFFF)
+    rp = np.arange((rows + 1) // 2, dtype=np.uint64)[:, None]
+    w = np.arange((cols + 15) // 16, dtype=np.uint64)[None, :]
+    key = ((rp * np.uint64(0x9E3779B1)) ^ (w * np.uint64(0x85EBCA77)) ^ ms) & m
+    thr = min(65535, int(p * 65536.0 + 0.5))
+    d = np.zeros(key.shape, dtype=np.uint64)
+    for i in range(16):
+        r = lowbias32(key ^ np.uint64((i * 0xC2B2AE35) & 0xFFFFFFFF))
+        d = (d | r) if (thr >> i) & 1 else (d & r)
+    valid = np.clip(cols - 16 * np.arange(d.shape[1]), 0, 16)                # columns that exist in each 16-column block
+    d &= ((np.uint64(1) << (2 * valid).astype(np.uint64)) - np.uint64(1))[None, :]
+    return d.astype(np.uint32)
+
+
 def lora_dropout_keep(seed: int, name: str, rows: int, cols: int, p: float) -> Tensor:
     """Keep mask (rows, cols) of the LoRA-branch dropout of module `name` (finetune.py:210 lora_dropout=0.05; PEFT lora.Linear
-    applies nn.Dropout to the LoRA branch input only).  A counter hash, so that the device kernels recompute any element
-    without storing the mask (include/neuspeech_b200.h, csrc/ns_lora.cu):
-        w = lowbias32(((row >> 1) * 0x9E3779B1) ^ (col * 0x85EBCA77) ^ seed ^ crc32(name))      (all mod 2^32)
-        half = (row & 1) ? w >> 16 : w & 0xFFFF ;      dropped  <=>  half < round(p * 65536)
-    One 32-bit word serves the two rows of a row pair.  PEFT itself draws from torch's generator, so with dropout on, parity
-    with the reference is statistical by construction; between this oracle and the CUDA path it is exact."""
+    applies nn.Dropout to the LoRA branch input only), read off the counter-based bit plane above: P(dropped) = round(p * 65536)
+    / 65536.  PEFT itself draws from torch's generator, so with dropout on, parity with the reference is statistical by
+    construction; between this oracle and the CUDA path it is exact."""
     import numpy as np
-    ms = np.uint64((seed ^ module_salt(name)) & 0xFFFFFFFF)
-    r = np.arange(rows, dtype=np.uint64)[:, None]
-    c = np.arange(cols, dtype=np.uint64)[None, :]
-    w = lowbias32((((r >> np.uint64(1)) * np.uint64(0x9E3779B1)) ^ (c * np.uint64(0x85EBCA77)) ^ ms))
-    half = np.where((r & np.uint64(1)) == 1, w >> np.uint64(16), w & np.uint64(0xFFFF))
-    thr = min(65535, int(p * 65536.0 + 0.5))
-    return torch.from_numpy(half >= np.uint64(thr))
+    plane = lora_dropout_plane(seed, name, rows, cols, p).astype(np.uint64)                 # (pairs, words)
+    sh = (2 * np.arange(16, dtype=np.uint64))[None, None, :]
+    two = (plane[:, :, None] >> sh) & np.uint64(3)                                           # (pairs, words, 16): bit0 even row, bit1 odd row
+    two = two.reshape(plane.shape[0], -1)[:, :cols]
+    dropped = np.stack([two & np.uint64(1), two >> np.uint64(1)], axis=1).reshape(-1, two.shape[1])[:rows]
+    return torch.from_numpy(dropped == 0)
 
 
 def linear(x: Tensor, P, name: str, lora=None, scale: float = 0.0) -> Tensor:

@@ -502,21 +502,38 @@ def _seed_tensor(seed):
     return torch.tensor([seed - (1 << 32) if seed >= (1 << 31) else seed], dtype=torch.int32, device=DEV)
 
 
+def _plane(seed, names, rows, cols, p):
+    """Device bit planes (G, pairs, words) of the modules `names`."""
+    from oracle import whisper_eeg as O
+    bits = torch.empty(len(names), (rows + 1) // 2, (cols + 15) // 16, dtype=torch.int32, device=DEV)
+    assert bits[0].numel() == ops.dropout_bits_words(rows, cols)
+    ops.dropout_bits(rows, cols, _seed_tensor(seed), [O.module_salt(n) for n in names], p, bits)
+    return bits
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 def test_dropout_mask_bit_exact_and_seed_sequence(dtype):
-    """ns_dropout_apply == oracle.lora_dropout_keep element for element (odd row count, ragged leading dimension), and
-    ns_seed_advance follows oracle.next_dropout_seed."""
+    """ns_dropout_bits == oracle.lora_dropout_plane word for word, ns_dropout_apply == oracle.lora_dropout_keep element for
+    element (odd row count, column count that is no multiple of 16, ragged leading dimension), and ns_seed_advance follows
+    oracle.next_dropout_seed."""
     from oracle import whisper_eeg as O
     rows, cols, p = 1501, 520, 0.05
     x = rnd(rows, cols + 8, dtype=dtype, seed=1)[:, :cols]
     x = torch.where(x == 0, torch.ones_like(x), x)
     for seed, name in ((7, "model.encoder.layers.0.fc1"), (0xDEADBEEF, "model.encoder.layers.3.self_attn.q_proj")):
+        bits = _plane(seed, [name], rows, cols, p)
+        ref = torch.from_numpy(O.lora_dropout_plane(seed, name, rows, cols, p).astype(np.int64)).to(DEV)
+        assert torch.equal(bits[0].to(torch.int64) & 0xFFFFFFFF, ref)
         y = torch.empty(rows, cols, dtype=dtype, device=DEV)
-        ops.dropout_apply(x, y, _seed_tensor(seed), O.module_salt(name), p)
+        ops.dropout_apply(x, y, bits[0])
         keep = _keep(seed, name, rows, cols, p)
         assert torch.equal(y != 0, keep)
         assert torch.equal(y[keep], x[keep])
         assert abs(float(keep.float().mean()) - 0.95) < 2e-3
+    k1 = _keep(7, "model.encoder.layers.0.fc1", 4096, 512, 0.05).float()
+    k2 = _keep(7, "model.encoder.layers.0.fc2", 4096, 512, 0.05).float()
+    assert abs(float((k1 * k2).mean()) - 0.95 ** 2) < 2e-3                # modules draw independently
+    assert abs(float((k1[:, 1:] * k1[:, :-1]).mean()) - 0.95 ** 2) < 2e-3 and abs(float((k1[1:] * k1[:-1]).mean()) - 0.95 ** 2) < 2e-3
     s = _seed_tensor(12345)
     ref = 12345
     for _ in range(3):
@@ -525,7 +542,7 @@ def test_dropout_mask_bit_exact_and_seed_sequence(dtype):
         assert (int(s.item()) & 0xFFFFFFFF) == ref
 
 
-LORA_CASES = [(3000, 512, 1, 32), (3000, 512, 3, 32), (1000, 2048, 1, 32), (333, 128, 1, 8), (333, 128, 3, 8), (640, 256, 3, 16),
+LORA_CASES = [(3000, 512, 1, 32), (3000, 512, 3, 32), (1000, 2048, 1, 32), (333, 128, 1, 8), (333, 128, 3, 8), (640, 256, 3, 16), (641, 320, 1, 16),
               (96001, 512, 3, 32)]
 
 
@@ -536,16 +553,16 @@ def test_lora_down_and_da(M, K, G, r, p):
     mask (3 stacked adapters = q/k/v on one input; an odd / ragged row count exercises the row-pair and tile tails)."""
     from oracle import whisper_eeg as O
     names = [f"model.encoder.layers.2.self_attn.{n}" for n in ("q_proj", "k_proj", "v_proj")][:G]
-    salts = [O.module_salt(n) for n in names]
     seed = 424242
     x = rnd(M, K, dtype=torch.bfloat16, seed=2)
     A = rnd(G * r, K, dtype=torch.bfloat16, scale=K ** -0.5, seed=3)
     dt = rnd(M, G * r, dtype=torch.bfloat16, scale=0.1, seed=4)
     t = torch.empty(M, G * r, dtype=torch.bfloat16, device=DEV)
     alpha = 2.0 / (1.0 - p)
-    ops.lora_down(x, A, t, alpha, G, _seed_tensor(seed), salts, p)
+    bits = _plane(seed, names, M, K, p) if p > 0 else None
+    ops.lora_down(x, A, t, alpha, G, bits)
     dA = torch.full((G * r, K), 0.25, dtype=torch.float32, device=DEV)
-    ops.lora_da(x, dt, dA, G, _seed_tensor(seed), salts, p)
+    ops.lora_da(x, dt, dA, G, bits)
     for g in range(G):
         xm = x.float() * (_keep(seed, names[g], M, K, p).float() if p > 0 else 1.0)
         t_ref = alpha * xm @ A[g * r:(g + 1) * r].float().t()
@@ -555,18 +572,20 @@ def test_lora_down_and_da(M, K, G, r, p):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
-@pytest.mark.parametrize("M,K,G,r,with_z", [(1001, 512, 3, 32, False), (700, 2048, 1, 32, True), (333, 128, 1, 8, False)])
+@pytest.mark.parametrize("M,K,G,r,with_z", [(1001, 512, 3, 32, False), (700, 2048, 1, 32, True), (333, 128, 1, 8, False), (96001, 512, 1, 32, True)])
 def test_lora_dx_fix(M, K, G, r, with_z, dtype):
-    """dx - dropped_g * (dt_g . A_g[:, k]) * gelu'(z): the sparse correction after the input-gradient GEMM."""
-    from oracle import whisper_eeg as O
+    """dx - dropped_g * (dt_g . A_g[:, k]) * gelu'(z): the sparse correction after the input-gradient GEMM -- the generic
+    kernel (any storage) and, in bf16, the copy fused into ns_lora_da (MMA product + packed bf16 reductions), whose dA must not
+    change when the correction rides along."""
     names = [f"model.encoder.layers.1.self_attn.{n}" for n in ("q_proj", "k_proj", "v_proj")][:G]
     seed, p = 99, 0.05
     dx0 = rnd(M, K, dtype=dtype, seed=5)
     dt = rnd(M, G * r, dtype=dtype, scale=0.3, seed=6)
     At = rnd(K, G * r, dtype=dtype, scale=0.2, seed=7)
     z = rnd(M, K, dtype=dtype, seed=8) if with_z else None
+    bits = _plane(seed, names, M, K, p)
     dx = dx0.clone()
-    ops.lora_dx_fix(dx, dt, At, _seed_tensor(seed), [O.module_salt(n) for n in names], p, G, z)
+    ops.lora_dx_fix(dx, dt, At, bits, G, z)
     ref = dx0.float()
     for g in range(G):
         drop = ~_keep(seed, names[g], M, K, p)
@@ -579,3 +598,13 @@ def test_lora_dx_fix(M, K, G, r, with_z, dtype):
     assert rel(dx.float(), ref) < (1e-2 if dtype == torch.bfloat16 else 1e-5)
     sel = (ref != dx0.float())
     assert rel(dx.float()[sel], ref[sel]) < (2e-2 if dtype == torch.bfloat16 else 1e-4)
+    if dtype == torch.bfloat16:
+        x = rnd(M, K, dtype=dtype, seed=9)
+        dA0 = torch.zeros(G * r, K, dtype=torch.float32, device=DEV)
+        ops.lora_da(x, dt, dA0, G, bits)
+        dA1 = torch.zeros_like(dA0)
+        dxb = dx0.clone()
+        ops.lora_da(x, dt, dA1, G, bits, dx=dxb, At=At, z=z)
+        assert rel(dA1, dA0) < 1e-5
+        assert not bool((dxb != dx0)[~sel].any())                     # nothing but dropped positions is touched
+        assert rel(dxb.float(), ref) < 1e-2 and rel(dxb.float()[sel], ref[sel]) < 2e-2

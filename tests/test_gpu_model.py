@@ -26,6 +26,15 @@ def rel(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
+def torch_bf16_grads(x, labels, P, dims, lora):
+    """The oracle's own forward/backward run by torch on the GPU with every tensor STORED in bf16 (cuBLAS accumulates in fp32):
+    the error floor the number format itself sets for a given tensor."""
+    Pb = {k: v.to(DEV, torch.bfloat16) for k, v in P.items()}
+    Lb = {k: (v.to(DEV, torch.bfloat16) if torch.is_tensor(v) else v) for k, v in lora.items()}
+    _, g, _ = O.grads(x.to(DEV, torch.bfloat16), labels.to(DEV), Pb, dims, Lb)
+    return {k: v.float().cpu() for k, v in g.items()}
+
+
 def build(dims, dtype, seed=0, b_std=0.05, with_lora=True):
     P = O.init_params(dims, seed=seed)
     lora = O.init_lora(dims, seed=seed + 1, b_std=b_std) if with_lora else None
@@ -432,6 +441,12 @@ def test_lora_dropout_forward_backward_matches_oracle(dims_name, dtype, p):
     eng.backward()
     errs = {n: rel(eng.trainable_grad(n), g) for n, g in grads_ref.items()}
     bad = {k: v for k, v in errs.items() if v > tg}
+    if bad and dtype == torch.bfloat16:
+        # a tensor above 2e-2 must be at the floor of the format: the same oracle code run by torch with bf16 storage (fp32
+        # accumulation) is within 2.5x as close to the fp32 oracle (tiny shapes: the q/k adapter gradients pass through a softmax over
+        # 64 keys and are small against their bf16 rounding noise)
+        floor = torch_bf16_grads(x, labels, P, dims, lo)
+        bad = {k: (v, rel(floor[k], grads_ref[k])) for k, v in bad.items() if v > 2.5 * rel(floor[k], grads_ref[k])}
     assert not bad, bad
     eng.training = False                                          # model.eval(): nn.Dropout is the identity
     loss_e, _, enc_e = eng.forward_loss(x.to(DEV), labels.to(DEV))

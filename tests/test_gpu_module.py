@@ -88,3 +88,47 @@ def test_fused_training_step_reduces_loss_bf16():
     m = WhisperForConditionalGeneration(ModelDims.from_any(dims), P, lora, dtype=torch.bfloat16, device=DEV)
     losses = [float(m.training_step(x.to(DEV), labels.to(DEV), lr=2e-3).loss) for _ in range(8)]
     assert losses[-1] < losses[0] - 0.05, losses
+
+
+def test_trainer_fit_follows_hf_schedule_and_saves_best_adapter(tmp_path):
+    """neuspeech1_b200.trainer.Trainer (finetune.py:231-282 without HF): linear warm-up/decay in HF's order (the first optimizer
+    step of a warm-up runs with lr = 0), clip + AdamW, periodic evaluation with the LoRA dropout off, best-eval adapter
+    checkpoints in PEFT's layout (utils/callback.py:11-22).  Weights after 6 steps == the oracle stepping with the same
+    learning rates and dropout masks."""
+    import os
+    from neuspeech1_b200.parallel import linear_warmup_decay
+    from neuspeech1_b200.trainer import Trainer
+    dims = O.TINY
+    P = O.init_params(dims, seed=0); lora = O.init_lora(dims, seed=1, b_std=0.05)
+    m = WhisperForConditionalGeneration(ModelDims.from_any(dims), P, lora, dtype=torch.float32, device=DEV, lora_dropout=0.05)
+    m.engine.set_dropout_seed(31)
+    batches = []
+    for k in range(3):
+        x, labels = O.synthetic_batch(dims, B=2, L=6, seed=20 + k)
+        batches.append({"input_features": x.to(DEV), "labels": labels.to(DEV)})
+    logs = []
+    tr = Trainer(m, lr=1e-3, warmup_steps=2, output_dir=str(tmp_path), eval_steps=3, logging_steps=1, log=logs.append)
+    tr.fit(batches, epochs=2, eval_loader=batches[:1])
+    assert tr.step == 6 and tr.total_steps == 6
+    assert [linear_warmup_decay(k, 1e-3, 2, 6) for k in range(3)] == [0.0, 5e-4, 1e-3]
+    Pc = {k: v.clone() for k, v in P.items()}; lc = {k: v.clone() for k, v in lora.items()}
+    st = O.AdamWState()
+    seed = 31
+    for k in range(6):
+        b = batches[k % 3]
+        seed = O.next_dropout_seed(seed)
+        lc["__dropout__"] = (0.05, seed)
+        O.train_step(b["input_features"].cpu(), b["labels"].cpu(), Pc, dims, lc, st, lr=linear_warmup_decay(k, 1e-3, 2, 6))
+    for name in O.trainable_names(Pc, lc):
+        ref = lc[name] if name in lc else Pc[name]
+        assert rel(m.engine.trainable(name), ref) < 2e-3, name
+    lc.pop("__dropout__")
+    with torch.no_grad():
+        ev_ref, _, _ = O.forward_loss(batches[0]["input_features"].cpu(), batches[0]["labels"].cpu(), Pc, dims, lc)
+    assert abs(tr.evaluate(batches[:1]) - float(ev_ref)) < 1e-3 * float(ev_ref)          # evaluation runs without dropout
+    assert m.training                                                                    # ... and restores train mode
+    assert any("eval_loss" in l for l in logs)
+    for ck in ("checkpoint-final",):
+        files = set(os.listdir(tmp_path / ck))
+        assert {"adapter_model.safetensors", "adapter_config.json"} <= files
+    assert any(d.startswith("checkpoint-3") or d.startswith("checkpoint-6") for d in os.listdir(tmp_path))

@@ -28,7 +28,31 @@ def timeit(fn, n=20, flush=None):
     return tot / n * 1000.0   # us
 
 
+def once():
+    """One launch of every kernel variant at K=512 (G=1, 3): the ncu target (tools/gpu_r02_d.sh)."""
+    seed = torch.tensor([1234], dtype=torch.int32, device=DEV)
+    for K, G in ((512, 1), (512, 3)):
+        x = torch.randn(M, K, device=DEV).to(torch.bfloat16)
+        A = (torch.randn(G * r, K, device=DEV) * K ** -0.5).to(torch.bfloat16)
+        At = A.t().contiguous()
+        t = torch.empty(M, G * r, dtype=torch.bfloat16, device=DEV)
+        dt = (torch.randn(M, G * r, device=DEV) * 0.1).to(torch.bfloat16)
+        dA = torch.zeros(G * r, K, dtype=torch.float32, device=DEV)
+        dx = torch.randn(M, K, device=DEV).to(torch.bfloat16)
+        salts = [11, 22, 33][:G]
+        bits = torch.empty(G, M // 2, K // 16, dtype=torch.int32, device=DEV)
+        ops.dropout_bits(M, K, seed, salts, 0.05, bits)
+        ops.lora_down(x, A, t, 2.0, G)
+        ops.lora_down(x, A, t, 2.0, G, bits)
+        ops.lora_da(x, dt, dA, G)
+        ops.lora_da(x, dt, dA, G, bits)
+        ops.lora_da(x, dt, dA, G, bits, dx=dx, At=At)
+    torch.cuda.synchronize()
+
+
 def main():
+    if "--once" in sys.argv:
+        return once()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
     seed = torch.tensor([1234], dtype=torch.int32, device=DEV)
     out = {}
@@ -42,16 +66,19 @@ def main():
         dx = torch.randn(M, K, device=DEV).to(torch.bfloat16)
         z = torch.randn(M, K, device=DEV).to(torch.bfloat16)
         salts = [11, 22, 33][:G]
+        bits = torch.empty(G, M // 2, K // 16, dtype=torch.int32, device=DEV)
+        ops.dropout_bits(M, K, seed, salts, 0.05, bits)
         key = f"K{K}_G{G}"
         out[key] = {
+            "dropout_bits": timeit(lambda: ops.dropout_bits(M, K, seed, salts, 0.05, bits), flush=flush),
             "gemm_nt_thin": timeit(lambda: ops.gemm_nt(x, A, t, ops.epilogue(alpha=2.0, alpha_cols=G * r)), flush=flush),
             "lora_down_p0": timeit(lambda: ops.lora_down(x, A, t, 2.0, G), flush=flush),
-            "lora_down_p05": timeit(lambda: ops.lora_down(x, A, t, 2.0, G, seed, salts, 0.05), flush=flush),
+            "lora_down_p05": timeit(lambda: ops.lora_down(x, A, t, 2.0, G, bits), flush=flush),
             "gemm_tn_dA": timeit(lambda: ops.gemm_tn(x, dt, dA, 1, K), flush=flush),
             "lora_da_p0": timeit(lambda: ops.lora_da(x, dt, dA, G), flush=flush),
-            "lora_da_p05": timeit(lambda: ops.lora_da(x, dt, dA, G, seed, salts, 0.05), flush=flush),
-            "dx_fix_p05": timeit(lambda: ops.lora_dx_fix(dx, dt, At, seed, salts, 0.05, G), flush=flush),
-            "dx_fix_p05_gelu": timeit(lambda: ops.lora_dx_fix(dx, dt, At, seed, salts, 0.05, G, z), flush=flush),
+            "lora_da_p05": timeit(lambda: ops.lora_da(x, dt, dA, G, bits), flush=flush),
+            "lora_da_fix_p05": timeit(lambda: ops.lora_da(x, dt, dA, G, bits, dx=dx, At=At), flush=flush),
+            "lora_da_fix_gelu_p05": timeit(lambda: ops.lora_da(x, dt, dA, G, bits, dx=dx, At=At, z=z), flush=flush),
             "x_MB": M * K * 2 / 1e6,
         }
         print(key, {k: round(v, 1) for k, v in out[key].items()})
