@@ -182,8 +182,9 @@ int ns_dgelu_mul(int dtype, long long n, const void* dy, const void* z, void* dz
  * 0.1 for AdaLoRA) and its autograd backward.  The keep mask of a module is a counter-based bit plane, drawn once per step:
  *   bits[g][(rows+1)/2][(cols+15)/16] (32-bit words); bit 2*(col % 16) + (row & 1) of word (g, rp = row >> 1, w = col / 16) set
  *   <=> element (row, col) of adapter g is dropped.  The 32 flags of a word are drawn together from 16 hashed words
- *   R_i = lowbias32((rp * 0x9E3779B1) ^ (w * 0x85EBCA77) ^ (i * 0xC2B2AE35) ^ *seed ^ salts[g]), combined along the binary
- *   expansion of thr = round(p * 65536), least significant bit first: D = bit_i(thr) ? (D | R_i) : (D & R_i)  (P(flag) = thr/65536).
+ *   R_i = mix1(km + (i + 1) * 0xC2B2AE35), km = lowbias32((rp * 0x9E3779B1) ^ (w * 0x85EBCA77) ^ *seed ^ salts[g]), mix1 = the
+ *   first multiply-xorshift round of lowbias32, combined along the binary expansion of thr = round(p * 65536), least
+ *   significant bit first: D = bit_i(thr) ? (D | R_i) : (D & R_i)  (P(flag) = thr / 65536).
  * `seed` is a DEVICE word (one per training step, advanced on the device so a replayed CUDA graph draws a new mask); `salts[g]`
  * identify the modules (crc32 of their names).  The kernels use the UNSCALED masked input: the caller folds 1/(1-p) into alpha
  * (t) and into dt.  G = adapters stacked on the same input (1, or 3 for q/k/v), r = rank. */

@@ -4,7 +4,8 @@
 //
 // The keep mask is a counter-based bit plane: word (module, row pair rp, column block w) holds the DROPPED flags of 16 columns x
 // the 2 rows of a row pair, bit 2*(col % 16) + (row & 1).  Its 32 Bernoulli(p) bits are drawn together from 16 hashed words
-//     R_i = lowbias32( (rp * 0x9E3779B1) ^ (w * 0x85EBCA77) ^ (i * 0xC2B2AE35) ^ seed ^ salt ),   i = 0..15
+//     km = lowbias32( (rp * 0x9E3779B1) ^ (w * 0x85EBCA77) ^ seed ^ salt )
+//     R_i = mix1( km + (i + 1) * 0xC2B2AE35 ),   i = 0..15        mix1(x): x ^= x >> 16; x *= 0x7FEB352D; x ^= x >> 15
 // combined along the binary expansion of thr16 = round(p * 65536), least significant bit first:
 //     D = 0;   D = bit_i(thr16) ? (D | R_i) : (D & R_i)         =>  every bit of D is set with probability thr16 / 65536
 // (bit position b of (R_15 .. R_0) read as a 16-bit uniform number U_b: D_b = [U_b < thr16]) -- half a hash per element and no
@@ -29,6 +30,8 @@
 //   ns_seed_advance   seed <- lowbias32(seed + 0x9E3779B9)          (inside the captured training step: a new mask per replay)
 #include "ns_common.cuh"
 
+#include <stdlib.h>
+
 namespace ns {
 
 __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
@@ -37,12 +40,13 @@ __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
 }
 constexpr uint32_t kRowMul = 0x9E3779B1u, kColMul = 0x85EBCA77u, kIdxMul = 0xC2B2AE35u;
 // the 32 dropped flags of (row pair, 16-column block): see the file header
+__device__ __forceinline__ uint32_t mix1(uint32_t x) { x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; return x; }
 __device__ __forceinline__ uint32_t drop_plane_word(uint32_t rp, uint32_t w, uint32_t module_seed, uint32_t thr) {
-  const uint32_t key = (rp * kRowMul) ^ (w * kColMul) ^ module_seed;
+  const uint32_t km = lowbias32((rp * kRowMul) ^ (w * kColMul) ^ module_seed);
   uint32_t d = 0;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const uint32_t r = lowbias32(key ^ (static_cast<uint32_t>(i) * kIdxMul));
+    const uint32_t r = mix1(km + static_cast<uint32_t>(i + 1) * kIdxMul);
     d = ((thr >> i) & 1u) ? (d | r) : (d & r);
   }
   return d;
@@ -526,11 +530,24 @@ static int launch_da_variant(long long M, int K, const void* x, long long ldx, c
   static bool attr_done = false;
   auto kern = lora_da_kernel<G, NT, FIX, ZG, STAGES>;
   if (!attr_done) { NS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
-  kern<<<dim3(col_slabs, row_slabs), DA_WARPS * 32, smem, st>>>(M, K, rps, static_cast<const __nv_bfloat16*>(x), ldx,
-                                                               static_cast<const __nv_bfloat16*>(dt), lddt, dA, ldg, bits,
-                                                               static_cast<__nv_bfloat16*>(dx), lddx, static_cast<const __nv_bfloat16*>(At), ldat,
-                                                               static_cast<const __nv_bfloat16*>(z), ldz);
-  NS_LAUNCH_CHECK();
+  // The column slabs of one row slab are launched as a thread-block CLUSTER: co-scheduled CTAs walk the same rows at the same
+  // pace, so the 512-byte pieces of a row are requested together and DRAM sees whole rows (pages) instead of scattered halves.
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(col_slabs, row_slabs);
+  cfg.blockDim = dim3(DA_WARPS * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (col_slabs <= 8 && getenv("NS_LORA_CLUSTER") != nullptr) ? col_slabs : 1;   // measured: no gain at 2 slabs, 2x slower at 8
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NS_CUDA(cudaLaunchKernelEx(&cfg, kern, M, K, rps, static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(dt), lddt, dA, ldg,
+                             bits, static_cast<__nv_bfloat16*>(dx), lddx, static_cast<const __nv_bfloat16*>(At), ldat,
+                             static_cast<const __nv_bfloat16*>(z), ldz));
   return NS_OK;
 }
 
@@ -541,6 +558,85 @@ static int launch_da(long long M, int K, const void* x, long long ldx, const voi
   if (dx && z) return launch_da_variant<G, NT, true, true>(M, K, x, ldx, dt, lddt, dA, ldg, bits, dx, lddx, At, ldat, z, ldz, st);
   if (dx) return launch_da_variant<G, NT, true, false>(M, K, x, ldx, dt, lddt, dA, ldg, bits, dx, lddx, At, ldat, z, ldz, st);
   return launch_da_variant<G, NT, false, false>(M, K, x, ldx, dt, lddt, dA, ldg, bits, dx, lddx, At, ldat, z, ldz, st);
+}
+
+// ------------------------------------------------------------------------------------------------ t = alpha' (x . keep) A^T, one adapter
+// Many small CTAs instead of one register-heavy CTA per SM: 4 warps x 16 rows, no software prefetch, 40-odd registers per
+// thread, A staged in shared memory in column chunks of KC -- latency is hidden by 30+ resident warps per SM (the LayerNorm
+// kernels reach 5.9 TB/s that way; the persistent version above sat at 3 TB/s waiting on the long scoreboard).
+constexpr int DT_KC = 512;
+template <int NT>
+__global__ void __launch_bounds__(128, 6) lora_down_tlp_kernel(long long M, int K, const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                              const __nv_bfloat16* __restrict__ A, long long lda,
+                                                              __nv_bfloat16* __restrict__ t, long long ldt, float alpha,
+                                                              const uint32_t* __restrict__ bits) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int R = NT * 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+  const long long R0 = (static_cast<long long>(blockIdx.x) * 4 + warp) * 16;
+  const long long re = R0 + 2 * g;
+  const bool okE = re < M, okO = re + 1 < M;
+  const __nv_bfloat16* xe = x + (okE ? re : 0) * ldx + tq * 8;
+  const __nv_bfloat16* xo = x + (okO ? re + 1 : 0) * ldx + tq * 8;
+  const int W = (K + 15) >> 4;
+  const uint32_t* brow = bits ? bits + (okE ? (re >> 1) : 0) * W + (tq >> 1) : nullptr;
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  float acc[NT][4];
+#pragma unroll
+  for (int c = 0; c < NT; ++c)
+#pragma unroll
+    for (int d = 0; d < 4; ++d) acc[c][d] = 0.f;
+  for (int kc = 0; kc < K; kc += DT_KC) {
+    const int kw = K - kc < DT_KC ? K - kc : DT_KC;          // columns of this chunk (multiple of 32)
+    const int pitch = kw * 2 + 64;
+    if (kc) __syncthreads();
+    for (int i = threadIdx.x; i < R * (kw / 8); i += 128) {
+      const int row = i / (kw / 8), v = i - row * (kw / 8);
+      *reinterpret_cast<uint4*>(smem_raw + row * pitch + v * 16) = __ldg(reinterpret_cast<const uint4*>(A + row * lda + kc) + v);
+    }
+    __syncthreads();
+    if (R0 < M) {
+#pragma unroll 4
+      for (int c0 = 0; c0 < kw; c0 += 32) {
+        uint4 e = okE ? __ldg(reinterpret_cast<const uint4*>(xe + kc + c0)) : zero4;
+        uint4 o = okO ? __ldg(reinterpret_cast<const uint4*>(xo + kc + c0)) : zero4;
+        if (bits) {
+          const uint32_t hb = __ldg(brow + ((kc + c0) >> 4)) >> (16 * (tq & 1));
+          e.x &= keep_mask2(hb, hb >> 2);       o.x &= keep_mask2(hb >> 1, hb >> 3);
+          e.y &= keep_mask2(hb >> 4, hb >> 6);  o.y &= keep_mask2(hb >> 5, hb >> 7);
+          e.z &= keep_mask2(hb >> 8, hb >> 10); o.z &= keep_mask2(hb >> 9, hb >> 11);
+          e.w &= keep_mask2(hb >> 12, hb >> 14); o.w &= keep_mask2(hb >> 13, hb >> 15);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const uint4 w = *reinterpret_cast<const uint4*>(smem_raw + (nt * 8 + g) * pitch + (c0 + tq * 8) * 2);
+          mma_bf16_16816(acc[nt], e.x, o.x, e.y, o.y, w.x, w.y);
+          mma_bf16_16816(acc[nt], e.z, o.z, e.w, o.w, w.z, w.w);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int col = nt * 8 + tq * 2;
+    if (okE) *reinterpret_cast<uint32_t*>(t + re * ldt + col) = pack_bf16x2(alpha * acc[nt][0], alpha * acc[nt][1]);
+    if (okO) *reinterpret_cast<uint32_t*>(t + (re + 1) * ldt + col) = pack_bf16x2(alpha * acc[nt][2], alpha * acc[nt][3]);
+  }
+}
+
+template <int NT>
+static int launch_down_tlp(long long M, int K, const void* x, long long ldx, const void* A, long long lda, void* t, long long ldt,
+                           float alpha, const uint32_t* bits, cudaStream_t st) {
+  const int kw = K < DT_KC ? K : DT_KC;
+  const size_t smem = static_cast<size_t>(NT) * 8 * (kw * 2 + 64);
+  static bool attr_done = false;
+  auto kern = lora_down_tlp_kernel<NT>;
+  if (!attr_done) { NS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, NT * 8 * (DT_KC * 2 + 64))); attr_done = true; }
+  kern<<<static_cast<unsigned>((M + 63) / 64), 128, smem, st>>>(M, K, static_cast<const __nv_bfloat16*>(x), ldx,
+                                                               static_cast<const __nv_bfloat16*>(A), lda, static_cast<__nv_bfloat16*>(t), ldt, alpha,
+                                                               bits);
+  NS_LAUNCH_CHECK();
+  return NS_OK;
 }
 
 template <typename Kern>
@@ -671,6 +767,12 @@ int ns_lora_down(long long M, int K, int G, int r, const void* x, long long ldx,
     return NS_ERR_UNSUPPORTED;
   }
   count(C_OTHER);
+  static const bool tlp = getenv("NS_LORA_DOWN_TLP") != nullptr;      // developer A/B switch: many small CTAs (slower: 51 vs 45 us)
+  if (G == 1 && tlp) {
+    if (r == 32) return launch_down_tlp<4>(M, K, x, ldx, A, lda, t, ldt, alpha, bits, st);
+    if (r == 16) return launch_down_tlp<2>(M, K, x, ldx, A, lda, t, ldt, alpha, bits, st);
+    if (r == 8) return launch_down_tlp<1>(M, K, x, ldx, A, lda, t, ldt, alpha, bits, st);
+  }
 #define NS_W1 , 16, 2
 #define NS_W3 , 8, 2
   NS_LORA_DISPATCH(launch_down, M, K, x, ldx, A, lda, t, ldt, alpha, bits, st);

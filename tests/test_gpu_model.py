@@ -35,6 +35,20 @@ def torch_bf16_grads(x, labels, P, dims, lora):
     return {k: v.float().cpu() for k, v in g.items()}
 
 
+def check_bf16_grads(eng, grads_ref, x, labels, P, dims, lora, tol=2e-2):
+    """Every LoRA / stem gradient within `tol` of the fp32 oracle.  A tensor above it must sit at the floor of the
+    number format: the same oracle code run by torch with bf16 storage and fp32 accumulation may be at most 2.5x closer to the
+    fp32 oracle (tiny shapes: the q/k adapter gradients pass through a softmax over 64-160 keys and are small against their own
+    bf16 rounding noise; at the benchmark shape every tensor passes `tol` outright)."""
+    errs = {n: rel(eng.trainable_grad(n), g) for n, g in grads_ref.items()}
+    bad = {k: v for k, v in errs.items() if v > tol}
+    if bad:
+        floor = torch_bf16_grads(x, labels, P, dims, lora)
+        bad = {k: (v, rel(floor[k], grads_ref[k])) for k, v in bad.items() if v > 2.5 * rel(floor[k], grads_ref[k]) or v > 2 * tol}
+    assert not bad, bad
+    return errs
+
+
 def build(dims, dtype, seed=0, b_std=0.05, with_lora=True):
     P = O.init_params(dims, seed=seed)
     lora = O.init_lora(dims, seed=seed + 1, b_std=b_std) if with_lora else None
@@ -83,9 +97,7 @@ def test_bf16_forward_loss_grads(dims_name):
     eng.backward()
     c = _abi.counters()
     assert c["gemm_tcgen05"] > 0, c
-    errs = {name: rel(eng.trainable_grad(name), g) for name, g in grads_ref.items()}
-    bad = {k: v for k, v in errs.items() if v > 2e-2}          # LoRA/stem grads at the bf16 tolerance of the states
-    assert not bad, bad
+    check_bf16_grads(eng, grads_ref, x, labels, P, dims, lora)  # LoRA/stem grads at the bf16 tolerance of the states
     # whole-gradient direction: cosine over the flat trainable vector
     ref_flat = torch.cat([grads_ref[n].reshape(-1) for n in sorted(grads_ref)])
     got_flat = torch.cat([eng.trainable_grad(n).reshape(-1).cpu() for n in sorted(grads_ref)])
@@ -379,8 +391,11 @@ def test_schoffelen_channels_and_large_v3_widths(dims_name, dtype):
     tol_e, tol_g = (1e-3, 2e-3) if dtype == torch.float32 else (2e-2, 2e-2)
     assert rel(enc, enc_ref) < tol_e, rel(enc, enc_ref)
     assert abs(float(loss) - float(loss_ref)) < tol_e * float(loss_ref)
-    worst = max(rel(eng.trainable_grad(n), g) for n, g in grads_ref.items())
-    assert worst < tol_g, worst
+    if dtype == torch.bfloat16:
+        check_bf16_grads(eng, grads_ref, x, labels, P, dims, lora, tol=tol_g)
+    else:
+        worst = max(rel(eng.trainable_grad(n), g) for n, g in grads_ref.items())
+        assert worst < tol_g, worst
     if dtype == torch.bfloat16:
         c = _abi.counters()
         assert c["gemm_tcgen05"] > 0 and c["attn_tc"] > 0, c
@@ -439,15 +454,11 @@ def test_lora_dropout_forward_backward_matches_oracle(dims_name, dtype, p):
     if dtype == torch.float32:
         assert rel(enc, enc_nodrop) > 5 * rel(enc, enc_ref)
     eng.backward()
-    errs = {n: rel(eng.trainable_grad(n), g) for n, g in grads_ref.items()}
-    bad = {k: v for k, v in errs.items() if v > tg}
-    if bad and dtype == torch.bfloat16:
-        # a tensor above 2e-2 must be at the floor of the format: the same oracle code run by torch with bf16 storage (fp32
-        # accumulation) is within 2.5x as close to the fp32 oracle (tiny shapes: the q/k adapter gradients pass through a softmax over
-        # 64 keys and are small against their bf16 rounding noise)
-        floor = torch_bf16_grads(x, labels, P, dims, lo)
-        bad = {k: (v, rel(floor[k], grads_ref[k])) for k, v in bad.items() if v > 2.5 * rel(floor[k], grads_ref[k])}
-    assert not bad, bad
+    if dtype == torch.bfloat16:
+        check_bf16_grads(eng, grads_ref, x, labels, P, dims, lo, tol=tg)
+    else:
+        bad = {n: rel(eng.trainable_grad(n), g) for n, g in grads_ref.items() if rel(eng.trainable_grad(n), g) > tg}
+        assert not bad, bad
     eng.training = False                                          # model.eval(): nn.Dropout is the identity
     loss_e, _, enc_e = eng.forward_loss(x.to(DEV), labels.to(DEV))
     assert rel(enc_e, enc_nodrop) < te and abs(float(loss_e) - float(loss_nodrop)) < te * float(loss_nodrop)
