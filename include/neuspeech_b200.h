@@ -177,6 +177,21 @@ int ns_add(int dtype, long long n, const void* a, const void* b, void* y, void* 
  * path whose backward cannot ride in a GEMM epilogue) */
 int ns_dgelu_mul(int dtype, long long n, const void* dy, const void* z, void* dz, void* stream);
 
+/* ---- beam search (evaluation.py:370-385: generate(num_beams=5, repetition_penalty=5.0, no_repeat_ngram_size=2)).
+ * ns_beam_row_topk: for every beam row the C (= 2 * num_beams <= 16) best continuations of
+ *   run_score[row] + processors(log_softmax(logits[row]))   with the processors of the reference's generate call in HF order:
+ * repetition penalty over the tokens in seqs[row, :t] (lp < 0: lp * penalty, else lp / penalty), no-repeat-n-gram ban, and
+ * `suppress` (begin_suppress_tokens, first generated position only) -- one pass over the logits (history as shared-memory bitmaps
+ * over the vocabulary, online softmax, per-thread partial top lists).  Outputs sorted by score (descending).  The per-sample merge
+ * of num_beams rows is a 2K x K problem left to the host loop.
+ * ns_attention_decode_rows: single-query attention whose key/value j of batch row b is read from cache row kv_row[b * kv_ld + j]:
+ * the beam reorder (utils/load_model.py:1353-1360 _reorder_cache) permutes this table instead of copying every layer's cache. */
+int ns_beam_row_topk(int dtype, int rows, int V, long long ld, const void* logits, const long long* seqs, long long lds, int t,
+                     const float* run_score, float penalty, int ngram, const int* suppress, int n_suppress, int C,
+                     float* out_score, int* out_tok, void* stream);
+int ns_attention_decode_rows(int dtype, const ns_attn_shape* s, const void* q, const void* k, const void* v, void* o,
+                             const int* kv_row, long long kv_ld, void* stream);
+
 /* ---- LoRA branch: dropout and the rank-r products around it.
  * Replaces PEFT lora.Linear's  result += lora_B(lora_A(lora_dropout(x))) * scaling  (finetune.py:206-212: lora_dropout 0.05,
  * 0.1 for AdaLoRA) and its autograd backward.  The keep mask of a module is a counter-based bit plane, drawn once per step:

@@ -75,6 +75,8 @@ SIGNATURES = {
     "ns_conv_weight_unpack_grad": [c_i, c_i, c_i, c_vp, c_vp, c_vp],
     "ns_add": [c_i, c_ll, c_vp, c_vp, c_vp, c_vp],
     "ns_dgelu_mul": [c_i, c_ll, c_vp, c_vp, c_vp, c_vp],
+    "ns_beam_row_topk": [c_i, c_i, c_i, c_ll, c_vp, c_vp, c_ll, c_i, c_vp, c_f, c_i, c_vp, c_i, c_i, c_vp, c_vp, c_vp],
+    "ns_attention_decode_rows": [c_i, C.POINTER(AttnShape), c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_vp],
     "ns_seed_advance": [c_vp, c_vp],
     "ns_dropout_apply": [c_i, c_ll, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, c_vp],
     "ns_lora_down": [c_ll, c_i, c_i, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_f, c_vp, c_vp],

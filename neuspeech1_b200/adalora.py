@@ -15,7 +15,8 @@ on EFFECTIVE operands A_eff = [E * A; 0], B_eff = [B, 0]; this adapter keeps the
 refreshes the effective operands before a step, maps the engine's gradients back by the chain rule
 (dA = E * dA_eff, dE = rowsum(dA_eff * A), dB = dB_eff), adds the regulariser's gradient, and runs the same fused
 clip + AdamW kernels over the master buffer; the stem convolutions stay with the engine's own optimizer step, both under ONE
-global gradient norm.  lora_dropout is not applied.
+global gradient norm.  lora_dropout (0.1 in the reference's AdaLoraConfig) is the engine's LoRA-branch dropout: the same
+counter-based bit plane and kernels as plain LoRA (csrc/ns_lora.cu), applied to the branch input x.
 """
 from __future__ import annotations
 
@@ -46,7 +47,7 @@ def orth_regulariser(A: torch.Tensor, B: torch.Tensor) -> Tuple[torch.Tensor, to
 class AdaLoraAdapter:
     def __init__(self, dims: ModelDims, params: Dict[str, torch.Tensor], init_r: int = 12, lora_alpha: float = 32.0,
                  orth_reg_weight: float = 0.5, dtype: torch.dtype = torch.bfloat16, device="cuda", seed: int = 0,
-                 state: Optional[Dict[str, torch.Tensor]] = None):
+                 state: Optional[Dict[str, torch.Tensor]] = None, lora_dropout: float = 0.1, dropout_seed: int = 0):
         assert 0 < init_r <= PAD_RANK, "init_r is padded to one UMMA K step (16)"
         self.r, self.alpha, self.w = init_r, float(lora_alpha), float(orth_reg_weight)
         scale = self.alpha / (init_r + 1e-5)
@@ -82,7 +83,8 @@ class AdaLoraAdapter:
         for name, fin, fout in self.modules:
             zero_lora[name + ".lora_A.default.weight"] = torch.zeros(PAD_RANK, fin)
             zero_lora[name + ".lora_B.default.weight"] = torch.zeros(fout, PAD_RANK)
-        self.engine = WhisperEEGEngine(self.dims, params, zero_lora, dtype=dtype, device=dev)
+        self.engine = WhisperEEGEngine(self.dims, params, zero_lora, dtype=dtype, device=dev, lora_dropout=lora_dropout,
+                                       dropout_seed=dropout_seed)
         self.opt_step = 0
         self.last_reg = None
 
@@ -151,6 +153,7 @@ class AdaLoraAdapter:
         from . import ops  # noqa: F401  (fails loudly when the library is missing)
         eng = self.engine
         self.sync_effective()
+        eng._advance_seed()                      # a new dropout mask per step (oracle.next_dropout_seed)
         eng.pack_trainable()
         ce, _, _ = eng.forward_loss(x, labels, aug=aug, save=True, ce_grad_scale=1.0)
         eng.backward()

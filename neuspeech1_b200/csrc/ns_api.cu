@@ -30,6 +30,8 @@ int sm_count() {
 }
 
 int attention_fwd_simt(int dtype, const ns_attn_shape& s, const void* q, const void* k, const void* v, void* o, float* lse, cudaStream_t st);
+int attention_decode_rows(int dtype, const ns_attn_shape& s, const void* q, const void* k, const void* v, void* o, const int* kv_row,
+                          long long kv_ld, cudaStream_t st);
 int attention_bwd_simt(int dtype, const ns_attn_shape& s, const void* q, const void* k, const void* v, const void* o, const void* d_o,
                        const float* lse, float* delta, void* dq, void* dk, void* dv, cudaStream_t st);
 int attention_fwd_tc(const ns_attn_shape& s, const void* q, const void* k, const void* v, void* o, float* lse, cudaStream_t st);
@@ -238,6 +240,14 @@ int ns_attention_fwd(int dtype, const ns_attn_shape* s, const void* q, const voi
     if (g_path == NS_PATH_FAST) return fast_required_failed("ns_attention_fwd");
   }
   return attention_fwd_simt(dtype, *s, q, k, v, o, lse, st);
+}
+
+int ns_attention_decode_rows(int dtype, const ns_attn_shape* s, const void* q, const void* k, const void* v, void* o, const int* kv_row,
+                             long long kv_ld, void* stream) {
+  NS_CHECK_ARG(valid_dtype(dtype) && q && k && v && o && kv_row, "ns_attention_decode_rows: bad arguments");
+  if (int r = check_attn(s)) return r;
+  NS_CHECK_ARG(s->Lq == 1 && kv_ld >= s->Lk, "ns_attention_decode_rows: one query per row and a table of at least Lk entries per row");
+  return attention_decode_rows(dtype, *s, q, k, v, o, kv_row, kv_ld, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int ns_attention_bwd(int dtype, const ns_attn_shape* s, const void* q, const void* k, const void* v, const void* o,

@@ -495,7 +495,8 @@ static bool tiny_eligible(const ns_attn_shape& s, const void* q, const void* k, 
 // merged in shared memory.  HBM-bound by construction: B*H*Lk*Dh*2 elements per call.
 template <typename T, int DH>
 __global__ void __launch_bounds__(256) attn_decode_kernel(const ns_attn_shape s, const T* __restrict__ q, const T* __restrict__ k,
-                                                          const T* __restrict__ v, T* __restrict__ o, float* __restrict__ lse) {
+                                                          const T* __restrict__ v, T* __restrict__ o, float* __restrict__ lse,
+                                                          const int* __restrict__ kv_row, long long kv_ld) {
   constexpr int EPV = 16 / sizeof(T);              // elements per 16-byte vector
   constexpr int CPR = DH / EPV;                    // vectors (lanes) per row
   constexpr int KPW = 32 / CPR;                    // keys per warp instruction
@@ -513,8 +514,11 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const ns_attn_shape s,
   float m = -INFINITY, l = 0.f, acc[EPV];
 #pragma unroll
   for (int e = 0; e < EPV; ++e) acc[e] = 0.f;
-  const T* kb = k + b * s.k_bs + h * DH + c * EPV;
-  const T* vb = v + b * s.v_bs + h * DH + c * EPV;
+  // kv_row (beam search): key/value j of batch row b lives in cache row kv_row[b][j] -- the beam reorder permutes this small
+  // table instead of copying the cache (utils/load_model.py:1353-1360 _reorder_cache index_selects every layer's K and V)
+  const int* rowtab = kv_row ? kv_row + b * kv_ld : nullptr;
+  const T* kb = k + (rowtab ? 0 : b * s.k_bs) + h * DH + c * EPV;
+  const T* vb = v + (rowtab ? 0 : b * s.v_bs) + h * DH + c * EPV;
   // UNR key groups per loop trip, all their 16-byte loads issued before the first use (memory-level parallelism is the whole
   // game here: ~64 KB must be in flight per SM to cover the HBM latency)
   constexpr int UNR = 4;
@@ -525,8 +529,9 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const ns_attn_shape s,
     for (int u = 0; u < UNR; ++u) {
       const int j = j0 + u * 8 * KPW + kk;
       ok[u] = j < s.Lk;
-      ku[u] = ok[u] ? __ldg(reinterpret_cast<const uint4*>(kb + static_cast<long long>(j) * s.k_rs)) : make_uint4(0, 0, 0, 0);
-      vu[u] = ok[u] ? __ldg(reinterpret_cast<const uint4*>(vb + static_cast<long long>(j) * s.v_rs)) : make_uint4(0, 0, 0, 0);
+      const long long pr = (rowtab && ok[u]) ? __ldg(rowtab + j) : 0;
+      ku[u] = ok[u] ? __ldg(reinterpret_cast<const uint4*>(kb + pr * s.k_bs + static_cast<long long>(j) * s.k_rs)) : make_uint4(0, 0, 0, 0);
+      vu[u] = ok[u] ? __ldg(reinterpret_cast<const uint4*>(vb + pr * s.v_bs + static_cast<long long>(j) * s.v_rs)) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
@@ -601,7 +606,7 @@ template <typename T, int DH>
 static int attn_fwd_simt_t(const ns_attn_shape& s, const void* q, const void* k, const void* v, void* o, float* lse, cudaStream_t st) {
   if (decode_eligible<T, DH>(s, q, k, v)) {
     attn_decode_kernel<T, DH><<<dim3(s.H, s.B), 256, 0, st>>>(s, reinterpret_cast<const T*>(q), reinterpret_cast<const T*>(k),
-                                                            reinterpret_cast<const T*>(v), reinterpret_cast<T*>(o), lse);
+                                                            reinterpret_cast<const T*>(v), reinterpret_cast<T*>(o), lse, nullptr, 0);
     NS_LAUNCH_CHECK();
     count(C_ATTN_SIMT);
     return NS_OK;
@@ -669,6 +674,27 @@ int attention_delta(int dtype, const ns_attn_shape& s, const void* o, const void
   NS_LAUNCH_CHECK();
   count(C_OTHER);
   return NS_OK;
+}
+
+template <typename T, int DH>
+static int attn_decode_rows_t(const ns_attn_shape& s, const void* q, const void* k, const void* v, void* o, const int* kv_row, long long kv_ld,
+                              cudaStream_t st) {
+  if (!decode_eligible<T, DH>(s, q, k, v)) {
+    set_error("ns_attention_decode_rows: needs Lq == 1 and 16-byte aligned K/V rows");
+    return NS_ERR_UNSUPPORTED;
+  }
+  attn_decode_kernel<T, DH><<<dim3(s.H, s.B), 256, 0, st>>>(s, reinterpret_cast<const T*>(q), reinterpret_cast<const T*>(k),
+                                                          reinterpret_cast<const T*>(v), reinterpret_cast<T*>(o), nullptr, kv_row, kv_ld);
+  NS_LAUNCH_CHECK();
+  count(C_ATTN_SIMT);
+  return NS_OK;
+}
+int attention_decode_rows(int dtype, const ns_attn_shape& s, const void* q, const void* k, const void* v, void* o, const int* kv_row,
+                          long long kv_ld, cudaStream_t st) {
+  if (dtype == NS_F32)
+    return s.Dh == 64 ? attn_decode_rows_t<float, 64>(s, q, k, v, o, kv_row, kv_ld, st) : attn_decode_rows_t<float, 32>(s, q, k, v, o, kv_row, kv_ld, st);
+  return s.Dh == 64 ? attn_decode_rows_t<__nv_bfloat16, 64>(s, q, k, v, o, kv_row, kv_ld, st)
+                    : attn_decode_rows_t<__nv_bfloat16, 32>(s, q, k, v, o, kv_row, kv_ld, st);
 }
 
 int attention_fwd_simt(int dtype, const ns_attn_shape& s, const void* q, const void* k, const void* v, void* o, float* lse, cudaStream_t st) {

@@ -532,8 +532,7 @@ static int launch_da_variant(long long M, int K, const void* x, long long ldx, c
   if (!attr_done) { NS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
   // The column slabs of one row slab are launched as a thread-block CLUSTER: co-scheduled CTAs walk the same rows at the same
   // pace, so the 512-byte pieces of a row are requested together and DRAM sees whole rows (pages) instead of scattered halves.
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(col_slabs, row_slabs);
   cfg.blockDim = dim3(DA_WARPS * 32);
   cfg.dynamicSmemBytes = smem;

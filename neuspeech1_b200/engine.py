@@ -839,7 +839,7 @@ class WhisperEEGEngine:
 
     # ------------------------------------------------------------------ one decoder pass with KV cache
     def _decode_logits(self, ids: torch.Tensor, pos: int, cache, kv_all: torch.Tensor, logits: torch.Tensor, Tmax: int,
-                       beams: int = 1):
+                       beams: int = 1, kv_rows: Optional[torch.Tensor] = None):
         """Decoder pass over `ids` (B, Lq) at cache position `pos` (utils/load_model.py:624,704,740-741, HF
         modeling_whisper.py:314-336): self-attention K/V appended to `cache[i]` (B, Tmax, 3d), cross-attention over the
         precomputed `kv_all` ((B / beams)*S, N_dec*2d); logits of the LAST position -> `logits` (B, Vp).
@@ -871,7 +871,11 @@ class WhisperEEGEngine:
             shp_s = ops.attn_shape(B, H, Lq, Lk, Dh, True, Tmax * 3 * d, 3 * d, Tmax * 3 * d, 3 * d, Tmax * 3 * d, 3 * d, Lq * d, d)
             o = ws.get(f"g_o.{tag}", (MLq, d), dt)
             c = cache[i]
-            ops.attention_fwd(shp_s, c[:, pos:], c[:, :, d:], c[:, :, 2 * d:], o)
+            if kv_rows is not None and Lq == 1:
+                # beam search: key/value j of row b sits in cache row kv_rows[b, j] (the reorder permutes the table, not the cache)
+                ops.attention_decode_rows(shp_s, c[:, pos:], c[:, :, d:], c[:, :, 2 * d:], o, kv_rows)
+            else:
+                ops.attention_fwd(shp_s, c[:, pos:], c[:, :, d:], c[:, :, 2 * d:], o)
             h1 = ws.get(f"g_h1.{tag}", (MLq, d), dt)
             ops.gemm_nt(o, W[k + ".wo"], h1, self._ep(bias=W[k + ".bo"], residual=hd, ldr=d))
             ops.layernorm_fwd(h1, W[k + ".ln2.g"], W[k + ".ln2.b"], u)
@@ -898,13 +902,15 @@ class WhisperEEGEngine:
     @torch.no_grad()
     def beam_search(self, x: torch.Tensor, max_length: int, num_beams: int = 5, repetition_penalty: float = 1.0,
                     no_repeat_ngram_size: int = 0, prompt: Optional[torch.Tensor] = None, aug: Optional[dict] = None,
-                    length_penalty: float = 1.0, use_graphs: bool = False) -> torch.Tensor:
+                    length_penalty: float = 1.0, use_graphs: bool = True, sequence_bias=None) -> torch.Tensor:
         """`generate(num_beams=K, repetition_penalty, no_repeat_ngram_size)`: the beams ride in the batch dimension of the
-        decoder pass (rows b*K + k) and in the query dimension of its cross-attention; the self-attention cache is gathered
-        after every step like `_reorder_cache` (utils/load_model.py:1353-1360); the scoring loop is
-        neuspeech1_b200/generation.py.  use_graphs: the decoder pass of every position is captured once into a CUDA graph and
-        replayed by later calls of the same shape (as in `greedy`).  Returns the generated suffix (B, <= max_length -
-        prompt_len), pad after EOS."""
+        decoder pass (rows b*K + k) and in the query dimension of its cross-attention.  `_reorder_cache` (utils/load_model.py:
+        1353-1360) becomes a permutation of a (rows, positions) table of cache rows that the self-attention reads through
+        (ns_attention_decode_rows): no cache bytes move.  The vocabulary-sized scoring (log-softmax, repetition penalty, n-gram
+        ban, begin-suppress, top-2K per row) is ONE kernel (ns_beam_row_topk); the host loop of neuspeech1_b200/generation.py only
+        handles (B, 2K)-sized tensors.  use_graphs: the decoder pass of every position is captured once into a CUDA graph and
+        replayed by later calls of the same shape (as in `greedy`).  sequence_bias (evaluation.py:339-343) takes the tensor-op
+        scorer.  Returns the generated suffix (B, <= max_length - prompt_len), pad after EOS."""
         from .generation import beam_search as run_beams
         dm, W, ws, dt = self.dims, self.P, self.ws, self.dtype
         d, S = dm.d_model, dm.max_source_positions
@@ -919,47 +925,71 @@ class WhisperEEGEngine:
             prompt = torch.full((B, 1), dm.decoder_start_token_id, dtype=torch.long, device=self.device)
         prompt = prompt.to(self.device, torch.long).contiguous()
         L0 = prompt.shape[1]
-        cache = [ws.get(f"bs_qkv.{K}.{i}", (B * K, max_length, 3 * d), dt) for i in range(dm.dec_layers)]
-        logits = ws.get(f"bs_logits.{K}", (B * K, dm.Vp), torch.float32 if dt == torch.float32 else dt)
+        N = B * K
+        cache = [ws.get(f"bs_qkv.{K}.{i}", (N, max_length, 3 * d), dt) for i in range(dm.dec_layers)]
+        logits = ws.get(f"bs_logits.{K}", (N, dm.Vp), torch.float32 if dt == torch.float32 else dt)
+        # cache-row table: position j of logical row r was written by (and still sits in) physical row rows[r, j]
+        rows = ws.get(f"bs_rows.{K}", (N, max_length), torch.int32)
+        rows.copy_(torch.arange(N, dtype=torch.int32, device=self.device)[:, None].expand(N, max_length))
+        ident = ws.get(f"bs_ident.{K}", (N,), torch.int32)
+        ident.copy_(torch.arange(N, dtype=torch.int32, device=self.device))
+        state = {"pos": 0}
 
         graphs = self._decode_graphs if use_graphs else None
 
         def step_fn(tokens: torch.Tensor, pos: int) -> torch.Tensor:
             Lq = tokens.shape[1]
-            ids = ws.get(f"bs_ids.{K}.{Lq}", (B * K, Lq), torch.long)       # static buffer: the pass below may be a graph replay
+            ids = ws.get(f"bs_ids.{K}.{Lq}", (N, Lq), torch.long)       # static buffer: the pass below may be a graph replay
             ids.copy_(tokens)
+            state["pos"] = pos + Lq
             if graphs is None:
-                self._decode_logits(ids, pos, cache, kv_all, logits, max_length, beams=K)
+                self._decode_logits(ids, pos, cache, kv_all, logits, max_length, beams=K, kv_rows=rows)
                 return logits
             key = ("beam", B, K, max_length, Lq, pos, self._weights_version)
             ent = graphs.get(key)
             if ent is None or ent[1] != ws.gen:
-                self._decode_logits(ids, pos, cache, kv_all, logits, max_length, beams=K)   # eager once: sizes the workspace
+                self._decode_logits(ids, pos, cache, kv_all, logits, max_length, beams=K, kv_rows=rows)   # eager once: sizes the workspace
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self._decode_logits(ids, pos, cache, kv_all, logits, max_length, beams=K)
+                    self._decode_logits(ids, pos, cache, kv_all, logits, max_length, beams=K, kv_rows=rows)
                 graphs[key] = (g, ws.gen)
             else:
                 ent[0].replay()
             return logits
 
         def reorder_fn(beam_idx: torch.Tensor):
-            for c in cache:
-                c.copy_(c.index_select(0, beam_idx))
+            # positions < pos: inherit the parent's table; the next token's K/V will be written by the row itself
+            p = state["pos"]
+            rows[:, :p] = rows[:, :p].index_select(0, beam_idx)
+
+        scorer = None
+        if not sequence_bias and 2 * K <= 16:
+            C2 = 2 * K
+            rs = ws.get(f"bs_rs.{K}", (N, C2), torch.float32)
+            rt = ws.get(f"bs_rt.{K}", (N, C2), torch.int32)
+
+            def scorer(lg, flat, run_score, first):
+                ops.beam_row_topk(lg, dm.vocab, flat.contiguous(), run_score.reshape(-1).contiguous(), repetition_penalty,
+                                  no_repeat_ngram_size, self.suppress if (first and self.suppress.numel()) else None, C2, rs, rt)
+                top_score, idx = torch.topk(rs.view(B, K * C2), C2, dim=1)
+                return top_score, idx // C2, rt.view(B, K * C2).gather(1, idx).long()
 
         out = run_beams(step_fn, reorder_fn, prompt, K, max_length, dm.vocab, dm.eos_token_id, dm.pad_token_id,
-                        dm.begin_suppress_tokens, repetition_penalty, no_repeat_ngram_size, length_penalty)
+                        dm.begin_suppress_tokens, repetition_penalty, no_repeat_ngram_size, length_penalty,
+                        sequence_bias=sequence_bias, scorer=scorer)
         return out[:, L0:].contiguous()
 
     # ------------------------------------------------------------------ greedy decode with KV cache
     @_on_device
     @torch.no_grad()
     def greedy(self, x: torch.Tensor, max_length: int, prompt: Optional[torch.Tensor] = None, aug: Optional[dict] = None,
-               use_graphs: bool = False) -> torch.Tensor:
+               use_graphs: bool = True, eos_check_every: int = 16) -> torch.Tensor:
         """Batched greedy generate (utils/load_model.py:1072-1351 -> GenerationMixin greedy): encoder once, cross-K/V once,
         then one-token decoder steps against the self-attention cache.  Returns the generated suffix (B, n_new) int64;
-        rows that hit EOS emit pad afterwards; begin_suppress_tokens are masked at the first generated position."""
+        rows that hit EOS emit pad afterwards; begin_suppress_tokens are masked at the first generated position.  Every
+        `eos_check_every` positions the host looks at the finished flags and stops once every row has emitted EOS (the
+        remaining positions are pad, as HF pads finished rows)."""
         dm, W, ws, dt = self.dims, self.P, self.ws, self.dtype
         d, S, F, H = dm.d_model, dm.max_source_positions, dm.dec_ffn, dm.dec_heads
         Dh = d // H
@@ -983,6 +1013,7 @@ class WhisperEEGEngine:
         nxt = ws.get("g_next", (B,), torch.long)
         logits = ws.get("g_logits", (B, dm.Vp), torch.float32 if dt == torch.float32 else dt)
         out = ws.get(f"g_out.{n_new}", (B, n_new), torch.long)
+        out.fill_(dm.pad_token_id)
         ids0 = ws.get(f"g_ids0.{L0}", (B, L0), torch.long)
         ids0.copy_(prompt)
 
@@ -1013,4 +1044,6 @@ class WhisperEEGEngine:
                 else:
                     ent[0].replay()
             pos += ids.shape[1]
+            if eos_check_every and step % eos_check_every == eos_check_every - 1 and step + 1 < n_new and bool(finished.all()):
+                break                                                 # every row is past its EOS: the rest stays pad
         return out.clone()

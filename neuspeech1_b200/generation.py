@@ -6,8 +6,9 @@ The loop is model-agnostic host logic over torch tensors on whatever device the 
 reference inherits from `transformers` (GenerationMixin beam search with the default `early_stopping=False`,
 `length_penalty=1.0`, one EOS id, `num_return_sequences=1`):
 
-  * scores are log-softmax of the logits; the processors act on them in this order: repetition penalty (a seen token's
-    score s becomes s*penalty if s < 0 else s/penalty), no-repeat-n-gram ban, begin-suppress at the first generated position
+  * scores are log-softmax of the logits; the processors act on them in HF's order: sequence bias (evaluation.py:339-343,
+    `sequence_bias={(token ids): bias}`), repetition penalty (a seen token's score s becomes s*penalty if s < 0 else
+    s/penalty), no-repeat-n-gram ban, begin-suppress at the first generated position
   * per sample the best 2K of the K*V continuations are kept; the K best that did NOT just stop continue, the ones among the
     first K that did stop (EOS, or the length limit) become finished hypotheses scored by sum-logprob / generated_length**lp
   * a sample is done when its best running score, normalised by the current generated length, can no longer beat its worst
@@ -58,13 +59,58 @@ def apply_no_repeat_ngram(scores: torch.Tensor, seqs: torch.Tensor, n: int) -> t
     return scores
 
 
+def apply_sequence_bias(scores: torch.Tensor, seqs: torch.Tensor, sequence_bias) -> torch.Tensor:
+    """transformers SequenceBiasLogitsProcessor: `sequence_bias` maps token-id tuples to a bias; a length-1 entry biases its
+    token everywhere, a longer one biases its last token in the rows whose latest tokens equal its prefix."""
+    if not sequence_bias:
+        return scores
+    scores = scores.clone()
+    t = seqs.shape[1]
+    for ids, bias in sequence_bias.items():
+        ids = tuple(int(i) for i in ids)
+        if any(i >= scores.shape[1] for i in ids):
+            raise ValueError(f"sequence_bias token out of the vocabulary: {ids}")
+        if len(ids) == 1:
+            scores[:, ids[0]] += float(bias)
+        elif len(ids) <= t:
+            pre = torch.tensor(ids[:-1], dtype=seqs.dtype, device=seqs.device)
+            rows = (seqs[:, t - len(pre):] == pre).all(dim=1)
+            scores[:, ids[-1]] += rows.to(scores.dtype) * float(bias)
+    return scores
+
+
+def torch_scorer(vocab: int, num_beams: int, begin_suppress_tokens: Sequence[int], repetition_penalty: float, no_repeat_ngram_size: int,
+                 sequence_bias=None):
+    """The scoring step as plain tensor ops (CPU tests, sequence_bias): (logits (B*K, >=V), seqs (B*K, t), run_score (B, K),
+    first) -> (top_score, src_beam, tok), each (B, 2K)."""
+    K = num_beams
+
+    def score(logits, flat, run_score, first):
+        B = run_score.shape[0]
+        lp = torch.log_softmax(logits[:, :vocab].to(torch.float32), dim=-1)
+        lp = apply_sequence_bias(lp, flat, sequence_bias)
+        lp = apply_repetition_penalty(lp, flat, repetition_penalty)
+        lp = apply_no_repeat_ngram(lp, flat, no_repeat_ngram_size)
+        if first and len(begin_suppress_tokens):
+            lp = lp.index_fill(1, torch.tensor(list(begin_suppress_tokens), dtype=torch.long, device=lp.device), float("-inf"))
+        acc = (lp.view(B, K, vocab) + run_score[:, :, None]).view(B, K * vocab)
+        top_score, top_idx = torch.topk(acc, 2 * K, dim=1)
+        return top_score, top_idx // vocab, top_idx % vocab
+
+    return score
+
+
 @torch.no_grad()
 def beam_search(step_fn: Callable[[torch.Tensor, int], torch.Tensor], reorder_fn: Callable[[torch.Tensor], None],
                 prompt: torch.Tensor, num_beams: int, max_length: int, vocab: int, eos_token_id: int, pad_token_id: int,
                 begin_suppress_tokens: Sequence[int] = (), repetition_penalty: float = 1.0, no_repeat_ngram_size: int = 0,
-                length_penalty: float = 1.0) -> torch.Tensor:
+                length_penalty: float = 1.0, sequence_bias=None, scorer=None) -> torch.Tensor:
     """-> best hypothesis per sample, (B, <= max_length) int64 including the prompt, padded with `pad_token_id`.
-    `prompt` is (B, L0); the first call of step_fn receives the prompt repeated K times per sample (rows b*K + k)."""
+    `prompt` is (B, L0); the first call of step_fn receives the prompt repeated K times per sample (rows b*K + k).
+    `scorer(logits, seqs, run_score, first) -> (top_score, src_beam, tok)` is the vocabulary-sized part of a step: the B200
+    engine passes its fused kernel (ns_beam_row_topk), the default is `torch_scorer`."""
+    if scorer is None:
+        scorer = torch_scorer(vocab, num_beams, begin_suppress_tokens, repetition_penalty, no_repeat_ngram_size, sequence_bias)
     dev = prompt.device
     B, L0 = prompt.shape
     K = num_beams
@@ -81,7 +127,6 @@ def beam_search(step_fn: Callable[[torch.Tensor, int], torch.Tensor], reorder_fn
     can_improve = torch.ones(B, 1, dtype=torch.bool, device=dev)
     first_k = torch.zeros(2 * K, dtype=torch.bool, device=dev)
     first_k[:K] = True
-    suppress = torch.tensor(list(begin_suppress_tokens), dtype=torch.long, device=dev) if len(begin_suppress_tokens) else None
     batch_off = (torch.arange(B, device=dev) * K)[:, None]
 
     def gather(x, idx):                                             # x (B, n, ...), idx (B, m) -> (B, m, ...)
@@ -93,16 +138,8 @@ def beam_search(step_fn: Callable[[torch.Tensor, int], torch.Tensor], reorder_fn
     while True:
         flat = run_seq[:, :, :cur].reshape(B * K, cur)
         tokens = flat if cur == L0 else flat[:, -1:]
-        logits = step_fn(tokens, 0 if cur == L0 else cur - 1)[:, :vocab].to(torch.float32)
-        lp = torch.log_softmax(logits, dim=-1)
-        lp = apply_repetition_penalty(lp, flat, repetition_penalty)
-        lp = apply_no_repeat_ngram(lp, flat, no_repeat_ngram_size)
-        if suppress is not None and cur == L0:
-            lp = lp.index_fill(1, suppress, float("-inf"))
-        acc = (lp.view(B, K, vocab) + run_score[:, :, None]).view(B, K * vocab)
-        top_score, top_idx = torch.topk(acc, 2 * K, dim=1)
-        src_beam = top_idx // vocab
-        tok = top_idx % vocab
+        logits = step_fn(tokens, 0 if cur == L0 else cur - 1)
+        top_score, src_beam, tok = scorer(logits, flat, run_score, cur == L0)
         cand = gather(run_seq, src_beam)
         cand[:, :, cur] = tok
         stop = (tok == eos_token_id) | (cur + 1 >= max_length)      # EOS, or the length limit reached by this token

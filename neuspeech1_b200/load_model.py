@@ -322,25 +322,35 @@ class WhisperEEGForConditionalGeneration(nn.Module):
     @torch.no_grad()
     def generate(self, input_features=None, do_sample: bool = False, num_beams: int = 1, max_length: Optional[int] = None,
                  max_new_tokens: Optional[int] = None, decoder_input_ids=None, repetition_penalty: float = 1.0,
-                 no_repeat_ngram_size: int = 0, **unused):
+                 no_repeat_ngram_size: int = 0, sequence_bias=None, **unused):
         """`generate` as the reference calls it: greedy with KV cache (utils/process_str.py:54-55) and the beam search of
-        evaluation.py:370-385 (`num_beams=5, repetition_penalty=5.0, no_repeat_ngram_size=2`).  Sampling, beam groups and
-        sequence_bias are refused loudly rather than approximated.  Returns the generated suffix like HF's Whisper wrapper."""
-        if do_sample or unused.get("num_beam_groups", 1) != 1 or unused.get("sequence_bias") is not None:
-            raise NotImplementedError("neuspeech1_b200.generate implements greedy and plain beam search (no sampling, "
-                                      "beam groups or sequence_bias)")
+        evaluation.py:370-385 (`num_beams=5, repetition_penalty=5.0, no_repeat_ngram_size=2`, optionally `sequence_bias`,
+        :339-343).  Sampling and beam groups are refused loudly rather than approximated.  The decoder passes replay CUDA
+        graphs (captured on first use per shape).  Returns the generated suffix like HF's Whisper wrapper."""
+        if do_sample or unused.get("num_beam_groups", 1) != 1:
+            raise NotImplementedError("neuspeech1_b200.generate implements greedy and plain beam search (no sampling, no beam groups)")
         L0 = 1 if decoder_input_ids is None else decoder_input_ids.shape[1]
         if max_new_tokens is not None:
             max_length = L0 + max_new_tokens
         if max_length is None:
             max_length = self.dims.max_target_positions
         eng = self._engine()
+        self._sync_trainables_to_engine()
         x = input_features.to(self.device_)
-        if num_beams == 1 and repetition_penalty == 1.0 and not no_repeat_ngram_size:
+        if num_beams == 1 and repetition_penalty == 1.0 and not no_repeat_ngram_size and not sequence_bias:
             return eng.greedy(x, max_length=max_length, prompt=decoder_input_ids)
+        if sequence_bias:
+            sequence_bias = {tuple(int(t) for t in k): float(v) for k, v in dict(sequence_bias).items()}
         return eng.beam_search(x, max_length=max_length, num_beams=num_beams, repetition_penalty=repetition_penalty,
                                no_repeat_ngram_size=no_repeat_ngram_size, prompt=decoder_input_ids,
-                               length_penalty=float(unused.get("length_penalty", 1.0)))
+                               length_penalty=float(unused.get("length_penalty", 1.0)), sequence_bias=sequence_bias)
+
+    @staticmethod
+    def _reorder_cache(past_key_values, beam_idx):
+        """utils/load_model.py:1353-1360: reorder a tuple-of-tuples KV cache along the batch axis.  The engine's own beam search
+        never calls it (it permutes a cache-row table instead, engine.beam_search); kept for callers that drive the decoder
+        with an external generation loop."""
+        return tuple(tuple(t.index_select(0, beam_idx.to(t.device)) for t in layer) for layer in past_key_values)
 
     def prepare_inputs_for_generation(self, decoder_input_ids, past_key_values=None, use_cache=None, encoder_outputs=None, **kw):
         if past_key_values is not None:                      # utils/load_model.py:1332-1351: feed only the last token

@@ -162,6 +162,22 @@ def attention_bwd_ws(shape: AttnShape, q, k, v, o, d_o, lse, delta, dq, dk, dv, 
     _call("ns_attention_bwd_ws", (10.0 * shape.B * shape.H * shape.Lq * shape.Lk * shape.Dh * (0.5 if shape.causal else 1.0), 0), ns_dtype(q), C.byref(shape), _p(q), _p(k), _p(v), _p(o), _p(d_o), _p(lse), _p(delta), _p(dq), _p(dk), _p(dv), _p(ws), nbytes, _stream())
 
 
+def attention_decode_rows(shape: AttnShape, q, k, v, o, kv_row):
+    """Single-query attention with a per-(row, position) cache-row table (beam search: no cache copies)."""
+    _call("ns_attention_decode_rows", (4.0 * shape.B * shape.H * shape.Lk * shape.Dh, 0), ns_dtype(q), C.byref(shape), _p(q), _p(k), _p(v), _p(o),
+          _p(kv_row), kv_row.stride(0), _stream())
+    return o
+
+
+def beam_row_topk(logits, V: int, seqs, run_score, penalty: float, ngram: int, suppress, C2: int, out_score, out_tok):
+    """Per beam row the C2 best continuations after log-softmax, repetition penalty, n-gram ban, begin-suppress, + running score."""
+    n_sup = 0 if suppress is None else suppress.numel()
+    _call("ns_beam_row_topk", (0, float(logits.shape[0]) * V * logits.element_size()), ns_dtype(logits), logits.shape[0], V, logits.stride(0),
+          _p(logits), _p(seqs), seqs.stride(0), seqs.shape[1], _p(run_score), float(penalty), int(ngram), _p(suppress), n_sup, C2,
+          _p(out_score), _p(out_tok), _stream())
+    return out_score, out_tok
+
+
 def embed(ids, E, P, pos0: int, h):
     B, L = ids.shape
     _call("ns_embed", (0, 0), ns_dtype(E), B, L, E.shape[1], _p(ids), _p(E), _p(P), pos0, _p(h), _stream())

@@ -369,6 +369,31 @@ def greedy_decode(x: Tensor, P, dims: Dims, max_length: int, lora=None, prompt: 
     return torch.stack(out, dim=1)
 
 
+# --------------------------------------------------------------------------- AdaLoRA (finetune.py:205-208)  -- PARITY UNPINNED
+
+def adalora_loss(x: Tensor, labels: Tensor, P, dims: Dims, master: Dict[str, Tensor], modules, init_r: int = 12,
+                 lora_alpha: float = 32.0, orth_reg_weight: float = 0.5, dropout=None) -> Tensor:
+    """Loss of the reference's AdaLoRA configuration (`AdaLoraConfig(init_r=12, target_r=4, lora_alpha=32, lora_dropout=0.1,
+    orth_reg_weight=0.5)`, finetune.py:205-208; `update_and_allocate` is never called, so the rank stays init_r):
+        y    = base(x) + (dropout(x) @ (A * E).T @ B.T) * lora_alpha / (ranknum + 1e-5)
+        loss = CE + orth_reg_weight * mean over all A, B of ||A A^T - I||_F resp. ||B^T B - I||_F
+    PARITY UNPINNED: PEFT is not on this box and the reference ships no vectors for it; this restates PEFT's SVDLinear /
+    AdaLoraModel.forward from the call site and from memory of PEFT ~0.5.  `master`: {<module>.lora_A.default (r, in),
+    .lora_E.default (r, 1), .lora_B.default (out, r)}; `modules`: module names; dropout = (p, seed) or None."""
+    eff = {}
+    for name in modules:
+        eff[name + ".lora_A.default.weight"] = master[name + ".lora_A.default"] * master[name + ".lora_E.default"]
+        eff[name + ".lora_B.default.weight"] = master[name + ".lora_B.default"]
+    if dropout is not None:
+        eff["__dropout__"] = dropout
+    od = Dims(**{**dims.__dict__, "lora_r": init_r, "lora_alpha": lora_alpha * init_r / (init_r + 1e-5)})
+    ce, _, _ = forward_loss(x, labels, P, od, eff)
+    eye = torch.eye(init_r)
+    reg = sum(torch.norm(master[n + ".lora_A.default"] @ master[n + ".lora_A.default"].T - eye, p="fro")
+              + torch.norm(master[n + ".lora_B.default"].T @ master[n + ".lora_B.default"] - eye, p="fro") for n in modules)
+    return ce + orth_reg_weight * reg / (2 * len(modules))
+
+
 # --------------------------------------------------------------------------- training step
 
 @dataclass

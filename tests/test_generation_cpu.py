@@ -119,3 +119,37 @@ def test_logit_processors():
     out = apply_no_repeat_ngram(scores, seqs3, 3)
     assert out[0, 0] == float("-inf") and torch.isfinite(out[1]).all()
     assert torch.equal(apply_no_repeat_ngram(scores, seqs[:, :1], 3), scores)      # shorter than an n-gram: untouched
+
+
+@pytest.mark.parametrize("seed", [2, 7])
+def test_beam_search_sequence_bias_matches_transformers(seed):
+    """evaluation.py:339-343,380: `generate(..., sequence_bias={(token ids): bias})` (GetSequenceBias, bias -1.0 on phrases of the
+    training set).  Single-token and multi-token entries, applied before the repetition penalty like HF's processor list."""
+    import transformers
+    transformers.logging.set_verbosity_error()
+    V = 60
+    dims = O.Dims(d_model=64, enc_layers=1, dec_layers=2, enc_heads=2, dec_heads=2, enc_ffn=128, dec_ffn=128, vocab=V,
+                  max_source_positions=40, max_target_positions=24, eeg_ch=6, pad_token_id=V - 3, eos_token_id=V - 3,
+                  decoder_start_token_id=V - 2, begin_suppress_tokens=(20, V - 4), lora_r=4, lora_alpha=8)
+    P = O.init_params(dims, seed=seed, std=0.5)
+    g = torch.Generator().manual_seed(seed)
+    B, K, max_length = 4, 5, 16
+    x = torch.randn(B, dims.eeg_ch, dims.T, generator=g) * 2
+    prompt = torch.full((B, 1), dims.decoder_start_token_id, dtype=torch.long)
+    m = build_hf(dims, P)
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        plain = m.generate(x, do_sample=False, num_beams=K, repetition_penalty=5.0, no_repeat_ngram_size=2, max_length=max_length)
+    # bias against what the unbiased search produced: its first token everywhere, and its first bigram / trigram of sample 0
+    bias = {(int(plain[0, 0]),): -3.0, (int(plain[1, 0]), int(plain[1, 1])): -4.0, (int(plain[2, 0]), int(plain[2, 1]), int(plain[2, 2])): -4.0,
+            (7,): 1.5}
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = m.generate(x, do_sample=False, num_beams=K, repetition_penalty=5.0, no_repeat_ngram_size=2, max_length=max_length,
+                         sequence_bias=bias)
+    assert not torch.equal(ref[:, :plain.shape[1]] if ref.shape[1] >= plain.shape[1] else ref, plain[:, :ref.shape[1]])   # the bias matters
+    step_fn, reorder_fn = _oracle_step_fns(dims, P, O.encoder(x, P, dims, None), K)
+    out = beam_search(step_fn, reorder_fn, prompt, K, max_length, dims.vocab, dims.eos_token_id, dims.pad_token_id,
+                      dims.begin_suppress_tokens, 5.0, 2, sequence_bias=bias)
+    for b in range(B):
+        assert _strip(out[b, 1:], dims.pad_token_id) == _strip(ref[b], dims.pad_token_id), (b, out[b], ref[b])

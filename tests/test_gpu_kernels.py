@@ -608,3 +608,57 @@ def test_lora_dx_fix(M, K, G, r, with_z, dtype):
         assert rel(dA1, dA0) < 1e-5
         assert not bool((dxb != dx0)[~sel].any())                     # nothing but dropped positions is touched
         assert rel(dxb.float(), ref) < 1e-2 and rel(dxb.float()[sel], ref[sel]) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------ beam-search step kernels
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("V,K,pen,ngram,t,first", [(51865, 5, 5.0, 2, 37, False), (51865, 5, 5.0, 2, 1, True), (120, 3, 1.3, 3, 9, False),
+                                                   (1000, 8, 2.0, 1, 20, False), (51865, 1, 1.0, 0, 5, True)])
+def test_beam_row_topk_matches_tensor_ops(V, K, pen, ngram, t, first, dtype):
+    """ns_beam_row_topk + the (B, K*2K) merge == log_softmax / repetition penalty / n-gram ban / begin-suppress / top-2K over
+    K*V done with tensor ops (neuspeech1_b200.generation.torch_scorer, the loop pinned to transformers on the CPU)."""
+    from neuspeech1_b200.generation import torch_scorer
+    B = 4
+    N, C2 = B * K, 2 * K
+    g = torch.Generator().manual_seed(V + K)
+    Vp = (V + 15) // 16 * 16
+    logits = (torch.randn(N, Vp, generator=g) * 3).to(DEV, dtype)
+    seqs = torch.randint(0, min(V, 50), (N, t), generator=g).to(DEV)            # few distinct tokens: repeats and n-gram hits
+    if t > 4:
+        seqs[:, -1] = seqs[:, 1]                                               # the last token has occurred before: bans happen
+    run = (torch.randn(B, K, generator=g) * 2).to(DEV)
+    sup = (3, 7, V - 1)
+    ref_s, ref_b, ref_t = torch_scorer(V, K, sup, pen, ngram)(logits, seqs, run, first)
+    rs = torch.empty(N, C2, dtype=torch.float32, device=DEV); rt = torch.empty(N, C2, dtype=torch.int32, device=DEV)
+    ops.beam_row_topk(logits, V, seqs, run.reshape(-1).contiguous(), pen, ngram,
+                      torch.tensor(sup, dtype=torch.int32, device=DEV) if first else None, C2, rs, rt)
+    assert bool((rs[:, :-1] >= rs[:, 1:]).all())                               # rows come out sorted
+    top, idx = torch.topk(rs.view(B, K * C2), C2, dim=1)
+    got_b, got_t = idx // C2, rt.view(B, K * C2).gather(1, idx).long()
+    assert torch.allclose(top, ref_s, atol=2e-4 * (1 + float(ref_s.abs().max())), rtol=1e-5)
+    same = (got_b == ref_b) & (got_t == ref_t)
+    # a swapped pair can only come from (near-)equal scores
+    assert bool((same | ((top - ref_s).abs() < 1e-3)).all()), (top, ref_s, got_b, ref_b, got_t, ref_t)
+    if dtype == torch.float32:                                                 # bf16 logits tie exactly all the time: any order of a tie is right
+        assert float(same.float().mean()) > 0.97
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_attention_decode_rows_reads_through_the_table(dtype):
+    """Single-query attention over a cache whose (row, position) entries live in other rows (beam reorder as a table
+    permutation): equals plain attention over the gathered cache."""
+    B, H, Dh, T, Lk = 10, 8, 64, 48, 29
+    d = H * Dh
+    cache = rnd(B, T, 3 * d, dtype=dtype, seed=3)
+    g = torch.Generator().manual_seed(1)
+    rows = torch.randint(0, B, (B, T), generator=g).to(torch.int32).to(DEV)
+    q = cache[:, Lk - 1, :d].contiguous()
+    gathered = torch.empty(B, T, 3 * d, dtype=dtype, device=DEV)
+    for j in range(T):
+        gathered[:, j] = cache[rows[:, j].long(), j]
+    shp = ops.attn_shape(B, H, 1, Lk, Dh, True, d, d, T * 3 * d, 3 * d, T * 3 * d, 3 * d, d, d)
+    o_ref = torch.empty(B, d, dtype=dtype, device=DEV)
+    ops.attention_fwd(shp, q, gathered[:, :, d:], gathered[:, :, 2 * d:], o_ref)
+    o = torch.empty(B, d, dtype=dtype, device=DEV)
+    ops.attention_decode_rows(shp, q, cache[:, :, d:], cache[:, :, 2 * d:], o, rows)
+    assert rel(o.float(), o_ref.float()) < 1e-5

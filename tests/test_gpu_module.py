@@ -132,3 +132,49 @@ def test_trainer_fit_follows_hf_schedule_and_saves_best_adapter(tmp_path):
         files = set(os.listdir(tmp_path / ck))
         assert {"adapter_model.safetensors", "adapter_config.json"} <= files
     assert any(d.startswith("checkpoint-3") or d.startswith("checkpoint-6") for d in os.listdir(tmp_path))
+
+
+def test_generate_contract_beams_bias_and_early_stop():
+    """model.generate as evaluation.py:370-385 calls it: beam 5 + penalties (+ sequence_bias, :339-343) return what the tensor-op
+    loop over the oracle decoder returns (that loop is pinned to transformers on the CPU); greedy stops early once every row
+    has emitted EOS; `_reorder_cache` is there for external loops (utils/load_model.py:1353-1360)."""
+    from neuspeech1_b200.generation import beam_search
+    dims = O.Dims(d_model=256, enc_layers=2, dec_layers=2, enc_heads=4, dec_heads=4, enc_ffn=512, dec_ffn=512, vocab=120,
+                  max_source_positions=160, max_target_positions=32, eeg_ch=24, pad_token_id=117, eos_token_id=117,
+                  decoder_start_token_id=118, begin_suppress_tokens=(20, 116), lora_r=32, lora_alpha=64)
+    P = O.init_params(dims, seed=0, std=0.12)
+    x, _ = O.synthetic_batch(dims, B=3, L=8, seed=1)
+    m = WhisperForConditionalGeneration(ModelDims.from_any(dims), P, None, dtype=torch.float32, device=DEV)
+    m.eval()
+    enc = O.encoder(x, P, dims, None)
+    K = 5
+
+    def ref_ids(bias):
+        state = {}
+
+        def step_fn(tokens, pos):
+            if pos == 0:
+                state["enc"] = enc.repeat_interleave(K, 0); state["past"] = None
+            y, state["past"] = O.decoder(tokens, state["enc"], P, dims, state["past"])
+            return y[:, -1] @ P["model.decoder.embed_tokens.weight"].t()
+
+        def reorder_fn(idx):
+            state["past"] = [[t.index_select(0, idx) for t in layer] for layer in state["past"]]
+
+        prompt = torch.full((3, 1), dims.decoder_start_token_id, dtype=torch.long)
+        return beam_search(step_fn, reorder_fn, prompt, K, 20, dims.vocab, dims.eos_token_id, dims.pad_token_id,
+                           dims.begin_suppress_tokens, 5.0, 2, sequence_bias=bias)[:, 1:]
+
+    plain = m.generate(x.to(DEV), num_beams=K, repetition_penalty=5.0, no_repeat_ngram_size=2, max_length=20).cpu()
+    assert torch.equal(plain, ref_ids(None))
+    bias = {(int(plain[0, 0]),): -5.0, (int(plain[1, 0]), int(plain[1, 1])): -5.0}
+    biased = m.generate(x.to(DEV), num_beams=K, repetition_penalty=5.0, no_repeat_ngram_size=2, max_length=20, sequence_bias=bias).cpu()
+    assert torch.equal(biased, ref_ids(bias)) and not torch.equal(biased[:, :plain.shape[1]], plain[:, :biased.shape[1]])
+    # greedy: with EOS made overwhelmingly likely after the first token every row finishes at once and the loop stops early
+    g1 = m.generate(x.to(DEV), max_length=dims.max_target_positions).cpu()
+    assert g1.shape == (3, dims.max_target_positions - 1)
+    ref = O.greedy_decode(x, P, dims, max_length=dims.max_target_positions)
+    assert torch.equal(g1[:, :ref.shape[1]], ref) and bool((g1[:, ref.shape[1]:] == dims.pad_token_id).all())
+    past = ((torch.arange(6.).view(3, 2), torch.ones(3, 2)),)
+    out = m._reorder_cache(past, torch.tensor([2, 0, 0]))
+    assert torch.equal(out[0][0], past[0][0][[2, 0, 0]])
