@@ -34,6 +34,31 @@ import torch
 
 FLOP_PER_SAMPLE = {208: 267.92e9, 273: 270.31e9}      # SURVEY.md 8(d) / BASELINE.md section 4 (Whisper-base, L=32, r=32)
 METRIC = "EEG train samples/sec (Whisper-base, eeg_ch=208)"
+# --config: BASELINE.json configs[1] (default, the configuration the metric is quoted on) and the other GPU configurations
+CONFIGS = {
+    "train": dict(eeg_ch=208, batch=64, metric=METRIC),
+    "c273": dict(eeg_ch=273, batch=64, metric="EEG train samples/sec (Whisper-base, eeg_ch=273)"),
+    "large": dict(eeg_ch=273, batch=16, metric="EEG train samples/sec (Whisper-large-v3 widths, eeg_ch=273)",
+                  dims=dict(d_model=1280, enc_layers=32, dec_layers=32, enc_heads=20, dec_heads=20, enc_ffn=5120, dec_ffn=5120,
+                            vocab=51866)),
+    "decode": dict(eeg_ch=273, batch=128, metric="EEG greedy decode samples/sec (Whisper-base, eeg_ch=273, B=128, max 448 tokens)"),
+    "pipeline": dict(eeg_ch=208, batch=64, metric="EEG train samples/sec from an HBM-resident unpadded sample store (Whisper-base, eeg_ch=208)"),
+}
+
+
+def flop_per_sample(d, L: int) -> float:
+    """Model of SURVEY.md 8(d): forward + backward of one sample (frozen weights: no wgrad except LoRA and the stem)."""
+    T, S, C, dm, r = d.T, d.max_source_positions, d.eeg_ch, d.d_model, d.lora_r
+    F, Fd, V = d.enc_ffn, d.dec_ffn, d.vocab
+    convA, convB, convC = 6 * T * C * dm, 3 * T * dm * dm, 1.5 * T * dm * dm
+    qkvo, attn, mlp = 8 * S * dm * dm, 4 * S * S * dm, 4 * S * dm * F
+    lora = 2 * S * r * (4 * (2 * dm) + 2 * (dm + F))
+    dec_lin = 8 * L * dm * dm + 4 * L * dm * dm + 4 * S * dm * dm + 4 * L * dm * Fd
+    dec_attn = 4 * L * L * dm + 4 * L * S * dm
+    proj = 2 * L * dm * V
+    fwd = convA + convB + convC + d.enc_layers * (qkvo + attn + mlp + lora) + d.dec_layers * (dec_lin + dec_attn) + proj
+    bwd = convA + 2 * (convB + convC) + d.enc_layers * (qkvo + 2 * attn + mlp + 2 * lora) + d.dec_layers * (dec_lin + 2 * dec_attn) + proj
+    return float(fwd + bwd)
 
 
 def measured_peaks():
@@ -137,23 +162,30 @@ def cpu_train_steps(B, L, steps, warmup, eeg_ch=208, threads=None, lora_dropout=
     return B * steps / dt, threads, dt / max(steps, 1)
 
 
-def workload_name(eeg_ch, B, L, p=0.05):
-    return (f"Gwilliams-shaped LoRA fine-tune step: Whisper-base, eeg_ch={eeg_ch}, B={B}/GPU, L={L}, "
-            f"LoRA r=32 alpha=64 lora_dropout={p:g} on 36 encoder linears + 3 stem convs, augmentation1 (identity) pass")
+def workload_name(eeg_ch, B, L, p=0.05, config="train"):
+    shape = {"train": "Gwilliams-shaped", "c273": "Schoffelen-shaped", "large": "Scale-up (large-v3 widths: d_model=1280, 32+32 layers)",
+             "pipeline": "Gwilliams-shaped, batches gathered from an HBM-resident unpadded bf16 sample store,"}.get(config, "")
+    model = "Whisper-large-v3-shaped" if config == "large" else "Whisper-base"
+    n_lin = 32 * 6 if config == "large" else 36
+    return (f"{shape} LoRA fine-tune step: {model}, eeg_ch={eeg_ch}, B={B}/GPU, L={L}, "
+            f"LoRA r=32 alpha=64 lora_dropout={p:g} on {n_lin} encoder linears + 3 stem convs, augmentation1 (identity) pass")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.config not in ("train", "c273"):
+        print(json.dumps({"impl": "reference", "unavailable": f"the CPU port is timed on the training configurations only (--config {args.config})"}))
+        return
     B = 4                                                   # bounded sample of the B=64 workload (about 1 s of host time per step)
     warm = min(args.warmup, 1)
     sps, cores, sec = cpu_train_steps(B, args.labels, args.steps, warm, args.eeg_ch, lora_dropout=args.lora_dropout)
     line = {
-        "impl": "reference", "metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": args.metric, "value": sps, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.eeg_ch, args.batch, args.labels, args.lora_dropout), "parallelism": "host cores",
+        "config": {"workload": workload_name(args.eeg_ch, args.batch, args.labels, args.lora_dropout, args.config), "parallelism": "host cores",
                    "sample": f"each step is a bounded sample of that workload: B={B} instead of {args.batch} per step"},
         "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} training steps of B={B} (oracle port of the reference path; PEFT/accelerate absent)"},
@@ -179,7 +211,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    dims = ModelDims(eeg_ch=args.eeg_ch)
+    dims = ModelDims(eeg_ch=args.eeg_ch, **CONFIGS[args.config].get("dims", {}))
     B, L = args.batch, args.labels
     model = WhisperEEGForConditionalGeneration(dims, random_params(dims, seed=0), random_lora(dims, seed=1, b_std=0.01),
                                                dtype=torch.bfloat16, device=dev, lora_dropout=args.lora_dropout)
@@ -301,18 +333,19 @@ def run_ours(args):
             ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": top_name, "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
                     "traffic": traffic, "launches": top["n"], "share_of_step": top["ms"] / tot, "peak_source": peaks["src"]}
-        step_tf = value / world * FLOP_PER_SAMPLE.get(args.eeg_ch, 267.92e9) / 1e12
+        fps = FLOP_PER_SAMPLE.get(args.eeg_ch, 267.92e9) if args.config in ("train", "c273") else flop_per_sample(dims, L)
+        step_tf = value / world * fps / 1e12
         shares = {k: round(v["ms"] / tot, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])[:8]}
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.config in ("train", "c273"):
             sps, cores, sec = cpu_train_steps(4, L, 2, 1, args.eeg_ch, lora_dropout=args.lora_dropout)
             cpu = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
                    "sample": "2 training steps of B=4 after 1 warm-up (oracle port of the reference path, fp32, all host threads)"}
         line = {
-            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": args.metric, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": workload_name(args.eeg_ch, B, L, args.lora_dropout),
+            "config": {"workload": workload_name(args.eeg_ch, B, L, args.lora_dropout, args.config),
                        "parallelism": f"dp{world}", "l2": "inputs and activations per step (>10 GB) exceed the 126 MB L2",
                        "launch": "pack + forward + backward replayed as one CUDA graph per input buffer, all-reduce and optimizer launched eagerly"},
             "clocks": clocks, "gpu_launches": launches,
@@ -320,7 +353,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": 4},
             "roofline": roof,
             "step_roofline": {"achieved_tflops": step_tf, "frac_of_sustained_peak": step_tf / peaks["tf_sustained"],
-                              "flop_per_sample": FLOP_PER_SAMPLE.get(args.eeg_ch)},
+                              "flop_per_sample": fps},
             "kernel_shares": shares,
             "cpu_baseline": cpu,
         }
@@ -333,21 +366,193 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ config #4: batched greedy decode
+def run_decode(args):
+    """BASELINE.json configs[3]: Whisper-base, eeg_ch=273, B=128, merged weights (evaluation.py:88-89), greedy with KV cache, max 448
+    tokens; random-init weights never emit EOS, so every row runs all 447 new tokens (the worst case).  A "step" is one batch.
+    value: samples/s with the batch resident in HBM; e2e: model.generate() on a pinned HOST batch, ids copied back.  roofline: the
+    bytes a token step MUST read (decoder weights once + the cross-attention K/V of every sample + the self-attention cache up to
+    the current position, averaged over positions) / the measured time per token step, against the HBM copy peak."""
+    from neuspeech1_b200 import _abi
+    from neuspeech1_b200.engine import ModelDims
+    from neuspeech1_b200.load_model import WhisperEEGForConditionalGeneration
+    from neuspeech1_b200.weights import random_params
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("--config decode runs replicas only (no exchange between ranks): launch it with --gpus 1")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    dims = ModelDims(eeg_ch=args.eeg_ch)
+    B, ML = args.batch, args.max_length
+    model = WhisperEEGForConditionalGeneration(dims, random_params(dims, seed=0), None, dtype=torch.bfloat16, device=dev)
+    model.eval()
+    eng = model.engine
+    g = torch.Generator().manual_seed(3)
+    x_host = (0.3 * torch.randn(B, dims.eeg_ch, dims.T, generator=g)).clamp_(-1, 1).pin_memory()
+    x_dev = x_host.to(dev)
+    out_host = torch.zeros(B, ML, dtype=torch.long).pin_memory()
+
+    def step_resident():
+        return eng.greedy(x_dev, max_length=ML, use_graphs=True)
+
+    def step_e2e():
+        ids = model.generate(x_host.to(dev, non_blocking=True), max_length=ML, do_sample=False, num_beams=1)
+        out_host[:, :ids.shape[1]].copy_(ids, non_blocking=True)
+        return ids
+
+    def timed(fn, steps):
+        lat = []
+        for _ in range(steps):
+            torch.cuda.synchronize()
+            s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+            s.record(); out = fn(); e.record()
+            torch.cuda.synchronize()
+            lat.append(s.elapsed_time(e))
+        return lat, out
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize()
+    _abi.reset_counters()
+    g0 = eng.graph_launches
+    with ClockSampler(0) as clk:
+        lat, out = timed(step_resident, args.steps)
+    launches = (sum(_abi.counters().values()) + (eng.graph_launches - g0)) // max(args.steps, 1)
+    clocks = clk.summary()
+    for _ in range(3):
+        step_e2e()
+    lat_e, _ = timed(step_e2e, args.steps)
+    lat.sort(); lat_e.sort()
+    ms, ms_e = sum(lat) / len(lat), sum(lat_e) / len(lat_e)
+    new_tokens = int(out.shape[1])
+    d, S, Ld, Fd, V = dims.d_model, dims.max_source_positions, dims.dec_layers, dims.dec_ffn, dims.vocab
+    w_bytes = 2.0 * (Ld * (8 * d * d + 2 * d * Fd) + V * d)                  # self q/k/v/o + cross q/o + MLP, tied projection
+    cross_bytes = 2.0 * B * S * Ld * 2 * d
+    self_bytes = 2.0 * B * Ld * 2 * d * (new_tokens / 2.0)                    # cache read, mean over positions
+    step_bytes = w_bytes + cross_bytes + self_bytes
+    peaks = measured_peaks()
+    ms_tok = ms / max(new_tokens, 1)
+    ach = step_bytes / (ms_tok * 1e-3) / 1e9
+    line = {
+        "metric": args.metric, "value": B * 1e3 / ms, "unit": "samples/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms, "p50_ms_per_batch": lat[len(lat) // 2], "ms_per_token_step": ms_tok, "new_tokens": new_tokens,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"Batched evaluation decode: Whisper-base, eeg_ch={args.eeg_ch}, batch {B}, greedy with KV cache, max {ML} tokens, "
+                               "merged weights, random init (no EOS: every row runs to the limit)",
+                   "parallelism": "dp1 (replicas only)", "l2": "the cross-attention K/V of a batch (2.4 GB) exceeds the 126 MB L2",
+                   "launch": "encoder eager, one CUDA graph replay per decoded position"},
+        "clocks": clocks, "gpu_launches": launches,
+        "e2e": {"value": B * 1e3 / ms_e, "unit": "samples/s", "ms_per_step": ms_e, "p50_ms_per_batch": lat_e[len(lat_e) // 2],
+                "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": B * new_tokens * 8},
+        "roofline": {"bound": "hbm", "kernel": "token step (all decoder kernels of one position)", "achieved": ach, "peak": peaks["hbm"],
+                     "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None, "bytes_per_token_step": step_bytes,
+                     "peak_source": peaks["src"]},
+        "cpu_baseline": None,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ resident sample store -> steps
+def run_pipeline(args):
+    """the training set's recordings UNPADDED in HBM (reader.SampleStore, bf16), a batch = three integer
+    vectors; ns_aug_pass gathers / pads / lays out.  value: samples/s of loader -> train_step over whole epochs (labels and tables
+    H2D every step, loss D2H), next to the resident-batch rate of the default config."""
+    import numpy as np
+    from neuspeech1_b200 import _abi
+    from neuspeech1_b200.engine import ModelDims
+    from neuspeech1_b200.load_model import WhisperEEGForConditionalGeneration
+    from neuspeech1_b200.reader import ResidentBatchLoader, SampleStore
+    from neuspeech1_b200.weights import random_lora, random_params
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("--config pipeline is a one-GPU measurement")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    dims = ModelDims(eeg_ch=args.eeg_ch)
+    B, L = args.batch, args.labels
+    rng = np.random.RandomState(0)
+    n_items = B * 8
+    items, labels = [], []
+    for i in range(n_items):                                                   # Gwilliams-like lengths: 2 s .. 25 s at 200 Hz
+        n = int(rng.randint(400, 5000))
+        items.append({"array": (0.3 * rng.standard_normal((dims.eeg_ch, n), dtype=np.float32)).clip(-1, 1), "path": f"/synthetic/gwilliams/{i}.npy"})
+        labels.append(rng.randint(0, 50257, size=L - 4).tolist())
+    t0 = time.perf_counter()
+    store = SampleStore(items, modal_ch=dims.eeg_ch, device=dev, dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    loader = ResidentBatchLoader(store, labels, batch_size=B, max_label_len=L)
+    model = WhisperEEGForConditionalGeneration(dims, random_params(dims, seed=0), random_lora(dims, seed=1, b_std=0.01),
+                                               dtype=torch.bfloat16, device=dev, lora_dropout=args.lora_dropout)
+    model.train()
+    eng = model.engine
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def epoch():
+        n = 0
+        for x, y, aug, slot in loader:
+            loss = eng.train_step(x, y, lr=1e-3, aug=aug)
+            loss_host.copy_(loss, non_blocking=True)
+            n += 1
+        return n
+
+    for _ in range(2):                                                         # both slots seen twice: graphs captured
+        epoch()
+    torch.cuda.synchronize()
+    _abi.reset_counters(); g0 = eng.graph_launches
+    epochs = max(1, args.steps // len(loader))
+    with ClockSampler(0) as clk:
+        s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+        s.record()
+        steps = sum(epoch() for _ in range(epochs))
+        e.record(); torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / steps
+    launches = sum(_abi.counters().values()) + (eng.graph_launches - g0)
+    mean_n = float(store.n.mean())
+    line = {
+        "metric": args.metric, "value": B * 1e3 / ms, "unit": "samples/s", "n_gpus": 1, "steps": steps, "warmup": 2 * len(loader),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload_name(args.eeg_ch, B, L, args.lora_dropout, "pipeline"), "parallelism": "dp1",
+                   "store": {"recordings": n_items, "mean_samples": mean_n, "bytes": int(store.bytes), "build_s": build_s,
+                             "bytes_per_recording_padded_fp32": dims.eeg_ch * dims.T * 4},
+                   "launch": "one CUDA graph per loader slot (tables and labels land in per-slot persistent tensors)"},
+        "clocks": clk.summary(), "gpu_launches": launches,
+        "e2e": {"value": B * 1e3 / ms, "unit": "samples/s", "ms_per_step": ms, "h2d_bytes_per_step": B * (8 + 4 + 4 * 5) + B * L * 8,
+                "d2h_bytes_per_step": 4},
+        "roofline": None, "cpu_baseline": None,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--config", default="train", choices=sorted(CONFIGS),
+                    help="train = BASELINE.json configs[1] (the metric's configuration); c273 / decode / large = configs[2..4]; "
+                         "pipeline = steps fed from the HBM-resident sample store")
+    ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--labels", type=int, default=32)
-    ap.add_argument("--eeg-ch", dest="eeg_ch", type=int, default=208)
+    ap.add_argument("--max-length", dest="max_length", type=int, default=448)
+    ap.add_argument("--eeg-ch", dest="eeg_ch", type=int, default=None)
     ap.add_argument("--lora-dropout", dest="lora_dropout", type=float, default=0.05)     # finetune.py:210
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None)
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    args.batch = args.batch or cfg["batch"]
+    args.eeg_ch = args.eeg_ch or cfg["eeg_ch"]
+    args.metric = cfg["metric"]
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "decode":
+        run_decode(args)
+    elif args.config == "pipeline":
+        run_pipeline(args)
     else:
         run_ours(args)
 

@@ -136,7 +136,9 @@ int ns_greedy_pick(int dtype, int B, int V, long long ld, const void* logits, co
                    int eos, int pad, unsigned char* finished, long long* next_ids, void* stream);
 
 /* ---- EEG augmentation + pad + cast + layout pass (utils/reader.py:552-594, :496-506; utils/augment_eeg.py:15-26,54-56;
- *  utils/utils.py:33-60).  One read of x (B,C,Tin) f32, one write of y.
+ *  utils/utils.py:33-60).  One read of x, one write of y.  x is either the collator's dense (B,C,Tin) batch (src_off NULL) or a
+ *  RAGGED SAMPLE STORE resident in HBM (utils/reader.py:253-303 keeps recordings as unpadded .npy files): channel row c of
+ *  batch slot b starts at x + src_off[b] + c * src_ld[b] (elements), n[b] valid samples; in_dtype says how x is stored.
  *   per sample b: n[b] valid samples, shift[b], taylor edges e0[b], e1[b]; keep-grid bits grid + b*grid_stride (row-major
  *   gc x gl bytes, NULL pointer or flags bit0 clear = no mask) expanded with rep_c[b], rep_t[b];
  *   noise (flags bit1): y = 2x + sigma[b,c]*N(0,1) (Philox, seed) -- the reference's 2x quirk kept.
@@ -146,10 +148,12 @@ typedef struct {
   const int* n; const int* shift; const int* e0; const int* e1; const int* flags;
   const unsigned char* grid; long long grid_stride; const int* gl; const int* rep_c; const int* rep_t;
   const float* sigma; unsigned long long seed;
+  int in_dtype; const long long* src_off; const int* src_ld;
 } ns_aug_args;
-int ns_aug_pass(const ns_aug_args* a, const float* x, void* y, void* stream);
-/* per-(b,c) mean square over the first n[b] samples (for the noise sigma): ms (B,C) fp32 */
-int ns_channel_meansq(int B, int C, int Tin, const int* n, const float* x, float* ms, void* stream);
+int ns_aug_pass(const ns_aug_args* a, const void* x, void* y, void* stream);
+/* per-(b,c) mean square over the first n[b] samples (for the noise sigma): ms (B,C) fp32; same source addressing as ns_aug_pass */
+int ns_channel_meansq(int dtype, int B, int C, int Tin, const int* n, const void* x, float* ms, const long long* src_off,
+                      const int* src_ld, void* stream);
 
 /* ---- small utilities */
 int ns_cast(int src_dtype, int dst_dtype, long long n, const void* src, void* dst, void* stream);

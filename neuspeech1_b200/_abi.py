@@ -41,7 +41,7 @@ class AugArgs(C.Structure):
     _fields_ = [("B", c_i), ("C", c_i), ("Tin", c_i), ("T", c_i), ("Cp", c_i), ("layout", c_i), ("out_dtype", c_i),
                 ("n", c_vp), ("shift", c_vp), ("e0", c_vp), ("e1", c_vp), ("flags", c_vp),
                 ("grid", c_vp), ("grid_stride", c_ll), ("gl", c_vp), ("rep_c", c_vp), ("rep_t", c_vp),
-                ("sigma", c_vp), ("seed", C.c_ulonglong)]
+                ("sigma", c_vp), ("seed", C.c_ulonglong), ("in_dtype", c_i), ("src_off", c_vp), ("src_ld", c_vp)]
 
 
 # name -> argtypes (restype is int unless noted).  Kept in one table so tests can check every symbol of the header.
@@ -67,7 +67,7 @@ SIGNATURES = {
     "ns_cross_entropy": [c_i, c_ll, c_i, c_ll, c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_f, c_vp],
     "ns_greedy_pick": [c_i, c_i, c_i, c_ll, c_vp, c_vp, c_i, c_i, c_i, c_vp, c_vp, c_vp],
     "ns_aug_pass": [C.POINTER(AugArgs), c_vp, c_vp, c_vp],
-    "ns_channel_meansq": [c_i, c_i, c_i, c_vp, c_vp, c_vp, c_vp],
+    "ns_channel_meansq": [c_i, c_i, c_i, c_i, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "ns_cast": [c_i, c_i, c_ll, c_vp, c_vp, c_vp],
     "ns_transpose": [c_i, c_i, c_i, c_i, c_vp, c_ll, c_vp, c_ll, c_f, c_vp],
     "ns_transpose_batched": [c_i, c_i, c_i, c_i, c_i, c_vp, c_vp],

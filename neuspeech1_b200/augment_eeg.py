@@ -92,8 +92,12 @@ class BatchAugmenter:
             p.shift = int(np.random.randint(max_shift, size=None))
         return p
 
-    def plan(self, shapes: Sequence[Sequence[int]], device, static: Optional[dict] = None) -> dict:
+    def plan(self, shapes: Sequence[Sequence[int]], device, static: Optional[dict] = None, x: Optional[torch.Tensor] = None,
+             src: Optional[dict] = None, seed: int = 0) -> dict:
         """Draw the batch's random decisions -> keyword arguments of ops.aug_pass / engine.encode(aug=...).
+
+        x (+ src = {"src_off", "src_ld"} for a ragged sample store): the batch on the device.  Needed only when the configuration
+        can draw gaussian noise: its per-channel sigma is a statistic of the samples (`ns_channel_meansq`).
 
         static: a dict made by `static_buffers(B, grid_cap, device)`.  The decisions are then written INTO those persistent
         device tensors and the returned tensors are views of them, so that the arguments keep their addresses from step to step
@@ -133,7 +137,26 @@ class BatchAugmenter:
                 gdev = grid.to(device, non_blocking=True)
             kw.update(grid=gdev, grid_stride=gmax, gl=devt[5], rep_c=devt[6], rep_t=devt[7])
         self._plans = plans
+        if any(p.flags & 2 for p in plans):
+            if x is None:
+                raise ValueError("a noise augmentation was drawn: plan() needs the device batch `x` to measure the channel power")
+            if static is not None:
+                # the Philox seed is a by-value kernel argument: a replayed CUDA graph would repeat one noise pattern for ever
+                raise NotImplementedError("gaussian-noise augmentation with graph-static plans (the seed is frozen by the capture); "
+                                          "plan without `static` and step with use_graph=False")
+            kw.update(self._noise_kwargs(x, kw["n"], plans, device, seed, src))
         return kw
+
+    def _noise_kwargs(self, x, n, plans, device, seed, src=None) -> dict:
+        from . import ops
+        B, C = len(plans), max(len(p.snr_db) for p in plans if p.snr_db is not None)
+        ms = torch.empty(B, C, dtype=torch.float32, device=device)
+        ops.channel_meansq(x, n, ms, **(src or {}))
+        snr = torch.zeros(B, C)
+        for b, p in enumerate(plans):
+            if p.snr_db is not None:
+                snr[b] = torch.from_numpy(p.snr_db).float()
+        return dict(sigma=torch.sqrt(ms / torch.pow(10.0, snr.to(device) / 10.0)), seed=seed)
 
     def static_buffers(self, B: int, n_channels: int, device) -> dict:
         """Persistent device tensors for `plan(..., static=...)`, sized for the finest mask grid the configuration can draw
@@ -157,13 +180,5 @@ class BatchAugmenter:
         for b, s in enumerate(samples):
             host[b, :, :s.shape[1]] = torch.from_numpy(np.ascontiguousarray(s, dtype=np.float32))
         x = host.to(dev, non_blocking=True)
-        kw = self.plan([s.shape for s in samples], dev)
-        if any(p.flags & 2 for p in self._plans):
-            ms = torch.empty(B, C, dtype=torch.float32, device=dev)
-            ops.channel_meansq(x, kw["n"], ms)
-            snr = torch.zeros(B, C)
-            for b, p in enumerate(self._plans):
-                if p.snr_db is not None:
-                    snr[b] = torch.from_numpy(p.snr_db).float()
-            kw.update(sigma=torch.sqrt(ms / torch.pow(10.0, snr.to(dev) / 10.0)), seed=seed)
+        kw = self.plan([s.shape for s in samples], dev, x=x, seed=seed)
         return ops.aug_pass(x, out, layout, **kw)

@@ -442,14 +442,34 @@ struct AugDev {
   const int* n; const int* shift; const int* e0; const int* e1; const int* flags;
   const unsigned char* grid; long long grid_stride; const int* gl; const int* rep_c; const int* rep_t;
   const float* sigma; unsigned long long seed;
+  const long long* src_off; const int* src_ld;     // ragged sample store: row c of sample b starts at x + src_off[b] + c * src_ld[b]
 };
+// source row of (sample b, channel c) and its readable length
+__device__ __forceinline__ long long aug_row(const AugDev& a, int b, int c, int& ld) {
+  if (a.src_off) { ld = a.src_ld[b]; return a.src_off[b] + static_cast<long long>(c) * ld; }
+  ld = a.Tin;
+  return (static_cast<long long>(b) * a.C + c) * a.Tin;
+}
+template <typename TI> __device__ __forceinline__ void load4(const TI* p, float (&v)[4]);
+template <> __device__ __forceinline__ void load4<float>(const float* p, float (&v)[4]) {
+  const float4 f = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+}
+template <> __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[4]) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
 
-__device__ __forceinline__ float aug_value(const AugDev& a, const float* __restrict__ x, int b, int c, int tau) {
+template <typename TI>
+__device__ __forceinline__ float aug_value(const AugDev& a, const TI* __restrict__ x, int b, int c, int tau) {
   const int sh = a.shift ? a.shift[b] : 0;
-  const int n = a.n ? min(a.n[b], a.Tin) : a.Tin;
+  int ld;
+  const long long row = aug_row(a, b, c, ld);
+  const int n = a.n ? min(a.n[b], ld) : ld;
   const int t = tau - sh;
   if (t < 0 || t >= n) return 0.f;
-  float v = __ldg(x + (static_cast<long long>(b) * a.C + c) * a.Tin + t);
+  float v = to_f<TI>(x[row + t]);
   const int fl = a.flags ? a.flags[b] : 0;
   if (fl & 2) {   // gaussian noise: reference returns signal + (signal + noise)
     const float sg = a.sigma[static_cast<long long>(b) * a.C + c];
@@ -465,8 +485,8 @@ __device__ __forceinline__ float aug_value(const AugDev& a, const float* __restr
 }
 
 // layout 0: (B,C,T) -> (B,C,T)
-template <typename TO>
-__global__ void aug_bct_kernel(const AugDev a, const float* __restrict__ x, TO* __restrict__ y) {
+template <typename TI, typename TO>
+__global__ void aug_bct_kernel(const AugDev a, const TI* __restrict__ x, TO* __restrict__ y) {
   const int b = blockIdx.z, c = blockIdx.y;
   const int tau = blockIdx.x * blockDim.x + threadIdx.x;
   if (tau >= a.T) return;
@@ -478,8 +498,8 @@ __global__ void aug_bct_kernel(const AugDev a, const float* __restrict__ x, TO* 
 // 512 contiguous bytes) and writes 16 bytes (eight channels of one sample).  The per-sample decisions (length, shift, edge
 // zeroing, mask grid geometry) are read once per block; the grid cell is looked up once per run of samples inside it.
 constexpr int kAugTT = 128, kAugTC = 64;
-template <typename TO>
-__global__ void __launch_bounds__(256) aug_btc_kernel(const AugDev a, const float* __restrict__ x, TO* __restrict__ y) {
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) aug_btc_kernel(const AugDev a, const TI* __restrict__ x, TO* __restrict__ y) {
   // tile[channel][sample], 16-byte groups of 4 samples XOR-swizzled with (channel / 8): the 16-byte stores of the read phase
   // and the scalar reads of the write phase (lanes = 4 samples x 8 channel groups) are both bank-conflict free
   __shared__ __align__(16) float tile[kAugTC][kAugTT];
@@ -488,29 +508,31 @@ __global__ void __launch_bounds__(256) aug_btc_kernel(const AugDev a, const floa
   const int c0 = blockIdx.y * kAugTC;
   const int t0 = blockIdx.x * kAugTT;
   const int sh = a.shift ? a.shift[b] : 0;
-  const int n = a.n ? min(a.n[b], a.Tin) : a.Tin;
+  int sld;
+  const long long row0 = aug_row(a, b, 0, sld);
+  const int n = a.n ? min(a.n[b], sld) : sld;
   const int fl = a.flags ? a.flags[b] : 0;
   const int e0 = a.e0 ? a.e0[b] : 0, e1 = a.e1 ? a.e1[b] : 0;
   const int lo = max(e0, 0), hi = min(n, n - e1);            // samples outside [lo, hi) of the source are zero
   const bool masked = (fl & 1) && a.grid && n > 0;
   const int rep_c = masked ? a.rep_c[b] : 1, rep_t = masked ? a.rep_t[b] : 1, gl = masked ? a.gl[b] : 1;
   const unsigned char* grid = masked ? a.grid + b * a.grid_stride : nullptr;
-  // 16-byte loads need the SOURCE index t = tau - shift of a lane's first sample to be a multiple of 4 (rows are Tin floats)
-  const bool vec = ((sh & 3) == 0) && ((a.Tin & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  // vector loads (4 samples) need the SOURCE index t = tau - shift of a lane's first sample to be a multiple of 4 and rows that
+  // start on a multiple of 4 elements
+  const bool vec = ((sh & 3) == 0) && ((sld & 3) == 0) && ((row0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   for (int e = threadIdx.x; e < kAugTC * (kAugTT / 4); e += 256) {
     const int cc = e / (kAugTT / 4), t4 = (e % (kAugTT / 4)) * 4;
     const int c = c0 + cc, tau = t0 + t4;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     const int t = tau - sh;
     if (c < a.C && t + 3 >= lo && t < hi) {
-      const float* xr = x + (static_cast<long long>(b) * a.C + c) * a.Tin;
-      if (vec && t >= 0 && t + 3 < a.Tin) {
-        const float4 f = __ldg(reinterpret_cast<const float4*>(xr + t));
-        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+      const TI* xr = x + row0 + static_cast<long long>(c) * sld;
+      if (vec && t >= 0 && t + 3 < sld) {
+        load4<TI>(xr + t, v);
       } else {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          if (t + k >= 0 && t + k < n) v[k] = __ldg(xr + t + k);
+          if (t + k >= 0 && t + k < n) v[k] = to_f<TI>(xr[t + k]);
       }
       if (fl & 2) {   // gaussian noise: the reference returns signal + (signal + noise)
         const float sg = a.sigma[static_cast<long long>(b) * a.C + c];
@@ -553,13 +575,16 @@ __global__ void __launch_bounds__(256) aug_btc_kernel(const AugDev a, const floa
   }
 }
 
-__global__ void channel_meansq_kernel(int C, int Tin, const int* __restrict__ n, const float* __restrict__ x, float* __restrict__ ms) {
+template <typename TI>
+__global__ void channel_meansq_kernel(int C, int Tin, const int* __restrict__ n, const TI* __restrict__ x, float* __restrict__ ms,
+                                      const long long* __restrict__ src_off, const int* __restrict__ src_ld) {
   __shared__ float sh[8];
   const int b = blockIdx.y, c = blockIdx.x;
-  const int len = n ? min(n[b], Tin) : Tin;
-  const float* xr = x + (static_cast<long long>(b) * C + c) * Tin;
+  const int ld = src_off ? src_ld[b] : Tin;
+  const int len = n ? min(n[b], ld) : ld;
+  const TI* xr = x + (src_off ? src_off[b] + static_cast<long long>(c) * ld : (static_cast<long long>(b) * C + c) * Tin);
   float s = 0.f;
-  for (int t = threadIdx.x; t < len; t += blockDim.x) { const float v = xr[t]; s = fmaf(v, v, s); }
+  for (int t = threadIdx.x; t < len; t += blockDim.x) { const float v = to_f<TI>(xr[t]); s = fmaf(v, v, s); }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
   __syncthreads();
@@ -806,31 +831,43 @@ int ns_greedy_pick(int dtype, int B, int V, long long ld, const void* logits, co
   return NS_OK;
 }
 
-int ns_aug_pass(const ns_aug_args* a, const float* x, void* y, void* stream) {
+int ns_aug_pass(const ns_aug_args* a, const void* x, void* y, void* stream) {
   NS_CHECK_ARG(a && x && y, "ns_aug_pass: null argument");
-  NS_CHECK_ARG(a->B > 0 && a->C > 0 && a->Tin > 0 && a->T > 0 && valid_dtype(a->out_dtype), "ns_aug_pass: bad shape");
+  NS_CHECK_ARG(a->B > 0 && a->C > 0 && a->Tin > 0 && a->T > 0 && valid_dtype(a->out_dtype) && valid_dtype(a->in_dtype), "ns_aug_pass: bad shape");
   NS_CHECK_ARG(a->layout == 0 || (a->layout == 1 && a->Cp >= a->C), "ns_aug_pass: bad layout / Cp");
   NS_CHECK_ARG(!a->grid || (a->gl && a->rep_c && a->rep_t && a->flags), "ns_aug_pass: grid needs gl/rep_c/rep_t/flags");
+  NS_CHECK_ARG((a->src_off == nullptr) == (a->src_ld == nullptr) && (!a->src_off || a->n), "ns_aug_pass: src_off, src_ld and n go together");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   AugDev d{a->B, a->C, a->Tin, a->T, a->Cp, a->n, a->shift, a->e0, a->e1, a->flags, a->grid, a->grid_stride, a->gl,
-           a->rep_c, a->rep_t, a->sigma, a->seed};
+           a->rep_c, a->rep_t, a->sigma, a->seed, a->src_off, a->src_ld};
+  const bool ibf = a->in_dtype == NS_BF16, obf = a->out_dtype == NS_BF16;
+  const float* xf = static_cast<const float*>(x);
+  const bf16* xb = static_cast<const bf16*>(x);
   if (a->layout == 0) {
     dim3 grid((a->T + 255) / 256, a->C, a->B);
-    if (a->out_dtype == NS_BF16) aug_bct_kernel<bf16><<<grid, 256, 0, st>>>(d, x, reinterpret_cast<bf16*>(y));
-    else aug_bct_kernel<float><<<grid, 256, 0, st>>>(d, x, reinterpret_cast<float*>(y));
+    if (ibf && obf) aug_bct_kernel<bf16, bf16><<<grid, 256, 0, st>>>(d, xb, reinterpret_cast<bf16*>(y));
+    else if (ibf) aug_bct_kernel<bf16, float><<<grid, 256, 0, st>>>(d, xb, reinterpret_cast<float*>(y));
+    else if (obf) aug_bct_kernel<float, bf16><<<grid, 256, 0, st>>>(d, xf, reinterpret_cast<bf16*>(y));
+    else aug_bct_kernel<float, float><<<grid, 256, 0, st>>>(d, xf, reinterpret_cast<float*>(y));
   } else {
     dim3 grid((a->T + kAugTT - 1) / kAugTT, (a->Cp + kAugTC - 1) / kAugTC, a->B);
-    if (a->out_dtype == NS_BF16) aug_btc_kernel<bf16><<<grid, 256, 0, st>>>(d, x, reinterpret_cast<bf16*>(y));
-    else aug_btc_kernel<float><<<grid, 256, 0, st>>>(d, x, reinterpret_cast<float*>(y));
+    if (ibf && obf) aug_btc_kernel<bf16, bf16><<<grid, 256, 0, st>>>(d, xb, reinterpret_cast<bf16*>(y));
+    else if (ibf) aug_btc_kernel<bf16, float><<<grid, 256, 0, st>>>(d, xb, reinterpret_cast<float*>(y));
+    else if (obf) aug_btc_kernel<float, bf16><<<grid, 256, 0, st>>>(d, xf, reinterpret_cast<bf16*>(y));
+    else aug_btc_kernel<float, float><<<grid, 256, 0, st>>>(d, xf, reinterpret_cast<float*>(y));
   }
   NS_LAUNCH_CHECK();
   count(C_OTHER);
   return NS_OK;
 }
 
-int ns_channel_meansq(int B, int C, int Tin, const int* n, const float* x, float* ms, void* stream) {
-  NS_CHECK_ARG(B > 0 && C > 0 && Tin > 0 && x && ms, "ns_channel_meansq: bad arguments");
-  channel_meansq_kernel<<<dim3(C, B), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(C, Tin, n, x, ms);
+int ns_channel_meansq(int dtype, int B, int C, int Tin, const int* n, const void* x, float* ms, const long long* src_off, const int* src_ld,
+                      void* stream) {
+  NS_CHECK_ARG(valid_dtype(dtype) && B > 0 && C > 0 && Tin > 0 && x && ms, "ns_channel_meansq: bad arguments");
+  NS_CHECK_ARG((src_off == nullptr) == (src_ld == nullptr) && (!src_off || n), "ns_channel_meansq: src_off, src_ld and n go together");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == NS_BF16) channel_meansq_kernel<bf16><<<dim3(C, B), 256, 0, st>>>(C, Tin, n, static_cast<const bf16*>(x), ms, src_off, src_ld);
+  else channel_meansq_kernel<float><<<dim3(C, B), 256, 0, st>>>(C, Tin, n, static_cast<const float*>(x), ms, src_off, src_ld);
   NS_LAUNCH_CHECK();
   count(C_OTHER);
   return NS_OK;

@@ -402,8 +402,15 @@ class WhisperEEGEngine:
         return ops.epilogue(**kw)
 
     def input_to_channels_last(self, x: torch.Tensor, aug: Optional[dict] = None) -> torch.Tensor:
-        """(B,C,T) fp32 -> (B,T,Cp) compute dtype through the augmentation/pad/cast pass (identity when aug is None)."""
+        """(B,C,T) fp32 -> (B,T,Cp) compute dtype through the augmentation/pad/cast pass (identity when aug is None).
+        With aug["src_off"] / aug["src_ld"], x is the flat ragged sample store (reader.SampleStore.flat, fp32 or bf16) and the
+        batch is gathered from it by the same pass."""
         dm = self.dims
+        if aug is not None and "src_off" in aug:
+            B = aug["src_off"].shape[0]
+            y = self.ws.get("x_cl", (B, dm.T, dm.Cp), self.dtype)
+            ops.aug_pass(x, y, layout=1, C_in=dm.eeg_ch, Tin=dm.T, **aug)
+            return y
         B = x.shape[0]
         if x.shape[1] != dm.eeg_ch:
             raise ValueError(f"expected {dm.eeg_ch} EEG channels, got {x.shape[1]}")
@@ -420,7 +427,7 @@ class WhisperEEGEngine:
             raise ValueError(f"Whisper expects the input features to be of length {dm.T}, but found {x.shape[-1]}")  # HF:613
         if not self._packed:
             self.pack_trainable()
-        B = x.shape[0]
+        B = aug["src_off"].shape[0] if (aug is not None and "src_off" in aug) else x.shape[0]
         d, S, T, F, r, H = dm.d_model, dm.max_source_positions, dm.T, dm.enc_ffn, dm.lora_r, dm.enc_heads
         M = B * S
         self._drop_p = self.lora_dropout if (save and self.training and self.has_lora) else 0.0
@@ -548,7 +555,7 @@ class WhisperEEGEngine:
         if decoder_input_ids is not None and labels is not None:
             pass  # HF allows both; labels only drive the loss then
         enc = self.encode(x, aug=aug, save=save)
-        B = x.shape[0]
+        B = enc.shape[0]
         if decoder_input_ids is None:
             if labels is None:
                 raise ValueError("You have to specify either decoder_input_ids or labels")

@@ -318,19 +318,31 @@ def adamw_clip(p, g, m, v, sumsq_t, gscale, max_norm, lr, beta1, beta2, eps, wd,
 
 
 def aug_pass(x, y, layout: int, n=None, shift=None, e0=None, e1=None, flags=None, grid=None, grid_stride=0, gl=None,
-             rep_c=None, rep_t=None, sigma=None, seed: int = 0):
-    B, Cc, Tin = x.shape
+             rep_c=None, rep_t=None, sigma=None, seed: int = 0, src_off=None, src_ld=None, C_in: Optional[int] = None,
+             Tin: Optional[int] = None):
+    """x: the dense (B, C, Tin) batch, or (src_off given) the flat ragged sample store with row c of slot b at
+    x[src_off[b] + c * src_ld[b] :][: n[b]]; fp32 or bf16."""
     if layout == 0:
-        T, Cp = y.shape[2], Cc
+        T, Cp = y.shape[2], y.shape[1]
     else:
         T, Cp = y.shape[1], y.shape[2]
+    if src_off is None:
+        B, Cc, Tin = x.shape
+    else:
+        B, Cc, Tin = y.shape[0], int(C_in), int(Tin or T)
+    if layout == 0:
+        Cp = Cc
     a = AugArgs(B, Cc, Tin, T, Cp, layout, ns_dtype(y), _p(n), _p(shift), _p(e0), _p(e1), _p(flags), _p(grid), grid_stride,
-                _p(gl), _p(rep_c), _p(rep_t), _p(sigma), seed)
-    _call("ns_aug_pass", (0, x.numel() * 4.0 + y.numel() * y.element_size()), C.byref(a), _p(x), _p(y), _stream())
+                _p(gl), _p(rep_c), _p(rep_t), _p(sigma), seed, ns_dtype(x), _p(src_off), _p(src_ld))
+    _call("ns_aug_pass", (0, x.numel() * float(x.element_size()) + y.numel() * y.element_size()), C.byref(a), _p(x), _p(y), _stream())
     return y
 
 
-def channel_meansq(x, n, ms):
-    B, Cc, Tin = x.shape
-    _call("ns_channel_meansq", (0, 0), B, Cc, Tin, _p(n), _p(x), _p(ms), _stream())
+def channel_meansq(x, n, ms, src_off=None, src_ld=None):
+    if src_off is None:
+        B, Cc, Tin = x.shape
+    else:
+        B, Cc = ms.shape
+        Tin = 1
+    _call("ns_channel_meansq", (0, 0), ns_dtype(x), B, Cc, Tin, _p(n), _p(x), _p(ms), _p(src_off), _p(src_ld), _stream())
     return ms

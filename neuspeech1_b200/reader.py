@@ -151,15 +151,123 @@ class DeviceBatchLoader:
                     self.stream.wait_event(self.free[slot])
                     xd[:nb].copy_(self.x_host[slot][:nb], non_blocking=True)      # whole rows: one contiguous pinned -> device copy
                     yd[:nb].copy_(lab, non_blocking=True)
-                    plan = self.aug.plan(shapes, self.device, static=self.aug_static[slot])
+                    plan = self.aug.plan(shapes, self.device, static=self.aug_static[slot], x=xd[:nb])
                     self.h2d_done[slot].record(self.stream)
                 torch.cuda.current_stream(self.device).wait_stream(self.stream)
             else:
                 xd[:nb].copy_(self.x_host[slot][:nb])
                 yd[:nb].copy_(lab)
-                plan = self.aug.plan(shapes, self.device, static=self.aug_static[slot])
+                plan = self.aug.plan(shapes, self.device, static=self.aug_static[slot], x=xd[:nb])
             self.host_free[slot].release()              # copy enqueued, h2d_done recorded: the worker may wait on it and refill
             # fixed-shape views of the persistent buffers: the label width is the widest batch the loader may ever yield
             prev_slot = slot
             yield xd[:nb], yd[:nb], plan, slot
         th.join()
+
+
+class SampleStore:
+    """The training set's recordings, UNPADDED, resident in HBM.
+
+    The reference re-reads every `.npy` each epoch, pads it to 30 s in fp32 and ships 5 MB per sample over PCIe
+    (`utils/reader.py:253-303,496-516`).  Here every recording is read ONCE, cut to its channel window and to 30 s, rounded to the
+    compute dtype the stem consumes anyway, and packed back to back into one flat device tensor: channel row c of item i starts at
+    element `off[i] + c * ld[i]` and holds `n[i]` samples (`ld` = n rounded up to 8 so that rows start on 16-byte boundaries).
+    A batch is then three small integer vectors (`src_off`, `src_ld`, `n`): `ns_aug_pass` gathers, augments, pads, and lays the
+    batch out channels-last straight from the store.  Gwilliams at C = 208 (mean length ~2700 samples): ~1.1 MB per recording in
+    bf16, i.e. 100 k recordings fit in 112 GB of the 180 GB.
+    """
+
+    def __init__(self, items: Sequence[Dict], modal_ch: int, device, dtype: torch.dtype = torch.bfloat16,
+                 max_duration: float = 30.0, sample_rate: int = 200, chunk_bytes: int = 256 << 20):
+        self.C, self.T = modal_ch, int(max_duration * sample_rate)
+        self.device, self.dtype = torch.device(device), dtype
+        cuda = self.device.type == "cuda"
+        arrays, off, total = [], [], 0
+        self.n = np.zeros(len(items), dtype=np.int32)
+        self.ld = np.zeros(len(items), dtype=np.int32)
+        for i, it in enumerate(items):
+            s = it["array"] if "array" in it else np.load(it["path"])
+            s = select_channels(np.asarray(s), it.get("path", ""), modal_ch)[:, :self.T]
+            n = s.shape[1]
+            ld = (n + 7) // 8 * 8
+            self.n[i], self.ld[i] = n, ld
+            off.append(total)
+            total += modal_ch * ld
+            arrays.append(s)
+        self.off = np.asarray(off, dtype=np.int64)
+        self.flat = torch.zeros(max(total, 8), dtype=dtype, device=self.device)
+        # upload in pinned chunks of whole recordings (conversion to `dtype` on the host: half the PCIe bytes for bf16)
+        esz = self.flat.element_size()
+        cap = max(chunk_bytes // esz, int((self.ld.astype(np.int64) * modal_ch).max()) if len(items) else 8)
+        stage = torch.zeros(cap, dtype=dtype, pin_memory=cuda)
+        start, fill = 0, 0
+        for i, s in enumerate(arrays):
+            sz = modal_ch * int(self.ld[i])
+            if fill + sz > cap:
+                self.flat[start:start + fill].copy_(stage[:fill], non_blocking=False)
+                start, fill = start + fill, 0
+            v = stage[fill:fill + sz].view(modal_ch, int(self.ld[i]))
+            v[:, :s.shape[1]] = torch.from_numpy(np.ascontiguousarray(s, dtype=np.float32)).to(dtype)
+            v[:, s.shape[1]:] = 0
+            fill += sz
+        if fill:
+            self.flat[start:start + fill].copy_(stage[:fill], non_blocking=False)
+        self.bytes = total * esz
+
+    def __len__(self) -> int:
+        return len(self.n)
+
+    def batch_tables(self, idxs: Sequence[int]) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        idxs = np.asarray(idxs, dtype=np.int64)
+        return self.off[idxs], self.ld[idxs], self.n[idxs]
+
+
+class ResidentBatchLoader:
+    """Batches over a `SampleStore`: yields `(store.flat, labels, aug, slot)` where `aug` carries the gather tables
+    (`src_off`, `src_ld`, `n`) and the augmentation decisions, all in two sets of persistent device tensors (so
+    `engine.train_step(use_graph=True)` replays one CUDA graph per slot).  Per batch the host moves 3 small integer vectors and
+    the labels; the samples never leave HBM."""
+
+    def __init__(self, store: SampleStore, labels: Sequence[Sequence[int]], batch_size: int, augment_configs: Optional[Dict] = None,
+                 max_label_len: int = 64, bos_token_id: Optional[int] = None, order: Optional[Iterable[int]] = None,
+                 drop_last: bool = True, train: bool = True, sample_rate: int = 200):
+        if len(labels) != len(store):
+            raise ValueError("one label row per stored recording")
+        self.store, self.labels, self.B = store, labels, batch_size
+        self.device, self.cuda = store.device, store.device.type == "cuda"
+        self.Lmax, self.bos = max_label_len, bos_token_id
+        self.order = list(order) if order is not None else list(range(len(store)))
+        self.drop_last = drop_last
+        self.aug = BatchAugmenter(augment_configs or {}, max_duration=store.T / sample_rate, sample_rate=sample_rate, train=train)
+        dev = self.device
+        self.y_dev = [torch.full((batch_size, max_label_len), -100, dtype=torch.long, device=dev) for _ in range(2)]
+        self.off_dev = [torch.zeros(batch_size, dtype=torch.long, device=dev) for _ in range(2)]
+        self.ld_dev = [torch.zeros(batch_size, dtype=torch.int32, device=dev) for _ in range(2)]
+        self.aug_static = [self.aug.static_buffers(batch_size, store.C, dev) for _ in range(2)]
+
+    def __len__(self) -> int:
+        n = len(self.order)
+        return n // self.B if self.drop_last else (n + self.B - 1) // self.B
+
+    def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor, dict, int]]:
+        batches = [self.order[k:k + self.B] for k in range(0, len(self.order), self.B)]
+        if self.drop_last:
+            batches = [b for b in batches if len(b) == self.B]
+        for k, idxs in enumerate(batches):
+            slot, nb = k & 1, len(idxs)
+            off, ld, n = self.store.batch_tables(idxs)
+            lab = torch.full((nb, self.Lmax), -100, dtype=torch.long, pin_memory=self.cuda)
+            rows = collate_labels([list(self.labels[i])[:self.Lmax] for i in idxs], self.bos)
+            lab[:, :rows.shape[1]] = rows
+            offh = torch.from_numpy(off.copy())
+            ldh = torch.from_numpy(ld.copy())
+            if self.cuda:
+                offh, ldh = offh.pin_memory(), ldh.pin_memory()
+            # stream order protects the per-slot tables: these copies queue behind the step that last read the slot
+            self.off_dev[slot][:nb].copy_(offh, non_blocking=True)
+            self.ld_dev[slot][:nb].copy_(ldh, non_blocking=True)
+            self.y_dev[slot][:nb].copy_(lab, non_blocking=True)
+            src = dict(src_off=self.off_dev[slot][:nb], src_ld=self.ld_dev[slot][:nb])
+            plan = self.aug.plan([(self.store.C, int(v)) for v in n], self.device, static=self.aug_static[slot], x=self.store.flat, src=src)
+            plan.update(src)
+            yield self.store.flat, self.y_dev[slot][:nb], plan, slot

@@ -475,6 +475,48 @@ def test_aug_pass_matches_oracle():
     assert bool((ya[0] != ya[1]).any())
 
 
+def test_aug_pass_reads_a_ragged_store():
+    """ns_aug_pass / ns_channel_meansq with src_off / src_ld (utils/reader.py:253-303 keeps recordings unpadded): the batch
+    gathered from a flat fp32 or bf16 store equals the pass over the collator's dense batch, bit for bit (mask + edge zeroing +
+    shift + pad; the bf16 store only rounds the samples the stem rounds anyway)."""
+    B, C, T, Cp = 5, 21, 600, 32
+    rng = np.random.RandomState(5)
+    ns = [int(v) for v in rng.randint(100, 400, size=B)]
+    ns[1] = 0 + 397                                              # an odd length next to vector-aligned ones
+    xs = [rng.randn(C, n).astype(np.float32) for n in ns]
+    Tin = max(ns)
+    for dt in (torch.float32, torch.bfloat16):
+        dense = torch.zeros(B, C, Tin)
+        flat, off, ld = [], [], []
+        tot = 0
+        for b, x in enumerate(xs):
+            xr = torch.from_numpy(x).to(dt)
+            dense[b, :, :ns[b]] = xr.float()
+            l = (ns[b] + 7) // 8 * 8
+            row = torch.zeros(C, l, dtype=dt); row[:, :ns[b]] = xr
+            flat.append(row.reshape(-1)); off.append(tot); ld.append(l); tot += C * l
+        order = [3, 0, 4, 1, 2]                                  # batch slots need not follow the store order
+        store = torch.cat(flat).to(DEV)
+        i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=DEV)
+        gl = [(ns[i] + 39) // 40 for i in order]
+        gmax = max(gl) * 11
+        grid = (torch.rand(B, gmax, generator=torch.Generator().manual_seed(1)) >= 0.25).to(torch.uint8).to(DEV)
+        kw = dict(n=i32([ns[i] for i in order]), shift=i32([8, 0, 13, 4, 0]), e0=i32([3, 0, 2, 1, 0]), e1=i32([1, 0, 5, 2, 9]),
+                  flags=i32([1, 0, 1, 1, 1]), grid=grid, grid_stride=gmax, gl=i32(gl), rep_c=i32([2] * B), rep_t=i32([40] * B))
+        src = dict(src_off=torch.tensor([off[i] for i in order], dtype=torch.long, device=DEV), src_ld=i32([ld[i] for i in order]))
+        xd = dense[order].to(DEV)
+        for layout, shape in ((1, (B, T, Cp)), (0, (B, C, T))):
+            for odt in (torch.bfloat16, torch.float32):
+                y_ref = torch.full(shape, 3.0, dtype=odt, device=DEV)
+                ops.aug_pass(xd, y_ref, layout, **kw)
+                y = torch.full(shape, 4.0, dtype=odt, device=DEV)
+                ops.aug_pass(store, y, layout, C_in=C, Tin=T, **kw, **src)
+                assert torch.equal(y, y_ref), (dt, layout, odt)
+        ms_ref = torch.empty(B, C, device=DEV); ops.channel_meansq(xd, kw["n"], ms_ref)
+        ms = torch.empty(B, C, device=DEV); ops.channel_meansq(store, kw["n"], ms, **src)
+        assert torch.equal(ms, ms_ref)
+
+
 def test_aug_noise_statistics():
     B, C, T = 2, 8, 4000
     x = (0.3 * torch.randn(B, C, T)).clamp(-1, 1).to(DEV)

@@ -298,6 +298,38 @@ def test_device_loader_feeds_graph_replayed_steps():
     assert e1.graph_launches > 0 and rel(e1.flat, e2.flat) < 1e-5
 
 
+def test_resident_store_feeds_graph_replayed_steps():
+    """reader.SampleStore + ResidentBatchLoader: recordings unpadded in HBM, a batch = three integer vectors; ns_aug_pass gathers
+    them.  fp32 store: same losses / weights as host-padded eager stepping; from the second epoch on the steps are graph replays."""
+    from neuspeech1_b200.reader import ResidentBatchLoader, SampleStore
+    dims = O.Dims(d_model=256, enc_layers=2, dec_layers=2, enc_heads=4, dec_heads=4, enc_ffn=512, dec_ffn=512, vocab=2000,
+                  max_source_positions=160, max_target_positions=32, eeg_ch=24, pad_token_id=1997, eos_token_id=1997,
+                  decoder_start_token_id=1998, begin_suppress_tokens=(220, 1996), lora_r=32, lora_alpha=64)
+    P = O.init_params(dims, seed=0)
+    lora = O.init_lora(dims, seed=1, b_std=0.05)
+    rng = np.random.RandomState(0)
+    items = []
+    for i in range(4):
+        n = int(rng.randint(100, 600))
+        items.append({"array": (0.3 * rng.randn(24, n)).clip(-1, 1).astype(np.float32), "path": f"/x/other/{i}.npy",
+                      "labels": rng.randint(0, 1990, size=5 + i).tolist()})
+    store = SampleStore(items, modal_ch=24, device=DEV, dtype=torch.float32, max_duration=dims.T / 200.0, sample_rate=200)
+    ld = ResidentBatchLoader(store, [it["labels"] for it in items], batch_size=2, max_label_len=8)
+    e1 = WhisperEEGEngine(ModelDims.from_any(dims), P, lora, dtype=torch.float32, device=DEV)
+    e2 = WhisperEEGEngine(ModelDims.from_any(dims), P, lora, dtype=torch.float32, device=DEV)
+    for epoch in range(3):
+        for k, (x, y, aug, slot) in enumerate(ld):
+            xp = torch.zeros(2, 24, dims.T); yp = torch.full((2, 8), -100, dtype=torch.long)
+            for b in range(2):
+                it = items[2 * k + b]
+                xp[b, :, :it["array"].shape[1]] = torch.from_numpy(it["array"])
+                yp[b, :len(it["labels"])] = torch.tensor(it["labels"])
+            l1 = float(e1.train_step(x, y, lr=2e-4, aug=aug))
+            l2 = float(e2.train_step(xp.to(DEV), yp.to(DEV), lr=2e-4, use_graph=False))
+            assert abs(l1 - l2) <= 1e-4 * abs(l2), (epoch, k, l1, l2)
+    assert e1.graph_launches > 0 and rel(e1.flat, e2.flat) < 1e-5
+
+
 def test_beam_search_matches_oracle_loop_fp32():
     """evaluation.py:370-385 (num_beams=5, repetition_penalty=5.0, no_repeat_ngram_size=2) on the B200 decoder step, fp32: the
     same token ids as the same scoring loop over the oracle's decoder (that loop is pinned to stock transformers generate in

@@ -66,3 +66,34 @@ def test_loader_slow_consumer_never_sees_a_later_batch():
             for b in range(2):
                 i = 2 * k + b
                 assert float(x[b, 0, 0]) == float(i + 1) and int(y[b, 0]) == i and int(aug["n"][b]) == 20 + i, (epoch, k, b)
+
+
+def test_sample_store_packs_unpadded_rows_and_loader_hands_out_tables():
+    """reader.SampleStore / ResidentBatchLoader on the CPU device: every recording sits unpadded in one flat tensor (rows start on
+    multiples of 8 elements), a batch is (src_off, src_ld, n) + labels in per-slot persistent tensors."""
+    from neuspeech1_b200.reader import ResidentBatchLoader, SampleStore
+    rng = np.random.RandomState(0)
+    items = []
+    for i in range(6):
+        n = int(rng.randint(30, 90))
+        items.append({"array": rng.randn(12, n).astype(np.float32), "path": f"/x/other/{i}.npy", "labels": list(range(2 + i))})
+    st = SampleStore(items, modal_ch=16, device="cpu", dtype=torch.float32, max_duration=0.4, sample_rate=200, chunk_bytes=16 * 88 * 4 * 2)
+    assert len(st) == 6 and st.flat.numel() == int((st.ld.astype(np.int64) * 16).sum())
+    for i, it in enumerate(items):
+        n = min(it["array"].shape[1], 80)                                   # cut to max_duration * sample_rate
+        assert st.n[i] == n and st.ld[i] % 8 == 0 and st.off[i] % 8 == 0
+        rows = st.flat[st.off[i]: st.off[i] + 16 * st.ld[i]].view(16, st.ld[i])
+        assert torch.equal(rows[:12, :n], torch.from_numpy(it["array"][:, :n])) and not rows[12:].any() and not rows[:, n:].any()
+    ld = ResidentBatchLoader(st, [it["labels"] for it in items], batch_size=2, max_label_len=8)
+    assert len(ld) == 3
+    ptrs = []
+    for k, (x, y, aug, slot) in enumerate(ld):
+        assert x.data_ptr() == st.flat.data_ptr() and slot == k % 2
+        for b in range(2):
+            i = 2 * k + b
+            assert int(aug["src_off"][b]) == st.off[i] and int(aug["src_ld"][b]) == st.ld[i] and int(aug["n"][b]) == st.n[i]
+            assert y[b, :len(items[i]["labels"])].tolist() == items[i]["labels"]
+        ptrs.append((y.data_ptr(), aug["src_off"].data_ptr(), aug["n"].data_ptr()))
+    assert ptrs[0] == ptrs[2] and ptrs[0] != ptrs[1]
+    st16 = SampleStore(items, modal_ch=16, device="cpu", dtype=torch.bfloat16, max_duration=0.4, sample_rate=200)
+    assert st16.bytes * 2 == st.bytes and torch.equal(st16.flat.float(), st.flat.to(torch.bfloat16).float())
