@@ -477,7 +477,7 @@ def run_pipeline(args):
     items, labels = [], []
     for i in range(n_items):                                                   # Gwilliams-like lengths: 2 s .. 25 s at 200 Hz
         n = int(rng.randint(400, 5000))
-        items.append({"array": (0.3 * rng.standard_normal((dims.eeg_ch, n), dtype=np.float32)).clip(-1, 1), "path": f"/synthetic/gwilliams/{i}.npy"})
+        items.append({"array": (0.3 * rng.standard_normal((dims.eeg_ch, n))).clip(-1, 1).astype(np.float32), "path": f"/synthetic/gwilliams/{i}.npy"})
         labels.append(rng.randint(0, 50257, size=L - 4).tolist())
     t0 = time.perf_counter()
     store = SampleStore(items, modal_ch=dims.eeg_ch, device=dev, dtype=torch.bfloat16)
