@@ -62,6 +62,12 @@ typedef struct {
   int          out_dtype;     /* ns_dtype of D (NS_F32 allowed with NS_BF16 inputs) */
   int          a2_group_cols; /* > 0: stacked adapters -- output columns [g*a2_group_cols, (g+1)*a2_group_cols) use
                                  A2[:, g*K2 : (g+1)*K2] (q/k/v share one t = x*[Aq;Ak;Av]^T buffer, lda2 >= G*K2) */
+  const unsigned int* drop_bits; /* != NULL: LoRA-branch dropout in the INPUT-gradient product (PEFT: the branch input is
+                                 dropout(x), so d/dx of the branch is keep . (dt A)):  D = epilogue-activation( A*W^T +
+                                 keep . (A2*W2^T) ), keep(m, n) = !bit (n % 32) of drop_bits[m * drop_ld + n / 32] (one adapter's
+                                 plane of ns_dropout_bits).  The second product gets its own TMEM accumulator and is masked in
+                                 the epilogue before the sum.  bf16 tcgen05 path only (N % 64 == 0); else NS_ERR_UNSUPPORTED. */
+  long long    drop_ld;       /* words per row of drop_bits */
 } ns_epilogue;
 
 int ns_gemm_nt(int dtype, long long M, int N, int K, const void* A, long long lda, const void* W, long long ldw,
@@ -199,9 +205,9 @@ int ns_attention_decode_rows(int dtype, const ns_attn_shape* s, const void* q, c
 /* ---- LoRA branch: dropout and the rank-r products around it.
  * Replaces PEFT lora.Linear's  result += lora_B(lora_A(lora_dropout(x))) * scaling  (finetune.py:206-212: lora_dropout 0.05,
  * 0.1 for AdaLoRA) and its autograd backward.  The keep mask of a module is a counter-based bit plane, drawn once per step:
- *   bits[g][(rows+1)/2][(cols+15)/16] (32-bit words); bit 2*(col % 16) + (row & 1) of word (g, rp = row >> 1, w = col / 16) set
+ *   bits[g][rows][(cols+31)/32] (32-bit words, row-major like the activation); bit (col % 32) of word (g, row, w = col / 32) set
  *   <=> element (row, col) of adapter g is dropped.  The 32 flags of a word are drawn together from 16 hashed words
- *   R_i = mix1(km + (i + 1) * 0xC2B2AE35), km = lowbias32((rp * 0x9E3779B1) ^ (w * 0x85EBCA77) ^ *seed ^ salts[g]), mix1 = the
+ *   R_i = mix1(km + (i + 1) * 0xC2B2AE35), km = lowbias32((row * 0x9E3779B1) ^ (w * 0x85EBCA77) ^ *seed ^ salts[g]), mix1 = the
  *   first multiply-xorshift round of lowbias32, combined along the binary expansion of thr = round(p * 65536), least
  *   significant bit first: D = bit_i(thr) ? (D | R_i) : (D & R_i)  (P(flag) = thr / 65536).
  * `seed` is a DEVICE word (one per training step, advanced on the device so a replayed CUDA graph draws a new mask); `salts[g]`

@@ -24,7 +24,7 @@ c_f = C.c_float
 class Epilogue(C.Structure):
     _fields_ = [("bias", c_vp), ("alpha", c_f), ("alpha_cols", c_i), ("act", c_i), ("aux_in", c_vp), ("aux_out", c_vp),
                 ("ldaux", c_ll), ("residual", c_vp), ("ldr", c_ll), ("res_mod", c_i), ("out_dtype", c_i),
-                ("a2_group_cols", c_i)]
+                ("a2_group_cols", c_i), ("drop_bits", c_vp), ("drop_ld", c_ll)]
 
 
 class AttnShape(C.Structure):

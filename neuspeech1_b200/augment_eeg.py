@@ -137,7 +137,7 @@ class BatchAugmenter:
                 gdev = grid.to(device, non_blocking=True)
             kw.update(grid=gdev, grid_stride=gmax, gl=devt[5], rep_c=devt[6], rep_t=devt[7])
         self._plans = plans
-        if any(p.flags & 2 for p in plans):
+        if any(p.flags & 2 for p in plans) and torch.device(device).type == "cuda":   # (host-only planning, as in the CPU tests, stops at the decisions)
             if x is None:
                 raise ValueError("a noise augmentation was drawn: plan() needs the device batch `x` to measure the channel power")
             if static is not None:

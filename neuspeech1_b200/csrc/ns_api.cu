@@ -96,6 +96,14 @@ int ns_gemm_nt(int dtype, long long M, int N, int K, const void* A, long long ld
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const EpiDev e = make_epi(ep, dtype);
   const int ngrp = (ep && A2) ? ep->a2_group_cols : 0;
+  if (e.drop_bits) {
+    // the masked second product exists on the tcgen05 path only: never fall through to a kernel that would ignore the mask
+    if (!want_fast(dtype)) {
+      set_error("ns_gemm_nt: drop_bits needs bf16 storage and the tcgen05 path");
+      return NS_ERR_UNSUPPORTED;
+    }
+    return gemm_nt_fast(M, N, K, A, lda, W, ldw, D, ldd, e, A2, lda2, W2, ldw2, K2, ngrp, st);
+  }
   if (want_fast(dtype)) {
     const int r = gemm_nt_fast(M, N, K, A, lda, W, ldw, D, ldd, e, A2, lda2, W2, ldw2, K2, ngrp, st);
     if (r != NS_ERR_UNSUPPORTED) return r;

@@ -147,6 +147,8 @@ struct EpiDev {
   long long ldr;
   int res_mod;
   int out_f32;   // 1: D is fp32
+  const uint32_t* drop_bits;   // masked second product (see ns_epilogue::drop_bits)
+  long long drop_ld;
 };
 
 inline EpiDev make_epi(const ns_epilogue* ep, int dtype) {
@@ -159,6 +161,7 @@ inline EpiDev make_epi(const ns_epilogue* ep, int dtype) {
     e.aux_in = ep->aux_in; e.aux_out = ep->aux_out; e.ldaux = ep->ldaux;
     e.residual = ep->residual; e.ldr = ep->ldr; e.res_mod = ep->res_mod;
     e.out_f32 = (ep->out_dtype == NS_F32);
+    e.drop_bits = ep->drop_bits; e.drop_ld = ep->drop_ld;
   }
   return e;
 }

@@ -159,12 +159,16 @@ constexpr int kNtThreads = 384;
 // stages its own 128 A rows and HALF of the weight tile (BN/2 rows), the leader issues M = 256 MMAs that read both halves,
 // and each CTA's TMEM receives its 128 accumulator rows.  Per MMA every SM then moves 8 KB through shared memory instead of
 // 12 KB and fetches a third less from L2 -- the two limits of the single-CTA kernel on the encoder shapes.
-template <int BN, int CG = 1> struct NtCfg {
+// PM = 1 ("product mask"): the LAST segment (the LoRA product of an input-gradient GEMM) accumulates into its own TMEM tile
+// and the epilogue adds it only where the branch's dropout kept the element (ns_epilogue::drop_bits):
+//   D = act( A W^T + keep . (A2 W2^T) ).  Two stages x (main + masked product) x BN columns = all 512 TMEM columns at BN = 128.
+template <int BN, int CG = 1, int PM = 0> struct NtCfg {
   static constexpr int kBBytes = (BN / CG) * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kMaxSmem = 232448;             // the 227 KB opt-in limit (the runtime's 1 KB per CTA is outside it)
   static constexpr int kTailBytes = 256 + 2048;       // barriers + the epilogue's bias rows (2 column halves x 2 tile parities)
-  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int kTmemCols = PM ? 4 * BN : ((2 * BN < 32) ? 32 : 2 * BN);
+  static_assert(!PM || BN == 128, "the masked second product is built for 128-wide tiles");
   // staging for the TMA epilogue: [128 rows][64 columns] bf16 tiles (128B swizzle), see TileProg::staging_tiles
   static constexpr int kStagingTile = kBM * 128;
   static int stages_for(int staging_tiles) {
@@ -230,10 +234,10 @@ __device__ __forceinline__ void store32_f32(float* p, bool vec, int ncols, const
 #else
 #define NS_EPI_TRACE(tag) do { } while (0)
 #endif
-template <int BN, int CG>
+template <int BN, int CG, int PM>
 __global__ void __launch_bounds__(kNtThreads, 1)
 gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TileProg p) {
-  using Cfg = NtCfg<BN, CG>;
+  using Cfg = NtCfg<BN, CG, PM>;
   const int S = p.stages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);      // 128B-swizzled tiles need 1 KB alignment: no static shared memory here,
@@ -362,10 +366,13 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
       const uint32_t acc_phase = (it >> 1) & 1u;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-      uint32_t accumulate = 0;
+      const uint32_t d_main = tmem_base + static_cast<uint32_t>(acc * BN);
+      uint32_t acc_main = 0, acc_p = 0;                   // accumulate flags: main tile, masked-product tile (PM)
       for (int s = 0; s < p.nseg; ++s) {
         const Seg& sg = p.seg[s];
+        const bool to_p = PM && s == p.nseg - 1;
+        const uint32_t d_tmem = d_main + (to_p ? static_cast<uint32_t>(2 * BN) : 0u);
+        uint32_t accumulate = to_p ? acc_p : acc_main;
         for (int kb = 0; kb < sg.kblocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
           if (lane == 0) trace(1, 200 + stage);
@@ -386,8 +393,10 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
             if (CG == 2) umma_commit_mc2(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
           }
           __syncwarp();
+          accumulate = 1;                                // (the elected lane set it; keep the warp's copies equal)
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
+        if (to_p) acc_p = accumulate; else acc_main = accumulate;
       }
       if (elect_one()) {
         if (CG == 2) umma_commit_mc2(tfull_bar(acc), 3); else umma_commit(tfull_bar(acc));
@@ -447,6 +456,24 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
       }
     };
     if (tile_first < total_tiles) fetch_bias(tile_first);
+    // PM: this thread's dropout flags of the tile's columns in its half (kHalfCols / 32 words of its row), fetched one tile
+    // ahead like the bias (an L2 round trip that must not sit between the accumulator wait and the arithmetic)
+    uint2 drop_next = make_uint2(0u, 0u);
+    auto fetch_drop = [&](int tile_) {
+      if constexpr (PM) {
+        int m_tile_, n_tile_;
+        decode(tile_, m_tile_, n_tile_);
+        const int b_ = p.fd_tpb.div(m_tile_);
+        const int t_ = (m_tile_ - b_ * p.tiles_per_batch) * kBM + q * 32 + lane;
+        const int col = n_tile_ * BN + half * kHalfCols;
+        drop_next = make_uint2(0u, 0u);
+        if (t_ < p.tout && m_tile_ < m_tiles_real && col < p.N) {
+          const long long gm = static_cast<long long>(b_) * p.out_bs + static_cast<long long>(t_) * p.out_rs + p.out_off;
+          drop_next = __ldg(reinterpret_cast<const uint2*>(e.drop_bits + gm * e.drop_ld + (col >> 5)));
+        }
+      }
+    };
+    if (tile_first < total_tiles) fetch_drop(tile_first);
     // The tile loop is compiled once per epilogue SHAPE (p.epi_mode, chosen on the host): with everything decided at run
     // time a plain bias epilogue executed ~1400 warp instructions per tile and warp for ~250 useful ones (branches over
     // the unused variants, register moves between them), spread over 90 KB of code.
@@ -484,6 +511,9 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
         __syncwarp();
         if (tile + tile_step < total_tiles) fetch_bias(tile + tile_step);
       }
+      const uint2 drop_cur = drop_next;
+      (void)drop_cur;
+      if (PM && tile + tile_step < total_tiles) fetch_drop(tile + tile_step);
       // One 32-column slice of this thread's row: TMEM -> registers -> bias / scale / activation / residual.
       // `z_out` receives the pre-activation when NS_ACT_GELU has an aux output.
       // `zin` (16 packed bf16 pairs) carries this slice of the TMA-staged input tile when has_in.
@@ -644,7 +674,22 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
             uint32_t v[2][32], pk[2][16];
             tmem_ld32(acc_addr + static_cast<uint32_t>(c), v[0]);
             tmem_ld32(acc_addr + static_cast<uint32_t>(c + 32), v[1]);
-            tmem_ld_wait();
+            if constexpr (PM) {
+              // masked second product: v += keep ? P : 0 (kHalfCols == 64: the chunk is the whole half, drop_cur its two words)
+              uint32_t pv[2][32];
+              tmem_ld32(acc_addr + static_cast<uint32_t>(2 * BN + c), pv[0]);
+              tmem_ld32(acc_addr + static_cast<uint32_t>(2 * BN + c + 32), pv[1]);
+              tmem_ld_wait();
+#pragma unroll
+              for (int sidx = 0; sidx < 2; ++sidx) {
+                const uint32_t dw = sidx == 0 ? drop_cur.x : drop_cur.y;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (!((dw >> j) & 1u)) v[sidx][j] = __float_as_uint(__uint_as_float(v[sidx][j]) + __uint_as_float(pv[sidx][j]));
+              }
+            } else {
+              tmem_ld_wait();
+            }
             NS_EPI_TRACE(322);
 #pragma unroll
             for (int sidx = 0; sidx < 2; ++sidx) {
@@ -700,7 +745,10 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
       NS_EPI_TRACE(370);
     }
     };
-    if constexpr (BN >= 128) {
+    if constexpr (PM) {                                   // the host only sends plain and dGELU epilogues here
+      if (p.epi_mode == 4) run_tiles(std::integral_constant<int, 4>{});
+      else run_tiles(std::integral_constant<int, 1>{});
+    } else if constexpr (BN >= 128) {
       switch (p.epi_mode) {
         case 1: run_tiles(std::integral_constant<int, 1>{}); break;
         case 2: run_tiles(std::integral_constant<int, 2>{}); break;
@@ -891,12 +939,12 @@ gemm_tn_kernel(const __grid_constant__ TnMaps maps, const __grid_constant__ TnPr
 // ------------------------------------------------------------------------------------------------ host launchers
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <int BN, int CG>
+template <int BN, int CG, int PM = 0>
 static int launch_nt(const Maps& maps, TileProg& prog, cudaStream_t st) {
-  using Cfg = NtCfg<BN, CG>;
+  using Cfg = NtCfg<BN, CG, PM>;
   static bool attr_done = false;
   if (!attr_done) {
-    NS_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kMaxSmem));
+    NS_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<BN, CG, PM>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kMaxSmem));
     attr_done = true;
   }
   prog.n_tiles = (prog.N + BN - 1) / BN;
@@ -937,7 +985,11 @@ static int launch_nt(const Maps& maps, TileProg& prog, cudaStream_t st) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
   }
-  NS_CUDA(cudaLaunchKernelEx(&cfg, gemm_nt_kernel<BN, CG>, maps, prog));
+  if (PM && !(prog.epi_mode == 1 || prog.epi_mode == 4)) {
+    set_error("ns_gemm_nt: the dropout-masked second product supports plain and NS_ACT_DGELU epilogues with bf16 TMA tiles only");
+    return NS_ERR_UNSUPPORTED;
+  }
+  NS_CUDA(cudaLaunchKernelEx(&cfg, gemm_nt_kernel<BN, CG, PM>, maps, prog));
   NS_LAUNCH_CHECK();
   count(C_GEMM_TC);
   return NS_OK;
@@ -961,6 +1013,7 @@ static int choose_cg(long long m_tiles, int N, int bn) {
 }
 
 static int dispatch_nt(const Maps& maps, TileProg& prog, cudaStream_t st, int bn, int cg) {
+  if (prog.epi.drop_bits) return cg == 2 ? launch_nt<128, 2, 1>(maps, prog, st) : launch_nt<128, 1, 1>(maps, prog, st);
   if (bn == 256) return cg == 2 ? launch_nt<256, 2>(maps, prog, st) : launch_nt<256, 1>(maps, prog, st);
   if (bn == 128) return launch_nt<128, 1>(maps, prog, st);
   if (bn == 64) return launch_nt<64, 1>(maps, prog, st);
@@ -1037,14 +1090,27 @@ int gemm_nt_fast(long long M, int N, int K, const void* A, long long lda, const 
                  long long ldd, const EpiDev& epi, const void* A2, long long lda2, const void* W2, long long ldw2,
                  int K2, int a2_ngrp, cudaStream_t st) {
   if (M <= 0 || N <= 0) return NS_OK;
+  if (epi.drop_bits) set_error("ns_gemm_nt: operands of the dropout-masked product do not qualify for the tcgen05 path (alignment / K %% 16)");
   if (K % 16 != 0 || lda % 8 != 0 || ldw % 8 != 0 || !aligned16(A) || !aligned16(W)) return NS_ERR_UNSUPPORTED;
   if (A2 && (K2 % 16 != 0 || lda2 % 8 != 0 || ldw2 % 8 != 0 || !aligned16(A2) || !aligned16(W2))) return NS_ERR_UNSUPPORTED;
   if (M > 0x7fffffffLL) return NS_ERR_UNSUPPORTED;
   Maps maps;
   TileProg prog;
   memset(&prog, 0, sizeof(prog));
-  const int bn = choose_bn((M + kBM - 1) / kBM, N);
-  const int cg = choose_cg((M + kBM - 1) / kBM, N, bn);
+  int bn = choose_bn((M + kBM - 1) / kBM, N);
+  int cg = choose_cg((M + kBM - 1) / kBM, N, bn);
+  if (epi.drop_bits) {
+    // masked second product: 128-wide tiles (TMEM holds main + product tiles twice), CTA pairs whenever there is work for them
+    if (!A2 || a2_ngrp > 0 || N % 64 != 0 || epi.drop_ld % 2 != 0 || epi.out_f32 || epi.residual || epi.act == NS_ACT_GELU ||
+        (reinterpret_cast<uintptr_t>(epi.drop_bits) & 7) != 0) {
+      set_error("ns_gemm_nt: drop_bits needs a second product (one adapter), N %% 64 == 0, even drop_ld, bf16 output, no residual / GELU");
+      return NS_ERR_UNSUPPORTED;
+    }
+    bn = 128;
+    const long long units = (((M + kBM - 1) / kBM + 1) / 2) * ((N + bn - 1) / bn);
+    static const bool no2 = getenv("NS_GEMM_NO_2CTA") != nullptr;
+    cg = (!no2 && units * 2 >= static_cast<long long>(sm_count()) * 3 / 4) ? 2 : 1;
+  }
   {
     uint64_t dims[4] = {(uint64_t)K, 1, (uint64_t)M, 1};
     uint64_t str[3] = {(uint64_t)lda * 2, (uint64_t)lda * 2, (uint64_t)lda * 2 * (uint64_t)M};
@@ -1136,6 +1202,7 @@ int conv3_fwd_fast(int B, int Tin, int Cp, int N, int stride, const void* x, con
   prog.ldd = N;
   prog.D = y;
   fill_epi(prog, epi);
+  prog.epi.drop_bits = nullptr;                           // convolutions carry no LoRA branch
   if (int r = setup_out_maps(maps, prog, bn)) return r;
   return dispatch_nt(maps, prog, st, bn, cg);
 }
@@ -1181,6 +1248,7 @@ int conv3_dgrad_fast(int B, int Tin, int Cp, int N, int stride, const void* dz, 
     prog.ldd = Cp;
     prog.D = dx;
     fill_epi(prog, epi);
+    prog.epi.drop_bits = nullptr;
     if ((r = setup_out_maps(maps, prog, bn))) return r;
     r = dispatch_nt(maps, prog, st, bn, cg);
     if (r) return r;

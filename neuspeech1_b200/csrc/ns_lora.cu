@@ -2,9 +2,11 @@
 //
 //   y = base(x) + (alpha/r) * B(A(dropout_p(x)))          finetune.py:210  lora_dropout = 0.05 (0.1 for AdaLoRA, :206-207)
 //
-// The keep mask is a counter-based bit plane: word (module, row pair rp, column block w) holds the DROPPED flags of 16 columns x
-// the 2 rows of a row pair, bit 2*(col % 16) + (row & 1).  Its 32 Bernoulli(p) bits are drawn together from 16 hashed words
-//     km = lowbias32( (rp * 0x9E3779B1) ^ (w * 0x85EBCA77) ^ seed ^ salt )
+// The keep mask is a counter-based bit plane, row-major like the activation it masks: word (module, row, w) holds the DROPPED
+// flags of columns [32 w, 32 w + 32) of that row, bit (col % 32).  One thread that owns a row of a tile (a tcgen05 epilogue
+// lane, a mask-stage lane) reads its flags as consecutive words.  The 32 Bernoulli(p) bits of a word are drawn together from 16
+// hashed words
+//     km = lowbias32( (row * 0x9E3779B1) ^ (w * 0x85EBCA77) ^ seed ^ salt )
 //     R_i = mix1( km + (i + 1) * 0xC2B2AE35 ),   i = 0..15        mix1(x): x ^= x >> 16; x *= 0x7FEB352D; x ^= x >> 15
 // combined along the binary expansion of thr16 = round(p * 65536), least significant bit first:
 //     D = 0;   D = bit_i(thr16) ? (D | R_i) : (D & R_i)         =>  every bit of D is set with probability thr16 / 65536
@@ -16,7 +18,7 @@
 // Convention: kernels work with the UNSCALED masked input x (.) keep; the 1/(1-p) lives in alpha' = (alpha/r)/(1-p), which
 // scales t = alpha' (x.keep) A^T forward and dt' = alpha' g B backward, so dA = dt'^T (x.keep) and dx += (dt' A).keep.
 //
-//   ns_dropout_bits   bits[g][row pair][col / 16]: bit 2*(col % 16) + (row & 1) set <=> dropped
+//   ns_dropout_bits   bits[g][row][col / 32]: bit (col % 32) set <=> dropped
 //   ns_lora_down      t[M, G*r] = alpha' * (x . keep_g) A_g^T      HBM-bound: x streams through registers once, A_g in shared
 //                     memory, mma.sync m16n8k16 on register fragments (a rank-32 product cannot feed tcgen05's 128-row tiles
 //                     from registers; the kernel is bound by the read of x, not by the tensor pipe)
@@ -39,10 +41,10 @@ __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
   return x;
 }
 constexpr uint32_t kRowMul = 0x9E3779B1u, kColMul = 0x85EBCA77u, kIdxMul = 0xC2B2AE35u;
-// the 32 dropped flags of (row pair, 16-column block): see the file header
+// the 32 dropped flags of (row, 32-column block): see the file header
 __device__ __forceinline__ uint32_t mix1(uint32_t x) { x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; return x; }
-__device__ __forceinline__ uint32_t drop_plane_word(uint32_t rp, uint32_t w, uint32_t module_seed, uint32_t thr) {
-  const uint32_t km = lowbias32((rp * kRowMul) ^ (w * kColMul) ^ module_seed);
+__device__ __forceinline__ uint32_t drop_plane_word(uint32_t row, uint32_t w, uint32_t module_seed, uint32_t thr) {
+  const uint32_t km = lowbias32((row * kRowMul) ^ (w * kColMul) ^ module_seed);
   uint32_t d = 0;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
@@ -61,33 +63,32 @@ struct Salts { uint32_t s[3]; };
 // ------------------------------------------------------------------------------------------------ seed / mask planes
 __global__ void seed_advance_kernel(uint32_t* seed) { *seed = lowbias32(*seed + 0x9E3779B9u); }
 
-// one thread per output word = 16 columns of one row pair; block = 8 row pairs x 32 words, grid (word blocks, row-pair blocks, G)
-__global__ void __launch_bounds__(256) dropout_bits_kernel(int row_pairs, int cols, int words, const uint32_t* __restrict__ seed,
+// one thread per output word = 32 columns of one row; consecutive threads write consecutive words of the plane
+__global__ void __launch_bounds__(256) dropout_bits_kernel(long long rows, int cols, int words, const uint32_t* __restrict__ seed,
                                                            Salts salts, uint32_t thr, uint32_t* __restrict__ bits) {
-  const int g = blockIdx.z;
+  const int g = blockIdx.y;
   const uint32_t ms = *seed ^ salts.s[g];
-  const int w = blockIdx.x * 32 + (threadIdx.x & 31);
-  if (w >= words) return;
-  const int valid = cols - w * 16;                              // columns of this block that exist
-  const uint32_t vmask = valid < 16 ? (1u << (2 * valid)) - 1u : 0xFFFFFFFFu;
-  uint32_t* out = bits + static_cast<long long>(g) * row_pairs * words + w;
-  for (int rp = blockIdx.y * 8 + (threadIdx.x >> 5); rp < row_pairs; rp += gridDim.y * 8)
-    out[static_cast<long long>(rp) * words] = drop_plane_word(static_cast<uint32_t>(rp), static_cast<uint32_t>(w), ms, thr) & vmask;
+  const long long total = rows * words;
+  uint32_t* out = bits + static_cast<long long>(g) * total;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / words;
+    const int w = static_cast<int>(i - row * words);
+    const int valid = cols - w * 32;                              // columns of this block that exist
+    const uint32_t vmask = valid < 32 ? (1u << valid) - 1u : 0xFFFFFFFFu;
+    out[i] = drop_plane_word(static_cast<uint32_t>(row), static_cast<uint32_t>(w), ms, thr) & vmask;
+  }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) dropout_apply_kernel(long long rows, int cols, const T* __restrict__ x, long long ldx,
                                                             T* __restrict__ y, long long ldy, const uint32_t* __restrict__ bits) {
-  const long long pairs = (rows + 1) >> 1;
-  const int words = (cols + 15) >> 4;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < pairs * cols;
+  const int words = (cols + 31) >> 5;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows * cols;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long rp = i / cols;
-    const int c = static_cast<int>(i - rp * cols);
-    const uint32_t d = (bits[rp * words + (c >> 4)] >> (2 * (c & 15))) & 3u;
-    const long long r0 = rp * 2;
-    y[r0 * ldy + c] = (d & 1u) ? from_f<T>(0.f) : x[r0 * ldx + c];
-    if (r0 + 1 < rows) y[(r0 + 1) * ldy + c] = (d & 2u) ? from_f<T>(0.f) : x[(r0 + 1) * ldx + c];
+    const long long r = i / cols;
+    const int c = static_cast<int>(i - r * cols);
+    const uint32_t d = (bits[r * words + (c >> 5)] >> (c & 31)) & 1u;
+    y[r * ldy + c] = d ? from_f<T>(0.f) : x[r * ldx + c];
   }
 }
 
@@ -116,14 +117,13 @@ __global__ void __launch_bounds__(256) lora_dx_fix_kernel(long long rows, int K,
     sd[gr + j] = two ? to_f<T>(dt[(r0 + 1) * lddt + j]) : 0.f;
   }
   __syncwarp();
-  const long long RP = (rows + 1) >> 1;
-  const int W = (K + 15) >> 4;
+  const int W = (K + 31) >> 5;
   for (int c = lane; c < K; c += 32) {
     float fix0 = 0.f, fix1 = 0.f;
     bool any0 = false, any1 = false;
     for (int g = 0; g < G; ++g) {
-      const uint32_t w = bits[(static_cast<long long>(g) * RP + rp) * W + (c >> 4)] >> (2 * (c & 15));
-      const bool d0 = (w & 1u) != 0, d1 = two && (w & 2u) != 0;
+      const uint32_t* bw = bits + (static_cast<long long>(g) * rows + r0) * W + (c >> 5);
+      const bool d0 = ((bw[0] >> (c & 31)) & 1u) != 0, d1 = two && ((bw[W] >> (c & 31)) & 1u) != 0;
       if (d0 | d1) {
         const T* a = At + static_cast<long long>(c) * ldat + g * r;
         float acc0 = 0.f, acc1 = 0.f;
@@ -164,6 +164,9 @@ __device__ __forceinline__ void ldsm_x2_trans(uint32_t (&r)[2], uint32_t saddr) 
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(g), "r"(src_bytes));
 }
+__device__ __forceinline__ void cp_async4(uint32_t saddr, const void* g, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(saddr), "l"(g), "r"(src_bytes));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -197,8 +200,7 @@ __global__ void __launch_bounds__(WARPS * 32) lora_down_kernel(long long M, int 
   const long long rpw = (((M + n_warps - 1) / n_warps) + 1) & ~1LL;      // equal, contiguous, even-aligned row range per warp
   const long long r_begin = (static_cast<long long>(blockIdx.x) * WARPS + warp) * rpw;
   const long long r_end = r_begin + rpw < M ? r_begin + rpw : M;
-  const long long RP = (M + 1) >> 1;
-  const int W = (K + 15) >> 4;
+  const int W = (K + 31) >> 5;
   const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
   for (long long R0 = r_begin; R0 < r_end; R0 += 16 * MT) {
     const bool two = MT == 2 && R0 + 16 < r_end;
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(WARPS * 32) lora_down_kernel(long long M, int 
       for (int o = 0; o < 2; ++o) { ok[mt][o] = re + o < r_end; xr[mt][o] = x + (ok[mt][o] ? re + o : 0) * ldx + tq * 8; }
 #pragma unroll
       for (int gi = 0; gi < G; ++gi)
-        brow[mt][gi] = bits ? bits + (static_cast<long long>(gi) * RP + (ok[mt][0] ? (re >> 1) : 0)) * W + (tq >> 1) : nullptr;
+        brow[mt][gi] = bits ? bits + (static_cast<long long>(gi) * M + (ok[mt][0] ? re : 0)) * W : nullptr;
     }
     uint4 buf[D][MT][2];
 #pragma unroll
@@ -253,12 +255,13 @@ __global__ void __launch_bounds__(WARPS * 32) lora_down_kernel(long long M, int 
               const uint32_t e[4] = {cur[mt][0].x, cur[mt][0].y, cur[mt][0].z, cur[mt][0].w};
               const uint32_t o[4] = {cur[mt][1].x, cur[mt][1].y, cur[mt][1].z, cur[mt][1].w};
               if (bits) {
-                // 16 bits of this thread's 8 columns: bit 2j = (even row, col j) dropped, bit 2j+1 = (odd row, col j)
-                const uint32_t hb = __ldg(brow[mt][gi] + (c0 >> 4)) >> (16 * (tq & 1));
+                // the flags of this thread's 8 columns in its even and odd row (one word per row and 32-column chunk)
+                const uint32_t be = __ldg(brow[mt][gi] + (c0 >> 5)) >> (8 * tq);
+                const uint32_t bo = ok[mt][1] ? __ldg(brow[mt][gi] + W + (c0 >> 5)) >> (8 * tq) : 0u;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  xe[mt][i] = e[i] & keep_mask2(hb >> (4 * i), hb >> (4 * i + 2));
-                  xo[mt][i] = o[i] & keep_mask2(hb >> (4 * i + 1), hb >> (4 * i + 3));
+                  xe[mt][i] = e[i] & keep_mask2(be >> (2 * i), be >> (2 * i + 1));
+                  xo[mt][i] = o[i] & keep_mask2(bo >> (2 * i), bo >> (2 * i + 1));
                 }
               } else {
 #pragma unroll
@@ -297,8 +300,7 @@ __global__ void __launch_bounds__(WARPS * 32) lora_down_kernel(long long M, int 
 // ------------------------------------------------------------------------------------------------ dA_g += dt'_g^T (x . keep_g)  (+ dx fix)
 // CTA = (256-column slab of K, row slab), 16 warps x 16 columns.  D'[col, r] = sum_m x[m, col] dt'[m, r]: both operands are
 // read "transposed" from their row-major shared tiles with ldmatrix.trans; a fragment register then holds the two rows of a row
-// pair at one column, which is exactly what one pair of mask bits covers.  cp.async ring of 32-row tiles of x, dt' and the
-// mask words of the slab (16 row pairs x 16 words per adapter).
+// pair at one column.  cp.async ring of 32-row tiles of x, dt' and the mask words of the slab (32 rows x 8 words per adapter).
 // FIX: the same pass removes the dropped terms from dx (the input-gradient GEMM added dt' A for every element).  Forming the
 // whole rank-r product P = dt' A for the warp's 16 rows x 16 columns costs 4 MMAs per adapter (its A^T fragments stay in
 // registers for the CTA's lifetime) -- cheaper than gathering r coefficients per dropped element with divergent lanes -- and P
@@ -322,8 +324,8 @@ __global__ void __launch_bounds__(DA_WARPS * 32) lora_da_kernel(long long M, int
   constexpr int R = NT * 8, GR = G * R, KS = (R + 15) / 16;
   constexpr int XP = (DA_COLS + 8) * 2;                 // x tile pitch (bytes): +16 B -> conflict-free ldmatrix
   constexpr int DP = (GR + 8) * 2;                      // dt' tile pitch
-  constexpr int BITS_OFF = DA_ROWS * XP + DA_ROWS * DP; // mask words: [G][16 row pairs][16 words]
-  constexpr int Z_OFF = BITS_OFF + G * 16 * 64;         // ZG: z tile, same pitch as x
+  constexpr int BITS_OFF = DA_ROWS * XP + DA_ROWS * DP; // mask words: [G][32 rows][8 words]
+  constexpr int Z_OFF = BITS_OFF + G * 32 * 32;         // ZG: z tile, same pitch as x
   constexpr int STAGE = Z_OFF + (ZG ? DA_ROWS * XP : 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
   const int k0 = blockIdx.x * DA_COLS;
@@ -331,8 +333,7 @@ __global__ void __launch_bounds__(DA_WARPS * 32) lora_da_kernel(long long M, int
   const long long m_end = m_begin + rows_per_slab < M ? m_begin + rows_per_slab : M;
   const int n_tiles = m_end > m_begin ? static_cast<int>((m_end - m_begin + DA_ROWS - 1) / DA_ROWS) : 0;
   const uint32_t sbase = smem_u32(smem_raw);
-  const long long RP = (M + 1) >> 1;
-  const int W = (K + 15) >> 4;
+  const int W = (K + 31) >> 5;
 
   auto issue = [&](int tile) {
     if (tile < n_tiles) {
@@ -350,12 +351,11 @@ __global__ void __launch_bounds__(DA_WARPS * 32) lora_da_kernel(long long M, int
         cp_async16(st + DA_ROWS * XP + rr * DP + v * 16, dt + (ok ? (mrow + rr) * lddt + v * 8 : 0), ok ? 16 : 0);
       }
       if (bits) {
-        for (int i = threadIdx.x; i < G * 16 * 4; i += DA_WARPS * 32) {       // 16 row pairs x 4 chunks of 4 words per adapter
-          const int gi = i >> 6, pr = (i >> 2) & 15, v = i & 3;
-          const long long rp = (mrow >> 1) + pr;
-          const bool ok = rp < RP && (k0 >> 4) + v * 4 < W;
-          cp_async16(st + BITS_OFF + (gi * 16 + pr) * 64 + v * 16, bits + (ok ? (static_cast<long long>(gi) * RP + rp) * W + (k0 >> 4) + v * 4 : 0),
-                     ok ? 16 : 0);
+        for (int i = threadIdx.x; i < G * 32 * 8; i += DA_WARPS * 32) {       // 32 rows x 8 words per adapter
+          const int gi = i >> 8, rr = (i >> 3) & 31, v = i & 7;
+          const bool ok = mrow + rr < M && (k0 >> 5) + v < W;
+          cp_async4(st + BITS_OFF + (gi * 32 + rr) * 32 + v * 4, bits + (ok ? (static_cast<long long>(gi) * M + mrow + rr) * W + (k0 >> 5) + v : 0),
+                    ok ? 4 : 0);
         }
       }
     }
@@ -412,12 +412,13 @@ __global__ void __launch_bounds__(DA_WARPS * 32) lora_da_kernel(long long M, int
         uint32_t am[4];
         if (bits) {
           // dA side: fragment registers hold rows (2t, 2t+1) [a0, a1] and (2t+8, 2t+9) [a2, a3] at columns g [a0, a2], g+8 [a1, a3]
-          const uint32_t* bw = reinterpret_cast<const uint32_t*>(stp + BITS_OFF + (gi * 16 + ks * 8 + tq) * 64) + warp;
-          const uint32_t w0 = bw[0] >> (2 * g), w1 = bw[4 * 16] >> (2 * g);
-          am[0] = a[0] & keep_mask2(w0, w0 >> 1);
-          am[1] = a[1] & keep_mask2(w0 >> 16, w0 >> 17);
-          am[2] = a[2] & keep_mask2(w1, w1 >> 1);
-          am[3] = a[3] & keep_mask2(w1 >> 16, w1 >> 17);
+          const uint32_t* bw = reinterpret_cast<const uint32_t*>(stp + BITS_OFF + (gi * 32 + ks * 16 + 2 * tq) * 32) + (warp >> 1);
+          const int sh = (warp & 1) * 16 + g;
+          const uint32_t w0 = bw[0] >> sh, w1 = bw[8] >> sh, w2 = bw[64] >> sh, w3 = bw[72] >> sh;   // rows 2t, 2t+1, 2t+8, 2t+9
+          am[0] = a[0] & keep_mask2(w0, w1);
+          am[1] = a[1] & keep_mask2(w0 >> 8, w1 >> 8);
+          am[2] = a[2] & keep_mask2(w2, w3);
+          am[3] = a[3] & keep_mask2(w2 >> 8, w3 >> 8);
         } else {
 #pragma unroll
           for (int i = 0; i < 4; ++i) am[i] = a[i];
@@ -451,10 +452,13 @@ __global__ void __launch_bounds__(DA_WARPS * 32) lora_da_kernel(long long M, int
 #pragma unroll
             for (int j = 0; j < 2; ++j) mma_bf16_16816(P[j], da[0], da[1], da[2], da[3], bf[gi][j][kk][0], bf[gi][j][kk][1]);
           }
-          const uint32_t wd = *(reinterpret_cast<const uint32_t*>(stp + BITS_OFF + (gi * 16 + ks * 8 + g) * 64) + warp);
+          const uint32_t* bd = reinterpret_cast<const uint32_t*>(stp + BITS_OFF + (gi * 32 + ks * 16 + 2 * g) * 32) + (warp >> 1);
+          const uint32_t we = bd[0] >> ((warp & 1) * 16), wo = bd[8] >> ((warp & 1) * 16);   // this thread's row pair
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            const uint32_t d = (wd >> (2 * (8 * j + 2 * tq))) & 15u;   // bit0 (even row, col) bit1 (odd, col) bit2 (even, col+1) bit3 (odd, col+1)
+            const int cj = 8 * j + 2 * tq;
+            // bit0 (even row, col) bit1 (odd, col) bit2 (even, col+1) bit3 (odd, col+1)
+            const uint32_t d = ((we >> cj) & 1u) | (((wo >> cj) & 1u) << 1) | (((we >> (cj + 1)) & 1u) << 2) | (((wo >> (cj + 1)) & 1u) << 3);
             f[j][0] += (d & 1u) ? P[j][0] : 0.f; f[j][1] += (d & 4u) ? P[j][1] : 0.f;
             f[j][2] += (d & 2u) ? P[j][2] : 0.f; f[j][3] += (d & 8u) ? P[j][3] : 0.f;
             fl[j] |= d;
@@ -516,7 +520,7 @@ static int launch_da_variant(long long M, int K, const void* x, long long ldx, c
                              const uint32_t* bits, void* dx, long long lddx, const void* At, long long ldat, const void* z, long long ldz,
                              cudaStream_t st) {
   constexpr int R = NT * 8, GR = G * R;
-  constexpr int STAGE = DA_ROWS * (DA_COLS + 8) * 2 * (ZG ? 2 : 1) + DA_ROWS * (GR + 8) * 2 + G * 16 * 64;
+  constexpr int STAGE = DA_ROWS * (DA_COLS + 8) * 2 * (ZG ? 2 : 1) + DA_ROWS * (GR + 8) * 2 + G * 32 * 32;
   constexpr int STAGES = (216 * 1024) / STAGE >= 8 ? 8 : (216 * 1024) / STAGE;
   static_assert(STAGES >= 3, "ring too shallow");
   constexpr size_t ring = static_cast<size_t>(STAGE) * STAGES;
@@ -557,85 +561,6 @@ static int launch_da(long long M, int K, const void* x, long long ldx, const voi
   if (dx && z) return launch_da_variant<G, NT, true, true>(M, K, x, ldx, dt, lddt, dA, ldg, bits, dx, lddx, At, ldat, z, ldz, st);
   if (dx) return launch_da_variant<G, NT, true, false>(M, K, x, ldx, dt, lddt, dA, ldg, bits, dx, lddx, At, ldat, z, ldz, st);
   return launch_da_variant<G, NT, false, false>(M, K, x, ldx, dt, lddt, dA, ldg, bits, dx, lddx, At, ldat, z, ldz, st);
-}
-
-// ------------------------------------------------------------------------------------------------ t = alpha' (x . keep) A^T, one adapter
-// Many small CTAs instead of one register-heavy CTA per SM: 4 warps x 16 rows, no software prefetch, 40-odd registers per
-// thread, A staged in shared memory in column chunks of KC -- latency is hidden by 30+ resident warps per SM (the LayerNorm
-// kernels reach 5.9 TB/s that way; the persistent version above sat at 3 TB/s waiting on the long scoreboard).
-constexpr int DT_KC = 512;
-template <int NT>
-__global__ void __launch_bounds__(128, 6) lora_down_tlp_kernel(long long M, int K, const __nv_bfloat16* __restrict__ x, long long ldx,
-                                                              const __nv_bfloat16* __restrict__ A, long long lda,
-                                                              __nv_bfloat16* __restrict__ t, long long ldt, float alpha,
-                                                              const uint32_t* __restrict__ bits) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int R = NT * 8;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
-  const long long R0 = (static_cast<long long>(blockIdx.x) * 4 + warp) * 16;
-  const long long re = R0 + 2 * g;
-  const bool okE = re < M, okO = re + 1 < M;
-  const __nv_bfloat16* xe = x + (okE ? re : 0) * ldx + tq * 8;
-  const __nv_bfloat16* xo = x + (okO ? re + 1 : 0) * ldx + tq * 8;
-  const int W = (K + 15) >> 4;
-  const uint32_t* brow = bits ? bits + (okE ? (re >> 1) : 0) * W + (tq >> 1) : nullptr;
-  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-  float acc[NT][4];
-#pragma unroll
-  for (int c = 0; c < NT; ++c)
-#pragma unroll
-    for (int d = 0; d < 4; ++d) acc[c][d] = 0.f;
-  for (int kc = 0; kc < K; kc += DT_KC) {
-    const int kw = K - kc < DT_KC ? K - kc : DT_KC;          // columns of this chunk (multiple of 32)
-    const int pitch = kw * 2 + 64;
-    if (kc) __syncthreads();
-    for (int i = threadIdx.x; i < R * (kw / 8); i += 128) {
-      const int row = i / (kw / 8), v = i - row * (kw / 8);
-      *reinterpret_cast<uint4*>(smem_raw + row * pitch + v * 16) = __ldg(reinterpret_cast<const uint4*>(A + row * lda + kc) + v);
-    }
-    __syncthreads();
-    if (R0 < M) {
-#pragma unroll 4
-      for (int c0 = 0; c0 < kw; c0 += 32) {
-        uint4 e = okE ? __ldg(reinterpret_cast<const uint4*>(xe + kc + c0)) : zero4;
-        uint4 o = okO ? __ldg(reinterpret_cast<const uint4*>(xo + kc + c0)) : zero4;
-        if (bits) {
-          const uint32_t hb = __ldg(brow + ((kc + c0) >> 4)) >> (16 * (tq & 1));
-          e.x &= keep_mask2(hb, hb >> 2);       o.x &= keep_mask2(hb >> 1, hb >> 3);
-          e.y &= keep_mask2(hb >> 4, hb >> 6);  o.y &= keep_mask2(hb >> 5, hb >> 7);
-          e.z &= keep_mask2(hb >> 8, hb >> 10); o.z &= keep_mask2(hb >> 9, hb >> 11);
-          e.w &= keep_mask2(hb >> 12, hb >> 14); o.w &= keep_mask2(hb >> 13, hb >> 15);
-        }
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          const uint4 w = *reinterpret_cast<const uint4*>(smem_raw + (nt * 8 + g) * pitch + (c0 + tq * 8) * 2);
-          mma_bf16_16816(acc[nt], e.x, o.x, e.y, o.y, w.x, w.y);
-          mma_bf16_16816(acc[nt], e.z, o.z, e.w, o.w, w.z, w.w);
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    const int col = nt * 8 + tq * 2;
-    if (okE) *reinterpret_cast<uint32_t*>(t + re * ldt + col) = pack_bf16x2(alpha * acc[nt][0], alpha * acc[nt][1]);
-    if (okO) *reinterpret_cast<uint32_t*>(t + (re + 1) * ldt + col) = pack_bf16x2(alpha * acc[nt][2], alpha * acc[nt][3]);
-  }
-}
-
-template <int NT>
-static int launch_down_tlp(long long M, int K, const void* x, long long ldx, const void* A, long long lda, void* t, long long ldt,
-                           float alpha, const uint32_t* bits, cudaStream_t st) {
-  const int kw = K < DT_KC ? K : DT_KC;
-  const size_t smem = static_cast<size_t>(NT) * 8 * (kw * 2 + 64);
-  static bool attr_done = false;
-  auto kern = lora_down_tlp_kernel<NT>;
-  if (!attr_done) { NS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, NT * 8 * (DT_KC * 2 + 64))); attr_done = true; }
-  kern<<<static_cast<unsigned>((M + 63) / 64), 128, smem, st>>>(M, K, static_cast<const __nv_bfloat16*>(x), ldx,
-                                                               static_cast<const __nv_bfloat16*>(A), lda, static_cast<__nv_bfloat16*>(t), ldt, alpha,
-                                                               bits);
-  NS_LAUNCH_CHECK();
-  return NS_OK;
 }
 
 template <typename Kern>
@@ -691,7 +616,7 @@ int ns_seed_advance(unsigned int* seed, void* stream) {
   return NS_OK;
 }
 
-long long ns_dropout_bits_words(long long rows, int cols) { return ((rows + 1) / 2) * ((cols + 15) / 16); }
+long long ns_dropout_bits_words(long long rows, int cols) { return rows * ((cols + 31) / 32); }
 
 int ns_dropout_bits(long long rows, int cols, int G, const unsigned int* seed, const unsigned int* salts, float p, unsigned int* bits,
                     void* stream) {
@@ -699,13 +624,11 @@ int ns_dropout_bits(long long rows, int cols, int G, const unsigned int* seed, c
   NS_CHECK_ARG(p >= 0.f && p < 1.f, "ns_dropout_bits: p = %f out of [0, 1)", p);
   if (rows == 0) return NS_OK;
   Salts s{{salts[0], G > 1 ? salts[1] : 0u, G > 2 ? salts[2] : 0u}};
-  const int rp = static_cast<int>((rows + 1) / 2);
-  const int words = (cols + 15) / 16;
-  const int wblocks = (words + 31) / 32;
-  int rblocks = (rp + 7) / 8;
-  const int cap = (148 * 8 + wblocks * G - 1) / (wblocks * G);     // about 8 CTAs per SM in total, each looping over row pairs
-  if (rblocks > cap) rblocks = cap;
-  dropout_bits_kernel<<<dim3(wblocks, rblocks, G), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(rp, cols, words, seed, s, thr16(p), bits);
+  const int words = (cols + 31) / 32;
+  long long blocks = (rows * words + 255) / 256;
+  const long long cap = (static_cast<long long>(sm_count()) * 8 + G - 1) / G;    // about 8 CTAs per SM in total, grid-stride loops
+  if (blocks > cap) blocks = cap;
+  dropout_bits_kernel<<<dim3(static_cast<unsigned>(blocks), G), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(rows, cols, words, seed, s, thr16(p), bits);
   NS_LAUNCH_CHECK();
   count(C_OTHER);
   return NS_OK;
@@ -717,7 +640,7 @@ int ns_dropout_apply(int dtype, long long rows, int cols, const void* x, long lo
   NS_CHECK_ARG(rows >= 0 && cols > 0 && x && y && bits && ldx >= cols && ldy >= cols, "ns_dropout_apply: bad shape/pointers");
   if (rows == 0) return NS_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const long long n = ((rows + 1) / 2) * cols;
+  const long long n = rows * cols;
   long long blocks = (n + 255) / 256;
   if (blocks > 148LL * 32) blocks = 148LL * 32;
   if (dtype == NS_BF16)
@@ -766,12 +689,6 @@ int ns_lora_down(long long M, int K, int G, int r, const void* x, long long ldx,
     return NS_ERR_UNSUPPORTED;
   }
   count(C_OTHER);
-  static const bool tlp = getenv("NS_LORA_DOWN_TLP") != nullptr;      // developer A/B switch: many small CTAs (slower: 51 vs 45 us)
-  if (G == 1 && tlp) {
-    if (r == 32) return launch_down_tlp<4>(M, K, x, ldx, A, lda, t, ldt, alpha, bits, st);
-    if (r == 16) return launch_down_tlp<2>(M, K, x, ldx, A, lda, t, ldt, alpha, bits, st);
-    if (r == 8) return launch_down_tlp<1>(M, K, x, ldx, A, lda, t, ldt, alpha, bits, st);
-  }
 #define NS_W1 , 16, 2
 #define NS_W3 , 8, 2
   NS_LORA_DISPATCH(launch_down, M, K, x, ldx, A, lda, t, ldt, alpha, bits, st);
@@ -787,7 +704,7 @@ int ns_lora_da(long long M, int K, int G, int r, const void* x, long long ldx, c
   NS_CHECK_ARG(M >= 0 && K > 0 && K % 64 == 0 && x && dt && dA, "ns_lora_da: bad shape/pointers (K must be a multiple of 64)");
   NS_CHECK_ARG(ldx >= K && lddt >= G * r && ldg >= K && ldx % 8 == 0 && lddt % 8 == 0 && ldg % 4 == 0, "ns_lora_da: bad leading dimensions");
   NS_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dt) & 15) == 0 && (reinterpret_cast<uintptr_t>(dA) & 15) == 0 &&
-                   (reinterpret_cast<uintptr_t>(bits) & 15) == 0,
+                   (reinterpret_cast<uintptr_t>(bits) & 3) == 0,
                "ns_lora_da: operands must be 16-byte aligned");
   NS_CHECK_ARG(!dx || (bits && At && lddx >= K && lddx % 2 == 0 && ldat >= G * r && ldat % 2 == 0 && M * lddx < (1LL << 32) &&
                        (reinterpret_cast<uintptr_t>(dx) & 3) == 0 && (reinterpret_cast<uintptr_t>(At) & 3) == 0),

@@ -27,6 +27,7 @@ from . import ops
 from ._abi import ACT_DGELU, ACT_GELU, ACT_NONE, NS_BF16, NS_F32
 
 _NO_TRAIN_GRAPH = bool(os.environ.get("NS_NO_TRAIN_GRAPH"))     # developer switch: launch every kernel of train_step one by one
+_NO_GEMM_MASK = bool(os.environ.get("NS_NO_GEMM_MASK"))         # developer A/B switch: dropout correction pass instead of the masked GEMM product
 ENC_LORA_TARGETS = ("q_proj", "k_proj", "v_proj", "out_proj", "fc1", "fc2")
 
 
@@ -205,7 +206,7 @@ class WhisperEEGEngine:
 
     def _bits(self, layer: int, targets, M: int, K: int) -> torch.Tensor:
         """Bit plane of the dropped elements of `targets`: drawn in the forward, kept for the backward consumers."""
-        return self.ws.get(f"dropbits.{layer}.{targets[0]}", (len(targets), (M + 1) // 2, (K + 15) // 16), torch.int32)
+        return self.ws.get(f"dropbits.{layer}.{targets[0]}", (len(targets), M, (K + 31) // 32), torch.int32)
 
     def _lora_down(self, x: torch.Tensor, A: torch.Tensor, t: torch.Tensor, layer: int, targets):
         """t[:, g*r:(g+1)*r] = alpha' * dropout_g(x) A_g^T for the adapters `targets` stacked in A (PEFT lora.Linear:
@@ -226,11 +227,20 @@ class WhisperEEGEngine:
                 ops.dropout_apply(x, xm, bits[g])
                 ops.gemm_nt(xm, A[g * r:(g + 1) * r], t[:, g * r:(g + 1) * r], self._ep(alpha=a, alpha_cols=r))
 
-    def _lora_da_fix(self, x: torch.Tensor, dt: torch.Tensor, dx: torch.Tensor, At: torch.Tensor, layer: int, targets,
+    def _drop_plane(self, layer: int, target: str, M: int, K: int) -> Optional[torch.Tensor]:
+        """The (M, K/32) dropout plane of ONE adapter for the input-gradient GEMM's masked second product (ns_epilogue.drop_bits:
+        dx = g W + keep . (dt' A), the LoRA product masked in the epilogue), or None when the step runs without dropout or the
+        shape / storage takes the correction pass instead (`_lora_da_fix(dx=...)`)."""
+        if self._drop_p == 0.0 or not self.use_lora_kernels or K % 64 != 0 or _NO_GEMM_MASK:
+            return None
+        return self._bits(layer, (target,), M, K)[0]
+
+    def _lora_da_fix(self, x: torch.Tensor, dt: torch.Tensor, dx: Optional[torch.Tensor], At: torch.Tensor, layer: int, targets,
                      z: Optional[torch.Tensor] = None):
         """dA_g += dt_g^T dropout_g(x) into the flat gradient buffer (the A gradients of `targets` are contiguous) and, under
-        dropout, the correction of the input gradient: the GEMM that produced `dx` added dt' A for EVERY element (K-segment);
-        the dropped ones are taken out again (times gelu'(z) where dx went through the GELU backward)."""
+        dropout with `dx` given, the correction of the input gradient: the GEMM that produced `dx` added dt' A for EVERY element
+        (K-segment); the dropped ones are taken out again (times gelu'(z) where dx went through the GELU backward).  dx = None:
+        the GEMM already masked its LoRA product (`_drop_plane`)."""
         p, r, G = self._drop_p, self.dims.lora_r, len(targets)
         M, K = x.shape
         off, _ = self.layout.entries[lora_module_name(layer, targets[0]) + ".lora_A.default.weight"]
@@ -240,13 +250,14 @@ class WhisperEEGEngine:
             return
         bits = self._bits(layer, targets, M, K)
         if self._fast_lora(K, G):
-            ops.lora_da(x, dt, gA, G, bits, dx=dx, At=At, z=z)
+            ops.lora_da(x, dt, gA, G, bits, dx=dx, At=At if dx is not None else None, z=z if dx is not None else None)
         else:
             xm = self.ws.get(f"xm.{K}", x.shape, self.dtype)
             for g in range(G):
                 ops.dropout_apply(x, xm, bits[g])
                 ops.gemm_tn(xm, dt[:, g * r:(g + 1) * r], gA[g * r:(g + 1) * r], 1, K)
-            ops.lora_dx_fix(dx, dt, At, bits, G, z)
+            if dx is not None:
+                ops.lora_dx_fix(dx, dt, At, bits, G, z)
 
     # ------------------------------------------------------------------ parameters
     def _c(self, t: torch.Tensor) -> torch.Tensor:
@@ -676,8 +687,10 @@ class WhisperEEGEngine:
                 dt2 = ws.get("dt_r", (M, r), dt)
                 ops.gemm_nt(dh, W[k + ".B_fc2_t"], dt2, self._ep(alpha=s, alpha_cols=r))
                 ops.gemm_tn(dh, g("t_2"), G("fc2", "B"), r, 1)
-                ops.gemm_nt(dh, W[k + ".w2_t"], dz1, self._ep(act=ACT_DGELU, aux_in=g("z1"), ldaux=F), a2=dt2, w2=W[k + ".A_fc2_t"], k2=r)
-                self._lora_da_fix(g("m"), dt2, dz1, W[k + ".A_fc2_t"], i, ("fc2",), z=g("z1"))
+                db = self._drop_plane(i, "fc2", M, F)
+                ops.gemm_nt(dh, W[k + ".w2_t"], dz1, self._ep(act=ACT_DGELU, aux_in=g("z1"), ldaux=F, drop_bits=db), a2=dt2,
+                            w2=W[k + ".A_fc2_t"], k2=r)
+                self._lora_da_fix(g("m"), dt2, dz1 if db is None else None, W[k + ".A_fc2_t"], i, ("fc2",), z=g("z1"))
             else:
                 ops.gemm_nt(dh, W[k + ".w2_t"], dz1, self._ep(act=ACT_DGELU, aux_in=g("z1"), ldaux=F))
             # fc1
@@ -686,8 +699,9 @@ class WhisperEEGEngine:
                 dt1 = ws.get("dt_r", (M, r), dt)
                 ops.gemm_nt(dz1, W[k + ".B_fc1_t"], dt1, self._ep(alpha=s, alpha_cols=r))
                 ops.gemm_tn(dz1, g("t_1"), G("fc1", "B"), r, 1)
-                ops.gemm_nt(dz1, W[k + ".w1_t"], du2, self._ep(), a2=dt1, w2=W[k + ".A_fc1_t"], k2=r)
-                self._lora_da_fix(g("u2"), dt1, du2, W[k + ".A_fc1_t"], i, ("fc1",))
+                db = self._drop_plane(i, "fc1", M, d)
+                ops.gemm_nt(dz1, W[k + ".w1_t"], du2, self._ep(drop_bits=db), a2=dt1, w2=W[k + ".A_fc1_t"], k2=r)
+                self._lora_da_fix(g("u2"), dt1, du2 if db is None else None, W[k + ".A_fc1_t"], i, ("fc1",))
             else:
                 ops.gemm_nt(dz1, W[k + ".w1_t"], du2, self._ep())
             dhm = ws.get("dh_b", (M, d), dt)
@@ -698,8 +712,9 @@ class WhisperEEGEngine:
                 dto = ws.get("dt_r", (M, r), dt)
                 ops.gemm_nt(dhm, W[k + ".B_out_proj_t"], dto, self._ep(alpha=s, alpha_cols=r))
                 ops.gemm_tn(dhm, g("t_o"), G("out_proj", "B"), r, 1)
-                ops.gemm_nt(dhm, W[k + ".wo_t"], do, self._ep(), a2=dto, w2=W[k + ".A_out_proj_t"], k2=r)
-                self._lora_da_fix(g("o"), dto, do, W[k + ".A_out_proj_t"], i, ("out_proj",))
+                db = self._drop_plane(i, "out_proj", M, d)
+                ops.gemm_nt(dhm, W[k + ".wo_t"], do, self._ep(drop_bits=db), a2=dto, w2=W[k + ".A_out_proj_t"], k2=r)
+                self._lora_da_fix(g("o"), dto, do if db is None else None, W[k + ".A_out_proj_t"], i, ("out_proj",))
             else:
                 ops.gemm_nt(dhm, W[k + ".wo_t"], do, self._ep())
             # attention

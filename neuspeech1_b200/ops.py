@@ -77,9 +77,11 @@ def _p(t: Optional[torch.Tensor]):
 
 
 def epilogue(bias=None, alpha=1.0, alpha_cols=0, act=ACT_NONE, aux_in=None, aux_out=None, ldaux=0, residual=None, ldr=0,
-             res_mod=0, out_dtype=NS_BF16, a2_group_cols=0) -> Epilogue:
+             res_mod=0, out_dtype=NS_BF16, a2_group_cols=0, drop_bits=None) -> Epilogue:
+    """drop_bits: ONE adapter's (rows, words) plane of dropout_bits -- the second product is masked with it (input gradient of a
+    LoRA branch under dropout, see include/neuspeech_b200.h ns_epilogue::drop_bits)."""
     return Epilogue(_p(bias), alpha, alpha_cols, act, _p(aux_in), _p(aux_out), ldaux, _p(residual), ldr, res_mod,
-                    out_dtype, a2_group_cols)
+                    out_dtype, a2_group_cols, _p(drop_bits), drop_bits.stride(0) if drop_bits is not None else 0)
 
 
 def gemm_nt(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, ep: Optional[Epilogue] = None, a2=None, w2=None,
@@ -275,7 +277,7 @@ def dropout_bits_words(rows: int, cols: int) -> int:
 
 
 def dropout_bits(rows: int, cols: int, seed, salts, p: float, bits):
-    """bits (G, (rows+1)//2, (cols+15)//16) int32 <- the dropped-element bit plane of the G modules `salts` (hashed once per step)."""
+    """bits (G, rows, (cols+31)//32) int32 <- the dropped-element bit plane of the G modules `salts` (hashed once per step)."""
     _call("ns_dropout_bits", (0, float(bits.numel() * 4)), rows, cols, len(salts), _p(seed), _salts(salts), float(p), _p(bits), _stream())
     return bits
 

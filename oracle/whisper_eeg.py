@@ -190,17 +190,17 @@ def module_salt(name: str) -> int:
 
 def lora_dropout_plane(seed: int, name: str, rows: int, cols: int, p: float):
     """The dropped-element bit plane of module `name` as the device draws it (include/neuspeech_b200.h, csrc/ns_lora.cu):
-    uint32 array ((rows+1)//2, (cols+15)//16); bit 2*(col % 16) + (row & 1) of word (row >> 1, col // 16) set <=> dropped.
-    The 32 flags of a word come from 16 hashed words R_i = mix1(km + (i + 1) * 0xC2B2AE35), km = lowbias32((rp * 0x9E3779B1) ^
+    uint32 array (rows, (cols+31)//32); bit (col % 32) of word (row, col // 32) set <=> dropped.
+    The 32 flags of a word come from 16 hashed words R_i = mix1(km + (i + 1) * 0xC2B2AE35), km = lowbias32((row * 0x9E3779B1) ^
     (w * 0x85EBCA77) ^ seed ^ crc32(name)), mix1(x): x ^= x >> 16; x *= 0x7FEB352D; x ^= x >> 15 (all mod 2^32), combined along
     the binary expansion of thr = round(p * 65536), least significant bit first:
     D = bit_i(thr) ? (D | R_i) : (D & R_i), i.e. flag_b = [U_b < thr] for the 16-bit number U_b made of bit b of R_15..R_0."""
     import numpy as np
     m = np.uint64(0xFFFFFFFF)
     ms = np.uint64((seed ^ module_salt(name)) & 0xFFFFFFFF)
-    rp = np.arange((rows + 1) // 2, dtype=np.uint64)[:, None]
-    w = np.arange((cols + 15) // 16, dtype=np.uint64)[None, :]
-    km = lowbias32(((rp * np.uint64(0x9E3779B1)) ^ (w * np.uint64(0x85EBCA77)) ^ ms) & m)
+    row = np.arange(rows, dtype=np.uint64)[:, None]
+    w = np.arange((cols + 31) // 32, dtype=np.uint64)[None, :]
+    km = lowbias32(((row * np.uint64(0x9E3779B1)) ^ (w * np.uint64(0x85EBCA77)) ^ ms) & m)
     thr = min(65535, int(p * 65536.0 + 0.5))
     d = np.zeros(km.shape, dtype=np.uint64)
     for i in range(16):
@@ -208,8 +208,8 @@ def lora_dropout_plane(seed: int, name: str, rows: int, cols: int, p: float):
         x ^= x >> np.uint64(16); x = (x * np.uint64(0x7FEB352D)) & m
         x ^= x >> np.uint64(15)
         d = (d | x) if (thr >> i) & 1 else (d & x)
-    valid = np.clip(cols - 16 * np.arange(d.shape[1]), 0, 16)                # columns that exist in each 16-column block
-    d &= ((np.uint64(1) << (2 * valid).astype(np.uint64)) - np.uint64(1))[None, :]
+    valid = np.clip(cols - 32 * np.arange(d.shape[1]), 0, 32)                # columns that exist in each 32-column block
+    d &= ((np.uint64(1) << valid.astype(np.uint64)) - np.uint64(1))[None, :]
     return d.astype(np.uint32)
 
 
@@ -219,11 +219,9 @@ def lora_dropout_keep(seed: int, name: str, rows: int, cols: int, p: float) -> T
     / 65536.  PEFT itself draws from torch's generator, so with dropout on, parity with the reference is statistical by
     construction; between this oracle and the CUDA path it is exact."""
     import numpy as np
-    plane = lora_dropout_plane(seed, name, rows, cols, p).astype(np.uint64)                 # (pairs, words)
-    sh = (2 * np.arange(16, dtype=np.uint64))[None, None, :]
-    two = (plane[:, :, None] >> sh) & np.uint64(3)                                           # (pairs, words, 16): bit0 even row, bit1 odd row
-    two = two.reshape(plane.shape[0], -1)[:, :cols]
-    dropped = np.stack([two & np.uint64(1), two >> np.uint64(1)], axis=1).reshape(-1, two.shape[1])[:rows]
+    plane = lora_dropout_plane(seed, name, rows, cols, p).astype(np.uint64)                 # (rows, words)
+    sh = np.arange(32, dtype=np.uint64)[None, None, :]
+    dropped = ((plane[:, :, None] >> sh) & np.uint64(1)).reshape(rows, -1)[:, :cols]
     return torch.from_numpy(dropped == 0)
 
 

@@ -138,6 +138,51 @@ def test_gemm_nt_lora_grouped(dtype, r):
     assert bool((out2[:, :d] == 0).all())
 
 
+@pytest.mark.parametrize("M,N,K,dgelu", [(300, 512, 512, False), (777, 2048, 512, True), (20000, 512, 2048, False), (19077, 2048, 512, True),
+                                         (129, 64, 128, False)])
+def test_gemm_nt_masked_second_product(M, N, K, dgelu):
+    """Input gradient of a LoRA-adapted linear under branch dropout, one launch: D = act'( g W + keep . (dt A) ).  The LoRA
+    product gets its own TMEM accumulator and is masked in the epilogue with the oracle's keep mask (ns_epilogue.drop_bits);
+    single-CTA and CTA-pair (M = 256 MMAs, odd row-tile count) sizes, plain and dGELU epilogues."""
+    from oracle import whisper_eeg as O
+    r, seed, p, name = 32, 31337, 0.05, "model.encoder.layers.4.fc2"
+    g = rnd(M, K, dtype=torch.bfloat16, seed=1); w = rnd(N, K, dtype=torch.bfloat16, scale=K ** -0.5, seed=2)
+    dt = rnd(M, r, dtype=torch.bfloat16, scale=0.5, seed=3); At = rnd(N, r, dtype=torch.bfloat16, scale=0.3, seed=4)
+    bits = _plane(seed, [name], M, N, p)
+    keep = _keep(seed, name, M, N, p).float()
+    ref = g.float() @ w.float().t() + keep * (dt.float() @ At.float().t())
+    kw = {}
+    if dgelu:
+        z = rnd(M, N, dtype=torch.bfloat16, seed=5)
+        kw.update(act=_abi.ACT_DGELU, aux_in=z, ldaux=N); ref = ref * gelu_grad(z.float())
+    out = torch.full((M, N), 7.0, dtype=torch.bfloat16, device=DEV)
+    _abi.reset_counters()
+    ops.gemm_nt(g, w, out, ops.epilogue(drop_bits=bits[0], **kw), a2=dt, w2=At, k2=r)
+    assert _abi.counters()["gemm_tcgen05"] == 1
+    assert rel(out.float(), ref) < tol(torch.bfloat16), rel(out.float(), ref)
+    # the dropped positions carry the base product alone: compare them on their own (5 % of the elements)
+    sel = keep == 0
+    base = g.float() @ w.float().t()
+    if dgelu:
+        base = base * gelu_grad(z.float())
+    assert rel(out.float()[sel], base[sel]) < tol(torch.bfloat16)
+    # unmasked call = the plain K-segment kernel
+    out2 = torch.empty_like(out)
+    ops.gemm_nt(g, w, out2, ops.epilogue(**kw), a2=dt, w2=At, k2=r)
+    assert rel(out2.float()[~sel], out.float()[~sel]) < 1e-2
+
+
+def test_gemm_nt_masked_second_product_refuses_what_it_cannot_do():
+    M, N, K, r = 256, 512, 256, 32
+    bits = torch.zeros(1, M, N // 32, dtype=torch.int32, device=DEV)
+    g32 = rnd(M, K, seed=1); w32 = rnd(N, K, seed=2); dt32 = rnd(M, r, seed=3); At32 = rnd(N, r, seed=4)
+    with pytest.raises(_abi.NeuSpeechB200Error):            # fp32 storage has no tcgen05 path: never silently unmasked
+        ops.gemm_nt(g32, w32, torch.empty(M, N, device=DEV), ops.epilogue(drop_bits=bits[0], out_dtype=_abi.NS_F32), a2=dt32, w2=At32, k2=r)
+    b = lambda t: t.to(torch.bfloat16)
+    with pytest.raises(_abi.NeuSpeechB200Error):            # no second product to mask
+        ops.gemm_nt(b(g32), b(w32), torch.empty(M, N, dtype=torch.bfloat16, device=DEV), ops.epilogue(drop_bits=bits[0]))
+
+
 def test_gemm_nt_simt_equals_fast():
     M, N, K = 500, 768, 512
     a = rnd(M, K, dtype=torch.bfloat16, seed=1); w = rnd(N, K, dtype=torch.bfloat16, scale=K ** -0.5, seed=2)
@@ -545,9 +590,9 @@ def _seed_tensor(seed):
 
 
 def _plane(seed, names, rows, cols, p):
-    """Device bit planes (G, pairs, words) of the modules `names`."""
+    """Device bit planes (G, rows, words) of the modules `names`."""
     from oracle import whisper_eeg as O
-    bits = torch.empty(len(names), (rows + 1) // 2, (cols + 15) // 16, dtype=torch.int32, device=DEV)
+    bits = torch.empty(len(names), rows, (cols + 31) // 32, dtype=torch.int32, device=DEV)
     assert bits[0].numel() == ops.dropout_bits_words(rows, cols)
     ops.dropout_bits(rows, cols, _seed_tensor(seed), [O.module_salt(n) for n in names], p, bits)
     return bits
@@ -556,7 +601,7 @@ def _plane(seed, names, rows, cols, p):
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 def test_dropout_mask_bit_exact_and_seed_sequence(dtype):
     """ns_dropout_bits == oracle.lora_dropout_plane word for word, ns_dropout_apply == oracle.lora_dropout_keep element for
-    element (odd row count, column count that is no multiple of 16, ragged leading dimension), and ns_seed_advance follows
+    element (odd row count, column count that is no multiple of 32, ragged leading dimension), and ns_seed_advance follows
     oracle.next_dropout_seed."""
     from oracle import whisper_eeg as O
     rows, cols, p = 1501, 520, 0.05

@@ -40,7 +40,7 @@ def once():
         dA = torch.zeros(G * r, K, dtype=torch.float32, device=DEV)
         dx = torch.randn(M, K, device=DEV).to(torch.bfloat16)
         salts = [11, 22, 33][:G]
-        bits = torch.empty(G, M // 2, K // 16, dtype=torch.int32, device=DEV)
+        bits = torch.empty(G, M, K // 32, dtype=torch.int32, device=DEV)
         ops.dropout_bits(M, K, seed, salts, 0.05, bits)
         ops.lora_down(x, A, t, 2.0, G)
         ops.lora_down(x, A, t, 2.0, G, bits)
@@ -66,7 +66,7 @@ def main():
         dx = torch.randn(M, K, device=DEV).to(torch.bfloat16)
         z = torch.randn(M, K, device=DEV).to(torch.bfloat16)
         salts = [11, 22, 33][:G]
-        bits = torch.empty(G, M // 2, K // 16, dtype=torch.int32, device=DEV)
+        bits = torch.empty(G, M, K // 32, dtype=torch.int32, device=DEV)
         ops.dropout_bits(M, K, seed, salts, 0.05, bits)
         key = f"K{K}_G{G}"
         out[key] = {
