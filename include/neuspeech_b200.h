@@ -68,6 +68,12 @@ typedef struct {
                                  plane of ns_dropout_bits).  The second product gets its own TMEM accumulator and is masked in
                                  the epilogue before the sum.  bf16 tcgen05 path only (N % 64 == 0); else NS_ERR_UNSUPPORTED. */
   long long    drop_ld;       /* words per row of drop_bits */
+  int          drop_mode;     /* 0: mask the second product (above).  1: mask the A OPERAND of the (single) product -- the LoRA
+                                 down product t = alpha * (x . keep_g) * A_g^T under branch dropout (finetune.py:210): adapter g
+                                 owns output columns [32 g, 32 g + 32) (rank 32) and the plane at drop_bits + g * drop_gstride;
+                                 the elements are zeroed in shared memory between the TMA and the MMA (bf16 tcgen05 path only,
+                                 N % 32 == 0, K % 64 == 0) */
+  long long    drop_gstride;  /* words between the planes of stacked adapters (drop_mode 1) */
 } ns_epilogue;
 
 int ns_gemm_nt(int dtype, long long M, int N, int K, const void* A, long long lda, const void* W, long long ldw,
@@ -78,6 +84,13 @@ int ns_gemm_nt(int dtype, long long M, int N, int K, const void* A, long long ld
  * Replaces autograd's wgrad of the LoRA A/B linears (PEFT) : dB = s*dy^T t, dA = dt^T x. */
 int ns_gemm_tn(int dtype, long long M, int I, int J, const void* X, long long ldx, const void* Y, long long ldy,
                float* G, long long si, long long sj, float alpha, void* stream);
+
+/* Same with X masked by a dropout plane (ns_dropout_bits, one adapter) on its way to the tensor cores:
+ *   G += alpha * (X . keep)^T Y  --  dA = dt'^T (x . keep) of a LoRA branch under dropout, x read once.  bf16 tcgen05 path only
+ *   (I % 64 == 0, xbits_ld even); NS_ERR_UNSUPPORTED otherwise. */
+int ns_gemm_tn_masked(int dtype, long long M, int I, int J, const void* X, long long ldx, const void* Y, long long ldy,
+                      float* G, long long si, long long sj, float alpha, const unsigned int* xbits, long long xbits_ld,
+                      void* stream);
 
 /* ---- stem convolution (kernel 3, pad 1, stride 1|2) on channels-last activations, as an implicit GEMM.
  * Replaces nn.Conv1d + GELU at utils/model_utils.py:12-16 and utils/load_model.py:410-411 (+ the permute and

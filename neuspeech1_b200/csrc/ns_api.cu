@@ -138,6 +138,19 @@ int ns_gemm_tn(int dtype, long long M, int I, int J, const void* X, long long ld
   return launch_tn_simt(dtype, p, st);
 }
 
+int ns_gemm_tn_masked(int dtype, long long M, int I, int J, const void* X, long long ldx, const void* Y, long long ldy, float* G,
+                      long long si, long long sj, float alpha, const unsigned int* xbits, long long xbits_ld, void* stream) {
+  NS_CHECK_ARG(valid_dtype(dtype), "ns_gemm_tn_masked: bad dtype %d", dtype);
+  NS_CHECK_ARG(M >= 0 && I > 0 && J > 0 && X && Y && G && xbits, "ns_gemm_tn_masked: bad shape/pointers");
+  if (M == 0) return NS_OK;
+  if (!want_fast(dtype)) {
+    set_error("ns_gemm_tn_masked: bf16 storage and the tcgen05 path only");
+    return NS_ERR_UNSUPPORTED;
+  }
+  set_error("ns_gemm_tn_masked: operands do not qualify for the tcgen05 path (alignment / sizes)");
+  return gemm_tn_fast(M, I, J, X, ldx, Y, ldy, G, si, sj, alpha, reinterpret_cast<cudaStream_t>(stream), xbits, xbits_ld);
+}
+
 int ns_conv3_fwd(int dtype, int B, int Tin, int Cp, int N, int stride, const void* x, const void* w, void* y,
                  const ns_epilogue* ep, void* stream) {
   NS_CHECK_ARG(valid_dtype(dtype), "ns_conv3_fwd: bad dtype");

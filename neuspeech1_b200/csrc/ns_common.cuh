@@ -147,8 +147,10 @@ struct EpiDev {
   long long ldr;
   int res_mod;
   int out_f32;   // 1: D is fp32
-  const uint32_t* drop_bits;   // masked second product (see ns_epilogue::drop_bits)
+  const uint32_t* drop_bits;   // masked second product / masked A operand (see ns_epilogue::drop_bits, drop_mode)
   long long drop_ld;
+  int drop_mode;
+  long long drop_gstride;
 };
 
 inline EpiDev make_epi(const ns_epilogue* ep, int dtype) {
@@ -161,7 +163,7 @@ inline EpiDev make_epi(const ns_epilogue* ep, int dtype) {
     e.aux_in = ep->aux_in; e.aux_out = ep->aux_out; e.ldaux = ep->ldaux;
     e.residual = ep->residual; e.ldr = ep->ldr; e.res_mod = ep->res_mod;
     e.out_f32 = (ep->out_dtype == NS_F32);
-    e.drop_bits = ep->drop_bits; e.drop_ld = ep->drop_ld;
+    e.drop_bits = ep->drop_bits; e.drop_ld = ep->drop_ld; e.drop_mode = ep->drop_mode; e.drop_gstride = ep->drop_gstride;
   }
   return e;
 }

@@ -46,7 +46,7 @@ int conv3_fwd_fast(int B, int Tin, int Cp, int N, int stride, const void* x, con
 int conv3_dgrad_fast(int B, int Tin, int Cp, int N, int stride, const void* dz, const void* wt, void* dx,
                      const EpiDev& epi, cudaStream_t st);
 int gemm_tn_fast(long long M, int I, int J, const void* X, long long ldx, const void* Y, long long ldy, float* G,
-                 long long si, long long sj, float alpha, cudaStream_t st);
+                 long long si, long long sj, float alpha, cudaStream_t st, const uint32_t* xbits = nullptr, long long xbits_ld = 0);
 int conv3_wgrad_fast(int B, int Tin, int Cp, int N, int stride, const void* dz, const void* x, float* dw, cudaStream_t st);
 
 int launch_nt_simt(int dtype, const SimtProg& p, cudaStream_t st);

@@ -140,6 +140,9 @@ struct TileProg {
   int staging_tiles;  // 0, 2 (one output tile per column half) or 4 (+ one aux-output or input tile per half)
   int epi_mode;     // which compiled copy of the epilogue loop runs (see gemm_nt_kernel)
   FastDiv fd_units, fd_ntiles, fd_tpb;   // m_units (row tiles, or row-tile pairs with CG = 2), n_tiles, tiles_per_batch
+  // AM (A-operand mask, the LoRA down product under branch dropout): plane of adapter g = n_tile starts at am_bits + g * am_gstride
+  const uint32_t* am_bits;
+  long long am_ld, am_gstride;
 };
 
 struct Maps {
@@ -234,10 +237,22 @@ __device__ __forceinline__ void store32_f32(float* p, bool vec, int ncols, const
 #else
 #define NS_EPI_TRACE(tag) do { } while (0)
 #endif
-template <int BN, int CG, int PM>
+// AND-mask for a packed bf16 pair from two drop flags (bit 0 of each argument): 0 where dropped
+__device__ __forceinline__ uint32_t keep_pair(uint32_t drop_lo, uint32_t drop_hi) {
+  return ~(((drop_lo & 1u) | ((drop_hi & 1u) << 16)) * 0xFFFFu);
+}
+// AM = 1 ("A-operand mask", BN = 32 only): t = alpha (x . keep_g) A_g^T, the LoRA down product under branch dropout.  The
+// 32-wide kernel's second epilogue warpgroup (warps 8..11, idle at this width) becomes a MASK STAGE between the TMA and the
+// MMA: thread = one row of the 128 x 64 A tile; it waits for the tile, zeroes the dropped elements of its 128-byte swizzled row
+// in place (flags from the row-major bit plane: one 8-byte load per row and k block, fetched two blocks ahead; 16-byte chunks
+// without a dropped element are not touched: two thirds of them at p = 0.05), fences the generic writes for the async proxy
+// and arrives on the barrier the MMA issuer waits on.  Stacked adapters (q/k/v) are consecutive column tiles: tile g masks the
+// same x tile (an L2 hit) with plane g.
+template <int BN, int CG, int PM, int AM>
 __global__ void __launch_bounds__(kNtThreads, 1)
 gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TileProg p) {
   using Cfg = NtCfg<BN, CG, PM>;
+  static_assert(!AM || (BN == 32 && CG == 1 && !PM), "the mask stage lives in the 32-wide single-CTA kernel");
   const int S = p.stages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);      // 128B-swizzled tiles need 1 KB alignment: no static shared memory here,
@@ -250,6 +265,8 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
   auto in_full = [&](int w) { return bar_base + 8u * (2 * S + 5 + w); };    // one per epilogue warp (8)
+  auto mfull_bar = [&](int s) { return in_full(s); };                       // AM: "tile masked" per ring stage (the TMA-staged
+                                                                            // epilogue inputs do not exist at BN = 32)
   const uint32_t bias_base = bar_base + 256u;         // [tile parity][column half][128] floats
   const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
@@ -300,9 +317,9 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8 * CG);   // one arrive per epilogue warp (of both CTAs)
+      mbar_init(tempty_bar(a), AM ? 4 : 8 * CG);   // one arrive per epilogue warp (of both CTAs)
     }
-    for (int w = 0; w < 8; ++w) mbar_init(in_full(w), 1);
+    for (int w = 0; w < 8; ++w) mbar_init(in_full(w), AM ? 4 : 1);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -374,7 +391,7 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
         const uint32_t d_tmem = d_main + (to_p ? static_cast<uint32_t>(2 * BN) : 0u);
         uint32_t accumulate = to_p ? acc_p : acc_main;
         for (int kb = 0; kb < sg.kblocks; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+          mbar_wait(AM ? mfull_bar(stage) : full_bar(stage), phase);
           if (lane == 0) trace(1, 200 + stage);
           tc_fence_after();
           if (elect_one()) {
@@ -405,6 +422,51 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
     }
   } else if (warp < 4) {
     setmaxnreg_dec<40>();
+  } else if (AM && warp >= 8) {
+    // ================================================================ mask stage (AM)
+    setmaxnreg_inc<232>();
+    const int r = (warp - 8) * 32 + lane;                // row of the A tile
+    const uint32_t sw = static_cast<uint32_t>(r & 7);
+    const int nkb = p.seg[0].kblocks;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+      int m_tile, n_tile;
+      decode(tile, m_tile, n_tile);
+      const int b = p.fd_tpb.div(m_tile);
+      const int t = (m_tile - b * p.tiles_per_batch) * kBM + r;
+      const bool valid = t < p.tout;                     // rows past the end arrive zero-filled
+      const uint2* brow = reinterpret_cast<const uint2*>(p.am_bits + static_cast<long long>(n_tile) * p.am_gstride +
+                                                         (static_cast<long long>(b) * p.tout + (valid ? t : 0)) * p.am_ld);
+      const uint2 none = make_uint2(0u, 0u);
+      uint2 w0 = (valid && nkb > 0) ? __ldg(brow) : none;
+      uint2 w1 = (valid && nkb > 1) ? __ldg(brow + 1) : none;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const uint2 wc = w0;
+        w0 = w1;
+        w1 = (valid && kb + 2 < nkb) ? __ldg(brow + kb + 2) : none;
+        mbar_wait(full_bar(stage), phase);
+        const uint32_t row_addr = smem_base + stage * Cfg::kStageBytes + static_cast<uint32_t>(r) * 128u;
+        if (wc.x | wc.y) {
+#pragma unroll
+          for (int pp = 0; pp < 8; ++pp) {
+            const uint32_t c = static_cast<uint32_t>(pp) ^ sw;                 // logical 8-column chunk stored at position pp
+            const uint32_t m8 = ((c < 4 ? wc.x : wc.y) >> (8 * (c & 3))) & 0xFFu;
+            if (m8) {
+              uint32_t x0, x1, x2, x3;
+              ld_shared_v4(row_addr + 16u * pp, x0, x1, x2, x3);
+              x0 &= keep_pair(m8, m8 >> 1); x1 &= keep_pair(m8 >> 2, m8 >> 3);
+              x2 &= keep_pair(m8 >> 4, m8 >> 5); x3 &= keep_pair(m8 >> 6, m8 >> 7);
+              st_shared_v4(row_addr + 16u * pp, x0, x1, x2, x3);
+            }
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(mfull_bar(stage));
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+    }
   } else {
     // ================================================================ epilogue
     setmaxnreg_inc<232>();
@@ -788,6 +850,8 @@ struct TnProg {
   int icta;                   // 128-row output tiles per CTA (1..4): with a narrow Y (J <= 64) one CTA streams up to 512
                               // contiguous X columns per contraction row and keeps icta accumulators (icta * bj TMEM columns)
   int stages;                 // operand ring depth
+  const uint32_t* xbits;      // != NULL: X is masked with this row-major dropout plane on its way to the MMA (dA = dt'^T (x . keep))
+  long long xbits_ld;
 };
 struct TnMaps {
   CUtensorMap x;
@@ -808,6 +872,8 @@ gemm_tn_kernel(const __grid_constant__ TnMaps maps, const __grid_constant__ TnPr
   auto empty_bar = [&](int s) { return bar_base + 8u * (kTnMaxStages + s); };
   const uint32_t tfull_bar = bar_base + 8u * (2 * kTnMaxStages);
   const uint32_t tmem_slot = bar_base + 8u * (2 * kTnMaxStages + 1);
+  auto mfull_bar = [&](int s) { return bar_base + 8u * (2 * kTnMaxStages + 2 + s); };   // X tile masked (xbits)
+  const bool masked = p.xbits != nullptr;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
@@ -832,6 +898,7 @@ gemm_tn_kernel(const __grid_constant__ TnMaps maps, const __grid_constant__ TnPr
     for (int s = 0; s < S; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
+      mbar_init(mfull_bar(s), 4);
     }
     mbar_init(tfull_bar, 1);
     mbar_fence_init();
@@ -869,7 +936,7 @@ gemm_tn_kernel(const __grid_constant__ TnMaps maps, const __grid_constant__ TnPr
     uint32_t phase = 0;
     uint32_t accumulate = 0;
     for (int blk = blk0; blk < blk1; ++blk) {
-      mbar_wait(full_bar(stage), phase);
+      mbar_wait(masked ? mfull_bar(stage) : full_bar(stage), phase);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sa = smem_base + stage * p.stage_bytes;
@@ -893,6 +960,59 @@ gemm_tn_kernel(const __grid_constant__ TnMaps maps, const __grid_constant__ TnPr
     __syncwarp();
   } else if (warp >= 4) {
     const int q = warp & 3;
+    if (masked) {
+      // Mask stage: the epilogue warps have nothing to do until the last block.  X boxes are [64 contraction rows][64 columns]
+      // (128-byte swizzled rows); thread = (row, box parity), icta boxes each, one 8-byte flag load per box, fetched a block ahead.
+      const int tid = (warp - 4) * 32 + lane;
+      const int row = tid & 63, bpar = tid >> 6;
+      const uint32_t sw = static_cast<uint32_t>(row & 7);
+      const uint2 none = make_uint2(0u, 0u);
+      auto fetch = [&](int blk, uint2 (&w)[4]) {
+        const int b = blk / p.blocks_per_batch;
+        const int t = (blk % p.blocks_per_batch) * 64 + row;
+        const bool ok = blk < blk1 && t < p.tout;
+        const uint32_t* br = p.xbits + (static_cast<long long>(b) * p.tout + (ok ? t : 0)) * p.xbits_ld;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int col = i0 + 64 * (2 * g + bpar);
+          w[g] = (ok && g < p.icta && col < p.I) ? __ldg(reinterpret_cast<const uint2*>(br + (col >> 5))) : none;
+        }
+      };
+      uint2 wn[4];
+      fetch(blk0, wn);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int blk = blk0; blk < blk1; ++blk) {
+        uint2 wc[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) wc[g] = wn[g];
+        fetch(blk + 1, wn);
+        mbar_wait(full_bar(stage), phase);
+        const uint32_t sa = smem_base + stage * p.stage_bytes;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (g < p.icta && (wc[g].x | wc[g].y)) {
+            const uint32_t row_addr = sa + 8192u * (2 * g + bpar) + static_cast<uint32_t>(row) * 128u;
+#pragma unroll
+            for (int pp = 0; pp < 8; ++pp) {
+              const uint32_t c = static_cast<uint32_t>(pp) ^ sw;
+              const uint32_t m8 = ((c < 4 ? wc[g].x : wc[g].y) >> (8 * (c & 3))) & 0xFFu;
+              if (m8) {
+                uint32_t x0, x1, x2, x3;
+                ld_shared_v4(row_addr + 16u * pp, x0, x1, x2, x3);
+                x0 &= keep_pair(m8, m8 >> 1); x1 &= keep_pair(m8 >> 2, m8 >> 3);
+                x2 &= keep_pair(m8 >> 4, m8 >> 5); x3 &= keep_pair(m8 >> 6, m8 >> 7);
+                st_shared_v4(row_addr + 16u * pp, x0, x1, x2, x3);
+              }
+            }
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(mfull_bar(stage));
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+    }
     if (nblk > 0) {
       mbar_wait(tfull_bar, 0);
       tc_fence_after();
@@ -939,12 +1059,12 @@ gemm_tn_kernel(const __grid_constant__ TnMaps maps, const __grid_constant__ TnPr
 // ------------------------------------------------------------------------------------------------ host launchers
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <int BN, int CG, int PM = 0>
+template <int BN, int CG, int PM = 0, int AM = 0>
 static int launch_nt(const Maps& maps, TileProg& prog, cudaStream_t st) {
   using Cfg = NtCfg<BN, CG, PM>;
   static bool attr_done = false;
   if (!attr_done) {
-    NS_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<BN, CG, PM>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kMaxSmem));
+    NS_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<BN, CG, PM, AM>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kMaxSmem));
     attr_done = true;
   }
   prog.n_tiles = (prog.N + BN - 1) / BN;
@@ -989,7 +1109,7 @@ static int launch_nt(const Maps& maps, TileProg& prog, cudaStream_t st) {
     set_error("ns_gemm_nt: the dropout-masked second product supports plain and NS_ACT_DGELU epilogues with bf16 TMA tiles only");
     return NS_ERR_UNSUPPORTED;
   }
-  NS_CUDA(cudaLaunchKernelEx(&cfg, gemm_nt_kernel<BN, CG, PM>, maps, prog));
+  NS_CUDA(cudaLaunchKernelEx(&cfg, gemm_nt_kernel<BN, CG, PM, AM>, maps, prog));
   NS_LAUNCH_CHECK();
   count(C_GEMM_TC);
   return NS_OK;
@@ -1013,6 +1133,7 @@ static int choose_cg(long long m_tiles, int N, int bn) {
 }
 
 static int dispatch_nt(const Maps& maps, TileProg& prog, cudaStream_t st, int bn, int cg) {
+  if (prog.am_bits) return launch_nt<32, 1, 0, 1>(maps, prog, st);
   if (prog.epi.drop_bits) return cg == 2 ? launch_nt<128, 2, 1>(maps, prog, st) : launch_nt<128, 1, 1>(maps, prog, st);
   if (bn == 256) return cg == 2 ? launch_nt<256, 2>(maps, prog, st) : launch_nt<256, 1>(maps, prog, st);
   if (bn == 128) return launch_nt<128, 1>(maps, prog, st);
@@ -1099,7 +1220,16 @@ int gemm_nt_fast(long long M, int N, int K, const void* A, long long lda, const 
   memset(&prog, 0, sizeof(prog));
   int bn = choose_bn((M + kBM - 1) / kBM, N);
   int cg = choose_cg((M + kBM - 1) / kBM, N, bn);
-  if (epi.drop_bits) {
+  const bool am = epi.drop_bits && epi.drop_mode == 1;
+  if (am) {
+    // A-operand mask (LoRA down product): 32-wide tiles, one adapter per column tile
+    if (A2 || N % 32 != 0 || K % 64 != 0 || epi.drop_ld % 2 != 0 || (reinterpret_cast<uintptr_t>(epi.drop_bits) & 7) != 0 ||
+        (N > 32 && epi.drop_gstride % 2 != 0)) {
+      set_error("ns_gemm_nt: the dropout-masked A operand needs a single product, N %% 32 == 0 (rank-32 adapters), K %% 64 == 0, even drop_ld");
+      return NS_ERR_UNSUPPORTED;
+    }
+    bn = 32; cg = 1;
+  } else if (epi.drop_bits) {
     // masked second product: 128-wide tiles (TMEM holds main + product tiles twice), CTA pairs whenever there is work for them
     if (!A2 || a2_ngrp > 0 || N % 64 != 0 || epi.drop_ld % 2 != 0 || epi.out_f32 || epi.residual || epi.act == NS_ACT_GELU ||
         (reinterpret_cast<uintptr_t>(epi.drop_bits) & 7) != 0) {
@@ -1155,6 +1285,10 @@ int gemm_nt_fast(long long M, int N, int K, const void* A, long long lda, const 
   prog.ldd = ldd;
   prog.D = D;
   fill_epi(prog, epi);
+  if (am) {
+    prog.am_bits = epi.drop_bits; prog.am_ld = epi.drop_ld; prog.am_gstride = epi.drop_gstride;
+    prog.epi.drop_bits = nullptr;
+  }
   if (int r = setup_out_maps(maps, prog, bn)) return r;
   return dispatch_nt(maps, prog, st, bn, cg);
 }
@@ -1299,12 +1433,16 @@ static int launch_tn(const TnMaps& maps, TnProg& p, cudaStream_t st) {
 }
 
 int gemm_tn_fast(long long M, int I, int J, const void* X, long long ldx, const void* Y, long long ldy, float* G,
-                 long long si, long long sj, float alpha, cudaStream_t st) {
+                 long long si, long long sj, float alpha, cudaStream_t st, const uint32_t* xbits, long long xbits_ld) {
   if (ldx % 8 != 0 || ldy % 8 != 0 || !aligned16(X) || !aligned16(Y) || M > 0x7fffffffLL) return NS_ERR_UNSUPPORTED;
   if (I % 8 != 0 || J % 8 != 0) return NS_ERR_UNSUPPORTED;
+  if (xbits && (I % 64 != 0 || xbits_ld % 2 != 0 || (reinterpret_cast<uintptr_t>(xbits) & 7) != 0)) {
+    set_error("ns_gemm_tn_masked: I must be a multiple of 64, xbits_ld even, xbits 8-byte aligned");
+    return NS_ERR_UNSUPPORTED;
+  }
   // G^T = Y^T X is the same sum: put the WIDE operand on the X side (rows of the MMA, several row tiles per CTA) and the
   // LoRA-rank-wide one on the Y side
-  if (I <= 64 && J >= 128) {
+  if (!xbits && I <= 64 && J >= 128) {
     std::swap(I, J); std::swap(X, Y); std::swap(ldx, ldy); std::swap(si, sj);
   }
   TnMaps maps;
@@ -1321,6 +1459,7 @@ int gemm_tn_fast(long long M, int I, int J, const void* X, long long ldx, const 
   memset(&p, 0, sizeof(p));
   p.batches = 1; p.tout = static_cast<int>(M); p.ntaps = 1;
   p.I = I; p.J = J; p.si = si; p.sj = sj; p.stap = 0; p.G = G; p.alpha = alpha;
+  p.xbits = xbits; p.xbits_ld = xbits_ld;
   return launch_tn(maps, p, st);
 }
 

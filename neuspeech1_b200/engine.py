@@ -27,6 +27,7 @@ from . import ops
 from ._abi import ACT_DGELU, ACT_GELU, ACT_NONE, NS_BF16, NS_F32
 
 _NO_TRAIN_GRAPH = bool(os.environ.get("NS_NO_TRAIN_GRAPH"))     # developer switch: launch every kernel of train_step one by one
+_NO_MASK_STAGE = bool(os.environ.get("NS_NO_MASK_STAGE"))       # developer A/B switch: mma.sync ns_lora_down / ns_lora_da instead of the mask stages
 _NO_GEMM_MASK = bool(os.environ.get("NS_NO_GEMM_MASK"))         # developer A/B switch: dropout correction pass instead of the masked GEMM product
 ENC_LORA_TARGETS = ("q_proj", "k_proj", "v_proj", "out_proj", "fc1", "fc2")
 
@@ -219,7 +220,10 @@ class WhisperEEGEngine:
             ops.gemm_nt(x, A, t, self._ep(alpha=a, alpha_cols=G * r))
             return
         bits = ops.dropout_bits(M, K, self.drop_seed, self._salts(layer, targets), p, self._bits(layer, targets, M, K))
-        if self._fast_lora(K, G):
+        if self.use_lora_kernels and r == 32 and K % 64 == 0 and not _NO_MASK_STAGE:
+            # the thin tcgen05 GEMM with a mask stage between TMA and MMA (one 32-column tile per adapter)
+            ops.gemm_nt(x, A, t, self._ep(alpha=a, alpha_cols=G * r, drop_a=bits))
+        elif self._fast_lora(K, G):
             ops.lora_down(x, A, t, a, G, bits)
         else:
             xm = self.ws.get(f"xm.{K}", x.shape, self.dtype)
@@ -249,7 +253,9 @@ class WhisperEEGEngine:
             ops.gemm_tn(x, dt, gA, 1, K)
             return
         bits = self._bits(layer, targets, M, K)
-        if self._fast_lora(K, G):
+        if dx is None and G == 1 and self.use_lora_kernels and K % 64 == 0 and not _NO_MASK_STAGE:
+            ops.gemm_tn_masked(x, dt, gA, 1, K, bits[0])          # split-K tcgen05 wgrad, x masked in shared memory
+        elif self._fast_lora(K, G):
             ops.lora_da(x, dt, gA, G, bits, dx=dx, At=At if dx is not None else None, z=z if dx is not None else None)
         else:
             xm = self.ws.get(f"xm.{K}", x.shape, self.dtype)
@@ -699,7 +705,9 @@ class WhisperEEGEngine:
                 dt1 = ws.get("dt_r", (M, r), dt)
                 ops.gemm_nt(dz1, W[k + ".B_fc1_t"], dt1, self._ep(alpha=s, alpha_cols=r))
                 ops.gemm_tn(dz1, g("t_1"), G("fc1", "B"), r, 1)
-                db = self._drop_plane(i, "fc1", M, d)
+                # (long contraction, narrow output: the 128-wide tiles of the masked product re-read dz1 from L2 twice as often
+                # and cost more than the correction pass saves -- measured 234 + 43 us against 154 + 83 us)
+                db = self._drop_plane(i, "fc1", M, d) if F <= d else None
                 ops.gemm_nt(dz1, W[k + ".w1_t"], du2, self._ep(drop_bits=db), a2=dt1, w2=W[k + ".A_fc1_t"], k2=r)
                 self._lora_da_fix(g("u2"), dt1, du2 if db is None else None, W[k + ".A_fc1_t"], i, ("fc1",))
             else:

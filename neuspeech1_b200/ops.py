@@ -77,11 +77,15 @@ def _p(t: Optional[torch.Tensor]):
 
 
 def epilogue(bias=None, alpha=1.0, alpha_cols=0, act=ACT_NONE, aux_in=None, aux_out=None, ldaux=0, residual=None, ldr=0,
-             res_mod=0, out_dtype=NS_BF16, a2_group_cols=0, drop_bits=None) -> Epilogue:
+             res_mod=0, out_dtype=NS_BF16, a2_group_cols=0, drop_bits=None, drop_a=None) -> Epilogue:
     """drop_bits: ONE adapter's (rows, words) plane of dropout_bits -- the second product is masked with it (input gradient of a
-    LoRA branch under dropout, see include/neuspeech_b200.h ns_epilogue::drop_bits)."""
+    LoRA branch under dropout).  drop_a: the (G, rows, words) planes of G stacked rank-32 adapters -- the A operand of the single
+    product is masked per 32-column output tile (the LoRA down product).  See include/neuspeech_b200.h ns_epilogue."""
+    if drop_a is not None:
+        return Epilogue(_p(bias), alpha, alpha_cols, act, _p(aux_in), _p(aux_out), ldaux, _p(residual), ldr, res_mod,
+                        out_dtype, a2_group_cols, _p(drop_a), drop_a.stride(1), 1, drop_a.stride(0))
     return Epilogue(_p(bias), alpha, alpha_cols, act, _p(aux_in), _p(aux_out), ldaux, _p(residual), ldr, res_mod,
-                    out_dtype, a2_group_cols, _p(drop_bits), drop_bits.stride(0) if drop_bits is not None else 0)
+                    out_dtype, a2_group_cols, _p(drop_bits), drop_bits.stride(0) if drop_bits is not None else 0, 0, 0)
 
 
 def gemm_nt(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, ep: Optional[Epilogue] = None, a2=None, w2=None,
@@ -265,6 +269,14 @@ def _salts(salts):
     return (C.c_uint * 3)(*([int(s) & 0xFFFFFFFF for s in salts] + [0] * (3 - len(salts))))
 
 
+def gemm_tn_masked(x: torch.Tensor, y: torch.Tensor, g: torch.Tensor, si: int, sj: int, xbits: torch.Tensor, alpha: float = 1.0):
+    """g[i*si + j*sj] += alpha * sum_m (x . keep)[m,i] * y[m,j]; xbits = ONE adapter's (rows, words) plane of dropout_bits."""
+    I, J = x.shape[1], y.shape[1]
+    _call("ns_gemm_tn_masked", (2.0 * x.shape[0] * I * J, 0), ns_dtype(x), x.shape[0], I, J, _p(x), x.stride(0), _p(y), y.stride(0),
+          _p(g), si, sj, float(alpha), _p(xbits), xbits.stride(0), _stream())
+    return g
+
+
 def dropout_apply(x, y, bits):
     """y = x with the dropped elements of one adapter's bit plane zeroed (unscaled); x, y 2-D views (rows, cols)."""
     _call("ns_dropout_apply", (0, 2.0 * x.numel() * x.element_size()), ns_dtype(x), x.shape[0], x.shape[1], _p(x), x.stride(0), _p(y),
@@ -273,7 +285,7 @@ def dropout_apply(x, y, bits):
 
 
 def dropout_bits_words(rows: int, cols: int) -> int:
-    return ((rows + 1) // 2) * ((cols + 15) // 16)
+    return int(lib().ns_dropout_bits_words(rows, cols))
 
 
 def dropout_bits(rows: int, cols: int, seed, salts, p: float, bits):

@@ -183,6 +183,33 @@ def test_gemm_nt_masked_second_product_refuses_what_it_cannot_do():
         ops.gemm_nt(b(g32), b(w32), torch.empty(M, N, dtype=torch.bfloat16, device=DEV), ops.epilogue(drop_bits=bits[0]))
 
 
+@pytest.mark.parametrize("M,K,G", [(3000, 512, 1), (3000, 512, 3), (1000, 2048, 1), (96001, 512, 3), (130, 64, 1), (20001, 1280, 3)])
+def test_mask_stage_down_and_da(M, K, G):
+    """The LoRA products under branch dropout on the tcgen05 kernels with a mask stage between TMA and MMA:
+    t = alpha (x . keep_g) A_g^T (ns_gemm_nt, ns_epilogue.drop_mode 1: one 32-column tile per stacked adapter) and
+    dA += dt^T (x . keep) (ns_gemm_tn_masked), against fp32 torch on the same bf16 operands and the oracle's keep mask."""
+    r, seed, p = 32, 2024, 0.05
+    names = [f"model.encoder.layers.5.self_attn.{n}" for n in ("q_proj", "k_proj", "v_proj")][:G]
+    x = rnd(M, K, dtype=torch.bfloat16, seed=2)
+    A = rnd(G * r, K, dtype=torch.bfloat16, scale=K ** -0.5, seed=3)
+    dt = rnd(M, G * r, dtype=torch.bfloat16, scale=0.1, seed=4)
+    bits = _plane(seed, names, M, K, p)
+    alpha = 2.0 / (1.0 - p)
+    t = torch.full((M, G * r), 9.0, dtype=torch.bfloat16, device=DEV)
+    _abi.reset_counters()
+    ops.gemm_nt(x, A, t, ops.epilogue(alpha=alpha, alpha_cols=G * r, drop_a=bits))
+    assert _abi.counters()["gemm_tcgen05"] == 1
+    for g in range(G):
+        xm = x.float() * _keep(seed, names[g], M, K, p).float()
+        t_ref = alpha * xm @ A[g * r:(g + 1) * r].float().t()
+        assert rel(t[:, g * r:(g + 1) * r].float(), t_ref) < 1e-2, (g, rel(t[:, g * r:(g + 1) * r].float(), t_ref))
+        dA = torch.full((r, K), 0.25, dtype=torch.float32, device=DEV)
+        ops.gemm_tn_masked(x, dt[:, g * r:(g + 1) * r], dA, 1, K, bits[g])
+        dA_ref = dt[:, g * r:(g + 1) * r].float().t() @ xm + 0.25
+        assert rel(dA, dA_ref) < 2e-3, (g, rel(dA, dA_ref))
+    assert torch.equal(x, rnd(M, K, dtype=torch.bfloat16, seed=2))            # the mask is applied in shared memory, never to x
+
+
 def test_gemm_nt_simt_equals_fast():
     M, N, K = 500, 768, 512
     a = rnd(M, K, dtype=torch.bfloat16, seed=1); w = rnd(N, K, dtype=torch.bfloat16, scale=K ** -0.5, seed=2)

@@ -74,7 +74,9 @@ def main():
             "gemm_nt_thin": timeit(lambda: ops.gemm_nt(x, A, t, ops.epilogue(alpha=2.0, alpha_cols=G * r)), flush=flush),
             "lora_down_p0": timeit(lambda: ops.lora_down(x, A, t, 2.0, G), flush=flush),
             "lora_down_p05": timeit(lambda: ops.lora_down(x, A, t, 2.0, G, bits), flush=flush),
+            "mask_stage_down_p05": timeit(lambda: ops.gemm_nt(x, A, t, ops.epilogue(alpha=2.0, alpha_cols=G * r, drop_a=bits)), flush=flush),
             "gemm_tn_dA": timeit(lambda: ops.gemm_tn(x, dt, dA, 1, K), flush=flush),
+            "mask_stage_dA_p05_per_adapter": timeit(lambda: ops.gemm_tn_masked(x, dt[:, :r], dA[:r], 1, K, bits[0]), flush=flush),
             "lora_da_p0": timeit(lambda: ops.lora_da(x, dt, dA, G), flush=flush),
             "lora_da_p05": timeit(lambda: ops.lora_da(x, dt, dA, G, bits), flush=flush),
             "lora_da_fix_p05": timeit(lambda: ops.lora_da(x, dt, dA, G, bits, dx=dx, At=At), flush=flush),
