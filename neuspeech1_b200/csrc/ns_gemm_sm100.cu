@@ -237,15 +237,33 @@ __device__ __forceinline__ void store32_f32(float* p, bool vec, int ncols, const
 #else
 #define NS_EPI_TRACE(tag) do { } while (0)
 #endif
-// AND-mask for a packed bf16 pair from two drop flags (bit 0 of each argument): 0 where dropped
-__device__ __forceinline__ uint32_t keep_pair(uint32_t drop_lo, uint32_t drop_hi) {
-  return ~(((drop_lo & 1u) | ((drop_hi & 1u) << 16)) * 0xFFFFu);
+// Mask stage helper: zero the dropped elements of one 128-byte row (64 bf16, eight 16-byte chunks stored 128B-swizzled:
+// logical chunk c sits at position c ^ sw) of an operand tile in shared memory.  w = the row's 64 drop flags, bit = column.
+// All eight loads are issued before the first use.  Four flags become four byte sign bits with one multiply
+// (bit j of a nibble lands on bit 8 j + 7: 0x10204080 = 2^7 + 2^14 + 2^21 + 2^28, no two partial products collide), and PRMT's
+// sign-replicate mode turns a pair of them into the 32-bit mask of a packed bf16 pair: 2 instructions per word after that.
+__device__ __forceinline__ void mask_row128(uint32_t row_addr, uint32_t sw, uint2 w) {
+  uint32_t v[8][4];
+#pragma unroll
+  for (int pp = 0; pp < 8; ++pp) ld_shared_v4(row_addr + 16u * pp, v[pp][0], v[pp][1], v[pp][2], v[pp][3]);
+#pragma unroll
+  for (int pp = 0; pp < 8; ++pp) {
+    const uint32_t c = static_cast<uint32_t>(pp) ^ sw;
+    const uint32_t m8 = (c < 4 ? w.x : w.y) >> (8 * (c & 3));
+    const uint32_t slo = (m8 & 0xFu) * 0x10204080u, shi = ((m8 >> 4) & 0xFu) * 0x10204080u;
+    v[pp][0] &= ~__byte_perm(slo, 0u, 0x9988u);
+    v[pp][1] &= ~__byte_perm(slo, 0u, 0xBBAAu);
+    v[pp][2] &= ~__byte_perm(shi, 0u, 0x9988u);
+    v[pp][3] &= ~__byte_perm(shi, 0u, 0xBBAAu);
+  }
+#pragma unroll
+  for (int pp = 0; pp < 8; ++pp) st_shared_v4(row_addr + 16u * pp, v[pp][0], v[pp][1], v[pp][2], v[pp][3]);
 }
 // AM = 1 ("A-operand mask", BN = 32 only): t = alpha (x . keep_g) A_g^T, the LoRA down product under branch dropout.  The
 // 32-wide kernel's second epilogue warpgroup (warps 8..11, idle at this width) becomes a MASK STAGE between the TMA and the
 // MMA: thread = one row of the 128 x 64 A tile; it waits for the tile, zeroes the dropped elements of its 128-byte swizzled row
-// in place (flags from the row-major bit plane: one 8-byte load per row and k block, fetched two blocks ahead; 16-byte chunks
-// without a dropped element are not touched: two thirds of them at p = 0.05), fences the generic writes for the async proxy
+// in place (flags from the row-major bit plane: one 8-byte load per row and k block, fetched two blocks ahead;
+// see mask_row128), fences the generic writes for the async proxy
 // and arrives on the barrier the MMA issuer waits on.  Stacked adapters (q/k/v) are consecutive column tiles: tile g masks the
 // same x tile (an L2 hit) with plane g.
 template <int BN, int CG, int PM, int AM>
@@ -446,21 +464,7 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
         w0 = w1;
         w1 = (valid && kb + 2 < nkb) ? __ldg(brow + kb + 2) : none;
         mbar_wait(full_bar(stage), phase);
-        const uint32_t row_addr = smem_base + stage * Cfg::kStageBytes + static_cast<uint32_t>(r) * 128u;
-        if (wc.x | wc.y) {
-#pragma unroll
-          for (int pp = 0; pp < 8; ++pp) {
-            const uint32_t c = static_cast<uint32_t>(pp) ^ sw;                 // logical 8-column chunk stored at position pp
-            const uint32_t m8 = ((c < 4 ? wc.x : wc.y) >> (8 * (c & 3))) & 0xFFu;
-            if (m8) {
-              uint32_t x0, x1, x2, x3;
-              ld_shared_v4(row_addr + 16u * pp, x0, x1, x2, x3);
-              x0 &= keep_pair(m8, m8 >> 1); x1 &= keep_pair(m8 >> 2, m8 >> 3);
-              x2 &= keep_pair(m8 >> 4, m8 >> 5); x3 &= keep_pair(m8 >> 6, m8 >> 7);
-              st_shared_v4(row_addr + 16u * pp, x0, x1, x2, x3);
-            }
-          }
-        }
+        mask_row128(smem_base + stage * Cfg::kStageBytes + static_cast<uint32_t>(r) * 128u, sw, wc);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(mfull_bar(stage));
@@ -991,21 +995,8 @@ gemm_tn_kernel(const __grid_constant__ TnMaps maps, const __grid_constant__ TnPr
         const uint32_t sa = smem_base + stage * p.stage_bytes;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          if (g < p.icta && (wc[g].x | wc[g].y)) {
-            const uint32_t row_addr = sa + 8192u * (2 * g + bpar) + static_cast<uint32_t>(row) * 128u;
-#pragma unroll
-            for (int pp = 0; pp < 8; ++pp) {
-              const uint32_t c = static_cast<uint32_t>(pp) ^ sw;
-              const uint32_t m8 = ((c < 4 ? wc[g].x : wc[g].y) >> (8 * (c & 3))) & 0xFFu;
-              if (m8) {
-                uint32_t x0, x1, x2, x3;
-                ld_shared_v4(row_addr + 16u * pp, x0, x1, x2, x3);
-                x0 &= keep_pair(m8, m8 >> 1); x1 &= keep_pair(m8 >> 2, m8 >> 3);
-                x2 &= keep_pair(m8 >> 4, m8 >> 5); x3 &= keep_pair(m8 >> 6, m8 >> 7);
-                st_shared_v4(row_addr + 16u * pp, x0, x1, x2, x3);
-              }
-            }
-          }
+          if (g < p.icta && (wc[g].x | wc[g].y))
+            mask_row128(sa + 8192u * (2 * g + bpar) + static_cast<uint32_t>(row) * 128u, sw, wc[g]);
         }
         fence_proxy_async();
         __syncwarp();

@@ -231,11 +231,13 @@ class WhisperEEGEngine:
                 ops.dropout_apply(x, xm, bits[g])
                 ops.gemm_nt(xm, A[g * r:(g + 1) * r], t[:, g * r:(g + 1) * r], self._ep(alpha=a, alpha_cols=r))
 
-    def _drop_plane(self, layer: int, target: str, M: int, K: int) -> Optional[torch.Tensor]:
+    def _drop_plane(self, layer: int, target: str, M: int, K: int, N: Optional[int] = None) -> Optional[torch.Tensor]:
         """The (M, K/32) dropout plane of ONE adapter for the input-gradient GEMM's masked second product (ns_epilogue.drop_bits:
         dx = g W + keep . (dt' A), the LoRA product masked in the epilogue), or None when the step runs without dropout or the
         shape / storage takes the correction pass instead (`_lora_da_fix(dx=...)`)."""
         if self._drop_p == 0.0 or not self.use_lora_kernels or K % 64 != 0 or _NO_GEMM_MASK:
+            return None
+        if self.dims.lora_r % 16 != 0 or (N is not None and N % 16 != 0):     # tcgen05 operand rules of both products
             return None
         return self._bits(layer, (target,), M, K)[0]
 
@@ -693,7 +695,7 @@ class WhisperEEGEngine:
                 dt2 = ws.get("dt_r", (M, r), dt)
                 ops.gemm_nt(dh, W[k + ".B_fc2_t"], dt2, self._ep(alpha=s, alpha_cols=r))
                 ops.gemm_tn(dh, g("t_2"), G("fc2", "B"), r, 1)
-                db = self._drop_plane(i, "fc2", M, F)
+                db = self._drop_plane(i, "fc2", M, F, d)
                 ops.gemm_nt(dh, W[k + ".w2_t"], dz1, self._ep(act=ACT_DGELU, aux_in=g("z1"), ldaux=F, drop_bits=db), a2=dt2,
                             w2=W[k + ".A_fc2_t"], k2=r)
                 self._lora_da_fix(g("m"), dt2, dz1 if db is None else None, W[k + ".A_fc2_t"], i, ("fc2",), z=g("z1"))
@@ -707,7 +709,7 @@ class WhisperEEGEngine:
                 ops.gemm_tn(dz1, g("t_1"), G("fc1", "B"), r, 1)
                 # (long contraction, narrow output: the 128-wide tiles of the masked product re-read dz1 from L2 twice as often
                 # and cost more than the correction pass saves -- measured 234 + 43 us against 154 + 83 us)
-                db = self._drop_plane(i, "fc1", M, d) if F <= d else None
+                db = self._drop_plane(i, "fc1", M, d, F) if F <= d else None
                 ops.gemm_nt(dz1, W[k + ".w1_t"], du2, self._ep(drop_bits=db), a2=dt1, w2=W[k + ".A_fc1_t"], k2=r)
                 self._lora_da_fix(g("u2"), dt1, du2 if db is None else None, W[k + ".A_fc1_t"], i, ("fc1",))
             else:
@@ -720,7 +722,7 @@ class WhisperEEGEngine:
                 dto = ws.get("dt_r", (M, r), dt)
                 ops.gemm_nt(dhm, W[k + ".B_out_proj_t"], dto, self._ep(alpha=s, alpha_cols=r))
                 ops.gemm_tn(dhm, g("t_o"), G("out_proj", "B"), r, 1)
-                db = self._drop_plane(i, "out_proj", M, d)
+                db = self._drop_plane(i, "out_proj", M, d, d)
                 ops.gemm_nt(dhm, W[k + ".wo_t"], do, self._ep(drop_bits=db), a2=dto, w2=W[k + ".A_out_proj_t"], k2=r)
                 self._lora_da_fix(g("o"), dto, do if db is None else None, W[k + ".A_out_proj_t"], i, ("out_proj",))
             else:
