@@ -239,25 +239,32 @@ __device__ __forceinline__ void store32_f32(float* p, bool vec, int ncols, const
 #endif
 // Mask stage helper: zero the dropped elements of one 128-byte row (64 bf16, eight 16-byte chunks stored 128B-swizzled:
 // logical chunk c sits at position c ^ sw) of an operand tile in shared memory.  w = the row's 64 drop flags, bit = column.
-// All eight loads are issued before the first use.  Four flags become four byte sign bits with one multiply
-// (bit j of a nibble lands on bit 8 j + 7: 0x10204080 = 2^7 + 2^14 + 2^21 + 2^28, no two partial products collide), and PRMT's
-// sign-replicate mode turns a pair of them into the 32-bit mask of a packed bf16 pair: 2 instructions per word after that.
+// The loop runs over LOGICAL chunks: the 8 consecutive rows of a quarter warp then touch 8 different positions, i.e. all 32
+// banks (walking positions instead puts every lane of the warp on the same four banks: 8-way conflicts on each of the 16
+// accesses, measured 48 -> 80 us at K = 512).  All eight loads are issued before the first use.  Four flags become four byte
+// sign bits with one multiply (bit j of a nibble lands on bit 8 j + 7: 0x10204080 = 2^7 + 2^14 + 2^21 + 2^28, no two partial
+// products collide), and PRMT's sign-replicate mode (selector nibble bit 3; __byte_perm documents only 3 bits, hence the PTX)
+// turns a pair of them into the 32-bit mask of a packed bf16 pair: 2 instructions per word after that.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
 __device__ __forceinline__ void mask_row128(uint32_t row_addr, uint32_t sw, uint2 w) {
   uint32_t v[8][4];
 #pragma unroll
-  for (int pp = 0; pp < 8; ++pp) ld_shared_v4(row_addr + 16u * pp, v[pp][0], v[pp][1], v[pp][2], v[pp][3]);
+  for (int c = 0; c < 8; ++c) ld_shared_v4(row_addr + ((static_cast<uint32_t>(c) ^ sw) << 4), v[c][0], v[c][1], v[c][2], v[c][3]);
 #pragma unroll
-  for (int pp = 0; pp < 8; ++pp) {
-    const uint32_t c = static_cast<uint32_t>(pp) ^ sw;
+  for (int c = 0; c < 8; ++c) {
     const uint32_t m8 = (c < 4 ? w.x : w.y) >> (8 * (c & 3));
     const uint32_t slo = (m8 & 0xFu) * 0x10204080u, shi = ((m8 >> 4) & 0xFu) * 0x10204080u;
-    v[pp][0] &= ~__byte_perm(slo, 0u, 0x9988u);
-    v[pp][1] &= ~__byte_perm(slo, 0u, 0xBBAAu);
-    v[pp][2] &= ~__byte_perm(shi, 0u, 0x9988u);
-    v[pp][3] &= ~__byte_perm(shi, 0u, 0xBBAAu);
+    v[c][0] &= ~prmt(slo, 0u, 0x9988u);
+    v[c][1] &= ~prmt(slo, 0u, 0xBBAAu);
+    v[c][2] &= ~prmt(shi, 0u, 0x9988u);
+    v[c][3] &= ~prmt(shi, 0u, 0xBBAAu);
   }
 #pragma unroll
-  for (int pp = 0; pp < 8; ++pp) st_shared_v4(row_addr + 16u * pp, v[pp][0], v[pp][1], v[pp][2], v[pp][3]);
+  for (int c = 0; c < 8; ++c) st_shared_v4(row_addr + ((static_cast<uint32_t>(c) ^ sw) << 4), v[c][0], v[c][1], v[c][2], v[c][3]);
 }
 // AM = 1 ("A-operand mask", BN = 32 only): t = alpha (x . keep_g) A_g^T, the LoRA down product under branch dropout.  The
 // 32-wide kernel's second epilogue warpgroup (warps 8..11, idle at this width) becomes a MASK STAGE between the TMA and the
