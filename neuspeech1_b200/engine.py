@@ -27,6 +27,7 @@ from . import ops
 from ._abi import ACT_DGELU, ACT_GELU, ACT_NONE, NS_BF16, NS_F32
 
 _NO_TRAIN_GRAPH = bool(os.environ.get("NS_NO_TRAIN_GRAPH"))     # developer switch: launch every kernel of train_step one by one
+_NO_AR_OVERLAP = bool(os.environ.get("NS_NO_AR_OVERLAP"))       # developer A/B switch: one all-reduce after the whole backward
 _NO_MASK_STAGE = bool(os.environ.get("NS_NO_MASK_STAGE"))       # developer A/B switch: mma.sync ns_lora_down / ns_lora_da instead of the mask stages
 _NO_GEMM_MASK = bool(os.environ.get("NS_NO_GEMM_MASK"))         # developer A/B switch: dropout correction pass instead of the masked GEMM product
 ENC_LORA_TARGETS = ("q_proj", "k_proj", "v_proj", "out_proj", "fc1", "fc2")
@@ -614,15 +615,19 @@ class WhisperEEGEngine:
 
     # ------------------------------------------------------------------ backward
     @_on_device
-    def backward(self, grad_scale: float = 1.0):
+    def backward(self, grad_scale: float = 1.0, part: Optional[int] = None):
         """Gradients of the mean token cross-entropy w.r.t. the trainable set into self.grad (flat fp32).
         Must follow forward_loss(..., labels=..., save=True).  Mirrors autograd through utils/load_model.py:976-1070 with
-        every non-LoRA / non-stem weight frozen (finetune.py:176-177)."""
+        every non-LoRA / non-stem weight frozen (finetune.py:176-177).
+        part: None = everything; 0 = loss .. encoder layers (every LoRA gradient is final after it: `layout.lora_end`), 1 = the
+        stem.  The data-parallel step runs them apart so that the all-reduce of the LoRA gradients overlaps the stem backward."""
         dm, W, ws, dt = self.dims, self.P, self.ws, self.dtype
         d, S, T, F, r, H = dm.d_model, dm.max_source_positions, dm.T, dm.enc_ffn, dm.lora_r, dm.enc_heads
         B, L = self._B, self._L
         M, ML = B * S, B * L
         s = dm.lora_scale / (1.0 - self._drop_p)         # dt' = alpha' g B (the 1/(1-p) of the dropped branch input lives here)
+        if part == 1:
+            return self._backward_stem(self._dh_stem)
         self.grad.zero_()
         # ---- loss -> logits (in place) -> decoder output
         logits = ws.bufs["logits"]
@@ -748,7 +753,16 @@ class WhisperEEGEngine:
             else:
                 ops.gemm_nt(dqkv, W[k + ".wqkv_t"], du1, self._ep())
             ops.layernorm_bwd(du1, self._saved_h[i], W[k + ".ln1.g"], g("mean1"), g("rstd1"), dh, dres=dhm)
-        # ---- stem (all three convs trainable; conv A's input needs no gradient)
+        self._dh_stem = dh
+        if part == 0:
+            return self.grad
+        return self._backward_stem(dh)
+
+    def _backward_stem(self, dh: torch.Tensor):
+        """Stem part of `backward` (all three convs trainable; conv A's input needs no gradient)."""
+        dm, W, ws, dt = self.dims, self.P, self.ws, self.dtype
+        d, S, T = dm.d_model, dm.max_source_positions, dm.T
+        B = self._B
         Cp = dm.Cp
         dzC = ws.get("dzC", (B, S, d), dt)
         ops.dgelu_mul(dh, ws.bufs["zC"], dzC)
@@ -806,33 +820,61 @@ class WhisperEEGEngine:
         addresses every step, a workspace that grew, reloaded weights -- simply keeps running eagerly.  The gradient
         all-reduce and the three optimizer launches stay outside the graph (learning rate and step count are host values)."""
         loss = None
+        # data parallel: the LoRA gradients (first part of the flat buffer) are complete before the stem backward starts, so
+        # their all-reduce runs on a side stream under it; the stem gradients follow on the main stream
+        split = all_reduce is not None and self.has_lora and not _NO_AR_OVERLAP
         if (use_graph and not getattr(self, "_graphs_off", False) and not _NO_TRAIN_GRAPH and ops._prof is None and x.is_cuda and x.is_contiguous()
                 and labels.is_cuda and labels.is_contiguous() and labels.dtype == torch.long):
-            loss = self._fwd_bwd_graph(x, labels, aug)
+            loss = self._fwd_bwd_graph(x, labels, aug, all_reduce if split else None)
+            reduced = split
         if loss is None:
             self._advance_seed()
             self.pack_trainable()
             loss, _, _ = self.forward_loss(x, labels, aug=aug, save=True, ce_grad_scale=1.0)
-            self.backward()
-        if all_reduce is not None:
+            if split:
+                self.backward(part=0)
+                self._reduce_overlapped(all_reduce, lambda: self.backward(part=1))
+            else:
+                self.backward()
+            reduced = split
+        if all_reduce is not None and not reduced:
             all_reduce(self.grad)
         self.optimizer_step(lr)
         return loss
+
+    def _reduce_overlapped(self, all_reduce, run_stem):
+        """all_reduce(LoRA gradients) on a side stream while `run_stem` (the stem backward) runs on the current one, then
+        all_reduce(stem gradients).  Both collectives are issued in the same order on every rank."""
+        n = self.layout.lora_end
+        cur = torch.cuda.current_stream(self.device)
+        side = self.__dict__.get("_ar_stream")
+        if side is None:
+            side = self._ar_stream = torch.cuda.Stream(device=self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            all_reduce(self.grad[:n])
+        run_stem()
+        all_reduce(self.grad[n:])
+        cur.wait_stream(side)
 
     def _advance_seed(self):
         if self.lora_dropout > 0.0 and self.training and self.has_lora:
             ops.seed_advance(self.drop_seed)
 
-    def _fwd_bwd_graph(self, x, labels, aug):
-        """Replay (or capture) the graph of pack_trainable + forward_loss + backward for these buffers; None = run eagerly."""
+    def _fwd_bwd_graph(self, x, labels, aug, all_reduce=None):
+        """Replay (or capture) the graph of pack_trainable + forward_loss + backward for these buffers; None = run eagerly.
+        With `all_reduce` the step is TWO graphs (.. encoder backward | stem backward) and the gradient all-reduce is issued
+        between / after them (`_reduce_overlapped`)."""
         from . import _abi
         akey = tuple(sorted((k, v.data_ptr() if torch.is_tensor(v) else v) for k, v in (aug or {}).items()))
-        key = (x.data_ptr(), tuple(x.shape), x.dtype, labels.data_ptr(), tuple(labels.shape), akey)
+        key = (x.data_ptr(), tuple(x.shape), x.dtype, labels.data_ptr(), tuple(labels.shape), akey, all_reduce is not None)
         stamp = (self.ws.gen, self._weights_version, self.lora_dropout, self.training)
         graphs = self.__dict__.setdefault("_train_graphs", {})
         ent = graphs.get(key)
         if ent is not None and ent[0] is not None and ent[3] == stamp:
             ent[0].replay()
+            if all_reduce is not None:
+                self._reduce_overlapped(all_reduce, ent[4].replay)
             self.graph_launches += ent[2]
             self._packed = False
             return ent[1].clone()                     # the graph's own output buffer is overwritten by the next replay
@@ -845,12 +887,16 @@ class WhisperEEGEngine:
         torch.cuda.synchronize()
         before = sum(_abi.counters().values())
         g = torch.cuda.CUDAGraph()
+        g2 = torch.cuda.CUDAGraph() if all_reduce is not None else None
         try:
             with torch.cuda.graph(g, capture_error_mode="thread_local"):   # loader threads may pin memory meanwhile
                 self._advance_seed()
                 self.pack_trainable()
                 loss, _, _ = self.forward_loss(x, labels, aug=aug, save=True, ce_grad_scale=1.0)
-                self.backward()
+                self.backward(part=None if g2 is None else 0)
+            if g2 is not None:
+                with torch.cuda.graph(g2, pool=g.pool(), capture_error_mode="thread_local"):
+                    self.backward(part=1)
         except Exception as e:                          # something on this path is not capturable: stay eager from now on
             import warnings
             warnings.warn(f"neuspeech1_b200: CUDA-graph capture of the training step failed ({e}); running eagerly")
@@ -863,8 +909,10 @@ class WhisperEEGEngine:
         if (self.ws.gen, self._weights_version, self.lora_dropout, self.training) != stamp:   # the capture itself allocated: do not trust it
             graphs.pop(key, None)
             return None
-        graphs[key] = (g, loss, n, stamp)
+        graphs[key] = (g, loss, n, stamp, g2)
         g.replay()
+        if g2 is not None:
+            self._reduce_overlapped(all_reduce, g2.replay)
         self.graph_launches += n
         self._packed = False
         return loss.clone()

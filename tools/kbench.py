@@ -23,7 +23,14 @@ DEV = torch.device("cuda")
 torch.backends.cuda.matmul.allow_tf32 = False
 
 
+NCU = False          # --ncu: every target kernel exactly once (no warm-up, no correctness pre-pass): the capture list stays short
+
+
 def timeit(fn, iters):
+    if NCU:
+        fn()
+        torch.cuda.synchronize()
+        return 1.0
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -64,6 +71,11 @@ def bench_attn(B, iters, out):
     off = (-ws.data_ptr()) % 1024
     ws = ws[off: off + ops.attention_bwd_workspace_bytes(shp)]
     ops.attention_fwd(shp, q, k, v, o, lse)
+    if NCU:
+        ops.attention_bwd_ws(shp, q, k, v, o, do, lse, delta, dq, dk, dv, ws)
+        torch.cuda.synchronize()
+        out["attn"] = {}
+        return
     # ---- correctness on the first 2 batch entries
     nb = min(B, 2)
     qf = q[: nb * S].float().reshape(nb, S, H, Dh).requires_grad_(True)
@@ -132,6 +144,38 @@ def bench_gemm(B, iters, out):
     G3 = torch.zeros(r * d, device=DEV)
     t = timeit(lambda: ops.gemm_tn(t32, x512, G3, d, 1), iters)
     res["wgrad 32x512 (dA)"] = {"ms": t, "tflops": 2.0 * M * d * r / t / 1e9}
+    # ---- LoRA-branch dropout (finetune.py:210, p = 0.05): bit plane, mask stages, masked second product, q/k/v correction pass
+    seed = torch.tensor([1234], dtype=torch.int32, device=DEV)
+    bits512 = torch.empty(3, M, d // 32, dtype=torch.int32, device=DEV)
+    bits2048 = torch.empty(1, M, F // 32, dtype=torch.int32, device=DEV)
+    t = timeit(lambda: ops.dropout_bits(M, d, seed, [11, 22, 33], 0.05, bits512), iters)
+    res["dropout_bits 3x(M,512)"] = {"ms": t, "gbs": bits512.numel() * 4 / t / 1e6}
+    ops.dropout_bits(M, F, seed, [44], 0.05, bits2048)
+    t1 = torch.empty(M, r, dtype=torch.bfloat16, device=DEV); t3 = torch.empty(M, 3 * r, dtype=torch.bfloat16, device=DEV)
+    A1, A3, A4 = mk(r, d), mk(3 * r, d), mk(r, F)
+    t = timeit(lambda: ops.gemm_nt(x512, A1, t1, ops.epilogue(alpha=2.0, alpha_cols=r, drop_a=bits512[:1])), iters)
+    res["lora_t 512->32 masked"] = {"ms": t, "gbs": M * d * 2 / t / 1e6}
+    t = timeit(lambda: ops.gemm_nt(x512, A3, t3, ops.epilogue(alpha=2.0, alpha_cols=3 * r, drop_a=bits512)), iters)
+    res["lora_t 512->96 masked"] = {"ms": t, "gbs": M * d * 2 / t / 1e6}
+    t = timeit(lambda: ops.gemm_nt(x2048, A4, t1, ops.epilogue(alpha=2.0, alpha_cols=r, drop_a=bits2048)), iters)
+    res["lora_t 2048->32 masked"] = {"ms": t, "gbs": M * F * 2 / t / 1e6}
+    t = timeit(lambda: ops.gemm_tn_masked(x512, t32, G3, 1, d, bits512[0]), iters)
+    res["wgrad dA 512 masked"] = {"ms": t, "gbs": M * d * 2 / t / 1e6}
+    G4 = torch.zeros(r * F, device=DEV)
+    t = timeit(lambda: ops.gemm_tn_masked(x2048, t32, G4, 1, F, bits2048[0]), iters)
+    res["wgrad dA 2048 masked"] = {"ms": t, "gbs": M * F * 2 / t / 1e6}
+    dz1 = torch.empty(M, F, dtype=torch.bfloat16, device=DEV)
+    w2t, a2t = mk(F, d), mk(F, r)
+    t = timeit(lambda: ops.gemm_nt(x512, w2t, dz1, ops.epilogue(act=ACT_DGELU, aux_in=z1, ldaux=F, drop_bits=bits2048[0]), a2=t32, w2=a2t, k2=r), iters)
+    res["dfc2+dgelu masked product"] = {"ms": t, "tflops": 2.0 * M * F * (d + r) / t / 1e9}
+    do_ = torch.empty(M, d, dtype=torch.bfloat16, device=DEV)
+    wot, aot = mk(d, d), mk(d, r)
+    t = timeit(lambda: ops.gemm_nt(x512, wot, do_, ops.epilogue(drop_bits=bits512[0]), a2=t32, w2=aot, k2=r), iters)
+    res["dout masked product"] = {"ms": t, "tflops": 2.0 * M * d * (d + r) / t / 1e9}
+    dA3 = torch.zeros(3 * r, d, device=DEV)
+    At3 = mk(d, 3 * r)
+    t = timeit(lambda: ops.lora_da(x512, t96, dA3, 3, bits512, dx=do_, At=At3), iters)
+    res["lora_da qkv + dx correction"] = {"ms": t, "gbs": M * d * 2 / t / 1e6}
     out["gemm"] = res
 
 
@@ -209,7 +253,10 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--out", default=None)
     ap.add_argument("--lib", default=None, help="A/B aid: load this build of the shared library instead of the in-tree one")
+    ap.add_argument("--ncu", action="store_true", help="launch every target kernel exactly once (for ncu --set full captures)")
     a = ap.parse_args()
+    global NCU
+    NCU = a.ncu
     if a.lib:
         from neuspeech1_b200 import _abi
         _abi.LIB_PATH = os.path.abspath(a.lib)
