@@ -320,14 +320,16 @@ def run_ours(args):
         # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/), null when not captured
         traffic = None
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01c_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
             traffic = tj.get(top_name, {}).get("dram_bytes_per_launch_avg")
         except Exception:
             traffic = None
         if top["flops"] > 0:
             ach = top["flops"] / (top["ms"] * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": top_name, "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["tf_sustained"], "traffic": traffic, "launches": top["n"], "share_of_step": top["ms"] / tot,
+                    "frac": ach / peaks["tf_sustained"], "traffic": traffic,
+                    "traffic_source": "profiles/r02_traffic.json: dram bytes per launch, ncu --set full of this build's kernels at the bench shapes (tools/gpu_ncu_r02.sh), averaged over the family's launches",
+                    "launches": top["n"], "share_of_step": top["ms"] / tot,
                     "peak_source": peaks["src"] + " (sustained bf16: kernel timed inside a long step)"}
         else:
             ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9
