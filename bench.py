@@ -335,6 +335,14 @@ def run_ours(args):
             ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": top_name, "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
                     "traffic": traffic, "launches": top["n"], "share_of_step": top["ms"] / tot, "peak_source": peaks["src"]}
+        # HBM-bound kernels of the step (bytes = algorithmic bytes per launch) against the measured copy peak
+        hbm = {}
+        for name in ("ns_aug_pass", "ns_layernorm_fwd", "ns_layernorm_bwd", "ns_cross_entropy", "ns_gemm_nt.rank_r", "ns_dropout_bits"):
+            f = fam.get(name)
+            if f and f["bytes"] > 0 and f["ms"] > 0:
+                gbs = f["bytes"] / (f["ms"] * 1e-3) / 1e9
+                hbm[name] = {"achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"], "launches": f["n"],
+                             "share_of_step": f["ms"] / tot}
         fps = FLOP_PER_SAMPLE.get(args.eeg_ch, 267.92e9) if args.config in ("train", "c273") else flop_per_sample(dims, L)
         step_tf = value / world * fps / 1e12
         shares = {k: round(v["ms"] / tot, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])[:8]}
@@ -354,6 +362,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": x_host.numel() * 4 + labels_host.numel() * 8,
                     "d2h_bytes_per_step": 4},
             "roofline": roof,
+            "hbm_roofline": hbm,
             "step_roofline": {"achieved_tflops": step_tf, "frac_of_sustained_peak": step_tf / peaks["tf_sustained"],
                               "flop_per_sample": fps},
             "kernel_shares": shares,

@@ -33,6 +33,12 @@ typedef enum { NS_PATH_AUTO = 0, NS_PATH_SIMT = 1, NS_PATH_FAST = 2 } ns_path;
 int         ns_version(void);
 const char* ns_last_error_string(void);
 int         ns_set_path(int path);                 /* ns_path; returns previous */
+/* Programmatic dependent launch for the calling thread's subsequent launches (returns the previous setting).  The kernels of
+ * the one-token decoder step (embedding, LayerNorm forward, tcgen05 GEMM, single-query attention, greedy pick) are then
+ * launched with cudaLaunchAttributeProgrammaticStreamSerialization: their prologues overlap the tail of the kernel before them
+ * and each waits (griddepcontrol.wait) before its first global-memory access.  Streams captured into CUDA graphs keep the
+ * programmatic edges.  Off by default. */
+int         ns_set_pdl(int on);
 int         ns_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* counters[0]=tcgen05 GEMM launches, [1]=SIMT GEMM launches, [2]=tensor-core attention launches, [3]=SIMT attention
  * launches, [4]=other kernel launches, [5]=tcgen05 wgrad launches.  Reset with ns_reset_counters(). */
@@ -149,10 +155,12 @@ int ns_embed(int dtype, int B, int L, int d, const long long* ids, const void* E
 int ns_cross_entropy(int dtype, long long rows, int V, long long ld, void* logits, const long long* labels,
                      float* row_loss, float* loss_sum_out, int* n_valid_out, int write_grad, float grad_scale,
                      void* stream);
-/* ---- greedy next token: argmax over logits[b, :V] with `suppress` ids at -inf, finished rows emit pad
- *  (GenerationMixin greedy + SuppressTokensAtBegin, HF generation_whisper.py:1774-1813). */
+/* ---- greedy next token: argmax over logits[b, :V] with `suppress` ids (at most 64) at -inf, finished rows emit pad
+ *  (GenerationMixin greedy + SuppressTokensAtBegin, HF generation_whisper.py:1774-1813).  out != NULL: the token is also
+ *  appended to the output sequence, out[b * out_ld] (the caller passes &sequences[0][step]). */
 int ns_greedy_pick(int dtype, int B, int V, long long ld, const void* logits, const int* suppress, int n_suppress,
-                   int eos, int pad, unsigned char* finished, long long* next_ids, void* stream);
+                   int eos, int pad, unsigned char* finished, long long* next_ids, long long* out, long long out_ld,
+                   void* stream);
 
 /* ---- EEG augmentation + pad + cast + layout pass (utils/reader.py:552-594, :496-506; utils/augment_eeg.py:15-26,54-56;
  *  utils/utils.py:33-60).  One read of x, one write of y.  x is either the collator's dense (B,C,Tin) batch (src_off NULL) or a

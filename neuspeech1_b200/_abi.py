@@ -67,7 +67,8 @@ SIGNATURES = {
     "ns_debug_attn_trace": [c_vp],
     "ns_embed": [c_i, c_i, c_i, c_i, c_vp, c_vp, c_vp, c_i, c_vp, c_vp],
     "ns_cross_entropy": [c_i, c_ll, c_i, c_ll, c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_f, c_vp],
-    "ns_greedy_pick": [c_i, c_i, c_i, c_ll, c_vp, c_vp, c_i, c_i, c_i, c_vp, c_vp, c_vp],
+    "ns_greedy_pick": [c_i, c_i, c_i, c_ll, c_vp, c_vp, c_i, c_i, c_i, c_vp, c_vp, c_vp, c_ll, c_vp],
+    "ns_set_pdl": [c_i],
     "ns_aug_pass": [C.POINTER(AugArgs), c_vp, c_vp, c_vp],
     "ns_channel_meansq": [c_i, c_i, c_i, c_i, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "ns_cast": [c_i, c_i, c_ll, c_vp, c_vp, c_vp],

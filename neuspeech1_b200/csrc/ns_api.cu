@@ -9,6 +9,7 @@ namespace ns {
 
 static thread_local char g_err[512] = "";
 thread_local int g_path = NS_PATH_AUTO;
+thread_local int g_pdl = 0;
 static std::atomic<long long> g_counters[C_NUM];
 
 void set_error(const char* fmt, ...) {
@@ -82,6 +83,12 @@ int ns_get_counters(long long* counters, int n) {
 int ns_reset_counters(void) {
   for (int i = 0; i < C_NUM; ++i) g_counters[i].store(0);
   return NS_OK;
+}
+
+int ns_set_pdl(int on) {
+  const int prev = g_pdl;
+  g_pdl = on ? 1 : 0;
+  return prev;
 }
 
 int ns_gemm_nt(int dtype, long long M, int N, int K, const void* A, long long lda, const void* W, long long ldw, void* D,

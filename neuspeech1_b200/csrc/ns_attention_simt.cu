@@ -502,6 +502,8 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const ns_attn_shape s,
   constexpr int KPW = 32 / CPR;                    // keys per warp instruction
   __shared__ float sm_m[8], sm_l[8];
   __shared__ __align__(16) float sm_o[8][DH];
+  pdl_launch_dependents();
+  pdl_wait();
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = lane % CPR, kk = lane / CPR;
@@ -605,8 +607,8 @@ static bool decode_eligible(const ns_attn_shape& s, const void* q, const void* k
 template <typename T, int DH>
 static int attn_fwd_simt_t(const ns_attn_shape& s, const void* q, const void* k, const void* v, void* o, float* lse, cudaStream_t st) {
   if (decode_eligible<T, DH>(s, q, k, v)) {
-    attn_decode_kernel<T, DH><<<dim3(s.H, s.B), 256, 0, st>>>(s, reinterpret_cast<const T*>(q), reinterpret_cast<const T*>(k),
-                                                            reinterpret_cast<const T*>(v), reinterpret_cast<T*>(o), lse, nullptr, 0);
+    NS_CUDA(launch_pdl(attn_decode_kernel<T, DH>, dim3(s.H, s.B), dim3(256), 0, st, s, reinterpret_cast<const T*>(q), reinterpret_cast<const T*>(k),
+                       reinterpret_cast<const T*>(v), reinterpret_cast<T*>(o), lse, static_cast<const int*>(nullptr), 0LL));
     NS_LAUNCH_CHECK();
     count(C_ATTN_SIMT);
     return NS_OK;

@@ -17,6 +17,27 @@ enum Counter { C_GEMM_TC = 0, C_GEMM_SIMT = 1, C_ATTN_TC = 2, C_ATTN_SIMT = 3, C
 void count(int which, long long n = 1);
 int sm_count();
 
+// ---------------------------------------------------------------- programmatic dependent launch (ns_set_pdl)
+// The decoder's one-token steps are ~70 tiny dependent kernels (M = batch rows): with the launch attribute below the next
+// kernel's CTAs are scheduled and run their prologue (barrier init, TMEM allocation, descriptor prefetch) while the previous
+// kernel is still running; every kernel that may be launched this way executes pdl_wait() before its first global-memory
+// access (griddepcontrol.wait: all prerequisite grids complete and flushed; a no-op without the attribute).
+extern thread_local int g_pdl;
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// <<<grid, block, smem, stream>>> with the programmatic-stream-serialization attribute when ns_set_pdl(1) is in effect
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 #define NS_CHECK_ARG(cond, ...)                       \
   do {                                                \
     if (!(cond)) {                                    \

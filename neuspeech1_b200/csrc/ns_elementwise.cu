@@ -13,6 +13,8 @@ __global__ void __launch_bounds__(256) ln_fwd_bf16_kernel(long long rows, const 
                                                           __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
                                                           float* __restrict__ rstd_out, float eps) {
   constexpr int d = NV * 256;
+  pdl_launch_dependents();
+  pdl_wait();
   const long long row0 = (static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5)) * 2;
   const int lane = threadIdx.x & 31;
   if (row0 >= rows) return;
@@ -183,6 +185,8 @@ __global__ void __launch_bounds__(256) ln_bwd_bf16_kernel(long long rows, const 
 template <typename T>
 __global__ void embed_kernel(int L, int d, const long long* __restrict__ ids, const T* __restrict__ E, const T* __restrict__ P,
                              int pos0, T* __restrict__ h) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long tok = blockIdx.x;   // b*L + l
   const int l = static_cast<int>(tok % L);
   const long long id = ids[tok];
@@ -361,20 +365,53 @@ __global__ void __launch_bounds__(512) ce_vec_kernel(int V, long long ld, __nv_b
 }
 
 // ------------------------------------------------------------------------------------------------ greedy pick
+// One CTA per row, 16-byte loads (the scalar version with a global suppress-list lookup per element took 53 us for 128 rows of
+// 51865 logits: latency-bound at 0.25 TB/s).  Ties go to the smallest index, as torch.argmax.
+constexpr int kMaxSuppress = 64;
 template <typename T>
 __global__ void __launch_bounds__(512) greedy_kernel(int V, long long ld, const T* __restrict__ logits, const int* __restrict__ suppress,
                                                      int n_suppress, int eos, int pad, unsigned char* finished,
-                                                     long long* __restrict__ next_ids) {
+                                                     long long* __restrict__ next_ids, long long* __restrict__ out, long long out_ld) {
+  constexpr int VEC = 16 / sizeof(T);
   __shared__ float shv[32];
   __shared__ int shi[32];
+  __shared__ int s_sup[kMaxSuppress];
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const T* lr = logits + static_cast<long long>(b) * ld;
+  if (threadIdx.x < n_suppress) s_sup[threadIdx.x] = suppress[threadIdx.x];
+  __syncthreads();
   float best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int c = threadIdx.x; c < V; c += blockDim.x) {
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(lr) & 15) == 0;
+  const int Vv = vec_ok ? (V / VEC) * VEC : 0;
+  for (int c0 = threadIdx.x * VEC; c0 < Vv; c0 += blockDim.x * VEC) {
+    float v[VEC];
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(lr + c0));
+    if constexpr (sizeof(T) == 2) {
+      float2 f;
+      f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y; f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+      f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y; f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+    } else {
+      v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
+    }
+    for (int s = 0; s < n_suppress; ++s) {
+      const unsigned dlt = static_cast<unsigned>(s_sup[s] - c0);
+      if (dlt < static_cast<unsigned>(VEC)) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+          if (static_cast<unsigned>(j) == dlt) v[j] = -INFINITY;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j)
+      if (v[j] > best) { best = v[j]; bi = c0 + j; }            // ascending indices inside a thread: strict > keeps the first
+  }
+  for (int c = Vv + threadIdx.x; c < V; c += blockDim.x) {      // tail (and rows that are not 16-byte aligned)
     float v = to_f<T>(lr[c]);
     for (int s = 0; s < n_suppress; ++s)
-      if (suppress[s] == c) v = -INFINITY;
+      if (s_sup[s] == c) v = -INFINITY;
     if (v > best || (v == best && c < bi)) { best = v; bi = c; }
   }
   for (int o = 16; o > 0; o >>= 1) {
@@ -400,6 +437,7 @@ __global__ void __launch_bounds__(512) greedy_kernel(int V, long long ld, const 
         else if (tok == eos) finished[b] = 1;
       }
       next_ids[b] = tok;
+      if (out) out[b * out_ld] = tok;
     }
   }
 }
@@ -736,11 +774,11 @@ int ns_layernorm_fwd(int dtype, long long rows, int d, const void* x, const floa
     bf16* yo = reinterpret_cast<bf16*>(y);
     const unsigned grid = static_cast<unsigned>((rows + 15) / 16);    // 8 warps x 2 rows per block
     switch (d / 256) {
-      case 1: ln_fwd_bf16_kernel<1><<<grid, 256, 0, st>>>(rows, xi, gamma, beta, yo, mean, rstd, eps); break;
-      case 2: ln_fwd_bf16_kernel<2><<<grid, 256, 0, st>>>(rows, xi, gamma, beta, yo, mean, rstd, eps); break;
-      case 3: ln_fwd_bf16_kernel<3><<<grid, 256, 0, st>>>(rows, xi, gamma, beta, yo, mean, rstd, eps); break;
-      case 4: ln_fwd_bf16_kernel<4><<<grid, 256, 0, st>>>(rows, xi, gamma, beta, yo, mean, rstd, eps); break;
-      default: ln_fwd_bf16_kernel<5><<<grid, 256, 0, st>>>(rows, xi, gamma, beta, yo, mean, rstd, eps); break;
+      case 1: NS_CUDA(launch_pdl(ln_fwd_bf16_kernel<1>, grid, 256, 0, st, rows, xi, gamma, beta, yo, mean, rstd, eps)); break;
+      case 2: NS_CUDA(launch_pdl(ln_fwd_bf16_kernel<2>, grid, 256, 0, st, rows, xi, gamma, beta, yo, mean, rstd, eps)); break;
+      case 3: NS_CUDA(launch_pdl(ln_fwd_bf16_kernel<3>, grid, 256, 0, st, rows, xi, gamma, beta, yo, mean, rstd, eps)); break;
+      case 4: NS_CUDA(launch_pdl(ln_fwd_bf16_kernel<4>, grid, 256, 0, st, rows, xi, gamma, beta, yo, mean, rstd, eps)); break;
+      default: NS_CUDA(launch_pdl(ln_fwd_bf16_kernel<5>, grid, 256, 0, st, rows, xi, gamma, beta, yo, mean, rstd, eps)); break;
     }
   } else if (dtype == NS_BF16) {
     ln_fwd_generic_kernel<bf16><<<grid, 256, 0, st>>>(rows, d, reinterpret_cast<const bf16*>(x), gamma, beta,
@@ -791,9 +829,11 @@ int ns_embed(int dtype, int B, int L, int d, const long long* ids, const void* E
   if (B * L == 0) return NS_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (dtype == NS_BF16)
-    embed_kernel<bf16><<<B * L, 128, 0, st>>>(L, d, ids, reinterpret_cast<const bf16*>(E), reinterpret_cast<const bf16*>(P), pos0, reinterpret_cast<bf16*>(h));
+    NS_CUDA(launch_pdl(embed_kernel<bf16>, dim3(B * L), dim3(128), 0, st, L, d, ids, reinterpret_cast<const bf16*>(E), reinterpret_cast<const bf16*>(P), pos0,
+                       reinterpret_cast<bf16*>(h)));
   else
-    embed_kernel<float><<<B * L, 128, 0, st>>>(L, d, ids, reinterpret_cast<const float*>(E), reinterpret_cast<const float*>(P), pos0, reinterpret_cast<float*>(h));
+    NS_CUDA(launch_pdl(embed_kernel<float>, dim3(B * L), dim3(128), 0, st, L, d, ids, reinterpret_cast<const float*>(E), reinterpret_cast<const float*>(P), pos0,
+                       reinterpret_cast<float*>(h)));
   NS_LAUNCH_CHECK();
   count(C_OTHER);
   return NS_OK;
@@ -818,14 +858,17 @@ int ns_cross_entropy(int dtype, long long rows, int V, long long ld, void* logit
 }
 
 int ns_greedy_pick(int dtype, int B, int V, long long ld, const void* logits, const int* suppress, int n_suppress, int eos,
-                   int pad, unsigned char* finished, long long* next_ids, void* stream) {
+                   int pad, unsigned char* finished, long long* next_ids, long long* out, long long out_ld, void* stream) {
   NS_CHECK_ARG(valid_dtype(dtype) && B >= 0 && V > 0 && ld >= V && logits && next_ids && (n_suppress == 0 || suppress), "ns_greedy_pick: bad arguments");
+  NS_CHECK_ARG(n_suppress >= 0 && n_suppress <= kMaxSuppress, "ns_greedy_pick: at most %d suppressed ids", kMaxSuppress);
   if (B == 0) return NS_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (dtype == NS_BF16)
-    greedy_kernel<bf16><<<B, 512, 0, st>>>(V, ld, reinterpret_cast<const bf16*>(logits), suppress, n_suppress, eos, pad, finished, next_ids);
+    NS_CUDA(launch_pdl(greedy_kernel<bf16>, dim3(B), dim3(512), 0, st, V, ld, reinterpret_cast<const bf16*>(logits), suppress, n_suppress, eos, pad,
+                       finished, next_ids, out, out_ld));
   else
-    greedy_kernel<float><<<B, 512, 0, st>>>(V, ld, reinterpret_cast<const float*>(logits), suppress, n_suppress, eos, pad, finished, next_ids);
+    NS_CUDA(launch_pdl(greedy_kernel<float>, dim3(B), dim3(512), 0, st, V, ld, reinterpret_cast<const float*>(logits), suppress, n_suppress, eos, pad,
+                       finished, next_ids, out, out_ld));
   NS_LAUNCH_CHECK();
   count(C_OTHER);
   return NS_OK;

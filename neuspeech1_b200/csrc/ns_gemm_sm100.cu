@@ -298,6 +298,7 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();     // ns_set_pdl: the next kernel may start its own prologue now
   // Work units.  CG = 1: one 128-row tile per CTA per step.  CG = 2: the pair walks "super tiles" of two consecutive row
   // tiles (same column tile); this CTA takes row tile 2 * pair_index + rank.  An odd row-tile count leaves one phantom tile
   // whose loads are all out of range (zero fill) and whose stores are clipped.
@@ -354,6 +355,7 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();   // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
+  pdl_wait();                  // everything above touched shared / tensor memory only; global memory from here on
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   // warps 0..3 (TMA, MMA, TMEM owner, idle) give registers to the two epilogue warpgroups; the setmaxnreg sits inside
@@ -1096,13 +1098,20 @@ static int launch_nt(const Maps& maps, TileProg& prog, cudaStream_t st) {
   cfg.blockDim = dim3(kNtThreads);
   cfg.dynamicSmemBytes = Cfg::smem_bytes(prog.stages, prog.staging_tiles);
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
+  int na = 0;
   if (CG == 2) {
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
   }
+  if (g_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
   if (PM && !(prog.epi_mode == 1 || prog.epi_mode == 4)) {
     set_error("ns_gemm_nt: the dropout-masked second product supports plain and NS_ACT_DGELU epilogues with bf16 TMA tiles only");
     return NS_ERR_UNSUPPORTED;

@@ -27,6 +27,7 @@ from . import ops
 from ._abi import ACT_DGELU, ACT_GELU, ACT_NONE, NS_BF16, NS_F32
 
 _NO_TRAIN_GRAPH = bool(os.environ.get("NS_NO_TRAIN_GRAPH"))     # developer switch: launch every kernel of train_step one by one
+_NO_PDL = bool(os.environ.get("NS_NO_PDL"))                     # developer A/B switch: plain stream-ordered launches in the decode loop
 _NO_AR_OVERLAP = bool(os.environ.get("NS_NO_AR_OVERLAP"))       # developer A/B switch: one all-reduce after the whole backward
 _NO_MASK_STAGE = bool(os.environ.get("NS_NO_MASK_STAGE"))       # developer A/B switch: mma.sync ns_lora_down / ns_lora_da instead of the mask stages
 _NO_GEMM_MASK = bool(os.environ.get("NS_NO_GEMM_MASK"))         # developer A/B switch: dropout correction pass instead of the masked GEMM product
@@ -1100,12 +1101,22 @@ class WhisperEEGEngine:
         def decode_step(step: int, ids: torch.Tensor, pos: int):
             """One decoder pass over `ids` (B, Lq) at cache position `pos` -> next token in `nxt`, appended to out[:, step]."""
             self._decode_logits(ids, pos, cache, kv_all, logits, Tmax)
-            ops.greedy_pick(logits, dm.vocab, self.suppress if step == 0 else None, dm.eos_token_id, dm.pad_token_id, finished, nxt)
-            out[:, step].copy_(nxt)
+            ops.greedy_pick(logits, dm.vocab, self.suppress if step == 0 else None, dm.eos_token_id, dm.pad_token_id, finished, nxt,
+                            out_col=out[:, step])
 
         # The ~150 launches of a decode step are latency-bound at M = B: each step is captured once into a CUDA graph (keyed by
         # batch / prompt length / position, all buffers live in the persistent workspace) and replayed afterwards.
         graphs = self._decode_graphs if use_graphs else None
+        pos = 0
+        # programmatic dependent launch: every kernel of a step starts its prologue under the tail of the one before it
+        pdl_prev = ops.set_pdl(not _NO_PDL)
+        try:
+            return self._greedy_loop(decode_step, graphs, n_new, B, Tmax, L0, ids0, nxt, finished, out, eos_check_every)
+        finally:
+            ops.set_pdl(pdl_prev)
+
+    def _greedy_loop(self, decode_step, graphs, n_new, B, Tmax, L0, ids0, nxt, finished, out, eos_check_every):
+        ws = self.ws
         pos = 0
         for step in range(n_new):
             ids = ids0 if step == 0 else nxt.view(B, 1)

@@ -32,7 +32,8 @@ def profile_end():
     return [dict(name=n, flops=f, bytes=b, ms=s.elapsed_time(e)) for (n, f, b, s, e) in rec]
 
 
-def _call(name, work, *args):
+def _call(name, work, *args, tag=None):
+    """tag: name the launch is filed under by the profiler (default: the entry point)."""
     fn = _fn_cache.get(name)
     if fn is None:
         fn = _fn_cache[name] = getattr(lib(), name)
@@ -43,7 +44,7 @@ def _call(name, work, *args):
         s.record()
         st = fn(*args)
         e.record()
-        _prof.append((name, float(work[0]), float(work[1]), s, e))
+        _prof.append((tag or name, float(work[0]), float(work[1]), s, e))
     if st != 0:
         check(st, name)
 
@@ -96,9 +97,12 @@ def gemm_nt(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, ep: Optional[Ep
     N = w.shape[0] if N is None else N
     if ep is None:
         ep = epilogue(out_dtype=ns_dtype(out))
-    _call("ns_gemm_nt", (2.0 * M * N * (K + k2), 0), ns_dtype(a), M, N, K, _p(a), a.stride(0), _p(w), w.stride(0), _p(out),
-          out.stride(0), C.byref(ep), _p(a2), a2.stride(0) if a2 is not None else 0, _p(w2),
-          w2.stride(0) if w2 is not None else 0, k2, _stream())
+    # the profiler files the rank-r products (N <= 96: t = x A^T, dt = g B; 32-wide kernel, bound by the read of the activation)
+    # apart from the dense products (256 / 128-wide kernels, tensor bound): different kernels, different rooflines
+    thin = N <= 96
+    _call("ns_gemm_nt", (2.0 * M * N * (K + k2), (M * K + M * N) * float(a.element_size()) if thin else 0), ns_dtype(a), M, N, K, _p(a),
+          a.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), C.byref(ep), _p(a2), a2.stride(0) if a2 is not None else 0, _p(w2),
+          w2.stride(0) if w2 is not None else 0, k2, _stream(), tag="ns_gemm_nt.rank_r" if thin else None)
     return out
 
 
@@ -195,10 +199,17 @@ def cross_entropy(logits, V: int, labels, row_loss, loss_sum, n_valid, write_gra
     _call("ns_cross_entropy", (0, (3.0 if write_grad else 2.0) * logits.numel() * logits.element_size()), ns_dtype(logits), rows, V, logits.stride(0), _p(logits), _p(labels), _p(row_loss), _p(loss_sum), _p(n_valid), int(write_grad), grad_scale, _stream())
 
 
-def greedy_pick(logits, V: int, suppress, eos: int, pad: int, finished, next_ids):
+def greedy_pick(logits, V: int, suppress, eos: int, pad: int, finished, next_ids, out_col=None):
+    """out_col: a column view sequences[:, step] (int64) that receives the picked token as well."""
     n_sup = 0 if suppress is None else suppress.numel()
-    _call("ns_greedy_pick", (0, 0), ns_dtype(logits), logits.shape[0], V, logits.stride(0), _p(logits), _p(suppress), n_sup, eos, pad, _p(finished), _p(next_ids), _stream())
+    _call("ns_greedy_pick", (0, 0), ns_dtype(logits), logits.shape[0], V, logits.stride(0), _p(logits), _p(suppress), n_sup, eos, pad, _p(finished),
+          _p(next_ids), _p(out_col), out_col.stride(0) if out_col is not None else 0, _stream())
     return next_ids
+
+
+def set_pdl(on: bool) -> bool:
+    """Programmatic dependent launch for this thread's decoder-step kernels (include/neuspeech_b200.h ns_set_pdl)."""
+    return bool(lib().ns_set_pdl(1 if on else 0))
 
 
 def cast(src, dst):

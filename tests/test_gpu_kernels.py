@@ -210,6 +210,54 @@ def test_mask_stage_down_and_da(M, K, G):
     assert torch.equal(x, rnd(M, K, dtype=torch.bfloat16, seed=2))            # the mask is applied in shared memory, never to x
 
 
+def test_programmatic_dependent_launch_chain_is_race_free():
+    """ns_set_pdl(1): the decoder-step kernels are launched with the programmatic-stream-serialization attribute and wait
+    (griddepcontrol.wait) before touching global memory.  A dependent chain LN -> GEMM(+bias, residual) -> single-query attention
+    -> LN -> GEMM -> greedy pick, each kernel consuming the previous one's output in place, must give bit-identical results with
+    and without it, eagerly and replayed from a CUDA graph, every time."""
+    B, d, H, Lk, V = 128, 512, 8, 200, 4000
+    x = rnd(B, d, dtype=torch.bfloat16, seed=1)
+    g = torch.ones(d, device=DEV); bta = torch.zeros(d, device=DEV)
+    w = rnd(3 * d, d, dtype=torch.bfloat16, scale=d ** -0.5, seed=2); bias = rnd(3 * d, seed=3)
+    wo = rnd(d, d, dtype=torch.bfloat16, scale=d ** -0.5, seed=4)
+    E = rnd(V, d, dtype=torch.bfloat16, scale=0.05, seed=5)
+    cache = rnd(B, Lk, 3 * d, dtype=torch.bfloat16, seed=6)
+    shp = ops.attn_shape(B, H, 1, Lk, d // H, True, Lk * 3 * d, 3 * d, Lk * 3 * d, 3 * d, Lk * 3 * d, 3 * d, d, d)
+    u = torch.empty_like(x); o = torch.empty_like(x); h1 = torch.empty_like(x); y = torch.empty_like(x)
+    logits = torch.empty(B, V, dtype=torch.bfloat16, device=DEV)
+    nxt = torch.zeros(B, dtype=torch.long, device=DEV); fin = torch.zeros(B, dtype=torch.uint8, device=DEV)
+    seqs = torch.zeros(B, 4, dtype=torch.long, device=DEV)
+    sup = torch.tensor([7, 1999], dtype=torch.int32, device=DEV)
+
+    def chain():
+        ops.layernorm_fwd(x, g, bta, u)
+        ops.gemm_nt(u, w, cache[:, Lk - 1], ops.epilogue(bias=bias, alpha=0.125, alpha_cols=d))
+        ops.attention_fwd(shp, cache[:, Lk - 1:], cache[:, :, d:], cache[:, :, 2 * d:], o)
+        ops.gemm_nt(o, wo, h1, ops.epilogue(residual=x, ldr=d))
+        ops.layernorm_fwd(h1, g, bta, y)
+        ops.gemm_nt(y, E, logits, ops.epilogue(), N=V)
+        ops.greedy_pick(logits, V, sup, 3999, 3998, fin, nxt, out_col=seqs[:, 2])
+
+    chain(); torch.cuda.synchronize()
+    ref_logits, ref_next = logits.clone(), nxt.clone()
+    assert torch.equal(seqs[:, 2], ref_next) and torch.equal(ref_next, logits.float().index_fill(1, sup.long(), -float("inf")).argmax(-1))
+    prev = ops.set_pdl(True)
+    try:
+        for _ in range(10):
+            logits.zero_(); nxt.zero_(); o.zero_(); h1.zero_()
+            chain(); torch.cuda.synchronize()
+            assert torch.equal(logits, ref_logits) and torch.equal(nxt, ref_next)
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            chain()
+        for _ in range(10):
+            logits.zero_(); nxt.zero_()
+            gr.replay(); torch.cuda.synchronize()
+            assert torch.equal(logits, ref_logits) and torch.equal(nxt, ref_next)
+    finally:
+        ops.set_pdl(prev)
+
+
 def test_gemm_nt_simt_equals_fast():
     M, N, K = 500, 768, 512
     a = rnd(M, K, dtype=torch.bfloat16, seed=1); w = rnd(N, K, dtype=torch.bfloat16, scale=K ** -0.5, seed=2)
