@@ -918,6 +918,20 @@ class WhisperEEGEngine:
         self._packed = False
         return loss.clone()
 
+    def _cross_kv_per_layer(self, enc: torch.Tensor, B: int) -> torch.Tensor:
+        """Cross-attention K|V for the decode loops as (N_dec, B*S, 2d): layer i's keys and values of one source position are
+        2 KB contiguous and consecutive positions follow each other, so the single-query attention of a (sample, layer)
+        streams one 3 MB run.  (The training step keeps all layers in one (B*S, N_dec*2d) matrix from one GEMM: there the
+        1500-query tiles reuse K/V from L2 and a key's row stride does not matter; in the decode step it is the whole cost --
+        2.36 GB per position at B = 128 -- and 128-byte pieces 12 KB apart reached 70 % of the copy bandwidth.)"""
+        dm, W, ws, dt = self.dims, self.P, self.ws, self.dtype
+        d, S = dm.d_model, dm.max_source_positions
+        kv = ws.get("kv_layers", (dm.dec_layers, B * S, 2 * d), dt)
+        x = enc.view(B * S, d)
+        for i in range(dm.dec_layers):
+            ops.gemm_nt(x, W["dec.wkv"][i * 2 * d:(i + 1) * 2 * d], kv[i], self._ep(bias=W["dec.bkv"][i * 2 * d:(i + 1) * 2 * d]))
+        return kv
+
     # ------------------------------------------------------------------ one decoder pass with KV cache
     def _decode_logits(self, ids: torch.Tensor, pos: int, cache, kv_all: torch.Tensor, logits: torch.Tensor, Tmax: int,
                        beams: int = 1, kv_rows: Optional[torch.Tensor] = None):
@@ -963,8 +977,12 @@ class WhisperEEGEngine:
             qc = ws.get(f"g_qc.{tag}", (MLq, d), dt)
             ops.gemm_nt(u, W[k + ".wqc"], qc, self._ep(bias=W[k + ".bqc"], alpha=Dh ** -0.5, alpha_cols=d))
             Lc = beams * Lq
-            shp_c = ops.attn_shape(B // beams, H, Lc, S, Dh, False, Lc * d, d, S * nkv, nkv, S * nkv, nkv, Lc * d, d)
-            ops.attention_fwd(shp_c, qc, kv_all[:, i * 2 * d:], kv_all[:, i * 2 * d + d:], o)
+            if kv_all.dim() == 3:                                    # per-layer (N_dec, B*S, 2d) from _cross_kv_per_layer
+                shp_c = ops.attn_shape(B // beams, H, Lc, S, Dh, False, Lc * d, d, S * 2 * d, 2 * d, S * 2 * d, 2 * d, Lc * d, d)
+                ops.attention_fwd(shp_c, qc, kv_all[i], kv_all[i][:, d:], o)
+            else:
+                shp_c = ops.attn_shape(B // beams, H, Lc, S, Dh, False, Lc * d, d, S * nkv, nkv, S * nkv, nkv, Lc * d, d)
+                ops.attention_fwd(shp_c, qc, kv_all[:, i * 2 * d:], kv_all[:, i * 2 * d + d:], o)
             h2 = ws.get(f"g_h2.{tag}", (MLq, d), dt)
             ops.gemm_nt(o, W[k + ".woc"], h2, self._ep(bias=W[k + ".boc"], residual=h1, ldr=d))
             ops.layernorm_fwd(h2, W[k + ".ln3.g"], W[k + ".ln3.b"], u)
@@ -1000,8 +1018,7 @@ class WhisperEEGEngine:
             raise ValueError(f"max_length {max_length} exceeds max_target_positions {dm.max_target_positions}")
         enc = self.encode(x, aug=aug, save=False)
         nkv = dm.dec_layers * 2 * d
-        kv_all = ws.get("kv_all", (B * S, nkv), dt)
-        ops.gemm_nt(enc.view(B * S, d), W["dec.wkv"], kv_all, self._ep(bias=W["dec.bkv"]))
+        kv_all = self._cross_kv_per_layer(enc, B)
         if prompt is None:
             prompt = torch.full((B, 1), dm.decoder_start_token_id, dtype=torch.long, device=self.device)
         prompt = prompt.to(self.device, torch.long).contiguous()
@@ -1077,8 +1094,7 @@ class WhisperEEGEngine:
         B = x.shape[0]
         enc = self.encode(x, aug=aug, save=False)
         nkv = dm.dec_layers * 2 * d
-        kv_all = ws.get("kv_all", (B * S, nkv), dt)
-        ops.gemm_nt(enc.view(B * S, d), W["dec.wkv"], kv_all, self._ep(bias=W["dec.bkv"]))
+        kv_all = self._cross_kv_per_layer(enc, B)
         if prompt is None:
             prompt = torch.full((B, 1), dm.decoder_start_token_id, dtype=torch.long, device=self.device)
         prompt = prompt.to(self.device, torch.long).contiguous()

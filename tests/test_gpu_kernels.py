@@ -239,19 +239,20 @@ def test_programmatic_dependent_launch_chain_is_race_free():
         ops.greedy_pick(logits, V, sup, 3999, 3998, fin, nxt, out_col=seqs[:, 2])
 
     chain(); torch.cuda.synchronize()
+    fin.zero_()
     ref_logits, ref_next = logits.clone(), nxt.clone()
     assert torch.equal(seqs[:, 2], ref_next) and torch.equal(ref_next, logits.float().index_fill(1, sup.long(), -float("inf")).argmax(-1))
     prev = ops.set_pdl(True)
     try:
         for _ in range(10):
-            logits.zero_(); nxt.zero_(); o.zero_(); h1.zero_()
+            logits.zero_(); nxt.zero_(); o.zero_(); h1.zero_(); fin.zero_()
             chain(); torch.cuda.synchronize()
             assert torch.equal(logits, ref_logits) and torch.equal(nxt, ref_next)
         gr = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gr):
             chain()
         for _ in range(10):
-            logits.zero_(); nxt.zero_()
+            logits.zero_(); nxt.zero_(); fin.zero_()
             gr.replay(); torch.cuda.synchronize()
             assert torch.equal(logits, ref_logits) and torch.equal(nxt, ref_next)
     finally:
