@@ -162,6 +162,34 @@ int ns_greedy_pick(int dtype, int B, int V, long long ld, const void* logits, co
                    int eos, int pad, unsigned char* finished, long long* next_ids, long long* out, long long out_ld,
                    void* stream);
 
+/* ---- the decode loop in two calls (SURVEY.md 8b decode_prefill / decode_step; utils/load_model.py:1072-1351, :1332-1351
+ *  prepare_inputs_for_generation feeds the last token only; HF modeling_whisper.py:314-336 KV cache).
+ *  ns_decode_prefill: cross-attention K|V of every decoder layer from the encoder output, enc (B*S, d) -> layers[i].cross_kv.
+ *  ns_decode_step   : ONE decoder pass for the token ids[b] at cache position pos (embedding + positions, per layer
+ *                     LN -> q|k|v written into self_cache[:, pos] -> single-query self-attention -> out_proj + residual -> LN ->
+ *                     cross-attention over cross_kv -> out_proj + residual -> LN -> fc1 + GELU -> fc2 + residual; final LN, tied
+ *                     vocabulary projection) followed by the greedy pick (ns_greedy_pick semantics).  About 70 kernel launches
+ *                     issued back to back from C++; nothing is allocated, every buffer is the caller's. */
+typedef struct {
+  const float* ln1_g; const float* ln1_b; const void* wqkv; const float* bqkv; const void* wo; const float* bo;
+  const float* ln2_g; const float* ln2_b; const void* wqc; const float* bqc; const void* woc; const float* boc;
+  const float* ln3_g; const float* ln3_b; const void* w1; const float* b1; const void* w2; const float* b2;
+  const void* wkv; const float* bkv;   /* (2d, d) / (2d): cross K|V projection of this layer (prefill) */
+  void* self_cache;                    /* (B, Tmax, 3d): q|k|v rows of this layer */
+  void* cross_kv;                      /* (B*S, cross_ld >= 2d): K|V of the encoder output */
+} ns_decoder_layer;
+typedef struct {
+  int dtype, n_layers, d, heads, ffn, vocab, S, Tmax, B, logits_dtype;
+  long long cross_ld, logits_ld;
+  const void* E; const void* pos_table; const float* lnf_g; const float* lnf_b;
+  const ns_decoder_layer* layers;      /* host array of n_layers entries */
+  void* h0; void* u; void* o; void* h1; void* qc; void* h2; void* mm; void* h3a; void* h3b; void* y;   /* (B, d) scratch; mm (B, ffn) */
+  void* logits;                        /* (B, logits_ld) */
+} ns_decoder;
+int ns_decode_prefill(const ns_decoder* dec, const void* enc, void* stream);
+int ns_decode_step(const ns_decoder* dec, const long long* ids, int pos, const int* suppress, int n_suppress, int eos, int pad,
+                   unsigned char* finished, long long* next_ids, long long* out, long long out_ld, void* stream);
+
 /* ---- EEG augmentation + pad + cast + layout pass (utils/reader.py:552-594, :496-506; utils/augment_eeg.py:15-26,54-56;
  *  utils/utils.py:33-60).  One read of x, one write of y.  x is either the collator's dense (B,C,Tin) batch (src_off NULL) or a
  *  RAGGED SAMPLE STORE resident in HBM (utils/reader.py:253-303 keeps recordings as unpadded .npy files): channel row c of

@@ -28,6 +28,18 @@ class Epilogue(C.Structure):
                 ("drop_gstride", c_ll)]
 
 
+class DecoderLayer(C.Structure):
+    _fields_ = [(n, c_vp) for n in ("ln1_g", "ln1_b", "wqkv", "bqkv", "wo", "bo", "ln2_g", "ln2_b", "wqc", "bqc", "woc", "boc",
+                                    "ln3_g", "ln3_b", "w1", "b1", "w2", "b2", "wkv", "bkv", "self_cache", "cross_kv")]
+
+
+class Decoder(C.Structure):
+    _fields_ = [(n, c_i) for n in ("dtype", "n_layers", "d", "heads", "ffn", "vocab", "S", "Tmax", "B", "logits_dtype")] + \
+               [("cross_ld", c_ll), ("logits_ld", c_ll), ("E", c_vp), ("pos_table", c_vp), ("lnf_g", c_vp), ("lnf_b", c_vp),
+                ("layers", C.POINTER(DecoderLayer))] + \
+               [(n, c_vp) for n in ("h0", "u", "o", "h1", "qc", "h2", "mm", "h3a", "h3b", "y", "logits")]
+
+
 class AttnShape(C.Structure):
     _fields_ = [("B", c_i), ("H", c_i), ("Lq", c_i), ("Lk", c_i), ("Dh", c_i), ("causal", c_i),
                 ("q_bs", c_ll), ("q_rs", c_ll), ("k_bs", c_ll), ("k_rs", c_ll), ("v_bs", c_ll), ("v_rs", c_ll),
@@ -69,6 +81,8 @@ SIGNATURES = {
     "ns_cross_entropy": [c_i, c_ll, c_i, c_ll, c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_f, c_vp],
     "ns_greedy_pick": [c_i, c_i, c_i, c_ll, c_vp, c_vp, c_i, c_i, c_i, c_vp, c_vp, c_vp, c_ll, c_vp],
     "ns_set_pdl": [c_i],
+    "ns_decode_prefill": [C.POINTER(Decoder), c_vp, c_vp],
+    "ns_decode_step": [C.POINTER(Decoder), c_vp, c_i, c_vp, c_i, c_i, c_i, c_vp, c_vp, c_vp, c_ll, c_vp],
     "ns_aug_pass": [C.POINTER(AugArgs), c_vp, c_vp, c_vp],
     "ns_channel_meansq": [c_i, c_i, c_i, c_i, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "ns_cast": [c_i, c_i, c_ll, c_vp, c_vp, c_vp],

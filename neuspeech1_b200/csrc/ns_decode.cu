@@ -1,0 +1,93 @@
+// Native decode loop body (decode_prefill / decode_step).  utils/load_model.py:1072-1351 -> GenerationMixin greedy:
+// the reference spends one Python-dispatched ATen call per op and position; here a position is ONE C call that launches the
+// ~70 kernels of the decoder pass + the greedy pick back to back from C++ (about 2 us of host time per launch: the host stays
+// ahead of the ~0.9 ms of device time per position, so no CUDA graph per position is needed to keep the GPU busy).
+#include "ns_common.cuh"
+
+using namespace ns;
+
+extern "C" {
+
+static ns_epilogue plain_epi(int dtype) {
+  ns_epilogue e;
+  memset(&e, 0, sizeof(e));
+  e.alpha = 1.0f;
+  e.out_dtype = dtype;
+  return e;
+}
+
+#define NS_TRY(expr)            \
+  do {                          \
+    const int _r = (expr);      \
+    if (_r != NS_OK) return _r; \
+  } while (0)
+
+int ns_decode_prefill(const ns_decoder* dec, const void* enc, void* stream) {
+  NS_CHECK_ARG(dec && enc && dec->layers && dec->n_layers > 0, "ns_decode_prefill: null argument");
+  const int d = dec->d;
+  const long long M = static_cast<long long>(dec->B) * dec->S;
+  for (int i = 0; i < dec->n_layers; ++i) {
+    const ns_decoder_layer& L = dec->layers[i];
+    NS_CHECK_ARG(L.wkv && L.cross_kv, "ns_decode_prefill: layer %d has no cross K/V weights / buffer", i);
+    ns_epilogue e = plain_epi(dec->dtype);
+    e.bias = L.bkv;
+    NS_TRY(ns_gemm_nt(dec->dtype, M, 2 * d, d, enc, d, L.wkv, d, L.cross_kv, dec->cross_ld, &e, nullptr, 0, nullptr, 0, 0, stream));
+  }
+  return NS_OK;
+}
+
+int ns_decode_step(const ns_decoder* dec, const long long* ids, int pos, const int* suppress, int n_suppress, int eos, int pad,
+                   unsigned char* finished, long long* next_ids, long long* out, long long out_ld, void* stream) {
+  NS_CHECK_ARG(dec && ids && next_ids && dec->layers && dec->n_layers > 0, "ns_decode_step: null argument");
+  NS_CHECK_ARG(pos >= 0 && pos < dec->Tmax, "ns_decode_step: position %d outside the cache (Tmax %d)", pos, dec->Tmax);
+  NS_CHECK_ARG(dec->d % dec->heads == 0, "ns_decode_step: d_model %d not divisible by %d heads", dec->d, dec->heads);
+  const int dt = dec->dtype, B = dec->B, d = dec->d, H = dec->heads, F = dec->ffn, S = dec->S, Tmax = dec->Tmax;
+  const int Dh = d / H;
+  const float qscale = 1.0f / sqrtf(static_cast<float>(Dh));
+  const size_t es = dsize(dt);
+  NS_TRY(ns_embed(dt, B, 1, d, ids, dec->E, dec->pos_table, pos, dec->h0, stream));
+  const void* hd = dec->h0;
+  ns_attn_shape ss{B, H, 1, pos + 1, Dh, 1, (long long)Tmax * 3 * d, 3LL * d, (long long)Tmax * 3 * d, 3LL * d, (long long)Tmax * 3 * d, 3LL * d, d, d};
+  ns_attn_shape sc{B, H, 1, S, Dh, 0, d, d, (long long)S * dec->cross_ld, dec->cross_ld, (long long)S * dec->cross_ld, dec->cross_ld, d, d};
+  for (int i = 0; i < dec->n_layers; ++i) {
+    const ns_decoder_layer& L = dec->layers[i];
+    char* cache = static_cast<char*>(L.self_cache);
+    char* row = cache + static_cast<size_t>(pos) * 3 * d * es;          // (b, pos, :) = row + b * Tmax * 3d
+    // self-attention: q|k|v of the new token go straight into the cache row (HF modeling_whisper.py:314-336)
+    NS_TRY(ns_layernorm_fwd(dt, B, d, hd, L.ln1_g, L.ln1_b, dec->u, nullptr, nullptr, 1e-5f, stream));
+    ns_epilogue e = plain_epi(dt);
+    e.bias = L.bqkv; e.alpha = qscale; e.alpha_cols = d;
+    NS_TRY(ns_gemm_nt(dt, B, 3 * d, d, dec->u, d, L.wqkv, d, row, (long long)Tmax * 3 * d, &e, nullptr, 0, nullptr, 0, 0, stream));
+    NS_TRY(ns_attention_fwd(dt, &ss, row, cache + static_cast<size_t>(d) * es, cache + static_cast<size_t>(2 * d) * es, dec->o, nullptr, stream));
+    e = plain_epi(dt);
+    e.bias = L.bo; e.residual = hd; e.ldr = d;
+    NS_TRY(ns_gemm_nt(dt, B, d, d, dec->o, d, L.wo, d, dec->h1, d, &e, nullptr, 0, nullptr, 0, 0, stream));
+    // cross-attention over the precomputed K|V of this layer
+    NS_TRY(ns_layernorm_fwd(dt, B, d, dec->h1, L.ln2_g, L.ln2_b, dec->u, nullptr, nullptr, 1e-5f, stream));
+    e = plain_epi(dt);
+    e.bias = L.bqc; e.alpha = qscale; e.alpha_cols = d;
+    NS_TRY(ns_gemm_nt(dt, B, d, d, dec->u, d, L.wqc, d, dec->qc, d, &e, nullptr, 0, nullptr, 0, 0, stream));
+    const char* ckv = static_cast<const char*>(L.cross_kv);
+    NS_TRY(ns_attention_fwd(dt, &sc, dec->qc, ckv, ckv + static_cast<size_t>(d) * es, dec->o, nullptr, stream));
+    e = plain_epi(dt);
+    e.bias = L.boc; e.residual = dec->h1; e.ldr = d;
+    NS_TRY(ns_gemm_nt(dt, B, d, d, dec->o, d, L.woc, d, dec->h2, d, &e, nullptr, 0, nullptr, 0, 0, stream));
+    // MLP
+    NS_TRY(ns_layernorm_fwd(dt, B, d, dec->h2, L.ln3_g, L.ln3_b, dec->u, nullptr, nullptr, 1e-5f, stream));
+    e = plain_epi(dt);
+    e.bias = L.b1; e.act = NS_ACT_GELU;
+    NS_TRY(ns_gemm_nt(dt, B, F, d, dec->u, d, L.w1, d, dec->mm, F, &e, nullptr, 0, nullptr, 0, 0, stream));
+    void* hn = (i & 1) ? dec->h3b : dec->h3a;
+    e = plain_epi(dt);
+    e.bias = L.b2; e.residual = dec->h2; e.ldr = d;
+    NS_TRY(ns_gemm_nt(dt, B, d, F, dec->mm, F, L.w2, F, hn, d, &e, nullptr, 0, nullptr, 0, 0, stream));
+    hd = hn;
+  }
+  NS_TRY(ns_layernorm_fwd(dt, B, d, hd, dec->lnf_g, dec->lnf_b, dec->y, nullptr, nullptr, 1e-5f, stream));
+  ns_epilogue e = plain_epi(dec->logits_dtype);
+  NS_TRY(ns_gemm_nt(dt, B, dec->vocab, d, dec->y, d, dec->E, d, dec->logits, dec->logits_ld, &e, nullptr, 0, nullptr, 0, 0, stream));
+  return ns_greedy_pick(dec->logits_dtype, B, dec->vocab, dec->logits_ld, dec->logits, suppress, n_suppress, eos, pad, finished, next_ids, out, out_ld,
+                        stream);
+}
+
+}  // extern "C"

@@ -259,7 +259,7 @@ class WhisperEEGEngine:
         bits = self._bits(layer, targets, M, K)
         if dx is None and G == 1 and self.use_lora_kernels and K % 64 == 0 and not _NO_MASK_STAGE:
             ops.gemm_tn_masked(x, dt, gA, 1, K, bits[0])          # split-K tcgen05 wgrad, x masked in shared memory
-        elif self._fast_lora(K, G):
+        elif self.use_lora_kernels and K % 64 == 0 and r in (8, 16, 32):     # (ns_lora_da keeps A^T in registers: no K limit)
             ops.lora_da(x, dt, gA, G, bits, dx=dx, At=At if dx is not None else None, z=z if dx is not None else None)
         else:
             xm = self.ws.get(f"xm.{K}", x.shape, self.dtype)
@@ -918,6 +918,38 @@ class WhisperEEGEngine:
         self._packed = False
         return loss.clone()
 
+    def _native_decoder(self, B: int, Tmax: int, cache, kv_layers: torch.Tensor, logits: torch.Tensor):
+        """The `ns_decoder` argument block of ns_decode_prefill / ns_decode_step for this batch shape: pointers into the weight
+        table, the self-attention cache, the per-layer cross K|V and persistent scratch.  Cached per (B, Tmax) while the
+        workspace and the weights stay in place."""
+        from . import _abi
+        dm, W, ws, dt = self.dims, self.P, self.ws, self.dtype
+        d, F = dm.d_model, dm.dec_ffn
+        key = (B, Tmax)
+        p = lambda t: t.data_ptr()
+        tag = f"nd.{B}"
+        buf = lambda n, cols=d: ws.get(f"{tag}.{n}", (B, cols), dt)
+        sc = [buf("h0"), buf("u"), buf("o"), buf("h1"), buf("qc"), buf("h2"), buf("mm", F), buf("h3a"), buf("h3b"), buf("y")]
+        stamp = (ws.gen, self._weights_version, tuple(p(c) for c in cache), p(kv_layers), p(logits))
+        ent = self.__dict__.setdefault("_native_dec", {}).get(key)
+        if ent is not None and ent[0] == stamp:
+            return ent[1]
+        layers = (_abi.DecoderLayer * dm.dec_layers)()
+        keep = []
+        for i in range(dm.dec_layers):
+            k = f"dec{i}"
+            wkv = W["dec.wkv"][i * 2 * d:(i + 1) * 2 * d]; bkv = W["dec.bkv"][i * 2 * d:(i + 1) * 2 * d]
+            keep += [wkv, bkv]
+            layers[i] = _abi.DecoderLayer(p(W[k + ".ln1.g"]), p(W[k + ".ln1.b"]), p(W[k + ".wqkv"]), p(W[k + ".bqkv"]), p(W[k + ".wo"]),
+                                          p(W[k + ".bo"]), p(W[k + ".ln2.g"]), p(W[k + ".ln2.b"]), p(W[k + ".wqc"]), p(W[k + ".bqc"]),
+                                          p(W[k + ".woc"]), p(W[k + ".boc"]), p(W[k + ".ln3.g"]), p(W[k + ".ln3.b"]), p(W[k + ".w1"]),
+                                          p(W[k + ".b1"]), p(W[k + ".w2"]), p(W[k + ".b2"]), p(wkv), p(bkv), p(cache[i]), p(kv_layers[i]))
+        dec = _abi.Decoder(self.ns, dm.dec_layers, d, dm.dec_heads, F, dm.vocab, dm.max_source_positions, Tmax, B, ops.ns_dtype(logits),
+                           kv_layers.stride(1), logits.stride(0), p(W["dec.E"]), p(W["dec.pos"]), p(W["dec.lnf.g"]), p(W["dec.lnf.b"]),
+                           layers, *[p(t) for t in sc], p(logits))
+        self._native_dec[key] = (stamp, dec, layers, keep, sc)
+        return dec
+
     def _cross_kv_per_layer(self, enc: torch.Tensor, B: int) -> torch.Tensor:
         """Cross-attention K|V for the decode loops as (N_dec, B*S, 2d): layer i's keys and values of one source position are
         2 KB contiguous and consecutive positions follow each other, so the single-query attention of a (sample, layer)
@@ -1017,84 +1049,6 @@ class WhisperEEGEngine:
         if max_length > dm.max_target_positions:
             raise ValueError(f"max_length {max_length} exceeds max_target_positions {dm.max_target_positions}")
         enc = self.encode(x, aug=aug, save=False)
-        nkv = dm.dec_layers * 2 * d
-        kv_all = self._cross_kv_per_layer(enc, B)
-        if prompt is None:
-            prompt = torch.full((B, 1), dm.decoder_start_token_id, dtype=torch.long, device=self.device)
-        prompt = prompt.to(self.device, torch.long).contiguous()
-        L0 = prompt.shape[1]
-        N = B * K
-        cache = [ws.get(f"bs_qkv.{K}.{i}", (N, max_length, 3 * d), dt) for i in range(dm.dec_layers)]
-        logits = ws.get(f"bs_logits.{K}", (N, dm.Vp), torch.float32 if dt == torch.float32 else dt)
-        # cache-row table: position j of logical row r was written by (and still sits in) physical row rows[r, j]
-        rows = ws.get(f"bs_rows.{K}", (N, max_length), torch.int32)
-        rows.copy_(torch.arange(N, dtype=torch.int32, device=self.device)[:, None].expand(N, max_length))
-        ident = ws.get(f"bs_ident.{K}", (N,), torch.int32)
-        ident.copy_(torch.arange(N, dtype=torch.int32, device=self.device))
-        state = {"pos": 0}
-
-        graphs = self._decode_graphs if use_graphs else None
-
-        def step_fn(tokens: torch.Tensor, pos: int) -> torch.Tensor:
-            Lq = tokens.shape[1]
-            ids = ws.get(f"bs_ids.{K}.{Lq}", (N, Lq), torch.long)       # static buffer: the pass below may be a graph replay
-            ids.copy_(tokens)
-            state["pos"] = pos + Lq
-            if graphs is None:
-                self._decode_logits(ids, pos, cache, kv_all, logits, max_length, beams=K, kv_rows=rows)
-                return logits
-            key = ("beam", B, K, max_length, Lq, pos, self._weights_version)
-            ent = graphs.get(key)
-            if ent is None or ent[1] != ws.gen:
-                self._decode_logits(ids, pos, cache, kv_all, logits, max_length, beams=K, kv_rows=rows)   # eager once: sizes the workspace
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._decode_logits(ids, pos, cache, kv_all, logits, max_length, beams=K, kv_rows=rows)
-                graphs[key] = (g, ws.gen)
-            else:
-                ent[0].replay()
-            return logits
-
-        def reorder_fn(beam_idx: torch.Tensor):
-            # positions < pos: inherit the parent's table; the next token's K/V will be written by the row itself
-            p = state["pos"]
-            rows[:, :p] = rows[:, :p].index_select(0, beam_idx)
-
-        scorer = None
-        if not sequence_bias and 2 * K <= 16:
-            C2 = 2 * K
-            rs = ws.get(f"bs_rs.{K}", (N, C2), torch.float32)
-            rt = ws.get(f"bs_rt.{K}", (N, C2), torch.int32)
-
-            def scorer(lg, flat, run_score, first):
-                ops.beam_row_topk(lg, dm.vocab, flat.contiguous(), run_score.reshape(-1).contiguous(), repetition_penalty,
-                                  no_repeat_ngram_size, self.suppress if (first and self.suppress.numel()) else None, C2, rs, rt)
-                top_score, idx = torch.topk(rs.view(B, K * C2), C2, dim=1)
-                return top_score, idx // C2, rt.view(B, K * C2).gather(1, idx).long()
-
-        out = run_beams(step_fn, reorder_fn, prompt, K, max_length, dm.vocab, dm.eos_token_id, dm.pad_token_id,
-                        dm.begin_suppress_tokens, repetition_penalty, no_repeat_ngram_size, length_penalty,
-                        sequence_bias=sequence_bias, scorer=scorer)
-        return out[:, L0:].contiguous()
-
-    # ------------------------------------------------------------------ greedy decode with KV cache
-    @_on_device
-    @torch.no_grad()
-    def greedy(self, x: torch.Tensor, max_length: int, prompt: Optional[torch.Tensor] = None, aug: Optional[dict] = None,
-               use_graphs: bool = True, eos_check_every: int = 16) -> torch.Tensor:
-        """Batched greedy generate (utils/load_model.py:1072-1351 -> GenerationMixin greedy): encoder once, cross-K/V once,
-        then one-token decoder steps against the self-attention cache.  Returns the generated suffix (B, n_new) int64;
-        rows that hit EOS emit pad afterwards; begin_suppress_tokens are masked at the first generated position.  Every
-        `eos_check_every` positions the host looks at the finished flags and stops once every row has emitted EOS (the
-        remaining positions are pad, as HF pads finished rows)."""
-        dm, W, ws, dt = self.dims, self.P, self.ws, self.dtype
-        d, S, F, H = dm.d_model, dm.max_source_positions, dm.dec_ffn, dm.dec_heads
-        Dh = d // H
-        B = x.shape[0]
-        enc = self.encode(x, aug=aug, save=False)
-        nkv = dm.dec_layers * 2 * d
-        kv_all = self._cross_kv_per_layer(enc, B)
         if prompt is None:
             prompt = torch.full((B, 1), dm.decoder_start_token_id, dtype=torch.long, device=self.device)
         prompt = prompt.to(self.device, torch.long).contiguous()
@@ -1106,6 +1060,7 @@ class WhisperEEGEngine:
         if n_new <= 0:
             return torch.empty((B, 0), dtype=torch.long, device=self.device)
         cache = [ws.get(f"g_qkv.{i}", (B, Tmax, 3 * d), dt) for i in range(dm.dec_layers)]
+        kv_all = ws.get("kv_layers", (dm.dec_layers, B * S, 2 * d), dt)
         finished = ws.get("g_fin", (B,), torch.uint8); finished.zero_()
         nxt = ws.get("g_next", (B,), torch.long)
         logits = ws.get("g_logits", (B, dm.Vp), torch.float32 if dt == torch.float32 else dt)
@@ -1113,17 +1068,23 @@ class WhisperEEGEngine:
         out.fill_(dm.pad_token_id)
         ids0 = ws.get(f"g_ids0.{L0}", (B, L0), torch.long)
         ids0.copy_(prompt)
+        # the loop body is native: ns_decode_prefill (cross K|V of all layers) and one ns_decode_step per position
+        dec = self._native_decoder(B, Tmax, cache, kv_all, logits)
+        ops.decode_prefill(dec, enc)
 
         def decode_step(step: int, ids: torch.Tensor, pos: int):
             """One decoder pass over `ids` (B, Lq) at cache position `pos` -> next token in `nxt`, appended to out[:, step]."""
-            self._decode_logits(ids, pos, cache, kv_all, logits, Tmax)
-            ops.greedy_pick(logits, dm.vocab, self.suppress if step == 0 else None, dm.eos_token_id, dm.pad_token_id, finished, nxt,
-                            out_col=out[:, step])
+            sup = self.suppress if step == 0 else None
+            if ids.shape[1] == 1:
+                ops.decode_step(dec, ids, pos, sup, dm.eos_token_id, dm.pad_token_id, finished, nxt, out_col=out[:, step])
+            else:                                                     # a multi-token prompt: the general pass, once
+                self._decode_logits(ids, pos, cache, kv_all, logits, Tmax)
+                ops.greedy_pick(logits, dm.vocab, sup, dm.eos_token_id, dm.pad_token_id, finished, nxt, out_col=out[:, step])
 
-        # The ~150 launches of a decode step are latency-bound at M = B: each step is captured once into a CUDA graph (keyed by
-        # batch / prompt length / position, all buffers live in the persistent workspace) and replayed afterwards.
+        # A position is one native call (~70 launches issued from C++ in ~0.2 ms of host time against ~0.9 ms of device time), so
+        # the loop is device-bound without CUDA graphs; use_graphs=True still replays one captured graph per position (keyed by
+        # batch / prompt length / position; all buffers live in the persistent workspace).
         graphs = self._decode_graphs if use_graphs else None
-        pos = 0
         # programmatic dependent launch: every kernel of a step starts its prologue under the tail of the one before it
         pdl_prev = ops.set_pdl(not _NO_PDL)
         try:

@@ -207,6 +207,19 @@ def greedy_pick(logits, V: int, suppress, eos: int, pad: int, finished, next_ids
     return next_ids
 
 
+def decode_prefill(dec, enc):
+    """Cross-attention K|V of every decoder layer (ns_decode_prefill); dec = _abi.Decoder built by the engine."""
+    _call("ns_decode_prefill", (0, 0), C.byref(dec), _p(enc), _stream())
+
+
+def decode_step(dec, ids, pos: int, suppress, eos: int, pad: int, finished, next_ids, out_col=None):
+    """One decoder position + greedy pick in one native call (ns_decode_step); ids (B,) int64 on the device."""
+    n_sup = 0 if suppress is None else suppress.numel()
+    _call("ns_decode_step", (0, 0), C.byref(dec), _p(ids), pos, _p(suppress), n_sup, eos, pad, _p(finished), _p(next_ids), _p(out_col),
+          out_col.stride(0) if out_col is not None else 0, _stream())
+    return next_ids
+
+
 def set_pdl(on: bool) -> bool:
     """Programmatic dependent launch for this thread's decoder-step kernels (include/neuspeech_b200.h ns_set_pdl)."""
     return bool(lib().ns_set_pdl(1 if on else 0))

@@ -1,6 +1,8 @@
 """Two-rank check of the data-parallel training step on real GPUs (run under torchrun, NCCL):
 the step with the gradient all-reduce split in two buckets and overlapped with the stem backward (two CUDA graphs per step)
-must leave the same weights as the step with one all-reduce after the whole backward, and the same on every rank.
+must produce the same reduced gradient as the step with one all-reduce after the whole backward (up to the summation order of
+the split-K / dQ reductions: fp32 atomics, ~1e-6 relative), the same weights within what that noise does to AdamW's normalised
+updates (measured against a second run of the single-bucket mode), and bit-identical weights on every rank.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dp_check.py"""
 import os, sys
@@ -31,18 +33,22 @@ def hook(flat):
 
 
 res = {}
-for name, no_overlap in (("overlap", False), ("single", True)):
+for name, no_overlap in (("overlap", False), ("single", True), ("single2", True)):
     E._NO_AR_OVERLAP = no_overlap
     eng = WhisperEEGEngine(dims, P, lora, dtype=torch.bfloat16, device=dev, lora_dropout=0.05, dropout_seed=3)
-    losses = [float(eng.train_step(x, labels, lr=1e-3, all_reduce=hook)) for _ in range(5)]     # eager, capture, replays
-    res[name] = (eng.flat.clone(), losses, eng.graph_launches)
-a, b = res["overlap"][0], res["single"][0]
-err = float((a - b).abs().max())
-other = a.clone()
+    losses = [float(eng.train_step(x, labels, lr=1e-3, all_reduce=hook))]
+    g1 = eng.grad.clone()                                                                         # reduced gradient of step 1
+    losses += [float(eng.train_step(x, labels, lr=1e-3, all_reduce=hook)) for _ in range(4)]    # capture, replays
+    res[name] = (eng.flat.clone(), losses, eng.graph_launches, g1)
+rel = lambda u, v: float((u - v).norm() / v.norm().clamp_min(1e-30))
+gerr, gnoise = rel(res["overlap"][3], res["single"][3]), rel(res["single2"][3], res["single"][3])
+werr = float((res["overlap"][0] - res["single"][0]).abs().max()); wnoise = float((res["single2"][0] - res["single"][0]).abs().max())
+other = res["overlap"][0].clone()
 dist.broadcast(other, src=0)
-sync = float((a - other).abs().max())
-ok = err == 0.0 and sync == 0.0 and res["overlap"][2] > 0
-print(f"rank {rank}: max |overlap - single| = {err:.3e}, max |rank - rank0| = {sync:.3e}, graph launches {res['overlap'][2]}, "
+sync = float((res["overlap"][0] - other).abs().max())
+ok = gerr <= max(10 * gnoise, 1e-5) and werr <= max(10 * wnoise, 1e-6) and sync == 0.0 and res["overlap"][2] > 0
+print(f"rank {rank}: reduced gradient overlap vs single {gerr:.2e} (run-to-run {gnoise:.2e}), weights after 5 steps {werr:.2e} "
+      f"(run-to-run {wnoise:.2e}), max |rank - rank0| = {sync:.1e}, graph launches {res['overlap'][2]}, "
       f"losses {['%.4f' % l for l in res['overlap'][1]]} -> {'OK' if ok else 'MISMATCH'}", flush=True)
 dist.barrier()
 dist.destroy_process_group()
