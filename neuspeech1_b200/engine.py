@@ -1049,6 +1049,82 @@ class WhisperEEGEngine:
         if max_length > dm.max_target_positions:
             raise ValueError(f"max_length {max_length} exceeds max_target_positions {dm.max_target_positions}")
         enc = self.encode(x, aug=aug, save=False)
+        nkv = dm.dec_layers * 2 * d
+        kv_all = self._cross_kv_per_layer(enc, B)
+        if prompt is None:
+            prompt = torch.full((B, 1), dm.decoder_start_token_id, dtype=torch.long, device=self.device)
+        prompt = prompt.to(self.device, torch.long).contiguous()
+        L0 = prompt.shape[1]
+        N = B * K
+        cache = [ws.get(f"bs_qkv.{K}.{i}", (N, max_length, 3 * d), dt) for i in range(dm.dec_layers)]
+        logits = ws.get(f"bs_logits.{K}", (N, dm.Vp), torch.float32 if dt == torch.float32 else dt)
+        # cache-row table: position j of logical row r was written by (and still sits in) physical row rows[r, j]
+        rows = ws.get(f"bs_rows.{K}", (N, max_length), torch.int32)
+        rows.copy_(torch.arange(N, dtype=torch.int32, device=self.device)[:, None].expand(N, max_length))
+        ident = ws.get(f"bs_ident.{K}", (N,), torch.int32)
+        ident.copy_(torch.arange(N, dtype=torch.int32, device=self.device))
+        state = {"pos": 0}
+
+        graphs = self._decode_graphs if use_graphs else None
+
+        def step_fn(tokens: torch.Tensor, pos: int) -> torch.Tensor:
+            Lq = tokens.shape[1]
+            ids = ws.get(f"bs_ids.{K}.{Lq}", (N, Lq), torch.long)       # static buffer: the pass below may be a graph replay
+            ids.copy_(tokens)
+            state["pos"] = pos + Lq
+            if graphs is None:
+                self._decode_logits(ids, pos, cache, kv_all, logits, max_length, beams=K, kv_rows=rows)
+                return logits
+            key = ("beam", B, K, max_length, Lq, pos, self._weights_version)
+            ent = graphs.get(key)
+            if ent is None or ent[1] != ws.gen:
+                self._decode_logits(ids, pos, cache, kv_all, logits, max_length, beams=K, kv_rows=rows)   # eager once: sizes the workspace
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._decode_logits(ids, pos, cache, kv_all, logits, max_length, beams=K, kv_rows=rows)
+                graphs[key] = (g, ws.gen)
+            else:
+                ent[0].replay()
+            return logits
+
+        def reorder_fn(beam_idx: torch.Tensor):
+            # positions < pos: inherit the parent's table; the next token's K/V will be written by the row itself
+            p = state["pos"]
+            rows[:, :p] = rows[:, :p].index_select(0, beam_idx)
+
+        scorer = None
+        if not sequence_bias and 2 * K <= 16:
+            C2 = 2 * K
+            rs = ws.get(f"bs_rs.{K}", (N, C2), torch.float32)
+            rt = ws.get(f"bs_rt.{K}", (N, C2), torch.int32)
+
+            def scorer(lg, flat, run_score, first):
+                ops.beam_row_topk(lg, dm.vocab, flat.contiguous(), run_score.reshape(-1).contiguous(), repetition_penalty,
+                                  no_repeat_ngram_size, self.suppress if (first and self.suppress.numel()) else None, C2, rs, rt)
+                top_score, idx = torch.topk(rs.view(B, K * C2), C2, dim=1)
+                return top_score, idx // C2, rt.view(B, K * C2).gather(1, idx).long()
+
+        out = run_beams(step_fn, reorder_fn, prompt, K, max_length, dm.vocab, dm.eos_token_id, dm.pad_token_id,
+                        dm.begin_suppress_tokens, repetition_penalty, no_repeat_ngram_size, length_penalty,
+                        sequence_bias=sequence_bias, scorer=scorer)
+        return out[:, L0:].contiguous()
+
+    # ------------------------------------------------------------------ greedy decode with KV cache
+    @_on_device
+    @torch.no_grad()
+    def greedy(self, x: torch.Tensor, max_length: int, prompt: Optional[torch.Tensor] = None, aug: Optional[dict] = None,
+               use_graphs: bool = True, eos_check_every: int = 16) -> torch.Tensor:
+        """Batched greedy generate (utils/load_model.py:1072-1351 -> GenerationMixin greedy): encoder once, cross-K/V once,
+        then one-token decoder steps against the self-attention cache.  Returns the generated suffix (B, n_new) int64;
+        rows that hit EOS emit pad afterwards; begin_suppress_tokens are masked at the first generated position.  Every
+        `eos_check_every` positions the host looks at the finished flags and stops once every row has emitted EOS (the
+        remaining positions are pad, as HF pads finished rows)."""
+        dm, W, ws, dt = self.dims, self.P, self.ws, self.dtype
+        d, S, F, H = dm.d_model, dm.max_source_positions, dm.dec_ffn, dm.dec_heads
+        Dh = d // H
+        B = x.shape[0]
+        enc = self.encode(x, aug=aug, save=False)
         if prompt is None:
             prompt = torch.full((B, 1), dm.decoder_start_token_id, dtype=torch.long, device=self.device)
         prompt = prompt.to(self.device, torch.long).contiguous()
