@@ -80,6 +80,9 @@ typedef struct {
                                  the elements are zeroed in shared memory between the TMA and the MMA (bf16 tcgen05 path only,
                                  N % 32 == 0, K % 64 == 0) */
   long long    drop_gstride;  /* words between the planes of stacked adapters (drop_mode 1) */
+  int          a_group_cols;  /* > 0: BLOCK-DIAGONAL main product -- output columns [g*a_group_cols, (g+1)*a_group_cols) contract
+                                 A[:, g*K : (g+1)*K] (lda >= G*K) with their own rows of W: dt_g = dy_g * B_g for the q/k/v adapters
+                                 in one launch (dy = [dq|dk|dv], W = [B_q^T; B_k^T; B_v^T]).  No second product with it. */
 } ns_epilogue;
 
 int ns_gemm_nt(int dtype, long long M, int N, int K, const void* A, long long lda, const void* W, long long ldw,
@@ -91,6 +94,11 @@ int ns_gemm_nt(int dtype, long long M, int N, int K, const void* A, long long ld
 int ns_gemm_tn(int dtype, long long M, int I, int J, const void* X, long long ldx, const void* Y, long long ldy,
                float* G, long long si, long long sj, float alpha, void* stream);
 
+/* Block-diagonal form: `groups` independent gradients in one launch, X (M, groups*I), Y (M, groups*J),
+ *   G[(g*I + i)*si + j*sj] += alphas[g] * sum_m X[m, g*I + i] * Y[m, g*J + j]      (dB_q, dB_k, dB_v from dy = [dq|dk|dv], t = [t_q|t_k|t_v]).
+ * alphas: host array of `groups` (<= 4) scales. */
+int ns_gemm_tn_grouped(int dtype, long long M, int I, int J, int groups, const void* X, long long ldx, const void* Y, long long ldy,
+                       float* G, long long si, long long sj, const float* alphas, void* stream);
 /* Same with X masked by a dropout plane (ns_dropout_bits, one adapter) on its way to the tensor cores:
  *   G += alpha * (X . keep)^T Y  --  dA = dt'^T (x . keep) of a LoRA branch under dropout, x read once.  bf16 tcgen05 path only
  *   (I % 64 == 0, xbits_ld even); NS_ERR_UNSUPPORTED otherwise. */

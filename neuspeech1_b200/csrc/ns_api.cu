@@ -97,6 +97,8 @@ int ns_gemm_nt(int dtype, long long M, int N, int K, const void* A, long long ld
   NS_CHECK_ARG(valid_dtype(dtype), "ns_gemm_nt: bad dtype %d", dtype);
   NS_CHECK_ARG(M >= 0 && N >= 0 && K > 0 && A && W && D, "ns_gemm_nt: bad shape/pointers (M=%lld N=%d K=%d)", M, N, K);
   NS_CHECK_ARG(lda >= K && ldw >= K && ldd >= N, "ns_gemm_nt: leading dimension too small");
+  NS_CHECK_ARG(!ep || ep->a_group_cols <= 0 || (N % ep->a_group_cols == 0 && lda >= static_cast<long long>(N / ep->a_group_cols) * K),
+               "ns_gemm_nt: a_group_cols needs N a multiple of it and lda >= groups * K");
   NS_CHECK_ARG((A2 == nullptr) == (W2 == nullptr), "ns_gemm_nt: A2 and W2 must be given together");
   NS_CHECK_ARG(!A2 || K2 > 0, "ns_gemm_nt: K2 must be positive with A2");
   if (ep) NS_CHECK_ARG(ep->act != NS_ACT_DGELU || ep->aux_in, "ns_gemm_nt: NS_ACT_DGELU needs aux_in");
@@ -115,6 +117,24 @@ int ns_gemm_nt(int dtype, long long M, int N, int K, const void* A, long long ld
     const int r = gemm_nt_fast(M, N, K, A, lda, W, ldw, D, ldd, e, A2, lda2, W2, ldw2, K2, ngrp, st);
     if (r != NS_ERR_UNSUPPORTED) return r;
     if (g_path == NS_PATH_FAST) return fast_required_failed("ns_gemm_nt");
+  }
+  if (e.a_group_cols > 0) {
+    // block-diagonal main product off the tcgen05 path: one plain launch per group
+    NS_CHECK_ARG(!A2 && N % e.a_group_cols == 0, "ns_gemm_nt: a_group_cols needs a single product and N a multiple of it");
+    const size_t es = dsize(dtype), eo = ep->out_dtype == NS_F32 ? 4 : 2;
+    ns_epilogue eg = *ep;
+    eg.a_group_cols = 0;
+    for (int g = 0; g < N / e.a_group_cols; ++g) {
+      const int c0 = g * e.a_group_cols;
+      eg.bias = ep->bias ? ep->bias + c0 : nullptr;
+      eg.alpha_cols = ep->alpha_cols - c0 < 0 ? 0 : (ep->alpha_cols - c0 > e.a_group_cols ? e.a_group_cols : ep->alpha_cols - c0);
+      NS_CHECK_ARG(!ep->residual && !ep->aux_in && !ep->aux_out, "ns_gemm_nt: a_group_cols with residual / aux is not supported off the fast path");
+      const int r = ns_gemm_nt(dtype, M, e.a_group_cols, K, static_cast<const char*>(A) + static_cast<size_t>(g) * K * es, lda,
+                               static_cast<const char*>(W) + static_cast<size_t>(c0) * ldw * es, ldw, static_cast<char*>(D) + static_cast<size_t>(c0) * eo,
+                               ldd, &eg, nullptr, 0, nullptr, 0, 0, stream);
+      if (r != NS_OK) return r;
+    }
+    return NS_OK;
   }
   SimtProg p;
   memset(&p, 0, sizeof(p));
@@ -143,6 +163,27 @@ int ns_gemm_tn(int dtype, long long M, int I, int J, const void* X, long long ld
   p.y_bs = 0; p.y_rs = 1; p.y_rows = (int)M; p.ntaps = 1; p.I = I; p.J = J; p.si = si; p.sj = sj; p.stap = 0;
   p.G = G; p.alpha = alpha;
   return launch_tn_simt(dtype, p, st);
+}
+
+int ns_gemm_tn_grouped(int dtype, long long M, int I, int J, int groups, const void* X, long long ldx, const void* Y, long long ldy,
+                       float* G, long long si, long long sj, const float* alphas, void* stream) {
+  NS_CHECK_ARG(valid_dtype(dtype), "ns_gemm_tn_grouped: bad dtype %d", dtype);
+  NS_CHECK_ARG(M >= 0 && I > 0 && J > 0 && groups >= 1 && groups <= 4 && X && Y && G && alphas, "ns_gemm_tn_grouped: bad shape/pointers");
+  NS_CHECK_ARG(ldx >= static_cast<long long>(groups) * I && ldy >= static_cast<long long>(groups) * J, "ns_gemm_tn_grouped: leading dimension too small");
+  if (M == 0) return NS_OK;
+  if (want_fast(dtype)) {
+    const int r = gemm_tn_grouped_fast(M, I, J, groups, X, ldx, Y, ldy, G, si, sj, alphas, reinterpret_cast<cudaStream_t>(stream));
+    if (r != NS_ERR_UNSUPPORTED) return r;
+    if (g_path == NS_PATH_FAST) return fast_required_failed("ns_gemm_tn_grouped");
+  }
+  const size_t es = dsize(dtype);
+  for (int g = 0; g < groups; ++g) {                      // one plain launch per group (SIMT or tcgen05, whichever takes the shape)
+    const int r = ns_gemm_tn(dtype, M, I, J, static_cast<const char*>(X) + static_cast<size_t>(g) * I * es, ldx,
+                             static_cast<const char*>(Y) + static_cast<size_t>(g) * J * es, ldy, G + static_cast<long long>(g) * I * si, si, sj,
+                             alphas[g], stream);
+    if (r != NS_OK) return r;
+  }
+  return NS_OK;
 }
 
 int ns_gemm_tn_masked(int dtype, long long M, int I, int J, const void* X, long long ldx, const void* Y, long long ldy, float* G,

@@ -172,6 +172,7 @@ struct EpiDev {
   long long drop_ld;
   int drop_mode;
   long long drop_gstride;
+  int a_group_cols;            // block-diagonal main product (see ns_epilogue::a_group_cols)
 };
 
 inline EpiDev make_epi(const ns_epilogue* ep, int dtype) {
@@ -185,6 +186,7 @@ inline EpiDev make_epi(const ns_epilogue* ep, int dtype) {
     e.residual = ep->residual; e.ldr = ep->ldr; e.res_mod = ep->res_mod;
     e.out_f32 = (ep->out_dtype == NS_F32);
     e.drop_bits = ep->drop_bits; e.drop_ld = ep->drop_ld; e.drop_mode = ep->drop_mode; e.drop_gstride = ep->drop_gstride;
+    e.a_group_cols = ep->a_group_cols;
   }
   return e;
 }

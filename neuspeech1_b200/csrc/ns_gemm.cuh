@@ -47,6 +47,8 @@ int conv3_dgrad_fast(int B, int Tin, int Cp, int N, int stride, const void* dz, 
                      const EpiDev& epi, cudaStream_t st);
 int gemm_tn_fast(long long M, int I, int J, const void* X, long long ldx, const void* Y, long long ldy, float* G,
                  long long si, long long sj, float alpha, cudaStream_t st, const uint32_t* xbits = nullptr, long long xbits_ld = 0);
+int gemm_tn_grouped_fast(long long M, int I, int J, int groups, const void* X, long long ldx, const void* Y, long long ldy, float* G,
+                         long long si, long long sj, const float* alphas, cudaStream_t st);
 int conv3_wgrad_fast(int B, int Tin, int Cp, int N, int stride, const void* dz, const void* x, float* dw, cudaStream_t st);
 
 int launch_nt_simt(int dtype, const SimtProg& p, cudaStream_t st);

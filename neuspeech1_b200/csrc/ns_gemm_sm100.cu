@@ -863,6 +863,8 @@ struct TnProg {
   int icta;                   // 128-row output tiles per CTA (1..4): with a narrow Y (J <= 64) one CTA streams up to 512
                               // contiguous X columns per contraction row and keeps icta accumulators (icta * bj TMEM columns)
   int stages;                 // operand ring depth
+  int grp_i, grp_j;           // > 0: block-diagonal -- i tile i0 belongs to group g = i0 / grp_i and uses Y columns [g*grp_j, g*grp_j + bj)
+  float alpha_grp[4];
   const uint32_t* xbits;      // != NULL: X is masked with this row-major dropout plane on its way to the MMA (dA = dt'^T (x . keep))
   long long xbits_ld;
 };
@@ -903,6 +905,9 @@ gemm_tn_kernel(const __grid_constant__ TnMaps maps, const __grid_constant__ TnPr
   const int nblk = max(0, blk1 - blk0);
   const int i0 = i_tile * 128 * p.icta;         // i_tile counts groups of icta row tiles
   const int j0 = j_tile * 256;
+  const int grp = p.grp_i > 0 ? i0 / p.grp_i : 0;
+  const int yj0 = p.grp_i > 0 ? grp * p.grp_j : j0;      // column of Y this tile starts at (block-diagonal: the group's block)
+  const float alpha = p.grp_i > 0 ? p.alpha_grp[grp] : p.alpha;
   const int jboxes = (p.bj + 63) / 64;
   const uint32_t a_bytes = static_cast<uint32_t>(p.icta) * kTnABytes;
   const uint32_t stage_tx = a_bytes + static_cast<uint32_t>(jboxes) * 8192u;
@@ -939,7 +944,7 @@ gemm_tn_kernel(const __grid_constant__ TnMaps maps, const __grid_constant__ TnPr
         for (int g = 0; g < 2 * p.icta; ++g)                  // boxes past I arrive zero-filled
           tma_load_4d(&maps.x, full_bar(stage), sa + 8192u * g, i0 + 64 * g, 0, t0, b);
         for (int g = 0; g < jboxes; ++g)
-          tma_load_4d(&maps.y, full_bar(stage), sb + 8192u * g, j0 + 64 * g, p.y_par[tap], t0 + p.y_off[tap], b);
+          tma_load_4d(&maps.y, full_bar(stage), sb + 8192u * g, yj0 + 64 * g, p.y_par[tap], t0 + p.y_off[tap], b);
         if (++stage == S) { stage = 0; phase ^= 1u; }
       }
     }
@@ -1032,15 +1037,15 @@ gemm_tn_kernel(const __grid_constant__ TnMaps maps, const __grid_constant__ TnPr
               // lines per warp instruction (the split-K tail was a third of the kernel at the LoRA shapes)
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g0 + j), "f"(p.alpha * __uint_as_float(v[j])),
-                             "f"(p.alpha * __uint_as_float(v[j + 1])), "f"(p.alpha * __uint_as_float(v[j + 2])),
-                             "f"(p.alpha * __uint_as_float(v[j + 3]))
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g0 + j), "f"(alpha * __uint_as_float(v[j])),
+                             "f"(alpha * __uint_as_float(v[j + 1])), "f"(alpha * __uint_as_float(v[j + 2])),
+                             "f"(alpha * __uint_as_float(v[j + 3]))
                              : "memory");
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const int jj = j0 + c + j;
-                if (jj < p.J) atomicAdd(g_row + static_cast<long long>(jj) * p.sj, p.alpha * __uint_as_float(v[j]));
+                if (jj < p.J) atomicAdd(g_row + static_cast<long long>(jj) * p.sj, alpha * __uint_as_float(v[j]));
               }
             }
           }
@@ -1229,6 +1234,15 @@ int gemm_nt_fast(long long M, int N, int K, const void* A, long long lda, const 
   memset(&prog, 0, sizeof(prog));
   int bn = choose_bn((M + kBM - 1) / kBM, N);
   int cg = choose_cg((M + kBM - 1) / kBM, N, bn);
+  const int a1g = epi.a_group_cols;
+  if (a1g > 0) {
+    // block-diagonal main product: one 32-wide tile per group (the rank-r products dt_g = dy_g B_g)
+    if (A2 || epi.drop_bits || a1g != 32 || N % 32 != 0) {
+      set_error("ns_gemm_nt: a_group_cols supports 32-column groups of a single product");
+      return NS_ERR_UNSUPPORTED;
+    }
+    bn = 32; cg = 1;
+  }
   const bool am = epi.drop_bits && epi.drop_mode == 1;
   if (am) {
     // A-operand mask (LoRA down product): 32-wide tiles, one adapter per column tile
@@ -1251,7 +1265,7 @@ int gemm_nt_fast(long long M, int N, int K, const void* A, long long lda, const 
     cg = (!no2 && units * 2 >= static_cast<long long>(sm_count()) * 3 / 4) ? 2 : 1;
   }
   {
-    uint64_t dims[4] = {(uint64_t)K, 1, (uint64_t)M, 1};
+    uint64_t dims[4] = {(uint64_t)(a1g > 0 ? static_cast<long long>(N / a1g) * K : K), 1, (uint64_t)M, 1};
     uint64_t str[3] = {(uint64_t)lda * 2, (uint64_t)lda * 2, (uint64_t)lda * 2 * (uint64_t)M};
     uint32_t box[4] = {kBK, 1, kBM, 1};
     int r = make_map(&maps.a[0], A, 4, dims, str, box);
@@ -1264,6 +1278,7 @@ int gemm_nt_fast(long long M, int N, int K, const void* A, long long lda, const 
   }
   prog.nseg = 1;
   seg_from_k(prog.seg[0], K);
+  if (a1g > 0) { prog.seg[0].a_ngrp = a1g; prog.seg[0].a_kstep = K; }
   if (A2) {
     // the LoRA operand may be a column window of a wider stacked buffer: expose the whole row (lda2 columns)
     uint64_t dims[4] = {(uint64_t)(a2_ngrp > 0 ? lda2 : K2), 1, (uint64_t)M, 1};
@@ -1416,6 +1431,7 @@ static int launch_tn(const TnMaps& maps, TnProg& p, cudaStream_t st) {
     const int it = (p.I + 127) / 128;
     p.icta = it >= 4 ? 4 : it;
   }
+  while (p.grp_i > 0 && p.icta > 1 && p.grp_i % (128 * p.icta) != 0) --p.icta;   // an i tile never straddles two groups
   p.i_tiles = (p.I + 128 * p.icta - 1) / (128 * p.icta);
   p.j_tiles = (p.J + 255) / 256;
   p.stage_bytes = p.icta * kTnABytes + ((p.bj + 63) / 64) * 8192;
@@ -1469,6 +1485,30 @@ int gemm_tn_fast(long long M, int I, int J, const void* X, long long ldx, const 
   p.batches = 1; p.tout = static_cast<int>(M); p.ntaps = 1;
   p.I = I; p.J = J; p.si = si; p.sj = sj; p.stap = 0; p.G = G; p.alpha = alpha;
   p.xbits = xbits; p.xbits_ld = xbits_ld;
+  return launch_tn(maps, p, st);
+}
+
+// Block-diagonal weight gradients (see ns_gemm_tn_grouped): X (M, groups*I), Y (M, groups*J), group g -> G rows [g*I, (g+1)*I)
+int gemm_tn_grouped_fast(long long M, int I, int J, int groups, const void* X, long long ldx, const void* Y, long long ldy, float* G,
+                         long long si, long long sj, const float* alphas, cudaStream_t st) {
+  if (ldx % 8 != 0 || ldy % 8 != 0 || !aligned16(X) || !aligned16(Y) || M > 0x7fffffffLL) return NS_ERR_UNSUPPORTED;
+  if (I % 128 != 0 || J % 16 != 0 || J > 64 || groups < 1 || groups > 4) return NS_ERR_UNSUPPORTED;
+  TnMaps maps;
+  uint64_t dx[4] = {(uint64_t)I * groups, 1, (uint64_t)M, 1};
+  uint64_t sx[3] = {(uint64_t)ldx * 2, (uint64_t)ldx * 2, (uint64_t)ldx * 2 * (uint64_t)M};
+  uint32_t box[4] = {64, 1, 64, 1};
+  int r = make_map(&maps.x, X, 4, dx, sx, box);
+  if (r) return r;
+  uint64_t dy[4] = {(uint64_t)J * groups, 1, (uint64_t)M, 1};
+  uint64_t sy[3] = {(uint64_t)ldy * 2, (uint64_t)ldy * 2, (uint64_t)ldy * 2 * (uint64_t)M};
+  r = make_map(&maps.y, Y, 4, dy, sy, box);
+  if (r) return r;
+  TnProg p;
+  memset(&p, 0, sizeof(p));
+  p.batches = 1; p.tout = static_cast<int>(M); p.ntaps = 1;
+  p.I = I * groups; p.J = J; p.si = si; p.sj = sj; p.stap = 0; p.G = G; p.alpha = 1.0f;
+  p.grp_i = I; p.grp_j = J;
+  for (int g = 0; g < groups; ++g) p.alpha_grp[g] = alphas[g];
   return launch_tn(maps, p, st);
 }
 

@@ -394,9 +394,12 @@ class WhisperEEGEngine:
                     W[k + ".B_qkv"] = lc[off_b: off_b + 3 * d * r].view(3 * d, r)        # stacked [Bq;Bk;Bv]
                     W[k + ".A_qkv_t"] = self.ws.get(k + ".A_qkv_t", (d, 3 * r), self.dtype)
                     pairs.append((W[k + ".A_qkv"], W[k + ".A_qkv_t"]))
+                    # [B_q^T * Dh^-0.5; B_k^T; B_v^T] stacked (3r, d): the block-diagonal dt = [dq|dk|dv] . B of the backward is one
+                    # launch (q's gradient carries the Dh^-0.5 of the forward: folded into this copy)
+                    W[k + ".B_qkv_t"] = self.ws.get(k + ".B_qkv_t", (3 * r, d), self.dtype)
                     for g in range(3):
-                        W[k + f".B_qkv_t{g}"] = self.ws.get(k + f".B_qkv_t{g}", (r, d), self.dtype)
-                        pairs.append((W[k + ".B_qkv"][g * d:(g + 1) * d], W[k + f".B_qkv_t{g}"]))
+                        pairs.append((W[k + ".B_qkv"][g * d:(g + 1) * d], W[k + ".B_qkv_t"][g * r:(g + 1) * r],
+                                      (d // dm.enc_heads) ** -0.5 if g == 0 else 1.0))
                     for t, fin, fout in (("out_proj", d, d), ("fc1", d, F), ("fc2", F, d)):
                         a = cv(lora_module_name(i, t) + ".lora_A.default.weight")
                         b = cv(lora_module_name(i, t) + ".lora_B.default.weight")
@@ -743,11 +746,10 @@ class WhisperEEGEngine:
             if self.has_lora:
                 dtq = ws.get("dt_qkv", (M, 3 * r), dt)
                 t_qkv = g("t_qkv")
-                for gi, tname in enumerate(("q_proj", "k_proj", "v_proj")):
-                    sc = qs if gi == 0 else 1.0
-                    ops.gemm_nt(dqkv[:, gi * d:(gi + 1) * d], W[k + f".B_qkv_t{gi}"], dtq[:, gi * r:(gi + 1) * r],
-                                self._ep(alpha=s * sc, alpha_cols=r))
-                    ops.gemm_tn(dqkv[:, gi * d:(gi + 1) * d], t_qkv[:, gi * r:(gi + 1) * r], G(tname, "B"), r, 1, alpha=sc)
+                # dt_g = alpha' dy_g B_g and dB_g = dy_g^T t_g for q, k, v: block-diagonal products, one launch each
+                ops.gemm_nt(dqkv, W[k + ".B_qkv_t"], dtq, self._ep(alpha=s, alpha_cols=3 * r, a_group_cols=r), K=d)
+                off_b, _ = lay.entries[lora_module_name(i, "q_proj") + ".lora_B.default.weight"]
+                ops.gemm_tn_grouped(dqkv, t_qkv, self.grad[off_b: off_b + 3 * d * r].view(3 * d, r), d, r, r, 1, [qs, 1.0, 1.0])
                 # dA for q,k,v in one launch: the three (r,d) gradients are contiguous = one (3r, d) matrix
                 ops.gemm_nt(dqkv, W[k + ".wqkv_t"], du1, self._ep(), a2=dtq, w2=W[k + ".A_qkv_t"], k2=3 * r)
                 self._lora_da_fix(g("u1"), dtq, du1, W[k + ".A_qkv_t"], i, ("q_proj", "k_proj", "v_proj"))

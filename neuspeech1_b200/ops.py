@@ -78,15 +78,15 @@ def _p(t: Optional[torch.Tensor]):
 
 
 def epilogue(bias=None, alpha=1.0, alpha_cols=0, act=ACT_NONE, aux_in=None, aux_out=None, ldaux=0, residual=None, ldr=0,
-             res_mod=0, out_dtype=NS_BF16, a2_group_cols=0, drop_bits=None, drop_a=None) -> Epilogue:
+             res_mod=0, out_dtype=NS_BF16, a2_group_cols=0, drop_bits=None, drop_a=None, a_group_cols=0) -> Epilogue:
     """drop_bits: ONE adapter's (rows, words) plane of dropout_bits -- the second product is masked with it (input gradient of a
     LoRA branch under dropout).  drop_a: the (G, rows, words) planes of G stacked rank-32 adapters -- the A operand of the single
     product is masked per 32-column output tile (the LoRA down product).  See include/neuspeech_b200.h ns_epilogue."""
     if drop_a is not None:
         return Epilogue(_p(bias), alpha, alpha_cols, act, _p(aux_in), _p(aux_out), ldaux, _p(residual), ldr, res_mod,
-                        out_dtype, a2_group_cols, _p(drop_a), drop_a.stride(1), 1, drop_a.stride(0))
+                        out_dtype, a2_group_cols, _p(drop_a), drop_a.stride(1), 1, drop_a.stride(0), a_group_cols)
     return Epilogue(_p(bias), alpha, alpha_cols, act, _p(aux_in), _p(aux_out), ldaux, _p(residual), ldr, res_mod,
-                    out_dtype, a2_group_cols, _p(drop_bits), drop_bits.stride(0) if drop_bits is not None else 0, 0, 0)
+                    out_dtype, a2_group_cols, _p(drop_bits), drop_bits.stride(0) if drop_bits is not None else 0, 0, 0, a_group_cols)
 
 
 def gemm_nt(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, ep: Optional[Epilogue] = None, a2=None, w2=None,
@@ -248,11 +248,13 @@ class TransposeBatch:
         self.keep = pairs
         jobs = (_abi.TransposeJob * len(pairs))()
         self.max_ldd = self.max_cols = 0
-        for i, (src, dst) in enumerate(pairs):
+        for i, pr in enumerate(pairs):                   # (src, dst) or (src, dst, scale)
+            src, dst = pr[0], pr[1]
+            scale = float(pr[2]) if len(pr) > 2 else 1.0
             assert ns_dtype(src) == self.sdt and ns_dtype(dst) == self.ddt and src.dim() == 2 and dst.dim() == 2
             rows, cols = src.shape
             assert dst.shape[0] == cols and dst.stride(0) >= rows
-            jobs[i] = _abi.TransposeJob(_p(src), _p(dst), rows, cols, src.stride(0), dst.stride(0), 1.0, 0)
+            jobs[i] = _abi.TransposeJob(_p(src), _p(dst), rows, cols, src.stride(0), dst.stride(0), scale, 0)
             self.max_ldd = max(self.max_ldd, dst.stride(0)); self.max_cols = max(self.max_cols, cols)
         raw = np.frombuffer(bytes(jobs), dtype=np.uint8).copy()
         self.table = torch.from_numpy(raw).to(device)
@@ -291,6 +293,15 @@ def seed_advance(seed: torch.Tensor):
 
 def _salts(salts):
     return (C.c_uint * 3)(*([int(s) & 0xFFFFFFFF for s in salts] + [0] * (3 - len(salts))))
+
+
+def gemm_tn_grouped(x: torch.Tensor, y: torch.Tensor, g: torch.Tensor, I: int, J: int, si: int, sj: int, alphas):
+    """Block-diagonal weight gradients in one launch: g[(k*I + i)*si + j*sj] += alphas[k] * sum_m x[m, k*I + i] * y[m, k*J + j]."""
+    groups = len(alphas)
+    arr = (C.c_float * groups)(*[float(a) for a in alphas])
+    _call("ns_gemm_tn_grouped", (2.0 * x.shape[0] * I * J * groups, 0), ns_dtype(x), x.shape[0], I, J, groups, _p(x), x.stride(0), _p(y),
+          y.stride(0), _p(g), si, sj, arr, _stream())
+    return g
 
 
 def gemm_tn_masked(x: torch.Tensor, y: torch.Tensor, g: torch.Tensor, si: int, sj: int, xbits: torch.Tensor, alpha: float = 1.0):

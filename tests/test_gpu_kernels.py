@@ -259,6 +259,28 @@ def test_programmatic_dependent_launch_chain_is_race_free():
         ops.set_pdl(prev)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("M,d,r", [(3000, 512, 32), (777, 256, 32), (20001, 1280, 32)])
+def test_block_diagonal_rank_products(M, d, r, dtype):
+    """dt_g = alpha dy_g B_g (ns_epilogue.a_group_cols) and dB_g += alphas[g] dy_g^T t_g (ns_gemm_tn_grouped) for the three
+    stacked q/k/v adapters in ONE launch each, against the per-adapter products in fp32 torch; fp32 storage takes the same calls
+    (one launch per group inside the library)."""
+    dy = rnd(M, 3 * d, dtype=dtype, seed=1)
+    Bt = rnd(3 * r, d, dtype=dtype, scale=d ** -0.5, seed=2)              # [B_q^T; B_k^T; B_v^T]
+    t = rnd(M, 3 * r, dtype=dtype, scale=0.3, seed=3)
+    dt = torch.full((M, 3 * r), 5.0, dtype=dtype, device=DEV)
+    ops.gemm_nt(dy, Bt, dt, ops.epilogue(alpha=1.5, alpha_cols=3 * r, a_group_cols=r, out_dtype=ops.ns_dtype(dtype)), K=d)
+    dB = torch.full((3 * d, r), 0.25, dtype=torch.float32, device=DEV)
+    alphas = [0.125, 1.0, 2.0]
+    ops.gemm_tn_grouped(dy, t, dB, d, r, r, 1, alphas)
+    for g in range(3):
+        yg = dy[:, g * d:(g + 1) * d].float()
+        ref = 1.5 * yg @ Bt[g * r:(g + 1) * r].float().t()
+        assert rel(dt[:, g * r:(g + 1) * r].float(), ref) < tol(dtype), (g, rel(dt[:, g * r:(g + 1) * r].float(), ref))
+        refB = alphas[g] * yg.t() @ t[:, g * r:(g + 1) * r].float() + 0.25
+        assert rel(dB[g * d:(g + 1) * d], refB) < (2e-3 if dtype == torch.bfloat16 else 1e-4), (g, rel(dB[g * d:(g + 1) * d], refB))
+
+
 def test_gemm_nt_simt_equals_fast():
     M, N, K = 500, 768, 512
     a = rnd(M, K, dtype=torch.bfloat16, seed=1); w = rnd(N, K, dtype=torch.bfloat16, scale=K ** -0.5, seed=2)
