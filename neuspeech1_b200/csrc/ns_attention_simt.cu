@@ -494,20 +494,12 @@ static bool tiny_eligible(const ns_attn_shape& s, const void* q, const void* k, 
 // instruction), scores / weights stay in registers, one online-softmax state per warp, partial results of the 8 warps are
 // merged in shared memory.  HBM-bound by construction: B*H*Lk*Dh*2 elements per call.
 template <typename T, int DH>
-__global__ void __launch_bounds__(256) attn_decode_kernel(const ns_attn_shape s, const T* __restrict__ q, const T* __restrict__ k,
+__global__ void __launch_bounds__(256, 3) attn_decode_kernel(const ns_attn_shape s, const T* __restrict__ q, const T* __restrict__ k,
                                                           const T* __restrict__ v, T* __restrict__ o, float* __restrict__ lse,
                                                           const int* __restrict__ kv_row, long long kv_ld) {
-  // 32 bytes (two 16-byte vectors) of a K row and of a V row per lane: 4 lanes per 128-byte bf16 row, 8 keys per warp
-  // instruction.  (With one vector per lane the kernel was ISSUE-bound at 58 % of the copy bandwidth -- ncu: issue active 58 %,
-  // 76 registers, 3 CTAs per SM: ~68 warp instructions per KB of K|V.  Twice the data per lane halves the shuffles, exponentials
-  // and bookkeeping per byte, and the running maximum -- warp-uniform by construction -- rescales the accumulators only when it
-  // moves, which after the first few keys it rarely does.)
   constexpr int EPV = 16 / sizeof(T);              // elements per 16-byte vector
-  constexpr int NV = 2;                            // vectors per lane and row
-  constexpr int EPL = EPV * NV;                    // elements per lane
-  constexpr int CPR = DH / EPL;                    // lanes per row
+  constexpr int CPR = DH / EPV;                    // vectors (lanes) per row
   constexpr int KPW = 32 / CPR;                    // keys per warp instruction
-  static_assert(DH % EPL == 0 && CPR >= 1 && CPR <= 32, "head_dim must be a multiple of 32 bytes");
   __shared__ float sm_m[8], sm_l[8];
   __shared__ __align__(16) float sm_o[8][DH];
   pdl_launch_dependents();
@@ -515,79 +507,68 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const ns_attn_shape s,
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = lane % CPR, kk = lane / CPR;
-  float qv[EPL];
+  float qv[EPV];
   {
-    const T* qp = q + b * s.q_bs + h * DH + c * EPL;       // Lq == 1: row 0
+    const T* qp = q + b * s.q_bs + h * DH + c * EPV;       // Lq == 1: row 0
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) qv[e] = to_f<T>(qp[e]);
+    for (int e = 0; e < EPV; ++e) qv[e] = to_f<T>(qp[e]);
   }
-  float m = -INFINITY, l = 0.f, acc[EPL];
+  float m = -INFINITY, l = 0.f, acc[EPV];
 #pragma unroll
-  for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
+  for (int e = 0; e < EPV; ++e) acc[e] = 0.f;
   // kv_row (beam search): key/value j of batch row b lives in cache row kv_row[b][j] -- the beam reorder permutes this small
   // table instead of copying the cache (utils/load_model.py:1353-1360 _reorder_cache index_selects every layer's K and V)
   const int* rowtab = kv_row ? kv_row + b * kv_ld : nullptr;
-  const T* kb = k + (rowtab ? 0 : b * s.k_bs) + h * DH + c * EPL;
-  const T* vb = v + (rowtab ? 0 : b * s.v_bs) + h * DH + c * EPL;
+  const T* kb = k + (rowtab ? 0 : b * s.k_bs) + h * DH + c * EPV;
+  const T* vb = v + (rowtab ? 0 : b * s.v_bs) + h * DH + c * EPV;
   // UNR key groups per loop trip, all their 16-byte loads issued before the first use (memory-level parallelism is the whole
   // game here: ~64 KB must be in flight per SM to cover the HBM latency)
-  constexpr int UNR = 2;
+  constexpr int UNR = 4;
   for (int j0 = warp * KPW; j0 < s.Lk; j0 += 8 * KPW * UNR) {
-    uint4 ku[UNR][NV], vu[UNR][NV];
+    uint4 ku[UNR], vu[UNR];
     bool ok[UNR];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const int j = j0 + u * 8 * KPW + kk;
       ok[u] = j < s.Lk;
       const long long pr = (rowtab && ok[u]) ? __ldg(rowtab + j) : 0;
-      const uint4* kp = reinterpret_cast<const uint4*>(kb + pr * s.k_bs + static_cast<long long>(j) * s.k_rs);
-      const uint4* vp = reinterpret_cast<const uint4*>(vb + pr * s.v_bs + static_cast<long long>(j) * s.v_rs);
-#pragma unroll
-      for (int n = 0; n < NV; ++n) {
-        ku[u][n] = ok[u] ? __ldg(kp + n) : make_uint4(0, 0, 0, 0);
-        vu[u][n] = ok[u] ? __ldg(vp + n) : make_uint4(0, 0, 0, 0);
-      }
+      ku[u] = ok[u] ? __ldg(reinterpret_cast<const uint4*>(kb + pr * s.k_bs + static_cast<long long>(j) * s.k_rs)) : make_uint4(0, 0, 0, 0);
+      vu[u] = ok[u] ? __ldg(reinterpret_cast<const uint4*>(vb + pr * s.v_bs + static_cast<long long>(j) * s.v_rs)) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       if (j0 + u * 8 * KPW >= s.Lk) break;           // warp-uniform: this group has no valid key
-      float kx[EPL], vx[EPL];
-#pragma unroll
-      for (int n = 0; n < NV; ++n) {
-        if constexpr (sizeof(T) == 4) {
-          kx[4 * n + 0] = __uint_as_float(ku[u][n].x); kx[4 * n + 1] = __uint_as_float(ku[u][n].y);
-          kx[4 * n + 2] = __uint_as_float(ku[u][n].z); kx[4 * n + 3] = __uint_as_float(ku[u][n].w);
-          vx[4 * n + 0] = __uint_as_float(vu[u][n].x); vx[4 * n + 1] = __uint_as_float(vu[u][n].y);
-          vx[4 * n + 2] = __uint_as_float(vu[u][n].z); vx[4 * n + 3] = __uint_as_float(vu[u][n].w);
-        } else {
-          float2 f;
-          f = unpack_bf16x2(ku[u][n].x); kx[8 * n + 0] = f.x; kx[8 * n + 1] = f.y; f = unpack_bf16x2(ku[u][n].y); kx[8 * n + 2] = f.x; kx[8 * n + 3] = f.y;
-          f = unpack_bf16x2(ku[u][n].z); kx[8 * n + 4] = f.x; kx[8 * n + 5] = f.y; f = unpack_bf16x2(ku[u][n].w); kx[8 * n + 6] = f.x; kx[8 * n + 7] = f.y;
-          f = unpack_bf16x2(vu[u][n].x); vx[8 * n + 0] = f.x; vx[8 * n + 1] = f.y; f = unpack_bf16x2(vu[u][n].y); vx[8 * n + 2] = f.x; vx[8 * n + 3] = f.y;
-          f = unpack_bf16x2(vu[u][n].z); vx[8 * n + 4] = f.x; vx[8 * n + 5] = f.y; f = unpack_bf16x2(vu[u][n].w); vx[8 * n + 6] = f.x; vx[8 * n + 7] = f.y;
-        }
+      float kx[EPV], vx[EPV];
+      if constexpr (sizeof(T) == 4) {
+        kx[0] = __uint_as_float(ku[u].x); kx[1] = __uint_as_float(ku[u].y); kx[2] = __uint_as_float(ku[u].z); kx[3] = __uint_as_float(ku[u].w);
+        vx[0] = __uint_as_float(vu[u].x); vx[1] = __uint_as_float(vu[u].y); vx[2] = __uint_as_float(vu[u].z); vx[3] = __uint_as_float(vu[u].w);
+      } else {
+        float2 f;
+        f = unpack_bf16x2(ku[u].x); kx[0] = f.x; kx[1] = f.y; f = unpack_bf16x2(ku[u].y); kx[2] = f.x; kx[3] = f.y;
+        f = unpack_bf16x2(ku[u].z); kx[4] = f.x; kx[5] = f.y; f = unpack_bf16x2(ku[u].w); kx[6] = f.x; kx[7] = f.y;
+        f = unpack_bf16x2(vu[u].x); vx[0] = f.x; vx[1] = f.y; f = unpack_bf16x2(vu[u].y); vx[2] = f.x; vx[3] = f.y;
+        f = unpack_bf16x2(vu[u].z); vx[4] = f.x; vx[5] = f.y; f = unpack_bf16x2(vu[u].w); vx[6] = f.x; vx[7] = f.y;
       }
-      float sc0 = 0.f, sc1 = 0.f;                    // two chains
+      float sc = 0.f;
 #pragma unroll
-      for (int e = 0; e < EPL; e += 2) { sc0 = fmaf(qv[e], kx[e], sc0); sc1 = fmaf(qv[e + 1], kx[e + 1], sc1); }
-      float sc = sc0 + sc1;
+      for (int e = 0; e < EPV; ++e) sc = fmaf(qv[e], kx[e], sc);
 #pragma unroll
       for (int off = CPR / 2; off > 0; off >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, off);   // over the lanes of one row
       if (!ok[u]) sc = -INFINITY;
       float mt = sc;                                                                             // max over the KPW keys
 #pragma unroll
       for (int off = CPR; off < 32; off <<= 1) mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, off));
-      if (mt > m) {                                  // warp-uniform (m and mt are): the running maximum moves
-        const float corr = __expf(m - mt);           // first group: exp(-inf) = 0 on zero accumulators
+      if (mt > m) {                                // warp-uniform (m and mt are): the running maximum moves -- rarely after the
+        const float corr = __expf(m - mt);         // first few keys; first group: exp(-inf) = 0 on zero accumulators
         l *= corr;
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) acc[e] *= corr;
+        for (int e = 0; e < EPV; ++e) acc[e] *= corr;
         m = mt;
       }
-      const float pj = __expf(sc - m);               // finite m: the first key of every group that gets here is valid
-      l += pj;                                       // per key slot; slots are summed at the end
+      const float pj = __expf(sc - m);             // finite m: the first key of every group that gets here is valid
+      l += pj;                                     // per key slot; slots are summed at the end
 #pragma unroll
-      for (int e = 0; e < EPL; ++e) acc[e] = fmaf(pj, vx[e], acc[e]);
+      for (int e = 0; e < EPV; ++e) acc[e] = fmaf(pj, vx[e], acc[e]);
     }
   }
   // merge the KPW key groups of this warp (they share m), then the 8 warps
@@ -595,11 +576,11 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const ns_attn_shape s,
   for (int off = CPR; off < 32; off <<= 1) {
     l += __shfl_xor_sync(0xffffffffu, l, off);
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], off);
+    for (int e = 0; e < EPV; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], off);
   }
   if (kk == 0) {
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) sm_o[warp][c * EPL + e] = acc[e];
+    for (int e = 0; e < EPV; ++e) sm_o[warp][c * EPV + e] = acc[e];
     if (c == 0) { sm_m[warp] = m; sm_l[warp] = l; }
   }
   __syncthreads();
