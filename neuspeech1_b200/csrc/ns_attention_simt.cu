@@ -521,11 +521,12 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const ns_attn_shape s,
   const int* rowtab = kv_row ? kv_row + b * kv_ld : nullptr;
   const T* kb = k + (rowtab ? 0 : b * s.k_bs) + h * DH + c * EPV;
   const T* vb = v + (rowtab ? 0 : b * s.v_bs) + h * DH + c * EPV;
-  // UNR key groups per trip, all their 16-byte loads issued before the first use, and the NEXT trip's loads issued before this
-  // trip's arithmetic (two register buffers): a warp never sits out a full memory latency between trips.
+  // UNR key groups per loop trip, all their 16-byte loads issued before the first use (memory-level parallelism is the whole
+  // game here: ~64 KB must be in flight per SM to cover the HBM latency)
   constexpr int UNR = 4;
-  constexpr int STEP = 8 * KPW * UNR;
-  auto load = [&](int j0, uint4 (&ku)[UNR], uint4 (&vu)[UNR], bool (&ok)[UNR]) {
+  for (int j0 = warp * KPW; j0 < s.Lk; j0 += 8 * KPW * UNR) {
+    uint4 ku[UNR], vu[UNR];
+    bool ok[UNR];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const int j = j0 + u * 8 * KPW + kk;
@@ -534,52 +535,35 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const ns_attn_shape s,
       ku[u] = ok[u] ? __ldg(reinterpret_cast<const uint4*>(kb + pr * s.k_bs + static_cast<long long>(j) * s.k_rs)) : make_uint4(0, 0, 0, 0);
       vu[u] = ok[u] ? __ldg(reinterpret_cast<const uint4*>(vb + pr * s.v_bs + static_cast<long long>(j) * s.v_rs)) : make_uint4(0, 0, 0, 0);
     }
-  };
-  auto compute = [&](int j0, const uint4 (&ku)[UNR], const uint4 (&vu)[UNR], const bool (&ok)[UNR]) {
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        if (j0 + u * 8 * KPW >= s.Lk) break;           // warp-uniform: this group has no valid key
-        float kx[EPV], vx[EPV];
-        if constexpr (sizeof(T) == 4) {
-          kx[0] = __uint_as_float(ku[u].x); kx[1] = __uint_as_float(ku[u].y); kx[2] = __uint_as_float(ku[u].z); kx[3] = __uint_as_float(ku[u].w);
-          vx[0] = __uint_as_float(vu[u].x); vx[1] = __uint_as_float(vu[u].y); vx[2] = __uint_as_float(vu[u].z); vx[3] = __uint_as_float(vu[u].w);
-        } else {
-          float2 f;
-          f = unpack_bf16x2(ku[u].x); kx[0] = f.x; kx[1] = f.y; f = unpack_bf16x2(ku[u].y); kx[2] = f.x; kx[3] = f.y;
-          f = unpack_bf16x2(ku[u].z); kx[4] = f.x; kx[5] = f.y; f = unpack_bf16x2(ku[u].w); kx[6] = f.x; kx[7] = f.y;
-          f = unpack_bf16x2(vu[u].x); vx[0] = f.x; vx[1] = f.y; f = unpack_bf16x2(vu[u].y); vx[2] = f.x; vx[3] = f.y;
-          f = unpack_bf16x2(vu[u].z); vx[4] = f.x; vx[5] = f.y; f = unpack_bf16x2(vu[u].w); vx[6] = f.x; vx[7] = f.y;
-        }
-        float sc = 0.f;
-#pragma unroll
-        for (int e = 0; e < EPV; ++e) sc = fmaf(qv[e], kx[e], sc);
-#pragma unroll
-        for (int off = CPR / 2; off > 0; off >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, off);   // over the lanes of one row
-        if (!ok[u]) sc = -INFINITY;
-        float mt = sc;                                                                             // max over the KPW keys
-#pragma unroll
-        for (int off = CPR; off < 32; off <<= 1) mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, off));
-        const float mn = fmaxf(m, mt);               // finite: the first key of this group is valid
-        const float corr = __expf(m - mn), pj = __expf(sc - mn);
-        m = mn;
-        l = l * corr + pj;                           // per key group; groups are summed at the end
-#pragma unroll
-        for (int e = 0; e < EPV; ++e) acc[e] = fmaf(pj, vx[e], acc[e] * corr);
+    for (int u = 0; u < UNR; ++u) {
+      if (j0 + u * 8 * KPW >= s.Lk) break;           // warp-uniform: this group has no valid key
+      float kx[EPV], vx[EPV];
+      if constexpr (sizeof(T) == 4) {
+        kx[0] = __uint_as_float(ku[u].x); kx[1] = __uint_as_float(ku[u].y); kx[2] = __uint_as_float(ku[u].z); kx[3] = __uint_as_float(ku[u].w);
+        vx[0] = __uint_as_float(vu[u].x); vx[1] = __uint_as_float(vu[u].y); vx[2] = __uint_as_float(vu[u].z); vx[3] = __uint_as_float(vu[u].w);
+      } else {
+        float2 f;
+        f = unpack_bf16x2(ku[u].x); kx[0] = f.x; kx[1] = f.y; f = unpack_bf16x2(ku[u].y); kx[2] = f.x; kx[3] = f.y;
+        f = unpack_bf16x2(ku[u].z); kx[4] = f.x; kx[5] = f.y; f = unpack_bf16x2(ku[u].w); kx[6] = f.x; kx[7] = f.y;
+        f = unpack_bf16x2(vu[u].x); vx[0] = f.x; vx[1] = f.y; f = unpack_bf16x2(vu[u].y); vx[2] = f.x; vx[3] = f.y;
+        f = unpack_bf16x2(vu[u].z); vx[4] = f.x; vx[5] = f.y; f = unpack_bf16x2(vu[u].w); vx[6] = f.x; vx[7] = f.y;
       }
-  };
-  {
-    uint4 kA[UNR], vA[UNR], kB[UNR], vB[UNR];
-    bool okA[UNR], okB[UNR];
-    int j0 = warp * KPW;
-    if (j0 < s.Lk) load(j0, kA, vA, okA);
-    for (; j0 < s.Lk; j0 += 2 * STEP) {
-      const bool more = j0 + STEP < s.Lk;
-      if (more) load(j0 + STEP, kB, vB, okB);
-      compute(j0, kA, vA, okA);
-      if (more) {
-        if (j0 + 2 * STEP < s.Lk) load(j0 + 2 * STEP, kA, vA, okA);
-        compute(j0 + STEP, kB, vB, okB);
-      }
+      float sc = 0.f;
+#pragma unroll
+      for (int e = 0; e < EPV; ++e) sc = fmaf(qv[e], kx[e], sc);
+#pragma unroll
+      for (int off = CPR / 2; off > 0; off >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, off);   // over the lanes of one row
+      if (!ok[u]) sc = -INFINITY;
+      float mt = sc;                                                                             // max over the KPW keys
+#pragma unroll
+      for (int off = CPR; off < 32; off <<= 1) mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, off));
+      const float mn = fmaxf(m, mt);               // finite: the first key of this group is valid
+      const float corr = __expf(m - mn), pj = __expf(sc - mn);
+      m = mn;
+      l = l * corr + pj;                           // per key group; groups are summed at the end
+#pragma unroll
+      for (int e = 0; e < EPV; ++e) acc[e] = fmaf(pj, vx[e], acc[e] * corr);
     }
   }
   // merge the KPW key groups of this warp (they share m), then the 8 warps

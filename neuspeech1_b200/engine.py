@@ -27,6 +27,7 @@ from . import ops
 from ._abi import ACT_DGELU, ACT_GELU, ACT_NONE, NS_BF16, NS_F32
 
 _NO_TRAIN_GRAPH = bool(os.environ.get("NS_NO_TRAIN_GRAPH"))     # developer switch: launch every kernel of train_step one by one
+_TRAIN_PDL = bool(os.environ.get("NS_TRAIN_PDL"))               # experiment: programmatic dependent launch for the training step's GEMM / LN launches
 _NO_PDL = bool(os.environ.get("NS_NO_PDL"))                     # developer A/B switch: plain stream-ordered launches in the decode loop
 _NO_AR_OVERLAP = bool(os.environ.get("NS_NO_AR_OVERLAP"))       # developer A/B switch: one all-reduce after the whole backward
 _NO_MASK_STAGE = bool(os.environ.get("NS_NO_MASK_STAGE"))       # developer A/B switch: mma.sync ns_lora_down / ns_lora_da instead of the mask stages
@@ -822,6 +823,14 @@ class WhisperEEGEngine:
         eagerly (it also warms the workspace up), the second one captures, later ones replay; anything else -- new
         addresses every step, a workspace that grew, reloaded weights -- simply keeps running eagerly.  The gradient
         all-reduce and the three optimizer launches stay outside the graph (learning rate and step count are host values)."""
+        if _TRAIN_PDL and not getattr(self, "_in_pdl", False):
+            self._in_pdl = True
+            prev = ops.set_pdl(True)
+            try:
+                return self.train_step(x, labels, lr, aug=aug, all_reduce=all_reduce, use_graph=use_graph)
+            finally:
+                ops.set_pdl(prev)
+                self._in_pdl = False
         loss = None
         # data parallel: the LoRA gradients (first part of the flat buffer) are complete before the stem backward starts, so
         # their all-reduce runs on a side stream under it; the stem gradients follow on the main stream
