@@ -40,6 +40,27 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// exp2 on the FMA pipe for a fraction of the softmax (the MUFU pipe does 16 ex2 per clock and SM and was 65 % busy: the
+// forward's first limit at head_dim 64).  Round-to-nearest split x = n + f by the 1.5 * 2^23 magic add, 2^f on [-0.5, 0.5] by a
+// degree-3 polynomial (Lawson-weighted fit, max relative error 7.5e-5: fifty times below a bf16 ulp of P), 2^n by adding n to
+// the exponent field.  Packed fp32 pairs: 7 FMA-pipe instructions + 2 clamps + 2 integer adds per pair.
+#ifndef NS_ATTN_POLY_EVERY
+#define NS_ATTN_POLY_EVERY 4        // every 4th pair of the 32 pairs of a half tile takes the polynomial (0 = never)
+#endif
+__device__ __forceinline__ void poly_exp2_pair(uint64_t x, float& p0, float& p1) {
+  float x0, x1;
+  f2_unpack(x, x0, x1);
+  x = f2_pack(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));                      // 2^-126: nothing below it survives the bf16 pack
+  const uint64_t t = f2_add(x, f2_splat(12582912.0f));                       // low mantissa bits of t = round(x)
+  const uint64_t f = f2_add(x, f2_fma(t, f2_splat(-1.0f), f2_splat(12582912.0f)));   // x - round(x)
+  const uint64_t p = f2_fma(f, f2_fma(f, f2_fma(f, f2_splat(0.05517146f), f2_splat(0.24261086f)), f2_splat(0.69326097f)), f2_splat(0.9999281f));
+  float t0, t1, q0, q1;
+  f2_unpack(t, t0, t1);
+  f2_unpack(p, q0, q1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+
 __global__ void __launch_bounds__(kAtThreads, 2)
 attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnFwdProg p) {
   extern __shared__ uint8_t smem_raw[];
@@ -406,9 +427,15 @@ attn_fwd_db_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
       for (int c = 0; c < 2; ++c) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float x0, x1;
-          f2_unpack(f2_fma(f2_pack(__uint_as_float(v[c][2 * i]), __uint_as_float(v[c][2 * i + 1])), l2e, nmb), x0, x1);
-          const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+          const uint64_t xx = f2_fma(f2_pack(__uint_as_float(v[c][2 * i]), __uint_as_float(v[c][2 * i + 1])), l2e, nmb);
+          float p0, p1;
+          if (NS_ATTN_POLY_EVERY > 0 && (16 * c + i) % (NS_ATTN_POLY_EVERY > 0 ? NS_ATTN_POLY_EVERY : 1) == NS_ATTN_POLY_EVERY - 1) {
+            poly_exp2_pair(xx, p0, p1);                 // FMA pipe
+          } else {
+            float x0, x1;
+            f2_unpack(xx, x0, x1);
+            p0 = fast_exp2(x0); p1 = fast_exp2(x1);      // MUFU pipe
+          }
           if (i & 1) acc1 = f2_add(acc1, f2_pack(p0, p1)); else acc0 = f2_add(acc0, f2_pack(p0, p1));
           pk[16 * c + i] = pack_bf16x2(p0, p1);
         }

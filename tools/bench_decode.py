@@ -50,7 +50,7 @@ if a.beams > 1:
     p50 = statistics.median(lat)
     res[f"beam{a.beams}"] = {"B": a.beam_B, "p50_ms_per_batch": p50, "samples_per_s": a.beam_B * 1e3 / p50, "new_tokens": int(out.shape[1]),
                              "ms_per_token_step": p50 / max(int(out.shape[1]), 1),
-                             "note": "beams in the batch dimension (query dimension of the cross-attention), decoder pass replayed as a CUDA graph per position, scoring loop in torch ops, cache gathered by copy"}
+                             "note": "beams in the batch dimension (query dimension of the cross-attention), decoder pass replayed as a CUDA graph per position, fused scoring kernel (ns_beam_row_topk), cache-row table instead of cache copies"}
 if os.environ.get("NS_DECODE_PROFILE"):
     from neuspeech1_b200 import ops
     ops.profile_begin()
