@@ -272,6 +272,7 @@ int ns_attention_decode_rows(int dtype, const ns_attn_shape* s, const void* q, c
  * (t) and into dt.  G = adapters stacked on the same input (1, or 3 for q/k/v), r = rank. */
 int ns_seed_advance(unsigned int* seed, void* stream);                          /* *seed = lowbias32(*seed + 0x9E3779B9) */
 long long ns_dropout_bits_words(long long rows, int cols);                      /* words per adapter of the bit plane */
+/* G <= 8 planes of the same shape in one launch (e.g. q, k, v, out_proj, fc1 of one encoder layer: all d_model columns wide) */
 int ns_dropout_bits(long long rows, int cols, int G, const unsigned int* seed, const unsigned int* salts, float p,
                     unsigned int* bits, void* stream);
 /* y = x with the dropped elements of ONE adapter's plane zeroed (materialised masked input: fp32 parity mode and tests) */

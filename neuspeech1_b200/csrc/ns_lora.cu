@@ -58,7 +58,8 @@ __device__ __forceinline__ uint32_t keep_mask2(uint32_t drop_lo, uint32_t drop_h
   return ~(((drop_lo & 1u) | ((drop_hi & 1u) << 16)) * 0xFFFFu);
 }
 
-struct Salts { uint32_t s[3]; };
+constexpr int kMaxPlanes = 8;
+struct Salts { uint32_t s[kMaxPlanes]; };
 
 // ------------------------------------------------------------------------------------------------ seed / mask planes
 __global__ void seed_advance_kernel(uint32_t* seed) { *seed = lowbias32(*seed + 0x9E3779B9u); }
@@ -620,10 +621,11 @@ long long ns_dropout_bits_words(long long rows, int cols) { return rows * ((cols
 
 int ns_dropout_bits(long long rows, int cols, int G, const unsigned int* seed, const unsigned int* salts, float p, unsigned int* bits,
                     void* stream) {
-  NS_CHECK_ARG(rows >= 0 && rows < (1LL << 31) && cols > 0 && G >= 1 && G <= 3 && seed && salts && bits, "ns_dropout_bits: bad arguments");
+  NS_CHECK_ARG(rows >= 0 && rows < (1LL << 31) && cols > 0 && G >= 1 && G <= kMaxPlanes && seed && salts && bits, "ns_dropout_bits: bad arguments");
   NS_CHECK_ARG(p >= 0.f && p < 1.f, "ns_dropout_bits: p = %f out of [0, 1)", p);
   if (rows == 0) return NS_OK;
-  Salts s{{salts[0], G > 1 ? salts[1] : 0u, G > 2 ? salts[2] : 0u}};
+  Salts s;
+  for (int g = 0; g < kMaxPlanes; ++g) s.s[g] = g < G ? salts[g] : 0u;
   const int words = (cols + 31) / 32;
   long long blocks = (rows * words + 255) / 256;
   const long long cap = (static_cast<long long>(sm_count()) * 8 + G - 1) / G;    // about 8 CTAs per SM in total, grid-stride loops

@@ -27,6 +27,7 @@ from . import ops
 from ._abi import ACT_DGELU, ACT_GELU, ACT_NONE, NS_BF16, NS_F32
 
 _NO_TRAIN_GRAPH = bool(os.environ.get("NS_NO_TRAIN_GRAPH"))     # developer switch: launch every kernel of train_step one by one
+_NO_PLANE_OVERLAP = bool(os.environ.get("NS_NO_PLANE_OVERLAP")) # developer A/B switch: draw the dropout planes on the main stream
 _TRAIN_PDL = bool(os.environ.get("NS_TRAIN_PDL"))               # experiment: programmatic dependent launch for the training step's GEMM / LN launches
 _NO_PDL = bool(os.environ.get("NS_NO_PDL"))                     # developer A/B switch: plain stream-ordered launches in the decode loop
 _NO_AR_OVERLAP = bool(os.environ.get("NS_NO_AR_OVERLAP"))       # developer A/B switch: one all-reduce after the whole backward
@@ -208,9 +209,45 @@ class WhisperEEGEngine:
         r = self.dims.lora_r
         return self.use_lora_kernels and K % 64 == 0 and r in (8, 16, 32) and G * r * (2 * K + 64) <= 220 * 1024
 
+    _PLANE_ORDER = ("q_proj", "k_proj", "v_proj", "out_proj", "fc1")       # the adapters whose input is d_model wide
+
     def _bits(self, layer: int, targets, M: int, K: int) -> torch.Tensor:
-        """Bit plane of the dropped elements of `targets`: drawn in the forward, kept for the backward consumers."""
-        return self.ws.get(f"dropbits.{layer}.{targets[0]}", (len(targets), M, (K + 31) // 32), torch.int32)
+        """Bit planes (len(targets), M, K/32) of the dropped elements of `targets` in encoder layer `layer`: drawn before the layer's
+        forward (`_draw_planes`), kept for the backward consumers.  q, k, v, out_proj and fc1 share one (5, M, d/32) buffer and
+        one generator launch; fc2 (K = ffn) has its own."""
+        dm = self.dims
+        if targets[0] == "fc2":
+            return self.ws.get(f"dropbits.{layer}.F", (1, M, (K + 31) // 32), torch.int32)
+        buf = self.ws.get(f"dropbits.{layer}.d", (len(self._PLANE_ORDER), M, (dm.d_model + 31) // 32), torch.int32)
+        i0 = self._PLANE_ORDER.index(targets[0])
+        return buf[i0: i0 + len(targets)]
+
+    def _draw_planes(self, layer: int, M: int):
+        """ns_dropout_bits for all six adapters of one encoder layer (two launches)."""
+        dm, p = self.dims, self._drop_p
+        ops.dropout_bits(M, dm.d_model, self.drop_seed, self._salts(layer, self._PLANE_ORDER), p, self._bits(layer, ("q_proj", "k_proj", "v_proj", "out_proj", "fc1"), M, dm.d_model))
+        ops.dropout_bits(M, dm.enc_ffn, self.drop_seed, self._salts(layer, ("fc2",)), p, self._bits(layer, ("fc2",), M, dm.enc_ffn))
+
+    def _planes_ahead(self, layer: int, M: int):
+        """Draw layer `layer`'s planes on a side stream, forked here: the generator is pure integer arithmetic (no memory reads,
+        issue-bound) and shares the SMs with whatever the main stream runs meanwhile -- the previous layer's attention leaves a
+        third of the register file and most issue slots free.  `_planes_join` makes the main stream wait for them."""
+        if self._drop_p == 0.0 or layer >= self.dims.enc_layers:
+            return
+        if _NO_PLANE_OVERLAP:
+            self._draw_planes(layer, M)
+            return
+        side = self.__dict__.get("_plane_stream")
+        if side is None:
+            side = self._plane_stream = torch.cuda.Stream(device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self._draw_planes(layer, M)
+
+    def _planes_join(self):
+        if self._drop_p > 0.0 and not _NO_PLANE_OVERLAP and self.__dict__.get("_plane_stream") is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._plane_stream)
 
     def _lora_down(self, x: torch.Tensor, A: torch.Tensor, t: torch.Tensor, layer: int, targets):
         """t[:, g*r:(g+1)*r] = alpha' * dropout_g(x) A_g^T for the adapters `targets` stacked in A (PEFT lora.Linear:
@@ -222,7 +259,7 @@ class WhisperEEGEngine:
         if p == 0.0:
             ops.gemm_nt(x, A, t, self._ep(alpha=a, alpha_cols=G * r))
             return
-        bits = ops.dropout_bits(M, K, self.drop_seed, self._salts(layer, targets), p, self._bits(layer, targets, M, K))
+        bits = self._bits(layer, targets, M, K)           # drawn by _draw_planes before the layer started
         if self.use_lora_kernels and r == 32 and K % 64 == 0 and not _NO_MASK_STAGE:
             # the thin tcgen05 GEMM with a mask stage between TMA and MMA (one 32-column tile per adapter)
             ops.gemm_nt(x, A, t, self._ep(alpha=a, alpha_cols=G * r, drop_a=bits))
@@ -456,6 +493,7 @@ class WhisperEEGEngine:
         d, S, T, F, r, H = dm.d_model, dm.max_source_positions, dm.T, dm.enc_ffn, dm.lora_r, dm.enc_heads
         M = B * S
         self._drop_p = self.lora_dropout if (save and self.training and self.has_lora) else 0.0
+        self._planes_ahead(0, M)                      # layer 0's dropout planes: drawn beside the augmentation pass and the stem
         xcl = self.input_to_channels_last(x, aug)
         zA = ws.get("zA", (B, T, d), dt); aA = ws.get("aA", (B, T, d), dt)
         ops.conv3_fwd(xcl, W["stemA.w"], aA, 1, self._ep(bias=W["stemA.b"], act=ACT_GELU, aux_out=zA if save else None, ldaux=d))
@@ -469,6 +507,8 @@ class WhisperEEGEngine:
         shp = ops.attn_shape(B, H, S, S, Dh, False, S * 3 * d, 3 * d, S * 3 * d, 3 * d, S * 3 * d, 3 * d, S * d, d)
         for i in range(dm.enc_layers):
             k = f"enc{i}"
+            self._planes_join()                   # this layer's dropout planes are ready ...
+            self._planes_ahead(i + 1, M)          # ... and the next layer's are drawn on the side stream while this one runs
             sfx = f".{i}" if save else ""        # per-layer buffers only when the backward needs them
             u1 = ws.get("u1" + sfx, (M, d), dt)
             mean1 = ws.get("mean1" + sfx, (M,), torch.float32); rstd1 = ws.get("rstd1" + sfx, (M,), torch.float32)

@@ -292,7 +292,7 @@ def seed_advance(seed: torch.Tensor):
 
 
 def _salts(salts):
-    return (C.c_uint * 3)(*([int(s) & 0xFFFFFFFF for s in salts] + [0] * (3 - len(salts))))
+    return (C.c_uint * 8)(*([int(s) & 0xFFFFFFFF for s in salts] + [0] * (8 - len(salts))))
 
 
 def gemm_tn_grouped(x: torch.Tensor, y: torch.Tensor, g: torch.Tensor, I: int, J: int, si: int, sj: int, alphas):
