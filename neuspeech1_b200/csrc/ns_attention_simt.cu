@@ -6,6 +6,8 @@
 // backward: delta = rowsum(dO*O); dq kernel (same structure as forward); dk/dv kernel (one warp per 2 keys, loops queries).
 #include "ns_common.cuh"
 
+#include <stdlib.h>
+
 namespace ns {
 
 constexpr int kQPB = 16;    // queries per block
@@ -493,15 +495,18 @@ static bool tiny_eligible(const ns_attn_shape& s, const void* q, const void* k, 
 // Pure streaming: every K and V row is read once with 16-byte loads (8 lanes per 128-byte bf16 row, 4 keys per warp
 // instruction), scores / weights stay in registers, one online-softmax state per warp, partial results of the 8 warps are
 // merged in shared memory.  HBM-bound by construction: B*H*Lk*Dh*2 elements per call.
-template <typename T, int DH>
-__global__ void __launch_bounds__(256) attn_decode_kernel(const ns_attn_shape s, const T* __restrict__ q, const T* __restrict__ k,
+// WARPS = 8 (256 threads, 3 CTAs per SM) or 4 (128 threads, 7 CTAs per SM).  At B * H = 1024 (batch 128) the 8-warp shape
+// needs 2.3 waves of 444 CTAs -- the third wave is a third full and the kernel reaches 58 % of the copy bandwidth -- while the
+// 4-warp shape holds all 1024 CTAs (1036 slots) at once: no tail.  Small batches keep 8 warps per (sample, head).
+template <typename T, int DH, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 7 : 3) attn_decode_kernel(const ns_attn_shape s, const T* __restrict__ q, const T* __restrict__ k,
                                                           const T* __restrict__ v, T* __restrict__ o, float* __restrict__ lse,
                                                           const int* __restrict__ kv_row, long long kv_ld) {
   constexpr int EPV = 16 / sizeof(T);              // elements per 16-byte vector
   constexpr int CPR = DH / EPV;                    // vectors (lanes) per row
   constexpr int KPW = 32 / CPR;                    // keys per warp instruction
-  __shared__ float sm_m[8], sm_l[8];
-  __shared__ __align__(16) float sm_o[8][DH];
+  __shared__ float sm_m[WARPS], sm_l[WARPS];
+  __shared__ __align__(16) float sm_o[WARPS][DH];
   pdl_launch_dependents();
   pdl_wait();
   const int h = blockIdx.x, b = blockIdx.y;
@@ -524,12 +529,12 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const ns_attn_shape s,
   // UNR key groups per loop trip, all their 16-byte loads issued before the first use (memory-level parallelism is the whole
   // game here: ~64 KB must be in flight per SM to cover the HBM latency)
   constexpr int UNR = 4;
-  for (int j0 = warp * KPW; j0 < s.Lk; j0 += 8 * KPW * UNR) {
+  for (int j0 = warp * KPW; j0 < s.Lk; j0 += WARPS * KPW * UNR) {
     uint4 ku[UNR], vu[UNR];
     bool ok[UNR];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
-      const int j = j0 + u * 8 * KPW + kk;
+      const int j = j0 + u * WARPS * KPW + kk;
       ok[u] = j < s.Lk;
       const long long pr = (rowtab && ok[u]) ? __ldg(rowtab + j) : 0;
       ku[u] = ok[u] ? __ldg(reinterpret_cast<const uint4*>(kb + pr * s.k_bs + static_cast<long long>(j) * s.k_rs)) : make_uint4(0, 0, 0, 0);
@@ -537,7 +542,7 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const ns_attn_shape s,
     }
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
-      if (j0 + u * 8 * KPW >= s.Lk) break;           // warp-uniform: this group has no valid key
+      if (j0 + u * WARPS * KPW >= s.Lk) break;           // warp-uniform: this group has no valid key
       float kx[EPV], vx[EPV];
       if constexpr (sizeof(T) == 4) {
         kx[0] = __uint_as_float(ku[u].x); kx[1] = __uint_as_float(ku[u].y); kx[2] = __uint_as_float(ku[u].z); kx[3] = __uint_as_float(ku[u].w);
@@ -582,10 +587,10 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const ns_attn_shape s,
   if (threadIdx.x < DH) {
     float mg = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) mg = fmaxf(mg, sm_m[w]);
+    for (int w = 0; w < WARPS; ++w) mg = fmaxf(mg, sm_m[w]);
     float lg = 0.f, og = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
+    for (int w = 0; w < WARPS; ++w) {
       const float sc = sm_m[w] == -INFINITY ? 0.f : __expf(sm_m[w] - mg);
       lg = fmaf(sm_l[w], sc, lg);
       og = fmaf(sm_o[w][threadIdx.x], sc, og);
@@ -593,6 +598,14 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const ns_attn_shape s,
     o[b * s.o_bs + h * DH + threadIdx.x] = from_f<T>(og / lg);
     if (lse && threadIdx.x == 0) lse[static_cast<long long>(b) * s.H + h] = mg + logf(lg);
   }
+}
+
+// 4 warps per (sample, head) once the CTAs alone saturate the GPU (see attn_decode_kernel); NS_DECODE_WARPS=4|8 overrides
+static bool decode_four_warps(const ns_attn_shape& s) {
+  static const int forced = getenv("NS_DECODE_WARPS") ? atoi(getenv("NS_DECODE_WARPS")) : 0;
+  if (forced == 4) return true;
+  if (forced == 8) return false;
+  return static_cast<long long>(s.B) * s.H > 3LL * sm_count() && s.Lk >= 256;
 }
 
 template <typename T, int DH>
@@ -607,8 +620,12 @@ static bool decode_eligible(const ns_attn_shape& s, const void* q, const void* k
 template <typename T, int DH>
 static int attn_fwd_simt_t(const ns_attn_shape& s, const void* q, const void* k, const void* v, void* o, float* lse, cudaStream_t st) {
   if (decode_eligible<T, DH>(s, q, k, v)) {
-    NS_CUDA(launch_pdl(attn_decode_kernel<T, DH>, dim3(s.H, s.B), dim3(256), 0, st, s, reinterpret_cast<const T*>(q), reinterpret_cast<const T*>(k),
-                       reinterpret_cast<const T*>(v), reinterpret_cast<T*>(o), lse, static_cast<const int*>(nullptr), 0LL));
+    if (decode_four_warps(s))
+      NS_CUDA(launch_pdl(attn_decode_kernel<T, DH, 4>, dim3(s.H, s.B), dim3(128), 0, st, s, reinterpret_cast<const T*>(q), reinterpret_cast<const T*>(k),
+                         reinterpret_cast<const T*>(v), reinterpret_cast<T*>(o), lse, static_cast<const int*>(nullptr), 0LL));
+    else
+      NS_CUDA(launch_pdl(attn_decode_kernel<T, DH, 8>, dim3(s.H, s.B), dim3(256), 0, st, s, reinterpret_cast<const T*>(q), reinterpret_cast<const T*>(k),
+                         reinterpret_cast<const T*>(v), reinterpret_cast<T*>(o), lse, static_cast<const int*>(nullptr), 0LL));
     NS_LAUNCH_CHECK();
     count(C_ATTN_SIMT);
     return NS_OK;
@@ -685,8 +702,12 @@ static int attn_decode_rows_t(const ns_attn_shape& s, const void* q, const void*
     set_error("ns_attention_decode_rows: needs Lq == 1 and 16-byte aligned K/V rows");
     return NS_ERR_UNSUPPORTED;
   }
-  attn_decode_kernel<T, DH><<<dim3(s.H, s.B), 256, 0, st>>>(s, reinterpret_cast<const T*>(q), reinterpret_cast<const T*>(k),
-                                                          reinterpret_cast<const T*>(v), reinterpret_cast<T*>(o), nullptr, kv_row, kv_ld);
+  if (decode_four_warps(s))
+    attn_decode_kernel<T, DH, 4><<<dim3(s.H, s.B), 128, 0, st>>>(s, reinterpret_cast<const T*>(q), reinterpret_cast<const T*>(k),
+                                                                reinterpret_cast<const T*>(v), reinterpret_cast<T*>(o), nullptr, kv_row, kv_ld);
+  else
+    attn_decode_kernel<T, DH, 8><<<dim3(s.H, s.B), 256, 0, st>>>(s, reinterpret_cast<const T*>(q), reinterpret_cast<const T*>(k),
+                                                                reinterpret_cast<const T*>(v), reinterpret_cast<T*>(o), nullptr, kv_row, kv_ld);
   NS_LAUNCH_CHECK();
   count(C_ATTN_SIMT);
   return NS_OK;
