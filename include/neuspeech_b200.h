@@ -89,6 +89,14 @@ int ns_gemm_nt(int dtype, long long M, int N, int K, const void* A, long long ld
                void* D, long long ldd, const ns_epilogue* ep,
                const void* A2, long long lda2, const void* W2, long long ldw2, int K2, void* stream);
 
+/* ---- LayerNorm + GEMM for few rows (the one-token decoder step, M <= 128): D = epilogue( LN(X)[M,K] * W[N,K]^T ), LN over the K
+ * columns with gamma / beta (both NULL: no LayerNorm, then K is unrestricted), eps as ns_layernorm_fwd.  One launch in place of
+ * ns_layernorm_fwd + ns_gemm_nt (HF modeling_whisper.py:393-414: every decoder sub-block starts with a LayerNorm); bias,
+ * alpha / alpha_cols, NS_ACT_GELU and residual of ns_epilogue.  bf16 storage, N <= 8192, K <= 512 with LayerNorm; returns
+ * NS_ERR_UNSUPPORTED otherwise (ns_decode_step falls back to the two calls by itself). */
+int ns_ln_gemm_nt(int dtype, long long M, int N, int K, const void* X, long long ldx, const float* gamma, const float* beta,
+                  float eps, const void* W, long long ldw, void* D, long long ldd, const ns_epilogue* ep, void* stream);
+
 /* ---- weight-gradient GEMM:  G[i*si + j*sj] += alpha * sum_m X[m,i] * Y[m,j]   (G fp32, caller zeroes it)
  * Replaces autograd's wgrad of the LoRA A/B linears (PEFT) : dB = s*dy^T t, dA = dt^T x. */
 int ns_gemm_tn(int dtype, long long M, int I, int J, const void* X, long long ldx, const void* Y, long long ldy,

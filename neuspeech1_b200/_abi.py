@@ -65,6 +65,7 @@ SIGNATURES = {
     "ns_get_counters": [C.POINTER(c_ll), c_i],
     "ns_reset_counters": [],
     "ns_gemm_nt": [c_i, c_ll, c_i, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, C.POINTER(Epilogue), c_vp, c_ll, c_vp, c_ll, c_i, c_vp],
+    "ns_ln_gemm_nt": [c_i, c_ll, c_i, c_i, c_vp, c_ll, c_vp, c_vp, c_f, c_vp, c_ll, c_vp, c_ll, C.POINTER(Epilogue), c_vp],
     "ns_gemm_tn": [c_i, c_ll, c_i, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_ll, c_f, c_vp],
     "ns_gemm_tn_grouped": [c_i, c_ll, c_i, c_i, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_ll, c_vp, c_vp],
     "ns_gemm_tn_masked": [c_i, c_ll, c_i, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_ll, c_f, c_vp, c_ll, c_vp],

@@ -605,7 +605,7 @@ static bool decode_four_warps(const ns_attn_shape& s) {
   static const int forced = getenv("NS_DECODE_WARPS") ? atoi(getenv("NS_DECODE_WARPS")) : 0;
   if (forced == 4) return true;
   if (forced == 8) return false;
-  return static_cast<long long>(s.B) * s.H > 3LL * sm_count() && s.Lk >= 256;
+  return static_cast<long long>(s.B) * s.H > 3LL * sm_count();
 }
 
 template <typename T, int DH>

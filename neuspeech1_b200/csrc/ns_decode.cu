@@ -3,6 +3,7 @@
 // ~70 kernels of the decoder pass + the greedy pick back to back from C++ (about 2 us of host time per launch: the host stays
 // ahead of the ~0.9 ms of device time per position, so no CUDA graph per position is needed to keep the GPU busy).
 #include "ns_common.cuh"
+#include "ns_gemm.cuh"
 
 using namespace ns;
 
@@ -14,6 +15,23 @@ static ns_epilogue plain_epi(int dtype) {
   e.alpha = 1.0f;
   e.out_dtype = dtype;
   return e;
+}
+
+// D = epi(LN(x) W^T) (gamma == NULL: no LayerNorm): one skinny-GEMM launch when the shape qualifies (bf16, M <= 128), else
+// ns_layernorm_fwd into `scratch` followed by ns_gemm_nt
+static int ln_gemm(int dt, int M, int N, int K, const void* x, const float* gamma, const float* beta, void* scratch, const void* W,
+                   void* D, long long ldd, const ns_epilogue* e, void* stream) {
+  if (dt == NS_BF16) {
+    const int r = skinny_gemm(M, N, K, x, K, gamma, beta, 1e-5f, W, K, D, ldd, e, reinterpret_cast<cudaStream_t>(stream));
+    if (r != NS_ERR_UNSUPPORTED) return r;
+  }
+  const void* a = x;
+  if (gamma) {
+    const int r = ns_layernorm_fwd(dt, M, K, x, gamma, beta, scratch, nullptr, nullptr, 1e-5f, stream);
+    if (r != NS_OK) return r;
+    a = scratch;
+  }
+  return ns_gemm_nt(dt, M, N, K, a, K, W, K, D, ldd, e, nullptr, 0, nullptr, 0, 0, stream);
 }
 
 #define NS_TRY(expr)            \
@@ -54,33 +72,30 @@ int ns_decode_step(const ns_decoder* dec, const long long* ids, int pos, const i
     char* cache = static_cast<char*>(L.self_cache);
     char* row = cache + static_cast<size_t>(pos) * 3 * d * es;          // (b, pos, :) = row + b * Tmax * 3d
     // self-attention: q|k|v of the new token go straight into the cache row (HF modeling_whisper.py:314-336)
-    NS_TRY(ns_layernorm_fwd(dt, B, d, hd, L.ln1_g, L.ln1_b, dec->u, nullptr, nullptr, 1e-5f, stream));
     ns_epilogue e = plain_epi(dt);
     e.bias = L.bqkv; e.alpha = qscale; e.alpha_cols = d;
-    NS_TRY(ns_gemm_nt(dt, B, 3 * d, d, dec->u, d, L.wqkv, d, row, (long long)Tmax * 3 * d, &e, nullptr, 0, nullptr, 0, 0, stream));
+    NS_TRY(ln_gemm(dt, B, 3 * d, d, hd, L.ln1_g, L.ln1_b, dec->u, L.wqkv, row, (long long)Tmax * 3 * d, &e, stream));
     NS_TRY(ns_attention_fwd(dt, &ss, row, cache + static_cast<size_t>(d) * es, cache + static_cast<size_t>(2 * d) * es, dec->o, nullptr, stream));
     e = plain_epi(dt);
     e.bias = L.bo; e.residual = hd; e.ldr = d;
-    NS_TRY(ns_gemm_nt(dt, B, d, d, dec->o, d, L.wo, d, dec->h1, d, &e, nullptr, 0, nullptr, 0, 0, stream));
+    NS_TRY(ln_gemm(dt, B, d, d, dec->o, nullptr, nullptr, nullptr, L.wo, dec->h1, d, &e, stream));
     // cross-attention over the precomputed K|V of this layer
-    NS_TRY(ns_layernorm_fwd(dt, B, d, dec->h1, L.ln2_g, L.ln2_b, dec->u, nullptr, nullptr, 1e-5f, stream));
     e = plain_epi(dt);
     e.bias = L.bqc; e.alpha = qscale; e.alpha_cols = d;
-    NS_TRY(ns_gemm_nt(dt, B, d, d, dec->u, d, L.wqc, d, dec->qc, d, &e, nullptr, 0, nullptr, 0, 0, stream));
+    NS_TRY(ln_gemm(dt, B, d, d, dec->h1, L.ln2_g, L.ln2_b, dec->u, L.wqc, dec->qc, d, &e, stream));
     const char* ckv = static_cast<const char*>(L.cross_kv);
     NS_TRY(ns_attention_fwd(dt, &sc, dec->qc, ckv, ckv + static_cast<size_t>(d) * es, dec->o, nullptr, stream));
     e = plain_epi(dt);
     e.bias = L.boc; e.residual = dec->h1; e.ldr = d;
-    NS_TRY(ns_gemm_nt(dt, B, d, d, dec->o, d, L.woc, d, dec->h2, d, &e, nullptr, 0, nullptr, 0, 0, stream));
+    NS_TRY(ln_gemm(dt, B, d, d, dec->o, nullptr, nullptr, nullptr, L.woc, dec->h2, d, &e, stream));
     // MLP
-    NS_TRY(ns_layernorm_fwd(dt, B, d, dec->h2, L.ln3_g, L.ln3_b, dec->u, nullptr, nullptr, 1e-5f, stream));
     e = plain_epi(dt);
     e.bias = L.b1; e.act = NS_ACT_GELU;
-    NS_TRY(ns_gemm_nt(dt, B, F, d, dec->u, d, L.w1, d, dec->mm, F, &e, nullptr, 0, nullptr, 0, 0, stream));
+    NS_TRY(ln_gemm(dt, B, F, d, dec->h2, L.ln3_g, L.ln3_b, dec->u, L.w1, dec->mm, F, &e, stream));
     void* hn = (i & 1) ? dec->h3b : dec->h3a;
     e = plain_epi(dt);
     e.bias = L.b2; e.residual = dec->h2; e.ldr = d;
-    NS_TRY(ns_gemm_nt(dt, B, d, F, dec->mm, F, L.w2, F, hn, d, &e, nullptr, 0, nullptr, 0, 0, stream));
+    NS_TRY(ln_gemm(dt, B, d, F, dec->mm, nullptr, nullptr, nullptr, L.w2, hn, d, &e, stream));
     hd = hn;
   }
   NS_TRY(ns_layernorm_fwd(dt, B, d, hd, dec->lnf_g, dec->lnf_b, dec->y, nullptr, nullptr, 1e-5f, stream));

@@ -51,6 +51,10 @@ int gemm_tn_grouped_fast(long long M, int I, int J, int groups, const void* X, l
                          long long si, long long sj, const float* alphas, cudaStream_t st);
 int conv3_wgrad_fast(int B, int Tin, int Cp, int N, int stride, const void* dz, const void* x, float* dw, cudaStream_t st);
 
+// ns_skinny.cu: D = epi(LN(x) W^T) for M <= 128 rows (decoder step); NS_ERR_UNSUPPORTED when the shape does not qualify
+int skinny_gemm(long long M, int N, int K, const void* x, long long ldx, const float* gamma, const float* beta, float eps,
+                const void* w, long long ldw, void* d, long long ldd, const ns_epilogue* ep, cudaStream_t st);
+
 int launch_nt_simt(int dtype, const SimtProg& p, cudaStream_t st);
 int launch_tn_simt(int dtype, SimtTnProg& p, cudaStream_t st);
 int launch_colsum(int dtype, long long rows, int N, const void* x, long long ld, float* out, cudaStream_t st);

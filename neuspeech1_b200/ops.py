@@ -106,6 +106,17 @@ def gemm_nt(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, ep: Optional[Ep
     return out
 
 
+def ln_gemm_nt(x: torch.Tensor, gamma, beta, w: torch.Tensor, out: torch.Tensor, ep: Optional[Epilogue] = None, eps: float = 1e-5):
+    """out[M,N] = epi(LN(x)[M,K] @ w[N,K]^T) for M <= 128 rows in one launch (gamma = beta = None: no LayerNorm)."""
+    M, K = x.shape
+    N = w.shape[0]
+    if ep is None:
+        ep = epilogue(out_dtype=ns_dtype(out))
+    _call("ns_ln_gemm_nt", (2.0 * M * N * K, 0), ns_dtype(x), M, N, K, _p(x), x.stride(0), _p(gamma), _p(beta), float(eps), _p(w), w.stride(0),
+          _p(out), out.stride(0), C.byref(ep), _stream())
+    return out
+
+
 def gemm_tn(x: torch.Tensor, y: torch.Tensor, g: torch.Tensor, si: int, sj: int, alpha: float = 1.0,
             I: Optional[int] = None, J: Optional[int] = None):
     """g[i*si + j*sj] += alpha * sum_m x[m,i] * y[m,j]   (g fp32)."""

@@ -281,6 +281,46 @@ def test_block_diagonal_rank_products(M, d, r, dtype):
         assert rel(dB[g * d:(g + 1) * d], refB) < (2e-3 if dtype == torch.bfloat16 else 1e-4), (g, rel(dB[g * d:(g + 1) * d], refB))
 
 
+@pytest.mark.parametrize("M,N,K,ln,flags", [(128, 1536, 512, True, "bias,alpha"), (128, 512, 512, False, "bias,res"), (128, 2048, 512, True, "bias,gelu"),
+                                            (128, 512, 2048, False, "bias,res"), (37, 512, 512, True, "bias"), (1, 100, 256, True, ""),
+                                            (100, 1000, 1280, False, "bias,gelu"), (128, 512, 512, True, "f32out")])
+def test_ln_gemm_nt_few_rows(M, N, K, ln, flags):
+    """ns_ln_gemm_nt: D = epi(LN(x) W^T) for the one-token decoder step (M <= 128 rows) in ONE launch, against LayerNorm (rounded to
+    bf16, as the two-call path stores it) + matmul + epilogue in fp32 torch; partial row / column tiles, K chunks, every epilogue
+    the decoder uses."""
+    fl = set(flags.split(","))
+    x = rnd(M, K, dtype=torch.bfloat16, seed=1)
+    w = rnd(N, K, dtype=torch.bfloat16, scale=K ** -0.5, seed=2)
+    g = 1.0 + 0.1 * rnd(K, seed=3); b = 0.1 * rnd(K, seed=4)
+    a = x.float()
+    if ln:
+        a = F.layer_norm(a, (K,), g, b, 1e-5).to(torch.bfloat16).float()
+    ref = a @ w.float().t()
+    kw = {}
+    if "bias" in fl:
+        bias = rnd(N, seed=5); ref = ref + bias; kw["bias"] = bias
+    if "alpha" in fl:
+        kw.update(alpha=0.125, alpha_cols=min(N, 512)); ref[:, :min(N, 512)] *= 0.125
+    if "gelu" in fl:
+        kw["act"] = _abi.ACT_GELU; ref = F.gelu(ref)
+    if "res" in fl:
+        r = rnd(M, N, dtype=torch.bfloat16, seed=6); kw.update(residual=r, ldr=N); ref = ref + r.float()
+    odt = torch.float32 if "f32out" in fl else torch.bfloat16
+    out = torch.full((M, N + 8), 7.0, dtype=odt, device=DEV)
+    ops.ln_gemm_nt(x, g if ln else None, b if ln else None, w, out[:, :N], ops.epilogue(out_dtype=ops.ns_dtype(odt), **kw))
+    assert rel(out[:, :N].float(), ref) < (2e-3 if odt == torch.float32 else tol(torch.bfloat16)), rel(out[:, :N].float(), ref)
+    assert bool((out[:, N:] == 7.0).all())                              # nothing beyond the N columns is touched
+
+
+def test_ln_gemm_nt_refuses_what_it_cannot_do():
+    x = rnd(256, 512, dtype=torch.bfloat16); w = rnd(64, 512, dtype=torch.bfloat16)
+    with pytest.raises(_abi.NeuSpeechB200Error):          # more than 128 rows
+        ops.ln_gemm_nt(x, None, None, w, torch.empty(256, 64, dtype=torch.bfloat16, device=DEV))
+    x = rnd(16, 1024, dtype=torch.bfloat16); w = rnd(64, 1024, dtype=torch.bfloat16)
+    with pytest.raises(_abi.NeuSpeechB200Error):          # LayerNorm over more than 512 columns
+        ops.ln_gemm_nt(x, torch.ones(1024, device=DEV), torch.zeros(1024, device=DEV), w, torch.empty(16, 64, dtype=torch.bfloat16, device=DEV))
+
+
 def test_gemm_nt_simt_equals_fast():
     M, N, K = 500, 768, 512
     a = rnd(M, K, dtype=torch.bfloat16, seed=1); w = rnd(N, K, dtype=torch.bfloat16, scale=K ** -0.5, seed=2)
