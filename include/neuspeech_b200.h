@@ -93,7 +93,8 @@ int ns_gemm_nt(int dtype, long long M, int N, int K, const void* A, long long ld
  * columns with gamma / beta (both NULL: no LayerNorm, then K is unrestricted), eps as ns_layernorm_fwd.  One launch in place of
  * ns_layernorm_fwd + ns_gemm_nt (HF modeling_whisper.py:393-414: every decoder sub-block starts with a LayerNorm); bias,
  * alpha / alpha_cols, NS_ACT_GELU and residual of ns_epilogue.  bf16 storage, N <= 8192, K <= 512 with LayerNorm; returns
- * NS_ERR_UNSUPPORTED otherwise (ns_decode_step falls back to the two calls by itself). */
+ * NS_ERR_UNSUPPORTED otherwise.  (Measured at 128 rows: no faster than the two calls, see csrc/ns_skinny.cu; ns_decode_step
+ * uses it only on request.) */
 int ns_ln_gemm_nt(int dtype, long long M, int N, int K, const void* X, long long ldx, const float* gamma, const float* beta,
                   float eps, const void* W, long long ldw, void* D, long long ldd, const ns_epilogue* ep, void* stream);
 

@@ -5,6 +5,8 @@
 #include "ns_common.cuh"
 #include "ns_gemm.cuh"
 
+#include <stdlib.h>
+
 using namespace ns;
 
 extern "C" {
@@ -21,7 +23,8 @@ static ns_epilogue plain_epi(int dtype) {
 // ns_layernorm_fwd into `scratch` followed by ns_gemm_nt
 static int ln_gemm(int dt, int M, int N, int K, const void* x, const float* gamma, const float* beta, void* scratch, const void* W,
                    void* D, long long ldd, const ns_epilogue* e, void* stream) {
-  if (dt == NS_BF16) {
+  static const bool skinny = getenv("NS_SKINNY") != nullptr;      // measured slower at B = 128 (see ns_skinny.cu): opt-in
+  if (skinny && dt == NS_BF16) {
     const int r = skinny_gemm(M, N, K, x, K, gamma, beta, 1e-5f, W, K, D, ldd, e, reinterpret_cast<cudaStream_t>(stream));
     if (r != NS_ERR_UNSUPPORTED) return r;
   }

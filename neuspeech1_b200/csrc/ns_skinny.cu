@@ -7,7 +7,10 @@
 // such launches per decoded position.  Here a CTA owns TN output columns: it copies the whole activation block (128 x K bf16,
 // L2 resident) and its TN weight rows (the only HBM traffic) into shared memory with cp.async, normalises the rows in place
 // (warp = 16 rows), and runs mma.sync m16n8k16 from ldmatrix fragments; bias / scale / GELU / residual on the fragments.  One
-// launch per sub-block instead of two, ~4 us instead of ~15.
+// launch per sub-block instead of two.  MEASURED: slower than the two calls it replaces at B = 128 (1.23 ms against 0.87 ms per
+// position): with 16-column tiles only 32..128 CTAs run, each repeating the 128 KB activation copy and the LayerNorm, and the
+// fixed cost per launch stays where it was.  ns_decode_step therefore uses it only with NS_SKINNY=1; the entry point stays for
+// callers with a handful of rows, where one launch does beat two.
 #include "ns_common.cuh"
 
 #include <stdlib.h>
@@ -159,8 +162,7 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(const SkinnyProg p) {
 // Returns NS_ERR_UNSUPPORTED when the shape does not qualify (the caller takes LayerNorm + ns_gemm_nt instead).
 int skinny_gemm(long long M, int N, int K, const void* x, long long ldx, const float* gamma, const float* beta, float eps,
                 const void* w, long long ldw, void* d, long long ldd, const ns_epilogue* ep, cudaStream_t st) {
-  static const bool off = getenv("NS_NO_SKINNY") != nullptr;
-  if (off || M <= 0 || M > kSkM || N <= 0 || N > 8192 || K <= 0 || K % 16 != 0 || ldx % 8 != 0 || ldw % 8 != 0) return NS_ERR_UNSUPPORTED;
+  if (M <= 0 || M > kSkM || N <= 0 || N > 8192 || K <= 0 || K % 16 != 0 || ldx % 8 != 0 || ldw % 8 != 0) return NS_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || (reinterpret_cast<uintptr_t>(w) & 15) != 0) return NS_ERR_UNSUPPORTED;
   if (gamma && (K > kSkKC || K % 32 != 0 || !beta)) return NS_ERR_UNSUPPORTED;
   if (ep && (ep->aux_in || ep->aux_out || ep->res_mod || ep->drop_bits || ep->a_group_cols || ep->a2_group_cols ||
