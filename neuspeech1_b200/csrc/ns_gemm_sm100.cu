@@ -656,12 +656,8 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
         // direct path below moves 16 bytes per lane from / to 32 different rows per instruction (LSU bound).
         const uint32_t row_off = static_cast<uint32_t>(q * 32 + lane) * 128u;
         const uint32_t sw = static_cast<uint32_t>(lane & 7);
-        // With an aux output two store groups are in flight per chunk (aux tile, then output tile, each in its own staging
-        // tile): the tile about to be rewritten belongs to the OLDER of the two, so one group may stay pending.
         auto stage_wait = [&]() {                                             // the previous store of this slice has read it
-          if (elect_one()) {
-            if (has_aux) bulk_wait_read1(); else bulk_wait_read0();
-          }
+          if (elect_one()) bulk_wait_read0();
           __syncwarp();
         };
         auto stage_write = [&](uint32_t tile_addr, int sidx, const float (&y)[32]) {   // this thread's 32 columns -> 4 swizzled chunks
@@ -733,15 +729,21 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
                 }
               }
             }
+            // ONE bulk group per chunk for the two tiles: one wait, one proxy fence, one commit instead of two each (the store
+            // plumbing -- commit, fence, the warp syncs around the elected lane -- was a quarter of this epilogue's samples)
             stage_wait();
 #pragma unroll
             for (int sidx = 0; sidx < 2; ++sidx) stage_write_packed(in_stage, sidx, pk_z[sidx]);
-            NS_EPI_TRACE(330);
-            stage_commit(&maps.aux, in_stage, col0);
-            stage_wait();
-            NS_EPI_TRACE(340);
 #pragma unroll
             for (int sidx = 0; sidx < 2; ++sidx) stage_write_packed(out_stage, sidx, pk_out[sidx]);
+            NS_EPI_TRACE(340);
+            fence_proxy_async();
+            __syncwarp();
+            if (elect_one()) {
+              tma_store_3d(&maps.aux, in_stage + slice_off, col0, t_tile + q * 32, b);
+              tma_store_3d(&maps.d, out_stage + slice_off, col0, t_tile + q * 32, b);
+              bulk_commit();
+            }
           } else {
             // both 32-column slices of the chunk: two TMEM loads in flight behind one wait, then the arithmetic -- all of it
             // while the previous chunk's TMA store still reads this warp's staging slice; the wait for that store sits right
@@ -786,7 +788,7 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
             for (int sidx = 0; sidx < 2; ++sidx) stage_write_packed(out_stage, sidx, pk[sidx]);
           }
           NS_EPI_TRACE(350);
-          stage_commit(&maps.d, out_stage, col0);
+          if (!has_aux) stage_commit(&maps.d, out_stage, col0);
           NS_EPI_TRACE(360);
         }
       } else if (BN >= 64 || half == 0) {
