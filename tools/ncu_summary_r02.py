@@ -33,7 +33,7 @@ def launch_list():
     tot = sum(v[1] for v in agg.values())
     with open(f"profiles/{tag}_launches_summary.txt", "w") as f:
         f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none over one EAGER training step of bench.py (lora_dropout 0.05):\n"
-                f"# {n} launches, {tot:.1f} us total -- cold-cache and serialised, so compare SHARES with kernel_shares of the bench line\n")
+                f"# {n} launches (a window of about one step), {tot:.1f} us total -- cold-cache and serialised, so compare SHARES with kernel_shares of the bench line\n")
         f.write("# share   total_us   launches  kernel\n")
         for k, (c, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{us / tot * 100:6.2f}%  {us:10.1f}  {c:5d}  {k}\n")
