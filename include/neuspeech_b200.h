@@ -83,6 +83,10 @@ typedef struct {
   int          a_group_cols;  /* > 0: BLOCK-DIAGONAL main product -- output columns [g*a_group_cols, (g+1)*a_group_cols) contract
                                  A[:, g*K : (g+1)*K] (lda >= G*K) with their own rows of W: dt_g = dy_g * B_g for the q/k/v adapters
                                  in one launch (dy = [dq|dk|dv], W = [B_q^T; B_k^T; B_v^T]).  No second product with it. */
+  int          aux_deriv;     /* != 0: the aux tensor holds gelu'(z), not z.  NS_ACT_GELU stores gelu'(z) into aux_out (same tanh as
+                                 the activation: a handful of FMAs more), NS_ACT_DGELU multiplies by aux_in as it is -- the
+                                 backward epilogue loses its transcendental and a dozen instructions per element.  The forward
+                                 and the backward call of one layer must agree on it. */
 } ns_epilogue;
 
 int ns_gemm_nt(int dtype, long long M, int N, int K, const void* A, long long lda, const void* W, long long ldw,

@@ -25,7 +25,7 @@ class Epilogue(C.Structure):
     _fields_ = [("bias", c_vp), ("alpha", c_f), ("alpha_cols", c_i), ("act", c_i), ("aux_in", c_vp), ("aux_out", c_vp),
                 ("ldaux", c_ll), ("residual", c_vp), ("ldr", c_ll), ("res_mod", c_i), ("out_dtype", c_i),
                 ("a2_group_cols", c_i), ("drop_bits", c_vp), ("drop_ld", c_ll), ("drop_mode", c_i),
-                ("drop_gstride", c_ll), ("a_group_cols", c_i)]
+                ("drop_gstride", c_ll), ("a_group_cols", c_i), ("aux_deriv", c_i)]
 
 
 class DecoderLayer(C.Structure):

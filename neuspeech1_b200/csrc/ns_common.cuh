@@ -127,6 +127,16 @@ __device__ __forceinline__ uint64_t gelu_fast2(uint64_t z) {
   const uint64_t hz = f2_mul(z, f2_splat(0.5f));
   return f2_fma(hz, T, hz);
 }
+// gelu_fast and its derivative of a pair from ONE tanh (the forward epilogue that saves gelu'(z) for the backward)
+__device__ __forceinline__ uint64_t gelu_both2(uint64_t z, uint64_t& dg) {
+  uint64_t t;
+  const uint64_t T = gelu_tanh2(z, t);
+  const uint64_t hz = f2_mul(z, f2_splat(0.5f));
+  const uint64_t up = f2_fma(t, f2_fma(t, f2_splat(5.0f * kGeluC), f2_splat(3.0f * kGeluB)), f2_splat(kGeluA));
+  const uint64_t s = f2_fma(f2_mul(T, f2_splat(-1.0f)), T, f2_splat(1.0f));
+  dg = f2_fma(f2_mul(hz, s), up, f2_fma(f2_splat(0.5f), T, f2_splat(0.5f)));
+  return f2_fma(hz, T, hz);
+}
 __device__ __forceinline__ uint64_t dgelu_fast2(uint64_t z) {
   uint64_t t;
   const uint64_t T = gelu_tanh2(z, t);
@@ -173,6 +183,7 @@ struct EpiDev {
   int drop_mode;
   long long drop_gstride;
   int a_group_cols;            // block-diagonal main product (see ns_epilogue::a_group_cols)
+  int aux_deriv;               // aux holds gelu'(z) instead of z (see ns_epilogue::aux_deriv)
 };
 
 inline EpiDev make_epi(const ns_epilogue* ep, int dtype) {
@@ -186,7 +197,7 @@ inline EpiDev make_epi(const ns_epilogue* ep, int dtype) {
     e.residual = ep->residual; e.ldr = ep->ldr; e.res_mod = ep->res_mod;
     e.out_f32 = (ep->out_dtype == NS_F32);
     e.drop_bits = ep->drop_bits; e.drop_ld = ep->drop_ld; e.drop_mode = ep->drop_mode; e.drop_gstride = ep->drop_gstride;
-    e.a_group_cols = ep->a_group_cols;
+    e.a_group_cols = ep->a_group_cols; e.aux_deriv = ep->aux_deriv;
   }
   return e;
 }
@@ -198,10 +209,11 @@ __device__ __forceinline__ float epi_apply(const EpiDev& e, float acc, long long
   if (e.bias) x += __ldg(e.bias + col);
   if (col < e.alpha_cols) x *= e.alpha;
   if (e.act == NS_ACT_GELU) {
-    if (e.aux_out) reinterpret_cast<T*>(e.aux_out)[row * e.ldaux + col] = from_f<T>(x);
+    if (e.aux_out) reinterpret_cast<T*>(e.aux_out)[row * e.ldaux + col] = from_f<T>(e.aux_deriv ? dgelu_erf(x) : x);
     x = gelu_erf(x);
   } else if (e.act == NS_ACT_DGELU) {
-    x *= dgelu_erf(to_f<T>(reinterpret_cast<const T*>(e.aux_in)[row * e.ldaux + col]));
+    const float a = to_f<T>(reinterpret_cast<const T*>(e.aux_in)[row * e.ldaux + col]);
+    x *= e.aux_deriv ? a : dgelu_erf(a);
   }
   if (e.residual) x += to_f<T>(reinterpret_cast<const T*>(e.residual)[res_row * e.ldr + col]);
   return x;

@@ -616,23 +616,40 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
         }
         const bool full = (ncols == 32);
         if (act == NS_ACT_GELU) {
+          if (e.aux_deriv) {                              // save gelu'(z) for the backward (one tanh serves both)
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            z_out[2 * j] = x[2 * j]; z_out[2 * j + 1] = x[2 * j + 1];
-            f2_unpack(gelu_fast2(f2_pack(x[2 * j], x[2 * j + 1])), x[2 * j], x[2 * j + 1]);
+            for (int j = 0; j < 16; ++j) {
+              uint64_t dg;
+              f2_unpack(gelu_both2(f2_pack(x[2 * j], x[2 * j + 1]), dg), x[2 * j], x[2 * j + 1]);
+              f2_unpack(dg, z_out[2 * j], z_out[2 * j + 1]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              z_out[2 * j] = x[2 * j]; z_out[2 * j + 1] = x[2 * j + 1];
+              f2_unpack(gelu_fast2(f2_pack(x[2 * j], x[2 * j + 1])), x[2 * j], x[2 * j + 1]);
+            }
           }
         } else if (act == NS_ACT_DGELU) {
           if (has_in && tma_in == 1) {
+            if (e.aux_deriv) {                            // the saved tensor IS the derivative
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float2 zz = unpack_bf16x2(zin[j]);
-              f2_unpack(f2_mul(f2_pack(x[2 * j], x[2 * j + 1]), dgelu_fast2(f2_pack(zz.x, zz.y))), x[2 * j], x[2 * j + 1]);
+              for (int j = 0; j < 16; ++j) {
+                const float2 zz = unpack_bf16x2(zin[j]);
+                f2_unpack(f2_mul(f2_pack(x[2 * j], x[2 * j + 1]), f2_pack(zz.x, zz.y)), x[2 * j], x[2 * j + 1]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float2 zz = unpack_bf16x2(zin[j]);
+                f2_unpack(f2_mul(f2_pack(x[2 * j], x[2 * j + 1]), dgelu_fast2(f2_pack(zz.x, zz.y))), x[2 * j], x[2 * j + 1]);
+              }
             }
           } else if (valid) {
             float z[32];
             load32_bf16(reinterpret_cast<const __nv_bfloat16*>(e.aux_in) + row * e.ldaux + col0, p.vec_aux && full, ncols, z);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] *= dgelu_fast(z[j]);
+            for (int j = 0; j < 32; ++j) x[j] *= e.aux_deriv ? z[j] : dgelu_fast(z[j]);
           }
         }
         if (has_res) {

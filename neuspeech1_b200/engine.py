@@ -34,6 +34,7 @@ _TRAIN_PDL = bool(os.environ.get("NS_TRAIN_PDL"))               # experiment: pr
 _NO_PDL = bool(os.environ.get("NS_NO_PDL"))                     # developer A/B switch: plain stream-ordered launches in the decode loop
 _NO_AR_OVERLAP = bool(os.environ.get("NS_NO_AR_OVERLAP"))       # developer A/B switch: one all-reduce after the whole backward
 _NO_MASK_STAGE = bool(os.environ.get("NS_NO_MASK_STAGE"))       # developer A/B switch: mma.sync ns_lora_down / ns_lora_da instead of the mask stages
+_NO_GELU_DERIV = bool(os.environ.get("NS_NO_GELU_DERIV"))       # developer A/B switch: save the GELU pre-activation, not the derivative
 _NO_GEMM_MASK = bool(os.environ.get("NS_NO_GEMM_MASK"))         # developer A/B switch: dropout correction pass instead of the masked GEMM product
 ENC_LORA_TARGETS = ("q_proj", "k_proj", "v_proj", "out_proj", "fc1", "fc2")
 
@@ -273,6 +274,18 @@ class WhisperEEGEngine:
                 ops.dropout_apply(x, xm, bits[g])
                 ops.gemm_nt(xm, A[g * r:(g + 1) * r], t[:, g * r:(g + 1) * r], self._ep(alpha=a, alpha_cols=r))
 
+    def _gelu_deriv(self, with_fc2_lora: bool = False) -> int:
+        """1: the GELU forward saves gelu'(z) and the backward multiplies by it (ns_epilogue.aux_deriv) -- bf16 storage only; the
+        parity mode keeps the pre-activation.  The encoder MLP under LoRA-branch dropout needs the masked second product for it
+        (the correction pass reads z as a pre-activation)."""
+        if self.dtype != torch.bfloat16 or _NO_GELU_DERIV:
+            return 0
+        if with_fc2_lora and self.has_lora and self._drop_p > 0.0:
+            dm = self.dims
+            ok = (self.use_lora_kernels and dm.enc_ffn % 64 == 0 and not _NO_GEMM_MASK and dm.lora_r % 16 == 0 and dm.d_model % 16 == 0)
+            return 1 if ok else 0
+        return 1
+
     def _drop_plane(self, layer: int, target: str, M: int, K: int, N: Optional[int] = None) -> Optional[torch.Tensor]:
         """The (M, K/32) dropout plane of ONE adapter for the input-gradient GEMM's masked second product (ns_epilogue.drop_bits:
         dx = g W + keep . (dt' A), the LoRA product masked in the epilogue), or None when the step runs without dropout or the
@@ -498,9 +511,9 @@ class WhisperEEGEngine:
         self._planes_ahead(0, M)                      # layer 0's dropout planes: drawn beside the augmentation pass and the stem
         xcl = self.input_to_channels_last(x, aug)
         zA = ws.get("zA", (B, T, d), dt); aA = ws.get("aA", (B, T, d), dt)
-        ops.conv3_fwd(xcl, W["stemA.w"], aA, 1, self._ep(bias=W["stemA.b"], act=ACT_GELU, aux_out=zA if save else None, ldaux=d))
+        ops.conv3_fwd(xcl, W["stemA.w"], aA, 1, self._ep(bias=W["stemA.b"], act=ACT_GELU, aux_out=zA if save else None, ldaux=d, aux_deriv=self._gelu_deriv()))
         zB = ws.get("zB", (B, T // 2, d), dt); aB = ws.get("aB", (B, T // 2, d), dt)
-        ops.conv3_fwd(aA, W["stemB.w"], aB, 2, self._ep(bias=W["stemB.b"], act=ACT_GELU, aux_out=zB if save else None, ldaux=d))
+        ops.conv3_fwd(aA, W["stemB.w"], aB, 2, self._ep(bias=W["stemB.b"], act=ACT_GELU, aux_out=zB if save else None, ldaux=d, aux_deriv=self._gelu_deriv()))
         zC = ws.get("zC", (B, S, d), dt)
         h = ws.get("h0", (M, d), dt)
         ops.conv3_fwd(aB, W["stemC.w"], h.view(B, S, d), 2,
@@ -541,9 +554,10 @@ class WhisperEEGEngine:
             if self.has_lora:
                 t_1 = ws.get("t_1" + sfx, (M, r), dt)
                 self._lora_down(u2, W[k + ".A_fc1"], t_1, i, ("fc1",))
-                ops.gemm_nt(u2, W[k + ".w1"], m, self._ep(bias=W[k + ".b1"], act=ACT_GELU, aux_out=z1, ldaux=F), a2=t_1, w2=W[k + ".B_fc1"], k2=r)
+                ops.gemm_nt(u2, W[k + ".w1"], m, self._ep(bias=W[k + ".b1"], act=ACT_GELU, aux_out=z1, ldaux=F, aux_deriv=self._gelu_deriv(True)), a2=t_1,
+                            w2=W[k + ".B_fc1"], k2=r)
             else:
-                ops.gemm_nt(u2, W[k + ".w1"], m, self._ep(bias=W[k + ".b1"], act=ACT_GELU, aux_out=z1, ldaux=F))
+                ops.gemm_nt(u2, W[k + ".w1"], m, self._ep(bias=W[k + ".b1"], act=ACT_GELU, aux_out=z1, ldaux=F, aux_deriv=self._gelu_deriv(True)))
             hn = ws.get(f"h{i + 1}" if save else f"h{(i + 1) % 2 + 1}", (M, d), dt)
             if self.has_lora:
                 t_2 = ws.get("t_2" + sfx, (M, r), dt)
@@ -602,7 +616,7 @@ class WhisperEEGEngine:
             ops.layernorm_fwd(h2, W[k + ".ln3.g"], W[k + ".ln3.b"], u, m3, r3)
             z = ws.get("d_z" + sfx, (ML, F), dt) if save else None
             mm = ws.get("d_m", (ML, F), dt)
-            ops.gemm_nt(u, W[k + ".w1"], mm, self._ep(bias=W[k + ".b1"], act=ACT_GELU, aux_out=z, ldaux=F))
+            ops.gemm_nt(u, W[k + ".w1"], mm, self._ep(bias=W[k + ".b1"], act=ACT_GELU, aux_out=z, ldaux=F, aux_deriv=self._gelu_deriv()))
             h3 = ws.get(f"d_h{i + 1}" if save else f"d_h{(i + 1) % 2 + 1}x", (ML, d), dt)
             ops.gemm_nt(mm, W[k + ".w2"], h3, self._ep(bias=W[k + ".b2"], residual=h2, ldr=d))
             if save:
@@ -705,7 +719,7 @@ class WhisperEEGEngine:
             sfx = f".{i}"
             g = lambda n: ws.bufs[n + sfx]
             dm_ = ws.get("d_dm", (ML, Fd), dt)
-            ops.gemm_nt(dh, W[k + ".w2_t"], dm_, self._ep(act=ACT_DGELU, aux_in=g("d_z"), ldaux=Fd))
+            ops.gemm_nt(dh, W[k + ".w2_t"], dm_, self._ep(act=ACT_DGELU, aux_in=g("d_z"), ldaux=Fd, aux_deriv=self._gelu_deriv()))
             du = ws.get("d_du", (ML, d), dt)
             ops.gemm_nt(dm_, W[k + ".w1_t"], du, self._ep())
             dh2 = ws.get("d_dh_b", (ML, d), dt)
@@ -748,11 +762,11 @@ class WhisperEEGEngine:
                 ops.gemm_nt(dh, W[k + ".B_fc2_t"], dt2, self._ep(alpha=s, alpha_cols=r))
                 ops.gemm_tn(dh, g("t_2"), G("fc2", "B"), r, 1)
                 db = self._drop_plane(i, "fc2", M, F, d)
-                ops.gemm_nt(dh, W[k + ".w2_t"], dz1, self._ep(act=ACT_DGELU, aux_in=g("z1"), ldaux=F, drop_bits=db), a2=dt2,
+                ops.gemm_nt(dh, W[k + ".w2_t"], dz1, self._ep(act=ACT_DGELU, aux_in=g("z1"), ldaux=F, drop_bits=db, aux_deriv=self._gelu_deriv(True)), a2=dt2,
                             w2=W[k + ".A_fc2_t"], k2=r)
                 self._lora_da_fix(g("m"), dt2, dz1 if db is None else None, W[k + ".A_fc2_t"], i, ("fc2",), z=g("z1"))
             else:
-                ops.gemm_nt(dh, W[k + ".w2_t"], dz1, self._ep(act=ACT_DGELU, aux_in=g("z1"), ldaux=F))
+                ops.gemm_nt(dh, W[k + ".w2_t"], dz1, self._ep(act=ACT_DGELU, aux_in=g("z1"), ldaux=F, aux_deriv=self._gelu_deriv(True)))
             # fc1
             du2 = ws.get("du", (M, d), dt)
             if self.has_lora:
@@ -815,10 +829,10 @@ class WhisperEEGEngine:
         aA, aB, xcl = ws.bufs["aA"], ws.bufs["aB"], ws.bufs["x_cl"]
         self._conv_wgrad("model.encoder.conv2", dzC, aB, 2, d, d)
         dzB = ws.get("dzB", (B, T // 2, d), dt)
-        ops.conv3_dgrad(dzC, W["stemC.wt"], dzB, 2, self._ep(act=ACT_DGELU, aux_in=ws.bufs["zB"], ldaux=d))
+        ops.conv3_dgrad(dzC, W["stemC.wt"], dzB, 2, self._ep(act=ACT_DGELU, aux_in=ws.bufs["zB"], ldaux=d, aux_deriv=self._gelu_deriv()))
         self._conv_wgrad("model.encoder.conv1.2", dzB, aA, 2, d, d)
         dzA = ws.get("dzA", (B, T, d), dt)
-        ops.conv3_dgrad(dzB, W["stemB.wt"], dzA, 2, self._ep(act=ACT_DGELU, aux_in=ws.bufs["zA"], ldaux=d))
+        ops.conv3_dgrad(dzB, W["stemB.wt"], dzA, 2, self._ep(act=ACT_DGELU, aux_in=ws.bufs["zA"], ldaux=d, aux_deriv=self._gelu_deriv()))
         self._conv_wgrad("model.encoder.conv1.0", dzA, xcl, 1, dm.eeg_ch, Cp)
         return self.grad
 

@@ -78,15 +78,15 @@ def _p(t: Optional[torch.Tensor]):
 
 
 def epilogue(bias=None, alpha=1.0, alpha_cols=0, act=ACT_NONE, aux_in=None, aux_out=None, ldaux=0, residual=None, ldr=0,
-             res_mod=0, out_dtype=NS_BF16, a2_group_cols=0, drop_bits=None, drop_a=None, a_group_cols=0) -> Epilogue:
+             res_mod=0, out_dtype=NS_BF16, a2_group_cols=0, drop_bits=None, drop_a=None, a_group_cols=0, aux_deriv=0) -> Epilogue:
     """drop_bits: ONE adapter's (rows, words) plane of dropout_bits -- the second product is masked with it (input gradient of a
     LoRA branch under dropout).  drop_a: the (G, rows, words) planes of G stacked rank-32 adapters -- the A operand of the single
     product is masked per 32-column output tile (the LoRA down product).  See include/neuspeech_b200.h ns_epilogue."""
     if drop_a is not None:
         return Epilogue(_p(bias), alpha, alpha_cols, act, _p(aux_in), _p(aux_out), ldaux, _p(residual), ldr, res_mod,
-                        out_dtype, a2_group_cols, _p(drop_a), drop_a.stride(1), 1, drop_a.stride(0), a_group_cols)
+                        out_dtype, a2_group_cols, _p(drop_a), drop_a.stride(1), 1, drop_a.stride(0), a_group_cols, aux_deriv)
     return Epilogue(_p(bias), alpha, alpha_cols, act, _p(aux_in), _p(aux_out), ldaux, _p(residual), ldr, res_mod,
-                    out_dtype, a2_group_cols, _p(drop_bits), drop_bits.stride(0) if drop_bits is not None else 0, 0, 0, a_group_cols)
+                    out_dtype, a2_group_cols, _p(drop_bits), drop_bits.stride(0) if drop_bits is not None else 0, 0, 0, a_group_cols, aux_deriv)
 
 
 def gemm_nt(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, ep: Optional[Epilogue] = None, a2=None, w2=None,

@@ -321,6 +321,24 @@ def test_ln_gemm_nt_refuses_what_it_cannot_do():
         ops.ln_gemm_nt(x, torch.ones(1024, device=DEV), torch.zeros(1024, device=DEV), w, torch.empty(16, 64, dtype=torch.bfloat16, device=DEV))
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("M,N,K", [(3000, 2048, 512), (333, 512, 256)])
+def test_gemm_nt_saved_gelu_derivative(M, N, K, dtype):
+    """ns_epilogue.aux_deriv: the GELU forward stores gelu'(z) in the aux tensor (not z) and the dGELU backward multiplies by it
+    as it is -- the pair must reproduce gelu / gelu' of fp32 torch like the pre-activation form does."""
+    a = rnd(M, K, dtype=dtype, seed=1); w = rnd(N, K, dtype=dtype, scale=K ** -0.5, seed=2); bias = rnd(N, seed=3)
+    z = a.float() @ w.float().t() + bias
+    y = torch.empty(M, N, dtype=dtype, device=DEV); aux = torch.empty(M, N, dtype=dtype, device=DEV)
+    ops.gemm_nt(a, w, y, ops.epilogue(bias=bias, act=_abi.ACT_GELU, aux_out=aux, ldaux=N, aux_deriv=1, out_dtype=ops.ns_dtype(dtype)))
+    assert rel(y.float(), F.gelu(z)) < tol(dtype)
+    assert rel(aux.float(), gelu_grad(z)) < tol(dtype), rel(aux.float(), gelu_grad(z))
+    g = rnd(M, K, dtype=dtype, seed=4); w2 = rnd(N, K, dtype=dtype, scale=K ** -0.5, seed=5)
+    dz = torch.empty(M, N, dtype=dtype, device=DEV)
+    ops.gemm_nt(g, w2, dz, ops.epilogue(act=_abi.ACT_DGELU, aux_in=aux, ldaux=N, aux_deriv=1, out_dtype=ops.ns_dtype(dtype)))
+    assert rel(dz.float(), (g.float() @ w2.float().t()) * aux.float()) < tol(dtype)
+    assert rel(dz.float(), (g.float() @ w2.float().t()) * gelu_grad(z)) < 2 * tol(dtype)
+
+
 def test_gemm_nt_simt_equals_fast():
     M, N, K = 500, 768, 512
     a = rnd(M, K, dtype=torch.bfloat16, seed=1); w = rnd(N, K, dtype=torch.bfloat16, scale=K ** -0.5, seed=2)
