@@ -344,8 +344,14 @@ attn_bwd_fused_kernel(const __grid_constant__ BwfMaps maps, const __grid_constan
       if (tr_w) NS_TRACE(2 + g, 100 + j);
       tc_fence_after();
       uint32_t v[32], pk[16];
-      tmem_ld32(tSg, v);
-      tmem_ld_wait();
+      const bool dbg_skip = (p.debug & 2) != 0;           // NS_BWF_DEBUG bit 1: no TMEM traffic from the compute warps (timing experiment)
+      if (!dbg_skip) {
+        tmem_ld32(tSg, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0u;
+      }
 #pragma unroll
       for (int q4 = 0; q4 < 8; ++q4) {
         // the table holds -lse * log2e: one packed FFMA per pair of exponents (the compute warps are issue-bound)
@@ -356,8 +362,10 @@ attn_bwd_fused_kernel(const __grid_constant__ BwfMaps maps, const __grid_constan
         pk[2 * q4] = pack_bf16x2(ex2f(x0), ex2f(x1));
         pk[2 * q4 + 1] = pack_bf16x2(ex2f(x2), ex2f(x3));
       }
-      tmem_st16(tSg, pk);                                   // bf16 P^T over the fp32 columns this thread has consumed
-      tmem_st_wait();
+      if (!dbg_skip) {
+        tmem_st16(tSg, pk);                                 // bf16 P^T over the fp32 columns this thread has consumed
+        tmem_st_wait();
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready(g));
@@ -367,8 +375,10 @@ attn_bwd_fused_kernel(const __grid_constant__ BwfMaps maps, const __grid_constan
       else mbar_wait(dp_full(g), ph);
       if (tr_w) NS_TRACE(2 + g, 300 + j);
       tc_fence_after();
-      tmem_ld32(tdPg, v);
-      tmem_ld_wait();
+      if (!dbg_skip) {
+        tmem_ld32(tdPg, v);
+        tmem_ld_wait();
+      }
       uint32_t dk[16];
 #pragma unroll
       for (int q4 = 0; q4 < 8; ++q4) {
@@ -381,7 +391,7 @@ attn_bwd_fused_kernel(const __grid_constant__ BwfMaps maps, const __grid_constan
         dk[2 * q4] = bf16x2_mul(pk[2 * q4], pack_bf16x2(e0, e1));
         dk[2 * q4 + 1] = bf16x2_mul(pk[2 * q4 + 1], pack_bf16x2(e2, e3));
       }
-      tmem_st16(tdPg, dk);                                  // A operand of dK += dS^T Q
+      if (!dbg_skip) tmem_st16(tdPg, dk);                   // A operand of dK += dS^T Q
       const uint32_t ds_row = sdS(dss) + 16384u * g + static_cast<uint32_t>(row) * 128u;
 #pragma unroll
       for (int e = 0; e < 4; ++e)                           // dS^T row (this key) x 8 queries per 16-byte chunk, 128B swizzle
