@@ -112,6 +112,15 @@ int ns_gemm_tn(int dtype, long long M, int I, int J, const void* X, long long ld
  * alphas: host array of `groups` (<= 4) scales. */
 int ns_gemm_tn_grouped(int dtype, long long M, int I, int J, int groups, const void* X, long long ldx, const void* Y, long long ldy,
                        float* G, long long si, long long sj, const float* alphas, void* stream);
+/* B side of a LoRA branch's backward in ONE pass over dy (PEFT lora.Linear under autograd, finetune.py:194-212: y += t B^T):
+ *   dt[m, g*r + j]        = alpha_dt[g] * sum_n dy[m, g*N + n] * Bt[g*r + j, n]      (dt = alpha' dy B; replaces ns_gemm_nt on a rank-r tile)
+ *   dB[(g*N + n)*r + j]  += alpha_db[g] * sum_m dy[m, g*N + n] * t[m, g*r + j]       (fp32, caller zeroes; replaces ns_gemm_tn[_grouped])
+ * for `groups` (<= 4) adapters stacked along the columns of dy (M, groups*N), t and dt (M, groups*r) and the rows of Bt
+ * (groups*r, N) = B^T.  bf16 tcgen05 path only: r == 32, N % 128 == 0, N <= 1408, 16-byte aligned operands; NS_ERR_UNSUPPORTED
+ * otherwise (the caller then issues the two separate products).  alpha_dt / alpha_db: host arrays of `groups` scales. */
+int ns_lora_bwd_b(int dtype, long long M, int N, int r, int groups, const void* dy, long long lddy, const void* Bt, long long ldbt,
+                  const void* t, long long ldt, void* dt, long long lddt, float* dB, const float* alpha_dt, const float* alpha_db,
+                  void* stream);
 /* Same with X masked by a dropout plane (ns_dropout_bits, one adapter) on its way to the tensor cores:
  *   G += alpha * (X . keep)^T Y  --  dA = dt'^T (x . keep) of a LoRA branch under dropout, x read once.  bf16 tcgen05 path only
  *   (I % 64 == 0, xbits_ld even); NS_ERR_UNSUPPORTED otherwise. */

@@ -68,6 +68,7 @@ SIGNATURES = {
     "ns_ln_gemm_nt": [c_i, c_ll, c_i, c_i, c_vp, c_ll, c_vp, c_vp, c_f, c_vp, c_ll, c_vp, c_ll, C.POINTER(Epilogue), c_vp],
     "ns_gemm_tn": [c_i, c_ll, c_i, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_ll, c_f, c_vp],
     "ns_gemm_tn_grouped": [c_i, c_ll, c_i, c_i, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_ll, c_vp, c_vp],
+    "ns_lora_bwd_b": [c_i, c_ll, c_i, c_i, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_vp, c_vp, c_vp],
     "ns_gemm_tn_masked": [c_i, c_ll, c_i, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_ll, c_f, c_vp, c_ll, c_vp],
     "ns_conv3_fwd": [c_i, c_i, c_i, c_i, c_i, c_i, c_vp, c_vp, c_vp, C.POINTER(Epilogue), c_vp],
     "ns_conv3_dgrad": [c_i, c_i, c_i, c_i, c_i, c_i, c_vp, c_vp, c_vp, C.POINTER(Epilogue), c_vp],

@@ -186,6 +186,24 @@ int ns_gemm_tn_grouped(int dtype, long long M, int I, int J, int groups, const v
   return NS_OK;
 }
 
+int ns_lora_bwd_b(int dtype, long long M, int N, int r, int groups, const void* dy, long long lddy, const void* Bt, long long ldbt,
+                  const void* t, long long ldt, void* dt, long long lddt, float* dB, const float* alpha_dt, const float* alpha_db,
+                  void* stream) {
+  NS_CHECK_ARG(valid_dtype(dtype), "ns_lora_bwd_b: bad dtype %d", dtype);
+  NS_CHECK_ARG(M >= 0 && N > 0 && r > 0 && groups >= 1 && groups <= 4 && dy && Bt && t && dt && dB && alpha_dt && alpha_db,
+               "ns_lora_bwd_b: bad shape/pointers");
+  NS_CHECK_ARG(lddy >= static_cast<long long>(groups) * N && ldbt >= N && ldt >= static_cast<long long>(groups) * r &&
+                   lddt >= static_cast<long long>(groups) * r,
+               "ns_lora_bwd_b: leading dimension too small");
+  if (M == 0) return NS_OK;
+  if (!want_fast(dtype)) {
+    set_error("ns_lora_bwd_b: bf16 storage and the tcgen05 path only");
+    return NS_ERR_UNSUPPORTED;
+  }
+  set_error("ns_lora_bwd_b: shape does not qualify (r == 32, N %% 128 == 0, N <= 1408, 16-byte aligned operands)");
+  return lora_bwd_b_fast(M, N, r, groups, dy, lddy, Bt, ldbt, t, ldt, dt, lddt, dB, alpha_dt, alpha_db, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int ns_gemm_tn_masked(int dtype, long long M, int I, int J, const void* X, long long ldx, const void* Y, long long ldy, float* G,
                       long long si, long long sj, float alpha, const unsigned int* xbits, long long xbits_ld, void* stream) {
   NS_CHECK_ARG(valid_dtype(dtype), "ns_gemm_tn_masked: bad dtype %d", dtype);

@@ -656,24 +656,30 @@ __global__ void transpose_kernel(int rows, int cols, const TS* __restrict__ s, l
   }
 }
 
-// Many small transposes in one launch (the per-step refresh of the LoRA A/B operand layouts): blockIdx.z picks the job.
+// Many small transposes in one launch (the per-step refresh of the LoRA A/B operand layouts): blockIdx.y picks the job, the
+// blocks of a job stride over ITS 32x32 tiles.  (A grid of max_rows x max_cols tiles per job launched 245 k blocks for the 60
+// rank-32 operands of the training step -- (32, 2048) and (2048, 32) share no tile beyond the first row / column -- and spent
+// 157 us dispatching blocks that returned at once.)
 template <typename TS, typename TD>
 __global__ void transpose_batched_kernel(const ns_transpose_job* __restrict__ jobs) {
   __shared__ float tile[32][33];
-  const ns_transpose_job j = jobs[blockIdx.z];
-  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-  if (r0 >= j.ldd || c0 >= j.cols) return;             // block-uniform
+  const ns_transpose_job j = jobs[blockIdx.y];
   const TS* s = reinterpret_cast<const TS*>(j.src);
   TD* d = reinterpret_cast<TD*>(j.dst);
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int i = ty; i < 32; i += 8) {
-    const int r = r0 + i, c = c0 + tx;
-    tile[i][tx] = (r < j.rows && c < j.cols) ? to_f<TS>(s[static_cast<long long>(r) * j.lds + c]) * j.scale : 0.f;
-  }
-  __syncthreads();
-  for (int i = ty; i < 32; i += 8) {
-    const int c = c0 + i, r = r0 + tx;   // dst[c][r]
-    if (c < j.cols && r < j.ldd) d[static_cast<long long>(c) * j.ldd + r] = from_f<TD>(tile[tx][i]);
+  const int tiles_c = (j.cols + 31) / 32, tiles_r = (static_cast<int>(j.ldd) + 31) / 32;
+  for (int t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {      // block-uniform trip count
+    const int r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+    for (int i = ty; i < 32; i += 8) {
+      const int r = r0 + i, c = c0 + tx;
+      tile[i][tx] = (r < j.rows && c < j.cols) ? to_f<TS>(s[static_cast<long long>(r) * j.lds + c]) * j.scale : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+      const int c = c0 + i, r = r0 + tx;   // dst[c][r]
+      if (c < j.cols && r < j.ldd) d[static_cast<long long>(c) * j.ldd + r] = from_f<TD>(tile[tx][i]);
+    }
+    __syncthreads();
   }
 }
 
@@ -709,6 +715,25 @@ template <typename T>
 __global__ void dgelu_mul_kernel(long long n, const T* __restrict__ dy, const T* __restrict__ z, T* __restrict__ dz) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
     dz[i] = from_f<T>(to_f<T>(dy[i]) * dgelu_erf(to_f<T>(z[i])));
+}
+// bf16 storage, 16-byte aligned, n % 8 == 0: eight elements per thread and trip, the derivative in the fitted-tanh form every bf16
+// GEMM epilogue uses (ns_common.cuh dgelu_fast: 1.3e-4 from the erf form, below a bf16 ulp).  The scalar erf loop above took
+// 108 us for the stem's (64, 1500, 512) gradient, 2.4x the time of its 295 MB of traffic.
+__global__ void __launch_bounds__(256) dgelu_mul_bf16x8_kernel(long long n8, const uint4* __restrict__ dy, const uint4* __restrict__ z,
+                                                                uint4* __restrict__ dz) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 a = __ldg(dy + i), b = __ldg(z + i);
+    const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&av[k]));
+      const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bv[k]));
+      const __nv_bfloat162 r = __floats2bfloat162_rn(g.x * dgelu_fast(x.x), g.y * dgelu_fast(x.y));
+      o[k] = *reinterpret_cast<const uint32_t*>(&r);
+    }
+    dz[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
 }
 
 __global__ void sumsq_kernel(long long n, const float* __restrict__ g, float* out) {
@@ -948,7 +973,8 @@ int ns_transpose_batched(int sdt, int ddt, int n_jobs, int max_rows_pad, int max
                "ns_transpose_batched: bad arguments");
   if (n_jobs == 0) return NS_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  dim3 grid((max_cols + 31) / 32, (max_rows_pad + 31) / 32, n_jobs);
+  const long long tiles = static_cast<long long>((max_cols + 31) / 32) * ((max_rows_pad + 31) / 32);
+  dim3 grid(static_cast<unsigned>(tiles < 256 ? tiles : 256), n_jobs);
   if (sdt == NS_F32 && ddt == NS_BF16) transpose_batched_kernel<float, bf16><<<grid, 256, 0, st>>>(jobs_device);
   else if (sdt == NS_F32 && ddt == NS_F32) transpose_batched_kernel<float, float><<<grid, 256, 0, st>>>(jobs_device);
   else if (sdt == NS_BF16 && ddt == NS_BF16) transpose_batched_kernel<bf16, bf16><<<grid, 256, 0, st>>>(jobs_device);
@@ -992,7 +1018,9 @@ int ns_dgelu_mul(int dtype, long long n, const void* dy, const void* z, void* dz
   NS_CHECK_ARG(valid_dtype(dtype) && n >= 0 && dy && z && dz, "ns_dgelu_mul: bad arguments");
   if (n == 0) return NS_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == NS_BF16) dgelu_mul_kernel<bf16><<<grid_for(n, 256), 256, 0, st>>>(n, reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(z), reinterpret_cast<bf16*>(dz));
+  const bool vec = dtype == NS_BF16 && n % 8 == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(dz)) & 15) == 0;
+  if (vec) dgelu_mul_bf16x8_kernel<<<grid_for(n / 8, 256), 256, 0, st>>>(n / 8, reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(z), reinterpret_cast<uint4*>(dz));
+  else if (dtype == NS_BF16) dgelu_mul_kernel<bf16><<<grid_for(n, 256), 256, 0, st>>>(n, reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(z), reinterpret_cast<bf16*>(dz));
   else dgelu_mul_kernel<float><<<grid_for(n, 256), 256, 0, st>>>(n, reinterpret_cast<const float*>(dy), reinterpret_cast<const float*>(z), reinterpret_cast<float*>(dz));
   NS_LAUNCH_CHECK();
   count(C_OTHER);

@@ -49,6 +49,9 @@ int gemm_tn_fast(long long M, int I, int J, const void* X, long long ldx, const 
                  long long si, long long sj, float alpha, cudaStream_t st, const uint32_t* xbits = nullptr, long long xbits_ld = 0);
 int gemm_tn_grouped_fast(long long M, int I, int J, int groups, const void* X, long long ldx, const void* Y, long long ldy, float* G,
                          long long si, long long sj, const float* alphas, cudaStream_t st);
+// ns_lora_bwd.cu: dt = alpha' dy B and dB += dy^T t in one pass over dy
+int lora_bwd_b_fast(long long M, int N, int r, int groups, const void* dy, long long lddy, const void* Bt, long long ldbt, const void* t,
+                    long long ldt, void* dt, long long lddt, float* dB, const float* alpha_dt, const float* alpha_db, cudaStream_t st);
 int conv3_wgrad_fast(int B, int Tin, int Cp, int N, int stride, const void* dz, const void* x, float* dw, cudaStream_t st);
 
 // ns_skinny.cu: D = epi(LN(x) W^T) for M <= 128 rows (decoder step); NS_ERR_UNSUPPORTED when the shape does not qualify

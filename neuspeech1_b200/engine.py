@@ -35,6 +35,7 @@ _NO_PDL = bool(os.environ.get("NS_NO_PDL"))                     # developer A/B 
 _NO_AR_OVERLAP = bool(os.environ.get("NS_NO_AR_OVERLAP"))       # developer A/B switch: one all-reduce after the whole backward
 _NO_MASK_STAGE = bool(os.environ.get("NS_NO_MASK_STAGE"))       # developer A/B switch: mma.sync ns_lora_down / ns_lora_da instead of the mask stages
 _NO_GELU_DERIV = bool(os.environ.get("NS_NO_GELU_DERIV"))       # developer A/B switch: save the GELU pre-activation, not the derivative
+_NO_FUSED_BWD_B = bool(os.environ.get("NS_NO_FUSED_BWD_B"))     # developer A/B switch: dt = dy B and dB = dy^T t as two passes over dy
 _NO_GEMM_MASK = bool(os.environ.get("NS_NO_GEMM_MASK"))         # developer A/B switch: dropout correction pass instead of the masked GEMM product
 ENC_LORA_TARGETS = ("q_proj", "k_proj", "v_proj", "out_proj", "fc1", "fc2")
 
@@ -295,6 +296,22 @@ class WhisperEEGEngine:
         if self.dims.lora_r % 16 != 0 or (N is not None and N % 16 != 0):     # tcgen05 operand rules of both products
             return None
         return self._bits(layer, (target,), M, K)[0]
+
+    def _fused_bwd_b(self, N: int) -> bool:
+        """ns_lora_bwd_b takes the shape: bf16 storage, rank 32, N a multiple of 128 whose N/128 dB accumulators and two dt
+        accumulators fit the 512 TMEM columns (fc1's N = 2048 gradient does not: 16 x 32 columns alone fill them)."""
+        return (not _NO_FUSED_BWD_B and self.dtype == torch.bfloat16 and self.dims.lora_r == 32 and N % 128 == 0 and N // 128 * 32 + 64 <= 512
+                and N // 64 * 4096 + 2 * 16384 + 2 * 32768 + 1280 <= 232448)
+
+    def _lora_bwd_b(self, dy: torch.Tensor, Bt: torch.Tensor, t: torch.Tensor, dt_out: torch.Tensor, dB: torch.Tensor, s: float):
+        """dt = alpha' dy B and dB += dy^T t of one adapter: one pass over dy when the shape qualifies, else two products."""
+        r = self.dims.lora_r
+        N = dy.shape[1]
+        if self._fused_bwd_b(N):
+            ops.lora_bwd_b(dy, Bt, t, dt_out, dB, N, r, [s], [1.0])
+        else:
+            ops.gemm_nt(dy, Bt, dt_out, self._ep(alpha=s, alpha_cols=r))
+            ops.gemm_tn(dy, t, dB, r, 1)
 
     def _lora_da_fix(self, x: torch.Tensor, dt: torch.Tensor, dx: Optional[torch.Tensor], At: torch.Tensor, layer: int, targets,
                      z: Optional[torch.Tensor] = None):
@@ -759,8 +776,7 @@ class WhisperEEGEngine:
             dz1 = ws.get("dz1", (M, F), dt)
             if self.has_lora:
                 dt2 = ws.get("dt_r", (M, r), dt)
-                ops.gemm_nt(dh, W[k + ".B_fc2_t"], dt2, self._ep(alpha=s, alpha_cols=r))
-                ops.gemm_tn(dh, g("t_2"), G("fc2", "B"), r, 1)
+                self._lora_bwd_b(dh, W[k + ".B_fc2_t"], g("t_2"), dt2, G("fc2", "B"), s)
                 db = self._drop_plane(i, "fc2", M, F, d)
                 ops.gemm_nt(dh, W[k + ".w2_t"], dz1, self._ep(act=ACT_DGELU, aux_in=g("z1"), ldaux=F, drop_bits=db, aux_deriv=self._gelu_deriv(True)), a2=dt2,
                             w2=W[k + ".A_fc2_t"], k2=r)
@@ -771,8 +787,7 @@ class WhisperEEGEngine:
             du2 = ws.get("du", (M, d), dt)
             if self.has_lora:
                 dt1 = ws.get("dt_r", (M, r), dt)
-                ops.gemm_nt(dz1, W[k + ".B_fc1_t"], dt1, self._ep(alpha=s, alpha_cols=r))
-                ops.gemm_tn(dz1, g("t_1"), G("fc1", "B"), r, 1)
+                self._lora_bwd_b(dz1, W[k + ".B_fc1_t"], g("t_1"), dt1, G("fc1", "B"), s)
                 # (long contraction, narrow output: the 128-wide tiles of the masked product re-read dz1 from L2 twice as often
                 # and cost more than the correction pass saves -- measured 234 + 43 us against 154 + 83 us)
                 db = self._drop_plane(i, "fc1", M, d, F) if F <= d else None
@@ -786,8 +801,7 @@ class WhisperEEGEngine:
             do = ws.get("do", (M, d), dt)
             if self.has_lora:
                 dto = ws.get("dt_r", (M, r), dt)
-                ops.gemm_nt(dhm, W[k + ".B_out_proj_t"], dto, self._ep(alpha=s, alpha_cols=r))
-                ops.gemm_tn(dhm, g("t_o"), G("out_proj", "B"), r, 1)
+                self._lora_bwd_b(dhm, W[k + ".B_out_proj_t"], g("t_o"), dto, G("out_proj", "B"), s)
                 db = self._drop_plane(i, "out_proj", M, d, d)
                 ops.gemm_nt(dhm, W[k + ".wo_t"], do, self._ep(drop_bits=db), a2=dto, w2=W[k + ".A_out_proj_t"], k2=r)
                 self._lora_da_fix(g("o"), dto, do if db is None else None, W[k + ".A_out_proj_t"], i, ("out_proj",))
@@ -804,9 +818,13 @@ class WhisperEEGEngine:
                 dtq = ws.get("dt_qkv", (M, 3 * r), dt)
                 t_qkv = g("t_qkv")
                 # dt_g = alpha' dy_g B_g and dB_g = dy_g^T t_g for q, k, v: block-diagonal products, one launch each
-                ops.gemm_nt(dqkv, W[k + ".B_qkv_t"], dtq, self._ep(alpha=s, alpha_cols=3 * r, a_group_cols=r), K=d)
                 off_b, _ = lay.entries[lora_module_name(i, "q_proj") + ".lora_B.default.weight"]
-                ops.gemm_tn_grouped(dqkv, t_qkv, self.grad[off_b: off_b + 3 * d * r].view(3 * d, r), d, r, r, 1, [qs, 1.0, 1.0])
+                dB_qkv = self.grad[off_b: off_b + 3 * d * r].view(3 * d, r)
+                if self._fused_bwd_b(d):
+                    ops.lora_bwd_b(dqkv, W[k + ".B_qkv_t"], t_qkv, dtq, dB_qkv, d, r, [s, s, s], [qs, 1.0, 1.0])
+                else:
+                    ops.gemm_nt(dqkv, W[k + ".B_qkv_t"], dtq, self._ep(alpha=s, alpha_cols=3 * r, a_group_cols=r), K=d)
+                    ops.gemm_tn_grouped(dqkv, t_qkv, dB_qkv, d, r, r, 1, [qs, 1.0, 1.0])
                 # dA for q,k,v in one launch: the three (r,d) gradients are contiguous = one (3r, d) matrix
                 ops.gemm_nt(dqkv, W[k + ".wqkv_t"], du1, self._ep(), a2=dtq, w2=W[k + ".A_qkv_t"], k2=3 * r)
                 self._lora_da_fix(g("u1"), dtq, du1, W[k + ".A_qkv_t"], i, ("q_proj", "k_proj", "v_proj"))

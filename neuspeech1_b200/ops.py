@@ -315,6 +315,19 @@ def gemm_tn_grouped(x: torch.Tensor, y: torch.Tensor, g: torch.Tensor, I: int, J
     return g
 
 
+def lora_bwd_b(dy: torch.Tensor, bt: torch.Tensor, t: torch.Tensor, dt: torch.Tensor, db: torch.Tensor, N: int, r: int, alpha_dt, alpha_db):
+    """One pass over dy (M, groups*N): dt[:, g*r:(g+1)*r] = alpha_dt[g] * dy_g @ bt_g^T and db[g*N:(g+1)*N] += alpha_db[g] * dy_g^T @ t_g
+    (ns_lora_bwd_b; bt (groups*r, N) = B^T, db (groups*N, r) fp32 contiguous)."""
+    groups = len(alpha_dt)
+    a1 = (C.c_float * groups)(*[float(a) for a in alpha_dt])
+    a2 = (C.c_float * groups)(*[float(a) for a in alpha_db])
+    M = dy.shape[0]
+    assert db.is_contiguous() and db.dtype == torch.float32 and db.shape == (groups * N, r)
+    _call("ns_lora_bwd_b", (4.0 * M * N * r * groups, 0), ns_dtype(dy), M, N, r, groups, _p(dy), dy.stride(0), _p(bt), bt.stride(0), _p(t),
+          t.stride(0), _p(dt), dt.stride(0), _p(db), a1, a2, _stream())
+    return dt
+
+
 def gemm_tn_masked(x: torch.Tensor, y: torch.Tensor, g: torch.Tensor, si: int, sj: int, xbits: torch.Tensor, alpha: float = 1.0):
     """g[i*si + j*sj] += alpha * sum_m (x . keep)[m,i] * y[m,j]; xbits = ONE adapter's (rows, words) plane of dropout_bits."""
     I, J = x.shape[1], y.shape[1]

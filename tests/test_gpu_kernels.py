@@ -281,6 +281,34 @@ def test_block_diagonal_rank_products(M, d, r, dtype):
         assert rel(dB[g * d:(g + 1) * d], refB) < (2e-3 if dtype == torch.bfloat16 else 1e-4), (g, rel(dB[g * d:(g + 1) * d], refB))
 
 
+@pytest.mark.parametrize("M,N,groups", [(3000, 512, 1), (96000, 512, 1), (777, 256, 3), (20001, 1280, 1), (12800, 512, 3), (130, 128, 2),
+                                        (64 * 1500, 512, 3)])
+def test_lora_bwd_b_one_pass(M, N, groups):
+    """ns_lora_bwd_b: dt_g = alpha_dt[g] dy_g B_g and dB_g += alpha_db[g] dy_g^T t_g from ONE pass over dy (both tcgen05 products
+    read the same shared-memory chunk, K-major and MN-major), against fp32 torch on the same bf16 operands; ragged last slab,
+    more slabs than CTAs, stacked groups, dB accumulated onto a non-zero buffer; dt untouched outside the groups' columns."""
+    r = 32
+    bf = torch.bfloat16
+    dy = rnd(M, groups * N, dtype=bf, seed=1)
+    Bt = rnd(groups * r, N, dtype=bf, scale=N ** -0.5, seed=2)
+    t = rnd(M, groups * r, dtype=bf, scale=0.3, seed=3)
+    dt = torch.full((M, groups * r + 8), 5.0, dtype=bf, device=DEV)        # wider buffer: the pad columns must survive
+    dB = torch.full((groups * N, r), 0.25, dtype=torch.float32, device=DEV)
+    a_dt = [1.5, 0.5, 2.0, 1.0][:groups]; a_db = [0.125, 1.0, 2.0, 0.5][:groups]
+    ops.lora_bwd_b(dy, Bt, t, dt, dB, N, r, a_dt, a_db)
+    assert bool((dt[:, groups * r:] == 5.0).all())
+    for g in range(groups):
+        yg = dy[:, g * N:(g + 1) * N].float()
+        ref = a_dt[g] * yg @ Bt[g * r:(g + 1) * r].float().t()
+        e = rel(dt[:, g * r:(g + 1) * r].float(), ref)
+        assert e < tol(bf), (g, e)
+        refB = a_db[g] * yg.t() @ t[:, g * r:(g + 1) * r].float() + 0.25
+        e = rel(dB[g * N:(g + 1) * N], refB)
+        assert e < 2e-3, (g, e)
+    with pytest.raises(Exception):                                        # r != 32: refused loudly, nothing silently skipped
+        ops.lora_bwd_b(dy, Bt[:, :N], t, dt, torch.zeros(groups * N, 16, device=DEV), N, 16, a_dt, a_db)
+
+
 @pytest.mark.parametrize("M,N,K,ln,flags", [(128, 1536, 512, True, "bias,alpha"), (128, 512, 512, False, "bias,res"), (128, 2048, 512, True, "bias,gelu"),
                                             (128, 512, 2048, False, "bias,res"), (37, 512, 512, True, "bias"), (1, 100, 256, True, ""),
                                             (100, 1000, 1280, False, "bias,gelu"), (128, 512, 512, True, "f32out")])
@@ -617,6 +645,29 @@ def test_transpose_cast_add_dgelu():
     y = torch.empty_like(a); assert torch.equal(ops.add(a, a, y), a + a)
     dz = torch.empty_like(a); ops.dgelu_mul(a, a * 2, dz)
     assert rel(dz, a * gelu_grad(a * 2)) < 1e-5
+    # bf16 storage: the 8-element vector path (fitted-tanh derivative, 1.3e-4 from erf) and the scalar tail path
+    for n in (8 * 1000, 8 * 1000 + 3):
+        g = rnd(n, seed=2).to(torch.bfloat16); z = (2 * rnd(n, seed=3)).to(torch.bfloat16)
+        dz = torch.empty_like(g); ops.dgelu_mul(g, z, dz)
+        assert rel(dz, g.float() * gelu_grad(z.float())) < 6e-3
+
+
+def test_transpose_batched_mixed_shapes():
+    """ns_transpose_batched with jobs whose tile grids share almost nothing (the rank-32 LoRA operands: (32, 2048) next to
+    (2048, 32)), a ragged one, a scaled one, and a job with more tiles than blocks per job (strided tile loop)."""
+    shapes = [(32, 2048), (2048, 32), (96, 512), (100, 37), (1024, 640)]
+    pairs = []
+    for i, (r, c) in enumerate(shapes):
+        src = rnd(r, c, seed=10 + i)
+        ld = (r + 15) // 16 * 16
+        dst = torch.full((c, ld), 7.0, dtype=torch.bfloat16, device=DEV)
+        pairs.append((src, dst, 0.5) if i == 2 else (src, dst))
+    ops.TransposeBatch(pairs, DEV).run()
+    for pr in pairs:
+        src, dst = pr[0], pr[1]
+        sc = pr[2] if len(pr) > 2 else 1.0
+        assert torch.equal(dst[:, :src.shape[0]], (src.t() * sc).to(torch.bfloat16))
+        assert bool((dst[:, src.shape[0]:] == 0).all())
 
 
 # ------------------------------------------------------------------------------------------------ augmentation pass
