@@ -87,6 +87,12 @@ typedef struct {
                                  the activation: a handful of FMAs more), NS_ACT_DGELU multiplies by aux_in as it is -- the
                                  backward epilogue loses its transcendental and a dozen instructions per element.  The forward
                                  and the backward call of one layer must agree on it. */
+  const unsigned int* drop_seed;  /* drop_mode 2: like 1, but the mask stage DRAWS the planes itself (the counter hash of
+                                 ns_dropout_bits: same words for the same seed / salt / p) and stores them to drop_bits for the
+                                 backward consumers -- no separate ns_dropout_bits launch, the integer hash runs under the
+                                 memory-bound stream of x.  drop_seed: device word holding the step seed. */
+  const unsigned int* drop_salts; /* drop_mode 2: HOST array, one salt per stacked adapter (N / 32 <= 4 of them) */
+  float        drop_p;            /* drop_mode 2: dropout probability */
 } ns_epilogue;
 
 int ns_gemm_nt(int dtype, long long M, int N, int K, const void* A, long long lda, const void* W, long long ldw,
@@ -116,11 +122,15 @@ int ns_gemm_tn_grouped(int dtype, long long M, int I, int J, int groups, const v
  *   dt[m, g*r + j]        = alpha_dt[g] * sum_n dy[m, g*N + n] * Bt[g*r + j, n]      (dt = alpha' dy B; replaces ns_gemm_nt on a rank-r tile)
  *   dB[(g*N + n)*r + j]  += alpha_db[g] * sum_m dy[m, g*N + n] * t[m, g*r + j]       (fp32, caller zeroes; replaces ns_gemm_tn[_grouped])
  * for `groups` (<= 4) adapters stacked along the columns of dy (M, groups*N), t and dt (M, groups*r) and the rows of Bt
- * (groups*r, N) = B^T.  bf16 tcgen05 path only: r == 32, N % 128 == 0, N <= 1408, 16-byte aligned operands; NS_ERR_UNSUPPORTED
- * otherwise (the caller then issues the two separate products).  alpha_dt / alpha_db: host arrays of `groups` scales. */
+ * (groups*r, N) = B^T.  bf16 tcgen05 path only: r == 32, N % 128 == 0, 16-byte aligned operands; NS_ERR_UNSUPPORTED otherwise
+ * (the caller then issues the two separate products).  alpha_dt / alpha_db: host arrays of `groups` scales.
+ * N > 1792 (fc1's 2048 output columns) runs as column parts on different CTAs that combine their partial dt through a
+ * caller-owned workspace: ns_lora_bwd_b_workspace_bytes() bytes (0: none needed, -1: shape not supported), 16-byte aligned,
+ * its first (groups * ceil(M/128) * 16, rounded up to 256) bytes zeroed ONCE by the caller -- the kernel leaves them zero. */
 int ns_lora_bwd_b(int dtype, long long M, int N, int r, int groups, const void* dy, long long lddy, const void* Bt, long long ldbt,
                   const void* t, long long ldt, void* dt, long long lddt, float* dB, const float* alpha_dt, const float* alpha_db,
-                  void* stream);
+                  void* workspace, long long workspace_bytes, void* stream);
+long long ns_lora_bwd_b_workspace_bytes(long long M, int N, int r, int groups);
 /* Same with X masked by a dropout plane (ns_dropout_bits, one adapter) on its way to the tensor cores:
  *   G += alpha * (X . keep)^T Y  --  dA = dt'^T (x . keep) of a LoRA branch under dropout, x read once.  bf16 tcgen05 path only
  *   (I % 64 == 0, xbits_ld even); NS_ERR_UNSUPPORTED otherwise. */

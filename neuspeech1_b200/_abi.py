@@ -25,7 +25,8 @@ class Epilogue(C.Structure):
     _fields_ = [("bias", c_vp), ("alpha", c_f), ("alpha_cols", c_i), ("act", c_i), ("aux_in", c_vp), ("aux_out", c_vp),
                 ("ldaux", c_ll), ("residual", c_vp), ("ldr", c_ll), ("res_mod", c_i), ("out_dtype", c_i),
                 ("a2_group_cols", c_i), ("drop_bits", c_vp), ("drop_ld", c_ll), ("drop_mode", c_i),
-                ("drop_gstride", c_ll), ("a_group_cols", c_i), ("aux_deriv", c_i)]
+                ("drop_gstride", c_ll), ("a_group_cols", c_i), ("aux_deriv", c_i), ("drop_seed", c_vp), ("drop_salts", c_vp),
+                ("drop_p", c_f)]
 
 
 class DecoderLayer(C.Structure):
@@ -68,7 +69,8 @@ SIGNATURES = {
     "ns_ln_gemm_nt": [c_i, c_ll, c_i, c_i, c_vp, c_ll, c_vp, c_vp, c_f, c_vp, c_ll, c_vp, c_ll, C.POINTER(Epilogue), c_vp],
     "ns_gemm_tn": [c_i, c_ll, c_i, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_ll, c_f, c_vp],
     "ns_gemm_tn_grouped": [c_i, c_ll, c_i, c_i, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_ll, c_vp, c_vp],
-    "ns_lora_bwd_b": [c_i, c_ll, c_i, c_i, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_vp, c_vp, c_vp],
+    "ns_lora_bwd_b": [c_i, c_ll, c_i, c_i, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_vp, c_vp, c_vp, c_ll, c_vp],
+    "ns_lora_bwd_b_workspace_bytes": [c_ll, c_i, c_i, c_i],
     "ns_gemm_tn_masked": [c_i, c_ll, c_i, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_ll, c_f, c_vp, c_ll, c_vp],
     "ns_conv3_fwd": [c_i, c_i, c_i, c_i, c_i, c_i, c_vp, c_vp, c_vp, C.POINTER(Epilogue), c_vp],
     "ns_conv3_dgrad": [c_i, c_i, c_i, c_i, c_i, c_i, c_vp, c_vp, c_vp, C.POINTER(Epilogue), c_vp],
@@ -108,7 +110,7 @@ SIGNATURES = {
     "ns_adamw_clip": [c_ll, c_vp, c_vp, c_vp, c_vp, c_vp, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_vp],
 }
 
-RESTYPES = {"ns_attention_bwd_workspace_bytes": c_ll, "ns_dropout_bits_words": c_ll}      # everything else returns an int status
+RESTYPES = {"ns_attention_bwd_workspace_bytes": c_ll, "ns_dropout_bits_words": c_ll, "ns_lora_bwd_b_workspace_bytes": c_ll}      # everything else returns an int status
 
 _lib = None
 

@@ -188,7 +188,7 @@ int ns_gemm_tn_grouped(int dtype, long long M, int I, int J, int groups, const v
 
 int ns_lora_bwd_b(int dtype, long long M, int N, int r, int groups, const void* dy, long long lddy, const void* Bt, long long ldbt,
                   const void* t, long long ldt, void* dt, long long lddt, float* dB, const float* alpha_dt, const float* alpha_db,
-                  void* stream) {
+                  void* workspace, long long workspace_bytes, void* stream) {
   NS_CHECK_ARG(valid_dtype(dtype), "ns_lora_bwd_b: bad dtype %d", dtype);
   NS_CHECK_ARG(M >= 0 && N > 0 && r > 0 && groups >= 1 && groups <= 4 && dy && Bt && t && dt && dB && alpha_dt && alpha_db,
                "ns_lora_bwd_b: bad shape/pointers");
@@ -200,9 +200,12 @@ int ns_lora_bwd_b(int dtype, long long M, int N, int r, int groups, const void* 
     set_error("ns_lora_bwd_b: bf16 storage and the tcgen05 path only");
     return NS_ERR_UNSUPPORTED;
   }
-  set_error("ns_lora_bwd_b: shape does not qualify (r == 32, N %% 128 == 0, N <= 1408, 16-byte aligned operands)");
-  return lora_bwd_b_fast(M, N, r, groups, dy, lddy, Bt, ldbt, t, ldt, dt, lddt, dB, alpha_dt, alpha_db, reinterpret_cast<cudaStream_t>(stream));
+  set_error("ns_lora_bwd_b: shape does not qualify (r == 32, N %% 128 == 0, at most 4 column parts of 14 chunks, 16-byte aligned operands)");
+  return lora_bwd_b_fast(M, N, r, groups, dy, lddy, Bt, ldbt, t, ldt, dt, lddt, dB, alpha_dt, alpha_db, workspace, workspace_bytes,
+                         reinterpret_cast<cudaStream_t>(stream));
 }
+
+long long ns_lora_bwd_b_workspace_bytes(long long M, int N, int r, int groups) { return lora_bwd_b_workspace_bytes(M, N, r, groups); }
 
 int ns_gemm_tn_masked(int dtype, long long M, int I, int J, const void* X, long long ldx, const void* Y, long long ldy, float* G,
                       long long si, long long sj, float alpha, const unsigned int* xbits, long long xbits_ld, void* stream) {

@@ -184,6 +184,9 @@ struct EpiDev {
   long long drop_gstride;
   int a_group_cols;            // block-diagonal main product (see ns_epilogue::a_group_cols)
   int aux_deriv;               // aux holds gelu'(z) instead of z (see ns_epilogue::aux_deriv)
+  const uint32_t* drop_seed;   // drop_mode 2: the mask stage draws the planes (see ns_epilogue::drop_seed)
+  uint32_t drop_salts[4];
+  float drop_p;
 };
 
 inline EpiDev make_epi(const ns_epilogue* ep, int dtype) {
@@ -198,6 +201,10 @@ inline EpiDev make_epi(const ns_epilogue* ep, int dtype) {
     e.out_f32 = (ep->out_dtype == NS_F32);
     e.drop_bits = ep->drop_bits; e.drop_ld = ep->drop_ld; e.drop_mode = ep->drop_mode; e.drop_gstride = ep->drop_gstride;
     e.a_group_cols = ep->a_group_cols; e.aux_deriv = ep->aux_deriv;
+    if (ep->drop_mode == 2 && ep->drop_salts) {
+      e.drop_seed = ep->drop_seed; e.drop_p = ep->drop_p;
+      for (int i = 0; i < 4; ++i) e.drop_salts[i] = ep->drop_salts[i];     // the caller sizes the array for 4 adapters
+    }
   }
   return e;
 }

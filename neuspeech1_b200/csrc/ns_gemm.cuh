@@ -51,7 +51,9 @@ int gemm_tn_grouped_fast(long long M, int I, int J, int groups, const void* X, l
                          long long si, long long sj, const float* alphas, cudaStream_t st);
 // ns_lora_bwd.cu: dt = alpha' dy B and dB += dy^T t in one pass over dy
 int lora_bwd_b_fast(long long M, int N, int r, int groups, const void* dy, long long lddy, const void* Bt, long long ldbt, const void* t,
-                    long long ldt, void* dt, long long lddt, float* dB, const float* alpha_dt, const float* alpha_db, cudaStream_t st);
+                    long long ldt, void* dt, long long lddt, float* dB, const float* alpha_dt, const float* alpha_db, void* workspace,
+                    long long workspace_bytes, cudaStream_t st);
+long long lora_bwd_b_workspace_bytes(long long M, int N, int r, int groups);
 int conv3_wgrad_fast(int B, int Tin, int Cp, int N, int stride, const void* dz, const void* x, float* dw, cudaStream_t st);
 
 // ns_skinny.cu: D = epi(LN(x) W^T) for M <= 128 rows (decoder step); NS_ERR_UNSUPPORTED when the shape does not qualify

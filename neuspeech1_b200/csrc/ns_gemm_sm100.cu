@@ -12,6 +12,7 @@
 #include "ns_common.cuh"
 #include "ns_sm100.cuh"
 #include "ns_gemm.cuh"
+#include "ns_dropout.cuh"
 
 #include <stdlib.h>
 
@@ -143,6 +144,9 @@ struct TileProg {
   // AM (A-operand mask, the LoRA down product under branch dropout): plane of adapter g = n_tile starts at am_bits + g * am_gstride
   const uint32_t* am_bits;
   long long am_ld, am_gstride;
+  // am_seed != NULL: the mask stage draws the plane words (drop_plane_word) and stores them to am_bits instead of loading them
+  const uint32_t* am_seed;
+  uint32_t am_salts[4], am_thr;
 };
 
 struct Maps {
@@ -463,9 +467,30 @@ gemm_nt_kernel(const __grid_constant__ Maps maps, const __grid_constant__ TilePr
       const int b = p.fd_tpb.div(m_tile);
       const int t = (m_tile - b * p.tiles_per_batch) * kBM + r;
       const bool valid = t < p.tout;                     // rows past the end arrive zero-filled
-      const uint2* brow = reinterpret_cast<const uint2*>(p.am_bits + static_cast<long long>(n_tile) * p.am_gstride +
-                                                         (static_cast<long long>(b) * p.tout + (valid ? t : 0)) * p.am_ld);
+      const long long grow = static_cast<long long>(b) * p.tout + (valid ? t : 0);      // row of the plane = row of x
+      uint2* brow = const_cast<uint2*>(reinterpret_cast<const uint2*>(p.am_bits + static_cast<long long>(n_tile) * p.am_gstride + grow * p.am_ld));
       const uint2 none = make_uint2(0u, 0u);
+      if (p.am_seed) {
+        // draw: the integer hash (about 240 instructions per row and k block) hides under the stream of x -- the stage has
+        // ~800 cycles per k block before the TMA ring runs dry, and the separate generator launch (and its read here) goes away
+        const uint32_t ms = __ldg(p.am_seed) ^ p.am_salts[n_tile & 3];
+        const uint32_t hrow = static_cast<uint32_t>(grow);
+        for (int kb = 0; kb < nkb; ++kb) {
+          uint2 wc = none;
+          if (valid) {
+            wc.x = drop_plane_word(hrow, static_cast<uint32_t>(2 * kb), ms, p.am_thr);
+            wc.y = drop_plane_word(hrow, static_cast<uint32_t>(2 * kb + 1), ms, p.am_thr);
+            brow[kb] = wc;
+          }
+          mbar_wait(full_bar(stage), phase);
+          mask_row128(smem_base + stage * Cfg::kStageBytes + static_cast<uint32_t>(r) * 128u, sw, wc);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(mfull_bar(stage));
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+        continue;
+      }
       uint2 w0 = (valid && nkb > 0) ? __ldg(brow) : none;
       uint2 w1 = (valid && nkb > 1) ? __ldg(brow + 1) : none;
       for (int kb = 0; kb < nkb; ++kb) {
@@ -1262,7 +1287,11 @@ int gemm_nt_fast(long long M, int N, int K, const void* A, long long lda, const 
     }
     bn = 32; cg = 1;
   }
-  const bool am = epi.drop_bits && epi.drop_mode == 1;
+  const bool am = epi.drop_bits && (epi.drop_mode == 1 || epi.drop_mode == 2);
+  if (am && epi.drop_mode == 2 && (!epi.drop_seed || N > 128 || epi.drop_p < 0.f || epi.drop_p >= 1.f)) {
+    set_error("ns_gemm_nt: drop_mode 2 needs drop_seed, drop_salts, 0 <= drop_p < 1 and at most 4 stacked adapters");
+    return NS_ERR_ARG;
+  }
   if (am) {
     // A-operand mask (LoRA down product): 32-wide tiles, one adapter per column tile
     if (A2 || N % 32 != 0 || K % 64 != 0 || epi.drop_ld % 2 != 0 || (reinterpret_cast<uintptr_t>(epi.drop_bits) & 7) != 0 ||
@@ -1330,6 +1359,10 @@ int gemm_nt_fast(long long M, int N, int K, const void* A, long long lda, const 
   fill_epi(prog, epi);
   if (am) {
     prog.am_bits = epi.drop_bits; prog.am_ld = epi.drop_ld; prog.am_gstride = epi.drop_gstride;
+    if (epi.drop_mode == 2) {
+      prog.am_seed = epi.drop_seed; prog.am_thr = drop_thr16(epi.drop_p);
+      for (int i = 0; i < 4; ++i) prog.am_salts[i] = epi.drop_salts[i];
+    }
     prog.epi.drop_bits = nullptr;
   }
   if (int r = setup_out_maps(maps, prog, bn)) return r;

@@ -31,28 +31,12 @@
 //   ns_dropout_apply  y = x . keep          (fp32 parity mode / reference path of the tests: materialises the masked input)
 //   ns_seed_advance   seed <- lowbias32(seed + 0x9E3779B9)          (inside the captured training step: a new mask per replay)
 #include "ns_common.cuh"
+#include "ns_dropout.cuh"
 
 #include <stdlib.h>
 
 namespace ns {
 
-__device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
-  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
-  return x;
-}
-constexpr uint32_t kRowMul = 0x9E3779B1u, kColMul = 0x85EBCA77u, kIdxMul = 0xC2B2AE35u;
-// the 32 dropped flags of (row, 32-column block): see the file header
-__device__ __forceinline__ uint32_t mix1(uint32_t x) { x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; return x; }
-__device__ __forceinline__ uint32_t drop_plane_word(uint32_t row, uint32_t w, uint32_t module_seed, uint32_t thr) {
-  const uint32_t km = lowbias32((row * kRowMul) ^ (w * kColMul) ^ module_seed);
-  uint32_t d = 0;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const uint32_t r = mix1(km + static_cast<uint32_t>(i + 1) * kIdxMul);
-    d = ((thr >> i) & 1u) ? (d | r) : (d & r);
-  }
-  return d;
-}
 // AND-mask for a packed bf16 pair from two drop bits: 0 where dropped
 __device__ __forceinline__ uint32_t keep_mask2(uint32_t drop_lo, uint32_t drop_hi) {
   return ~(((drop_lo & 1u) | ((drop_hi & 1u) << 16)) * 0xFFFFu);
@@ -587,10 +571,6 @@ static int launch_down(long long M, int K, const void* x, long long ldx, const v
   return launch_down_kernel(lora_down_kernel<G, NT, WARPS, MT, 1>, ctas, WARPS * 32, smem, M, K, x, ldx, A, lda, t, ldt, alpha, bits, st);
 }
 
-static uint32_t thr16(float p) {
-  const double v = static_cast<double>(p) * 65536.0 + 0.5;
-  return v <= 0 ? 0u : (v >= 65535.0 ? 65535u : static_cast<uint32_t>(v));
-}
 
 }  // namespace ns
 
@@ -630,7 +610,7 @@ int ns_dropout_bits(long long rows, int cols, int G, const unsigned int* seed, c
   long long blocks = (rows * words + 255) / 256;
   const long long cap = (static_cast<long long>(sm_count()) * 8 + G - 1) / G;    // about 8 CTAs per SM in total, grid-stride loops
   if (blocks > cap) blocks = cap;
-  dropout_bits_kernel<<<dim3(static_cast<unsigned>(blocks), G), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(rows, cols, words, seed, s, thr16(p), bits);
+  dropout_bits_kernel<<<dim3(static_cast<unsigned>(blocks), G), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(rows, cols, words, seed, s, drop_thr16(p), bits);
   NS_LAUNCH_CHECK();
   count(C_OTHER);
   return NS_OK;

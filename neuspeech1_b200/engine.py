@@ -35,6 +35,7 @@ _NO_PDL = bool(os.environ.get("NS_NO_PDL"))                     # developer A/B 
 _NO_AR_OVERLAP = bool(os.environ.get("NS_NO_AR_OVERLAP"))       # developer A/B switch: one all-reduce after the whole backward
 _NO_MASK_STAGE = bool(os.environ.get("NS_NO_MASK_STAGE"))       # developer A/B switch: mma.sync ns_lora_down / ns_lora_da instead of the mask stages
 _NO_GELU_DERIV = bool(os.environ.get("NS_NO_GELU_DERIV"))       # developer A/B switch: save the GELU pre-activation, not the derivative
+_NO_PLANE_FUSE = bool(os.environ.get("NS_NO_PLANE_FUSE"))       # developer A/B switch: dropout planes from ns_dropout_bits launches, not from the mask stage
 _NO_FUSED_BWD_B = bool(os.environ.get("NS_NO_FUSED_BWD_B"))     # developer A/B switch: dt = dy B and dB = dy^T t as two passes over dy
 _NO_GEMM_MASK = bool(os.environ.get("NS_NO_GEMM_MASK"))         # developer A/B switch: dropout correction pass instead of the masked GEMM product
 ENC_LORA_TARGETS = ("q_proj", "k_proj", "v_proj", "out_proj", "fc1", "fc2")
@@ -226,11 +227,19 @@ class WhisperEEGEngine:
         i0 = self._PLANE_ORDER.index(targets[0])
         return buf[i0: i0 + len(targets)]
 
+    def _mask_stage_draws(self, K: int) -> bool:
+        """The rank-32 down product of a K-wide input goes through the tcgen05 mask stage, which then also DRAWS the dropout
+        plane (ns_epilogue.drop_mode 2) and leaves it in `_bits` for the backward: no generator launch for that width."""
+        return (self.use_lora_kernels and self.dims.lora_r == 32 and K % 64 == 0 and self.dtype == torch.bfloat16
+                and not _NO_MASK_STAGE and not _NO_PLANE_FUSE)
+
     def _draw_planes(self, layer: int, M: int):
-        """ns_dropout_bits for all six adapters of one encoder layer (two launches)."""
+        """ns_dropout_bits for the adapters of one encoder layer whose planes the forward does not draw on the fly."""
         dm, p = self.dims, self._drop_p
-        ops.dropout_bits(M, dm.d_model, self.drop_seed, self._salts(layer, self._PLANE_ORDER), p, self._bits(layer, ("q_proj", "k_proj", "v_proj", "out_proj", "fc1"), M, dm.d_model))
-        ops.dropout_bits(M, dm.enc_ffn, self.drop_seed, self._salts(layer, ("fc2",)), p, self._bits(layer, ("fc2",), M, dm.enc_ffn))
+        if not self._mask_stage_draws(dm.d_model):
+            ops.dropout_bits(M, dm.d_model, self.drop_seed, self._salts(layer, self._PLANE_ORDER), p, self._bits(layer, ("q_proj", "k_proj", "v_proj", "out_proj", "fc1"), M, dm.d_model))
+        if not self._mask_stage_draws(dm.enc_ffn):
+            ops.dropout_bits(M, dm.enc_ffn, self.drop_seed, self._salts(layer, ("fc2",)), p, self._bits(layer, ("fc2",), M, dm.enc_ffn))
 
     def _planes_ahead(self, layer: int, M: int):
         """Draw layer `layer`'s planes on a side stream, forked here: the generator is pure integer arithmetic (no memory reads,
@@ -264,8 +273,10 @@ class WhisperEEGEngine:
             ops.gemm_nt(x, A, t, self._ep(alpha=a, alpha_cols=G * r))
             return
         bits = self._bits(layer, targets, M, K)           # drawn by _draw_planes before the layer started
-        if self.use_lora_kernels and r == 32 and K % 64 == 0 and not _NO_MASK_STAGE:
-            # the thin tcgen05 GEMM with a mask stage between TMA and MMA (one 32-column tile per adapter)
+        if self._mask_stage_draws(K):
+            # the thin tcgen05 GEMM whose mask stage (between TMA and MMA, one 32-column tile per adapter) draws the planes
+            ops.gemm_nt(x, A, t, self._ep(alpha=a, alpha_cols=G * r, drop_a=bits, drop_gen=(self.drop_seed, self._salts(layer, targets), p)))
+        elif self.use_lora_kernels and r == 32 and K % 64 == 0 and not _NO_MASK_STAGE:
             ops.gemm_nt(x, A, t, self._ep(alpha=a, alpha_cols=G * r, drop_a=bits))
         elif self._fast_lora(K, G):
             ops.lora_down(x, A, t, a, G, bits)
@@ -297,18 +308,25 @@ class WhisperEEGEngine:
             return None
         return self._bits(layer, (target,), M, K)[0]
 
-    def _fused_bwd_b(self, N: int) -> bool:
-        """ns_lora_bwd_b takes the shape: bf16 storage, rank 32, N a multiple of 128 whose N/128 dB accumulators and two dt
-        accumulators fit the 512 TMEM columns (fc1's N = 2048 gradient does not: 16 x 32 columns alone fill them)."""
-        return (not _NO_FUSED_BWD_B and self.dtype == torch.bfloat16 and self.dims.lora_r == 32 and N % 128 == 0 and N // 128 * 32 + 64 <= 512
-                and N // 64 * 4096 + 2 * 16384 + 2 * 32768 + 1280 <= 232448)
+    def _fused_bwd_b(self, N: int, M: int, groups: int = 1):
+        """Workspace of ns_lora_bwd_b for this shape (None: no workspace needed), or False when the one-pass kernel does not take it
+        (fp32 parity storage, rank != 32, N not a multiple of 128)."""
+        if _NO_FUSED_BWD_B or self.dtype != torch.bfloat16:
+            return False
+        n = ops.lora_bwd_b_workspace_bytes(M, N, self.dims.lora_r, groups)
+        if n < 0:
+            return False
+        if n == 0:
+            return None
+        return self.ws.get(f"lora_bwd_b_ws.{n}", (n,), torch.uint8, zero=True)       # tickets zeroed once; the kernel leaves them zero
 
     def _lora_bwd_b(self, dy: torch.Tensor, Bt: torch.Tensor, t: torch.Tensor, dt_out: torch.Tensor, dB: torch.Tensor, s: float):
         """dt = alpha' dy B and dB += dy^T t of one adapter: one pass over dy when the shape qualifies, else two products."""
         r = self.dims.lora_r
-        N = dy.shape[1]
-        if self._fused_bwd_b(N):
-            ops.lora_bwd_b(dy, Bt, t, dt_out, dB, N, r, [s], [1.0])
+        M, N = dy.shape
+        wsb = self._fused_bwd_b(N, M)
+        if wsb is not False:
+            ops.lora_bwd_b(dy, Bt, t, dt_out, dB, N, r, [s], [1.0], workspace=wsb)
         else:
             ops.gemm_nt(dy, Bt, dt_out, self._ep(alpha=s, alpha_cols=r))
             ops.gemm_tn(dy, t, dB, r, 1)
@@ -820,8 +838,9 @@ class WhisperEEGEngine:
                 # dt_g = alpha' dy_g B_g and dB_g = dy_g^T t_g for q, k, v: block-diagonal products, one launch each
                 off_b, _ = lay.entries[lora_module_name(i, "q_proj") + ".lora_B.default.weight"]
                 dB_qkv = self.grad[off_b: off_b + 3 * d * r].view(3 * d, r)
-                if self._fused_bwd_b(d):
-                    ops.lora_bwd_b(dqkv, W[k + ".B_qkv_t"], t_qkv, dtq, dB_qkv, d, r, [s, s, s], [qs, 1.0, 1.0])
+                wsb = self._fused_bwd_b(d, M, 3)
+                if wsb is not False:
+                    ops.lora_bwd_b(dqkv, W[k + ".B_qkv_t"], t_qkv, dtq, dB_qkv, d, r, [s, s, s], [qs, 1.0, 1.0], workspace=wsb)
                 else:
                     ops.gemm_nt(dqkv, W[k + ".B_qkv_t"], dtq, self._ep(alpha=s, alpha_cols=3 * r, a_group_cols=r), K=d)
                     ops.gemm_tn_grouped(dqkv, t_qkv, dB_qkv, d, r, r, 1, [qs, 1.0, 1.0])

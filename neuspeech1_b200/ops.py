@@ -78,15 +78,26 @@ def _p(t: Optional[torch.Tensor]):
 
 
 def epilogue(bias=None, alpha=1.0, alpha_cols=0, act=ACT_NONE, aux_in=None, aux_out=None, ldaux=0, residual=None, ldr=0,
-             res_mod=0, out_dtype=NS_BF16, a2_group_cols=0, drop_bits=None, drop_a=None, a_group_cols=0, aux_deriv=0) -> Epilogue:
+             res_mod=0, out_dtype=NS_BF16, a2_group_cols=0, drop_bits=None, drop_a=None, a_group_cols=0, aux_deriv=0, drop_gen=None) -> Epilogue:
     """drop_bits: ONE adapter's (rows, words) plane of dropout_bits -- the second product is masked with it (input gradient of a
     LoRA branch under dropout).  drop_a: the (G, rows, words) planes of G stacked rank-32 adapters -- the A operand of the single
-    product is masked per 32-column output tile (the LoRA down product).  See include/neuspeech_b200.h ns_epilogue."""
+    product is masked per 32-column output tile (the LoRA down product); with drop_gen = (seed tensor, salts, p) the kernel
+    draws those planes itself and stores them into drop_a (drop_mode 2).  See include/neuspeech_b200.h ns_epilogue."""
     if drop_a is not None:
-        return Epilogue(_p(bias), alpha, alpha_cols, act, _p(aux_in), _p(aux_out), ldaux, _p(residual), ldr, res_mod,
-                        out_dtype, a2_group_cols, _p(drop_a), drop_a.stride(1), 1, drop_a.stride(0), a_group_cols, aux_deriv)
+        ep = Epilogue(_p(bias), alpha, alpha_cols, act, _p(aux_in), _p(aux_out), ldaux, _p(residual), ldr, res_mod,
+                      out_dtype, a2_group_cols, _p(drop_a), drop_a.stride(1), 1, drop_a.stride(0), a_group_cols, aux_deriv, None, None, 0.0)
+        if drop_gen is not None:
+            seed, salts, p = drop_gen
+            arr = (C.c_uint * 4)(*([int(x) & 0xFFFFFFFF for x in salts] + [0] * (4 - len(salts))))
+            ep.drop_mode = 2
+            ep.drop_seed = _p(seed)
+            ep.drop_salts = C.cast(arr, C.c_void_p)
+            ep.drop_p = float(p)
+            ep._salts_keepalive = arr                    # the library copies the salts during the call
+        return ep
     return Epilogue(_p(bias), alpha, alpha_cols, act, _p(aux_in), _p(aux_out), ldaux, _p(residual), ldr, res_mod,
-                    out_dtype, a2_group_cols, _p(drop_bits), drop_bits.stride(0) if drop_bits is not None else 0, 0, 0, a_group_cols, aux_deriv)
+                    out_dtype, a2_group_cols, _p(drop_bits), drop_bits.stride(0) if drop_bits is not None else 0, 0, 0, a_group_cols, aux_deriv,
+                    None, None, 0.0)
 
 
 def gemm_nt(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, ep: Optional[Epilogue] = None, a2=None, w2=None,
@@ -315,16 +326,24 @@ def gemm_tn_grouped(x: torch.Tensor, y: torch.Tensor, g: torch.Tensor, I: int, J
     return g
 
 
-def lora_bwd_b(dy: torch.Tensor, bt: torch.Tensor, t: torch.Tensor, dt: torch.Tensor, db: torch.Tensor, N: int, r: int, alpha_dt, alpha_db):
+def lora_bwd_b_workspace_bytes(M: int, N: int, r: int, groups: int) -> int:
+    """Bytes of caller-owned workspace ns_lora_bwd_b needs for this shape: 0 = none, -1 = the shape does not qualify."""
+    return int(lib().ns_lora_bwd_b_workspace_bytes(M, N, r, groups))
+
+
+def lora_bwd_b(dy: torch.Tensor, bt: torch.Tensor, t: torch.Tensor, dt: torch.Tensor, db: torch.Tensor, N: int, r: int, alpha_dt, alpha_db,
+               workspace: Optional[torch.Tensor] = None):
     """One pass over dy (M, groups*N): dt[:, g*r:(g+1)*r] = alpha_dt[g] * dy_g @ bt_g^T and db[g*N:(g+1)*N] += alpha_db[g] * dy_g^T @ t_g
-    (ns_lora_bwd_b; bt (groups*r, N) = B^T, db (groups*N, r) fp32 contiguous)."""
+    (ns_lora_bwd_b; bt (groups*r, N) = B^T, db (groups*N, r) fp32 contiguous).  workspace: uint8 tensor of
+    lora_bwd_b_workspace_bytes() bytes whose ticket words were zeroed once (wide N only)."""
     groups = len(alpha_dt)
     a1 = (C.c_float * groups)(*[float(a) for a in alpha_dt])
     a2 = (C.c_float * groups)(*[float(a) for a in alpha_db])
     M = dy.shape[0]
     assert db.is_contiguous() and db.dtype == torch.float32 and db.shape == (groups * N, r)
-    _call("ns_lora_bwd_b", (4.0 * M * N * r * groups, 0), ns_dtype(dy), M, N, r, groups, _p(dy), dy.stride(0), _p(bt), bt.stride(0), _p(t),
-          t.stride(0), _p(dt), dt.stride(0), _p(db), a1, a2, _stream())
+    _call("ns_lora_bwd_b", (4.0 * M * N * r * groups, 2.0 * M * N * groups), ns_dtype(dy), M, N, r, groups, _p(dy), dy.stride(0), _p(bt),
+          bt.stride(0), _p(t), t.stride(0), _p(dt), dt.stride(0), _p(db), a1, a2, _p(workspace),
+          workspace.numel() if workspace is not None else 0, _stream())
     return dt
 
 

@@ -208,6 +208,14 @@ def test_mask_stage_down_and_da(M, K, G):
         dA_ref = dt[:, g * r:(g + 1) * r].float().t() @ xm + 0.25
         assert rel(dA, dA_ref) < 2e-3, (g, rel(dA, dA_ref))
     assert torch.equal(x, rnd(M, K, dtype=torch.bfloat16, seed=2))            # the mask is applied in shared memory, never to x
+    # drop_mode 2: the mask stage draws the planes itself -- same words as ns_dropout_bits (= the oracle's plane), same t bit for bit
+    import zlib
+    seed_t = torch.tensor([seed], dtype=torch.int32, device=DEV)
+    salts = [zlib.crc32(n.encode()) & 0xFFFFFFFF for n in names]
+    bits2 = torch.full_like(bits, -1)
+    t2 = torch.full((M, G * r), 9.0, dtype=torch.bfloat16, device=DEV)
+    ops.gemm_nt(x, A, t2, ops.epilogue(alpha=alpha, alpha_cols=G * r, drop_a=bits2, drop_gen=(seed_t, salts, p)))
+    assert torch.equal(bits2, bits) and torch.equal(t2, t)
 
 
 def test_programmatic_dependent_launch_chain_is_race_free():
@@ -282,11 +290,13 @@ def test_block_diagonal_rank_products(M, d, r, dtype):
 
 
 @pytest.mark.parametrize("M,N,groups", [(3000, 512, 1), (96000, 512, 1), (777, 256, 3), (20001, 1280, 1), (12800, 512, 3), (130, 128, 2),
-                                        (64 * 1500, 512, 3)])
+                                        (64 * 1500, 512, 3), (30000, 2048, 1), (96000, 2048, 1), (5000, 5120, 1), (4000, 2048, 2)])
 def test_lora_bwd_b_one_pass(M, N, groups):
     """ns_lora_bwd_b: dt_g = alpha_dt[g] dy_g B_g and dB_g += alpha_db[g] dy_g^T t_g from ONE pass over dy (both tcgen05 products
     read the same shared-memory chunk, K-major and MN-major), against fp32 torch on the same bf16 operands; ragged last slab,
-    more slabs than CTAs, stacked groups, dB accumulated onto a non-zero buffer; dt untouched outside the groups' columns."""
+    more slabs than CTAs, stacked groups, dB accumulated onto a non-zero buffer; dt untouched outside the groups' columns.  N = 2048
+    / 5120 run as 2 / 4 column parts per group that combine their partial dt through the workspace (twice: the tickets must come
+    back to zero)."""
     r = 32
     bf = torch.bfloat16
     dy = rnd(M, groups * N, dtype=bf, seed=1)
@@ -295,7 +305,15 @@ def test_lora_bwd_b_one_pass(M, N, groups):
     dt = torch.full((M, groups * r + 8), 5.0, dtype=bf, device=DEV)        # wider buffer: the pad columns must survive
     dB = torch.full((groups * N, r), 0.25, dtype=torch.float32, device=DEV)
     a_dt = [1.5, 0.5, 2.0, 1.0][:groups]; a_db = [0.125, 1.0, 2.0, 0.5][:groups]
-    ops.lora_bwd_b(dy, Bt, t, dt, dB, N, r, a_dt, a_db)
+    assert ops.lora_bwd_b_workspace_bytes(M, N, 16, groups) == -1 and ops.lora_bwd_b_workspace_bytes(M, N + 64, r, groups) == -1
+    nws = ops.lora_bwd_b_workspace_bytes(M, N, r, groups)
+    assert nws >= 0 and (nws > 0) == (N > 1792)
+    wsb = torch.zeros(nws, dtype=torch.uint8, device=DEV) if nws else None
+    if nws:                                                               # first call on scratch outputs: leaves the tickets at zero
+        ops.lora_bwd_b(dy, Bt, t, torch.empty_like(dt), torch.zeros_like(dB), N, r, a_dt, a_db, workspace=wsb)
+        with pytest.raises(Exception):
+            ops.lora_bwd_b(dy, Bt, t, dt, dB, N, r, a_dt, a_db)            # wide N without its workspace: refused
+    ops.lora_bwd_b(dy, Bt, t, dt, dB, N, r, a_dt, a_db, workspace=wsb)
     assert bool((dt[:, groups * r:] == 5.0).all())
     for g in range(groups):
         yg = dy[:, g * N:(g + 1) * N].float()

@@ -50,9 +50,27 @@ def once():
     torch.cuda.synchronize()
 
 
+def bwd_b_only():
+    """python tools/lora_bench.py --bwd-b: the one-pass B-side kernel alone (NS_LB_DEBUG experiments)."""
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    for N, G in ((512, 1), (512, 3), (2048, 1)):
+        dy = torch.randn(M, G * N, device=DEV).to(torch.bfloat16)
+        Bt = (torch.randn(G * r, N, device=DEV) * N ** -0.5).to(torch.bfloat16)
+        t = torch.randn(M, G * r, device=DEV).to(torch.bfloat16)
+        dt = torch.empty(M, G * r, dtype=torch.bfloat16, device=DEV)
+        dB = torch.zeros(G * N, r, dtype=torch.float32, device=DEV)
+        nws = ops.lora_bwd_b_workspace_bytes(M, N, r, G)
+        wsb = torch.zeros(nws, dtype=torch.uint8, device=DEV) if nws > 0 else None
+        us = timeit(lambda: ops.lora_bwd_b(dy, Bt, t, dt, dB, N, r, [2.0] * G, [1.0] * G, workspace=wsb), flush=flush)
+        us_hot = timeit(lambda: ops.lora_bwd_b(dy, Bt, t, dt, dB, N, r, [2.0] * G, [1.0] * G, workspace=wsb))
+        print(f"bwd_b N={N} G={G} dbg={os.environ.get('NS_LB_DEBUG', '0')}: {us:.1f} us flushed ({M * G * N * 2 / us / 1e6:.2f} TB/s), {us_hot:.1f} us back to back")
+
+
 def main():
     if "--once" in sys.argv:
         return once()
+    if "--bwd-b" in sys.argv:
+        return bwd_b_only()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
     seed = torch.tensor([1234], dtype=torch.int32, device=DEV)
     out = {}
@@ -82,6 +100,24 @@ def main():
             "lora_da_fix_p05": timeit(lambda: ops.lora_da(x, dt, dA, G, bits, dx=dx, At=At), flush=flush),
             "lora_da_fix_gelu_p05": timeit(lambda: ops.lora_da(x, dt, dA, G, bits, dx=dx, At=At, z=z), flush=flush),
             "x_MB": M * K * 2 / 1e6,
+        }
+        print(key, {k: round(v, 1) for k, v in out[key].items()})
+    # B side of the backward: dt = dy B and dB = dy^T t as two passes over dy and as one (ns_lora_bwd_b)
+    for N, G in ((512, 1), (512, 3), (2048, 1)):
+        dy = torch.randn(M, G * N, device=DEV).to(torch.bfloat16)
+        Bt = (torch.randn(G * r, N, device=DEV) * N ** -0.5).to(torch.bfloat16)
+        t = torch.randn(M, G * r, device=DEV).to(torch.bfloat16)
+        dt = torch.empty(M, G * r, dtype=torch.bfloat16, device=DEV)
+        dB = torch.zeros(G * N, r, dtype=torch.float32, device=DEV)
+        nws = ops.lora_bwd_b_workspace_bytes(M, N, r, G)
+        wsb = torch.zeros(nws, dtype=torch.uint8, device=DEV) if nws > 0 else None
+        key = f"bwd_b_N{N}_G{G}"
+        ep = ops.epilogue(alpha=2.0, alpha_cols=G * r, a_group_cols=r) if G > 1 else ops.epilogue(alpha=2.0, alpha_cols=r)
+        out[key] = {
+            "gemm_nt_dt": timeit(lambda: ops.gemm_nt(dy, Bt, dt, ep, K=N), flush=flush),
+            "gemm_tn_dB": timeit(lambda: (ops.gemm_tn_grouped(dy, t, dB, N, r, r, 1, [1.0] * G) if G > 1 else ops.gemm_tn(dy, t, dB, r, 1)), flush=flush),
+            "lora_bwd_b": timeit(lambda: ops.lora_bwd_b(dy, Bt, t, dt, dB, N, r, [2.0] * G, [1.0] * G, workspace=wsb), flush=flush),
+            "dy_MB": M * G * N * 2 / 1e6,
         }
         print(key, {k: round(v, 1) for k, v in out[key].items()})
     os.makedirs("gpurun_out", exist_ok=True)
