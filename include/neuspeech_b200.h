@@ -82,7 +82,8 @@ typedef struct {
   long long    drop_gstride;  /* words between the planes of stacked adapters (drop_mode 1) */
   int          a_group_cols;  /* > 0: BLOCK-DIAGONAL main product -- output columns [g*a_group_cols, (g+1)*a_group_cols) contract
                                  A[:, g*K : (g+1)*K] (lda >= G*K) with their own rows of W: dt_g = dy_g * B_g for the q/k/v adapters
-                                 in one launch (dy = [dq|dk|dv], W = [B_q^T; B_k^T; B_v^T]).  No second product with it. */
+                                 in one launch (dy = [dq|dk|dv], W = [B_q^T; B_k^T; B_v^T]).  Any multiple of 32 that divides N
+                                 (32-wide tiles).  No second product with it. */
   int          aux_deriv;     /* != 0: the aux tensor holds gelu'(z), not z.  NS_ACT_GELU stores gelu'(z) into aux_out (same tanh as
                                  the activation: a handful of FMAs more), NS_ACT_DGELU multiplies by aux_in as it is -- the
                                  backward epilogue loses its transcendental and a dozen instructions per element.  The forward
@@ -216,7 +217,10 @@ typedef struct {
   const float* ln3_g; const float* ln3_b; const void* w1; const float* b1; const void* w2; const float* b2;
   const void* wkv; const float* bkv;   /* (2d, d) / (2d): cross K|V projection of this layer (prefill) */
   void* self_cache;                    /* (B, Tmax, 3d): q|k|v rows of this layer */
-  void* cross_kv;                      /* (B*S, cross_ld >= 2d): K|V of the encoder output */
+  void* cross_kv;                      /* (B*S, cross_ld >= 2d): K|V of the encoder output (unused in the absorbed form) */
+  const void* wq_abs;                  /* absorbed form (below): (heads * d, d), the query AND key projections of this layer in one
+                                          weight, wq_abs[h * d + n, m] = Dh^-0.5 * sum_c Wk[h * Dh + c, n] * Wq[h * Dh + c, m] */
+  const float* bq_abs;                 /* (heads * d): bq_abs[h * d + n] = Dh^-0.5 * sum_c bq[h * Dh + c] * Wk[h * Dh + c, n] */
 } ns_decoder_layer;
 typedef struct {
   int dtype, n_layers, d, heads, ffn, vocab, S, Tmax, B, logits_dtype;
@@ -225,7 +229,20 @@ typedef struct {
   const ns_decoder_layer* layers;      /* host array of n_layers entries */
   void* h0; void* u; void* o; void* h1; void* qc; void* h2; void* mm; void* h3a; void* h3b; void* y;   /* (B, d) scratch; mm (B, ffn) */
   void* logits;                        /* (B, logits_ld) */
+  /* Absorbed cross-attention (csrc/ns_attention_absorbed.cu): when enc, qp, cp and every layers[i].wq_abs / bq_abs are set
+   * (bf16, d == 512, heads <= 8) the step never reads cross_kv: the key projection moves to the query side and folds into the
+   * query projection (Q'_h = LN(x) wq_abs_h^T + bq_abs_h, ONE GEMM instead of the q projection), all heads attend over the
+   * encoder rows themselves (C'_h = softmax(Q'_h enc^T) enc) and the value projection follows (out_h = C'_h Wv_h^T + bv_h,
+   * block-diagonal GEMM on rows [d, 2d) of wkv) -- S*d instead of 2*S*d elements read per (sample, layer) and position, and
+   * ns_decode_prefill has nothing to do. */
+  const void* enc;                     /* (B*S, d) encoder output */
+  void* qp; void* cp;                  /* (B, heads * d) scratch: Q' and C' */
 } ns_decoder;
+/* The middle part of the absorbed cross-attention on its own (tests, other callers): ctx[b, h, :] = softmax_j(qp[b, h, :] .
+ * enc[b, j, :]) enc[b], all H <= 8 heads of a sample in one CTA.  qp / ctx rows of a sample are ldq / ldo elements apart
+ * (>= H * d), enc samples enc_bs elements apart (rows d apart).  bf16, d == 512 only; NS_ERR_UNSUPPORTED otherwise. */
+int ns_cross_attention_absorbed(int dtype, int B, int S, int H, int d, const void* qp, long long ldq, const void* enc, long long enc_bs,
+                                void* ctx, long long ldo, void* stream);
 int ns_decode_prefill(const ns_decoder* dec, const void* enc, void* stream);
 int ns_decode_step(const ns_decoder* dec, const long long* ids, int pos, const int* suppress, int n_suppress, int eos, int pad,
                    unsigned char* finished, long long* next_ids, long long* out, long long out_ld, void* stream);

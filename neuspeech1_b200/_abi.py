@@ -31,14 +31,14 @@ class Epilogue(C.Structure):
 
 class DecoderLayer(C.Structure):
     _fields_ = [(n, c_vp) for n in ("ln1_g", "ln1_b", "wqkv", "bqkv", "wo", "bo", "ln2_g", "ln2_b", "wqc", "bqc", "woc", "boc",
-                                    "ln3_g", "ln3_b", "w1", "b1", "w2", "b2", "wkv", "bkv", "self_cache", "cross_kv")]
+                                    "ln3_g", "ln3_b", "w1", "b1", "w2", "b2", "wkv", "bkv", "self_cache", "cross_kv", "wq_abs", "bq_abs")]
 
 
 class Decoder(C.Structure):
     _fields_ = [(n, c_i) for n in ("dtype", "n_layers", "d", "heads", "ffn", "vocab", "S", "Tmax", "B", "logits_dtype")] + \
                [("cross_ld", c_ll), ("logits_ld", c_ll), ("E", c_vp), ("pos_table", c_vp), ("lnf_g", c_vp), ("lnf_b", c_vp),
                 ("layers", C.POINTER(DecoderLayer))] + \
-               [(n, c_vp) for n in ("h0", "u", "o", "h1", "qc", "h2", "mm", "h3a", "h3b", "y", "logits")]
+               [(n, c_vp) for n in ("h0", "u", "o", "h1", "qc", "h2", "mm", "h3a", "h3b", "y", "logits", "enc", "qp", "cp")]
 
 
 class AttnShape(C.Structure):
@@ -86,6 +86,7 @@ SIGNATURES = {
     "ns_cross_entropy": [c_i, c_ll, c_i, c_ll, c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_f, c_vp],
     "ns_greedy_pick": [c_i, c_i, c_i, c_ll, c_vp, c_vp, c_i, c_i, c_i, c_vp, c_vp, c_vp, c_ll, c_vp],
     "ns_set_pdl": [c_i],
+    "ns_cross_attention_absorbed": [c_i, c_i, c_i, c_i, c_i, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp],
     "ns_decode_prefill": [C.POINTER(Decoder), c_vp, c_vp],
     "ns_decode_step": [C.POINTER(Decoder), c_vp, c_i, c_vp, c_i, c_i, c_i, c_vp, c_vp, c_vp, c_ll, c_vp],
     "ns_aug_pass": [C.POINTER(AugArgs), c_vp, c_vp, c_vp],

@@ -1280,9 +1280,10 @@ int gemm_nt_fast(long long M, int N, int K, const void* A, long long lda, const 
   int cg = choose_cg((M + kBM - 1) / kBM, N, bn);
   const int a1g = epi.a_group_cols;
   if (a1g > 0) {
-    // block-diagonal main product: one 32-wide tile per group (the rank-r products dt_g = dy_g B_g)
-    if (A2 || epi.drop_bits || a1g != 32 || N % 32 != 0) {
-      set_error("ns_gemm_nt: a_group_cols supports 32-column groups of a single product");
+    // block-diagonal main product on 32-wide tiles: a group is one tile (the rank-r products dt_g = dy_g B_g) or several (the
+    // per-head projections of the absorbed cross-attention)
+    if (A2 || epi.drop_bits || a1g % 32 != 0 || N % a1g != 0) {
+      set_error("ns_gemm_nt: a_group_cols supports groups of a multiple of 32 columns of a single product, N a multiple of the group");
       return NS_ERR_UNSUPPORTED;
     }
     bn = 32; cg = 1;

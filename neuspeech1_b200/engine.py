@@ -35,6 +35,7 @@ _NO_PDL = bool(os.environ.get("NS_NO_PDL"))                     # developer A/B 
 _NO_AR_OVERLAP = bool(os.environ.get("NS_NO_AR_OVERLAP"))       # developer A/B switch: one all-reduce after the whole backward
 _NO_MASK_STAGE = bool(os.environ.get("NS_NO_MASK_STAGE"))       # developer A/B switch: mma.sync ns_lora_down / ns_lora_da instead of the mask stages
 _NO_GELU_DERIV = bool(os.environ.get("NS_NO_GELU_DERIV"))       # developer A/B switch: save the GELU pre-activation, not the derivative
+_ABSORB = os.environ.get("NS_ABSORB")                           # "0" / "1": force the absorbed decode cross-attention off / on (default: by batch size)
 _NO_PLANE_FUSE = bool(os.environ.get("NS_NO_PLANE_FUSE"))       # developer A/B switch: dropout planes from ns_dropout_bits launches, not from the mask stage
 _NO_FUSED_BWD_B = bool(os.environ.get("NS_NO_FUSED_BWD_B"))     # developer A/B switch: dt = dy B and dB = dy^T t as two passes over dy
 _NO_GEMM_MASK = bool(os.environ.get("NS_NO_GEMM_MASK"))         # developer A/B switch: dropout correction pass instead of the masked GEMM product
@@ -438,6 +439,18 @@ class WhisperEEGEngine:
             ln(pre + ".self_attn_layer_norm", k + ".ln1"); ln(pre + ".encoder_attn_layer_norm", k + ".ln2")
             ln(pre + ".final_layer_norm", k + ".ln3")
         ln("model.decoder.layer_norm", "dec.lnf")
+        # absorbed cross-attention of the decode step (csrc/ns_attention_absorbed.cu): query and key projections in one weight,
+        # wq_abs[h*d + n, m] = Dh^-0.5 sum_c Wk[h*Dh + c, n] Wq[h*Dh + c, m], bq_abs[h*d + n] = Dh^-0.5 sum_c bq[h*Dh + c] Wk[h*Dh + c, n]
+        # (products in fp32, rounded to the storage type once)
+        Hd = dm.dec_heads
+        Dhd = d // Hd
+        for i in range(dm.dec_layers if (self.dtype == torch.bfloat16 and d == 512 and Hd <= 8) else 0):   # the shapes the kernel takes
+            pre = f"model.decoder.layers.{i}"
+            wk = kv_w[2 * i].view(Hd, Dhd, d)
+            wq = f32(f"{pre}.encoder_attn.q_proj.weight").view(Hd, Dhd, d)
+            bq = f32(f"{pre}.encoder_attn.q_proj.bias").view(Hd, Dhd)
+            W[f"dec{i}.wq_abs"] = self._c((torch.einsum("hcn,hcm->hnm", wk, wq) * Dhd ** -0.5).reshape(Hd * d, d).contiguous())
+            W[f"dec{i}.bq_abs"] = (torch.einsum("hc,hcn->hn", bq, wk) * Dhd ** -0.5).reshape(Hd * d).contiguous()
         wkv = torch.cat(kv_w, dim=0)                                     # (Nd*2d, d): [k0; v0; k1; v1; ...]
         W["dec.wkv"] = self._c(wkv); W["dec.wkv_t"] = self._ct(wkv); W["dec.bkv"] = torch.cat(kv_b)
         self.P = W
@@ -1022,19 +1035,30 @@ class WhisperEEGEngine:
         self._packed = False
         return loss.clone()
 
-    def _native_decoder(self, B: int, Tmax: int, cache, kv_layers: torch.Tensor, logits: torch.Tensor):
+    def _absorbed_decode(self, B: int) -> bool:
+        """The decode step attends over the encoder output itself (key / value projections moved to the query / output side,
+        csrc/ns_attention_absorbed.cu): half the bytes per position and no cross K|V buffer.  One CTA per sample streams its
+        encoder rows, so the batch has to cover the SMs; smaller batches keep one CTA per (sample, head) over cached K|V."""
+        dm = self.dims
+        ok = self.dtype == torch.bfloat16 and dm.d_model == 512 and dm.dec_heads <= 8
+        if _ABSORB is not None:
+            return ok and _ABSORB != "0"
+        return ok and B >= 96
+
+    def _native_decoder(self, B: int, Tmax: int, cache, kv_layers: Optional[torch.Tensor], logits: torch.Tensor, enc: Optional[torch.Tensor] = None):
         """The `ns_decoder` argument block of ns_decode_prefill / ns_decode_step for this batch shape: pointers into the weight
         table, the self-attention cache, the per-layer cross K|V and persistent scratch.  Cached per (B, Tmax) while the
-        workspace and the weights stay in place."""
+        workspace and the weights stay in place.  enc (B*S, d) instead of kv_layers: the absorbed form (`_absorbed_decode`)."""
         from . import _abi
         dm, W, ws, dt = self.dims, self.P, self.ws, self.dtype
         d, F = dm.d_model, dm.dec_ffn
-        key = (B, Tmax)
+        key = (B, Tmax, enc is not None)
         p = lambda t: t.data_ptr()
         tag = f"nd.{B}"
         buf = lambda n, cols=d: ws.get(f"{tag}.{n}", (B, cols), dt)
         sc = [buf("h0"), buf("u"), buf("o"), buf("h1"), buf("qc"), buf("h2"), buf("mm", F), buf("h3a"), buf("h3b"), buf("y")]
-        stamp = (ws.gen, self._weights_version, tuple(p(c) for c in cache), p(kv_layers), p(logits))
+        ab = [buf("qp", dm.dec_heads * d), buf("cp", dm.dec_heads * d)] if enc is not None else []
+        stamp = (ws.gen, self._weights_version, tuple(p(c) for c in cache), p(kv_layers) if kv_layers is not None else p(enc), p(logits))
         ent = self.__dict__.setdefault("_native_dec", {}).get(key)
         if ent is not None and ent[0] == stamp:
             return ent[1]
@@ -1047,11 +1071,14 @@ class WhisperEEGEngine:
             layers[i] = _abi.DecoderLayer(p(W[k + ".ln1.g"]), p(W[k + ".ln1.b"]), p(W[k + ".wqkv"]), p(W[k + ".bqkv"]), p(W[k + ".wo"]),
                                           p(W[k + ".bo"]), p(W[k + ".ln2.g"]), p(W[k + ".ln2.b"]), p(W[k + ".wqc"]), p(W[k + ".bqc"]),
                                           p(W[k + ".woc"]), p(W[k + ".boc"]), p(W[k + ".ln3.g"]), p(W[k + ".ln3.b"]), p(W[k + ".w1"]),
-                                          p(W[k + ".b1"]), p(W[k + ".w2"]), p(W[k + ".b2"]), p(wkv), p(bkv), p(cache[i]), p(kv_layers[i]))
+                                          p(W[k + ".b1"]), p(W[k + ".w2"]), p(W[k + ".b2"]), p(wkv), p(bkv), p(cache[i]),
+                                          p(kv_layers[i]) if kv_layers is not None else None,
+                                          p(W[k + ".wq_abs"]) if enc is not None else None, p(W[k + ".bq_abs"]) if enc is not None else None)
         dec = _abi.Decoder(self.ns, dm.dec_layers, d, dm.dec_heads, F, dm.vocab, dm.max_source_positions, Tmax, B, ops.ns_dtype(logits),
-                           kv_layers.stride(1), logits.stride(0), p(W["dec.E"]), p(W["dec.pos"]), p(W["dec.lnf.g"]), p(W["dec.lnf.b"]),
-                           layers, *[p(t) for t in sc], p(logits))
-        self._native_dec[key] = (stamp, dec, layers, keep, sc)
+                           kv_layers.stride(1) if kv_layers is not None else 0, logits.stride(0), p(W["dec.E"]), p(W["dec.pos"]),
+                           p(W["dec.lnf.g"]), p(W["dec.lnf.b"]), layers, *[p(t) for t in sc], p(logits),
+                           p(enc) if enc is not None else None, *([p(t) for t in ab] if ab else [None, None]))
+        self._native_dec[key] = (stamp, dec, layers, keep, sc, ab)
         return dec
 
     def _cross_kv_per_layer(self, enc: torch.Tensor, B: int) -> torch.Tensor:
@@ -1240,7 +1267,8 @@ class WhisperEEGEngine:
         if n_new <= 0:
             return torch.empty((B, 0), dtype=torch.long, device=self.device)
         cache = [ws.get(f"g_qkv.{i}", (B, Tmax, 3 * d), dt) for i in range(dm.dec_layers)]
-        kv_all = ws.get("kv_layers", (dm.dec_layers, B * S, 2 * d), dt)
+        absorb = L0 == 1 and self._absorbed_decode(B)        # (a multi-token prompt takes the general pass over cached K|V once)
+        kv_all = None if absorb else ws.get("kv_layers", (dm.dec_layers, B * S, 2 * d), dt)
         finished = ws.get("g_fin", (B,), torch.uint8); finished.zero_()
         nxt = ws.get("g_next", (B,), torch.long)
         logits = ws.get("g_logits", (B, dm.Vp), torch.float32 if dt == torch.float32 else dt)
@@ -1249,7 +1277,7 @@ class WhisperEEGEngine:
         ids0 = ws.get(f"g_ids0.{L0}", (B, L0), torch.long)
         ids0.copy_(prompt)
         # the loop body is native: ns_decode_prefill (cross K|V of all layers) and one ns_decode_step per position
-        dec = self._native_decoder(B, Tmax, cache, kv_all, logits)
+        dec = self._native_decoder(B, Tmax, cache, kv_all, logits, enc=enc.view(B * S, d) if absorb else None)
         ops.decode_prefill(dec, enc)
 
         def decode_step(step: int, ids: torch.Tensor, pos: int):

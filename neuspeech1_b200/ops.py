@@ -229,6 +229,16 @@ def greedy_pick(logits, V: int, suppress, eos: int, pad: int, finished, next_ids
     return next_ids
 
 
+def cross_attention_absorbed(qp: torch.Tensor, enc: torch.Tensor, ctx: torch.Tensor):
+    """ctx[b, h] = softmax_j(qp[b, h] . enc[b, j]) enc[b]  (qp, ctx (B, H, d); enc (B, S, d); bf16, d = 512): the decode-step
+    cross-attention with the key / value projections absorbed into the query / output side (ns_cross_attention_absorbed)."""
+    B, H, d = qp.shape
+    S = enc.shape[1]
+    _call("ns_cross_attention_absorbed", (4.0 * B * H * S * d, 2.0 * B * S * d), ns_dtype(qp), B, S, H, d, _p(qp), qp.stride(0), _p(enc),
+          enc.stride(0), _p(ctx), ctx.stride(0), _stream())
+    return ctx
+
+
 def decode_prefill(dec, enc):
     """Cross-attention K|V of every decoder layer (ns_decode_prefill); dec = _abi.Decoder built by the engine."""
     _call("ns_decode_prefill", (0, 0), C.byref(dec), _p(enc), _stream())

@@ -52,7 +52,7 @@ def test_struct_sizes_match_c_layout():
     from neuspeech1_b200 import _abi
     # ns_epilogue: ptr,float,int,int,(pad),ptr,ptr,ll,ptr,ll,int,int,int,(pad),ptr,ll,int,(pad),ll,int,int,ptr,ptr,float,(pad)
     assert ctypes.sizeof(_abi.Epilogue) == 144
-    assert ctypes.sizeof(_abi.DecoderLayer) == 22 * 8 and ctypes.sizeof(_abi.Decoder) == 10 * 4 + 2 * 8 + 16 * 8
+    assert ctypes.sizeof(_abi.DecoderLayer) == 24 * 8 and ctypes.sizeof(_abi.Decoder) == 10 * 4 + 2 * 8 + 19 * 8
     assert ctypes.sizeof(_abi.AttnShape) == 6 * 4 + 8 * 8
     # ... seed, then in_dtype (int, padded to 8), src_off, src_ld
     assert ctypes.sizeof(_abi.AugArgs) == 7 * 4 + 4 + 5 * 8 + 8 + 8 + 3 * 8 + 8 + 8 + 8 + 8 + 8

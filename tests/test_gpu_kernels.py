@@ -218,6 +218,23 @@ def test_mask_stage_down_and_da(M, K, G):
     assert torch.equal(bits2, bits) and torch.equal(t2, t)
 
 
+@pytest.mark.parametrize("B,S,H", [(3, 1500, 8), (2, 64, 8), (5, 130, 6), (1, 1, 8), (4, 200, 1)])
+def test_cross_attention_absorbed(B, S, H):
+    """ns_cross_attention_absorbed: ctx[b, h] = softmax_j(qp[b, h] . enc[b, j]) enc[b] for all heads of a sample in one CTA
+    (mma.sync flash-decoding over the encoder rows), against fp32 torch on the same bf16 operands; ragged last key tile, fewer
+    than 8 heads (the pad rows of the 16-row MMA tile), buffers wider than H * d."""
+    d = 512
+    bf = torch.bfloat16
+    qp = rnd(B, 8, d, dtype=bf, scale=0.08, seed=1)[:, :H]                 # rows of a sample 8 * d apart
+    enc = rnd(B, S, d, dtype=bf, seed=2)
+    ctx = torch.full((B, 8, d), 7.0, dtype=bf, device=DEV)[:, :H]
+    ops.cross_attention_absorbed(qp, enc, ctx)
+    w = torch.softmax(qp.float() @ enc.float().transpose(1, 2), dim=-1)     # (B, H, S)
+    ref = w @ enc.float()
+    assert rel(ctx.float(), ref) < 1e-2, rel(ctx.float(), ref)
+    assert S < 8 or float(w.max()) > 3.0 / S                                 # the softmax is not flat: the test sees the weights
+
+
 def test_programmatic_dependent_launch_chain_is_race_free():
     """ns_set_pdl(1): the decoder-step kernels are launched with the programmatic-stream-serialization attribute and wait
     (griddepcontrol.wait) before touching global memory.  A dependent chain LN -> GEMM(+bias, residual) -> single-query attention

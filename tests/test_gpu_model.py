@@ -462,6 +462,42 @@ def test_config4_c273_merged_greedy_ids_identical_fp32():
     assert len({tuple(r.tolist()) for r in ref}) > 1              # the samples do decode differently
 
 
+def test_absorbed_decode_cross_attention_matches_cached_kv(monkeypatch):
+    """engine.greedy with the cross-attention key / value projections absorbed into the query / output side (default at B >= 96,
+    forced here at B = 6): Whisper-base widths, bf16.  Same function as attention over cached K|V: the logits of a decoded
+    position agree within the bf16 tolerance, the ids agree with the cached-K|V path on (almost) every position and with the fp32
+    oracle as often as that path does, and the per-position CUDA graphs reproduce the eager launches."""
+    import neuspeech1_b200.engine as E
+    dims = O.Dims(eeg_ch=24, enc_layers=1, dec_layers=3, max_source_positions=300)
+    P = O.init_params(dims, seed=0, std=0.1)
+    B, Tmax = 6, 12
+    x, _ = O.synthetic_batch(dims, B=B, L=8, seed=4)
+    ref = O.greedy_decode(x, P, dims, max_length=Tmax)
+    eng = WhisperEEGEngine(ModelDims.from_any(dims), P, None, dtype=torch.bfloat16, device=DEV)
+    monkeypatch.setattr(E, "_ABSORB", "0")
+    assert not eng._absorbed_decode(B)
+    cached = eng.greedy(x.to(DEV), max_length=Tmax, use_graphs=False).cpu()
+    eng.greedy(x.to(DEV), max_length=2, use_graphs=False)
+    lg_cached = eng.ws.bufs["g_logits"][:, :dims.vocab].float().clone()
+    monkeypatch.setattr(E, "_ABSORB", "1")
+    assert eng._absorbed_decode(B)
+    eng._decode_graphs.clear()
+    eng.greedy(x.to(DEV), max_length=2, use_graphs=False)
+    lg_abs = eng.ws.bufs["g_logits"][:, :dims.vocab].float().clone()
+    assert rel(lg_abs, lg_cached) < 2e-2, rel(lg_abs, lg_cached)
+    got = eng.greedy(x.to(DEV), max_length=Tmax, use_graphs=False).cpu()
+    assert float((got == cached).float().mean()) >= 0.9
+    # (against the fp32 oracle both bf16 paths drift alike on these random-init margins: identity is an fp32 requirement)
+    agree = lambda a: float((a[:, :ref.shape[1]] == ref).float().mean())
+    assert agree(got) >= agree(cached) - 0.15, (agree(got), agree(cached))
+    for _ in range(3):                                            # capture, re-capture, replay
+        assert torch.equal(eng.greedy(x.to(DEV), max_length=Tmax, use_graphs=True).cpu(), got)
+    prompt = torch.cat([torch.full((B, 1), dims.decoder_start_token_id), torch.randint(0, 50000, (B, 3))], dim=1)
+    gp = eng.greedy(x.to(DEV), max_length=Tmax, prompt=prompt, use_graphs=False).cpu()       # multi-token prompt: cached K|V path
+    monkeypatch.setattr(E, "_ABSORB", "0")
+    assert torch.equal(eng.greedy(x.to(DEV), max_length=Tmax, prompt=prompt, use_graphs=False).cpu(), gp)
+
+
 # ------------------------------------------------------------------------------------------------ LoRA-branch dropout (finetune.py:210)
 @pytest.mark.parametrize("dims_name,dtype,p", [("TINY", torch.float32, 0.05), ("MID", torch.float32, 0.1), ("TINY", torch.bfloat16, 0.05),
                                                ("MID", torch.bfloat16, 0.05), ("SCHOF", torch.bfloat16, 0.1)])
