@@ -320,7 +320,7 @@ def run_ours(args):
         # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/), null when not captured
         traffic = None
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02f_traffic.json")))
             traffic = tj.get(top_name, {}).get("dram_bytes_per_launch_avg")
         except Exception:
             traffic = None
@@ -328,7 +328,7 @@ def run_ours(args):
             ach = top["flops"] / (top["ms"] * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": top_name, "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                     "frac": ach / peaks["tf_sustained"], "traffic": traffic,
-                    "traffic_source": "profiles/r02_traffic.json: dram bytes per launch, ncu --set full of this build's kernels at the bench shapes (tools/gpu_ncu_r02.sh), averaged over the family's launches",
+                    "traffic_source": "profiles/r02f_traffic.json: dram bytes per launch, ncu --set full of this build's kernels at the bench shapes (tools/gpu_ncu_r02.sh), averaged over the family's launches",
                     "launches": top["n"], "share_of_step": top["ms"] / tot,
                     "peak_source": peaks["src"] + " (sustained bf16: kernel timed inside a long step)"}
         else:
@@ -337,7 +337,7 @@ def run_ours(args):
                     "traffic": traffic, "launches": top["n"], "share_of_step": top["ms"] / tot, "peak_source": peaks["src"]}
         # HBM-bound kernels of the step (bytes = algorithmic bytes per launch) against the measured copy peak
         hbm = {}
-        for name in ("ns_aug_pass", "ns_layernorm_fwd", "ns_layernorm_bwd", "ns_cross_entropy", "ns_gemm_nt.rank_r", "ns_dropout_bits"):
+        for name in ("ns_aug_pass", "ns_layernorm_fwd", "ns_layernorm_bwd", "ns_cross_entropy", "ns_gemm_nt.rank_r", "ns_lora_bwd_b", "ns_dropout_bits"):
             f = fam.get(name)
             if f and f["bytes"] > 0 and f["ms"] > 0:
                 gbs = f["bytes"] / (f["ms"] * 1e-3) / 1e9

@@ -9,10 +9,11 @@
 // then the encoder output itself: S * d elements per (sample, layer) -- half the bytes -- and no cross K|V buffer at all.
 // The two small projections run on the block-diagonal tcgen05 GEMM (ns_epilogue.a_group_cols); this file is the middle part:
 //     C'[b, h, :] = softmax_j( Q'[b, h, :] . enc[b, j, :] ) enc[b]          one CTA per sample, all H <= 8 heads at once
-// as a flash-decoding loop on mma.sync m16n8k16 (the 8 heads are the 8 valid rows of the 16-row A tile): the encoder rows stream
-// through a 3-stage cp.async ring of 64-key tiles (64 KB each); phase 1: warp w scores keys [8w, 8w+8) of the tile over all 512
-// dimensions; row maxima / sums meet in shared memory; phase 2: warp w accumulates dimensions [64w, 64w+64) of C' over the 64
-// keys (P through shared memory as bf16, the tile read a second time with ldmatrix.trans).  d_model = 512 only (Whisper-base).
+// as a flash-decoding loop on mma.sync m16n8k16 (the 8 heads are the 8 valid rows of the 16-row A tile).  Two groups of four
+// warps walk the even / odd 32-key tiles (32 KB each) with their own 3-stage cp.async ring, softmax state and named barrier, and
+// merge at the end; per tile, phase 1: warp w scores keys [8w, 8w+8) over all 512 dimensions; row maxima / sums meet in shared
+// memory; phase 2: warp w accumulates dimensions [128w, 128w+128) of C' over the tile's keys (P through shared memory as bf16,
+// the tile read a second time with ldmatrix.trans).  d_model = 512 only (Whisper-base).
 #include "ns_common.cuh"
 
 namespace ns {
@@ -20,12 +21,15 @@ namespace ns {
 namespace {
 
 constexpr int AB_D = 512;                 // model width = "head dimension" of the absorbed form
-constexpr int AB_KT = 64;                 // keys per tile
-constexpr int AB_STAGES = 3;
-constexpr int AB_WARPS = 8;
+constexpr int AB_KT = 32;                 // keys per tile
+constexpr int AB_GROUPS = 2;              // independent pipelines per CTA (4 warps each): one runs its MMAs while the other sits at a barrier
+constexpr int AB_GW = 4;                  // warps per group
+constexpr int AB_STAGES = 3;              // ring stages per group
 constexpr int AB_ROW = AB_D * 2 + 16;     // bytes per shared-memory row: 16 bytes of padding -> conflict-free ldmatrix
 constexpr int AB_PROW = AB_KT * 2 + 16;   // P rows
-constexpr int AB_SMEM = AB_STAGES * AB_KT * AB_ROW + 8 * AB_ROW + 8 * AB_PROW + 2 * AB_WARPS * 8 * 4;
+constexpr int AB_GROUP_BYTES = AB_STAGES * AB_KT * AB_ROW + 8 * AB_PROW + 2 * AB_GW * 8 * 4;   // ring + P + maxima + sums
+constexpr int AB_SMEM = AB_GROUPS * AB_GROUP_BYTES + 8 * AB_ROW;                               // + Q'
+static_assert(8 * AB_D * 4 + 2 * 8 * 4 * 32 <= AB_STAGES * AB_KT * AB_ROW, "the merge buffer reuses group 1's ring");
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void ab_cp16(uint32_t saddr, const void* g, int src_bytes) {
@@ -33,6 +37,7 @@ __device__ __forceinline__ void ab_cp16(uint32_t saddr, const void* g, int src_b
 }
 __device__ __forceinline__ void ab_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N> __device__ __forceinline__ void ab_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+__device__ __forceinline__ void ab_group_sync(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(AB_GW * 32) : "memory"); }
 __device__ __forceinline__ void ab_ldsm4(uint32_t (&r)[4], uint32_t saddr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
 }
@@ -45,30 +50,36 @@ __device__ __forceinline__ void ab_mma(float (&c)[4], uint32_t a0, uint32_t a1, 
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// qp (B, H, 512) bf16 (row stride ldq per sample), enc (B, S, 512) bf16 (sample stride enc_bs, row stride 512), out like qp
-__global__ void __launch_bounds__(AB_WARPS * 32, 1) cross_absorbed_kernel(int S, int H, const __nv_bfloat16* __restrict__ qp, long long ldq,
-                                                                          const __nv_bfloat16* __restrict__ enc, long long enc_bs,
-                                                                          __nv_bfloat16* __restrict__ out, long long ldo) {
+// qp (B, H, 512) bf16 (row stride ldq per sample), enc (B, S, 512) bf16 (sample stride enc_bs, row stride 512), out like qp.
+// The two warp groups walk the even / odd 32-key tiles with their own cp.async ring, softmax state and named barrier -- a group
+// waiting at one of its three barriers per tile leaves the tensor and load pipes to the other -- and merge at the end.
+__global__ void __launch_bounds__(AB_GROUPS * AB_GW * 32, 1) cross_absorbed_kernel(int S, int H, const __nv_bfloat16* __restrict__ qp, long long ldq,
+                                                                                    const __nv_bfloat16* __restrict__ enc, long long enc_bs,
+                                                                                    __nv_bfloat16* __restrict__ out, long long ldo) {
   extern __shared__ __align__(16) unsigned char smem[];
-  unsigned char* sE = smem;                                          // [STAGES][KT][AB_ROW]
-  unsigned char* sQ = sE + AB_STAGES * AB_KT * AB_ROW;               // [8][AB_ROW]
-  unsigned char* sP = sQ + 8 * AB_ROW;                               // [8][AB_PROW]
-  float* sMax = reinterpret_cast<float*>(sP + 8 * AB_PROW);          // [WARPS][8]
-  float* sSum = sMax + AB_WARPS * 8;                                 // [WARPS][8]
+  const int grp = threadIdx.x >> 7;                                  // warp group
+  const int gtid = threadIdx.x & 127;
+  const int warp = gtid >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+  unsigned char* sQ = smem + AB_GROUPS * AB_GROUP_BYTES;             // [8][AB_ROW], shared by both groups
+  unsigned char* sE = smem + grp * AB_GROUP_BYTES;                   // [STAGES][KT][AB_ROW]
+  unsigned char* sP = sE + AB_STAGES * AB_KT * AB_ROW;               // [8][AB_PROW]
+  float* sMax = reinterpret_cast<float*>(sP + 8 * AB_PROW);          // [GW][8]
+  float* sSum = sMax + AB_GW * 8;                                    // [GW][8]
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
   const __nv_bfloat16* eb = enc + static_cast<long long>(b) * enc_bs;
   const int n_tiles = (S + AB_KT - 1) / AB_KT;
+  const int my_tiles = (n_tiles - grp + AB_GROUPS - 1) / AB_GROUPS;  // tiles grp, grp + 2, ...
 
-  auto issue_tile = [&](int t) {
-    if (t < n_tiles) {
-      const uint32_t st = smem_addr(sE) + (t % AB_STAGES) * (AB_KT * AB_ROW);
+  auto issue_tile = [&](int i) {                                     // i-th tile of this group
+    if (i < my_tiles) {
+      const int t = grp + i * AB_GROUPS;
+      const uint32_t st = smem_addr(sE) + (i % AB_STAGES) * (AB_KT * AB_ROW);
 #pragma unroll
-      for (int j = 0; j < (AB_KT * 64) / (AB_WARPS * 32); ++j) {
-        const int i = threadIdx.x + j * (AB_WARPS * 32);
-        const int row = i >> 6, ch = i & 63;
+      for (int j = 0; j < (AB_KT * 64) / (AB_GW * 32); ++j) {
+        const int c = gtid + j * (AB_GW * 32);
+        const int row = c >> 6, ch = c & 63;
         const int key = t * AB_KT + row;
         const bool ok = key < S;
         ab_cp16(st + row * AB_ROW + ch * 16, eb + static_cast<long long>(ok ? key : 0) * AB_D + ch * 8, ok ? 16 : 0);
@@ -76,18 +87,18 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) cross_absorbed_kernel(int S,
     }
     ab_commit();
   };
-  // Q' rows of the valid heads (rows >= H stay zero: they only feed accumulator rows nobody reads)
-  for (int i = threadIdx.x; i < 8 * 64; i += AB_WARPS * 32) {
+  // Q' rows of the valid heads (rows >= H stay zero: they only feed accumulator rows nobody reads); every thread's first group
+  for (int i = threadIdx.x; i < 8 * 64; i += AB_GROUPS * AB_GW * 32) {
     const int row = i >> 6, ch = i & 63;
     ab_cp16(smem_addr(sQ) + row * AB_ROW + ch * 16, qp + static_cast<long long>(b) * ldq + static_cast<long long>(row < H ? row : 0) * AB_D + ch * 8,
             row < H ? 16 : 0);
   }
-  issue_tile(0);                                                     // group 0 = Q' + tile 0
+  issue_tile(0);                                                     // cp.async group 0 of every thread = its share of Q' + the first tile
   issue_tile(1);
 
-  float o[8][4];
+  float o[16][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 16; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
   float m_run = -INFINITY, l_run = 0.f;
@@ -98,11 +109,15 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) cross_absorbed_kernel(int S,
   // phase-2 transposed loads: row = key (lane % 16), matrices 2, 3 = the next 8 dimensions
   const uint32_t t_lane = static_cast<uint32_t>((lane & 15) * AB_ROW + (lane >> 4) * 16);
 
-  for (int t = 0; t < n_tiles; ++t) {
-    ab_wait<AB_STAGES - 2>();
-    __syncthreads();                                                 // tile t landed for everyone; the stage of tile t-1 is free
-    issue_tile(t + AB_STAGES - 1);
-    const uint32_t st = smem_addr(sE) + (t % AB_STAGES) * (AB_KT * AB_ROW);
+  // Q' has to be visible to BOTH groups before anyone scores: every thread waits for its own copies, then one block barrier
+  ab_wait<1>();
+  __syncthreads();
+  for (int i = 0; i < my_tiles; ++i) {
+    ab_wait<1>();                                                    // this thread's copies of tile i (tile i + 1 may be in flight)
+    ab_group_sync(grp);                                              // tile i landed for the group; everyone left iteration i - 1
+    issue_tile(i + 2);                                               // into the stage tile i - 1 was read from
+    const int t = grp + i * AB_GROUPS;
+    const uint32_t st = smem_addr(sE) + (i % AB_STAGES) * (AB_KT * AB_ROW);
     // ---- phase 1: scores of keys [8 warp, 8 warp + 8) x 8 heads over all 512 dimensions
     float s[4] = {0.f, 0.f, 0.f, 0.f};
     const uint32_t qa = smem_addr(sQ) + a_lane;
@@ -122,10 +137,10 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) cross_absorbed_kernel(int S,
     mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, 1));
     mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, 2));
     if (tq == 0) sMax[warp * 8 + g] = mx;
-    __syncthreads();
+    ab_group_sync(grp);
     float m_new = m_run;
 #pragma unroll
-    for (int w = 0; w < AB_WARPS; ++w) m_new = fmaxf(m_new, sMax[w * 8 + g]);
+    for (int w = 0; w < AB_GW; ++w) m_new = fmaxf(m_new, sMax[w * 8 + g]);
     const float alpha = exp2f(m_run - m_new);                        // first tile: exp2(-inf) = 0
     const float p0 = exp2f(s0 - m_new), p1 = exp2f(s1 - m_new);
     float rs = p0 + p1;
@@ -136,40 +151,55 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) cross_absorbed_kernel(int S,
       const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
       *reinterpret_cast<__nv_bfloat162*>(sP + g * AB_PROW + (warp * 8 + 2 * tq) * 2) = pb;
     }
-    __syncthreads();
+    ab_group_sync(grp);
     float ls = 0.f;
 #pragma unroll
-    for (int w = 0; w < AB_WARPS; ++w) ls += sSum[w * 8 + g];
+    for (int w = 0; w < AB_GW; ++w) ls += sSum[w * 8 + g];
     l_run = l_run * alpha + ls;
     m_run = m_new;
-    // ---- phase 2: C'[heads][64 warp .. 64 warp + 64) += P (8 x 64 keys) * tile (64 keys x 64 dimensions)
+    // ---- phase 2: C'[heads][128 warp .. 128 warp + 128) += P (8 x 32 keys) * tile (32 keys x 128 dimensions)
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) { o[nt][0] *= alpha; o[nt][1] *= alpha; }
-    const uint32_t pa = smem_addr(sP) + p_lane;
-    const uint32_t va = st + t_lane + warp * 128;
+    for (int nt = 0; nt < 16; ++nt) { o[nt][0] *= alpha; o[nt][1] *= alpha; }
+    uint32_t a[4];
+    ab_ldsm4(a, smem_addr(sP) + p_lane);                             // all 32 keys of the tile: two k steps
+    const uint32_t va = st + t_lane + warp * 256;
 #pragma unroll
-    for (int k2 = 0; k2 < AB_KT / 32; ++k2) {                        // 32 keys per ldmatrix.x4 of P
-      uint32_t a[4];
-      ab_ldsm4(a, pa + k2 * 64);
+    for (int kk = 0; kk < 2; ++kk) {
+      const uint32_t vrow = va + kk * 16 * AB_ROW;
 #pragma unroll
-      for (int kk = 0; kk < 2; ++kk) {
-        const uint32_t vrow = va + (k2 * 32 + kk * 16) * AB_ROW;
-#pragma unroll
-        for (int np = 0; np < 4; ++np) {                             // 16 dimensions (two n tiles) per transposed load
-          uint32_t bb[4];
-          ab_ldsm4t(bb, vrow + np * 32);
-          ab_mma(o[2 * np], a[2 * kk], 0u, a[2 * kk + 1], 0u, bb[0], bb[1]);
-          ab_mma(o[2 * np + 1], a[2 * kk], 0u, a[2 * kk + 1], 0u, bb[2], bb[3]);
-        }
+      for (int np = 0; np < 8; ++np) {                               // 16 dimensions (two n tiles) per transposed load
+        uint32_t bb[4];
+        ab_ldsm4t(bb, vrow + np * 32);
+        ab_mma(o[2 * np], a[2 * kk], 0u, a[2 * kk + 1], 0u, bb[0], bb[1]);
+        ab_mma(o[2 * np + 1], a[2 * kk], 0u, a[2 * kk + 1], 0u, bb[2], bb[3]);
       }
     }
+    // (the barrier at the top of the next iteration separates these reads of the stage and of P / maxima / sums from the
+    // writes of iteration i + 1; the stage itself is refilled only after that barrier)
   }
   ab_wait<0>();
-  if (g < H) {
-    const float inv = 1.0f / l_run;
-    __nv_bfloat16* orow = out + static_cast<long long>(b) * ldo + static_cast<long long>(g) * AB_D + warp * 64 + 2 * tq;
+  __syncthreads();                                                   // both groups done with their rings
+  // ---- merge: group 1 leaves (m, l, C') in its ring, group 0 combines and writes
+  float* mo = reinterpret_cast<float*>(smem + AB_GROUP_BYTES);       // [16 n tiles][2][128 threads] accumulators, then [2][128] m, l
+  if (grp == 1) {
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<__nv_bfloat162*>(orow + nt * 8) = __floats2bfloat162_rn(o[nt][0] * inv, o[nt][1] * inv);
+    for (int nt = 0; nt < 16; ++nt) { mo[(nt * 2) * 128 + gtid] = o[nt][0]; mo[(nt * 2 + 1) * 128 + gtid] = o[nt][1]; }
+    mo[32 * 128 + gtid] = m_run;
+    mo[33 * 128 + gtid] = l_run;
+  }
+  __syncthreads();
+  if (grp == 0 && g < H) {
+    const float m1 = mo[32 * 128 + gtid], l1 = mo[33 * 128 + gtid];
+    const float m = fmaxf(m_run, m1);
+    const float f0 = exp2f(m_run - m), f1 = exp2f(m1 - m);           // a group without tiles has m = -inf, l = 0: factor 0
+    const float inv = 1.0f / (l_run * f0 + l1 * f1);
+    __nv_bfloat16* orow = out + static_cast<long long>(b) * ldo + static_cast<long long>(g) * AB_D + warp * 128 + 2 * tq;
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+      const float v0 = (o[nt][0] * f0 + mo[(nt * 2) * 128 + gtid] * f1) * inv;
+      const float v1 = (o[nt][1] * f0 + mo[(nt * 2 + 1) * 128 + gtid] * f1) * inv;
+      *reinterpret_cast<__nv_bfloat162*>(orow + nt * 8) = __floats2bfloat162_rn(v0, v1);
+    }
   }
 }
 
@@ -185,7 +215,7 @@ int cross_attention_absorbed(int B, int S, int H, int d, const void* qp, long lo
     NS_CUDA(cudaFuncSetAttribute(cross_absorbed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
     attr_done = true;
   }
-  NS_CUDA(launch_pdl(cross_absorbed_kernel, dim3(B), dim3(AB_WARPS * 32), static_cast<size_t>(AB_SMEM), st, S, H, static_cast<const __nv_bfloat16*>(qp), ldq,
+  NS_CUDA(launch_pdl(cross_absorbed_kernel, dim3(B), dim3(AB_GROUPS * AB_GW * 32), static_cast<size_t>(AB_SMEM), st, S, H, static_cast<const __nv_bfloat16*>(qp), ldq,
                      static_cast<const __nv_bfloat16*>(enc), enc_bs, static_cast<__nv_bfloat16*>(out), ldo));
   NS_LAUNCH_CHECK();
   count(C_ATTN_TC);

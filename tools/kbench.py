@@ -176,6 +176,19 @@ def bench_gemm(B, iters, out):
     At3 = mk(d, 3 * r)
     t = timeit(lambda: ops.lora_da(x512, t96, dA3, 3, bits512, dx=do_, At=At3), iters)
     res["lora_da qkv + dx correction"] = {"ms": t, "gbs": M * d * 2 / t / 1e6}
+    # ---- round 2, late: the plane drawn in the mask stage (drop_mode 2), the one-pass B-side backward (dt = dy B, dB = dy^T t)
+    salts = [11, 22, 33]
+    t = timeit(lambda: ops.gemm_nt(x512, A3, t3, ops.epilogue(alpha=2.0, alpha_cols=3 * r, drop_a=bits512, drop_gen=(seed, salts, 0.05))), iters)
+    res["lora_t 512->96 masked, plane drawn in the stage"] = {"ms": t, "gbs": M * d * 2 / t / 1e6}
+    t = timeit(lambda: ops.gemm_nt(x2048, A4, t1, ops.epilogue(alpha=2.0, alpha_cols=r, drop_a=bits2048, drop_gen=(seed, [44], 0.05))), iters)
+    res["lora_t 2048->32 masked, plane drawn in the stage"] = {"ms": t, "gbs": M * F * 2 / t / 1e6}
+    for N, Gn in ((d, 1), (d, 3), (F, 1)):
+        dy = mk(M, Gn * N); Bt = mk(Gn * r, N); tt = mk(M, Gn * r)
+        dtb = torch.empty(M, Gn * r, dtype=torch.bfloat16, device=DEV); dB = torch.zeros(Gn * N, r, device=DEV)
+        nws = ops.lora_bwd_b_workspace_bytes(M, N, r, Gn)
+        wsb = torch.zeros(nws, dtype=torch.uint8, device=DEV) if nws > 0 else None
+        t = timeit(lambda: ops.lora_bwd_b(dy, Bt, tt, dtb, dB, N, r, [2.0] * Gn, [1.0] * Gn, workspace=wsb), iters)
+        res[f"lora_bwd_b N={N} groups={Gn}"] = {"ms": t, "gbs": M * Gn * N * 2 / t / 1e6}
     out["gemm"] = res
 
 

@@ -11,7 +11,8 @@ os.makedirs("profiles", exist_ok=True)
 
 FAMILY = [("gemm_nt_kernel", "ns_gemm_nt"), ("gemm_tn_kernel", "ns_gemm_tn"), ("attn_fwd_db", "ns_attention_fwd"),
           ("attn_bwd_fused", "ns_attention_bwd_ws"), ("ln_fwd", "ns_layernorm_fwd"), ("ln_bwd", "ns_layernorm_bwd"),
-          ("aug_btc", "ns_aug_pass"), ("ce_", "ns_cross_entropy"), ("lora_da_kernel", "ns_lora_da"), ("dropout_bits", "ns_dropout_bits")]
+          ("aug_btc", "ns_aug_pass"), ("ce_", "ns_cross_entropy"), ("lora_da_kernel", "ns_lora_da"), ("dropout_bits", "ns_dropout_bits"), ("lora_bwd_b_kernel", "ns_lora_bwd_b"),
+          ("cross_absorbed", "ns_cross_attention_absorbed")]
 
 
 def short(name):
