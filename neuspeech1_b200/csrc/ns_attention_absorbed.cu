@@ -112,6 +112,11 @@ __global__ void __launch_bounds__(AB_GROUPS * AB_GW * 32, 1) cross_absorbed_kern
   // Q' has to be visible to BOTH groups before anyone scores: every thread waits for its own copies, then one block barrier
   ab_wait<1>();
   __syncthreads();
+  // Q' as A fragments in registers for the whole kernel (rows 0-7 only: a1 = a3 = 0): 64 registers instead of 8 KB of
+  // shared-memory reads per warp and tile -- a third of the kernel's shared-memory traffic
+  uint32_t qf[AB_D / 32][4];
+#pragma unroll
+  for (int k2 = 0; k2 < AB_D / 32; ++k2) ab_ldsm4(qf[k2], smem_addr(sQ) + a_lane + k2 * 64);
   for (int i = 0; i < my_tiles; ++i) {
     ab_wait<1>();                                                    // this thread's copies of tile i (tile i + 1 may be in flight)
     ab_group_sync(grp);                                              // tile i landed for the group; everyone left iteration i - 1
@@ -120,15 +125,13 @@ __global__ void __launch_bounds__(AB_GROUPS * AB_GW * 32, 1) cross_absorbed_kern
     const uint32_t st = smem_addr(sE) + (i % AB_STAGES) * (AB_KT * AB_ROW);
     // ---- phase 1: scores of keys [8 warp, 8 warp + 8) x 8 heads over all 512 dimensions
     float s[4] = {0.f, 0.f, 0.f, 0.f};
-    const uint32_t qa = smem_addr(sQ) + a_lane;
     const uint32_t ka = st + warp * 8 * AB_ROW + a_lane;
-#pragma unroll 4
-    for (int k2 = 0; k2 < AB_D / 32; ++k2) {                         // two k steps (32 dimensions) per pair of ldmatrix.x4
-      uint32_t a[4], bb[4];
-      ab_ldsm4(a, qa + k2 * 64);
+#pragma unroll
+    for (int k2 = 0; k2 < AB_D / 32; ++k2) {                         // two k steps (32 dimensions) per ldmatrix.x4 of the keys
+      uint32_t bb[4];
       ab_ldsm4(bb, ka + k2 * 64);
-      ab_mma(s, a[0], 0u, a[1], 0u, bb[0], bb[1]);
-      ab_mma(s, a[2], 0u, a[3], 0u, bb[2], bb[3]);
+      ab_mma(s, qf[k2][0], 0u, qf[k2][1], 0u, bb[0], bb[1]);
+      ab_mma(s, qf[k2][2], 0u, qf[k2][3], 0u, bb[2], bb[3]);
     }
     const int key0 = t * AB_KT + warp * 8 + 2 * tq;
     float s0 = key0 < S ? s[0] * kLog2e : -INFINITY;
