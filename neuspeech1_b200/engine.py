@@ -1267,7 +1267,7 @@ class WhisperEEGEngine:
         if n_new <= 0:
             return torch.empty((B, 0), dtype=torch.long, device=self.device)
         cache = [ws.get(f"g_qkv.{i}", (B, Tmax, 3 * d), dt) for i in range(dm.dec_layers)]
-        absorb = L0 == 1 and self._absorbed_decode(B)        # (a multi-token prompt takes the general pass over cached K|V once)
+        absorb = self._absorbed_decode(B)
         kv_all = None if absorb else ws.get("kv_layers", (dm.dec_layers, B * S, 2 * d), dt)
         finished = ws.get("g_fin", (B,), torch.uint8); finished.zero_()
         nxt = ws.get("g_next", (B,), torch.long)
@@ -1296,13 +1296,25 @@ class WhisperEEGEngine:
         # programmatic dependent launch: every kernel of a step starts its prologue under the tail of the one before it
         pdl_prev = ops.set_pdl(not _NO_PDL)
         try:
-            return self._greedy_loop(decode_step, graphs, n_new, B, Tmax, L0, ids0, nxt, finished, out, eos_check_every)
+            first, pos0 = ids0, 0
+            if absorb and L0 > 1:
+                # The absorbed form has no cached K|V for the general multi-token pass: the prompt (evaluation.py:357-359 hands
+                # generate() four decoder tokens) goes through the native step one position at a time -- the same causal
+                # computation, its picks discarded (scratch flags / ids) -- and the loop starts at the last prompt token.
+                fin_d = ws.get("g_fin_prompt", (B,), torch.uint8); nxt_d = ws.get("g_next_prompt", (B,), torch.long)
+                cols = ws.get(f"g_prompt_cols.{L0}", (L0, B), torch.long)
+                cols.copy_(ids0.t())
+                for j in range(L0 - 1):
+                    fin_d.zero_()
+                    ops.decode_step(dec, cols[j], j, None, dm.eos_token_id, dm.pad_token_id, fin_d, nxt_d)
+                first, pos0 = cols[L0 - 1].view(B, 1), L0 - 1
+            return self._greedy_loop(decode_step, graphs, n_new, B, Tmax, L0, first, nxt, finished, out, eos_check_every, pos0)
         finally:
             ops.set_pdl(pdl_prev)
 
-    def _greedy_loop(self, decode_step, graphs, n_new, B, Tmax, L0, ids0, nxt, finished, out, eos_check_every):
+    def _greedy_loop(self, decode_step, graphs, n_new, B, Tmax, L0, ids0, nxt, finished, out, eos_check_every, pos0: int = 0):
         ws = self.ws
-        pos = 0
+        pos = pos0
         for step in range(n_new):
             ids = ids0 if step == 0 else nxt.view(B, 1)
             key = (B, Tmax, L0, step, self._weights_version)
