@@ -86,6 +86,20 @@ class ModelDims:
         return cls(**{f: get(f) for f in cls.__dataclass_fields__})
 
 
+def absorb_query_key(wq: torch.Tensor, bq: torch.Tensor, wk: torch.Tensor, heads: int):
+    """Query AND key projection of a cross-attention as one weight for the absorbed decode form (csrc/ns_attention_absorbed.cu):
+    with q = (x Wq^T + bq) Dh^-0.5 and K = enc Wk^T (no bias, HF modeling_whisper.py:284-310), the scores of head h are
+    q_h . K_h[j] = Q'_h . enc[j] with Q' = x wq_abs^T + bq_abs,
+        wq_abs[h*d + n, m] = Dh^-0.5 sum_c Wk[h*Dh + c, n] Wq[h*Dh + c, m],   bq_abs[h*d + n] = Dh^-0.5 sum_c bq[h*Dh + c] Wk[h*Dh + c, n].
+    fp32 in, fp32 out ((heads*d, d), (heads*d,)): the caller rounds to the storage type once."""
+    d = wq.shape[1]
+    dh = wq.shape[0] // heads
+    wkh, wqh = wk.view(heads, dh, d), wq.view(heads, dh, d)
+    w = torch.einsum("hcn,hcm->hnm", wkh, wqh) * dh ** -0.5
+    b = torch.einsum("hc,hcn->hn", bq.view(heads, dh), wkh) * dh ** -0.5
+    return w.reshape(heads * d, d).contiguous(), b.reshape(heads * d).contiguous()
+
+
 def lora_module_name(layer: int, target: str) -> str:
     return f"model.encoder.layers.{layer}." + (target if target.startswith("fc") else f"self_attn.{target}")
 
@@ -443,14 +457,11 @@ class WhisperEEGEngine:
         # wq_abs[h*d + n, m] = Dh^-0.5 sum_c Wk[h*Dh + c, n] Wq[h*Dh + c, m], bq_abs[h*d + n] = Dh^-0.5 sum_c bq[h*Dh + c] Wk[h*Dh + c, n]
         # (products in fp32, rounded to the storage type once)
         Hd = dm.dec_heads
-        Dhd = d // Hd
         for i in range(dm.dec_layers if (self.dtype == torch.bfloat16 and d == 512 and Hd <= 8) else 0):   # the shapes the kernel takes
             pre = f"model.decoder.layers.{i}"
-            wk = kv_w[2 * i].view(Hd, Dhd, d)
-            wq = f32(f"{pre}.encoder_attn.q_proj.weight").view(Hd, Dhd, d)
-            bq = f32(f"{pre}.encoder_attn.q_proj.bias").view(Hd, Dhd)
-            W[f"dec{i}.wq_abs"] = self._c((torch.einsum("hcn,hcm->hnm", wk, wq) * Dhd ** -0.5).reshape(Hd * d, d).contiguous())
-            W[f"dec{i}.bq_abs"] = (torch.einsum("hc,hcn->hn", bq, wk) * Dhd ** -0.5).reshape(Hd * d).contiguous()
+            w_abs, b_abs = absorb_query_key(f32(f"{pre}.encoder_attn.q_proj.weight"), f32(f"{pre}.encoder_attn.q_proj.bias"), kv_w[2 * i], Hd)
+            W[f"dec{i}.wq_abs"] = self._c(w_abs)
+            W[f"dec{i}.bq_abs"] = b_abs
         wkv = torch.cat(kv_w, dim=0)                                     # (Nd*2d, d): [k0; v0; k1; v1; ...]
         W["dec.wkv"] = self._c(wkv); W["dec.wkv_t"] = self._ct(wkv); W["dec.bkv"] = torch.cat(kv_b)
         self.P = W

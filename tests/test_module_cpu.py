@@ -175,3 +175,31 @@ def test_forward_argument_errors():
         m.generate(torch.zeros(1, 16, 256), do_sample=True)
     with pytest.raises(NotImplementedError):
         m.generate(torch.zeros(1, 16, 256), num_beams=4, num_beam_groups=2)
+
+
+def test_absorbed_query_key_weight_matches_attention_scores():
+    """engine.absorb_query_key: the decode step's absorbed cross-attention scores with the folded weight equal q . K of HF
+    modeling_whisper.py:284-336 (q scaled by Dh^-0.5 with its bias, bias-free keys), head by head, and the value side identity
+    softmax(S) (enc Wv^T + bv) = (softmax(S) enc) Wv^T + bv holds (rows of a softmax sum to one)."""
+    import torch
+    from neuspeech1_b200.engine import absorb_query_key
+    g = torch.Generator().manual_seed(0)
+    d, H, S, B = 64, 4, 37, 3
+    dh = d // H
+    wq, wk, wv = (torch.randn(d, d, generator=g, dtype=torch.float64) * 0.2 for _ in range(3))
+    bq, bv = torch.randn(d, generator=g, dtype=torch.float64), torch.randn(d, generator=g, dtype=torch.float64)
+    x = torch.randn(B, d, generator=g, dtype=torch.float64)
+    enc = torch.randn(B, S, d, generator=g, dtype=torch.float64)
+    q = ((x @ wq.t() + bq) * dh ** -0.5).view(B, H, dh)
+    K = (enc @ wk.t()).view(B, S, H, dh)
+    V = (enc @ wv.t() + bv).view(B, S, H, dh)
+    scores = torch.einsum("bhc,bshc->bhs", q, K)
+    out = torch.einsum("bhs,bshc->bhc", scores.softmax(-1), V).reshape(B, d)
+    w_abs, b_abs = absorb_query_key(wq, bq, wk, H)
+    assert w_abs.shape == (H * d, d) and b_abs.shape == (H * d,)
+    qp = (x @ w_abs.t() + b_abs).view(B, H, d)
+    scores2 = torch.einsum("bhn,bsn->bhs", qp, enc)
+    assert torch.allclose(scores, scores2, atol=1e-10)
+    cp = torch.einsum("bhs,bsn->bhn", scores2.softmax(-1), enc)                     # C'_h = P_h enc
+    out2 = torch.stack([cp[:, h] @ wv[h * dh:(h + 1) * dh].t() + bv[h * dh:(h + 1) * dh] for h in range(H)], dim=1).reshape(B, d)
+    assert torch.allclose(out, out2, atol=1e-10)
