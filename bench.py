@@ -463,6 +463,8 @@ def run_decode(args):
         "roofline": {"bound": "hbm", "kernel": "token step (all decoder kernels of one position)", "achieved": ach, "peak": peaks["hbm"],
                      "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None, "bytes_per_token_step": step_bytes,
                      "bytes_per_token_step_cached_kv": step_bytes + (2.0 * B * S * Ld * d if absorbed else 0.0),
+                     # the same time against the bytes attention over cached K|V has to read (round 1 / VERDICT's yardstick)
+                     "frac_vs_cached_kv_bytes": (step_bytes + (2.0 * B * S * Ld * d if absorbed else 0.0)) / (ms_tok * 1e-3) / 1e9 / peaks["hbm"],
                      "peak_source": peaks["src"]},
         "cpu_baseline": None,
     }
